@@ -1,0 +1,129 @@
+"""ctypes binding of libflowtron_b200.so (the C ABI in include/flowtron_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails the product path
+raises.  torch is used only for device memory, streams and torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libflowtron_b200.so")
+
+FT_F16, FT_BF16, FT_TF32 = 0, 1, 2
+_FMT = {torch.float16: FT_F16, torch.bfloat16: FT_BF16, torch.float32: FT_TF32}
+
+_lib = None
+
+
+class FlowtronB200Error(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FlowtronB200Error(
+                f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(the CUDA extension is mandatory; there is no CPU fallback)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.ft_last_error.restype = c_char_p
+        _lib.ft_launch_count.restype = c_longlong
+        _declare(_lib)
+    return _lib
+
+
+def _declare(L):
+    L.ft_gemm.argtypes = [c_int, c_int, c_int, c_void_p, c_longlong, c_int, c_int, c_void_p, c_longlong, c_int, c_int,
+                          c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_longlong, c_void_p, c_longlong,
+                          c_int, c_void_p]
+    L.ft_gemm.restype = c_int
+
+
+    L.ft_lstm_fwd.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p,
+                              c_void_p, c_longlong, c_void_p, c_void_p]
+    L.ft_lstm_fwd.restype = c_int
+    L.ft_lstm_bwd.argtypes = [c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p]
+    L.ft_lstm_bwd.restype = c_int
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise FlowtronB200Error(f"{what} failed (rc={rc}): {lib().ft_last_error().decode()}")
+
+
+def ptr(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def device_status() -> int:
+    return int(lib().ft_device_status())
+
+
+def launch_count() -> int:
+    return int(lib().ft_launch_count())
+
+
+def reset_launch_count():
+    lib().ft_reset_launch_count()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise FlowtronB200Error("flowtron_b200 kernels need CUDA tensors (no CPU fallback exists)")
+
+
+def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, bias2=None, act=0, beta=0, alpha=1.0,
+         out32=None, out16=None):
+    """C = act(alpha * A @ B^T + bias + bias2) (+ out32 if beta).  A:[M,K] (or [K,M] if a_mn), B:[N,K] (or [K,N])."""
+    _need_cuda(A, B)
+    if a_mn:
+        K, M = A.shape
+    else:
+        M, K = A.shape
+    if b_mn:
+        Kb, N = B.shape
+    else:
+        N, Kb = B.shape
+    assert K == Kb, (A.shape, B.shape)
+    assert A.stride(-1) == 1 and B.stride(-1) == 1
+    c16_fmt = 0
+    if out16 is not None:
+        c16_fmt = _FMT[out16.dtype]
+    check(lib().ft_gemm(M, N, K, ptr(A), A.stride(0), _FMT[A.dtype], int(a_mn), ptr(B), B.stride(0), _FMT[B.dtype],
+                        int(b_mn), ptr(bias), ptr(bias2), act, beta, float(alpha),
+                        ptr(out32), 0 if out32 is None else out32.stride(0),
+                        ptr(out16), 0 if out16 is None else out16.stride(0), c16_fmt, stream_ptr()), "ft_gemm")
+
+
+def lstm_fwd(xproj, whh16, lens, hseq16, gates16=None, cstate=None, h32=None):
+    """xproj [T,B,4096] f32, whh16 [4096,1024] f16, lens int32 [B]|None, hseq16 [T,B,>=1024 view] f16 (written)."""
+    _need_cuda(xproj, whh16, hseq16)
+    T, B = xproj.shape[0], xproj.shape[1]
+    assert xproj.is_contiguous() and whh16.dtype == torch.float16 and hseq16.dtype == torch.float16
+    assert hseq16.stride(1) == hseq16.stride(0) // B or T == 1
+    flags = torch.empty(T * 16, dtype=torch.int32, device=xproj.device)
+    check(lib().ft_lstm_fwd(T, B, ptr(xproj), ptr(whh16), ptr(lens), ptr(hseq16), hseq16.stride(1), ptr(gates16),
+                            ptr(cstate), ptr(h32), 0 if h32 is None else h32.stride(1), ptr(flags), stream_ptr()),
+          "ft_lstm_fwd")
+
+
+def lstm_bwd(dh_ext, whhT16, gates16, cstate, lens, dG16):
+    """dh_ext [T,B,ld view] f32, whhT16 [1024,4096] bf16, dG16 [T,B,4096] bf16 (written)."""
+    _need_cuda(dh_ext, whhT16, dG16)
+    T, B = dG16.shape[0], dG16.shape[1]
+    assert whhT16.dtype == torch.bfloat16 and dG16.dtype == torch.bfloat16 and dG16.is_contiguous()
+    flags = torch.empty(T * 64, dtype=torch.int32, device=dG16.device)
+    check(lib().ft_lstm_bwd(T, B, ptr(dh_ext), dh_ext.stride(1), ptr(whhT16), ptr(gates16), ptr(cstate), ptr(lens),
+                            ptr(dG16), ptr(flags), stream_ptr()), "ft_lstm_bwd")
