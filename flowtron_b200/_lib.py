@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
+from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 import torch
 
@@ -18,6 +18,23 @@ FT_F16, FT_BF16, FT_TF32 = 0, 1, 2
 _FMT = {torch.float16: FT_F16, torch.bfloat16: FT_BF16, torch.float32: FT_TF32}
 
 _lib = None
+
+
+class FtArStepDesc(Structure):
+    _fields_ = [("T", c_int), ("B", c_int), ("L", c_int), ("n_mel", c_int), ("n_hidden", c_int), ("n_attn", c_int),
+                ("n_text", c_int), ("reversed", c_int), ("has_gate", c_int), ("has_prior", c_int),
+                ("temperature", c_float)]
+
+
+AR_WEIGHT_FIELDS = ["attn_lstm_w_ih", "attn_lstm_w_hh", "attn_lstm_b_ih", "attn_lstm_b_hh",
+                    "lstm_w_ih0", "lstm_w_hh0", "lstm_b_ih0", "lstm_b_hh0",
+                    "lstm_w_ih1", "lstm_w_hh1", "lstm_b_ih1", "lstm_b_hh1",
+                    "att_query", "att_key", "att_value", "att_v",
+                    "dense_w0", "dense_b0", "dense_w1", "dense_b1", "conv_w", "conv_b", "gate_w", "gate_b"]
+
+
+class FtArStepWeights(Structure):
+    _fields_ = [(n, c_void_p) for n in AR_WEIGHT_FIELDS]
 
 
 class FlowtronB200Error(RuntimeError):
@@ -51,6 +68,24 @@ def _declare(L):
     L.ft_lstm_bwd.argtypes = [c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p]
     L.ft_lstm_bwd.restype = c_int
+
+
+    L.ft_ar_step_saved_bytes.argtypes = [POINTER(FtArStepDesc)]
+    L.ft_ar_step_saved_bytes.restype = c_size_t
+    L.ft_ar_step_scratch_bytes.argtypes = [POINTER(FtArStepDesc)]
+    L.ft_ar_step_scratch_bytes.restype = c_size_t
+    L.ft_ar_step_saved_lookup.argtypes = [POINTER(FtArStepDesc), c_char_p, POINTER(c_size_t), POINTER(c_size_t)]
+    L.ft_ar_step_saved_lookup.restype = c_int
+    L.ft_ar_step_fwd.argtypes = [POINTER(FtArStepDesc), POINTER(FtArStepWeights)] + [c_void_p] * 13
+    L.ft_ar_step_fwd.restype = c_int
+    L.ft_ar_step_bwd.argtypes = [POINTER(FtArStepDesc), POINTER(FtArStepWeights)] + [c_void_p] * 11 + \
+        [POINTER(FtArStepWeights), c_void_p, c_void_p, c_void_p]
+    L.ft_ar_step_bwd.restype = c_int
+    L.ft_nll_reduce.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
+    L.ft_nll_reduce.restype = c_int
+    L.ft_nll_grad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.ft_nll_grad.restype = c_int
 
 
 def check(rc: int, what: str = ""):
@@ -127,3 +162,66 @@ def lstm_bwd(dh_ext, whhT16, gates16, cstate, lens, dG16):
     flags = torch.empty(T * 64, dtype=torch.int32, device=dG16.device)
     check(lib().ft_lstm_bwd(T, B, ptr(dh_ext), dh_ext.stride(1), ptr(whhT16), ptr(gates16), ptr(cstate), ptr(lens),
                             ptr(dG16), ptr(flags), stream_ptr()), "ft_lstm_bwd")
+
+
+# ----------------------------------------------------------------------------------------------- AR step
+_scratch = {}
+
+
+def scratch_buffer(nbytes: int, device) -> torch.Tensor:
+    """Per-device transient work area shared by every flow (grown on demand, never shrunk)."""
+    key = (device.type, device.index)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _scratch[key] = None
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+def make_weights(tensors) -> FtArStepWeights:
+    w = FtArStepWeights()
+    for name, t in zip(AR_WEIGHT_FIELDS, tensors):
+        if t is not None:
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda, name
+            setattr(w, name, t.data_ptr())
+        else:
+            setattr(w, name, None)
+    return w
+
+
+def ar_step_sizes(desc: FtArStepDesc):
+    L = lib()
+    return int(L.ft_ar_step_saved_bytes(byref(desc))), int(L.ft_ar_step_scratch_bytes(byref(desc)))
+
+
+def ar_step_saved_view(desc: FtArStepDesc, saved: torch.Tensor, name: str, dtype) -> torch.Tensor:
+    off, nb = c_size_t(), c_size_t()
+    check(lib().ft_ar_step_saved_lookup(byref(desc), name.encode(), byref(off), byref(nb)), "ft_ar_step_saved_lookup")
+    return saved[off.value: off.value + nb.value].view(dtype)
+
+
+def ar_step_fwd(desc, weights, mel, text, in_lens, out_lens, prior, mel_out, log_s, gates, attn, logprob, saved, scratch):
+    check(lib().ft_ar_step_fwd(byref(desc), byref(weights), ptr(mel), ptr(text), ptr(in_lens), ptr(out_lens), ptr(prior),
+                               ptr(mel_out), ptr(log_s), ptr(gates), ptr(attn), ptr(logprob), ptr(saved), ptr(scratch),
+                               stream_ptr()), "ft_ar_step_fwd")
+
+
+def ar_step_bwd(desc, weights, mel, in_lens, out_lens, attn, d_mel_out, d_log_s, d_gates, d_attn, d_logprob, d_mel, d_text,
+                grads, saved, scratch):
+    check(lib().ft_ar_step_bwd(byref(desc), byref(weights), ptr(mel), ptr(in_lens), ptr(out_lens), ptr(attn),
+                               ptr(d_mel_out), ptr(d_log_s), ptr(d_gates), ptr(d_attn), ptr(d_logprob), ptr(d_mel),
+                               ptr(d_text), byref(grads), ptr(saved), ptr(scratch), stream_ptr()), "ft_ar_step_bwd")
+
+
+def nll_reduce(z, log_s_ptrs, n_flows, gate, gate_target, out_lens, sums):
+    T, B, M = z.shape
+    check(lib().ft_nll_reduce(ptr(z), ptr(log_s_ptrs), n_flows, ptr(gate), ptr(gate_target), ptr(out_lens), T, B, M,
+                              ptr(sums), stream_ptr()), "ft_nll_reduce")
+
+
+def nll_grad(z, gate, gate_target, out_lens, sigma, sums, g_nll, g_gate, dz, dlog_s, dgate):
+    T, B, M = z.shape
+    check(lib().ft_nll_grad(ptr(z), ptr(gate), ptr(gate_target), ptr(out_lens), T, B, M, float(sigma), ptr(sums),
+                            ptr(g_nll), ptr(g_gate), ptr(dz), ptr(dlog_s), ptr(dgate), stream_ptr()), "ft_nll_grad")

@@ -1,0 +1,417 @@
+// Host-side orchestration of one Flowtron AR flow step (training direction) on a CUDA stream:
+// AR_Step.forward / AR_Back_Step.forward (flowtron.py:725-773, 605-627) and their autograd.
+// No allocation, no synchronisation: every intermediate lives in the caller's `saved` / `scratch` areas,
+// whose layouts are planned by the same code that uses them (Plan below).
+//
+// Precision plan: forward tensor-core operands are fp16 (11-bit significand, same as tf32; every
+// forward operand is either a weight or a bounded activation), backward operands are bf16 (gradients need
+// fp32's exponent range); accumulation, LSTM cell state, softmax, exp/log and all reductions are fp32.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ft_internal.h"
+#include "../../include/flowtron_b200.h"
+
+namespace ft {
+
+namespace {
+
+constexpr int H = 1024, G = 4096;
+
+struct Region { const char* name; size_t off, bytes; };
+
+struct Plan {
+    uint8_t* base = nullptr;
+    size_t off = 0;
+    std::vector<Region>* regs = nullptr;
+    template <typename T>
+    T* get(const char* name, size_t n) {
+        const size_t bytes = n * sizeof(T);
+        const size_t o = off;
+        off = (off + bytes + 255) & ~static_cast<size_t>(255);
+        if (regs) regs->push_back({name, o, bytes});
+        return base ? reinterpret_cast<T*>(base + o) : nullptr;
+    }
+};
+
+struct Dims {
+    long long R, RL;
+    int T, B, L, M, A, E, D;
+    explicit Dims(const FtArStepDesc& d)
+        : R(static_cast<long long>(d.T) * d.B), RL(static_cast<long long>(d.L) * d.B), T(d.T), B(d.B), L(d.L), M(d.n_mel),
+          A(d.n_attn), E(d.n_text), D(H + d.n_attn) {}
+};
+
+// ---- tensors that persist from forward to backward
+struct Saved {
+    uint16_t *mel_in16, *d16, *gatesA, *text16, *h0_16, *gates0, *h1_16, *gates1, *y1_16, *y2_16;
+    float *mel_flow, *cA, *Kp, *Vp, *Q, *p_save, *c0, *c1, *o32;
+    void plan(Plan& p, const FtArStepDesc& d) {
+        const Dims n(d);
+        mel_in16 = p.get<uint16_t>("mel_in16", n.R * n.M);
+        mel_flow = d.reversed ? p.get<float>("mel_flow", n.R * n.M) : nullptr;
+        d16 = p.get<uint16_t>("d16", n.R * n.D);
+        gatesA = p.get<uint16_t>("gatesA", n.R * G);
+        cA = p.get<float>("cA", n.R * H);
+        text16 = p.get<uint16_t>("text16", n.RL * n.E);
+        Kp = p.get<float>("Kp", n.RL * n.A);
+        Vp = p.get<float>("Vp", n.RL * n.A);
+        Q = p.get<float>("Q", n.R * n.A);
+        p_save = d.has_prior ? p.get<float>("p_save", static_cast<size_t>(n.B) * n.T * n.L) : nullptr;
+        h0_16 = p.get<uint16_t>("h0_16", n.R * H);
+        gates0 = p.get<uint16_t>("gates0", n.R * G);
+        c0 = p.get<float>("c0", n.R * H);
+        h1_16 = p.get<uint16_t>("h1_16", n.R * H);
+        gates1 = p.get<uint16_t>("gates1", n.R * G);
+        c1 = p.get<float>("c1", n.R * H);
+        y1_16 = p.get<uint16_t>("y1_16", n.R * H);
+        y2_16 = p.get<uint16_t>("y2_16", n.R * H);
+        o32 = p.get<float>("o32", n.R * 2 * n.M);
+    }
+};
+
+// ---- 16-bit weight copies (fp16 for forward, bf16 for backward)
+struct W16 {
+    uint16_t *w_ih_a, *w_hh_a, *w_ih0, *w_hh0, *w_ih1, *w_hh1, *wq, *wk, *wv, *w1, *w2, *wc;
+    void plan(Plan& p, const Dims& n) {
+        w_ih_a = p.get<uint16_t>("w_ih_a", static_cast<size_t>(G) * n.M);
+        w_hh_a = p.get<uint16_t>("w_hh_a", static_cast<size_t>(G) * H);
+        w_ih0 = p.get<uint16_t>("w_ih0", static_cast<size_t>(G) * n.D);
+        w_hh0 = p.get<uint16_t>("w_hh0", static_cast<size_t>(G) * H);
+        w_ih1 = p.get<uint16_t>("w_ih1", static_cast<size_t>(G) * H);
+        w_hh1 = p.get<uint16_t>("w_hh1", static_cast<size_t>(G) * H);
+        wq = p.get<uint16_t>("wq", static_cast<size_t>(n.A) * H);
+        wk = p.get<uint16_t>("wk", static_cast<size_t>(n.A) * n.E);
+        wv = p.get<uint16_t>("wv", static_cast<size_t>(n.A) * n.E);
+        w1 = p.get<uint16_t>("w1", static_cast<size_t>(H) * H);
+        w2 = p.get<uint16_t>("w2", static_cast<size_t>(H) * H);
+        wc = p.get<uint16_t>("wc", static_cast<size_t>(2 * n.M) * H);
+    }
+};
+
+struct FwdScratch {
+    W16 w;
+    float* X;
+    int* flags;
+    void plan(Plan& p, const FtArStepDesc& d) {
+        const Dims n(d);
+        w.plan(p, n);
+        X = p.get<float>("X", n.R * G);
+        flags = p.get<int>("flags", static_cast<size_t>(n.T) * 64);
+    }
+};
+
+struct BwdScratch {
+    W16 w;                      // bf16, natural layouts (w_hh* hold the TRANSPOSED recurrent weights [H, 4H])
+    uint16_t *dG, *cvt, *melin_bf, *text_bf, *do16, *dy2, *dy1, *dQ16, *dK16, *dV16;
+    float *dh, *dd, *dQ, *dK, *dV, *dmel_flow, *dmel_in;
+    int* flags;
+    void plan(Plan& p, const FtArStepDesc& d) {
+        const Dims n(d);
+        w.plan(p, n);
+        dG = p.get<uint16_t>("dG", n.R * G);
+        cvt = p.get<uint16_t>("cvt", n.R * n.D);
+        melin_bf = p.get<uint16_t>("melin_bf", n.R * n.M);
+        text_bf = p.get<uint16_t>("text_bf", n.RL * n.E);
+        do16 = p.get<uint16_t>("do16", n.R * 2 * n.M);
+        dy2 = p.get<uint16_t>("dy2", n.R * H);
+        dy1 = p.get<uint16_t>("dy1", n.R * H);
+        dQ16 = p.get<uint16_t>("dQ16", n.R * n.A);
+        dK16 = p.get<uint16_t>("dK16", n.RL * n.A);
+        dV16 = p.get<uint16_t>("dV16", n.RL * n.A);
+        dh = p.get<float>("dh", n.R * H);
+        dd = p.get<float>("dd", n.R * n.D);
+        dQ = p.get<float>("dQ", n.R * n.A);
+        dK = p.get<float>("dK", n.RL * n.A);
+        dV = p.get<float>("dV", n.RL * n.A);
+        dmel_flow = p.get<float>("dmel_flow", n.R * n.M);
+        dmel_in = p.get<float>("dmel_in", n.R * n.M);
+        flags = p.get<int>("flags", static_cast<size_t>(n.T) * 64);
+    }
+};
+
+int check_desc(const FtArStepDesc& d) {
+    if (d.n_hidden != H) return ft_set_error("ar_step: this build supports n_hidden == 1024 only");
+    if (d.T <= 0 || d.B <= 0 || d.L <= 0) return ft_set_error("ar_step: empty shape");
+    if (d.B > 128) return ft_set_error("ar_step: batch > 128 per call not supported (split the batch)");
+    if (d.n_mel % 8 || d.n_attn % 64 || d.n_text % 8) return ft_set_error("ar_step: n_mel %8, n_attn %64, n_text %8 required");
+    if (d.L > 256) return ft_set_error("ar_step: L > 256 not supported");
+    return 0;
+}
+
+#define FT_TRY(x) do { if ((x) != 0) return -1; } while (0)
+
+// C = A[M,K] B[N,K]^T helpers -----------------------------------------------------------------------------
+int gemm_fwd(cudaStream_t st, long long M, int N, int K, const void* A, long long lda, const void* B, long long ldb,
+             const float* bias, const float* bias2, int act, float* C32, long long ldc32, void* C16, long long ldc16) {
+    GemmArgs g;
+    g.M = static_cast<int>(M); g.N = N; g.K = K;
+    g.A = A; g.lda = lda; g.a_fmt = FMT_F16; g.B = B; g.ldb = ldb; g.b_fmt = FMT_F16;
+    g.bias = bias; g.bias2 = bias2; g.act = act;
+    g.C32 = C32; g.ldc32 = ldc32; g.C16 = C16; g.ldc16 = ldc16; g.c16_fmt = FMT_F16;
+    return launch_gemm(g, st);
+}
+// dgrad: dX[M,K] = dY[M,N] W[N,K]      (A = dY K-major, B = W given MN-major)
+int gemm_dgrad(cudaStream_t st, long long M, int Kout, int Nred, const void* dY, long long lddy, const void* W, long long ldw,
+               int beta, float* C32, long long ldc32, void* C16, long long ldc16, const void* aux16, long long ldaux) {
+    GemmArgs g;
+    g.M = static_cast<int>(M); g.N = Kout; g.K = Nred;
+    g.A = dY; g.lda = lddy; g.a_fmt = FMT_BF16; g.B = W; g.ldb = ldw; g.b_fmt = FMT_BF16; g.b_mn = 1;
+    g.beta = beta; g.C32 = C32; g.ldc32 = ldc32; g.C16 = C16; g.ldc16 = ldc16; g.c16_fmt = FMT_BF16;
+    if (aux16) { g.act = 2; g.aux16 = aux16; g.ldaux = ldaux; }
+    return launch_gemm(g, st);
+}
+// wgrad: dW[N,K] = dY[R,N]^T X[R,K]     (both operands MN-major views of the natural tensors)
+int gemm_wgrad(cudaStream_t st, int N, int K, long long R, const void* dY, long long lddy, const void* X, long long ldx,
+               float* dW, long long ldw) {
+    if (R <= 0) return cudaMemsetAsync(dW, 0, sizeof(float) * N * ldw, st) == cudaSuccess ? 0 : ft_set_error("memset failed");
+    GemmArgs g;
+    g.M = N; g.N = K; g.K = static_cast<int>(R);
+    g.A = dY; g.lda = lddy; g.a_fmt = FMT_BF16; g.a_mn = 1; g.B = X; g.ldb = ldx; g.b_fmt = FMT_BF16; g.b_mn = 1;
+    g.C32 = dW; g.ldc32 = ldw;
+    return launch_gemm(g, st);
+}
+
+int zero(void* p, size_t bytes, cudaStream_t st) {
+    return cudaMemsetAsync(p, 0, bytes, st) == cudaSuccess ? 0 : ft_set_error("cudaMemsetAsync failed");
+}
+int copy_f32(float* dst, const float* src, size_t n, cudaStream_t st) {
+    return cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st) == cudaSuccess ? 0 : ft_set_error("cudaMemcpyAsync failed");
+}
+
+}  // namespace
+
+// =================================================================================================== forward
+int ar_step_fwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* mel, const float* text, const int* in_lens,
+                const int* out_lens, const float* prior, float* mel_out, float* log_s, float* gates, float* attn,
+                float* logprob, void* saved, void* scratch, cudaStream_t st) {
+    FT_TRY(check_desc(d));
+    if (d.has_prior && !prior) return ft_set_error("ar_step_fwd: has_prior set but attn_prior is NULL");
+    if (d.has_gate && (!gates || !w.gate_w)) return ft_set_error("ar_step_fwd: has_gate set but gate pointers are NULL");
+    const Dims n(d);
+    Plan ps; ps.base = static_cast<uint8_t*>(saved);
+    Saved S; S.plan(ps, d);
+    Plan pf; pf.base = static_cast<uint8_t*>(scratch);
+    FwdScratch F; F.plan(pf, d);
+
+    // fp16 operand copies of the weights (61 M params -> ~0.1 ms; redone every call so optimizer updates are seen)
+    FT_TRY(launch_cast(w.attn_lstm_w_ih, 2, F.w.w_ih_a, 0, static_cast<long long>(G) * n.M, st));
+    FT_TRY(launch_cast(w.attn_lstm_w_hh, 2, F.w.w_hh_a, 0, static_cast<long long>(G) * H, st));
+    FT_TRY(launch_cast(w.lstm_w_ih0, 2, F.w.w_ih0, 0, static_cast<long long>(G) * n.D, st));
+    FT_TRY(launch_cast(w.lstm_w_hh0, 2, F.w.w_hh0, 0, static_cast<long long>(G) * H, st));
+    FT_TRY(launch_cast(w.lstm_w_ih1, 2, F.w.w_ih1, 0, static_cast<long long>(G) * H, st));
+    FT_TRY(launch_cast(w.lstm_w_hh1, 2, F.w.w_hh1, 0, static_cast<long long>(G) * H, st));
+    FT_TRY(launch_cast(w.att_query, 2, F.w.wq, 0, static_cast<long long>(n.A) * H, st));
+    FT_TRY(launch_cast(w.att_key, 2, F.w.wk, 0, static_cast<long long>(n.A) * n.E, st));
+    FT_TRY(launch_cast(w.att_value, 2, F.w.wv, 0, static_cast<long long>(n.A) * n.E, st));
+    FT_TRY(launch_cast(w.dense_w0, 2, F.w.w1, 0, static_cast<long long>(H) * H, st));
+    FT_TRY(launch_cast(w.dense_w1, 2, F.w.w2, 0, static_cast<long long>(H) * H, st));
+    FT_TRY(launch_cast(w.conv_w, 2, F.w.wc, 0, static_cast<long long>(2 * n.M) * H, st));
+
+    // teacher-forcing shift (+ AR_Back_Step time reversal folded into the gather)
+    FT_TRY(launch_prep_mel(mel, out_lens, n.T, n.B, n.M, d.reversed, S.mel_in16, S.mel_flow, st));
+    const float* mel_flow = d.reversed ? S.mel_flow : mel;
+
+    // attention_lstm: input projection GEMM, then the persistent recurrence; h lands in d16[:, 0:H]
+    FT_TRY(gemm_fwd(st, n.R, G, n.M, S.mel_in16, n.M, F.w.w_ih_a, n.M, w.attn_lstm_b_ih, w.attn_lstm_b_hh, 0, F.X, G, nullptr, 0));
+    FT_TRY(launch_lstm_fwd(n.T, n.B, F.X, F.w.w_hh_a, out_lens, S.d16, n.D, S.gatesA, S.cA, nullptr, 0, F.flags, st));
+
+    // attention: K/V/Q projections, fused score+softmax(+prior)+context; ctx lands in d16[:, H:H+A]
+    FT_TRY(launch_cast(text, 2, S.text16, 0, n.RL * n.E, st));
+    FT_TRY(gemm_fwd(st, n.RL, n.A, n.E, S.text16, n.E, F.w.wk, n.E, nullptr, nullptr, 0, S.Kp, n.A, nullptr, 0));
+    FT_TRY(gemm_fwd(st, n.RL, n.A, n.E, S.text16, n.E, F.w.wv, n.E, nullptr, nullptr, 0, S.Vp, n.A, nullptr, 0));
+    FT_TRY(gemm_fwd(st, n.R, n.A, H, S.d16, n.D, F.w.wq, H, nullptr, nullptr, 0, S.Q, n.A, nullptr, 0));
+    {
+        AttnFwdArgs a;
+        a.T = n.T; a.B = n.B; a.L = n.L; a.A = n.A;
+        a.Q = S.Q; a.ldq = n.A; a.K = S.Kp; a.ldk = n.A; a.V = S.Vp; a.ldv = n.A; a.v = w.att_v;
+        a.in_lens = in_lens; a.out_lens = out_lens; a.prior = d.has_prior ? prior : nullptr; a.reversed = d.reversed;
+        a.temperature = d.temperature; a.attn = attn; a.logprob = logprob; a.p_save = S.p_save;
+        a.ctx16 = S.d16 + H; a.ldc = n.D; a.ctx32 = nullptr; a.ldc32 = 0;
+        FT_TRY(launch_attn_fwd(a, st));
+    }
+    if (d.has_gate) FT_TRY(launch_gate_fwd(S.d16, n.D, n.D, w.gate_w, w.gate_b, n.R, gates, st));
+
+    // 2-layer lstm
+    FT_TRY(gemm_fwd(st, n.R, G, n.D, S.d16, n.D, F.w.w_ih0, n.D, w.lstm_b_ih0, w.lstm_b_hh0, 0, F.X, G, nullptr, 0));
+    FT_TRY(launch_lstm_fwd(n.T, n.B, F.X, F.w.w_hh0, out_lens, S.h0_16, H, S.gates0, S.c0, nullptr, 0, F.flags, st));
+    FT_TRY(gemm_fwd(st, n.R, G, H, S.h0_16, H, F.w.w_ih1, H, w.lstm_b_ih1, w.lstm_b_hh1, 0, F.X, G, nullptr, 0));
+    FT_TRY(launch_lstm_fwd(n.T, n.B, F.X, F.w.w_hh1, out_lens, S.h1_16, H, S.gates1, S.c1, nullptr, 0, F.flags, st));
+
+    // dense x2 (tanh fused in the GEMM epilogue), 1x1 conv, affine coupling
+    FT_TRY(gemm_fwd(st, n.R, H, H, S.h1_16, H, F.w.w1, H, w.dense_b0, nullptr, 1, nullptr, 0, S.y1_16, H));
+    FT_TRY(gemm_fwd(st, n.R, H, H, S.y1_16, H, F.w.w2, H, w.dense_b1, nullptr, 1, nullptr, 0, S.y2_16, H));
+    FT_TRY(gemm_fwd(st, n.R, 2 * n.M, H, S.y2_16, H, F.w.wc, H, w.conv_b, nullptr, 0, S.o32, 2 * n.M, nullptr, 0));
+    FT_TRY(launch_affine_fwd(S.o32, mel_flow, out_lens, n.T, n.B, n.M, d.reversed, mel_out, log_s, st));
+    return 0;
+}
+
+// =================================================================================================== backward
+int ar_step_bwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* mel, const int* in_lens, const int* out_lens,
+                const float* attn, const float* d_mel_out, const float* d_log_s, const float* d_gates, const float* d_attn,
+                const float* d_logprob, float* d_mel, float* d_text, const FtArStepWeights& g, void* saved, void* scratch,
+                cudaStream_t st) {
+    FT_TRY(check_desc(d));
+    const Dims n(d);
+    Plan ps; ps.base = static_cast<uint8_t*>(saved);
+    Saved S; S.plan(ps, d);
+    Plan pb; pb.base = static_cast<uint8_t*>(scratch);
+    BwdScratch F; F.plan(pb, d);
+    const float* mel_flow = d.reversed ? S.mel_flow : mel;
+    const long long R = n.R, RL = n.RL, Rm = n.R - n.B;     // Rm: rows with a predecessor step
+
+    // bf16 operand copies: natural layouts for dgrad (B operand MN-major), transposed recurrent weights for BPTT
+    FT_TRY(launch_cast(w.attn_lstm_w_ih, 2, F.w.w_ih_a, 1, static_cast<long long>(G) * n.M, st));
+    FT_TRY(launch_cast(w.lstm_w_ih0, 2, F.w.w_ih0, 1, static_cast<long long>(G) * n.D, st));
+    FT_TRY(launch_cast(w.lstm_w_ih1, 2, F.w.w_ih1, 1, static_cast<long long>(G) * H, st));
+    FT_TRY(launch_cast(w.att_query, 2, F.w.wq, 1, static_cast<long long>(n.A) * H, st));
+    FT_TRY(launch_cast(w.att_key, 2, F.w.wk, 1, static_cast<long long>(n.A) * n.E, st));
+    FT_TRY(launch_cast(w.att_value, 2, F.w.wv, 1, static_cast<long long>(n.A) * n.E, st));
+    FT_TRY(launch_cast(w.dense_w0, 2, F.w.w1, 1, static_cast<long long>(H) * H, st));
+    FT_TRY(launch_cast(w.dense_w1, 2, F.w.w2, 1, static_cast<long long>(H) * H, st));
+    FT_TRY(launch_cast(w.conv_w, 2, F.w.wc, 1, static_cast<long long>(2 * n.M) * H, st));
+    FT_TRY(launch_transpose_cast_bf16(w.attn_lstm_w_hh, F.w.w_hh_a, G, H, st));
+    FT_TRY(launch_transpose_cast_bf16(w.lstm_w_hh0, F.w.w_hh0, G, H, st));
+    FT_TRY(launch_transpose_cast_bf16(w.lstm_w_hh1, F.w.w_hh1, G, H, st));
+
+    // 1. affine coupling
+    FT_TRY(launch_affine_bwd(d_mel_out, d_log_s, S.o32, mel_flow, out_lens, n.T, n.B, n.M, d.reversed, F.do16, F.dmel_flow, st));
+
+    // 2. 1x1 conv
+    FT_TRY(launch_cast(S.y2_16, 0, F.cvt, 1, R * H, st));
+    FT_TRY(gemm_wgrad(st, 2 * n.M, H, R, F.do16, 2 * n.M, F.cvt, H, g.conv_w, H));
+    FT_TRY(launch_colsum(F.do16, 1, 2 * n.M, R, 2 * n.M, g.conv_b, st));
+    FT_TRY(gemm_dgrad(st, R, H, 2 * n.M, F.do16, 2 * n.M, F.w.wc, H, 0, nullptr, 0, F.dy2, H, S.y2_16, H));      // * (1 - y2^2)
+
+    // 3. dense layer 1 (second linear)
+    FT_TRY(launch_cast(S.y1_16, 0, F.cvt, 1, R * H, st));
+    FT_TRY(gemm_wgrad(st, H, H, R, F.dy2, H, F.cvt, H, g.dense_w1, H));
+    FT_TRY(launch_colsum(F.dy2, 1, H, R, H, g.dense_b1, st));
+    FT_TRY(gemm_dgrad(st, R, H, H, F.dy2, H, F.w.w2, H, 0, nullptr, 0, F.dy1, H, S.y1_16, H));                    // * (1 - y1^2)
+
+    // 4. dense layer 0
+    FT_TRY(launch_cast(S.h1_16, 0, F.cvt, 1, R * H, st));
+    FT_TRY(gemm_wgrad(st, H, H, R, F.dy1, H, F.cvt, H, g.dense_w0, H));
+    FT_TRY(launch_colsum(F.dy1, 1, H, R, H, g.dense_b0, st));
+    FT_TRY(gemm_dgrad(st, R, H, H, F.dy1, H, F.w.w1, H, 0, F.dh, H, nullptr, 0, nullptr, 0));
+
+    // 5. lstm layer 1  (F.cvt still holds h1 in bf16)
+    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dh, H, F.w.w_hh1, S.gates1, S.c1, out_lens, F.dG, F.flags, st));
+    FT_TRY(gemm_wgrad(st, G, H, Rm, F.dG + static_cast<size_t>(n.B) * G, G, F.cvt, H, g.lstm_w_hh1, H));
+    FT_TRY(launch_cast(S.h0_16, 0, F.cvt, 1, R * H, st));
+    FT_TRY(gemm_wgrad(st, G, H, R, F.dG, G, F.cvt, H, g.lstm_w_ih1, H));
+    FT_TRY(launch_colsum(F.dG, 1, G, R, G, g.lstm_b_ih1, st));
+    FT_TRY(copy_f32(g.lstm_b_hh1, g.lstm_b_ih1, G, st));
+    FT_TRY(gemm_dgrad(st, R, H, G, F.dG, G, F.w.w_ih1, H, 0, F.dh, H, nullptr, 0, nullptr, 0));
+
+    // 6. lstm layer 0  (F.cvt holds h0 in bf16)
+    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dh, H, F.w.w_hh0, S.gates0, S.c0, out_lens, F.dG, F.flags, st));
+    FT_TRY(gemm_wgrad(st, G, H, Rm, F.dG + static_cast<size_t>(n.B) * G, G, F.cvt, H, g.lstm_w_hh0, H));
+    FT_TRY(launch_cast(S.d16, 0, F.cvt, 1, R * n.D, st));
+    FT_TRY(gemm_wgrad(st, G, n.D, R, F.dG, G, F.cvt, n.D, g.lstm_w_ih0, n.D));
+    FT_TRY(launch_colsum(F.dG, 1, G, R, G, g.lstm_b_ih0, st));
+    FT_TRY(copy_f32(g.lstm_b_hh0, g.lstm_b_ih0, G, st));
+    FT_TRY(gemm_dgrad(st, R, n.D, G, F.dG, G, F.w.w_ih0, n.D, 0, F.dd, n.D, nullptr, 0, nullptr, 0));
+
+    // 7. gate layer (last flow only)
+    if (d.has_gate && g.gate_w) {
+        FT_TRY(zero(g.gate_w, sizeof(float) * n.D, st));
+        FT_TRY(zero(g.gate_b, sizeof(float), st));
+        if (d_gates) FT_TRY(launch_gate_bwd(S.d16, n.D, n.D, w.gate_w, d_gates, R, F.dd, n.D, g.gate_w, g.gate_b, st));
+    }
+
+    // 8. attention (score/softmax/context) with tanh recompute
+    FT_TRY(zero(F.dK, sizeof(float) * RL * n.A, st));
+    FT_TRY(zero(F.dV, sizeof(float) * RL * n.A, st));
+    FT_TRY(zero(g.att_v, sizeof(float) * n.A, st));
+    {
+        AttnBwdArgs a;
+        a.T = n.T; a.B = n.B; a.L = n.L; a.A = n.A;
+        a.Q = S.Q; a.ldq = n.A; a.K = S.Kp; a.ldk = n.A; a.V = S.Vp; a.ldv = n.A; a.v = w.att_v;
+        a.in_lens = in_lens; a.out_lens = out_lens; a.attn = attn; a.p_save = S.p_save; a.temperature = d.temperature;
+        a.dctx = F.dd + H; a.lddc = n.D; a.dattn_ext = d_attn; a.dlp_ext = d_logprob;
+        a.dQ = F.dQ; a.lddq = n.A; a.dK = F.dK; a.lddk = n.A; a.dV = F.dV; a.lddv = n.A; a.dv = g.att_v;
+        FT_TRY(launch_attn_bwd(a, st));
+    }
+
+    // 9. Q/K/V projections  (F.cvt holds d = [hA ; ctx] in bf16, row pitch D)
+    FT_TRY(launch_cast(F.dQ, 2, F.dQ16, 1, R * n.A, st));
+    FT_TRY(gemm_wgrad(st, n.A, H, R, F.dQ16, n.A, F.cvt, n.D, g.att_query, H));
+    FT_TRY(gemm_dgrad(st, R, H, n.A, F.dQ16, n.A, F.w.wq, H, 1, F.dd, n.D, nullptr, 0, nullptr, 0));   // dhA += dQ Wq
+    FT_TRY(launch_cast(F.dK, 2, F.dK16, 1, RL * n.A, st));
+    FT_TRY(launch_cast(F.dV, 2, F.dV16, 1, RL * n.A, st));
+    FT_TRY(launch_cast(S.text16, 0, F.text_bf, 1, RL * n.E, st));
+    FT_TRY(gemm_wgrad(st, n.A, n.E, RL, F.dK16, n.A, F.text_bf, n.E, g.att_key, n.E));
+    FT_TRY(gemm_wgrad(st, n.A, n.E, RL, F.dV16, n.A, F.text_bf, n.E, g.att_value, n.E));
+    FT_TRY(gemm_dgrad(st, RL, n.E, n.A, F.dK16, n.A, F.w.wk, n.E, 0, d_text, n.E, nullptr, 0, nullptr, 0));
+    FT_TRY(gemm_dgrad(st, RL, n.E, n.A, F.dV16, n.A, F.w.wv, n.E, 1, d_text, n.E, nullptr, 0, nullptr, 0));
+
+    // 10. attention_lstm  (dhA = F.dd[:, 0:H], pitch D)
+    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dd, n.D, F.w.w_hh_a, S.gatesA, S.cA, out_lens, F.dG, F.flags, st));
+    FT_TRY(gemm_wgrad(st, G, H, Rm, F.dG + static_cast<size_t>(n.B) * G, G, F.cvt, n.D, g.attn_lstm_w_hh, H));
+    FT_TRY(launch_cast(S.mel_in16, 0, F.melin_bf, 1, R * n.M, st));
+    FT_TRY(gemm_wgrad(st, G, n.M, R, F.dG, G, F.melin_bf, n.M, g.attn_lstm_w_ih, n.M));
+    FT_TRY(launch_colsum(F.dG, 1, G, R, G, g.attn_lstm_b_ih, st));
+    FT_TRY(copy_f32(g.attn_lstm_b_hh, g.attn_lstm_b_ih, G, st));
+    FT_TRY(gemm_dgrad(st, R, n.M, G, F.dG, G, F.w.w_ih_a, n.M, 0, F.dmel_in, n.M, nullptr, 0, nullptr, 0));
+
+    // 11. input gradient: coupling path + (shifted) attention_lstm path, back to natural time
+    if (d_mel) FT_TRY(launch_combine_dmel(F.dmel_flow, F.dmel_in, out_lens, n.T, n.B, n.M, d.reversed, d_mel, st));
+    return 0;
+}
+
+}  // namespace ft
+
+// =================================================================================================== C ABI
+extern "C" {
+
+size_t ft_ar_step_saved_bytes(const FtArStepDesc* d) {
+    ft::Plan p; ft::Saved s; s.plan(p, *d);
+    return p.off + 256;
+}
+size_t ft_ar_step_scratch_bytes(const FtArStepDesc* d) {
+    ft::Plan pf; ft::FwdScratch f; f.plan(pf, *d);
+    ft::Plan pb; ft::BwdScratch b; b.plan(pb, *d);
+    return (pf.off > pb.off ? pf.off : pb.off) + 256;
+}
+int ft_ar_step_saved_lookup(const FtArStepDesc* d, const char* name, size_t* offset, size_t* bytes) {
+    std::vector<ft::Region> regs;
+    ft::Plan p; p.regs = &regs;
+    ft::Saved s; s.plan(p, *d);
+    for (const auto& r : regs)
+        if (std::strcmp(r.name, name) == 0) { *offset = r.off; *bytes = r.bytes; return 0; }
+    return ft::ft_set_error("ft_ar_step_saved_lookup: unknown region");
+}
+
+int ft_ar_step_fwd(const FtArStepDesc* d, const FtArStepWeights* w, const float* mel, const float* text,
+                   const int* in_lens, const int* out_lens, const float* attn_prior, float* mel_out, float* log_s,
+                   float* gates, float* attn, float* attn_logprob, void* saved, void* scratch, void* stream) {
+    if (!d || !w || !mel || !text || !mel_out || !log_s || !attn || !attn_logprob || !saved || !scratch)
+        return ft::ft_set_error("ft_ar_step_fwd: NULL argument");
+    return ft::ar_step_fwd(*d, *w, mel, text, in_lens, out_lens, attn_prior, mel_out, log_s, gates, attn, attn_logprob,
+                           saved, scratch, static_cast<cudaStream_t>(stream));
+}
+
+int ft_ar_step_bwd(const FtArStepDesc* d, const FtArStepWeights* w, const float* mel, const int* in_lens,
+                   const int* out_lens, const float* attn, const float* d_mel_out, const float* d_log_s,
+                   const float* d_gates, const float* d_attn, const float* d_attn_logprob, float* d_mel, float* d_text,
+                   const FtArStepWeights* g, void* saved, void* scratch, void* stream) {
+    if (!d || !w || !mel || !attn || !d_text || !g || !saved || !scratch) return ft::ft_set_error("ft_ar_step_bwd: NULL argument");
+    return ft::ar_step_bwd(*d, *w, mel, in_lens, out_lens, attn, d_mel_out, d_log_s, d_gates, d_attn, d_attn_logprob,
+                           d_mel, d_text, *g, saved, scratch, static_cast<cudaStream_t>(stream));
+}
+
+int ft_nll_reduce(const float* z, const float* const* log_s_list, int n_flows, const float* gate,
+                  const float* gate_target, const int* out_lens, int T, int B, int M, float* sums, void* stream) {
+    return ft::launch_nll_reduce(z, log_s_list, n_flows, gate, gate_target, out_lens, T, B, M, sums,
+                                 static_cast<cudaStream_t>(stream));
+}
+int ft_nll_grad(const float* z, const float* gate, const float* gate_target, const int* out_lens, int T, int B, int M,
+                float sigma, const float* sums, const float* g_nll, const float* g_gate, float* dz, float* dlog_s,
+                float* dgate, void* stream) {
+    return ft::launch_nll_grad(z, gate, gate_target, out_lens, T, B, M, sigma, sums, g_nll, g_gate, dz, dlog_s, dgate,
+                               static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -24,6 +24,7 @@ struct GemmArgs {
     const void* B = nullptr; long long ldb = 0; int b_fmt = 0; int b_mn = 0;
     const float* bias = nullptr; const float* bias2 = nullptr;
     int act = 0; int beta = 0; float alpha = 1.0f;
+    const void* aux16 = nullptr; long long ldaux = 0;   // act == 2: fp16 [M,N] saved tanh output
     float* C32 = nullptr; long long ldc32 = 0;
     void* C16 = nullptr; long long ldc16 = 0; int c16_fmt = 0;
 };
@@ -35,5 +36,40 @@ int launch_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const i
                     void* gates16, float* cstate, float* h32, long long ldh32, int* flags, cudaStream_t st);
 int launch_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void* whhT16, const void* gates16,
                     const float* cstate, const int* lens, void* dG16, int* flags, cudaStream_t st);
+
+int launch_cast(const void* src, int src_fmt, void* dst, int dst_fmt, long long n, cudaStream_t st);   // 0 f16, 1 bf16, 2 f32
+int launch_transpose_cast_bf16(const float* src, void* dst, int rows, int cols, cudaStream_t st);
+int launch_prep_mel(const float* mel, const int* lens, int T, int B, int M, int reversed, void* mel_in16, float* mel_flow, cudaStream_t st);
+int launch_gate_fwd(const void* d16, long long ldd, int K, const float* wg, const float* bg, long long R, float* gate, cudaStream_t st);
+int launch_gate_bwd(const void* d16, long long ldd, int K, const float* wg, const float* dgate, long long R, float* dd,
+                    long long lddd, float* dwg, float* dbg, cudaStream_t st);
+int launch_affine_fwd(const float* o, const float* mel_flow, const int* lens, int T, int B, int M, int reversed, float* z,
+                      float* log_s, cudaStream_t st);
+int launch_affine_bwd(const float* dz, const float* dlog_s_ext, const float* o, const float* mel_flow, const int* lens, int T,
+                      int B, int M, int reversed, void* do16, float* dmel_flow, cudaStream_t st);
+int launch_combine_dmel(const float* dmel_flow, const float* dmel_in, const int* lens, int T, int B, int M, int reversed,
+                        float* dmel, cudaStream_t st);
+int launch_colsum(const void* src, int fmt, long long ld, long long R, int C, float* out, cudaStream_t st);
+int launch_nll_reduce(const float* z, const float* const* log_s_list_dev, int n_flows, const float* gate,
+                      const float* gate_target, const int* lens, int T, int B, int M, float* sums, cudaStream_t st);
+int launch_nll_grad(const float* z, const float* gate, const float* gate_target, const int* lens, int T, int B, int M,
+                    float sigma, const float* sums, const float* g_nll, const float* g_gate, float* dz, float* dlog_s,
+                    float* dgate, cudaStream_t st);
+
+struct AttnFwdArgs {
+    int T, B, L, A;
+    const float* Q; long long ldq; const float* K; long long ldk; const float* V; long long ldv; const float* v;
+    const int* in_lens; const int* out_lens; const float* prior; int reversed; float temperature;
+    float* attn; float* logprob; float* p_save; void* ctx16; long long ldc; float* ctx32; long long ldc32;
+};
+struct AttnBwdArgs {
+    int T, B, L, A;
+    const float* Q; long long ldq; const float* K; long long ldk; const float* V; long long ldv; const float* v;
+    const int* in_lens; const int* out_lens; const float* attn; const float* p_save; float temperature;
+    const float* dctx; long long lddc; const float* dattn_ext; const float* dlp_ext;
+    float* dQ; long long lddq; float* dK; long long lddk; float* dV; long long lddv; float* dv;
+};
+int launch_attn_fwd(const AttnFwdArgs& a, cudaStream_t st);
+int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t st);
 
 }  // namespace ft

@@ -29,7 +29,8 @@ struct GemmParams {
     int a_mn, b_mn;            // 1 = operand given MN-major ([K, rows] row-major)
     const float* bias;         // [N] or null
     const float* bias2;        // [N] or null
-    int act;                   // 0 none, 1 tanh
+    int act;                   // 0 none, 1 tanh, 2 multiply by (1 - aux^2)  (tanh backward; aux = saved tanh output)
+    const __half* aux16; long long ldaux;
     int beta;                  // 1: C32 += result (C32 read-modify-write)
     float alpha;               // scale on the accumulator before bias
     float* C32; long long ldc32;
@@ -146,6 +147,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (p.act == 1) x = tanh_f(x);
                 v[j] = x;
             }
+            if (p.act == 2) {
+                const __half* ax = p.aux16 + m * p.ldaux + n0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (j < nvalid) {
+                        const float y = __half2float(ax[j]);
+                        v[j] *= (1.f - y * y);
+                    }
+                }
+            }
             if (p.C32) {
                 float* dst = p.C32 + m * p.ldc32 + n0;
                 if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -244,7 +255,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
     if (rc) return rc;
     GemmParams p;
     p.M = g.M; p.N = g.N; p.K = g.K; p.a_fmt = g.a_fmt; p.b_fmt = g.b_fmt; p.a_mn = g.a_mn; p.b_mn = g.b_mn;
-    p.bias = g.bias; p.bias2 = g.bias2; p.act = g.act; p.beta = g.beta; p.alpha = g.alpha;
+    p.bias = g.bias; p.bias2 = g.bias2; p.act = g.act; p.aux16 = static_cast<const __half*>(g.aux16); p.ldaux = g.ldaux; p.beta = g.beta; p.alpha = g.alpha;
     p.C32 = g.C32; p.ldc32 = g.ldc32; p.C16 = g.C16; p.ldc16 = g.ldc16; p.c16_fmt = g.c16_fmt;
     p.status = ft_status_word();
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);

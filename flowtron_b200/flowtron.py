@@ -1,0 +1,448 @@
+"""Host-side mirror of the reference's model API for the AR-flow hot path.
+
+Same class names, constructor signatures, attribute names and ``state_dict`` layout as
+/root/reference/flowtron.py (Flowtron :831-961, AR_Step :645-828, AR_Back_Step :595-642,
+Attention :528-592, DenseLayer :453-464, LinearNorm :278-288, Encoder :467-525, FlowtronLoss :185-275), so a
+reference checkpoint loads with ``strict=True`` and callers switch by changing the import.
+
+The flow steps, the NLL/gate loss and inference run on hand-written sm_100a kernels through the C ABI
+(include/flowtron_b200.h).  There is NO torch/CPU fallback for that path: CPU tensors raise.  The Encoder and
+the embeddings (run once per utterance over L tokens, <2% of FLOPs; SURVEY.md §8f "next") stay ordinary
+PyTorch modules, written device-agnostically.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn, Tensor
+from torch.nn import functional as F
+
+from . import _lib
+from ._lib import FlowtronB200Error
+
+
+def get_mask_from_lengths(lengths: Tensor) -> Tensor:
+    """flowtron.py:39-50 (device-agnostic: the reference hard-codes torch.cuda.LongTensor)."""
+    max_len = int(torch.max(lengths).item())
+    ids = torch.arange(0, max_len, device=lengths.device, dtype=lengths.dtype)
+    return (ids < lengths.unsqueeze(1)).bool()
+
+
+get_gate_mask_from_lengths = get_mask_from_lengths
+
+
+# --------------------------------------------------------------------------------------------- encoder (torch)
+def masked_instance_norm(input, mask, weight, bias, eps: float = 1e-5):
+    """flowtron.py:53-92 with use_input_stats=True, no running stats."""
+    lengths = mask.sum((-1,))
+    mean = (input * mask).sum((-1,)) / lengths
+    var = (((input - mean[..., None]) * mask) ** 2).sum((-1,)) / lengths
+    out = (input - mean[..., None]) / torch.sqrt(var[..., None] + eps)
+    return out * weight[None, :, None] + bias[None, :, None]
+
+
+class MaskedInstanceNorm1d(nn.InstanceNorm1d):
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=False, track_running_stats=False):
+        super().__init__(num_features, eps, momentum, affine, track_running_stats)
+
+    def forward(self, input, mask=None):
+        if mask is None:
+            return F.instance_norm(input, self.running_mean, self.running_var, self.weight, self.bias,
+                                   self.training or not self.track_running_stats, self.momentum, self.eps)
+        return masked_instance_norm(input, mask.to(input.dtype), self.weight, self.bias, self.eps)
+
+
+class LinearNorm(nn.Module):
+    def __init__(self, in_dim, out_dim, bias=True, w_init_gain='linear'):
+        super().__init__()
+        self.linear_layer = nn.Linear(in_dim, out_dim, bias=bias)
+        nn.init.xavier_uniform_(self.linear_layer.weight, gain=nn.init.calculate_gain(w_init_gain))
+
+    def forward(self, x):
+        return self.linear_layer(x)
+
+
+class ConvNorm(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size=1, stride=1, padding=None, dilation=1, bias=True,
+                 w_init_gain='linear'):
+        super().__init__()
+        if padding is None:
+            assert kernel_size % 2 == 1
+            padding = int(dilation * (kernel_size - 1) / 2)
+        self.conv = nn.Conv1d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding,
+                              dilation=dilation, bias=bias)
+        nn.init.xavier_uniform_(self.conv.weight, gain=nn.init.calculate_gain(w_init_gain))
+
+    def forward(self, signal):
+        return self.conv(signal)
+
+
+class DenseLayer(nn.Module):
+    def __init__(self, in_dim=1024, sizes=[1024, 1024]):
+        super().__init__()
+        in_sizes = [in_dim] + sizes[:-1]
+        self.layers = nn.ModuleList([LinearNorm(i, o, bias=True) for (i, o) in zip(in_sizes, sizes)])
+
+    def forward(self, x):
+        for linear in self.layers:
+            x = torch.tanh(linear(x))
+        return x
+
+
+class Encoder(nn.Module):
+    """flowtron.py:467-525 (3 x conv+masked instance norm+relu+dropout, packed BiLSTM)."""
+
+    def __init__(self, encoder_n_convolutions=3, encoder_embedding_dim=512, encoder_kernel_size=5, norm_fn=nn.BatchNorm1d):
+        super().__init__()
+        convolutions = []
+        for _ in range(encoder_n_convolutions):
+            convolutions.append(nn.Sequential(
+                ConvNorm(encoder_embedding_dim, encoder_embedding_dim, kernel_size=encoder_kernel_size, stride=1,
+                         padding=int((encoder_kernel_size - 1) / 2), dilation=1, w_init_gain='relu'),
+                norm_fn(encoder_embedding_dim, affine=True)))
+        self.convolutions = nn.ModuleList(convolutions)
+        self.lstm = nn.LSTM(encoder_embedding_dim, int(encoder_embedding_dim / 2), 1, batch_first=True, bidirectional=True)
+
+    def forward(self, x, in_lens):
+        mask = get_mask_from_lengths(in_lens).unsqueeze(1) if x.size(0) > 1 else None
+        for conv, norm in self.convolutions:
+            if mask is not None:
+                x = x.masked_fill(~mask, 0.)
+            x = F.dropout(F.relu(norm(conv(x), mask=mask)), 0.5, self.training)
+        x = x.transpose(1, 2)
+        x = nn.utils.rnn.pack_padded_sequence(x, in_lens.cpu(), batch_first=True)
+        self.lstm.flatten_parameters()
+        outputs, _ = self.lstm(x)
+        outputs, _ = nn.utils.rnn.pad_packed_sequence(outputs, batch_first=True)
+        return outputs
+
+    def infer(self, x):
+        for conv in self.convolutions:
+            x = F.dropout(F.relu(conv(x)), 0.5, self.training)
+        x = x.transpose(1, 2)
+        self.lstm.flatten_parameters()
+        outputs, _ = self.lstm(x)
+        return outputs
+
+
+# --------------------------------------------------------------------------------------------- attention params
+class Attention(nn.Module):
+    """Parameter container + mutable ``temperature`` of flowtron.py:528-592.  The math (Q/K/V projections,
+    tanh score, masking, softmax, prior posterior, context) runs inside the fused CUDA attention kernels invoked by
+    AR_Step; this module is never called on its own by the model."""
+
+    def __init__(self, n_mel_channels=80, n_speaker_dim=128, n_text_channels=512, n_att_channels=128, temperature=1.0):
+        super().__init__()
+        self.temperature = temperature
+        self.query = LinearNorm(n_mel_channels, n_att_channels, bias=False, w_init_gain='tanh')
+        self.key = LinearNorm(n_text_channels + n_speaker_dim, n_att_channels, bias=False, w_init_gain='tanh')
+        self.value = LinearNorm(n_text_channels + n_speaker_dim, n_att_channels, bias=False, w_init_gain='tanh')
+        self.v = LinearNorm(n_att_channels, 1, bias=False, w_init_gain='tanh')
+        self.score_mask_value = -float("inf")
+
+    def forward(self, *args, **kwargs):
+        raise FlowtronB200Error("Attention runs fused inside AR_Step on the CUDA path; call AR_Step / Flowtron instead")
+
+
+# --------------------------------------------------------------------------------------------- AR step
+def _lens_i32(lens: Optional[Tensor], device) -> Optional[Tensor]:
+    if lens is None:
+        return None
+    return lens.to(device=device, dtype=torch.int32).contiguous()
+
+
+class _ArStepFn(torch.autograd.Function):
+    """autograd wrapper around ft_ar_step_fwd / ft_ar_step_bwd."""
+
+    @staticmethod
+    def forward(ctx, step, reversed_flag, mel, text, in_lens, out_lens, attn_prior, *params):
+        if not mel.is_cuda:
+            raise FlowtronB200Error("AR_Step needs CUDA tensors: the sm_100a kernels are the only implementation")
+        T, B, M = mel.shape
+        L, _, E = text.shape
+        dev = mel.device
+        has_gate = hasattr(step, 'gate_layer')
+        desc = _lib.FtArStepDesc(T, B, L, M, step.lstm.hidden_size, step.attention_layer.query.linear_layer.out_features,
+                                 E, int(reversed_flag), int(has_gate), int(attn_prior is not None),
+                                 float(step.attention_layer.temperature))
+        mel_c = mel.detach().float().contiguous()
+        text_c = text.detach().float().contiguous()
+        prior_c = None if attn_prior is None else attn_prior.detach().float().contiguous()
+        plist = [p.detach() if p is not None else None for p in params]
+        plist = [p if (p is None or p.is_contiguous()) else p.contiguous() for p in plist]
+        weights = _lib.make_weights(plist)
+        saved_bytes, scratch_bytes = _lib.ar_step_sizes(desc)
+        saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
+        scratch = _lib.scratch_buffer(scratch_bytes, dev)
+        mel_out = torch.empty(T, B, M, device=dev)
+        log_s = torch.empty(T, B, M, device=dev)
+        gates = torch.empty(T, B, 1, device=dev) if has_gate else None
+        attn = torch.empty(B, T, L, device=dev)
+        logprob = torch.empty(B, T, L, device=dev)
+        _lib.ar_step_fwd(desc, weights, mel_c, text_c, in_lens, out_lens, prior_c, mel_out, log_s, gates, attn, logprob,
+                         saved, scratch)
+        ctx.desc, ctx.saved_buf, ctx.plist = desc, saved, plist
+        ctx.mel_c, ctx.in_lens, ctx.out_lens, ctx.attn = mel_c, in_lens, out_lens, attn
+        ctx.text_shape = text.shape
+        ctx.has_gate = has_gate
+        if has_gate:
+            return mel_out, log_s, gates, attn, logprob
+        return mel_out, log_s, attn, logprob
+
+    @staticmethod
+    def backward(ctx, *grads):
+        if ctx.has_gate:
+            d_mel_out, d_log_s, d_gates, d_attn, d_lp = grads
+        else:
+            d_mel_out, d_log_s, d_attn, d_lp = grads
+            d_gates = None
+        c = lambda g: None if g is None else g.float().contiguous()
+        d_mel_out, d_log_s, d_gates, d_attn, d_lp = map(c, (d_mel_out, d_log_s, d_gates, d_attn, d_lp))
+        desc = ctx.desc
+        dev = ctx.mel_c.device
+        d_mel = torch.empty_like(ctx.mel_c)
+        d_text = torch.empty(ctx.text_shape, device=dev, dtype=torch.float32)
+        gl = [None if p is None else torch.empty_like(p) for p in ctx.plist]
+        weights, grads_s = _lib.make_weights(ctx.plist), _lib.make_weights(gl)
+        _, scratch_bytes = _lib.ar_step_sizes(desc)
+        scratch = _lib.scratch_buffer(scratch_bytes, dev)
+        _lib.ar_step_bwd(desc, weights, ctx.mel_c, ctx.in_lens, ctx.out_lens, ctx.attn, d_mel_out, d_log_s, d_gates, d_attn,
+                         d_lp, d_mel, d_text, grads_s, ctx.saved_buf, scratch)
+        ctx.saved_buf = None
+        return (None, None, d_mel, d_text, None, None, None, *gl)
+
+
+class AR_Step(nn.Module):
+    """flowtron.py:645-828.  Same parameters / state_dict keys; forward/infer run on the sm_100a kernels."""
+
+    def __init__(self, n_mel_channels, n_speaker_dim, n_text_channels, n_in_channels, n_hidden, n_attn_channels,
+                 n_lstm_layers, add_gate, use_cumm_attention):
+        super().__init__()
+        if use_cumm_attention:
+            raise NotImplementedError("use_cumm_attention is outside the B200 hot-path scope (off in every shipped config)")
+        if n_lstm_layers != 2 or n_hidden != 1024:
+            raise NotImplementedError("the sm_100a kernels are built for n_lstm_layers=2, n_hidden=1024 (config.json:56-57)")
+        self.use_cumm_attention = use_cumm_attention
+        self.conv = nn.Conv1d(n_hidden, 2 * n_mel_channels, 1)
+        self.conv.weight.data = 0.0 * self.conv.weight.data
+        self.conv.bias.data = 0.0 * self.conv.bias.data
+        self.lstm = nn.LSTM(n_hidden + n_attn_channels, n_hidden, n_lstm_layers)
+        self.attention_lstm = nn.LSTM(n_mel_channels, n_hidden)
+        self.attention_layer = Attention(n_hidden, n_speaker_dim, n_text_channels, n_attn_channels)
+        self.dense_layer = DenseLayer(in_dim=n_hidden, sizes=[n_hidden, n_hidden])
+        if add_gate:
+            self.gate_threshold = 0.5
+            self.gate_layer = LinearNorm(n_hidden + n_attn_channels, 1, bias=True, w_init_gain='sigmoid')
+
+    def _param_list(self):
+        """Order of _lib.AR_WEIGHT_FIELDS."""
+        al, ls, at, dl = self.attention_lstm, self.lstm, self.attention_layer, self.dense_layer
+        gate = getattr(self, 'gate_layer', None)
+        return [al.weight_ih_l0, al.weight_hh_l0, al.bias_ih_l0, al.bias_hh_l0,
+                ls.weight_ih_l0, ls.weight_hh_l0, ls.bias_ih_l0, ls.bias_hh_l0,
+                ls.weight_ih_l1, ls.weight_hh_l1, ls.bias_ih_l1, ls.bias_hh_l1,
+                at.query.linear_layer.weight, at.key.linear_layer.weight, at.value.linear_layer.weight,
+                at.v.linear_layer.weight,
+                dl.layers[0].linear_layer.weight, dl.layers[0].linear_layer.bias,
+                dl.layers[1].linear_layer.weight, dl.layers[1].linear_layer.bias,
+                self.conv.weight, self.conv.bias,
+                None if gate is None else gate.linear_layer.weight, None if gate is None else gate.linear_layer.bias]
+
+    def _run(self, mel, text, mask, out_lens, attn_prior, reversed_flag):
+        dev = mel.device
+        in_lens = None
+        if mask is not None:
+            in_lens = (~mask[..., 0]).sum(1).to(torch.int32).contiguous()
+        out = _ArStepFn.apply(self, reversed_flag, mel, text, in_lens, _lens_i32(out_lens, dev), attn_prior,
+                              *self._param_list())
+        if hasattr(self, 'gate_layer'):
+            mel_out, log_s, gates, attn, lp = out
+        else:
+            (mel_out, log_s, attn, lp), gates = out, None
+        return mel_out, log_s, gates, attn, lp
+
+    def forward(self, mel, text, mask, out_lens, attn_prior=None):
+        return self._run(mel, text, mask, out_lens, attn_prior, False)
+
+    def infer(self, residual, text, attns, attn_prior=None):
+        from .inference import ar_step_infer
+        return ar_step_infer(self, residual, text, attns, attn_prior, reversed_flag=False)
+
+
+class AR_Back_Step(nn.Module):
+    """flowtron.py:595-642.  The flip/roll of the reference is an index map inside the kernels (no copies, no host syncs)."""
+
+    def __init__(self, n_mel_channels, n_speaker_dim, n_text_dim, n_in_channels, n_hidden, n_attn_channels, n_lstm_layers,
+                 add_gate, use_cumm_attention):
+        super().__init__()
+        self.ar_step = AR_Step(n_mel_channels, n_speaker_dim, n_text_dim, n_mel_channels + n_speaker_dim, n_hidden,
+                               n_attn_channels, n_lstm_layers, add_gate, use_cumm_attention)
+
+    def forward(self, mel, text, mask, out_lens, attn_prior=None):
+        if out_lens is None:
+            out_lens = torch.full((mel.size(1),), mel.size(0), dtype=torch.long, device=mel.device)
+        return self.ar_step._run(mel, text, mask, out_lens, attn_prior, True)
+
+    def infer(self, residual, text, attns, attn_prior=None):
+        from .inference import ar_step_infer
+        return ar_step_infer(self.ar_step, residual, text, attns, attn_prior, reversed_flag=True)
+
+
+# --------------------------------------------------------------------------------------------- model
+class Flowtron(nn.Module):
+    """flowtron.py:831-961 (n_components=0 / no cumulative attention: the variants every shipped config uses)."""
+
+    def __init__(self, n_speakers, n_speaker_dim, n_text, n_text_dim, n_flows, n_mel_channels, n_hidden,
+                 n_attn_channels, n_lstm_layers, use_gate_layer, mel_encoder_n_hidden, n_components, fixed_gaussian,
+                 mean_scale, dummy_speaker_embedding, use_cumm_attention):
+        super().__init__()
+        if n_components > 1:
+            raise NotImplementedError("the GMM prior (n_components > 1) is outside the B200 hot-path scope")
+        norm_fn = MaskedInstanceNorm1d
+        self.speaker_embedding = nn.Embedding(n_speakers, n_speaker_dim)
+        self.embedding = nn.Embedding(n_text, n_text_dim)
+        self.flows = nn.ModuleList()
+        self.encoder = Encoder(norm_fn=norm_fn, encoder_embedding_dim=n_text_dim)
+        self.dummy_speaker_embedding = dummy_speaker_embedding
+        for i in range(n_flows):
+            add_gate = True if (i == (n_flows - 1) and use_gate_layer) else False
+            cls = AR_Step if i % 2 == 0 else AR_Back_Step
+            self.flows.append(cls(n_mel_channels, n_speaker_dim, n_text_dim, n_mel_channels + n_speaker_dim, n_hidden,
+                                  n_attn_channels, n_lstm_layers, add_gate, use_cumm_attention))
+
+    def forward(self, mel, speaker_ids, text, in_lens, out_lens, attn_prior=None):
+        speaker_ids = speaker_ids * 0 if self.dummy_speaker_embedding else speaker_ids
+        speaker_vecs = self.speaker_embedding(speaker_ids)
+        text = self.embedding(text).transpose(1, 2)
+        text = self.encoder(text, in_lens)
+        mean, log_var, prob = None, None, None
+        text = text.transpose(0, 1)
+        mel = mel.permute(2, 0, 1)
+        encoder_outputs = torch.cat([text, speaker_vecs.expand(text.size(0), -1, -1)], 2)
+        log_s_list, attns_list, attns_logprob_list = [], [], []
+        mask = ~get_mask_from_lengths(in_lens)[..., None]
+        gate = None
+        for i, flow in enumerate(self.flows):
+            mel, log_s, gate, attn_out, attn_logprob_out = flow(mel, encoder_outputs, mask, out_lens, attn_prior)
+            log_s_list.append(log_s)
+            attns_list.append(attn_out)
+            attns_logprob_list.append(attn_logprob_out)
+        return (mel, log_s_list, gate, attns_list, attns_logprob_list, mean, log_var, prob)
+
+    def infer(self, residual, speaker_ids, text, temperature=1.0, gate_threshold=0.5, attns=None, attn_prior=None):
+        speaker_ids = speaker_ids * 0 if self.dummy_speaker_embedding else speaker_ids
+        speaker_vecs = self.speaker_embedding(speaker_ids)
+        text = self.embedding(text).transpose(1, 2)
+        text = self.encoder.infer(text)
+        text = text.transpose(0, 1)
+        encoder_outputs = torch.cat([text, speaker_vecs.expand(text.size(0), -1, -1)], 2)
+        residual = residual.permute(2, 0, 1)
+        attention_weights = []
+        for i, flow in enumerate(reversed(self.flows)):
+            attn = None if attns is None else list(reversed(attns))[i]
+            self.set_temperature_and_gate(flow, temperature, gate_threshold)
+            residual, attention_weight = flow.infer(residual, encoder_outputs, attn, attn_prior=attn_prior)
+            attention_weights.append(attention_weight)
+        return residual.permute(1, 2, 0), attention_weights
+
+    @staticmethod
+    def set_temperature_and_gate(flow, temperature, gate_threshold):
+        flow = flow.ar_step if hasattr(flow, "ar_step") else flow
+        flow.attention_layer.temperature = temperature
+        if hasattr(flow, 'gate_layer'):
+            flow.gate_threshold = gate_threshold
+
+
+# --------------------------------------------------------------------------------------------- loss
+class _NllGateFn(torch.autograd.Function):
+    """Masked Gaussian NLL + log-det + gate BCE (flowtron.py:205-243) as two CUDA reductions."""
+
+    @staticmethod
+    def forward(ctx, sigma, z, gate_pred, gate_target, out_lens, *log_s_list):
+        if not z.is_cuda:
+            raise FlowtronB200Error("FlowtronLoss needs CUDA tensors")
+        T, B, M = z.shape
+        dev = z.device
+        zc = z.detach().float().contiguous()
+        lsl = [ls.detach().float().contiguous() for ls in log_s_list]
+        ptrs = torch.tensor([t.data_ptr() for t in lsl], dtype=torch.int64, device=dev)
+        gp = None if gate_pred is None else gate_pred.detach().float().contiguous()
+        gt = None if gate_pred is None else gate_target.detach().float().contiguous()
+        lens = out_lens.to(device=dev, dtype=torch.int32).contiguous()
+        sums = torch.empty(4, device=dev)
+        _lib.nll_reduce(zc, ptrs, len(lsl), gp, gt, lens, sums)
+        n = sums[3]
+        nll = (sums[0] / (2 * sigma * sigma) - sums[1]) / (n * M)
+        gate_loss = (sums[2] / n).reshape(1)
+        ctx.sigma, ctx.n_flows = sigma, len(lsl)
+        ctx.save = (zc, gp, gt, lens, sums, lsl)
+        return nll, gate_loss
+
+    @staticmethod
+    def backward(ctx, g_nll, g_gate):
+        zc, gp, gt, lens, sums, lsl = ctx.save
+        dz = torch.empty_like(zc)
+        dls = torch.empty_like(zc)
+        dgate = None if gp is None else torch.empty_like(gp)
+        gn = g_nll.reshape(1).float().contiguous()
+        gg = None if g_gate is None else g_gate.reshape(1).float().contiguous()
+        _lib.nll_grad(zc, gp, gt, lens, ctx.sigma, sums, gn, gg, dz, dls, dgate)
+        return (None, dz, dgate, None, None, *([dls] * ctx.n_flows))
+
+
+class AttentionCTCLoss(nn.Module):
+    """flowtron.py:155-182 — out of the kernel scope: plain torch over the kernels' attn_logprob;
+    its gradient re-enters the CUDA path through ft_ar_step_bwd's d_attn_logprob."""
+
+    def __init__(self, blank_logprob=-1):
+        super().__init__()
+        self.log_softmax = nn.LogSoftmax(dim=3)
+        self.blank_logprob = blank_logprob
+        self.CTCLoss = nn.CTCLoss(zero_infinity=True)
+
+    def forward(self, attn, in_lens, out_lens, attn_logprob):
+        assert attn_logprob is not None
+        key_lens, query_lens = in_lens, out_lens
+        attn_logprob_padded = F.pad(input=attn_logprob, pad=(1, 0, 0, 0, 0, 0, 0, 0), value=self.blank_logprob)
+        cost_total = 0.0
+        for bid in range(attn_logprob.shape[0]):
+            target_seq = torch.arange(1, int(key_lens[bid]) + 1).unsqueeze(0)
+            curr_logprob = attn_logprob_padded[bid].permute(1, 0, 2)[:int(query_lens[bid]), :, :int(key_lens[bid]) + 1]
+            curr_logprob = self.log_softmax(curr_logprob[None])[0]
+            cost_total += self.CTCLoss(curr_logprob, target_seq, input_lengths=query_lens[bid:bid + 1],
+                                       target_lengths=key_lens[bid:bid + 1])
+        return cost_total / attn_logprob.shape[0]
+
+
+class FlowtronLoss(nn.Module):
+    def __init__(self, sigma=1.0, gm_loss=False, gate_loss=True, use_ctc_loss=False, ctc_loss_weight=0.0, blank_logprob=-1):
+        super().__init__()
+        if gm_loss:
+            raise NotImplementedError("gm_loss (GMM prior) is outside the B200 hot-path scope")
+        self.sigma = sigma
+        self.gm_loss = gm_loss
+        self.gate_loss = gate_loss
+        self.use_ctc_loss = use_ctc_loss
+        self.ctc_loss_weight = ctc_loss_weight
+        self.blank_logprob = blank_logprob
+        self.attention_loss = AttentionCTCLoss(blank_logprob=self.blank_logprob)
+
+    def forward(self, model_output, gate_target, in_lengths, out_lengths, is_validation=False):
+        z, log_s_list, gate_pred, attn_list, attn_logprob_list, mean, log_var, prob = model_output
+        use_gate = self.gate_loss > 0 and gate_pred is not None
+        loss, gate_loss = _NllGateFn.apply(self.sigma, z, gate_pred if use_gate else None, gate_target, out_lengths,
+                                           *log_s_list)
+        if not use_gate:
+            gate_loss = torch.zeros(1, device=z.device)
+        loss_ctc = torch.zeros_like(gate_loss)
+        if self.use_ctc_loss:
+            for cur_flow_idx, flow_attn in enumerate(attn_list):
+                cur = attn_logprob_list[cur_flow_idx]
+                if cur_flow_idx % 2 != 0:       # back steps return flipped time (flowtron.py:250-256): un-roll, un-flip
+                    cur = torch.stack([cur[k].roll(-int(out_lengths[k]), dims=0) for k in range(cur.size(0))])
+                    cur = torch.flip(cur, (1,))
+                loss_ctc = loss_ctc + self.attention_loss(flow_attn.unsqueeze(1), in_lengths, out_lengths,
+                                                          attn_logprob=cur.unsqueeze(1))
+            loss_ctc = loss_ctc / float(len(attn_list))
+        return loss, gate_loss, loss_ctc

@@ -52,6 +52,66 @@ int ft_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const int* 
 int ft_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void* whhT16, const void* gates16,
                 const float* cstate, const int* lens, void* dG16, int* flags, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * AR_Step / AR_Back_Step (flowtron.py:595-828): one autoregressive flow step, training direction.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int T, B, L;        /* mel frames (padded max), batch, text tokens (padded max) */
+    int n_mel;          /* 80  (n_mel_channels)                                     */
+    int n_hidden;       /* 1024 (must be 1024 in this build)                        */
+    int n_attn;         /* 640 (n_attn_channels)                                    */
+    int n_text;         /* 640 = n_text_dim + n_speaker_dim                         */
+    int reversed;       /* 1 = AR_Back_Step semantics (flowtron.py:605-627)         */
+    int has_gate;       /* flow owns gate_layer (last flow only, flowtron.py:854)   */
+    int has_prior;      /* attn_prior given                                         */
+    float temperature;  /* Attention.temperature (flowtron.py:532, 573)             */
+} FtArStepDesc;
+
+/* fp32 device pointers in PyTorch's native layouts == the state_dict entries of one AR_Step
+ * (SURVEY.md 8a row 15).  The same struct type carries the parameter gradients in ft_ar_step_bwd. */
+typedef struct {
+    float *attn_lstm_w_ih, *attn_lstm_w_hh, *attn_lstm_b_ih, *attn_lstm_b_hh;   /* attention_lstm.*_l0  [4H,M] [4H,H] [4H] [4H] */
+    float *lstm_w_ih0, *lstm_w_hh0, *lstm_b_ih0, *lstm_b_hh0;                   /* lstm.*_l0            [4H,H+A] [4H,H] ...      */
+    float *lstm_w_ih1, *lstm_w_hh1, *lstm_b_ih1, *lstm_b_hh1;                   /* lstm.*_l1            [4H,H] [4H,H] ...        */
+    float *att_query, *att_key, *att_value, *att_v;                            /* attention_layer.{query,key,value,v}.linear_layer.weight */
+    float *dense_w0, *dense_b0, *dense_w1, *dense_b1;                          /* dense_layer.layers.{0,1}.linear_layer.{weight,bias}     */
+    float *conv_w, *conv_b;                                                     /* conv.weight [2M,H,1], conv.bias [2M]                    */
+    float *gate_w, *gate_b;                                                     /* gate_layer.linear_layer.{weight,bias} or NULL           */
+} FtArStepWeights;
+
+/* Bytes of the two caller-owned work areas: `saved` persists from ft_ar_step_fwd to ft_ar_step_bwd of the
+ * same flow; `scratch` is transient and may be shared by all flows on a stream. */
+size_t ft_ar_step_saved_bytes(const FtArStepDesc* d);
+size_t ft_ar_step_scratch_bytes(const FtArStepDesc* d);
+/* Byte offset / size of a named intermediate inside `saved` (debug + tests): returns 0 on success. */
+int ft_ar_step_saved_lookup(const FtArStepDesc* d, const char* name, size_t* offset, size_t* bytes);
+
+/* AR_Step.forward / AR_Back_Step.forward (flowtron.py:725-773, 605-627).
+ *   mel [T,B,M] f32, text [L,B,E] f32 (encoder outputs), in_lens/out_lens int32 [B] (NULL = no padding),
+ *   attn_prior [B,T,L] f32 or NULL  ->  mel_out [T,B,M], log_s [T,B,M], gates [T,B] (NULL if !has_gate),
+ *   attn [B,T,L], attn_logprob [B,T,L].  For reversed flows log_s/gates/attn are in flipped time exactly as
+ *   the reference returns them. */
+int ft_ar_step_fwd(const FtArStepDesc* d, const FtArStepWeights* w, const float* mel, const float* text,
+                   const int* in_lens, const int* out_lens, const float* attn_prior, float* mel_out, float* log_s,
+                   float* gates, float* attn, float* attn_logprob, void* saved, void* scratch, void* stream);
+
+/* Autograd of the above.  Incoming gradients (any may be NULL = zero): d_mel_out, d_log_s [T,B,M], d_gates [T,B],
+ * d_attn, d_attn_logprob [B,T,L].  Outputs: d_mel [T,B,M], d_text [L,B,E] (overwritten), parameter gradients
+ * into `g` (overwritten; same layouts as the weights). */
+int ft_ar_step_bwd(const FtArStepDesc* d, const FtArStepWeights* w, const float* mel, const int* in_lens,
+                   const int* out_lens, const float* attn, const float* d_mel_out, const float* d_log_s,
+                   const float* d_gates, const float* d_attn, const float* d_attn_logprob, float* d_mel, float* d_text,
+                   const FtArStepWeights* g, void* saved, void* scratch, void* stream);
+
+/* FlowtronLoss default branch (flowtron.py:205-243): sums[0]=sum (z m)^2, [1]=sum_flows sum log_s m,
+ * [2]=sum m BCEWithLogits(gate m, target), [3]=n=sum m.  log_s_list: device array of n_flows device pointers. */
+int ft_nll_reduce(const float* z, const float* const* log_s_list, int n_flows, const float* gate,
+                  const float* gate_target, const int* out_lens, int T, int B, int M, float* sums, void* stream);
+/* Gradients of g_nll*nll + g_gate*gate_loss w.r.t. z, every log_s (identical tensor), gate logits. */
+int ft_nll_grad(const float* z, const float* gate, const float* gate_target, const int* out_lens, int T, int B, int M,
+                float sigma, const float* sums, const float* g_nll, const float* g_gate, float* dz, float* dlog_s,
+                float* dgate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,124 @@
+"""GPU parity (through the C ABI): Flowtron.forward + FlowtronLoss + backward vs fixtures generated from the
+reference itself (tests/golden/train_*.npz) and vs the CPU oracle.  Tolerance: 1e-3 of the tensor's max |value|
+(north_star: 'within 1e-3 relative fp32') for z / log_s / gate / attn / attn_logprob on VALID positions;
+losses 1e-4 relative... (see each assert); gradients 1e-2 relative per tensor."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+OUT_LENS = {"cfg1": [128, 100], "f2prior": [96, 61, 80], "f2ragged": [64, 1, 33, 64, 17]}
+
+
+def _load(name):
+    return dict(np.load(os.path.join(GOLDEN, name), allow_pickle=False))
+
+
+def _grad_idx(name, numel, n=32):
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()))
+    return torch.randint(0, numel, (n,), generator=g)
+
+
+def build_model(cfg, seed, device="cuda"):
+    from flowtron_b200.flowtron import Flowtron
+    model = Flowtron(**cfg)
+    model.load_state_dict(synth.synth_params(cfg, seed), strict=True)
+    return model.to(device).eval()
+
+
+def rel_err(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-12)
+
+
+@pytest.mark.parametrize("tag", ["cfg1", "f2prior", "f2ragged"])
+def test_forward_loss_backward_match_reference_goldens(tag):
+    from flowtron_b200 import _lib
+    from flowtron_b200.flowtron import FlowtronLoss
+    gold = _load(f"train_{tag}.npz")
+    n_flows, B, T, L = (int(gold[k]) for k in ("cfg_n_flows", "B", "T", "L"))
+    cfg = dict(synth.DEFAULT_MODEL_CONFIG, n_flows=n_flows)
+    model = build_model(cfg, int(gold["seed"]))
+    batch = synth.synth_batch(B, T, L, cfg, int(gold["seed"]), out_lens=OUT_LENS[tag], with_prior=bool(gold["with_prior"]))
+    dev = "cuda"
+    cu = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    for p in model.parameters():
+        p.requires_grad_(True)
+    out = model(cu["mel"], cu["speaker_ids"], cu["text"], cu["in_lens"], cu["out_lens"], cu["attn_prior"])
+    z, log_s_list, gate, attns, lps = out[:5]
+    crit = FlowtronLoss(sigma=1.0, gate_loss=True)
+    nll, gl, _ = crit(out, cu["gate_target"], cu["in_lens"], cu["out_lens"])
+    (nll + gl).sum().backward()
+    torch.cuda.synchronize()
+    assert _lib.device_status() == 0
+
+    vm = (torch.arange(T)[:, None] < batch["out_lens"][None, :])
+    errs = {}
+    errs["z"] = rel_err(z.detach().cpu()[vm], torch.from_numpy(gold["z"])[vm])
+    errs["gate"] = rel_err(gate.detach().cpu()[vm], torch.from_numpy(gold["gate"])[vm])
+    for i in range(n_flows):
+        errs[f"log_s_{i}"] = rel_err(log_s_list[i].detach().cpu()[vm], torch.from_numpy(gold[f"log_s_{i}"])[vm])
+        errs[f"attn_{i}"] = rel_err(attns[i].detach().cpu()[vm.t()], torch.from_numpy(gold[f"attn_{i}"])[vm.t()])
+        errs[f"attn_logprob_{i}"] = rel_err(lps[i].detach().cpu()[vm.t()], torch.from_numpy(gold[f"attn_logprob_{i}"])[vm.t()])
+    errs["nll"] = abs(float(nll) - float(gold["nll"])) / abs(float(gold["nll"]))
+    errs["gate_loss"] = abs(float(gl) - float(gold["gate_loss"])) / abs(float(gold["gate_loss"]))
+    print("forward errors:", {k: f"{v:.2e}" for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if not v <= 1e-3}
+    assert not bad, bad
+
+    gerrs = {}
+    for name, p in model.named_parameters():
+        g = p.grad.detach().reshape(-1).cpu()
+        gn = float(gold[f"gnorm::{name}"])
+        ref = torch.from_numpy(gold[f"gsamp::{name}"])
+        samp = g[_grad_idx(name, g.numel())]
+        typical = gn / np.sqrt(g.numel())
+        e_norm = abs(float(g.double().norm()) - gn) / (gn + 1e-7)
+        e_samp = (samp - ref).abs().max().item() / (ref.abs().max().item() + typical + 1e-8)
+        gerrs[name] = (e_norm, e_samp)
+    worst = sorted(gerrs.items(), key=lambda kv: -max(kv[1]))[:6]
+    print("worst grads:", [(k, f"{a:.2e}", f"{b:.2e}") for k, (a, b) in worst])
+    bad = {k: v for k, v in gerrs.items() if not (v[0] <= 1e-2 and v[1] <= 3e-2)}
+    assert not bad, bad
+
+
+def test_zero_init_identity_flow():
+    """Known-answer test from the reference's own init (flowtron.py:652-653): conv.weight = conv.bias = 0
+    => z == mel and log_s == 0 exactly."""
+    from flowtron_b200.flowtron import Flowtron
+    cfg = dict(synth.DEFAULT_MODEL_CONFIG, n_flows=2)
+    torch.manual_seed(0)
+    model = Flowtron(**cfg).cuda().eval()
+    batch = synth.synth_batch(3, 40, 12, cfg, 11, out_lens=[40, 7, 22])
+    cu = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    with torch.no_grad():
+        out = model(cu["mel"], cu["speaker_ids"], cu["text"], cu["in_lens"], cu["out_lens"])
+    z = out[0].permute(1, 2, 0)
+    assert torch.equal(z, cu["mel"])
+    assert all(float(ls.abs().max()) == 0.0 for ls in out[1])
+
+
+def test_pad_independence():
+    """Valid outputs must not depend on pad contents."""
+    cfg = dict(synth.DEFAULT_MODEL_CONFIG, n_flows=2)
+    model = build_model(cfg, 77)
+    batch = synth.synth_batch(3, 48, 16, cfg, 5, out_lens=[48, 20, 31])
+    cu = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    mel2 = cu["mel"].clone()
+    T = 48
+    tm = (torch.arange(T, device="cuda")[None, :] >= cu["out_lens"][:, None])
+    mel2 = torch.where(tm[:, None, :], torch.full_like(mel2, 3.7), mel2)
+    with torch.no_grad():
+        a = model(cu["mel"], cu["speaker_ids"], cu["text"], cu["in_lens"], cu["out_lens"])
+        b = model(mel2, cu["speaker_ids"], cu["text"], cu["in_lens"], cu["out_lens"])
+    vm = ~tm.t()
+    assert torch.equal(a[0][vm], b[0][vm])
+    for x, y in zip(a[1], b[1]):
+        assert torch.equal(x[vm], y[vm])
