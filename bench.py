@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""Headline benchmark: training mel-frames/sec of the 2-flow Flowtron step (BASELINE.json configs[1]:
+LJS single-speaker 2-flow, n_mel=80, per-GPU batch 32, T<=1000) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+A step = H2D of one synthetic batch (e2e leg only) -> Flowtron.forward -> FlowtronLoss -> backward ->
+bucketed NCCL gradient all-reduce (N>1) -> grad-norm clip -> RAdam step (train.py:281-331).
+`value` = valid mel frames (sum of out_lens over all ranks) per second with inputs resident in HBM;
+`e2e` = the same through the public module API with pinned-host inputs copied every step and the loss read back.
+Precision: fp16 tensor-core operands in forward, bf16 in backward, fp32 accumulation/state.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_FRAME_FWD = lambda L: 53_677_312 + 1_280 * L        # SURVEY.md §8d, per flow, tensor ops only
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--frames", type=int, default=1000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_ev = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_ev.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in r.stdout.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop_ev.wait(0.2)
+
+    def stop(self):
+        self._stop_ev.set()
+        self.join(timeout=3)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no_samples"]}
+        sm = sorted(int(float(s[0])) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
+                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def make_batch(cfg, B, T, seed):
+    from flowtron_b200 import synth
+    out_lens, in_lens = synth.ljs_like_lengths(B, T, seed)
+    L = int(in_lens.max())
+    batch = synth.synth_batch(B, T, L, cfg, seed, out_lens=out_lens.tolist(), in_lens=in_lens.tolist(), with_prior=True,
+                              logmel_stats=True)
+    return batch, L
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p.get("bf16_tflops", 1590.0), p.get("bf16_tflops_sustained", 1400.0), p.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+def cpu_baseline(cfg, threads, seconds=20.0):
+    """The reference algorithm (oracle port, ATen fused CPU LSTM like the reference's nn.LSTM) on the host cores:
+    forward + loss + backward on a bounded sample of the workload."""
+    from oracle import flowtron_oracle as O
+    from flowtron_b200 import synth
+    torch.set_num_threads(threads)
+    B, T, L = 2, 128, 32
+    p = {k: v.requires_grad_(True) for k, v in synth.synth_params(cfg, 1234).items()}
+    batch = synth.synth_batch(B, T, L, cfg, 1234, with_prior=True, logmel_stats=True)
+    frames, steps, t_total = int(batch["out_lens"].sum()), 0, 0.0
+
+    def step():
+        out = O.flowtron_forward(p, batch["mel"], batch["speaker_ids"], batch["text"], batch["in_lens"], batch["out_lens"],
+                                 batch["attn_prior"], fast=True)
+        nll, gl = O.flowtron_loss(out, batch["gate_target"], batch["in_lens"], batch["out_lens"])
+        for t in p.values():
+            t.grad = None
+        (nll + gl).sum().backward()
+    step()                                                   # warm-up
+    while steps < 3 or (t_total < seconds and steps < 50):
+        t0 = time.perf_counter()
+        step()
+        t_total += time.perf_counter() - t0
+        steps += 1
+    return {"value": frames * steps / t_total, "unit": "valid mel-frames/s", "cores": threads, "kind": "port",
+            "sample": f"oracle port of the reference, 2 flows, B={B}, T={T}, L={L}, fwd+loss+bwd, {steps} steps, fp32"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from flowtron_b200 import synth
+    cfg = dict(synth.DEFAULT_MODEL_CONFIG)
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    cb = cpu_baseline(cfg, threads, seconds=max(5.0, 4.0 * args.steps))
+    out = {"impl": "reference", "metric": "training mel-frames/sec", "value": cb["value"], "unit": "valid mel-frames/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "ms_per_step": None,
+           "config": {"workload": "2-flow Flowtron train step (fwd+loss+bwd) on host CPU, bounded sample", "sample": cb["sample"]},
+           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "valid mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": time.perf_counter() - t0}
+    print(json.dumps(out))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    from flowtron_b200 import _lib, synth
+    from flowtron_b200.flowtron import Flowtron, FlowtronLoss
+    from flowtron_b200 import distributed as ftd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        ftd.init_distributed(rank, world, "nccl")
+
+    cfg = dict(synth.DEFAULT_MODEL_CONFIG)                    # config.json model_config: 2 flows, LJS single speaker
+    B, T = args.batch, args.frames
+    model = Flowtron(**cfg)
+    model.load_state_dict(synth.synth_params(cfg, 1234), strict=True)
+    model = model.to(dev).train()
+    crit = FlowtronLoss(sigma=1.0, gate_loss=True, use_ctc_loss=False)
+    if world > 1:
+        ftd.apply_gradient_allreduce(model)
+    opt = torch.optim.RAdam(model.parameters(), lr=1e-3, weight_decay=1e-6)
+
+    batch, L = make_batch(cfg, B, T, 1234 + rank)            # every rank gets its own utterances (weak scaling)
+    keys = ["mel", "speaker_ids", "text", "in_lens", "out_lens", "gate_target", "attn_prior"]
+    host = {k: batch[k].pin_memory() for k in keys}
+    resident = {k: host[k].to(dev) for k in keys}
+    frames_rank = int(batch["out_lens"].sum())
+    frames_t = torch.tensor([frames_rank], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(frames_t)
+    frames_all = float(frames_t.item())
+    h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in keys)
+
+    def zero_grads():
+        if world > 1:
+            model.zero_grad_buckets()
+        else:
+            opt.zero_grad(set_to_none=True)
+
+    def step(d):
+        zero_grads()
+        out = model(d["mel"], d["speaker_ids"], d["text"], d["in_lens"], d["out_lens"], d["attn_prior"])
+        nll, gl, _ = crit(out, d["gate_target"], d["in_lens"], d["out_lens"])
+        loss = (nll + gl).sum()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        return loss
+
+    def step_e2e():
+        d = {k: host[k].to(dev, non_blocking=True) for k in keys}
+        return float(step(d).item())                          # D2H read of the step's result
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms.item())
+
+    for _ in range(max(3, args.warmup)):
+        step(resident)
+    torch.cuda.synchronize()
+    assert _lib.device_status() == 0, "device watchdog tripped"
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    _lib.reset_launch_count()
+    _lib.timing(True)
+    ms = timed(lambda: step(resident), args.steps)
+    launches = _lib.launch_count()
+    trep = _lib.timing_report()
+    _lib.timing(False)
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop()
+
+    if rank != 0:
+        return
+    value = frames_all * args.steps / (ms / 1e3)
+    e2e = frames_all * args.steps / (ms_e2e / 1e3)
+    # roofline of the dominant kernel family (by device time inside the timed region)
+    burst, sustained, hbm, src = peaks()
+    by_name = {}
+    for name, m, n, k, cnt, tms in trep:
+        a = by_name.setdefault(name, {"count": 0, "ms": 0.0, "flop": 0.0})
+        a["count"] += cnt
+        a["ms"] += tms
+        if name.startswith("gemm"):
+            a["flop"] += 2.0 * m * n * k * cnt
+        elif name.startswith("lstm"):
+            a["flop"] += 2.0 * n * 1024 * 4096 * max(m - 1, 0) * cnt       # (T-1) recurrent [B,1024]x[1024,4096] products
+        elif name.startswith("attn"):
+            a["flop"] += (2.0 if name == "attn_fwd" else 6.0) * n * m * k * 640 * cnt
+    top = max(by_name.items(), key=lambda kv: kv[1]["ms"]) if by_name else (None, None)
+    roof = None
+    if top[0]:
+        t = top[1]
+        ach = t["flop"] / (t["ms"] / 1e3) / 1e12
+        roof = {"kernel": top[0], "bound": "tensor", "achieved": ach, "peak": sustained, "unit": "TFLOP/s", "frac": ach / sustained,
+                "traffic": None, "peak_source": f"{src} bf16 sustained (kernel timed inside a long step)",
+                "launches": t["count"], "avg_ms": t["ms"] / t["count"],
+                "share_of_step": t["ms"] / ms, "note": "latency-bound T-step dependency chain (DESIGN.md): algorithmic FLOPs "
+                "= 2*B*1024*4096*(T-1) per launch"}
+    kernel_table = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["count"] / args.steps,
+                        "tflops": (v["flop"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 else None} for k, v in by_name.items()}
+    flop_step = 3.0 * 2 * FLOP_PER_FRAME_FWD(L) * B * T * world       # fwd+bwd, 2 flows, padded frames
+    out = {
+        "metric": "training mel-frames/sec", "value": value, "unit": "valid mel-frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16 fwd / bf16 bwd operands, f32 accumulate+state", "data": "synthetic",
+        "config": {"workload": "configs[1]: LJS single-speaker 2-flow Flowtron train step, n_mel=80, per-GPU batch 32, T<=1000",
+                   "per_gpu_batch": B, "global_batch": B * world, "max_frames": T, "max_text": L, "attn_prior": True,
+                   "optimizer": "RAdam lr=1e-3 wd=1e-6 + clip_grad_norm 1.0", "parallelism": f"dp{world}",
+                   "padded_frames_per_s": B * T * world * args.steps / (ms / 1e3),
+                   "l2": "working set per step (>3 GB of activations) exceeds the 126 MB L2; no explicit flush"},
+        "e2e": {"value": e2e, "unit": "valid mel-frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernel_table,
+        "model_tflops": flop_step * args.steps / (ms / 1e3) / 1e12,
+        "model_tensor_frac": flop_step * args.steps / (ms / 1e3) / 1e12 / (sustained * world),
+    }
+    if not args.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_baseline(cfg, os.cpu_count() or 1, seconds=15.0)
+    elif not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(cfg, os.cpu_count() or 1, seconds=8.0)
+    print(json.dumps(out))
+    if world > 1:
+        pass
+
+
+if __name__ == "__main__":
+    main()
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass

@@ -113,6 +113,23 @@ def reset_launch_count():
     lib().ft_reset_launch_count()
 
 
+def timing(enable: bool):
+    lib().ft_timing_reset()
+    lib().ft_timing_enable(1 if enable else 0)
+
+
+def timing_report():
+    """[(name, m, n, k, count, total_ms)] aggregated per kernel and shape; synchronises the device."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib().ft_timing_report.argtypes = [c_char_p, c_int]
+    n = lib().ft_timing_report(buf, len(buf))
+    out = []
+    for line in buf.raw[:n].decode().splitlines():
+        name, m, nn, k, cnt, ms = line.split()
+        out.append((name, int(m), int(nn), int(k), int(cnt), float(ms)))
+    return out
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:

@@ -4,6 +4,9 @@
 #include <string>
 #include <atomic>
 #include <cstdio>
+#include <vector>
+#include <map>
+#include <tuple>
 
 #include "ft_internal.h"
 #include "../../include/flowtron_b200.h"
@@ -37,6 +40,29 @@ int* ft_status_word() {
 }
 void ft_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---- optional per-kernel device timing (CUDA events on the launching stream; bench.py's roofline leg)
+struct TimeRec { const char* name; long long m, n, k; cudaEvent_t a, b; };
+static bool g_timing = false;
+static std::vector<TimeRec> g_recs;
+static std::vector<cudaEvent_t> g_pool;
+static cudaEvent_t get_event() {
+    if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+TimeScope::TimeScope(const char* name, long long m, long long n, long long k, cudaStream_t st) : st_(st), idx_(-1) {
+    if (!g_timing) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    TimeRec r{name, m, n, k, get_event(), get_event()};
+    cudaEventRecord(r.a, st);
+    g_recs.push_back(r);
+    idx_ = static_cast<int>(g_recs.size()) - 1;
+}
+TimeScope::~TimeScope() {
+    if (idx_ < 0) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaEventRecord(g_recs[idx_].b, st_);
+}
+
 }  // namespace ft
 
 extern "C" {
@@ -51,6 +77,33 @@ int ft_device_status(void) {
     int v = 0;
     if (cudaMemcpy(&v, w, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
     return v;
+}
+
+void ft_timing_enable(int on) { ft::g_timing = on != 0; }
+void ft_timing_reset(void) {
+    std::lock_guard<std::mutex> lk(ft::g_mu);
+    for (auto& r : ft::g_recs) { ft::g_pool.push_back(r.a); ft::g_pool.push_back(r.b); }
+    ft::g_recs.clear();
+}
+/* Synchronises the device; writes one line per (kernel, shape): "name m n k count total_ms\n". Returns bytes written. */
+int ft_timing_report(char* buf, int cap) {
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(ft::g_mu);
+    std::map<std::tuple<std::string, long long, long long, long long>, std::pair<int, double>> agg;
+    for (auto& r : ft::g_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+        auto& e = agg[std::make_tuple(std::string(r.name), r.m, r.n, r.k)];
+        e.first += 1; e.second += ms;
+    }
+    int off = 0;
+    for (auto& kv : agg) {
+        int w = snprintf(buf + off, cap - off, "%s %lld %lld %lld %d %.6f\n", std::get<0>(kv.first).c_str(),
+                         std::get<1>(kv.first), std::get<2>(kv.first), std::get<3>(kv.first), kv.second.first, kv.second.second);
+        if (w < 0 || off + w >= cap) break;
+        off += w;
+    }
+    return off;
 }
 
 long long ft_launch_count(void) { return ft::g_launches.load(); }

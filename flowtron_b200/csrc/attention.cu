@@ -55,7 +55,7 @@ attn_fwd_kernel(AttnFwdParams p) {
     extern __shared__ float smf[];
     const int Lpad = ((p.L + AT_LB - 1) / AT_LB) * AT_LB;
     float* sQ = smf;                                  // [AT_AC][SQ_LD]
-    float* sK = sQ + AT_AC * SQ_LD;                   // [AT_AC][SK_LD]   (also V chunk [AT_LB][AT_AC+4])
+    float* sK = sQ + AT_AC * SQ_LD;                   // [AT_AC][SK_LD]   (also the V chunk [64][AT_AC+4])
     float* sE = sK + AT_AC * SK_LD;                   // [AT_TT][Lpad+4]
     float* sv = sE + AT_TT * (Lpad + 4);              // [A]
     __shared__ float s_sumv;
@@ -203,7 +203,7 @@ attn_fwd_kernel(AttnFwdParams p) {
     __syncthreads();
 
     // ---------------------------------------------------------------- context: ctx[t, a] = sum_l attn[t,l] V[l,a]
-    float* sV = sK;                                    // [AT_LB][AT_AC + 4]
+    float* sV = sK;                                    // [64 keys][AT_AC + 4]  (64*68 floats fit inside sK's 64*132)
     constexpr int SV_LD = AT_AC + 4;
     for (int ac = 0; ac < p.A; ac += AT_AC) {
         float c4[4][4];
@@ -211,24 +211,24 @@ attn_fwd_kernel(AttnFwdParams p) {
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) c4[i][j] = 0.f;
-        for (int lb = 0; lb < nlb; ++lb) {
+        for (int l0 = 0; l0 < p.L; l0 += 64) {
             __syncthreads();
             {
                 const int aa = tid & 63;
-                for (int ll = tid >> 6; ll < AT_LB; ll += AT_THREADS / 64) {
-                    const int l = lb * AT_LB + ll;
+                for (int ll = tid >> 6; ll < 64; ll += AT_THREADS / 64) {
+                    const int l = l0 + ll;
                     float x = 0.f;
                     if (l < p.L && ac + aa < p.A) x = p.V[(static_cast<long long>(l) * p.B + b) * p.ldv + ac + aa];
                     sV[ll * SV_LD + aa] = x;
                 }
             }
             __syncthreads();
-            const int nl = min(AT_LB, p.L - lb * AT_LB);
+            const int nl = min(64, p.L - l0);
             for (int l = 0; l < nl; ++l) {
                 const float4 v4 = *reinterpret_cast<const float4*>(&sV[l * SV_LD + 4 * tx]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float w = sE[(4 * ty + i) * SE_LD + lb * AT_LB + l];
+                    const float w = sE[(4 * ty + i) * SE_LD + l0 + l];
                     c4[i][0] = fmaf(w, v4.x, c4[i][0]);
                     c4[i][1] = fmaf(w, v4.y, c4[i][1]);
                     c4[i][2] = fmaf(w, v4.z, c4[i][2]);
@@ -559,6 +559,7 @@ int launch_attn_fwd(const AttnFwdArgs& a, cudaStream_t st) {
     const size_t smem = attn_fwd_smem(a.L, a.A);
     cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     dim3 grid((a.T + AT_TT - 1) / AT_TT, a.B);
+    TimeScope ts("attn_fwd", a.T, a.B, a.L, st);
     attn_fwd_kernel<<<grid, AT_THREADS, smem, st>>>(p);
     ft_count_launch(1);
     return ft_check_launch("attn_fwd_kernel");
@@ -576,6 +577,7 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t st) {
     const size_t smem = attn_bwd_smem(a.L, a.A);
     cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     dim3 grid((a.T + AT_TT - 1) / AT_TT, a.B);
+    TimeScope ts("attn_bwd", a.T, a.B, a.L, st);
     attn_bwd_kernel<<<grid, AT_THREADS, smem, st>>>(p);
     ft_count_launch(1);
     return ft_check_launch("attn_bwd_kernel");

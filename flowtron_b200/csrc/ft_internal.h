@@ -16,6 +16,13 @@ int ft_check_launch(const char* what);        // cudaGetLastError -> ft_set_erro
 int* ft_status_word();                        // device int written by kernel watchdogs (0 = ok)
 void ft_count_launch(int n);
 
+// RAII device-time bracket around a launch (no-op unless ft_timing_enable(1))
+struct TimeScope {
+    TimeScope(const char* name, long long m, long long n, long long k, cudaStream_t st);
+    ~TimeScope();
+    cudaStream_t st_; int idx_;
+};
+
 enum { FMT_F16 = 0, FMT_BF16 = 1, FMT_TF32 = 2 };
 
 struct GemmArgs {

@@ -265,6 +265,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
         cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
         attr_set = true;
     }
+    TimeScope ts(g.a_mn ? "gemm_wgrad" : (g.b_mn ? "gemm_dgrad" : "gemm_fwd"), g.M, g.N, g.K, st);
     if (tf32) gemm_kernel<true><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmB, p);
     else      gemm_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmB, p);
     ft_count_launch(1);

@@ -417,6 +417,7 @@ int launch_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const i
     if (cudaMemsetAsync(flags, 0, sizeof(int) * T * FWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_fwd: memset failed");
     const int smem = nslot * slot + fixed;
     cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    TimeScope ts("lstm_fwd", T, B, 0, st);
     void* args[] = {&tmW, &tmH, &p};
     cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_fwd_kernel), dim3(FWD_CTAS),
                                                 dim3(LSTM_THREADS), args, smem, st);
@@ -445,6 +446,7 @@ int launch_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void
     if (cudaMemsetAsync(flags, 0, sizeof(int) * T * BWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_bwd: memset failed");
     const int smem = nslot * slot + fixed;
     cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    TimeScope ts("lstm_bwd", T, B, 0, st);
     void* args[] = {&tmWT, &tmG, &p};
     cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_bwd_kernel), dim3(BWD_CTAS),
                                                 dim3(LSTM_THREADS), args, smem, st);

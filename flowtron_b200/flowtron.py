@@ -103,13 +103,14 @@ class Encoder(nn.Module):
                 norm_fn(encoder_embedding_dim, affine=True)))
         self.convolutions = nn.ModuleList(convolutions)
         self.lstm = nn.LSTM(encoder_embedding_dim, int(encoder_embedding_dim / 2), 1, batch_first=True, bidirectional=True)
+        self.p_dropout = 0.5        # flowtron.py:502 hard-codes 0.5; exposed so tests can run deterministic train-mode steps
 
     def forward(self, x, in_lens):
         mask = get_mask_from_lengths(in_lens).unsqueeze(1) if x.size(0) > 1 else None
         for conv, norm in self.convolutions:
             if mask is not None:
                 x = x.masked_fill(~mask, 0.)
-            x = F.dropout(F.relu(norm(conv(x), mask=mask)), 0.5, self.training)
+            x = F.dropout(F.relu(norm(conv(x), mask=mask)), self.p_dropout, self.training)
         x = x.transpose(1, 2)
         x = nn.utils.rnn.pack_padded_sequence(x, in_lens.cpu(), batch_first=True)
         self.lstm.flatten_parameters()
@@ -119,7 +120,7 @@ class Encoder(nn.Module):
 
     def infer(self, x):
         for conv in self.convolutions:
-            x = F.dropout(F.relu(conv(x)), 0.5, self.training)
+            x = F.dropout(F.relu(conv(x)), self.p_dropout, self.training)
         x = x.transpose(1, 2)
         self.lstm.flatten_parameters()
         outputs, _ = self.lstm(x)

@@ -25,6 +25,10 @@ int ft_version(void);
 const char* ft_last_error(void);
 /* 0 = ok; non-zero = code written by a device-side watchdog (a bounded spin-wait expired). Synchronises. */
 int ft_device_status(void);
+/* Optional per-kernel device timing with CUDA events on the launching stream (bench.py roofline leg). */
+void ft_timing_enable(int on);
+void ft_timing_reset(void);
+int ft_timing_report(char* buf, int cap);   /* synchronises; "name m n k count total_ms" per line */
 /* number of kernels this library has launched (bench.py's gpu_launches) */
 long long ft_launch_count(void);
 void ft_reset_launch_count(void);

@@ -368,13 +368,12 @@ def flowtron_loss(model_output, gate_target: Tensor, in_lens: Tensor, out_lens: 
 
 # --------------------------------------------------------------------------- attention prior
 def beta_binomial_prior(phoneme_count: int, mel_count: int, scaling: float = 1.0) -> np.ndarray:
-    """data.py:31-41 via log-gamma (closed-form BetaBinomial pmf), float64 [mel_count, phoneme_count]."""
-    from scipy.special import gammaln
-    P, Mx = phoneme_count, mel_count
-    k = np.arange(P, dtype=np.float64)[None, :]
-    i = np.arange(1, Mx + 1, dtype=np.float64)[:, None]
-    a, b, n = scaling * i, scaling * (Mx + 1 - i), float(P - 1)
-    logc = gammaln(n + 1) - gammaln(k + 1) - gammaln(n - k + 1)
-    logb = (gammaln(k + a) + gammaln(n - k + b) - gammaln(n + a + b)
-            - (gammaln(a) + gammaln(b) - gammaln(a + b)))
-    return np.exp(logc + logb)
+    """data.py:31-41 restated literally with scipy.stats.betabinom (the closed-form version used by the
+    data helpers is checked against this in tests/test_oracle_golden.py)."""
+    from scipy.stats import betabinom
+    x = np.arange(0, phoneme_count)
+    rows = []
+    for i in range(1, mel_count + 1):
+        a, b = scaling * i, scaling * (mel_count + 1 - i)
+        rows.append(betabinom(phoneme_count - 1, a, b).pmf(x))
+    return np.array(rows)

@@ -49,6 +49,8 @@ def test_forward_loss_backward_match_reference_goldens(tag):
     batch = synth.synth_batch(B, T, L, cfg, int(gold["seed"]), out_lens=OUT_LENS[tag], with_prior=bool(gold["with_prior"]))
     dev = "cuda"
     cu = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    model.train()                      # cuDNN's encoder BiLSTM needs train mode for backward ...
+    model.encoder.p_dropout = 0.0      # ... with the (random) encoder dropout disabled, like the golden generator
     for p in model.parameters():
         p.requires_grad_(True)
     out = model(cu["mel"], cu["speaker_ids"], cu["text"], cu["in_lens"], cu["out_lens"], cu["attn_prior"])
