@@ -81,6 +81,11 @@ def _declare(L):
     L.ft_ar_step_bwd.argtypes = [POINTER(FtArStepDesc), POINTER(FtArStepWeights)] + [c_void_p] * 11 + \
         [POINTER(FtArStepWeights), c_void_p, c_void_p, c_void_p]
     L.ft_ar_step_bwd.restype = c_int
+    L.ft_ar_step_infer_scratch_bytes.argtypes = [POINTER(FtArStepDesc)]
+    L.ft_ar_step_infer_scratch_bytes.restype = c_size_t
+    L.ft_ar_step_infer.argtypes = [POINTER(FtArStepDesc), POINTER(FtArStepWeights), c_void_p, c_void_p, c_void_p, c_float,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.ft_ar_step_infer.restype = c_int
     L.ft_nll_reduce.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
     L.ft_nll_reduce.restype = c_int
     L.ft_nll_grad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
@@ -242,3 +247,10 @@ def nll_grad(z, gate, gate_target, out_lens, sigma, sums, g_nll, g_gate, dz, dlo
     T, B, M = z.shape
     check(lib().ft_nll_grad(ptr(z), ptr(gate), ptr(gate_target), ptr(out_lens), T, B, M, float(sigma), ptr(sums),
                             ptr(g_nll), ptr(g_gate), ptr(dz), ptr(dlog_s), ptr(dgate), stream_ptr()), "ft_nll_grad")
+
+
+def ar_step_infer(desc, weights, residual, text, prior, gate_threshold, out, attn_out, n_frames):
+    nbytes = int(lib().ft_ar_step_infer_scratch_bytes(byref(desc)))
+    scratch = scratch_buffer(nbytes, residual.device)
+    check(lib().ft_ar_step_infer(byref(desc), byref(weights), ptr(residual), ptr(text), ptr(prior), float(gate_threshold),
+                                 ptr(out), ptr(attn_out), ptr(n_frames), ptr(scratch), stream_ptr()), "ft_ar_step_infer")

@@ -1,0 +1,46 @@
+"""Host side of AR_Step.infer / AR_Back_Step.infer (flowtron.py:775-828, 629-642) over ft_ar_step_infer."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import FlowtronB200Error
+
+
+def ar_step_infer(step, residual, text, attns, attn_prior=None, reversed_flag=False):
+    """residual [T,B,M], text [L,B,E] -> (total_output [T',B,M], [attention_weight [B,1,L]] * T').
+
+    B == 1: T' is where the gate fired (the reference's `break`); B > 1: per-sample stop (rows emit zeros after
+    their own gate fires), T' = the longest row.  AR_Back_Step flips time on the way in and out (:629-642)."""
+    if attns is not None:
+        raise NotImplementedError("forced alignments (attns=...) are outside the B200 hot-path scope")
+    if not residual.is_cuda:
+        raise FlowtronB200Error("AR_Step.infer needs CUDA tensors: the sm_100a kernel is the only implementation")
+    T, B, M = residual.shape
+    L, _, E = text.shape
+    dev = residual.device
+    res = residual.detach().float()
+    prior = None if attn_prior is None else attn_prior.detach().float()
+    if reversed_flag:
+        res = torch.flip(res, (0,))
+        if prior is not None:
+            prior = torch.flip(prior, (1,))
+    res = res.contiguous()
+    prior = None if prior is None else prior.contiguous()
+    has_gate = hasattr(step, 'gate_layer')
+    desc = _lib.FtArStepDesc(T, B, L, M, step.lstm.hidden_size, step.attention_layer.query.linear_layer.out_features, E, 0,
+                             int(has_gate), int(prior is not None), float(step.attention_layer.temperature))
+    plist = [None if p is None else p.detach().contiguous() for p in step._param_list()]
+    weights = _lib.make_weights(plist)
+    out = torch.empty(T, B, M, device=dev)
+    attn_out = torch.empty(T, B, L, device=dev)
+    n_frames = torch.empty(B, dtype=torch.int32, device=dev)
+    thr = float(getattr(step, 'gate_threshold', 0.5))
+    _lib.ar_step_infer(desc, weights, res, text.detach().float().contiguous(), prior, thr, out, attn_out, n_frames)
+    n = int(n_frames.max().item())                      # one host sync per flow (the reference syncs every frame)
+    if has_gate and n < T:
+        print("Hitting gate limit")
+    out, attn_out = out[:n], attn_out[:n]
+    if reversed_flag:
+        out = torch.flip(out, (0,))
+    return out, [a.unsqueeze(1) for a in attn_out]

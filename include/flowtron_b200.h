@@ -116,6 +116,18 @@ int ft_nll_grad(const float* z, const float* gate, const float* gate_target, con
                 float sigma, const float* sums, const float* g_nll, const float* g_gate, float* dz, float* dlog_s,
                 float* dgate, void* stream);
 
+/* AR_Step.infer (flowtron.py:775-828): sequential inverse of one flow for all T frames in ONE persistent launch.
+ *   residual [T,B,M] f32 in flow-time order (the caller flips for AR_Back_Step, :629-642), text [L,B,E] f32,
+ *   attn_prior [B,T,L] or NULL (row i is used at frame i).  Uses d->T/B/L/n_*, has_gate, has_prior, temperature.
+ *   out [T,B,M]: generated frames (zeros after a sample's gate fired; the frame that trips the gate is emitted),
+ *   attn_out [T,B,L]: per-frame attention weights, n_frames [B] int32: frames emitted per sample.
+ *   With B == 1 this is exactly the reference's loop-with-break; B > 1 with a gate is the per-sample-stop
+ *   extension (the reference raises there). */
+size_t ft_ar_step_infer_scratch_bytes(const FtArStepDesc* d);
+int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const float* residual, const float* text,
+                     const float* attn_prior, float gate_threshold, float* out, float* attn_out, int* n_frames,
+                     void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

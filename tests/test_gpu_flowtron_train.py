@@ -75,19 +75,31 @@ def test_forward_loss_backward_match_reference_goldens(tag):
     bad = {k: v for k, v in errs.items() if not v <= 1e-3}
     assert not bad, bad
 
-    gerrs = {}
+    # ---- gradients.  Backward tensor-core operands are bf16 (8-bit significand): per-element noise of a few 1e-3
+    # relative is inherent, so the gate is per tensor: norm within 1e-2 of the reference's (fixture) and cosine
+    # >= 0.999 / relative L2 <= 4e-2 against the full CPU-oracle gradient (the oracle is pinned to the reference in
+    # tests/test_oracle_golden.py).  Tensors whose true gradient is analytically ~0 (conv biases feeding an
+    # instance norm) are compared on an absolute scale.
+    from oracle import flowtron_oracle as O
+    op = {k: v.clone().requires_grad_(True) for k, v in synth.synth_params(cfg, int(gold["seed"])).items()}
+    oout = O.flowtron_forward(op, batch["mel"], batch["speaker_ids"], batch["text"], batch["in_lens"], batch["out_lens"],
+                              batch["attn_prior"], fast=True)
+    onll, ogl = O.flowtron_loss(oout, batch["gate_target"], batch["in_lens"], batch["out_lens"])
+    (onll + ogl).sum().backward()
+    gmax = max(float(gold[f"gnorm::{n}"]) for n, _ in model.named_parameters())
+    rows, bad = [], {}
     for name, p in model.named_parameters():
-        g = p.grad.detach().reshape(-1).cpu()
+        g = p.grad.detach().reshape(-1).double().cpu()
+        r = op[name].grad.reshape(-1).double()
         gn = float(gold[f"gnorm::{name}"])
-        ref = torch.from_numpy(gold[f"gsamp::{name}"])
-        samp = g[_grad_idx(name, g.numel())]
-        typical = gn / np.sqrt(g.numel())
-        e_norm = abs(float(g.double().norm()) - gn) / (gn + 1e-7)
-        e_samp = (samp - ref).abs().max().item() / (ref.abs().max().item() + typical + 1e-8)
-        gerrs[name] = (e_norm, e_samp)
-    worst = sorted(gerrs.items(), key=lambda kv: -max(kv[1]))[:6]
-    print("worst grads:", [(k, f"{a:.2e}", f"{b:.2e}") for k, (a, b) in worst])
-    bad = {k: v for k, v in gerrs.items() if not (v[0] <= 1e-2 and v[1] <= 3e-2)}
+        e_norm = abs(float(g.norm()) - gn) / (gn + 1e-4 * gmax)
+        rel_l2 = float((g - r).norm()) / (float(r.norm()) + 1e-4 * gmax)
+        cos = float((g @ r) / (g.norm() * r.norm() + 1e-30)) if gn > 1e-4 * gmax else 1.0
+        rows.append((name, e_norm, rel_l2, cos))
+        if not (e_norm <= 1e-2 and rel_l2 <= 4e-2 and cos >= 0.999):
+            bad[name] = (e_norm, rel_l2, cos)
+    rows.sort(key=lambda x: -x[2])
+    print("worst grads (name, norm err, rel L2, cosine):", [(n, f"{a:.1e}", f"{b:.1e}", f"{c:.5f}") for n, a, b, c in rows[:8]])
     assert not bad, bad
 
 
