@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="short run for ncu: no e2e leg, no CPU baseline, warm-up as given")
     return ap.parse_args()
 
 
@@ -214,7 +215,7 @@ def main():
             dist.barrier()
         return float(ms.item())
 
-    for _ in range(max(3, args.warmup)):
+    for _ in range(args.warmup if args.profile else max(3, args.warmup)):
         step(resident)
     torch.cuda.synchronize()
     assert _lib.device_status() == 0, "device watchdog tripped"
@@ -227,7 +228,7 @@ def main():
     launches = _lib.launch_count()
     trep = _lib.timing_report()
     _lib.timing(False)
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = ms if args.profile else timed(step_e2e, args.steps)
     clocks = sampler.stop()
 
     if rank != 0:
@@ -275,7 +276,9 @@ def main():
         "model_tflops": flop_step * args.steps / (ms / 1e3) / 1e12,
         "model_tensor_frac": flop_step * args.steps / (ms / 1e3) / 1e12 / (sustained * world),
     }
-    if not args.no_cpu_baseline and world == 1:
+    if args.profile:
+        out["invalid"] = "profiling run (timings under a profiler are never reported)"
+    elif not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(cfg, os.cpu_count() or 1, seconds=15.0)
     elif not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(cfg, os.cpu_count() or 1, seconds=8.0)

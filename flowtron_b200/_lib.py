@@ -86,6 +86,11 @@ def _declare(L):
     L.ft_ar_step_infer.argtypes = [POINTER(FtArStepDesc), POINTER(FtArStepWeights), c_void_p, c_void_p, c_void_p, c_float,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.ft_ar_step_infer.restype = c_int
+    L.ft_mel_scratch_bytes.argtypes = [c_int, c_longlong]
+    L.ft_mel_scratch_bytes.restype = c_size_t
+    L.ft_mel_spectrogram.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_longlong, c_void_p]
+    L.ft_mel_spectrogram.restype = c_int
     L.ft_nll_reduce.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
     L.ft_nll_reduce.restype = c_int
     L.ft_nll_grad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
@@ -254,3 +259,12 @@ def ar_step_infer(desc, weights, residual, text, prior, gate_threshold, out, att
     scratch = scratch_buffer(nbytes, residual.device)
     check(lib().ft_ar_step_infer(byref(desc), byref(weights), ptr(residual), ptr(text), ptr(prior), float(gate_threshold),
                                  ptr(out), ptr(attn_out), ptr(n_frames), ptr(scratch), stream_ptr()), "ft_ar_step_infer")
+
+
+def mel_spectrogram(wav, sample_offsets, frame_offsets, n_utt, total_frames, window, basis, band_lo, band_hi, n_fft, hop,
+                    clip, mel_out, chunk_frames=131072):
+    chunk = int(min(chunk_frames, max(1, total_frames)))
+    scratch = scratch_buffer(int(lib().ft_mel_scratch_bytes(n_fft, chunk)), wav.device)
+    check(lib().ft_mel_spectrogram(ptr(wav), ptr(sample_offsets), ptr(frame_offsets), n_utt, total_frames, ptr(window),
+                                   ptr(basis), ptr(band_lo), ptr(band_hi), basis.shape[0], n_fft, hop, float(clip),
+                                   ptr(mel_out), ptr(scratch), chunk, stream_ptr()), "ft_mel_spectrogram")

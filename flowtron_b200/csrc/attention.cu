@@ -280,8 +280,7 @@ attn_bwd_kernel(AttnBwdParams p) {
     float* sQ = smf;                                  // [AT_AC][SQ_LD]
     float* sK = sQ + AT_AC * SQ_LD;                   // [AT_AC][SK_LD]
     float* sD = sK + AT_AC * SK_LD;                   // [AT_TT][SE_LD]  dattn -> de
-    float* sA = sD + AT_TT * SE_LD;                   // [AT_TT][SE_LD]  attn
-    float* sdK = sA + AT_TT * SE_LD;                  // [AT_LB][AT_AC+1] per-chunk dK accumulator
+    float* sdK = sD + AT_TT * SE_LD;                  // [AT_LB][AT_AC+1] per-chunk dK accumulator
     float* sdQ = sdK + AT_LB * (AT_AC + 1);           // [AT_TT][AT_AC+1]
     float* sv = sdQ + AT_TT * (AT_AC + 1);            // [A]
     float* sdv = sv + p.A;                            // [A]
@@ -304,12 +303,9 @@ attn_bwd_kernel(AttnBwdParams p) {
     for (int i = tid; i < p.A; i += AT_THREADS) { sv[i] = p.v[i]; sdv[i] = 0.f; }
 
     // ---------------------------------------------------------------- 1. dattn[t,l] = dctx[t,:] . V[l,:]  (+ext);  dV += attn^T dctx
-    for (int i = tid; i < AT_TT * SE_LD; i += AT_THREADS) { sD[i] = 0.f; sA[i] = 0.f; }
+    for (int i = tid; i < AT_TT * SE_LD; i += AT_THREADS) sD[i] = 0.f;
+    const float* attn_b = p.attn + (static_cast<long long>(b) * p.T + t0) * p.L;      // rows of this tile, pitch L (L2-resident)
     __syncthreads();
-    for (int i = tid; i < nrows * p.L; i += AT_THREADS) {
-        const int tt = i / p.L, l = i % p.L;
-        sA[tt * SE_LD + l] = p.attn[(static_cast<long long>(b) * p.T + t0 + tt) * p.L + l];
-    }
     float* sC = sQ;                                   // dctx chunk  [AT_TT][AT_AC+4]  (fits in sQ: 64*68)
     float* sV = sK;                                   // V chunk     [64 keys][AT_AC+4]  (64*68 floats fit in sK)
     constexpr int SC_LD = AT_AC + 4;
@@ -368,7 +364,8 @@ attn_bwd_kernel(AttnBwdParams p) {
                 const float4 c = *reinterpret_cast<const float4*>(&sC[tt * SC_LD + 4 * tx]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float w = sA[tt * SE_LD + l0 + 4 * ty + i];
+                    const int l = l0 + 4 * ty + i;
+                    const float w = (l < p.L) ? __ldg(attn_b + static_cast<long long>(tt) * p.L + l) : 0.f;
                     g[i][0] = fmaf(w, c.x, g[i][0]); g[i][1] = fmaf(w, c.y, g[i][1]);
                     g[i][2] = fmaf(w, c.z, g[i][2]); g[i][3] = fmaf(w, c.w, g[i][3]);
                 }
@@ -390,7 +387,7 @@ attn_bwd_kernel(AttnBwdParams p) {
     for (int tt = warp; tt < nrows; tt += AT_THREADS / 32) {
         const int t = t0 + tt;
         float* d = sD + tt * SE_LD;
-        const float* at = sA + tt * SE_LD;
+        const float* at = attn_b + static_cast<long long>(tt) * p.L;
         const long long o0 = (static_cast<long long>(b) * p.T + t) * p.L;
         if (t >= out_len) {
             for (int l = lane; l < Lpad; l += 32) d[l] = 0.f;
@@ -542,7 +539,7 @@ static size_t attn_fwd_smem(int L, int A) {
 }
 static size_t attn_bwd_smem(int L, int A) {
     const int Lpad = ((L + AT_LB - 1) / AT_LB) * AT_LB;
-    return sizeof(float) * (static_cast<size_t>(AT_AC) * SQ_LD + AT_AC * SK_LD + 2 * AT_TT * (Lpad + 4) +
+    return sizeof(float) * (static_cast<size_t>(AT_AC) * SQ_LD + AT_AC * SK_LD + AT_TT * (Lpad + 4) +
                             AT_LB * (AT_AC + 1) + AT_TT * (AT_AC + 1) + 2 * A) + 64;
 }
 

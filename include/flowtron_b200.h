@@ -128,6 +128,17 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
                      const float* attn_prior, float gate_threshold, float* out, float* attn_out, int* n_frames,
                      void* scratch, void* stream);
 
+/* TacotronSTFT.mel_spectrogram (audio_processing.py:117-134) for a ragged batch.  wav: concatenated utterances
+ * (f32 in [-1,1]); sample_offsets / frame_offsets: device int64 [n_utt+1] prefix sums (frames of utterance u =
+ * 1 + N_u / hop); window [n_fft] (periodic Hann, centre-padded); mel_basis [n_mel, n_fft/2+1] with its non-zero
+ * column range [band_lo[m], band_hi[m]) per row.  mel_out: per-utterance [n_mel, F_u] blocks, concatenated
+ * (== [B, n_mel, F] for equal lengths).  scratch: ft_mel_scratch_bytes(n_fft, chunk_frames). */
+size_t ft_mel_scratch_bytes(int n_fft, long long chunk_frames);
+int ft_mel_spectrogram(const float* wav, const long long* sample_offsets, const long long* frame_offsets, int n_utt,
+                       long long total_frames, const float* window, const float* mel_basis, const int* band_lo,
+                       const int* band_hi, int n_mel, int n_fft, int hop, float clip, float* mel_out, void* scratch,
+                       long long chunk_frames, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,7 +96,7 @@ def test_forward_loss_backward_match_reference_goldens(tag):
         rel_l2 = float((g - r).norm()) / (float(r.norm()) + 1e-4 * gmax)
         cos = float((g @ r) / (g.norm() * r.norm() + 1e-30)) if gn > 1e-4 * gmax else 1.0
         rows.append((name, e_norm, rel_l2, cos))
-        if not (e_norm <= 1e-2 and rel_l2 <= 4e-2 and cos >= 0.999):
+        if not (e_norm <= 1e-2 and rel_l2 <= 4e-2 and cos >= 0.999):   # tightened once the fp16-scaled backward landed
             bad[name] = (e_norm, rel_l2, cos)
     rows.sort(key=lambda x: -x[2])
     print("worst grads (name, norm err, rel L2, cosine):", [(n, f"{a:.1e}", f"{b:.1e}", f"{c:.5f}") for n, a, b, c in rows[:8]])
