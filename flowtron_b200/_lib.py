@@ -182,10 +182,10 @@ def lstm_fwd(xproj, whh16, lens, hseq16, gates16=None, cstate=None, h32=None):
 
 
 def lstm_bwd(dh_ext, whhT16, gates16, cstate, lens, dG16):
-    """dh_ext [T,B,ld view] f32, whhT16 [1024,4096] bf16, dG16 [T,B,4096] bf16 (written)."""
+    """dh_ext [T,B,ld view] f32, whhT16 [1024,4096] f16, dG16 [T,B,4096] f16 (written, saturating)."""
     _need_cuda(dh_ext, whhT16, dG16)
     T, B = dG16.shape[0], dG16.shape[1]
-    assert whhT16.dtype == torch.bfloat16 and dG16.dtype == torch.bfloat16 and dG16.is_contiguous()
+    assert whhT16.dtype == torch.float16 and dG16.dtype == torch.float16 and dG16.is_contiguous()
     flags = torch.empty(T * 64, dtype=torch.int32, device=dG16.device)
     check(lib().ft_lstm_bwd(T, B, ptr(dh_ext), dh_ext.stride(1), ptr(whhT16), ptr(gates16), ptr(cstate), ptr(lens),
                             ptr(dG16), ptr(flags), stream_ptr()), "ft_lstm_bwd")

@@ -4,8 +4,8 @@
 // whose layouts are planned by the same code that uses them (Plan below).
 //
 // Precision plan: forward tensor-core operands are fp16 (11-bit significand, same as tf32; every
-// forward operand is either a weight or a bounded activation), backward operands are bf16 (gradients need
-// fp32's exponent range); accumulation, LSTM cell state, softmax, exp/log and all reductions are fp32.
+// forward operand is either a weight or a bounded activation); backward operands are fp16 too, on gradients
+// multiplied by a per-flow power-of-two loss scale chosen on the device (launch_grad_scale); accumulation, LSTM cell state, softmax, exp/log and all reductions are fp32.
 #include <cstring>
 #include <string>
 #include <vector>
@@ -103,17 +103,14 @@ struct FwdScratch {
 };
 
 struct BwdScratch {
-    W16 w;                      // bf16, natural layouts (w_hh* hold the TRANSPOSED recurrent weights [H, 4H])
-    uint16_t *dG, *cvt, *melin_bf, *text_bf, *do16, *dy2, *dy1, *dQ16, *dK16, *dV16;
-    float *dh, *dd, *dQ, *dK, *dV, *dmel_flow, *dmel_in;
+    W16 w;                      // fp16, natural layouts (w_hh* hold the TRANSPOSED recurrent weights [H, 4H])
+    uint16_t *dG, *do16, *dy2, *dy1, *dQ16, *dK16, *dV16;
+    float *dh, *dd, *dQ, *dK, *dV, *dmel_flow, *dmel_in, *scale;
     int* flags;
     void plan(Plan& p, const FtArStepDesc& d) {
         const Dims n(d);
         w.plan(p, n);
         dG = p.get<uint16_t>("dG", n.R * G);
-        cvt = p.get<uint16_t>("cvt", n.R * n.D);
-        melin_bf = p.get<uint16_t>("melin_bf", n.R * n.M);
-        text_bf = p.get<uint16_t>("text_bf", n.RL * n.E);
         do16 = p.get<uint16_t>("do16", n.R * 2 * n.M);
         dy2 = p.get<uint16_t>("dy2", n.R * H);
         dy1 = p.get<uint16_t>("dy1", n.R * H);
@@ -127,6 +124,7 @@ struct BwdScratch {
         dV = p.get<float>("dV", n.RL * n.A);
         dmel_flow = p.get<float>("dmel_flow", n.R * n.M);
         dmel_in = p.get<float>("dmel_in", n.R * n.M);
+        scale = p.get<float>("scale", 8);
         flags = p.get<int>("flags", static_cast<size_t>(n.T) * 64);
     }
 };
@@ -154,21 +152,24 @@ int gemm_fwd(cudaStream_t st, long long M, int N, int K, const void* A, long lon
 }
 // dgrad: dX[M,K] = dY[M,N] W[N,K]      (A = dY K-major, B = W given MN-major)
 int gemm_dgrad(cudaStream_t st, long long M, int Kout, int Nred, const void* dY, long long lddy, const void* W, long long ldw,
-               int beta, float* C32, long long ldc32, void* C16, long long ldc16, const void* aux16, long long ldaux) {
+               int beta, float* C32, long long ldc32, void* C16, long long ldc16, const void* aux16, long long ldaux,
+               const float* alpha_ptr = nullptr) {
     GemmArgs g;
     g.M = static_cast<int>(M); g.N = Kout; g.K = Nred;
-    g.A = dY; g.lda = lddy; g.a_fmt = FMT_BF16; g.B = W; g.ldb = ldw; g.b_fmt = FMT_BF16; g.b_mn = 1;
-    g.beta = beta; g.C32 = C32; g.ldc32 = ldc32; g.C16 = C16; g.ldc16 = ldc16; g.c16_fmt = FMT_BF16;
+    g.A = dY; g.lda = lddy; g.a_fmt = FMT_F16; g.B = W; g.ldb = ldw; g.b_fmt = FMT_F16; g.b_mn = 1;
+    g.alpha_ptr = alpha_ptr;
+    g.beta = beta; g.C32 = C32; g.ldc32 = ldc32; g.C16 = C16; g.ldc16 = ldc16; g.c16_fmt = FMT_F16;
     if (aux16) { g.act = 2; g.aux16 = aux16; g.ldaux = ldaux; }
     return launch_gemm(g, st);
 }
 // wgrad: dW[N,K] = dY[R,N]^T X[R,K]     (both operands MN-major views of the natural tensors)
 int gemm_wgrad(cudaStream_t st, int N, int K, long long R, const void* dY, long long lddy, const void* X, long long ldx,
-               float* dW, long long ldw) {
+               float* dW, long long ldw, const float* inv_scale) {
     if (R <= 0) return cudaMemsetAsync(dW, 0, sizeof(float) * N * ldw, st) == cudaSuccess ? 0 : ft_set_error("memset failed");
     GemmArgs g;
     g.M = N; g.N = K; g.K = static_cast<int>(R);
-    g.A = dY; g.lda = lddy; g.a_fmt = FMT_BF16; g.a_mn = 1; g.B = X; g.ldb = ldx; g.b_fmt = FMT_BF16; g.b_mn = 1;
+    g.A = dY; g.lda = lddy; g.a_fmt = FMT_F16; g.a_mn = 1; g.B = X; g.ldb = ldx; g.b_fmt = FMT_F16; g.b_mn = 1;
+    g.alpha_ptr = inv_scale;          // undo the loss scale on the way out
     g.C32 = dW; g.ldc32 = ldw;
     return launch_gemm(g, st);
 }
@@ -255,70 +256,71 @@ int ar_step_bwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
     FT_TRY(check_desc(d));
     const Dims n(d);
     Plan ps; ps.base = static_cast<uint8_t*>(saved);
-    Saved S; S.plan(ps, d);
+    Saved S_; S_.plan(ps, d);
     Plan pb; pb.base = static_cast<uint8_t*>(scratch);
     BwdScratch F; F.plan(pb, d);
-    const float* mel_flow = d.reversed ? S.mel_flow : mel;
+    const float* mel_flow = d.reversed ? S_.mel_flow : mel;
     const long long R = n.R, RL = n.RL, Rm = n.R - n.B;     // Rm: rows with a predecessor step
 
-    // bf16 operand copies: natural layouts for dgrad (B operand MN-major), transposed recurrent weights for BPTT
-    FT_TRY(launch_cast(w.attn_lstm_w_ih, 2, F.w.w_ih_a, 1, static_cast<long long>(G) * n.M, st));
-    FT_TRY(launch_cast(w.lstm_w_ih0, 2, F.w.w_ih0, 1, static_cast<long long>(G) * n.D, st));
-    FT_TRY(launch_cast(w.lstm_w_ih1, 2, F.w.w_ih1, 1, static_cast<long long>(G) * H, st));
-    FT_TRY(launch_cast(w.att_query, 2, F.w.wq, 1, static_cast<long long>(n.A) * H, st));
-    FT_TRY(launch_cast(w.att_key, 2, F.w.wk, 1, static_cast<long long>(n.A) * n.E, st));
-    FT_TRY(launch_cast(w.att_value, 2, F.w.wv, 1, static_cast<long long>(n.A) * n.E, st));
-    FT_TRY(launch_cast(w.dense_w0, 2, F.w.w1, 1, static_cast<long long>(H) * H, st));
-    FT_TRY(launch_cast(w.dense_w1, 2, F.w.w2, 1, static_cast<long long>(H) * H, st));
-    FT_TRY(launch_cast(w.conv_w, 2, F.w.wc, 1, static_cast<long long>(2 * n.M) * H, st));
-    FT_TRY(launch_transpose_cast_bf16(w.attn_lstm_w_hh, F.w.w_hh_a, G, H, st));
-    FT_TRY(launch_transpose_cast_bf16(w.lstm_w_hh0, F.w.w_hh0, G, H, st));
-    FT_TRY(launch_transpose_cast_bf16(w.lstm_w_hh1, F.w.w_hh1, G, H, st));
+    // fp16 operand copies: natural layouts for dgrad (B operand MN-major), transposed recurrent weights for BPTT
+    FT_TRY(launch_cast(w.attn_lstm_w_ih, 2, F.w.w_ih_a, 0, static_cast<long long>(G) * n.M, st));
+    FT_TRY(launch_cast(w.lstm_w_ih0, 2, F.w.w_ih0, 0, static_cast<long long>(G) * n.D, st));
+    FT_TRY(launch_cast(w.lstm_w_ih1, 2, F.w.w_ih1, 0, static_cast<long long>(G) * H, st));
+    FT_TRY(launch_cast(w.att_query, 2, F.w.wq, 0, static_cast<long long>(n.A) * H, st));
+    FT_TRY(launch_cast(w.att_key, 2, F.w.wk, 0, static_cast<long long>(n.A) * n.E, st));
+    FT_TRY(launch_cast(w.att_value, 2, F.w.wv, 0, static_cast<long long>(n.A) * n.E, st));
+    FT_TRY(launch_cast(w.dense_w0, 2, F.w.w1, 0, static_cast<long long>(H) * H, st));
+    FT_TRY(launch_cast(w.dense_w1, 2, F.w.w2, 0, static_cast<long long>(H) * H, st));
+    FT_TRY(launch_cast(w.conv_w, 2, F.w.wc, 0, static_cast<long long>(2 * n.M) * H, st));
+    FT_TRY(launch_transpose_cast_f16(w.attn_lstm_w_hh, F.w.w_hh_a, G, H, st));
+    FT_TRY(launch_transpose_cast_f16(w.lstm_w_hh0, F.w.w_hh0, G, H, st));
+    FT_TRY(launch_transpose_cast_f16(w.lstm_w_hh1, F.w.w_hh1, G, H, st));
 
-    // 1. affine coupling
-    FT_TRY(launch_affine_bwd(d_mel_out, d_log_s, S.o32, mel_flow, out_lens, n.T, n.B, n.M, d.reversed, F.do16, F.dmel_flow, st));
+    // 0. loss scale for this flow's backward: S = 2^k with S * max|incoming grad| ~ 64 (device-side, no host sync)
+    const long long RM = R * n.M;
+    FT_TRY(launch_grad_scale(d_mel_out, d_mel_out ? RM : 0, d_log_s, d_log_s ? RM : 0, d_gates, d_gates ? R : 0, 64.f, F.scale, st));
+    const float* S = F.scale;            // S[0] = scale, S[1] = 1/scale
+    const float* iS = F.scale + 1;
+
+    // 1. affine coupling (scales the incoming gradients by S)
+    FT_TRY(launch_affine_bwd(d_mel_out, d_log_s, S_.o32, mel_flow, out_lens, n.T, n.B, n.M, d.reversed, F.do16, F.dmel_flow, S, st));
 
     // 2. 1x1 conv
-    FT_TRY(launch_cast(S.y2_16, 0, F.cvt, 1, R * H, st));
-    FT_TRY(gemm_wgrad(st, 2 * n.M, H, R, F.do16, 2 * n.M, F.cvt, H, g.conv_w, H));
-    FT_TRY(launch_colsum(F.do16, 1, 2 * n.M, R, 2 * n.M, g.conv_b, st));
-    FT_TRY(gemm_dgrad(st, R, H, 2 * n.M, F.do16, 2 * n.M, F.w.wc, H, 0, nullptr, 0, F.dy2, H, S.y2_16, H));      // * (1 - y2^2)
+    FT_TRY(gemm_wgrad(st, 2 * n.M, H, R, F.do16, 2 * n.M, S_.y2_16, H, g.conv_w, H, iS));
+    FT_TRY(launch_colsum(F.do16, 0, 2 * n.M, R, 2 * n.M, g.conv_b, iS, st));
+    FT_TRY(gemm_dgrad(st, R, H, 2 * n.M, F.do16, 2 * n.M, F.w.wc, H, 0, nullptr, 0, F.dy2, H, S_.y2_16, H));     // * (1 - y2^2)
 
     // 3. dense layer 1 (second linear)
-    FT_TRY(launch_cast(S.y1_16, 0, F.cvt, 1, R * H, st));
-    FT_TRY(gemm_wgrad(st, H, H, R, F.dy2, H, F.cvt, H, g.dense_w1, H));
-    FT_TRY(launch_colsum(F.dy2, 1, H, R, H, g.dense_b1, st));
-    FT_TRY(gemm_dgrad(st, R, H, H, F.dy2, H, F.w.w2, H, 0, nullptr, 0, F.dy1, H, S.y1_16, H));                    // * (1 - y1^2)
+    FT_TRY(gemm_wgrad(st, H, H, R, F.dy2, H, S_.y1_16, H, g.dense_w1, H, iS));
+    FT_TRY(launch_colsum(F.dy2, 0, H, R, H, g.dense_b1, iS, st));
+    FT_TRY(gemm_dgrad(st, R, H, H, F.dy2, H, F.w.w2, H, 0, nullptr, 0, F.dy1, H, S_.y1_16, H));                   // * (1 - y1^2)
 
     // 4. dense layer 0
-    FT_TRY(launch_cast(S.h1_16, 0, F.cvt, 1, R * H, st));
-    FT_TRY(gemm_wgrad(st, H, H, R, F.dy1, H, F.cvt, H, g.dense_w0, H));
-    FT_TRY(launch_colsum(F.dy1, 1, H, R, H, g.dense_b0, st));
+    FT_TRY(gemm_wgrad(st, H, H, R, F.dy1, H, S_.h1_16, H, g.dense_w0, H, iS));
+    FT_TRY(launch_colsum(F.dy1, 0, H, R, H, g.dense_b0, iS, st));
     FT_TRY(gemm_dgrad(st, R, H, H, F.dy1, H, F.w.w1, H, 0, F.dh, H, nullptr, 0, nullptr, 0));
 
-    // 5. lstm layer 1  (F.cvt still holds h1 in bf16)
-    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dh, H, F.w.w_hh1, S.gates1, S.c1, out_lens, F.dG, F.flags, st));
-    FT_TRY(gemm_wgrad(st, G, H, Rm, F.dG + static_cast<size_t>(n.B) * G, G, F.cvt, H, g.lstm_w_hh1, H));
-    FT_TRY(launch_cast(S.h0_16, 0, F.cvt, 1, R * H, st));
-    FT_TRY(gemm_wgrad(st, G, H, R, F.dG, G, F.cvt, H, g.lstm_w_ih1, H));
-    FT_TRY(launch_colsum(F.dG, 1, G, R, G, g.lstm_b_ih1, st));
+    // 5. lstm layer 1
+    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dh, H, F.w.w_hh1, S_.gates1, S_.c1, out_lens, F.dG, F.flags, st));
+    FT_TRY(gemm_wgrad(st, G, H, Rm, F.dG + static_cast<size_t>(n.B) * G, G, S_.h1_16, H, g.lstm_w_hh1, H, iS));
+    FT_TRY(gemm_wgrad(st, G, H, R, F.dG, G, S_.h0_16, H, g.lstm_w_ih1, H, iS));
+    FT_TRY(launch_colsum(F.dG, 0, G, R, G, g.lstm_b_ih1, iS, st));
     FT_TRY(copy_f32(g.lstm_b_hh1, g.lstm_b_ih1, G, st));
     FT_TRY(gemm_dgrad(st, R, H, G, F.dG, G, F.w.w_ih1, H, 0, F.dh, H, nullptr, 0, nullptr, 0));
 
-    // 6. lstm layer 0  (F.cvt holds h0 in bf16)
-    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dh, H, F.w.w_hh0, S.gates0, S.c0, out_lens, F.dG, F.flags, st));
-    FT_TRY(gemm_wgrad(st, G, H, Rm, F.dG + static_cast<size_t>(n.B) * G, G, F.cvt, H, g.lstm_w_hh0, H));
-    FT_TRY(launch_cast(S.d16, 0, F.cvt, 1, R * n.D, st));
-    FT_TRY(gemm_wgrad(st, G, n.D, R, F.dG, G, F.cvt, n.D, g.lstm_w_ih0, n.D));
-    FT_TRY(launch_colsum(F.dG, 1, G, R, G, g.lstm_b_ih0, st));
+    // 6. lstm layer 0
+    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dh, H, F.w.w_hh0, S_.gates0, S_.c0, out_lens, F.dG, F.flags, st));
+    FT_TRY(gemm_wgrad(st, G, H, Rm, F.dG + static_cast<size_t>(n.B) * G, G, S_.h0_16, H, g.lstm_w_hh0, H, iS));
+    FT_TRY(gemm_wgrad(st, G, n.D, R, F.dG, G, S_.d16, n.D, g.lstm_w_ih0, n.D, iS));
+    FT_TRY(launch_colsum(F.dG, 0, G, R, G, g.lstm_b_ih0, iS, st));
     FT_TRY(copy_f32(g.lstm_b_hh0, g.lstm_b_ih0, G, st));
     FT_TRY(gemm_dgrad(st, R, n.D, G, F.dG, G, F.w.w_ih0, n.D, 0, F.dd, n.D, nullptr, 0, nullptr, 0));
 
-    // 7. gate layer (last flow only)
+    // 7. gate layer (last flow only): dd is in the scaled domain, the gate's own parameter gradients are not
     if (d.has_gate && g.gate_w) {
         FT_TRY(zero(g.gate_w, sizeof(float) * n.D, st));
         FT_TRY(zero(g.gate_b, sizeof(float), st));
-        if (d_gates) FT_TRY(launch_gate_bwd(S.d16, n.D, n.D, w.gate_w, d_gates, R, F.dd, n.D, g.gate_w, g.gate_b, st));
+        if (d_gates) FT_TRY(launch_gate_bwd(S_.d16, n.D, n.D, w.gate_w, d_gates, R, F.dd, n.D, g.gate_w, g.gate_b, S, st));
     }
 
     // 8. attention (score/softmax/context) with tanh recompute
@@ -328,36 +330,34 @@ int ar_step_bwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
     {
         AttnBwdArgs a;
         a.T = n.T; a.B = n.B; a.L = n.L; a.A = n.A;
-        a.Q = S.Q; a.ldq = n.A; a.K = S.Kp; a.ldk = n.A; a.V = S.Vp; a.ldv = n.A; a.v = w.att_v;
-        a.in_lens = in_lens; a.out_lens = out_lens; a.attn = attn; a.p_save = S.p_save; a.temperature = d.temperature;
-        a.dctx = F.dd + H; a.lddc = n.D; a.dattn_ext = d_attn; a.dlp_ext = d_logprob;
+        a.Q = S_.Q; a.ldq = n.A; a.K = S_.Kp; a.ldk = n.A; a.V = S_.Vp; a.ldv = n.A; a.v = w.att_v;
+        a.in_lens = in_lens; a.out_lens = out_lens; a.attn = attn; a.p_save = S_.p_save; a.temperature = d.temperature;
+        a.dctx = F.dd + H; a.lddc = n.D; a.dattn_ext = d_attn; a.dlp_ext = d_logprob; a.scale = S;
         a.dQ = F.dQ; a.lddq = n.A; a.dK = F.dK; a.lddk = n.A; a.dV = F.dV; a.lddv = n.A; a.dv = g.att_v;
         FT_TRY(launch_attn_bwd(a, st));
     }
 
-    // 9. Q/K/V projections  (F.cvt holds d = [hA ; ctx] in bf16, row pitch D)
-    FT_TRY(launch_cast(F.dQ, 2, F.dQ16, 1, R * n.A, st));
-    FT_TRY(gemm_wgrad(st, n.A, H, R, F.dQ16, n.A, F.cvt, n.D, g.att_query, H));
+    // 9. Q/K/V projections  (d16 = [hA ; ctx] saved in fp16, row pitch D)
+    FT_TRY(launch_cast(F.dQ, 2, F.dQ16, 0, R * n.A, st));
+    FT_TRY(gemm_wgrad(st, n.A, H, R, F.dQ16, n.A, S_.d16, n.D, g.att_query, H, iS));
     FT_TRY(gemm_dgrad(st, R, H, n.A, F.dQ16, n.A, F.w.wq, H, 1, F.dd, n.D, nullptr, 0, nullptr, 0));   // dhA += dQ Wq
-    FT_TRY(launch_cast(F.dK, 2, F.dK16, 1, RL * n.A, st));
-    FT_TRY(launch_cast(F.dV, 2, F.dV16, 1, RL * n.A, st));
-    FT_TRY(launch_cast(S.text16, 0, F.text_bf, 1, RL * n.E, st));
-    FT_TRY(gemm_wgrad(st, n.A, n.E, RL, F.dK16, n.A, F.text_bf, n.E, g.att_key, n.E));
-    FT_TRY(gemm_wgrad(st, n.A, n.E, RL, F.dV16, n.A, F.text_bf, n.E, g.att_value, n.E));
-    FT_TRY(gemm_dgrad(st, RL, n.E, n.A, F.dK16, n.A, F.w.wk, n.E, 0, d_text, n.E, nullptr, 0, nullptr, 0));
-    FT_TRY(gemm_dgrad(st, RL, n.E, n.A, F.dV16, n.A, F.w.wv, n.E, 1, d_text, n.E, nullptr, 0, nullptr, 0));
+    FT_TRY(launch_cast(F.dK, 2, F.dK16, 0, RL * n.A, st));
+    FT_TRY(launch_cast(F.dV, 2, F.dV16, 0, RL * n.A, st));
+    FT_TRY(gemm_wgrad(st, n.A, n.E, RL, F.dK16, n.A, S_.text16, n.E, g.att_key, n.E, iS));
+    FT_TRY(gemm_wgrad(st, n.A, n.E, RL, F.dV16, n.A, S_.text16, n.E, g.att_value, n.E, iS));
+    FT_TRY(gemm_dgrad(st, RL, n.E, n.A, F.dK16, n.A, F.w.wk, n.E, 0, d_text, n.E, nullptr, 0, nullptr, 0, iS));
+    FT_TRY(gemm_dgrad(st, RL, n.E, n.A, F.dV16, n.A, F.w.wv, n.E, 1, d_text, n.E, nullptr, 0, nullptr, 0, iS));
 
     // 10. attention_lstm  (dhA = F.dd[:, 0:H], pitch D)
-    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dd, n.D, F.w.w_hh_a, S.gatesA, S.cA, out_lens, F.dG, F.flags, st));
-    FT_TRY(gemm_wgrad(st, G, H, Rm, F.dG + static_cast<size_t>(n.B) * G, G, F.cvt, n.D, g.attn_lstm_w_hh, H));
-    FT_TRY(launch_cast(S.mel_in16, 0, F.melin_bf, 1, R * n.M, st));
-    FT_TRY(gemm_wgrad(st, G, n.M, R, F.dG, G, F.melin_bf, n.M, g.attn_lstm_w_ih, n.M));
-    FT_TRY(launch_colsum(F.dG, 1, G, R, G, g.attn_lstm_b_ih, st));
+    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dd, n.D, F.w.w_hh_a, S_.gatesA, S_.cA, out_lens, F.dG, F.flags, st));
+    FT_TRY(gemm_wgrad(st, G, H, Rm, F.dG + static_cast<size_t>(n.B) * G, G, S_.d16, n.D, g.attn_lstm_w_hh, H, iS));
+    FT_TRY(gemm_wgrad(st, G, n.M, R, F.dG, G, S_.mel_in16, n.M, g.attn_lstm_w_ih, n.M, iS));
+    FT_TRY(launch_colsum(F.dG, 0, G, R, G, g.attn_lstm_b_ih, iS, st));
     FT_TRY(copy_f32(g.attn_lstm_b_hh, g.attn_lstm_b_ih, G, st));
     FT_TRY(gemm_dgrad(st, R, n.M, G, F.dG, G, F.w.w_ih_a, n.M, 0, F.dmel_in, n.M, nullptr, 0, nullptr, 0));
 
-    // 11. input gradient: coupling path + (shifted) attention_lstm path, back to natural time
-    if (d_mel) FT_TRY(launch_combine_dmel(F.dmel_flow, F.dmel_in, out_lens, n.T, n.B, n.M, d.reversed, d_mel, st));
+    // 11. input gradient: coupling path + (shifted) attention_lstm path, back to natural time, loss scale undone
+    if (d_mel) FT_TRY(launch_combine_dmel(F.dmel_flow, F.dmel_in, out_lens, n.T, n.B, n.M, d.reversed, d_mel, iS, st));
     return 0;
 }
 

@@ -266,6 +266,7 @@ struct AttnBwdParams {
     const float* dctx; long long lddc;    // [T*B, lddc] gradient w.r.t. ctx (fp32)
     const float* dattn_ext;               // [B,T,L] or null : gradient w.r.t. returned attn
     const float* dlp_ext;                 // [B,T,L] or null : gradient w.r.t. returned attn_logprob
+    const float* scale;                   // device {S, 1/S} or null: external grads * S, dv * 1/S
     float* dQ; long long lddq;            // [T*B, A] written
     float* dK; long long lddk;            // [L*B, A] accumulated (atomicAdd; caller zeroes)
     float* dV; long long lddv;            // [L*B, A] accumulated
@@ -301,6 +302,7 @@ attn_bwd_kernel(AttnBwdParams p) {
         return;
     }
     for (int i = tid; i < p.A; i += AT_THREADS) { sv[i] = p.v[i]; sdv[i] = 0.f; }
+    const float S = p.scale ? p.scale[0] : 1.f, iS = p.scale ? p.scale[1] : 1.f;
 
     // ---------------------------------------------------------------- 1. dattn[t,l] = dctx[t,:] . V[l,:]  (+ext);  dV += attn^T dctx
     for (int i = tid; i < AT_TT * SE_LD; i += AT_THREADS) sD[i] = 0.f;
@@ -398,8 +400,8 @@ attn_bwd_kernel(AttnBwdParams p) {
             float dot = 0.f;
             for (int l = lane; l < p.L; l += 32) {
                 float g = d[l];
-                if (p.dattn_ext) g += p.dattn_ext[o0 + l];
-                if (p.dlp_ext) g += p.dlp_ext[o0 + l] / (at[l] + 1e-8f);
+                if (p.dattn_ext) g += S * p.dattn_ext[o0 + l];
+                if (p.dlp_ext) g += S * p.dlp_ext[o0 + l] / (at[l] + 1e-8f);
                 d[l] = g;
                 dot += g * at[l];
             }
@@ -411,7 +413,7 @@ attn_bwd_kernel(AttnBwdParams p) {
             float dot = 0.f;
             for (int l = lane; l < p.L; l += 32) {
                 float g = d[l];
-                if (p.dattn_ext) g += p.dattn_ext[o0 + l];
+                if (p.dattn_ext) g += S * p.dattn_ext[o0 + l];
                 d[l] = g;
                 dot += g * at[l];
             }
@@ -420,7 +422,7 @@ attn_bwd_kernel(AttnBwdParams p) {
             float dot2 = 0.f;
             for (int l = lane; l < p.L; l += 32) {
                 float dlp = (l < in_len) ? at[l] * (d[l] - dot) : 0.f;       // through the masked 2nd softmax
-                if (p.dlp_ext) dlp += p.dlp_ext[o0 + l];                     // logprob is the pre-mask clone
+                if (p.dlp_ext) dlp += S * p.dlp_ext[o0 + l];                 // logprob is the pre-mask clone
                 const float pr = p.p_save[o0 + l];
                 const float dp = dlp / (pr + 1e-20f);
                 d[l] = dp;
@@ -528,7 +530,7 @@ attn_bwd_kernel(AttnBwdParams p) {
     __syncthreads();
     for (int i = tid; i < p.A; i += AT_THREADS) {
         const float x = sdv[i];
-        if (x != 0.f) atomicAdd(p.dv + i, x);
+        if (x != 0.f) atomicAdd(p.dv + i, x * iS);
     }
 }
 
@@ -569,7 +571,7 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t st) {
     p.Q = a.Q; p.ldq = a.ldq; p.K = a.K; p.ldk = a.ldk; p.V = a.V; p.ldv = a.ldv; p.v = a.v;
     p.in_lens = a.in_lens; p.out_lens = a.out_lens; p.attn = a.attn; p.p_save = a.p_save;
     p.has_prior = a.p_save != nullptr; p.inv_temperature = 1.0f / a.temperature;
-    p.dctx = a.dctx; p.lddc = a.lddc; p.dattn_ext = a.dattn_ext; p.dlp_ext = a.dlp_ext;
+    p.dctx = a.dctx; p.lddc = a.lddc; p.dattn_ext = a.dattn_ext; p.dlp_ext = a.dlp_ext; p.scale = a.scale;
     p.dQ = a.dQ; p.lddq = a.lddq; p.dK = a.dK; p.lddk = a.lddk; p.dV = a.dV; p.lddv = a.lddv; p.dv = a.dv;
     const size_t smem = attn_bwd_smem(a.L, a.A);
     cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

@@ -27,7 +27,7 @@ __device__ __forceinline__ int back_index_d(int t, int len, int T) { return t < 
 // ------------------------------------------------------------------------------------------------ casts
 template <typename TO>
 __device__ __forceinline__ TO cvt_from_float(float x);
-template <> __device__ __forceinline__ __half cvt_from_float<__half>(float x) { return __float2half_rn(x); }
+template <> __device__ __forceinline__ __half cvt_from_float<__half>(float x) { return __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)); }
 template <> __device__ __forceinline__ __nv_bfloat16 cvt_from_float<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
 template <> __device__ __forceinline__ float cvt_from_float<float>(float x) { return x; }
 __device__ __forceinline__ float cvt_to_float(float x) { return x; }
@@ -50,8 +50,8 @@ __global__ void cast_kernel(const TI* __restrict__ src, TO* __restrict__ dst, lo
     }
 }
 
-// dst[c, r] = src[r, c]  (fp32 -> bf16), used for W_hh^T
-__global__ void transpose_cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int cols) {
+// dst[c, r] = src[r, c]  (fp32 -> fp16), used for W_hh^T
+__global__ void transpose_cast_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int rows, int cols) {
     __shared__ float tile[32][33];
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -61,7 +61,7 @@ __global__ void transpose_cast_bf16_kernel(const float* __restrict__ src, __nv_b
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int c = c0 + i, r = r0 + threadIdx.x;
-        if (c < cols && r < rows) dst[static_cast<long long>(c) * rows + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+        if (c < cols && r < rows) dst[static_cast<long long>(c) * rows + r] = __float2half_rn(tile[threadIdx.x][i]);
     }
 }
 
@@ -79,11 +79,51 @@ int launch_cast(const void* src, int src_fmt, void* dst, int dst_fmt, long long 
     return ft_check_launch("cast_kernel");
 }
 
-int launch_transpose_cast_bf16(const float* src, void* dst, int rows, int cols, cudaStream_t st) {
+int launch_transpose_cast_f16(const float* src, void* dst, int rows, int cols, cudaStream_t st) {
     dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-    transpose_cast_bf16_kernel<<<grid, block, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst), rows, cols);
+    transpose_cast_f16_kernel<<<grid, block, 0, st>>>(src, static_cast<__half*>(dst), rows, cols);
     ft_count_launch(1);
-    return ft_check_launch("transpose_cast_bf16_kernel");
+    return ft_check_launch("transpose_cast_f16_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------ backward loss scale
+// Backward tensor-core operands are fp16 (11-bit significand).  Every backward op is linear in the incoming
+// gradient, so the flow's backward runs on S * grad with S a power of two chosen on the device from the
+// incoming gradients (max|.| -> `target`), and every result leaving the flow is multiplied by 1/S.  This is the
+// reference's own fp16 recipe (train.py:254 GradScaler) applied per flow and without host involvement.
+__global__ void absmax_kernel(const float* __restrict__ a, long long na, const float* __restrict__ b, long long nb,
+                              const float* __restrict__ c, long long nc, unsigned int* __restrict__ out) {
+    float m = 0.f;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (a) for (long long i = i0; i < na; i += stride) m = fmaxf(m, fabsf(a[i]));
+    if (b) for (long long i = i0; i < nb; i += stride) m = fmaxf(m, fabsf(b[i]));
+    if (c) for (long long i = i0; i < nc; i += stride) m = fmaxf(m, fabsf(c[i]));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f && isfinite(m)) atomicMax(out, __float_as_uint(m));   // non-negative floats order as uints
+}
+__global__ void scale_finalize_kernel(const unsigned int* __restrict__ mx, float target, float* __restrict__ scale2) {
+    const float m = __uint_as_float(mx[0]);
+    float s = 1.f;
+    if (m > 0.f) {
+        int e = static_cast<int>(floorf(log2f(target / m)));
+        e = e < -60 ? -60 : (e > 60 ? 60 : e);
+        s = exp2f(static_cast<float>(e));
+    }
+    scale2[0] = s;
+    scale2[1] = 1.f / s;
+}
+int launch_grad_scale(const float* a, long long na, const float* b, long long nb, const float* c, long long nc, float target,
+                      float* scale2, cudaStream_t st) {
+    unsigned int* mx = reinterpret_cast<unsigned int*>(scale2 + 2);
+    if (cudaMemsetAsync(mx, 0, sizeof(unsigned int), st) != cudaSuccess) return ft_set_error("grad_scale: memset failed");
+    long long n = na > nb ? na : nb;
+    n = n > nc ? n : nc;
+    absmax_kernel<<<grid_for(n, 256, 4), 256, 0, st>>>(a, na, b, nb, c, nc, mx);
+    scale_finalize_kernel<<<1, 1, 0, st>>>(mx, target, scale2);
+    ft_count_launch(2);
+    return ft_check_launch("grad_scale");
 }
 
 // ------------------------------------------------------------------------------------------------ mel prep
@@ -155,7 +195,8 @@ int launch_gate_fwd(const void* d16, long long ldd, int K, const float* wg, cons
 // backward of the gate GEMV: dd[r,:] += dgate[r] * wg ;  dwg[k] += sum_r dgate[r] d[r,k] ;  dbg += sum_r dgate[r]
 __global__ void gate_bwd_kernel(const __half* __restrict__ d16, long long ldd, int K, const float* __restrict__ wg,
                                 const float* __restrict__ dgate, long long R, float* __restrict__ dd, long long lddd,
-                                float* __restrict__ dwg, float* __restrict__ dbg) {
+                                float* __restrict__ dwg, float* __restrict__ dbg, const float* __restrict__ scale) {
+    const float S = scale ? scale[0] : 1.f;      // dd lives in the loss-scaled domain, dwg / dbg do not
     // block handles a slab of rows; thread k-strided accumulators for dwg
     extern __shared__ float sacc[];                   // [K]
     for (int k = threadIdx.x; k < K; k += blockDim.x) sacc[k] = 0.f;
@@ -170,7 +211,7 @@ __global__ void gate_bwd_kernel(const __half* __restrict__ d16, long long ldd, i
             const float g = dgate[r];
             if (g != 0.f) {
                 a = fmaf(g, __half2float(d16[r * ldd + k]), a);
-                dd[r * lddd + k] += g * w;
+                dd[r * lddd + k] += S * g * w;
             }
         }
         sacc[k] = a;
@@ -183,11 +224,11 @@ __global__ void gate_bwd_kernel(const __half* __restrict__ d16, long long ldd, i
     for (int k = threadIdx.x; k < K; k += blockDim.x) atomicAdd(dwg + k, sacc[k]);
 }
 int launch_gate_bwd(const void* d16, long long ldd, int K, const float* wg, const float* dgate, long long R, float* dd,
-                    long long lddd, float* dwg, float* dbg, cudaStream_t st) {
+                    long long lddd, float* dwg, float* dbg, const float* scale, cudaStream_t st) {
     long long gl = (R + 15) / 16, gcap = static_cast<long long>(num_sms()) * 4;
     int g = static_cast<int>(gl > gcap ? gcap : gl);
     if (g < 1) g = 1;
-    gate_bwd_kernel<<<g, 256, K * sizeof(float), st>>>(static_cast<const __half*>(d16), ldd, K, wg, dgate, R, dd, lddd, dwg, dbg);
+    gate_bwd_kernel<<<g, 256, K * sizeof(float), st>>>(static_cast<const __half*>(d16), ldd, K, wg, dgate, R, dd, lddd, dwg, dbg, scale);
     ft_count_launch(1);
     return ft_check_launch("gate_bwd_kernel");
 }
@@ -223,8 +264,9 @@ int launch_affine_fwd(const float* o, const float* mel_flow, const int* lens, in
 //   dzq = dz[src(q)] ;  d log_s = dlog_s_ext + dzq * mel_flow * exp(log_s) ;  d b = dzq ;  d mel_flow = dzq * exp(log_s)
 __global__ void affine_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ dlog_s_ext,
                                   const float* __restrict__ o, const float* __restrict__ mel_flow, const int* __restrict__ lens,
-                                  int T, int B, int M, int reversed, __nv_bfloat16* __restrict__ do16,
-                                  float* __restrict__ dmel_flow) {
+                                  int T, int B, int M, int reversed, __half* __restrict__ do16,
+                                  float* __restrict__ dmel_flow, const float* __restrict__ scale) {
+    const float S = scale ? scale[0] : 1.f;
     const long long n = static_cast<long long>(T) * B * M;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -234,20 +276,20 @@ __global__ void affine_bwd_kernel(const float* __restrict__ dz, const float* __r
         const int len = lens ? lens[b] : T;
         int s = q;
         if (reversed) s = back_index_d(q, len, T);
-        const float dzq = dz ? dz[(static_cast<long long>(s) * B + b) * M + m] : 0.f;
+        const float dzq = dz ? S * dz[(static_cast<long long>(s) * B + b) * M + m] : 0.f;
         const float es = expf(o[rb * 2 * M + m]);
         float dls = dzq * mel_flow[i] * es;
-        if (dlog_s_ext) dls += dlog_s_ext[i];
-        do16[rb * 2 * M + m] = __float2bfloat16_rn(dls);
-        do16[rb * 2 * M + M + m] = __float2bfloat16_rn(dzq);
+        if (dlog_s_ext) dls += S * dlog_s_ext[i];
+        do16[rb * 2 * M + m] = cvt_from_float<__half>(dls);
+        do16[rb * 2 * M + M + m] = cvt_from_float<__half>(dzq);
         dmel_flow[i] = dzq * es;
     }
 }
 int launch_affine_bwd(const float* dz, const float* dlog_s_ext, const float* o, const float* mel_flow, const int* lens, int T,
-                      int B, int M, int reversed, void* do16, float* dmel_flow, cudaStream_t st) {
+                      int B, int M, int reversed, void* do16, float* dmel_flow, const float* scale, cudaStream_t st) {
     const long long n = static_cast<long long>(T) * B * M;
     affine_bwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(dz, dlog_s_ext, o, mel_flow, lens, T, B, M, reversed,
-                                                         static_cast<__nv_bfloat16*>(do16), dmel_flow);
+                                                         static_cast<__half*>(do16), dmel_flow, scale);
     ft_count_launch(1);
     return ft_check_launch("affine_bwd_kernel");
 }
@@ -255,7 +297,9 @@ int launch_affine_bwd(const float* dz, const float* dlog_s_ext, const float* o, 
 // final input gradient of a flow, natural time:
 //   dmel[src(q), b, :] = dmel_flow[q,b,:] + (q+1 < T ? dmel_in[q+1,b,:] : 0)      (undo the teacher-forcing shift)
 __global__ void combine_dmel_kernel(const float* __restrict__ dmel_flow, const float* __restrict__ dmel_in,
-                                    const int* __restrict__ lens, int T, int B, int M, int reversed, float* __restrict__ dmel) {
+                                    const int* __restrict__ lens, int T, int B, int M, int reversed, float* __restrict__ dmel,
+                                    const float* __restrict__ inv_scale) {
+    const float iS = inv_scale ? inv_scale[0] : 1.f;
     const long long n = static_cast<long long>(T) * B * M;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -266,13 +310,13 @@ __global__ void combine_dmel_kernel(const float* __restrict__ dmel_flow, const f
         if (q + 1 < T) g += dmel_in[i + static_cast<long long>(B) * M];
         int s = q;
         if (reversed) s = back_index_d(q, lens ? lens[b] : T, T);
-        dmel[(static_cast<long long>(s) * B + b) * M + m] = g;
+        dmel[(static_cast<long long>(s) * B + b) * M + m] = g * iS;
     }
 }
 int launch_combine_dmel(const float* dmel_flow, const float* dmel_in, const int* lens, int T, int B, int M, int reversed,
-                        float* dmel, cudaStream_t st) {
+                        float* dmel, const float* inv_scale, cudaStream_t st) {
     const long long n = static_cast<long long>(T) * B * M;
-    combine_dmel_kernel<<<grid_for(n, 256), 256, 0, st>>>(dmel_flow, dmel_in, lens, T, B, M, reversed, dmel);
+    combine_dmel_kernel<<<grid_for(n, 256), 256, 0, st>>>(dmel_flow, dmel_in, lens, T, B, M, reversed, dmel, inv_scale);
     ft_count_launch(1);
     return ft_check_launch("combine_dmel_kernel");
 }
@@ -280,7 +324,8 @@ int launch_combine_dmel(const float* dmel_flow, const float* dmel_in, const int*
 // ------------------------------------------------------------------------------------------------ column sums
 // out[c] (+)= sum_r src[r, c]   (src bf16 or fp32, row pitch ld)
 template <typename TI>
-__global__ void colsum_kernel(const TI* __restrict__ src, long long ld, long long R, int C, float* __restrict__ out) {
+__global__ void colsum_kernel(const TI* __restrict__ src, long long ld, long long R, int C, float* __restrict__ out,
+                              const float* __restrict__ out_scale) {
     // grid.x tiles columns by 32*? ; grid.y slabs of rows; block (32, 8)
     const int c = blockIdx.x * 32 + threadIdx.x;
     const long long rows_per = (R + gridDim.y - 1) / gridDim.y;
@@ -294,17 +339,18 @@ __global__ void colsum_kernel(const TI* __restrict__ src, long long ld, long lon
     if (threadIdx.y == 0 && c < C) {
         float t = 0.f;
         for (int i = 0; i < blockDim.y; ++i) t += sm[i][threadIdx.x];
-        atomicAdd(out + c, t);
+        atomicAdd(out + c, out_scale ? t * out_scale[0] : t);
     }
 }
-int launch_colsum(const void* src, int fmt, long long ld, long long R, int C, float* out, cudaStream_t st) {
+int launch_colsum(const void* src, int fmt, long long ld, long long R, int C, float* out, const float* out_scale, cudaStream_t st) {
     if (cudaMemsetAsync(out, 0, sizeof(float) * C, st) != cudaSuccess) return ft_set_error("colsum: memset failed");
     long long gyl = (R + 255) / 256;
     int gy = static_cast<int>(gyl > 64 ? 64 : gyl);
     if (gy < 1) gy = 1;
     dim3 grid((C + 31) / 32, gy), block(32, 8);
-    if (fmt == 1) colsum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(src), ld, R, C, out);
-    else if (fmt == 2) colsum_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(src), ld, R, C, out);
+    if (fmt == 1) colsum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(src), ld, R, C, out, out_scale);
+    else if (fmt == 0) colsum_kernel<__half><<<grid, block, 0, st>>>(static_cast<const __half*>(src), ld, R, C, out, out_scale);
+    else if (fmt == 2) colsum_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(src), ld, R, C, out, out_scale);
     else return ft_set_error("colsum: unsupported format");
     ft_count_launch(1);
     return ft_check_launch("colsum_kernel");

@@ -30,7 +30,7 @@ struct GemmArgs {
     const void* A = nullptr; long long lda = 0; int a_fmt = 0; int a_mn = 0;
     const void* B = nullptr; long long ldb = 0; int b_fmt = 0; int b_mn = 0;
     const float* bias = nullptr; const float* bias2 = nullptr;
-    int act = 0; int beta = 0; float alpha = 1.0f;
+    int act = 0; int beta = 0; float alpha = 1.0f; const float* alpha_ptr = nullptr;
     const void* aux16 = nullptr; long long ldaux = 0;   // act == 2: fp16 [M,N] saved tanh output
     float* C32 = nullptr; long long ldc32 = 0;
     void* C16 = nullptr; long long ldc16 = 0; int c16_fmt = 0;
@@ -45,18 +45,20 @@ int launch_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void
                     const float* cstate, const int* lens, void* dG16, int* flags, cudaStream_t st);
 
 int launch_cast(const void* src, int src_fmt, void* dst, int dst_fmt, long long n, cudaStream_t st);   // 0 f16, 1 bf16, 2 f32
-int launch_transpose_cast_bf16(const float* src, void* dst, int rows, int cols, cudaStream_t st);
+int launch_transpose_cast_f16(const float* src, void* dst, int rows, int cols, cudaStream_t st);
+int launch_grad_scale(const float* a, long long na, const float* b, long long nb, const float* c, long long nc, float target,
+                      float* scale2, cudaStream_t st);   // scale2[0] = S (power of two), scale2[1] = 1/S
 int launch_prep_mel(const float* mel, const int* lens, int T, int B, int M, int reversed, void* mel_in16, float* mel_flow, cudaStream_t st);
 int launch_gate_fwd(const void* d16, long long ldd, int K, const float* wg, const float* bg, long long R, float* gate, cudaStream_t st);
 int launch_gate_bwd(const void* d16, long long ldd, int K, const float* wg, const float* dgate, long long R, float* dd,
-                    long long lddd, float* dwg, float* dbg, cudaStream_t st);
+                    long long lddd, float* dwg, float* dbg, const float* scale, cudaStream_t st);
 int launch_affine_fwd(const float* o, const float* mel_flow, const int* lens, int T, int B, int M, int reversed, float* z,
                       float* log_s, cudaStream_t st);
 int launch_affine_bwd(const float* dz, const float* dlog_s_ext, const float* o, const float* mel_flow, const int* lens, int T,
-                      int B, int M, int reversed, void* do16, float* dmel_flow, cudaStream_t st);
+                      int B, int M, int reversed, void* do16, float* dmel_flow, const float* scale, cudaStream_t st);
 int launch_combine_dmel(const float* dmel_flow, const float* dmel_in, const int* lens, int T, int B, int M, int reversed,
-                        float* dmel, cudaStream_t st);
-int launch_colsum(const void* src, int fmt, long long ld, long long R, int C, float* out, cudaStream_t st);
+                        float* dmel, const float* inv_scale, cudaStream_t st);
+int launch_colsum(const void* src, int fmt, long long ld, long long R, int C, float* out, const float* out_scale, cudaStream_t st);
 int launch_nll_reduce(const float* z, const float* const* log_s_list_dev, int n_flows, const float* gate,
                       const float* gate_target, const int* lens, int T, int B, int M, float* sums, cudaStream_t st);
 int launch_nll_grad(const float* z, const float* gate, const float* gate_target, const int* lens, int T, int B, int M,
@@ -74,6 +76,7 @@ struct AttnBwdArgs {
     const float* Q; long long ldq; const float* K; long long ldk; const float* V; long long ldv; const float* v;
     const int* in_lens; const int* out_lens; const float* attn; const float* p_save; float temperature;
     const float* dctx; long long lddc; const float* dattn_ext; const float* dlp_ext;
+    const float* scale;      // device [2] = {S, 1/S}: external grads are multiplied by S, dv by 1/S (null = 1)
     float* dQ; long long lddq; float* dK; long long lddk; float* dV; long long lddv; float* dv;
 };
 int launch_attn_fwd(const AttnFwdArgs& a, cudaStream_t st);

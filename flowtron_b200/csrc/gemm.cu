@@ -33,6 +33,7 @@ struct GemmParams {
     const __half* aux16; long long ldaux;
     int beta;                  // 1: C32 += result (C32 read-modify-write)
     float alpha;               // scale on the accumulator before bias
+    const float* alpha_ptr;    // optional device scalar multiplied into alpha (loss-scale undo)
     float* C32; long long ldc32;
     void* C16; long long ldc16; int c16_fmt;   // 0 f16, 1 bf16
     int* status;
@@ -137,9 +138,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tmem_ld_wait();
             if (!row_ok) continue;
             const int nvalid = min(32, p.N - n0);
+            const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                float x = v[j] * p.alpha;
+                float x = v[j] * alpha;
                 if (j < nvalid) {
                     if (p.bias) x += __ldg(p.bias + n0 + j);
                     if (p.bias2) x += __ldg(p.bias2 + n0 + j);
@@ -182,8 +184,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 uint32_t pk[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    if (p.c16_fmt == 0) {
-                        __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                    if (p.c16_fmt == 0) {      // fp16: saturate instead of overflowing to inf
+                        __half2 h = __floats2half2_rn(fminf(fmaxf(v[2 * j], -65504.f), 65504.f),
+                                                      fminf(fmaxf(v[2 * j + 1], -65504.f), 65504.f));
                         pk[j] = *reinterpret_cast<uint32_t*>(&h);
                     } else {
                         __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
@@ -255,7 +258,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
     if (rc) return rc;
     GemmParams p;
     p.M = g.M; p.N = g.N; p.K = g.K; p.a_fmt = g.a_fmt; p.b_fmt = g.b_fmt; p.a_mn = g.a_mn; p.b_mn = g.b_mn;
-    p.bias = g.bias; p.bias2 = g.bias2; p.act = g.act; p.aux16 = static_cast<const __half*>(g.aux16); p.ldaux = g.ldaux; p.beta = g.beta; p.alpha = g.alpha;
+    p.bias = g.bias; p.bias2 = g.bias2; p.act = g.act; p.alpha_ptr = g.alpha_ptr; p.aux16 = static_cast<const __half*>(g.aux16); p.ldaux = g.ldaux; p.beta = g.beta; p.alpha = g.alpha;
     p.C32 = g.C32; p.ldc32 = g.ldc32; p.C16 = g.C16; p.ldc16 = g.ldc16; p.c16_fmt = g.c16_fmt;
     p.status = ft_status_word();
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);

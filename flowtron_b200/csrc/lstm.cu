@@ -15,7 +15,7 @@
 //     registers for the whole sequence), and publish h_t (fp16) + per-chunk release flags in global
 //     memory; consumers acquire the flag, fence the async proxy, and TMA the chunk.
 // Backward (lstm_bwd_kernel), 64 CTAs x 16 units: dh_{t-1} = dG_t W_hh with W_hh^T slice resident
-//   (bf16, 128 KB), dG_t ([B,4096] bf16) streamed through the ring, the pointwise LSTM backward in the
+//   (fp16, 128 KB), dG_t ([B,4096] fp16, loss-scaled) streamed through the ring, the pointwise LSTM backward in the
 //   epilogue; dG is written once and reused by the wgrad/dgrad GEMMs.
 #include "ptx.cuh"
 #include "ft_internal.h"
@@ -82,18 +82,24 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             for (int kc = 0; kc < FWD_NCH; ++kc)
                 for (int g = 0; g < 4; ++g)
                     tma_load_2d(sW + kc * (FWD_N * 128) + g * 1024, &tmW, wbar, kc * KCH, g * LH + FWD_UNITS * cta);
-            const int target = 8 * nq;             // 8 producer CTAs per 64-unit chunk, one release per active quadrant warp
-            int it = 0;
-            for (int t = 1; t < p.T; ++t) {
+        }
+        const int target = 8 * nq;                 // 8 producer CTAs per 64-unit chunk, one release per active quadrant warp
+        int it = 0;
+        for (int t = 1; t < p.T; ++t) {
+            // all 16 chunk flags of step t-1 are polled IN PARALLEL (one lane each): a serial poll costs one L2
+            // round trip per chunk and was 10 us/step in the first version
+            if (lane < FWD_NCH) wait_flag_ge(&p.flags[(t - 1) * FWD_NCH + lane], target, p.status, 202);
+            __syncwarp();
+            if (lane == 0) {
+                fence_proxy_async();               // generic-proxy writes of other SMs -> async-proxy (TMA) reads
                 for (int kc = 0; kc < FWD_NCH; ++kc, ++it) {
                     const int s = it % p.nslot, ph = (it / p.nslot) & 1;
                     mbar_wait(&empty[s], ph ^ 1, p.status, 201);
-                    wait_flag_ge(&p.flags[(t - 1) * FWD_NCH + kc], target, p.status, 202);
-                    fence_proxy_async();           // generic-proxy writes of other SMs -> async-proxy (TMA) read
                     mbar_expect_tx(&full[s], slot_bytes);
                     tma_load_2d(ring + s * slot_bytes, &tmH, &full[s], kc * KCH, (t - 1) * p.B);
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -191,9 +197,11 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                         d[1] = make_float4(c[4], c[5], c[6], c[7]);
                     }
                 }
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) red_release_add(&p.flags[t * FWD_NCH + cta / 8], 1);
+                __syncwarp();                      // lanes' stores happen-before lane 0's cumulative fence + release
+                if (lane == 0) {
+                    __threadfence();
+                    red_release_add(&p.flags[t * FWD_NCH + cta / 8], 1);
+                }
             }
         }
     }
@@ -212,7 +220,7 @@ struct LstmBwdParams {
     const __half* gates;       // [T*B, 4096] saved i,f,g,o
     const float* cstate;       // [T*B, 1024] saved c_t
     const int* lens;
-    __nv_bfloat16* dG;         // [T*B, 4096] out: gradient w.r.t. gate pre-activations (bf16)
+    __half* dG;                // [T*B, 4096] out: (loss-scaled) gradient w.r.t. gate pre-activations (fp16, saturating)
     int* flags;                // [T * 64]
     int* status;
 };
@@ -254,23 +262,28 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
             mbar_expect_tx(wbar, BWD_W_BYTES);
             for (int kc = 0; kc < BWD_NCH; ++kc)       // W_hh^T rows [16c,16c+16), K chunk kc
                 tma_load_2d(sW + kc * (BWD_UNITS * 128), &tmWT, wbar, kc * KCH, BWD_UNITS * cta);
-            const int target = 4 * nq;                 // 4 producer CTAs per 64-column chunk of dG
-            int it = 0;
-            for (int t = p.T - 2; t >= 0; --t) {
+        }
+        const int target = 4 * nq;                     // 4 producer CTAs per 64-column chunk of dG
+        int it = 0;
+        for (int t = p.T - 2; t >= 0; --t) {
+            for (int c = lane; c < BWD_NCH; c += 32)   // parallel poll of the 64 chunk flags of step t+1
+                wait_flag_ge(&p.flags[(t + 1) * BWD_NCH + c], target, p.status, 212);
+            __syncwarp();
+            if (lane == 0) {
+                fence_proxy_async();
                 for (int kc = 0; kc < BWD_NCH; ++kc, ++it) {
                     const int s = it % p.nslot, ph = (it / p.nslot) & 1;
                     mbar_wait(&empty[s], ph ^ 1, p.status, 211);
-                    wait_flag_ge(&p.flags[(t + 1) * BWD_NCH + kc], target, p.status, 212);
-                    fence_proxy_async();
                     mbar_expect_tx(&full[s], slot_bytes);
                     tma_load_2d(ring + s * slot_bytes, &tmG, &full[s], kc * KCH, (t + 1) * p.B);
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         if (lane == 0) {
             mbar_wait(wbar, 0, p.status, 213);
-            const uint32_t idesc = umma_idesc(128, BWD_UNITS, FMT_BF16, FMT_BF16, 0, 0);
+            const uint32_t idesc = umma_idesc(128, BWD_UNITS, FMT_F16, FMT_F16, 0, 0);
             const uint32_t w0 = smem_u32(sW), r0 = smem_u32(ring);
             int it = 0;
             for (int t = p.T - 2; t >= 0; --t) {
@@ -335,7 +348,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
                     tc_fence_before();
                 }
                 if (row_ok) {
-                    __nv_bfloat162 out[4][BWD_UNITS / 2];
+                    __half2 out[4][BWD_UNITS / 2];
                     if (valid) {
 #pragma unroll
                         for (int j2 = 0; j2 < BWD_UNITS / 2; ++j2) {
@@ -357,13 +370,14 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
                                 dcs[j] = dc * gf;
                             }
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) out[g][j2] = __floats2bfloat162_rn(da[g][0], da[g][1]);
+                            for (int g = 0; g < 4; ++g)
+                                out[g][j2] = __floats2half2_rn(fminf(fmaxf(da[g][0], -65504.f), 65504.f), fminf(fmaxf(da[g][1], -65504.f), 65504.f));
                         }
                     } else {
 #pragma unroll
                         for (int g = 0; g < 4; ++g)
 #pragma unroll
-                            for (int j2 = 0; j2 < BWD_UNITS / 2; ++j2) out[g][j2] = __floats2bfloat162_rn(0.f, 0.f);
+                            for (int j2 = 0; j2 < BWD_UNITS / 2; ++j2) out[g][j2] = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
                         for (int j = 0; j < BWD_UNITS; ++j) dcs[j] = 0.f;
                     }
@@ -374,9 +388,11 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
                         dst[1] = *reinterpret_cast<uint4*>(&out[g][4]);
                     }
                 }
-                __threadfence();
                 __syncwarp();
-                if (lane < 4) red_release_add(&p.flags[t * BWD_NCH + lane * 16 + cta / 4], 1);
+                if (lane < 4) {
+                    __threadfence();
+                    red_release_add(&p.flags[t * BWD_NCH + lane * 16 + cta / 4], 1);
+                }
             }
         }
     }
@@ -439,10 +455,10 @@ int launch_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void
     if (nslot < 2) return ft_set_error("lstm_bwd: not enough shared memory for the dG ring");
     p.nslot = nslot;
     p.dh_ext = dh_ext; p.ldd = ldd; p.gates = static_cast<const __half*>(gates16); p.cstate = cstate; p.lens = lens;
-    p.dG = static_cast<__nv_bfloat16*>(dG16); p.flags = flags; p.status = ft_status_word();
+    p.dG = static_cast<__half*>(dG16); p.flags = flags; p.status = ft_status_word();
     CUtensorMap tmWT, tmG;
-    if (make_tmap_2d(&tmWT, whhT16, FMT_BF16, LH, LG, LG, KCH, BWD_UNITS)) return -1;
-    if (make_tmap_2d(&tmG, dG16, FMT_BF16, static_cast<long long>(T) * B, LG, LG, KCH, p.Bbox)) return -1;
+    if (make_tmap_2d(&tmWT, whhT16, FMT_F16, LH, LG, LG, KCH, BWD_UNITS)) return -1;
+    if (make_tmap_2d(&tmG, dG16, FMT_F16, static_cast<long long>(T) * B, LG, LG, KCH, p.Bbox)) return -1;
     if (cudaMemsetAsync(flags, 0, sizeof(int) * T * BWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_bwd: memset failed");
     const int smem = nslot * slot + fixed;
     cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

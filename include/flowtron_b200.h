@@ -50,9 +50,10 @@ int ft_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const int* 
                 void* gates16, float* cstate, float* h32, long long ldh32, int* flags, void* stream);
 
 /* BPTT of the same layer (autograd of nn.LSTM).  dh_ext: gradient w.r.t. the layer outputs, fp32
- * [T*B, ldd] (ignored at t >= lens[b]).  whhT16: bf16 copy of weight_hh^T [1024,4096].  Writes dG (bf16
- * [T*B,4096]), the gradient w.r.t. the gate pre-activations; dW_ih, dW_hh, db and dx are GEMMs / column
- * sums over dG done by the caller.  flags: int scratch [T*64]. */
+ * [T*B, ldd] (ignored at t >= lens[b]; the caller may pre-multiply it by a power-of-two loss scale).  whhT16:
+ * fp16 copy of weight_hh^T [1024,4096].  Writes dG (fp16 [T*B,4096], saturating), the gradient w.r.t. the gate
+ * pre-activations; dW_ih, dW_hh, db and dx are GEMMs / column sums over dG done by the caller.
+ * flags: int scratch [T*64]. */
 int ft_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void* whhT16, const void* gates16,
                 const float* cstate, const int* lens, void* dG16, int* flags, void* stream);
 
