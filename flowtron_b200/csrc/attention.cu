@@ -50,16 +50,35 @@ __device__ __forceinline__ float exp2x_clamped(float x) {               // e^{2x
     return fast_ex2(2.8853900817779268f * xc);
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+// score accumulation for one staged (query, key, channel) chunk; NJ = key columns per thread actually needed
+template <int NJ>
+__device__ __forceinline__ void score_chunk(float (&acc)[4][8], const float* __restrict__ sQ, const float* __restrict__ sK,
+                                            const float* __restrict__ sva, int na, int ty, int tx) {
+#pragma unroll 2
+    for (int a = 0; a < na; ++a) {
+        const float4 q4 = *reinterpret_cast<const float4*>(&sQ[a * SQ_LD + 4 * ty]);
+        const float va = sva[a];
+        float k[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) k[j] = sK[a * SK_LD + tx + 16 * j];
+        const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(va, fast_rcp(fmaf(q[i], k[j], 1.0f)), acc[i][j]);
+    }
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_kernel(AttnFwdParams p) {
     extern __shared__ float smf[];
-    const int Lpad = ((p.L + AT_LB - 1) / AT_LB) * AT_LB;
+    const int Lr = (p.L + 31) & ~31;                  // score row pitch: keys rounded up to a warp
     float* sQ = smf;                                  // [AT_AC][SQ_LD]
     float* sK = sQ + AT_AC * SQ_LD;                   // [AT_AC][SK_LD]   (also the V chunk [64][AT_AC+4])
-    float* sE = sK + AT_AC * SK_LD;                   // [AT_TT][Lpad+4]
-    float* sv = sE + AT_TT * (Lpad + 4);              // [A]
+    float* sE = sK + AT_AC * SK_LD;                   // [AT_TT][Lr+4]
+    float* sv = sE + AT_TT * (Lr + 4);                // [A]
     __shared__ float s_sumv;
-    const int SE_LD = Lpad + 4;
+    const int SE_LD = Lr + 4;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y, t0 = blockIdx.x * AT_TT;
@@ -96,8 +115,10 @@ attn_fwd_kernel(AttnFwdParams p) {
     }
 
     const int ty = tid >> 4, tx = tid & 15;           // 16 x 16 thread grid: rows 4*ty.., keys tx + 16*j
-    const int nlb = Lpad / AT_LB;
+    const int nlb = (p.L + AT_LB - 1) / AT_LB;
     for (int lb = 0; lb < nlb; ++lb) {
+        const int nl = min(AT_LB, p.L - lb * AT_LB);
+        const int nj = (nl + 15) >> 4;                // key columns per thread that hold real keys (block-uniform)
         float acc[4][8];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -105,14 +126,14 @@ attn_fwd_kernel(AttnFwdParams p) {
             for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
         for (int ac = 0; ac < p.A; ac += AT_AC) {
             __syncthreads();
-            {   // stage e^{2Q} chunk: 64 t x 64 a
+            {   // stage e^{2Q} chunk: 64 t x 64 a, and e^{2K}: nj*16 keys x 64 a
                 const int aa = tid & 63;
                 for (int tt = tid >> 6; tt < AT_TT; tt += AT_THREADS / 64) {
                     float q = 0.f;
                     if (tt < nrows && ac + aa < p.A) q = p.Q[(static_cast<long long>(t0 + tt) * p.B + b) * p.ldq + ac + aa];
                     sQ[aa * SQ_LD + tt] = exp2x_clamped(q);
                 }
-                for (int ll = tid >> 6; ll < AT_LB; ll += AT_THREADS / 64) {
+                for (int ll = tid >> 6; ll < nj * 16; ll += AT_THREADS / 64) {
                     const int l = lb * AT_LB + ll;
                     float k = 0.f;
                     if (l < p.L && ac + aa < p.A) k = p.K[(static_cast<long long>(l) * p.B + b) * p.ldk + ac + aa];
@@ -121,26 +142,21 @@ attn_fwd_kernel(AttnFwdParams p) {
             }
             __syncthreads();
             const int na = min(AT_AC, p.A - ac);
-#pragma unroll 2
-            for (int a = 0; a < na; ++a) {
-                const float4 q4 = *reinterpret_cast<const float4*>(&sQ[a * SQ_LD + 4 * ty]);
-                const float va = sv[ac + a];
-                float k[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) k[j] = sK[a * SK_LD + tx + 16 * j];
-                const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(va, fast_rcp(fmaf(q[i], k[j], 1.0f)), acc[i][j]);
+            switch ((nj + 1) >> 1) {
+                case 1: score_chunk<2>(acc, sQ, sK, sv + ac, na, ty, tx); break;
+                case 2: score_chunk<4>(acc, sQ, sK, sv + ac, na, ty, tx); break;
+                case 3: score_chunk<6>(acc, sQ, sK, sv + ac, na, ty, tx); break;
+                default: score_chunk<8>(acc, sQ, sK, sv + ac, na, ty, tx); break;
             }
         }
         const float sumv = s_sumv;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                sE[(4 * ty + i) * SE_LD + lb * AT_LB + tx + 16 * j] = (sumv - 2.f * acc[i][j]) * p.inv_temperature;
+            for (int j = 0; j < 8; ++j) {
+                const int col = lb * AT_LB + tx + 16 * j;
+                if (col < Lr) sE[(4 * ty + i) * SE_LD + col] = (sumv - 2.f * acc[i][j]) * p.inv_temperature;
+            }
     }
     __syncthreads();
 
@@ -198,7 +214,7 @@ attn_fwd_kernel(AttnFwdParams p) {
                 p.attn[o0 + l] = a2;
             }
         }
-        for (int l = p.L + lane; l < Lpad; l += 32) e[l] = 0.f;
+        for (int l = p.L + lane; l < Lr; l += 32) e[l] = 0.f;
     }
     __syncthreads();
 
@@ -536,8 +552,8 @@ attn_bwd_kernel(AttnBwdParams p) {
 
 // =================================================================================================== host
 static size_t attn_fwd_smem(int L, int A) {
-    const int Lpad = ((L + AT_LB - 1) / AT_LB) * AT_LB;
-    return sizeof(float) * (static_cast<size_t>(AT_AC) * SQ_LD + AT_AC * SK_LD + AT_TT * (Lpad + 4) + A) + 64;
+    const int Lr = (L + 31) & ~31;
+    return sizeof(float) * (static_cast<size_t>(AT_AC) * SQ_LD + AT_AC * SK_LD + AT_TT * (Lr + 4) + A) + 64;
 }
 static size_t attn_bwd_smem(int L, int A) {
     const int Lpad = ((L + AT_LB - 1) / AT_LB) * AT_LB;

@@ -22,6 +22,10 @@
 
 namespace ft {
 
+#define FT_TRACE(p, t, slot) do { if ((p).trace && blockIdx.x == 0) (p).trace[(t) * 8 + (slot)] = clock64(); } while (0)
+static long long* g_lstm_trace = nullptr;      // set through ft_debug_set_lstm_trace
+void set_lstm_trace(long long* p) { g_lstm_trace = p; }
+
 constexpr int LH = 1024;
 constexpr int LG = 4 * LH;
 constexpr int KCH = 64;                        // K elements per 128-byte chunk (16-bit operands)
@@ -41,6 +45,7 @@ struct LstmFwdParams {
     float* h32; long long ldh32;   // optional fp32 copy of h (or null)
     int* flags;                // [T * 16], zeroed by the launcher
     int* status;
+    long long* trace;          // optional [T][8] clock64 stamps of CTA 0 (debug/profiling), or null
 };
 
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
@@ -91,6 +96,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             if (lane < FWD_NCH) wait_flag_ge(&p.flags[(t - 1) * FWD_NCH + lane], target, p.status, 202);
             __syncwarp();
             if (lane == 0) {
+                FT_TRACE(p, t, 0);                 // flags of step t-1 all visible
                 fence_proxy_async();               // generic-proxy writes of other SMs -> async-proxy (TMA) reads
                 for (int kc = 0; kc < FWD_NCH; ++kc, ++it) {
                     const int s = it % p.nslot, ph = (it / p.nslot) & 1;
@@ -98,6 +104,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     mbar_expect_tx(&full[s], slot_bytes);
                     tma_load_2d(ring + s * slot_bytes, &tmH, &full[s], kc * KCH, (t - 1) * p.B);
                 }
+                FT_TRACE(p, t, 1);                 // all TMA loads issued
             }
             __syncwarp();
         }
@@ -119,7 +126,9 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                         umma_f16(tmem_base, da, db, idesc, (kc | k) != 0);
                     }
                     umma_commit(&empty[s]);
+                    if (kc == 0) FT_TRACE(p, t, 2);          // first chunk landed
                 }
+                FT_TRACE(p, t, 3);                 // last chunk landed, all MMAs issued
                 umma_commit(accum_full);
             }
         }
@@ -152,6 +161,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     float acc[32];
                     mbar_wait(accum_full, (t - 1) & 1, p.status, 205);
                     tc_fence_after();
+                    if (lane == 0 && q == 0) FT_TRACE(p, t, 4);      // accumulator complete
                     tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16), acc);
                     tmem_ld_wait();
                     tc_fence_before();
@@ -199,8 +209,11 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 }
                 __syncwarp();                      // lanes' stores happen-before lane 0's cumulative fence + release
                 if (lane == 0) {
+                    if (q == 0) FT_TRACE(p, t, 5);  // cell + stores done
                     __threadfence();
+                    if (q == 0) FT_TRACE(p, t, 6);  // fence done
                     red_release_add(&p.flags[t * FWD_NCH + cta / 8], 1);
+                    if (q == 0) FT_TRACE(p, t, 7);  // release issued
                 }
             }
         }
@@ -223,6 +236,7 @@ struct LstmBwdParams {
     __half* dG;                // [T*B, 4096] out: (loss-scaled) gradient w.r.t. gate pre-activations (fp16, saturating)
     int* flags;                // [T * 64]
     int* status;
+    long long* trace;
 };
 
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
@@ -426,7 +440,7 @@ int launch_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const i
     p.nslot = nslot;
     p.xproj = xproj; p.lens = lens; p.hseq = static_cast<__half*>(hseq16); p.ldh = ldh;
     p.gates = static_cast<__half*>(gates16); p.cstate = cstate; p.h32 = h32; p.ldh32 = ldh32;
-    p.flags = flags; p.status = ft_status_word();
+    p.flags = flags; p.status = ft_status_word(); p.trace = g_lstm_trace;
     CUtensorMap tmW, tmH;
     if (make_tmap_2d(&tmW, whh16, FMT_F16, LG, LH, LH, KCH, FWD_UNITS)) return -1;
     if (make_tmap_2d(&tmH, hseq16, FMT_F16, static_cast<long long>(T) * B, LH, ldh, KCH, p.Bbox)) return -1;
@@ -455,7 +469,7 @@ int launch_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void
     if (nslot < 2) return ft_set_error("lstm_bwd: not enough shared memory for the dG ring");
     p.nslot = nslot;
     p.dh_ext = dh_ext; p.ldd = ldd; p.gates = static_cast<const __half*>(gates16); p.cstate = cstate; p.lens = lens;
-    p.dG = static_cast<__half*>(dG16); p.flags = flags; p.status = ft_status_word();
+    p.dG = static_cast<__half*>(dG16); p.flags = flags; p.status = ft_status_word(); p.trace = nullptr;
     CUtensorMap tmWT, tmG;
     if (make_tmap_2d(&tmWT, whhT16, FMT_F16, LH, LG, LG, KCH, BWD_UNITS)) return -1;
     if (make_tmap_2d(&tmG, dG16, FMT_F16, static_cast<long long>(T) * B, LG, LG, KCH, p.Bbox)) return -1;

@@ -49,6 +49,9 @@ int ft_gemm(int M, int N, int K, const void* A, long long lda, int a_fmt, int a_
 int ft_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const int* lens, void* hseq16, long long ldh,
                 void* gates16, float* cstate, float* h32, long long ldh32, int* flags, void* stream);
 
+/* debug/profiling: device buffer [T][8] that receives clock64 stamps of CTA 0 of later ft_lstm_fwd launches */
+void ft_debug_set_lstm_trace(long long* buf);
+
 /* BPTT of the same layer (autograd of nn.LSTM).  dh_ext: gradient w.r.t. the layer outputs, fp32
  * [T*B, ldd] (ignored at t >= lens[b]; the caller may pre-multiply it by a power-of-two loss scale).  whhT16:
  * fp16 copy of weight_hh^T [1024,4096].  Writes dG (fp16 [T*B,4096], saturating), the gradient w.r.t. the gate
