@@ -132,7 +132,7 @@ struct BwdScratch {
 int check_desc(const FtArStepDesc& d) {
     if (d.n_hidden != H) return ft_set_error("ar_step: this build supports n_hidden == 1024 only");
     if (d.T <= 0 || d.B <= 0 || d.L <= 0) return ft_set_error("ar_step: empty shape");
-    if (d.B > 128) return ft_set_error("ar_step: batch > 128 per call not supported (split the batch)");
+    if (d.B > 64) return ft_set_error("ar_step: batch > 64 per call not supported (split the batch)");
     if (d.n_mel % 8 || d.n_attn % 64 || d.n_text % 8) return ft_set_error("ar_step: n_mel %8, n_attn %64, n_text %8 required");
     if (d.L > 256) return ft_set_error("ar_step: L > 256 not supported");
     return 0;

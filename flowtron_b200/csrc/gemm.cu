@@ -222,6 +222,8 @@ int ensure_tma_encoder() {
     return 0;
 }
 
+PFN_encodeTiled get_tma_encoder() { return ensure_tma_encoder() ? nullptr : g_encode; }
+
 // 2D row-major tensor [rows, cols] (cols contiguous, row pitch ld elements), box {box_cols, box_rows}, SW128.
 int make_tmap_2d(CUtensorMap* out, const void* ptr, int fmt, long long rows, long long cols, long long ld,
                  int box_cols, int box_rows) {

@@ -8,15 +8,22 @@
 // Forward (lstm_fwd_kernel), one cooperative launch, 128 CTAs:
 //   * CTA c owns hidden units [8c, 8c+8): its 32 rows of W_hh (4 gates x 8 units, fp16, 64 KB) are
 //     TMA-loaded once and stay resident in shared memory as the UMMA B operand (N = 32).
-//   * every step: h_{t-1} ([B,1024] fp16, read straight out of the layer's output tensor) is TMA-streamed
-//     in 16 K-chunks into an mbarrier ring as the UMMA A operand (M = 128 rows, batch rows first; the
-//     remaining rows are don't-care), tcgen05.mma accumulates the 32 gate pre-activations in TMEM,
-//     the epilogue warps add the input projection, apply the LSTM cell in fp32 (cell state lives in
-//     registers for the whole sequence), and publish h_t (fp16) + per-chunk release flags in global
-//     memory; consumers acquire the flag, fence the async proxy, and TMA the chunk.
-// Backward (lstm_bwd_kernel), 64 CTAs x 16 units: dh_{t-1} = dG_t W_hh with W_hh^T slice resident
-//   (fp16, 128 KB), dG_t ([B,4096] fp16, loss-scaled) streamed through the ring, the pointwise LSTM backward in the
-//   epilogue; dG is written once and reused by the wgrad/dgrad GEMMs.
+//   * every step: h_{t-1} ([B,1024] fp16, read straight out of the layer's output tensor) arrives through
+//     TWO 3-D TMA loads (8 K-chunks each, box {64 elems, B rows, 8 chunks}: the smem image is chunk-major
+//     SWIZZLE_128B K-major tiles, the UMMA A operand with M = 128 rows of which the first B are real),
+//     tcgen05.mma accumulates the 32 gate pre-activations in TMEM, the accumulator rows are handed to all
+//     four epilogue warps through shared memory, which add the input projection, apply the cell in fp32
+//     (cell state lives in registers for the whole sequence), store h_t (fp16) and publish ONE release per
+//     CTA into a per-(step, chunk) counter; consumers poll the 16 counters in parallel (one lane each),
+//     fence the async proxy, and issue the next loads.  gates / c for the backward pass are stored AFTER
+//     the release so they stay off the critical path.
+// Backward (lstm_bwd_kernel), 64 CTAs x 16 units: dh_{t-1} = dG_t W_hh with the W_hh^T slice resident
+//   (fp16, 128 KB), dG_t ([B,4096] fp16, loss-scaled) streamed in groups of chunks through a small ring,
+//   the pointwise LSTM backward in the epilogue; dG is written once and reused by the wgrad/dgrad GEMMs.
+//
+// History (profiles/, tools/trace_lstm.py): v1 polled the chunk flags and issued 16 (64) 2-D TMA loads
+// serially from one thread: 4 us of an 8.9 us forward step was TMA issue, 0.85 us a single-warp epilogue,
+// 1 us fence+release behind 112 B/lane of stores.
 #include "ptx.cuh"
 #include "ft_internal.h"
 
@@ -29,14 +36,24 @@ void set_lstm_trace(long long* p) { g_lstm_trace = p; }
 constexpr int LH = 1024;
 constexpr int LG = 4 * LH;
 constexpr int KCH = 64;                        // K elements per 128-byte chunk (16-bit operands)
-constexpr int LSTM_THREADS = 192;
+constexpr int LSTM_THREADS = 192;              // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
+constexpr int EPI_THREADS = 128;
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
 
 // ------------------------------------------------------------------------------------------- forward
 constexpr int FWD_CTAS = 128, FWD_UNITS = 8, FWD_N = 32, FWD_NCH = LH / KCH;     // 16 chunks / step
 constexpr int FWD_W_BYTES = FWD_NCH * FWD_N * 128;                                 // 64 KB
+constexpr int FWD_GS = 8, FWD_NG = FWD_NCH / FWD_GS;                               // 2 TMA groups / step
 
 struct LstmFwdParams {
-    int T, B, Bbox, nslot;
+    int T, B, Bbox;
     const float* xproj;        // [T*B, 4096] input projection + both biases
     const int* lens;           // [B] or null
     __half* hseq; long long ldh;   // [T*B, ldh] output (fp16), also the recurrent exchange buffer
@@ -53,14 +70,14 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int slot_bytes = p.Bbox * 128;
-    uint8_t* ring = smem;
-    uint8_t* sW = smem + p.nslot * slot_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + FWD_W_BYTES);   // the M=128 over-read of the last ring slot lands in sW
-    uint64_t* full = bars;                       // [nslot]
-    uint64_t* empty = bars + 32;                 // [nslot]
-    uint64_t* wbar = bars + 64;
-    uint64_t* accum_full = bars + 65;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 66);
+    uint8_t* sA = smem;                                          // [16 chunks][Bbox rows][128 B]
+    uint8_t* sW = smem + FWD_NCH * slot_bytes;                   // the M=128 over-read of the last chunks lands here
+    float* sAcc = reinterpret_cast<float*>(sW + FWD_W_BYTES);    // [128 rows][33]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + 128 * 33);
+    uint64_t* full = bars;                       // [FWD_NG]
+    uint64_t* wbar = bars + 4;
+    uint64_t* accum_full = bars + 5;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x;
@@ -69,7 +86,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmW);
         tma_prefetch_desc(&tmH);
-        for (int s = 0; s < p.nslot; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int g = 0; g < FWD_NG; ++g) mbar_init(&full[g], 1);
         mbar_init(wbar, 1);
         mbar_init(accum_full, 1);
         fence_mbar_init();
@@ -88,23 +105,21 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 for (int g = 0; g < 4; ++g)
                     tma_load_2d(sW + kc * (FWD_N * 128) + g * 1024, &tmW, wbar, kc * KCH, g * LH + FWD_UNITS * cta);
         }
-        const int target = 8 * nq;                 // 8 producer CTAs per 64-unit chunk, one release per active quadrant warp
-        int it = 0;
         for (int t = 1; t < p.T; ++t) {
-            // all 16 chunk flags of step t-1 are polled IN PARALLEL (one lane each): a serial poll costs one L2
-            // round trip per chunk and was 10 us/step in the first version
-            if (lane < FWD_NCH) wait_flag_ge(&p.flags[(t - 1) * FWD_NCH + lane], target, p.status, 202);
+            // the 16 chunk counters of step t-1 (8 producer CTAs each) are polled in parallel, one lane each.
+            // Seeing them all also proves this CTA's own step t-1 retired (its release is among them), so the A
+            // buffer is free: no empty-slot barrier is needed.
+            if (lane < FWD_NCH) wait_flag_ge(&p.flags[(t - 1) * FWD_NCH + lane], 8, p.status, 202);
             __syncwarp();
             if (lane == 0) {
-                FT_TRACE(p, t, 0);                 // flags of step t-1 all visible
+                FT_TRACE(p, t, 0);
                 fence_proxy_async();               // generic-proxy writes of other SMs -> async-proxy (TMA) reads
-                for (int kc = 0; kc < FWD_NCH; ++kc, ++it) {
-                    const int s = it % p.nslot, ph = (it / p.nslot) & 1;
-                    mbar_wait(&empty[s], ph ^ 1, p.status, 201);
-                    mbar_expect_tx(&full[s], slot_bytes);
-                    tma_load_2d(ring + s * slot_bytes, &tmH, &full[s], kc * KCH, (t - 1) * p.B);
+#pragma unroll
+                for (int g = 0; g < FWD_NG; ++g) {
+                    mbar_expect_tx(&full[g], FWD_GS * slot_bytes);
+                    tma_load_3d(sA + g * FWD_GS * slot_bytes, &tmH, &full[g], 0, (t - 1) * p.B, g * FWD_GS);
                 }
-                FT_TRACE(p, t, 1);                 // all TMA loads issued
+                FT_TRACE(p, t, 1);
             }
             __syncwarp();
         }
@@ -112,108 +127,126 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         if (lane == 0) {
             mbar_wait(wbar, 0, p.status, 203);
             const uint32_t idesc = umma_idesc(128, FWD_N, FMT_F16, FMT_F16, 0, 0);
-            const uint32_t w0 = smem_u32(sW), r0 = smem_u32(ring);
-            int it = 0;
+            const uint32_t w0 = smem_u32(sW), a0 = smem_u32(sA);
             for (int t = 1; t < p.T; ++t) {
-                for (int kc = 0; kc < FWD_NCH; ++kc, ++it) {
-                    const int s = it % p.nslot, ph = (it / p.nslot) & 1;
-                    mbar_wait(&full[s], ph, p.status, 204);
-                    tc_fence_after();
+                const int ph = (t - 1) & 1;
 #pragma unroll
-                    for (int k = 0; k < KCH / 16; ++k) {
-                        const uint64_t da = umma_smem_desc(r0 + s * slot_bytes + k * 32, 16, 1024);
-                        const uint64_t db = umma_smem_desc(w0 + kc * (FWD_N * 128) + k * 32, 16, 1024);
-                        umma_f16(tmem_base, da, db, idesc, (kc | k) != 0);
+                for (int g = 0; g < FWD_NG; ++g) {
+                    mbar_wait(&full[g], ph, p.status, 204);
+                    tc_fence_after();
+                    if (g == 0) FT_TRACE(p, t, 2);
+#pragma unroll
+                    for (int c = 0; c < FWD_GS; ++c) {
+                        const int kc = g * FWD_GS + c;
+#pragma unroll
+                        for (int k = 0; k < KCH / 16; ++k) {
+                            const uint64_t da = umma_smem_desc(a0 + kc * slot_bytes + k * 32, 16, 1024);
+                            const uint64_t db = umma_smem_desc(w0 + kc * (FWD_N * 128) + k * 32, 16, 1024);
+                            umma_f16(tmem_base, da, db, idesc, (kc | k) != 0);
+                        }
                     }
-                    umma_commit(&empty[s]);
-                    if (kc == 0) FT_TRACE(p, t, 2);          // first chunk landed
                 }
-                FT_TRACE(p, t, 3);                 // last chunk landed, all MMAs issued
+                FT_TRACE(p, t, 3);
                 umma_commit(accum_full);
             }
         }
     } else {
-        const int q = warp & 3;
-        if (q < nq) {
-            const int b = q * 32 + lane;
-            const bool row_ok = b < p.B;
-            const int len = (row_ok && p.lens) ? p.lens[b] : p.T;
-            const int u0 = FWD_UNITS * cta;
-            float c[FWD_UNITS];
+        // ---------------------------------------------------------------- epilogue: 4 warps, 128 threads
+        const int q = warp & 3;                               // TMEM lane quadrant this warp may read
+        const int et = threadIdx.x - 64;                      // 0..127
+        // work items: (batch row b, unit pair up) -> item = b * 4 + up ; thread handles items et, et + 128
+        const int n_items = p.B * 4;
+        float c[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        int len_i[2];
 #pragma unroll
-            for (int j = 0; j < FWD_UNITS; ++j) c[j] = 0.f;
-            for (int t = 0; t < p.T; ++t) {
-                const long long r = static_cast<long long>(t) * p.B + b;
-                float x[32];
-                if (row_ok) {
+        for (int s = 0; s < 2; ++s) {
+            const int item = et + s * EPI_THREADS;
+            len_i[s] = (item < n_items && p.lens) ? p.lens[item >> 2] : p.T;
+        }
+        const int u0 = FWD_UNITS * cta;
+        for (int t = 0; t < p.T; ++t) {
+            float x[2][8];                                    // [item][gate*2 + e]
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int item = et + s * EPI_THREADS;
+                if (item < n_items) {
+                    const int b = item >> 2, up = item & 3;
+                    const float* src = p.xproj + (static_cast<long long>(t) * p.B + b) * LG + u0 + 2 * up;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const float4* src = reinterpret_cast<const float4*>(p.xproj + r * LG + g * LH + u0);
-                        const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
-                        x[g * 8 + 0] = v0.x; x[g * 8 + 1] = v0.y; x[g * 8 + 2] = v0.z; x[g * 8 + 3] = v0.w;
-                        x[g * 8 + 4] = v1.x; x[g * 8 + 5] = v1.y; x[g * 8 + 6] = v1.z; x[g * 8 + 7] = v1.w;
+                        const float2 v = __ldg(reinterpret_cast<const float2*>(src + g * LH));
+                        x[s][2 * g] = v.x; x[s][2 * g + 1] = v.y;
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = 0.f;
                 }
-                if (t > 0) {
+            }
+            if (t > 0) {
+                if (q < nq) {                                 // this warp owns TMEM rows [32q, 32q+32)
                     float acc[32];
                     mbar_wait(accum_full, (t - 1) & 1, p.status, 205);
                     tc_fence_after();
-                    if (lane == 0 && q == 0) FT_TRACE(p, t, 4);      // accumulator complete
+                    if (et == 64) FT_TRACE(p, t, 4);          // warp 4 == quadrant 0
                     tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16), acc);
                     tmem_ld_wait();
                     tc_fence_before();
+                    float* dst = sAcc + (q * 32 + lane) * 33;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] += acc[j];
+                    for (int j = 0; j < 32; ++j) dst[j] = acc[j];
                 }
-                if (row_ok) {
-                    const bool valid = t < len;
-                    float hv[FWD_UNITS], gi[FWD_UNITS], gf[FWD_UNITS], gg[FWD_UNITS], go[FWD_UNITS];
+                epi_bar();
 #pragma unroll
-                    for (int j = 0; j < FWD_UNITS; ++j) {
-                        gi[j] = sigmoid_f(x[j]);
-                        gf[j] = sigmoid_f(x[8 + j]);
-                        gg[j] = tanh_f(x[16 + j]);
-                        go[j] = sigmoid_f(x[24 + j]);
-                        c[j] = gf[j] * c[j] + gi[j] * gg[j];
-                        hv[j] = valid ? go[j] * tanh_f(c[j]) : 0.f;
-                    }
-                    {   // h_t (fp16) -> layer output / exchange buffer
-                        __half2 h2[4];
+                for (int s = 0; s < 2; ++s) {
+                    const int item = et + s * EPI_THREADS;
+                    if (item < n_items) {
+                        const int b = item >> 2, up = item & 3;
+                        const float* a = sAcc + b * 33 + 2 * up;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(hv[2 * j], hv[2 * j + 1]);
-                        *reinterpret_cast<uint4*>(p.hseq + r * p.ldh + u0) = *reinterpret_cast<uint4*>(h2);
+                        for (int g = 0; g < 4; ++g) { x[s][2 * g] += a[g * 8]; x[s][2 * g + 1] += a[g * 8 + 1]; }
                     }
-                    if (p.h32) {
-                        float4* d = reinterpret_cast<float4*>(p.h32 + r * p.ldh32 + u0);
-                        d[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
-                        d[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                }
+            }
+            float gi[2][2], gf[2][2], gg[2][2], go[2][2], hv[2][2];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int item = et + s * EPI_THREADS;
+                if (item < n_items) {
+                    const int b = item >> 2, up = item & 3;
+                    const bool valid = t < len_i[s];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        gi[s][e] = sigmoid_f(x[s][0 + e]);
+                        gf[s][e] = sigmoid_f(x[s][2 + e]);
+                        gg[s][e] = tanh_f(x[s][4 + e]);
+                        go[s][e] = sigmoid_f(x[s][6 + e]);
+                        c[s][e] = gf[s][e] * c[s][e] + gi[s][e] * gg[s][e];
+                        hv[s][e] = valid ? go[s][e] * tanh_f(c[s][e]) : 0.f;
                     }
+                    const long long r = static_cast<long long>(t) * p.B + b;
+                    const __half2 h2 = __floats2half2_rn(hv[s][0], hv[s][1]);
+                    *reinterpret_cast<__half2*>(p.hseq + r * p.ldh + u0 + 2 * up) = h2;     // critical path: h_t first
+                }
+            }
+            epi_bar();                                        // all h_t stores of this CTA precede the release
+            if (et == 0) {
+                FT_TRACE(p, t, 5);
+                red_release_add(&p.flags[t * FWD_NCH + cta / 8], 1);      // cumulative release (gpu scope)
+                FT_TRACE(p, t, 7);
+            }
+            // off the critical path: tensors only the backward pass reads
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int item = et + s * EPI_THREADS;
+                if (item < n_items) {
+                    const int b = item >> 2, up = item & 3;
+                    const long long r = static_cast<long long>(t) * p.B + b;
+                    if (p.h32) *reinterpret_cast<float2*>(p.h32 + r * p.ldh32 + u0 + 2 * up) = make_float2(hv[s][0], hv[s][1]);
                     if (p.gates) {
-                        const float* gsrc[4] = {gi, gf, gg, go};
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            __half2 h2[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(gsrc[g][2 * j], gsrc[g][2 * j + 1]);
-                            *reinterpret_cast<uint4*>(p.gates + r * LG + g * LH + u0) = *reinterpret_cast<uint4*>(h2);
-                        }
+                        __half* gp = p.gates + r * LG + u0 + 2 * up;
+                        *reinterpret_cast<__half2*>(gp) = __floats2half2_rn(gi[s][0], gi[s][1]);
+                        *reinterpret_cast<__half2*>(gp + LH) = __floats2half2_rn(gf[s][0], gf[s][1]);
+                        *reinterpret_cast<__half2*>(gp + 2 * LH) = __floats2half2_rn(gg[s][0], gg[s][1]);
+                        *reinterpret_cast<__half2*>(gp + 3 * LH) = __floats2half2_rn(go[s][0], go[s][1]);
                     }
-                    if (p.cstate) {
-                        float4* d = reinterpret_cast<float4*>(p.cstate + r * LH + u0);
-                        d[0] = make_float4(c[0], c[1], c[2], c[3]);
-                        d[1] = make_float4(c[4], c[5], c[6], c[7]);
-                    }
-                }
-                __syncwarp();                      // lanes' stores happen-before lane 0's cumulative fence + release
-                if (lane == 0) {
-                    if (q == 0) FT_TRACE(p, t, 5);  // cell + stores done
-                    __threadfence();
-                    if (q == 0) FT_TRACE(p, t, 6);  // fence done
-                    red_release_add(&p.flags[t * FWD_NCH + cta / 8], 1);
-                    if (q == 0) FT_TRACE(p, t, 7);  // release issued
+                    if (p.cstate) *reinterpret_cast<float2*>(p.cstate + r * LH + u0 + 2 * up) = make_float2(c[s][0], c[s][1]);
                 }
             }
         }
@@ -228,8 +261,9 @@ constexpr int BWD_CTAS = 64, BWD_UNITS = 16, BWD_NCH = LG / KCH;                
 constexpr int BWD_W_BYTES = BWD_NCH * BWD_UNITS * 128;                              // 128 KB
 
 struct LstmBwdParams {
-    int T, B, Bbox, nslot;
-    const float* dh_ext; long long ldd;   // [T*B, ldd] gradient w.r.t. the layer outputs (fp32)
+    int T, B, Bbox;
+    int gs, ng, nring;         // chunks per TMA group, groups per step (64 / gs), ring depth in groups
+    const float* dh_ext; long long ldd;   // [T*B, ldd] gradient w.r.t. the layer outputs (fp32, loss-scaled)
     const __half* gates;       // [T*B, 4096] saved i,f,g,o
     const float* cstate;       // [T*B, 1024] saved c_t
     const int* lens;
@@ -244,14 +278,17 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int slot_bytes = p.Bbox * 128;
-    uint8_t* ring = smem;
-    uint8_t* sW = smem + p.nslot * slot_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + BWD_W_BYTES);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + 32;
-    uint64_t* wbar = bars + 64;
-    uint64_t* accum_full = bars + 65;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 66);
+    const int group_bytes = p.gs * slot_bytes;
+    uint8_t* ring = smem;                                        // [nring groups][gs chunks][Bbox rows][128 B]
+    uint8_t* sW = smem + p.nring * group_bytes;                  // over-read of the last ring chunk lands here
+    float* sAcc = reinterpret_cast<float*>(sW + BWD_W_BYTES);    // [128 rows][17]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + 128 * 17 + 1);
+    bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bars) + 7) & ~uintptr_t(7));
+    uint64_t* full = bars;                       // [nring]
+    uint64_t* empty = bars + 8;                  // [nring]
+    uint64_t* wbar = bars + 16;
+    uint64_t* accum_full = bars + 17;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x;
@@ -260,7 +297,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmWT);
         tma_prefetch_desc(&tmG);
-        for (int s = 0; s < p.nslot; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < p.nring; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(wbar, 1);
         mbar_init(accum_full, 1);
         fence_mbar_init();
@@ -277,19 +314,18 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
             for (int kc = 0; kc < BWD_NCH; ++kc)       // W_hh^T rows [16c,16c+16), K chunk kc
                 tma_load_2d(sW + kc * (BWD_UNITS * 128), &tmWT, wbar, kc * KCH, BWD_UNITS * cta);
         }
-        const int target = 4 * nq;                     // 4 producer CTAs per 64-column chunk of dG
-        int it = 0;
+        int s = 0, ph = 0;                             // ring slot / phase, advanced incrementally (no div/mod)
         for (int t = p.T - 2; t >= 0; --t) {
-            for (int c = lane; c < BWD_NCH; c += 32)   // parallel poll of the 64 chunk flags of step t+1
-                wait_flag_ge(&p.flags[(t + 1) * BWD_NCH + c], target, p.status, 212);
+            for (int c = lane; c < BWD_NCH; c += 32)   // parallel poll: 4 producer CTAs per 64-column chunk of dG_{t+1}
+                wait_flag_ge(&p.flags[(t + 1) * BWD_NCH + c], 4, p.status, 212);
             __syncwarp();
             if (lane == 0) {
                 fence_proxy_async();
-                for (int kc = 0; kc < BWD_NCH; ++kc, ++it) {
-                    const int s = it % p.nslot, ph = (it / p.nslot) & 1;
+                for (int g = 0; g < p.ng; ++g) {
                     mbar_wait(&empty[s], ph ^ 1, p.status, 211);
-                    mbar_expect_tx(&full[s], slot_bytes);
-                    tma_load_2d(ring + s * slot_bytes, &tmG, &full[s], kc * KCH, (t + 1) * p.B);
+                    mbar_expect_tx(&full[s], group_bytes);
+                    tma_load_3d(ring + s * group_bytes, &tmG, &full[s], 0, (t + 1) * p.B, g * p.gs);
+                    if (++s == p.nring) { s = 0; ph ^= 1; }
                 }
             }
             __syncwarp();
@@ -299,115 +335,130 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
             mbar_wait(wbar, 0, p.status, 213);
             const uint32_t idesc = umma_idesc(128, BWD_UNITS, FMT_F16, FMT_F16, 0, 0);
             const uint32_t w0 = smem_u32(sW), r0 = smem_u32(ring);
-            int it = 0;
+            int s = 0, ph = 0;
             for (int t = p.T - 2; t >= 0; --t) {
-                for (int kc = 0; kc < BWD_NCH; ++kc, ++it) {
-                    const int s = it % p.nslot, ph = (it / p.nslot) & 1;
+                for (int g = 0; g < p.ng; ++g) {
                     mbar_wait(&full[s], ph, p.status, 214);
                     tc_fence_after();
+                    for (int c = 0; c < p.gs; ++c) {
+                        const int kc = g * p.gs + c;
 #pragma unroll
-                    for (int k = 0; k < KCH / 16; ++k) {
-                        const uint64_t da = umma_smem_desc(r0 + s * slot_bytes + k * 32, 16, 1024);
-                        const uint64_t db = umma_smem_desc(w0 + kc * (BWD_UNITS * 128) + k * 32, 16, 1024);
-                        umma_f16(tmem_base, da, db, idesc, (kc | k) != 0);
+                        for (int k = 0; k < KCH / 16; ++k) {
+                            const uint64_t da = umma_smem_desc(r0 + s * group_bytes + c * slot_bytes + k * 32, 16, 1024);
+                            const uint64_t db = umma_smem_desc(w0 + kc * (BWD_UNITS * 128) + k * 32, 16, 1024);
+                            umma_f16(tmem_base, da, db, idesc, (kc | k) != 0);
+                        }
                     }
                     umma_commit(&empty[s]);
+                    if (++s == p.nring) { s = 0; ph ^= 1; }
                 }
                 umma_commit(accum_full);
             }
         }
     } else {
+        // ---------------------------------------------------------------- epilogue: items (batch row, 4 units)
         const int q = warp & 3;
-        if (q < nq) {
-            const int b = q * 32 + lane;
-            const bool row_ok = b < p.B;
-            const int len = (row_ok && p.lens) ? p.lens[b] : p.T;
-            const int u0 = BWD_UNITS * cta;
-            float dcs[BWD_UNITS];
+        const int et = threadIdx.x - 64;
+        const int n_items = p.B * 4;
+        const int u0 = BWD_UNITS * cta;
+        float dcs[2][4];
 #pragma unroll
-            for (int j = 0; j < BWD_UNITS; ++j) dcs[j] = 0.f;
-            int step = 0;
-            for (int t = p.T - 1; t >= 0; --t, ++step) {
-                const long long r = static_cast<long long>(t) * p.B + b;
-                float dh[BWD_UNITS], ct[BWD_UNITS], cp[BWD_UNITS];
-                __half2 gt[4][BWD_UNITS / 2];
-                const bool valid = row_ok && (t < len);
-                if (valid) {
+        for (int s = 0; s < 2; ++s)
 #pragma unroll
-                    for (int j = 0; j < BWD_UNITS / 4; ++j) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(p.dh_ext + r * p.ldd + u0) + j);
-                        dh[4 * j] = v.x; dh[4 * j + 1] = v.y; dh[4 * j + 2] = v.z; dh[4 * j + 3] = v.w;
-                        const float4 cc = __ldg(reinterpret_cast<const float4*>(p.cstate + r * LH + u0) + j);
-                        ct[4 * j] = cc.x; ct[4 * j + 1] = cc.y; ct[4 * j + 2] = cc.z; ct[4 * j + 3] = cc.w;
-                        float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (t > 0) pp = __ldg(reinterpret_cast<const float4*>(p.cstate + (r - p.B) * LH + u0) + j);
-                        cp[4 * j] = pp.x; cp[4 * j + 1] = pp.y; cp[4 * j + 2] = pp.z; cp[4 * j + 3] = pp.w;
-                    }
+            for (int j = 0; j < 4; ++j) dcs[s][j] = 0.f;
+        int len_i[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int item = et + s * EPI_THREADS;
+            len_i[s] = (item < n_items && p.lens) ? p.lens[item >> 2] : p.T;
+        }
+        int step = 0;
+        for (int t = p.T - 1; t >= 0; --t, ++step) {
+            float dh[2][4], ct[2][4], cp[2][4];
+            __half2 gt[2][4][2];                              // [item][gate][2 x half2]
+            bool valid[2];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int item = et + s * EPI_THREADS;
+                valid[s] = (item < n_items) && (t < len_i[s]);
+                if (valid[s]) {
+                    const int b = item >> 2, uq = item & 3;
+                    const long long r = static_cast<long long>(t) * p.B + b;
+                    const int uo = u0 + 4 * uq;
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(p.dh_ext + r * p.ldd + uo));
+                    dh[s][0] = v.x; dh[s][1] = v.y; dh[s][2] = v.z; dh[s][3] = v.w;
+                    const float4 cc = __ldg(reinterpret_cast<const float4*>(p.cstate + r * LH + uo));
+                    ct[s][0] = cc.x; ct[s][1] = cc.y; ct[s][2] = cc.z; ct[s][3] = cc.w;
+                    float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (t > 0) pp = __ldg(reinterpret_cast<const float4*>(p.cstate + (r - p.B) * LH + uo));
+                    cp[s][0] = pp.x; cp[s][1] = pp.y; cp[s][2] = pp.z; cp[s][3] = pp.w;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const uint4* src = reinterpret_cast<const uint4*>(p.gates + r * LG + g * LH + u0);
-                        uint4 a = __ldg(src), bb = __ldg(src + 1);
-                        *reinterpret_cast<uint4*>(&gt[g][0]) = a;
-                        *reinterpret_cast<uint4*>(&gt[g][4]) = bb;
+                        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(p.gates + r * LG + g * LH + uo));
+                        *reinterpret_cast<uint2*>(&gt[s][g][0]) = pk;
                     }
                 }
-                float acc[BWD_UNITS];
-#pragma unroll
-                for (int j = 0; j < BWD_UNITS; ++j) acc[j] = 0.f;
-                if (step > 0) {
+            }
+            if (step > 0) {
+                if (q < nq) {
+                    float acc[16];
                     mbar_wait(accum_full, (step - 1) & 1, p.status, 215);
                     tc_fence_after();
                     tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16), acc);
                     tmem_ld_wait();
                     tc_fence_before();
-                }
-                if (row_ok) {
-                    __half2 out[4][BWD_UNITS / 2];
-                    if (valid) {
+                    float* dst = sAcc + (q * 32 + lane) * 17;
 #pragma unroll
-                        for (int j2 = 0; j2 < BWD_UNITS / 2; ++j2) {
+                    for (int j = 0; j < 16; ++j) dst[j] = acc[j];
+                }
+                epi_bar();
+            }
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int item = et + s * EPI_THREADS;
+                if (item < n_items) {
+                    const int b = item >> 2, uq = item & 3;
+                    const long long r = static_cast<long long>(t) * p.B + b;
+                    __half2 out[4][2];
+                    if (valid[s]) {
+#pragma unroll
+                        for (int j2 = 0; j2 < 2; ++j2) {
                             float da[4][2];
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 const int j = 2 * j2 + e;
-                                const float gi = e ? __high2float(gt[0][j2]) : __low2float(gt[0][j2]);
-                                const float gf = e ? __high2float(gt[1][j2]) : __low2float(gt[1][j2]);
-                                const float gg = e ? __high2float(gt[2][j2]) : __low2float(gt[2][j2]);
-                                const float go = e ? __high2float(gt[3][j2]) : __low2float(gt[3][j2]);
-                                const float dht = dh[j] + acc[j];
-                                const float tc = tanh_f(ct[j]);
-                                const float dc = dcs[j] + dht * go * (1.f - tc * tc);
+                                const float gi = e ? __high2float(gt[s][0][j2]) : __low2float(gt[s][0][j2]);
+                                const float gf = e ? __high2float(gt[s][1][j2]) : __low2float(gt[s][1][j2]);
+                                const float gg = e ? __high2float(gt[s][2][j2]) : __low2float(gt[s][2][j2]);
+                                const float go = e ? __high2float(gt[s][3][j2]) : __low2float(gt[s][3][j2]);
+                                float dht = dh[s][j];
+                                if (step > 0) dht += sAcc[b * 17 + 4 * uq + j];
+                                const float tc = tanh_f(ct[s][j]);
+                                const float dc = dcs[s][j] + dht * go * (1.f - tc * tc);
                                 da[3][e] = dht * tc * go * (1.f - go);
                                 da[0][e] = dc * gg * gi * (1.f - gi);
                                 da[2][e] = dc * gi * (1.f - gg * gg);
-                                da[1][e] = dc * cp[j] * gf * (1.f - gf);
-                                dcs[j] = dc * gf;
+                                da[1][e] = dc * cp[s][j] * gf * (1.f - gf);
+                                dcs[s][j] = dc * gf;
                             }
 #pragma unroll
                             for (int g = 0; g < 4; ++g)
-                                out[g][j2] = __floats2half2_rn(fminf(fmaxf(da[g][0], -65504.f), 65504.f), fminf(fmaxf(da[g][1], -65504.f), 65504.f));
+                                out[g][j2] = __floats2half2_rn(fminf(fmaxf(da[g][0], -65504.f), 65504.f),
+                                                               fminf(fmaxf(da[g][1], -65504.f), 65504.f));
                         }
                     } else {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g)
+                        for (int g = 0; g < 4; ++g) { out[g][0] = __floats2half2_rn(0.f, 0.f); out[g][1] = out[g][0]; }
 #pragma unroll
-                            for (int j2 = 0; j2 < BWD_UNITS / 2; ++j2) out[g][j2] = __floats2half2_rn(0.f, 0.f);
-#pragma unroll
-                        for (int j = 0; j < BWD_UNITS; ++j) dcs[j] = 0.f;
+                        for (int j = 0; j < 4; ++j) dcs[s][j] = 0.f;
                     }
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint4* dst = reinterpret_cast<uint4*>(p.dG + r * LG + g * LH + u0);
-                        dst[0] = *reinterpret_cast<uint4*>(&out[g][0]);
-                        dst[1] = *reinterpret_cast<uint4*>(&out[g][4]);
-                    }
-                }
-                __syncwarp();
-                if (lane < 4) {
-                    __threadfence();
-                    red_release_add(&p.flags[t * BWD_NCH + lane * 16 + cta / 4], 1);
+                    for (int g = 0; g < 4; ++g)
+                        *reinterpret_cast<uint2*>(p.dG + r * LG + g * LH + u0 + 4 * uq) = *reinterpret_cast<uint2*>(&out[g][0]);
                 }
             }
+            epi_bar();                                        // every dG_t store of this CTA precedes the releases
+            if (et < 4) red_release_add(&p.flags[t * BWD_NCH + et * 16 + cta / 4], 1);   // one release per gate chunk
         }
     }
     tc_fence_before();
@@ -426,26 +477,43 @@ static int smem_optin() {
     return v;
 }
 
+PFN_encodeTiled get_tma_encoder();     // gemm.cu
+
+// 3-D view of a row-major [rows, 64*nchunks] 16-bit tensor as {64 elems, rows, chunks}; box {64, box_rows, box_chunks}.
+// The shared-memory image of one box is chunk-major: [chunk][row][128 B], SWIZZLE_128B -- i.e. `box_chunks`
+// consecutive K-major UMMA tiles.
+static int make_tmap_chunks(CUtensorMap* out, const void* ptr, long long rows, int nchunks, long long ld, int box_rows,
+                            int box_chunks) {
+    PFN_encodeTiled enc = get_tma_encoder();
+    if (!enc) return -1;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) return ft_set_error("TMA operand must be 16-byte aligned with a 16-byte-multiple row pitch");
+    cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(nchunks)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld * 2), 128};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_chunks)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ft_set_error("cuTensorMapEncodeTiled (3-D chunk view) failed");
+    return 0;
+}
+
 int launch_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const int* lens, void* hseq16, long long ldh,
                     void* gates16, float* cstate, float* h32, long long ldh32, int* flags, cudaStream_t st) {
     if (T <= 0 || B <= 0) return 0;
-    if (B > 128) return ft_set_error("lstm_fwd: batch > 128 per call not supported");
+    if (B > 64) return ft_set_error("lstm_fwd: batch > 64 per call not supported (split the batch)");
     LstmFwdParams p;
     p.T = T; p.B = B; p.Bbox = (B + 7) & ~7;
     const int slot = p.Bbox * 128;
-    const int fixed = FWD_W_BYTES + 1024 + 1024;                  // W + barriers + align
-    int nslot = (smem_optin() - fixed) / slot;
-    if (nslot > 16) nslot = 16;
-    if (nslot < 2) return ft_set_error("lstm_fwd: not enough shared memory for the h ring");
-    p.nslot = nslot;
+    const int smem = FWD_NCH * slot + FWD_W_BYTES + 128 * 33 * 4 + 256 + 1024;
+    if (smem > smem_optin()) return ft_set_error("lstm_fwd: not enough shared memory");
     p.xproj = xproj; p.lens = lens; p.hseq = static_cast<__half*>(hseq16); p.ldh = ldh;
     p.gates = static_cast<__half*>(gates16); p.cstate = cstate; p.h32 = h32; p.ldh32 = ldh32;
     p.flags = flags; p.status = ft_status_word(); p.trace = g_lstm_trace;
     CUtensorMap tmW, tmH;
     if (make_tmap_2d(&tmW, whh16, FMT_F16, LG, LH, LH, KCH, FWD_UNITS)) return -1;
-    if (make_tmap_2d(&tmH, hseq16, FMT_F16, static_cast<long long>(T) * B, LH, ldh, KCH, p.Bbox)) return -1;
+    if (make_tmap_chunks(&tmH, hseq16, static_cast<long long>(T) * B, FWD_NCH, ldh, p.Bbox, FWD_GS)) return -1;
     if (cudaMemsetAsync(flags, 0, sizeof(int) * T * FWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_fwd: memset failed");
-    const int smem = nslot * slot + fixed;
     cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     TimeScope ts("lstm_fwd", T, B, 0, st);
     void* args[] = {&tmW, &tmH, &p};
@@ -459,22 +527,25 @@ int launch_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const i
 int launch_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void* whhT16, const void* gates16,
                     const float* cstate, const int* lens, void* dG16, int* flags, cudaStream_t st) {
     if (T <= 0 || B <= 0) return 0;
-    if (B > 128) return ft_set_error("lstm_bwd: batch > 128 per call not supported");
+    if (B > 64) return ft_set_error("lstm_bwd: batch > 64 per call not supported (split the batch)");
     LstmBwdParams p;
     p.T = T; p.B = B; p.Bbox = (B + 7) & ~7;
     const int slot = p.Bbox * 128;
-    const int fixed = BWD_W_BYTES + 1024 + 1024;
-    int nslot = (smem_optin() - fixed) / slot;          // over-read of the last slot lands in sW (128 KB >= 16 KB)
-    if (nslot > 32) nslot = 32;
-    if (nslot < 2) return ft_set_error("lstm_bwd: not enough shared memory for the dG ring");
-    p.nslot = nslot;
+    const int fixed = BWD_W_BYTES + 128 * 17 * 4 + 512 + 1024;
+    const int avail = smem_optin() - fixed;
+    int gs = 8;
+    while (gs > 1 && 2 * gs * slot > avail) gs >>= 1;          // at least a 2-deep ring of groups
+    int nring = avail / (gs * slot);
+    if (nring > 4) nring = 4;
+    if (nring < 2) return ft_set_error("lstm_bwd: not enough shared memory for the dG ring");
+    p.gs = gs; p.ng = BWD_NCH / gs; p.nring = nring;
     p.dh_ext = dh_ext; p.ldd = ldd; p.gates = static_cast<const __half*>(gates16); p.cstate = cstate; p.lens = lens;
     p.dG = static_cast<__half*>(dG16); p.flags = flags; p.status = ft_status_word(); p.trace = nullptr;
     CUtensorMap tmWT, tmG;
     if (make_tmap_2d(&tmWT, whhT16, FMT_F16, LH, LG, LG, KCH, BWD_UNITS)) return -1;
-    if (make_tmap_2d(&tmG, dG16, FMT_F16, static_cast<long long>(T) * B, LG, LG, KCH, p.Bbox)) return -1;
+    if (make_tmap_chunks(&tmG, dG16, static_cast<long long>(T) * B, BWD_NCH, LG, p.Bbox, gs)) return -1;
     if (cudaMemsetAsync(flags, 0, sizeof(int) * T * BWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_bwd: memset failed");
-    const int smem = nslot * slot + fixed;
+    const int smem = nring * gs * slot + fixed;
     cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     TimeScope ts("lstm_bwd", T, B, 0, st);
     void* args[] = {&tmWT, &tmG, &p};
