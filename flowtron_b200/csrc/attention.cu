@@ -289,17 +289,15 @@ struct AttnBwdParams {
     float* dv;                            // [A] accumulated
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(AT_THREADS, 2)
 attn_bwd_kernel(AttnBwdParams p) {
     extern __shared__ float smf[];
-    const int Lpad = ((p.L + AT_LB - 1) / AT_LB) * AT_LB;
-    const int SE_LD = Lpad + 4;
-    float* sQ = smf;                                  // [AT_AC][SQ_LD]
-    float* sK = sQ + AT_AC * SQ_LD;                   // [AT_AC][SK_LD]
+    const int Lr = (p.L + 31) & ~31;
+    const int SE_LD = Lr + 4;
+    float* sQ = smf;                                  // [AT_AC][SQ_LD]   (phase 3: e^{2q} as [AT_TT][65])
+    float* sK = sQ + AT_AC * SQ_LD;                   // [AT_AC][SK_LD]   (phase 3: e^{2k} as [AT_LB][65])
     float* sD = sK + AT_AC * SK_LD;                   // [AT_TT][SE_LD]  dattn -> de
-    float* sdK = sD + AT_TT * SE_LD;                  // [AT_LB][AT_AC+1] per-chunk dK accumulator
-    float* sdQ = sdK + AT_LB * (AT_AC + 1);           // [AT_TT][AT_AC+1]
-    float* sv = sdQ + AT_TT * (AT_AC + 1);            // [A]
+    float* sv = sD + AT_TT * SE_LD;                   // [A]
     float* sdv = sv + p.A;                            // [A]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -308,7 +306,7 @@ attn_bwd_kernel(AttnBwdParams p) {
     const int in_len = p.in_lens ? p.in_lens[b] : p.L;
     const int nrows = min(AT_TT, p.T - t0);
     const int ty = tid >> 4, tx = tid & 15;
-    const int nlb = Lpad / AT_LB;
+    const int nlb = (p.L + AT_LB - 1) / AT_LB;
 
     if (t0 >= out_len) {                              // forward wrote constants here: no gradient
         for (int i = tid; i < nrows * p.A; i += AT_THREADS) {
@@ -371,7 +369,10 @@ attn_bwd_kernel(AttnBwdParams p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) sD[(4 * ty + i) * SE_LD + l0 + tx + 16 * j] += d[i][j];
+                for (int j = 0; j < 4; ++j) {
+                    const int col = l0 + tx + 16 * j;
+                    if (col < Lr) sD[(4 * ty + i) * SE_LD + col] += d[i][j];
+                }
             // dV[l, a] += sum_t attn[t,l] dctx[t,a]: thread -> keys l0 + 4*ty.. +3, channels 4*tx..+3
             float g[4][4];
 #pragma unroll
@@ -408,7 +409,7 @@ attn_bwd_kernel(AttnBwdParams p) {
         const float* at = attn_b + static_cast<long long>(tt) * p.L;
         const long long o0 = (static_cast<long long>(b) * p.T + t) * p.L;
         if (t >= out_len) {
-            for (int l = lane; l < Lpad; l += 32) d[l] = 0.f;
+            for (int l = lane; l < Lr; l += 32) d[l] = 0.f;
             continue;
         }
         if (!p.has_prior) {
@@ -423,7 +424,7 @@ attn_bwd_kernel(AttnBwdParams p) {
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-            for (int l = lane; l < Lpad; l += 32) d[l] = (l < in_len) ? at[l] * (d[l] - dot) * p.inv_temperature : 0.f;
+            for (int l = lane; l < Lr; l += 32) d[l] = (l < in_len) ? at[l] * (d[l] - dot) * p.inv_temperature : 0.f;
         } else {
             // attn = softmax(mask(lp)), lp = log(p+1e-20) + log(prior+1e-20), p = softmax(e)
             float dot = 0.f;
@@ -446,7 +447,7 @@ attn_bwd_kernel(AttnBwdParams p) {
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) dot2 += __shfl_xor_sync(0xffffffffu, dot2, o);
-            for (int l = lane; l < Lpad; l += 32) {
+            for (int l = lane; l < Lr; l += 32) {
                 const float pr = (l < p.L) ? p.p_save[o0 + l] : 0.f;
                 d[l] = (l < in_len) ? pr * (d[l] - dot2) * p.inv_temperature : 0.f;
             }
@@ -454,92 +455,102 @@ attn_bwd_kernel(AttnBwdParams p) {
     }
     __syncthreads();
 
-    // ---------------------------------------------------------------- 3. score backward with tanh recompute
-    for (int lb = 0; lb < nlb; ++lb) {
-        float de[4][8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) de[i][j] = sD[(4 * ty + i) * SE_LD + lb * AT_LB + tx + 16 * j];
+    // ---------------------------------------------------------------- 3. score backward, tanh recomputed
+    // Two reduction-free passes per (channel chunk, key block): in pass A a thread owns (16 rows, 1 channel) and
+    // runs over the keys (-> dQ, dv); in pass B it owns (16 keys, 1 channel) and runs over the rows (-> dK).
+    // Each pass re-evaluates r = 1/(e^{2q} e^{2k} + 1) (tanh = 1 - 2r, 1 - tanh^2 = 4 r (1 - r)); the first version
+    // evaluated it once but paid ~30 shuffles + 8 shared atomics per 32 elements to reduce dQ/dK across threads.
+    {
+        constexpr int QP = 65;                        // [row][channel] pitch: lanes walk channels -> conflict-free
+        float* sQt = sQ;                              // [AT_TT][QP]
+        float* sKt = sK;                              // [AT_LB][QP]
+        const int a_l = tid & 63, grp = tid >> 6;     // channel lane; row group (pass A) / key group (pass B)
         for (int ac = 0; ac < p.A; ac += AT_AC) {
+            float dq[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dq[i] = 0.f;
+            float dva = 0.f;
+            const bool a_ok = ac + a_l < p.A;
             __syncthreads();
-            {
-                const int aa = tid & 63;
-                for (int tt = tid >> 6; tt < AT_TT; tt += AT_THREADS / 64) {
-                    float q = 0.f;
-                    if (tt < nrows && ac + aa < p.A) q = p.Q[(static_cast<long long>(t0 + tt) * p.B + b) * p.ldq + ac + aa];
-                    sQ[aa * SQ_LD + tt] = exp2x_clamped(q);
-                }
-                for (int ll = tid >> 6; ll < AT_LB; ll += AT_THREADS / 64) {
+            for (int i = tid; i < AT_TT * AT_AC; i += AT_THREADS) {
+                const int tt = i >> 6, aa = i & 63;
+                float q = 0.f;
+                if (tt < nrows && ac + aa < p.A) q = p.Q[(static_cast<long long>(t0 + tt) * p.B + b) * p.ldq + ac + aa];
+                sQt[tt * QP + aa] = exp2x_clamped(q);
+            }
+            for (int lb = 0; lb < nlb; ++lb) {
+                const int nl = min(AT_LB, p.L - lb * AT_LB);
+                __syncthreads();
+                for (int i = tid; i < AT_LB * AT_AC; i += AT_THREADS) {
+                    const int ll = i >> 6, aa = i & 63;
                     const int l = lb * AT_LB + ll;
                     float k = 0.f;
                     if (l < p.L && ac + aa < p.A) k = p.K[(static_cast<long long>(l) * p.B + b) * p.ldk + ac + aa];
-                    sK[aa * SK_LD + ll] = exp2x_clamped(k);
+                    sKt[ll * QP + aa] = exp2x_clamped(k);
                 }
-                for (int i = tid; i < AT_LB * (AT_AC + 1); i += AT_THREADS) sdK[i] = 0.f;
-                for (int i = tid; i < AT_TT * (AT_AC + 1); i += AT_THREADS) sdQ[i] = 0.f;
-            }
-            __syncthreads();
-            const int na = min(AT_AC, p.A - ac);
-            for (int a = 0; a < na; ++a) {
-                const float4 q4 = *reinterpret_cast<const float4*>(&sQ[a * SQ_LD + 4 * ty]);
-                const float va = sv[ac + a];
-                float k[8];
+                __syncthreads();
+                {   // ---- pass A: dQ[t, a] += sum_l de[t,l] r (1 - r) ;  dv[a] += sum de (1 - 2 r)
+                    float eq[16];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) k[j] = sK[a * SK_LD + tx + 16 * j];
-                const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-                float dq[4] = {0.f, 0.f, 0.f, 0.f}, dk[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dva = 0.f;
+                    for (int i = 0; i < 16; ++i) eq[i] = sQt[(grp * 16 + i) * QP + a_l];
+                    const int nl4 = (nl + 3) & ~3;    // de is 0 in [L, Lr)
+                    for (int l = 0; l < nl4; l += 4) {
+                        float ek[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                        for (int j = 0; j < 4; ++j) ek[j] = sKt[(l + j) * QP + a_l];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float r = fast_rcp(fmaf(q[i], k[j], 1.0f));        // tanh = 1 - 2r ; 1 - tanh^2 = 4 r (1 - r)
-                        const float w = de[i][j] * (4.f * r * (1.f - r));
-                        dq[i] += w;
-                        dk[j] += w;
-                        dva = fmaf(de[i][j], 1.f - 2.f * r, dva);
+                        for (int i = 0; i < 16; ++i) {
+                            const float4 d4 = *reinterpret_cast<const float4*>(&sD[(grp * 16 + i) * SE_LD + lb * AT_LB + l]);
+                            const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float r = fast_rcp(fmaf(eq[i], ek[j], 1.0f));
+                                dq[i] = fmaf(dd[j], fmaf(-r, r, r), dq[i]);
+                                dva = fmaf(dd[j], fmaf(-2.f, r, 1.f), dva);
+                            }
+                        }
                     }
-                // dQ[t,a] += va * sum_l w : reduce over the 16 tx lanes (xor 1,2,4,8 stays inside a 16-lane half)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float x = dq[i] * va;
-#pragma unroll
-                    for (int o = 8; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-                    dq[i] = x;
                 }
-                if (tx == 0) {
+                // ---- pass B: dK[l, a] += sum_t de[t,l] r (1 - r)   (two 64-key halves, 16 keys per thread)
+                for (int half = 0; half < 2; ++half) {
+                    const int lo = half * 64 + grp * 16;
+                    if (lo >= nl) continue;           // warp-uniform
+                    float ek[16], dk[16];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) sdQ[(4 * ty + i) * (AT_AC + 1) + a] += dq[i];     // one owner per (row, a)
+                    for (int j = 0; j < 16; ++j) { ek[j] = sKt[(lo + j) * QP + a_l]; dk[j] = 0.f; }
+                    for (int tt = 0; tt < nrows; ++tt) {
+                        const float eqv = sQt[tt * QP + a_l];
+                        const float* drow = sD + tt * SE_LD + lb * AT_LB + lo;
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 d4 = *reinterpret_cast<const float4*>(drow + 4 * j4);
+                            const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float r = fast_rcp(fmaf(eqv, ek[4 * j4 + e], 1.0f));
+                                dk[4 * j4 + e] = fmaf(dd[e], fmaf(-r, r, r), dk[4 * j4 + e]);
+                            }
+                        }
+                    }
+                    if (a_ok) {
+                        const float s4 = 4.f * sv[ac + a_l];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int l = lb * AT_LB + lo + j;
+                            const float x = dk[j] * s4;
+                            if (l < p.L && x != 0.f) atomicAdd(p.dK + (static_cast<long long>(l) * p.B + b) * p.lddk + ac + a_l, x);
+                        }
+                    }
                 }
-                // dK[l,a] += va * sum_t w : sum the two ty halves in-warp, then shared atomics across the 8 warps
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float x = dk[j] * va;
-                    x += __shfl_xor_sync(0xffffffffu, x, 16);
-                    if (lane < 16) atomicAdd(&sdK[(tx + 16 * j) * (AT_AC + 1) + a], x);
-                }
-#pragma unroll
-                for (int o = 16; o; o >>= 1) dva += __shfl_xor_sync(0xffffffffu, dva, o);
-                if (lane == 0) atomicAdd(&sdv[ac + a], dva);
             }
-            __syncthreads();
-            // flush dK chunk (atomics across t-tiles)
-            for (int i = tid; i < AT_LB * AT_AC; i += AT_THREADS) {
-                const int ll = i / AT_AC, aa = i % AT_AC;
-                const int l = lb * AT_LB + ll;
-                if (l < p.L && ac + aa < p.A) {
-                    const float x = sdK[ll * (AT_AC + 1) + aa];
-                    if (x != 0.f) atomicAdd(p.dK + (static_cast<long long>(l) * p.B + b) * p.lddk + ac + aa, x);
+            if (a_ok) {
+                const float s4 = 4.f * sv[ac + a_l];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int tt = grp * 16 + i;
+                    if (tt < nrows) p.dQ[(static_cast<long long>(t0 + tt) * p.B + b) * p.lddq + ac + a_l] = dq[i] * s4;
                 }
-            }
-            // dQ rows are owned by this CTA: first key block stores, later key blocks accumulate (same thread, same element)
-            for (int i = tid; i < AT_TT * AT_AC; i += AT_THREADS) {
-                const int tt = i / AT_AC, aa = i % AT_AC;
-                if (tt < nrows && ac + aa < p.A) {
-                    float* dst = p.dQ + (static_cast<long long>(t0 + tt) * p.B + b) * p.lddq + ac + aa;
-                    const float x = sdQ[tt * (AT_AC + 1) + aa];
-                    *dst = (lb == 0) ? x : (*dst + x);
-                }
+                atomicAdd(&sdv[ac + a_l], dva);
             }
         }
     }
@@ -556,9 +567,8 @@ static size_t attn_fwd_smem(int L, int A) {
     return sizeof(float) * (static_cast<size_t>(AT_AC) * SQ_LD + AT_AC * SK_LD + AT_TT * (Lr + 4) + A) + 64;
 }
 static size_t attn_bwd_smem(int L, int A) {
-    const int Lpad = ((L + AT_LB - 1) / AT_LB) * AT_LB;
-    return sizeof(float) * (static_cast<size_t>(AT_AC) * SQ_LD + AT_AC * SK_LD + AT_TT * (Lpad + 4) +
-                            AT_LB * (AT_AC + 1) + AT_TT * (AT_AC + 1) + 2 * A) + 64;
+    const int Lr = (L + 31) & ~31;
+    return sizeof(float) * (static_cast<size_t>(AT_AC) * SQ_LD + AT_AC * SK_LD + AT_TT * (Lr + 4) + 2 * A) + 64;
 }
 
 int launch_attn_fwd(const AttnFwdArgs& a, cudaStream_t st) {

@@ -127,9 +127,13 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         if (lane == 0) {
             mbar_wait(wbar, 0, p.status, 203);
             const uint32_t idesc = umma_idesc(128, FWD_N, FMT_F16, FMT_F16, 0, 0);
-            const uint32_t w0 = smem_u32(sW), a0 = smem_u32(sA);
+            // descriptors advance by plain 64-bit adds on the (address >> 4) field: building each of the 64
+            // per-step descriptors from scratch made MMA *issue* (one thread) cost 2 us per step
+            const uint64_t da_base = umma_smem_desc(smem_u32(sA), 16, 1024), db_base = umma_smem_desc(smem_u32(sW), 16, 1024);
+            const uint64_t a_chunk = static_cast<uint64_t>(slot_bytes >> 4), b_chunk = (FWD_N * 128) >> 4;
             for (int t = 1; t < p.T; ++t) {
                 const int ph = (t - 1) & 1;
+                uint64_t da = da_base, db = db_base;
 #pragma unroll
                 for (int g = 0; g < FWD_NG; ++g) {
                     mbar_wait(&full[g], ph, p.status, 204);
@@ -137,13 +141,11 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     if (g == 0) FT_TRACE(p, t, 2);
 #pragma unroll
                     for (int c = 0; c < FWD_GS; ++c) {
-                        const int kc = g * FWD_GS + c;
 #pragma unroll
-                        for (int k = 0; k < KCH / 16; ++k) {
-                            const uint64_t da = umma_smem_desc(a0 + kc * slot_bytes + k * 32, 16, 1024);
-                            const uint64_t db = umma_smem_desc(w0 + kc * (FWD_N * 128) + k * 32, 16, 1024);
-                            umma_f16(tmem_base, da, db, idesc, (kc | k) != 0);
-                        }
+                        for (int k = 0; k < KCH / 16; ++k)
+                            umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (g | c | k) != 0);
+                        da += a_chunk;
+                        db += b_chunk;
                     }
                 }
                 FT_TRACE(p, t, 3);
@@ -334,23 +336,30 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
         if (lane == 0) {
             mbar_wait(wbar, 0, p.status, 213);
             const uint32_t idesc = umma_idesc(128, BWD_UNITS, FMT_F16, FMT_F16, 0, 0);
-            const uint32_t w0 = smem_u32(sW), r0 = smem_u32(ring);
+            const uint64_t da_ring = umma_smem_desc(smem_u32(ring), 16, 1024), db_base = umma_smem_desc(smem_u32(sW), 16, 1024);
+            const uint64_t a_chunk = static_cast<uint64_t>(slot_bytes >> 4), a_group = static_cast<uint64_t>(group_bytes >> 4);
+            const uint64_t b_chunk = (BWD_UNITS * 128) >> 4;
             int s = 0, ph = 0;
+            uint64_t da_slot = da_ring;
             for (int t = p.T - 2; t >= 0; --t) {
+                uint64_t db = db_base;
+                uint32_t acc = 0;
                 for (int g = 0; g < p.ng; ++g) {
                     mbar_wait(&full[s], ph, p.status, 214);
                     tc_fence_after();
+                    uint64_t da = da_slot;
                     for (int c = 0; c < p.gs; ++c) {
-                        const int kc = g * p.gs + c;
-#pragma unroll
-                        for (int k = 0; k < KCH / 16; ++k) {
-                            const uint64_t da = umma_smem_desc(r0 + s * group_bytes + c * slot_bytes + k * 32, 16, 1024);
-                            const uint64_t db = umma_smem_desc(w0 + kc * (BWD_UNITS * 128) + k * 32, 16, 1024);
-                            umma_f16(tmem_base, da, db, idesc, (kc | k) != 0);
-                        }
+                        umma_f16(tmem_base, da, db, idesc, acc);
+                        umma_f16(tmem_base, da + 2, db + 2, idesc, 1);
+                        umma_f16(tmem_base, da + 4, db + 4, idesc, 1);
+                        umma_f16(tmem_base, da + 6, db + 6, idesc, 1);
+                        acc = 1;
+                        da += a_chunk;
+                        db += b_chunk;
                     }
                     umma_commit(&empty[s]);
-                    if (++s == p.nring) { s = 0; ph ^= 1; }
+                    da_slot += a_group;
+                    if (++s == p.nring) { s = 0; ph ^= 1; da_slot = da_ring; }
                 }
                 umma_commit(accum_full);
             }
