@@ -24,6 +24,8 @@
 // History (profiles/, tools/trace_lstm.py): v1 polled the chunk flags and issued 16 (64) 2-D TMA loads
 // serially from one thread: 4 us of an 8.9 us forward step was TMA issue, 0.85 us a single-warp epilogue,
 // 1 us fence+release behind 112 B/lane of stores.
+#include <cstdlib>
+
 #include "ptx.cuh"
 #include "ft_internal.h"
 
@@ -50,7 +52,6 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: 
 // ------------------------------------------------------------------------------------------- forward
 constexpr int FWD_CTAS = 128, FWD_UNITS = 8, FWD_N = 32, FWD_NCH = LH / KCH;     // 16 chunks / step
 constexpr int FWD_W_BYTES = FWD_NCH * FWD_N * 128;                                 // 64 KB
-constexpr int FWD_GS = 8, FWD_NG = FWD_NCH / FWD_GS;                               // 2 TMA groups / step
 
 struct LstmFwdParams {
     int T, B, Bbox;
@@ -65,8 +66,10 @@ struct LstmFwdParams {
     long long* trace;          // optional [T][8] clock64 stamps of CTA 0 (debug/profiling), or null
 };
 
+template <int FWD_GS>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, LstmFwdParams p) {
+    constexpr int FWD_NG = FWD_NCH / FWD_GS;                     // TMA groups per step
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int slot_bytes = p.Bbox * 128;
@@ -74,10 +77,10 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     uint8_t* sW = smem + FWD_NCH * slot_bytes;                   // the M=128 over-read of the last chunks lands here
     float* sAcc = reinterpret_cast<float*>(sW + FWD_W_BYTES);    // [128 rows][33]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + 128 * 33);
-    uint64_t* full = bars;                       // [FWD_NG]
-    uint64_t* wbar = bars + 4;
-    uint64_t* accum_full = bars + 5;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t* full = bars;                       // [FWD_NG] (<= 16)
+    uint64_t* wbar = bars + 16;
+    uint64_t* accum_full = bars + 17;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x;
@@ -91,7 +94,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         mbar_init(accum_full, 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<32>(tmem_slot);
+    if (warp == 1) tmem_alloc<128>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -113,7 +116,8 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             __syncwarp();
             if (lane == 0) {
                 FT_TRACE(p, t, 0);
-                fence_proxy_async();               // generic-proxy writes of other SMs -> async-proxy (TMA) reads
+                fence_proxy_async_global();        // generic-proxy writes of other SMs -> async-proxy (TMA) reads
+                FT_TRACE(p, t, 6);
 #pragma unroll
                 for (int g = 0; g < FWD_NG; ++g) {
                     mbar_expect_tx(&full[g], FWD_GS * slot_bytes);
@@ -139,11 +143,15 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     mbar_wait(&full[g], ph, p.status, 204);
                     tc_fence_after();
                     if (g == 0) FT_TRACE(p, t, 2);
+                    if (g == FWD_NG - 1) FT_TRACE(p, t, 5);
 #pragma unroll
                     for (int c = 0; c < FWD_GS; ++c) {
+                        // consecutive MMAs into ONE accumulator serialise on the D read-modify-write (~60 clk each for
+                        // this tiny N=32 tile: 64 MMAs = 2 us/step); the 4 k-steps of a chunk therefore go to 4
+                        // independent TMEM accumulators that the epilogue sums
 #pragma unroll
                         for (int k = 0; k < KCH / 16; ++k)
-                            umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (g | c | k) != 0);
+                            umma_f16(tmem_base + k * FWD_N, da + 2 * k, db + 2 * k, idesc, (g | c) != 0);
                         da += a_chunk;
                         db += b_chunk;
                     }
@@ -189,6 +197,14 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     if (et == 64) FT_TRACE(p, t, 4);          // warp 4 == quadrant 0
                     tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16), acc);
                     tmem_ld_wait();
+#pragma unroll
+                    for (int a = 1; a < 4; ++a) {             // sum the 4 partial accumulators
+                        float part[32];
+                        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * FWD_N, part);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] += part[j];
+                    }
                     tc_fence_before();
                     float* dst = sAcc + (q * 32 + lane) * 33;
 #pragma unroll
@@ -229,7 +245,6 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             }
             epi_bar();                                        // all h_t stores of this CTA precede the release
             if (et == 0) {
-                FT_TRACE(p, t, 5);
                 red_release_add(&p.flags[t * FWD_NCH + cta / 8], 1);      // cumulative release (gpu scope)
                 FT_TRACE(p, t, 7);
             }
@@ -255,7 +270,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<32>(tmem_base);
+    if (warp == 1) tmem_dealloc<128>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------- backward
@@ -304,7 +319,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
         mbar_init(accum_full, 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<32>(tmem_slot);
+    if (warp == 1) tmem_alloc<128>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -322,7 +337,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
                 wait_flag_ge(&p.flags[(t + 1) * BWD_NCH + c], 4, p.status, 212);
             __syncwarp();
             if (lane == 0) {
-                fence_proxy_async();
+                fence_proxy_async_global();
                 for (int g = 0; g < p.ng; ++g) {
                     mbar_wait(&empty[s], ph ^ 1, p.status, 211);
                     mbar_expect_tx(&full[s], group_bytes);
@@ -348,14 +363,16 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
                     mbar_wait(&full[s], ph, p.status, 214);
                     tc_fence_after();
                     uint64_t da = da_slot;
-                    for (int c = 0; c < p.gs; ++c) {
-                        umma_f16(tmem_base, da, db, idesc, acc);
-                        umma_f16(tmem_base, da + 2, db + 2, idesc, 1);
-                        umma_f16(tmem_base, da + 4, db + 4, idesc, 1);
-                        umma_f16(tmem_base, da + 6, db + 6, idesc, 1);
+                    for (int c = 0; c < p.gs; c += 2) {       // 8 independent accumulators (see the forward kernel)
+#pragma unroll
+                        for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_f16(tmem_base + (cc * 4 + k) * BWD_UNITS, da + 2 * k, db + 2 * k, idesc, acc);
+                            da += a_chunk;
+                            db += b_chunk;
+                        }
                         acc = 1;
-                        da += a_chunk;
-                        db += b_chunk;
                     }
                     umma_commit(&empty[s]);
                     da_slot += a_group;
@@ -415,6 +432,14 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
                     tc_fence_after();
                     tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16), acc);
                     tmem_ld_wait();
+#pragma unroll
+                    for (int a = 1; a < 8; ++a) {
+                        float part[16];
+                        tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BWD_UNITS, part);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[j] += part[j];
+                    }
                     tc_fence_before();
                     float* dst = sAcc + (q * 32 + lane) * 17;
 #pragma unroll
@@ -472,7 +497,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<32>(tmem_base);
+    if (warp == 1) tmem_dealloc<128>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------- host
@@ -521,13 +546,16 @@ int launch_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const i
     p.flags = flags; p.status = ft_status_word(); p.trace = g_lstm_trace;
     CUtensorMap tmW, tmH;
     if (make_tmap_2d(&tmW, whh16, FMT_F16, LG, LH, LH, KCH, FWD_UNITS)) return -1;
-    if (make_tmap_chunks(&tmH, hseq16, static_cast<long long>(T) * B, FWD_NCH, ldh, p.Bbox, FWD_GS)) return -1;
+    static int gs = 0;
+    if (!gs) { const char* e = getenv("FT_LSTM_GS"); gs = e ? atoi(e) : 8; if (gs != 2 && gs != 4 && gs != 8 && gs != 16) gs = 8; }
+    if (make_tmap_chunks(&tmH, hseq16, static_cast<long long>(T) * B, FWD_NCH, ldh, p.Bbox, gs)) return -1;
     if (cudaMemsetAsync(flags, 0, sizeof(int) * T * FWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_fwd: memset failed");
-    cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    void* fn = gs == 2 ? reinterpret_cast<void*>(lstm_fwd_kernel<2>) : gs == 4 ? reinterpret_cast<void*>(lstm_fwd_kernel<4>)
+             : gs == 16 ? reinterpret_cast<void*>(lstm_fwd_kernel<16>) : reinterpret_cast<void*>(lstm_fwd_kernel<8>);
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     TimeScope ts("lstm_fwd", T, B, 0, st);
     void* args[] = {&tmW, &tmH, &p};
-    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_fwd_kernel), dim3(FWD_CTAS),
-                                                dim3(LSTM_THREADS), args, smem, st);
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(FWD_CTAS), dim3(LSTM_THREADS), args, smem, st);
     if (e != cudaSuccess) return ft_set_error(cudaGetErrorString(e));
     ft_count_launch(1);
     return ft_check_launch("lstm_fwd_kernel");
@@ -543,7 +571,7 @@ int launch_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void
     const int fixed = BWD_W_BYTES + 128 * 17 * 4 + 512 + 1024;
     const int avail = smem_optin() - fixed;
     int gs = 8;
-    while (gs > 1 && 2 * gs * slot > avail) gs >>= 1;          // at least a 2-deep ring of groups
+    while (gs > 2 && 2 * gs * slot > avail) gs >>= 1;          // at least a 2-deep ring of groups (gs stays even)
     int nring = avail / (gs * slot);
     if (nring > 4) nring = 4;
     if (nring < 2) return ft_set_error("lstm_bwd: not enough shared memory for the dG ring");

@@ -75,6 +75,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* s
 __device__ __forceinline__ void fence_proxy_async() {          // generic <-> async proxy (all spaces)
     asm volatile("fence.proxy.async;" ::: "memory");
 }
+__device__ __forceinline__ void fence_proxy_async_global() {   // generic <-> async proxy, global state space only
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

@@ -27,7 +27,7 @@ def main():
         print(f"run {it}: {e0.elapsed_time(e1) * 1e3 / T:.2f} us/step")
     L.ft_debug_set_lstm_trace(None)
     tr = trace.cpu().double()[50:350]
-    names = ["flags_seen", "tma_issued", "first_group_landed", "all_landed+mma_issued", "accum_done", "h_stored(all warps)", "-", "release_issued"]
+    names = ["flags_seen", "tma_issued", "first_group_landed", "all_mma_issued", "accum_done(epi)", "last_group_landed", "proxy_fence_done", "release_issued"]
     period = (tr[1:, 0] - tr[:-1, 0]).mean().item()
     print(f"step period: {period:.0f} clk = {period / 1.965e3:.2f} us @1.965GHz")
     base = tr[:, 0:1]
