@@ -72,15 +72,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Producer / MMA warps run their loops warp-uniformly and only the instruction issue is predicated on one elected
+    // lane: operands of UTMALDG / UTCHMMA must live in uniform registers, and computing them inside an `if (lane == 0)`
+    // region makes the compiler wrap every issue in an R2UR + ELECT "waterfall" loop (~60 clk per MMA, measured).
     if (warp == 0) {
-        if (lane == 0) {
-            // ------------------------------------------------ TMA producer
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1, p.status, 101);
+        // ------------------------------------------------ TMA producer
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1, p.status, 101);
+            uint8_t* a = sA + s * TILE_BYTES;
+            uint8_t* b = sB + s * TILE_BYTES;
+            if (elect_one()) {
                 mbar_expect_tx(&full[s], 2 * TILE_BYTES);
-                uint8_t* a = sA + s * TILE_BYTES;
-                uint8_t* b = sB + s * TILE_BYTES;
                 if (!p.a_mn) {
                     tma_load_2d(a, &tmA, &full[s], kb * BK, tile_m * BM);             // box {BK, 128 rows}
                 } else {                                                                // box {BK mn-elems, BK k-rows} x (BM/BK)
@@ -94,32 +97,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         tma_load_2d(b + j * (BK * 128), &tmB, &full[s], tile_n * BN + j * BK, kb * BK);
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------ MMA issuer (single thread)
-            const uint32_t idesc = umma_idesc(BM, BN, p.a_fmt, p.b_fmt, p.a_mn, p.b_mn);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-                mbar_wait(&full[s], ph, p.status, 102);
-                tc_fence_after();
-                const uint32_t a0 = smem_u32(sA + s * TILE_BYTES), b0 = smem_u32(sB + s * TILE_BYTES);
+        // ------------------------------------------------ MMA issuer (one elected lane issues)
+        const uint32_t idesc = umma_idesc(BM, BN, p.a_fmt, p.b_fmt, p.a_mn, p.b_mn);
+        const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
+        // K-major : rows 128 B apart, 8-row groups 1024 B apart (SBO); K step = 32 B inside the row.
+        // MN-major: k-rows 128 B apart, 8-k-row groups 1024 B apart (SBO), MN atoms BK*128 B apart (LBO); K step = UK k-rows.
+        const uint64_t da0 = p.a_mn ? umma_smem_desc(smem_u32(sA), BK * 128, 1024) : umma_smem_desc(smem_u32(sA), 16, 1024);
+        const uint64_t db0 = p.b_mn ? umma_smem_desc(smem_u32(sB), BK * 128, 1024) : umma_smem_desc(smem_u32(sB), 16, 1024);
+        const uint64_t ka = p.a_mn ? (UK * 128) >> 4 : 2, kbs = p.b_mn ? (UK * 128) >> 4 : 2;   // per-MMA K advance (16-byte units)
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+            mbar_wait(&full[s], ph, p.status, 102);
+            tc_fence_after();
+            const uint64_t da = da0 + static_cast<uint64_t>(s * (TILE_BYTES >> 4)), db = db0 + static_cast<uint64_t>(s * (TILE_BYTES >> 4));
+            if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < BK / UK; ++k) {
-                    // K-major : rows 128 B apart, 8-row groups 1024 B apart (SBO); K step = 32 B inside the row.
-                    // MN-major: k-rows 128 B apart, 8-k-row groups 1024 B apart (SBO), MN atoms BK*128 B apart (LBO);
-                    //           K step = UK k-rows.
-                    const uint64_t da = p.a_mn ? umma_smem_desc(a0 + k * UK * 128, BK * 128, 1024)
-                                               : umma_smem_desc(a0 + k * 32, 16, 1024);
-                    const uint64_t db = p.b_mn ? umma_smem_desc(b0 + k * UK * 128, BK * 128, 1024)
-                                               : umma_smem_desc(b0 + k * 32, 16, 1024);
                     const uint32_t acc = (kb | k) != 0;
-                    if (kTf32) umma_tf32(tmem_base, da, db, idesc, acc);
-                    else       umma_f16(tmem_base, da, db, idesc, acc);
+                    if (kTf32) umma_tf32(tmem_d, da + k * ka, db + k * kbs, idesc, acc);
+                    else       umma_f16(tmem_d, da + k * ka, db + k * kbs, idesc, acc);
                 }
                 umma_commit(&empty[s]);                 // frees the smem slot once these MMAs retire
+                if (kb == num_kb - 1) umma_commit(accum_full);
             }
-            umma_commit(accum_full);
+            __syncwarp();
         }
     } else {
         // ---------------------------------------------------- epilogue warps (TMEM lane quadrant = warp % 4)

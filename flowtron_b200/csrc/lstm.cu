@@ -114,7 +114,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             // buffer is free: no empty-slot barrier is needed.
             if (lane < FWD_NCH) wait_flag_ge(&p.flags[(t - 1) * FWD_NCH + lane], 8, p.status, 202);
             __syncwarp();
-            if (lane == 0) {
+            if (elect_one()) {
                 FT_TRACE(p, t, 0);
                 fence_proxy_async_global();        // generic-proxy writes of other SMs -> async-proxy (TMA) reads
                 FT_TRACE(p, t, 6);
@@ -128,36 +128,38 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            mbar_wait(wbar, 0, p.status, 203);
-            const uint32_t idesc = umma_idesc(128, FWD_N, FMT_F16, FMT_F16, 0, 0);
-            // descriptors advance by plain 64-bit adds on the (address >> 4) field: building each of the 64
-            // per-step descriptors from scratch made MMA *issue* (one thread) cost 2 us per step
-            const uint64_t da_base = umma_smem_desc(smem_u32(sA), 16, 1024), db_base = umma_smem_desc(smem_u32(sW), 16, 1024);
-            const uint64_t a_chunk = static_cast<uint64_t>(slot_bytes >> 4), b_chunk = (FWD_N * 128) >> 4;
-            for (int t = 1; t < p.T; ++t) {
-                const int ph = (t - 1) & 1;
-                uint64_t da = da_base, db = db_base;
+        // warp-uniform loop, one elected lane issues (see gemm.cu: descriptors must be uniform-register operands)
+        mbar_wait(wbar, 0, p.status, 203);
+        const uint32_t idesc = umma_idesc(128, FWD_N, FMT_F16, FMT_F16, 0, 0);
+        const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint64_t da_base = umma_smem_desc(smem_u32(sA), 16, 1024), db_base = umma_smem_desc(smem_u32(sW), 16, 1024);
+        const uint64_t a_chunk = static_cast<uint64_t>(slot_bytes >> 4), b_chunk = (FWD_N * 128) >> 4;
+        for (int t = 1; t < p.T; ++t) {
+            const int ph = (t - 1) & 1;
+            uint64_t da = da_base, db = db_base;
 #pragma unroll
-                for (int g = 0; g < FWD_NG; ++g) {
-                    mbar_wait(&full[g], ph, p.status, 204);
-                    tc_fence_after();
+            for (int g = 0; g < FWD_NG; ++g) {
+                mbar_wait(&full[g], ph, p.status, 204);
+                tc_fence_after();
+                if (elect_one()) {
                     if (g == 0) FT_TRACE(p, t, 2);
                     if (g == FWD_NG - 1) FT_TRACE(p, t, 5);
+                    uint64_t xa = da, xb = db;
 #pragma unroll
                     for (int c = 0; c < FWD_GS; ++c) {
-                        // consecutive MMAs into ONE accumulator serialise on the D read-modify-write (~60 clk each for
-                        // this tiny N=32 tile: 64 MMAs = 2 us/step); the 4 k-steps of a chunk therefore go to 4
-                        // independent TMEM accumulators that the epilogue sums
+                        // the 4 k-steps of a chunk go to 4 independent TMEM accumulators (summed by the epilogue):
+                        // back-to-back MMAs into one accumulator serialise on its read-modify-write
 #pragma unroll
                         for (int k = 0; k < KCH / 16; ++k)
-                            umma_f16(tmem_base + k * FWD_N, da + 2 * k, db + 2 * k, idesc, (g | c) != 0);
-                        da += a_chunk;
-                        db += b_chunk;
+                            umma_f16(tmem_d + k * FWD_N, xa + 2 * k, xb + 2 * k, idesc, (g | c) != 0);
+                        xa += a_chunk;
+                        xb += b_chunk;
                     }
+                    if (g == FWD_NG - 1) { FT_TRACE(p, t, 3); umma_commit(accum_full); }
                 }
-                FT_TRACE(p, t, 3);
-                umma_commit(accum_full);
+                __syncwarp();
+                da += FWD_GS * a_chunk;
+                db += FWD_GS * b_chunk;
             }
         }
     } else {
@@ -336,49 +338,53 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
             for (int c = lane; c < BWD_NCH; c += 32)   // parallel poll: 4 producer CTAs per 64-column chunk of dG_{t+1}
                 wait_flag_ge(&p.flags[(t + 1) * BWD_NCH + c], 4, p.status, 212);
             __syncwarp();
-            if (lane == 0) {
-                fence_proxy_async_global();
-                for (int g = 0; g < p.ng; ++g) {
-                    mbar_wait(&empty[s], ph ^ 1, p.status, 211);
+            if (elect_one()) fence_proxy_async_global();
+            __syncwarp();
+            for (int g = 0; g < p.ng; ++g) {
+                mbar_wait(&empty[s], ph ^ 1, p.status, 211);
+                if (elect_one()) {
                     mbar_expect_tx(&full[s], group_bytes);
                     tma_load_3d(ring + s * group_bytes, &tmG, &full[s], 0, (t + 1) * p.B, g * p.gs);
-                    if (++s == p.nring) { s = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++s == p.nring) { s = 0; ph ^= 1; }
             }
-            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            mbar_wait(wbar, 0, p.status, 213);
-            const uint32_t idesc = umma_idesc(128, BWD_UNITS, FMT_F16, FMT_F16, 0, 0);
-            const uint64_t da_ring = umma_smem_desc(smem_u32(ring), 16, 1024), db_base = umma_smem_desc(smem_u32(sW), 16, 1024);
-            const uint64_t a_chunk = static_cast<uint64_t>(slot_bytes >> 4), a_group = static_cast<uint64_t>(group_bytes >> 4);
-            const uint64_t b_chunk = (BWD_UNITS * 128) >> 4;
-            int s = 0, ph = 0;
-            uint64_t da_slot = da_ring;
-            for (int t = p.T - 2; t >= 0; --t) {
-                uint64_t db = db_base;
-                uint32_t acc = 0;
-                for (int g = 0; g < p.ng; ++g) {
-                    mbar_wait(&full[s], ph, p.status, 214);
-                    tc_fence_after();
-                    uint64_t da = da_slot;
+        mbar_wait(wbar, 0, p.status, 213);
+        const uint32_t idesc = umma_idesc(128, BWD_UNITS, FMT_F16, FMT_F16, 0, 0);
+        const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint64_t da_ring = umma_smem_desc(smem_u32(ring), 16, 1024), db_base = umma_smem_desc(smem_u32(sW), 16, 1024);
+        const uint64_t a_chunk = static_cast<uint64_t>(slot_bytes >> 4), a_group = static_cast<uint64_t>(group_bytes >> 4);
+        const uint64_t b_chunk = (BWD_UNITS * 128) >> 4;
+        int s = 0, ph = 0;
+        uint64_t da_slot = da_ring;
+        for (int t = p.T - 2; t >= 0; --t) {
+            uint64_t db = db_base;
+            for (int g = 0; g < p.ng; ++g) {
+                mbar_wait(&full[s], ph, p.status, 214);
+                tc_fence_after();
+                if (elect_one()) {
+                    uint64_t xa = da_slot, xb = db;
+                    uint32_t acc = g != 0;
                     for (int c = 0; c < p.gs; c += 2) {       // 8 independent accumulators (see the forward kernel)
 #pragma unroll
                         for (int cc = 0; cc < 2; ++cc) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                umma_f16(tmem_base + (cc * 4 + k) * BWD_UNITS, da + 2 * k, db + 2 * k, idesc, acc);
-                            da += a_chunk;
-                            db += b_chunk;
+                                umma_f16(tmem_d + (cc * 4 + k) * BWD_UNITS, xa + 2 * k, xb + 2 * k, idesc, acc);
+                            xa += a_chunk;
+                            xb += b_chunk;
                         }
                         acc = 1;
                     }
                     umma_commit(&empty[s]);
-                    da_slot += a_group;
-                    if (++s == p.nring) { s = 0; ph ^= 1; da_slot = da_ring; }
+                    if (g == p.ng - 1) umma_commit(accum_full);
                 }
-                umma_commit(accum_full);
+                __syncwarp();
+                db += static_cast<uint64_t>(p.gs) * b_chunk;
+                da_slot += a_group;
+                if (++s == p.nring) { s = 0; ph ^= 1; da_slot = da_ring; }
             }
         }
     } else {
