@@ -197,16 +197,15 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     mbar_wait(accum_full, (t - 1) & 1, p.status, 205);
                     tc_fence_after();
                     if (et == 64) FT_TRACE(p, t, 4);          // warp 4 == quadrant 0
-                    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16), acc);
+                    const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+                    float p1[32], p2[32], p3[32];             // the 4 partial accumulators, one wait
+                    tmem_ld_32x32(tq, acc);
+                    tmem_ld_32x32(tq + FWD_N, p1);
+                    tmem_ld_32x32(tq + 2 * FWD_N, p2);
+                    tmem_ld_32x32(tq + 3 * FWD_N, p3);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int a = 1; a < 4; ++a) {             // sum the 4 partial accumulators
-                        float part[32];
-                        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * FWD_N, part);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[j] += part[j];
-                    }
+                    for (int j = 0; j < 32; ++j) acc[j] = (acc[j] + p1[j]) + (p2[j] + p3[j]);
                     tc_fence_before();
                     float* dst = sAcc + (q * 32 + lane) * 33;
 #pragma unroll
@@ -338,13 +337,15 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
             for (int c = lane; c < BWD_NCH; c += 32)   // parallel poll: 4 producer CTAs per 64-column chunk of dG_{t+1}
                 wait_flag_ge(&p.flags[(t + 1) * BWD_NCH + c], 4, p.status, 212);
             __syncwarp();
-            if (elect_one()) fence_proxy_async_global();
+            if (elect_one()) { FT_TRACE(p, t, 0); fence_proxy_async_global(); }
             __syncwarp();
             for (int g = 0; g < p.ng; ++g) {
                 mbar_wait(&empty[s], ph ^ 1, p.status, 211);
                 if (elect_one()) {
                     mbar_expect_tx(&full[s], group_bytes);
                     tma_load_3d(ring + s * group_bytes, &tmG, &full[s], 0, (t + 1) * p.B, g * p.gs);
+                    if (g == 0) FT_TRACE(p, t, 1);
+                    if (g == p.ng - 1) FT_TRACE(p, t, 6);
                 }
                 __syncwarp();
                 if (++s == p.nring) { s = 0; ph ^= 1; }
@@ -365,6 +366,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
                 mbar_wait(&full[s], ph, p.status, 214);
                 tc_fence_after();
                 if (elect_one()) {
+                    if (g == 0) FT_TRACE(p, t, 2);
                     uint64_t xa = da_slot, xb = db;
                     uint32_t acc = g != 0;
                     for (int c = 0; c < p.gs; c += 2) {       // 8 independent accumulators (see the forward kernel)
@@ -379,7 +381,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
                         acc = 1;
                     }
                     umma_commit(&empty[s]);
-                    if (g == p.ng - 1) umma_commit(accum_full);
+                    if (g == p.ng - 1) { FT_TRACE(p, t, 3); umma_commit(accum_full); }
                 }
                 __syncwarp();
                 db += static_cast<uint64_t>(p.gs) * b_chunk;
@@ -436,16 +438,24 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
                     float acc[16];
                     mbar_wait(accum_full, (step - 1) & 1, p.status, 215);
                     tc_fence_after();
-                    tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16), acc);
+                    if (et == 64) FT_TRACE(p, t, 4);
+                    const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+                    float p1[16], p2[16], p3[16];
+                    tmem_ld_32x16(tq, acc);                       // 8 partial accumulators, loaded 4 at a time
+                    tmem_ld_32x16(tq + 1 * BWD_UNITS, p1);
+                    tmem_ld_32x16(tq + 2 * BWD_UNITS, p2);
+                    tmem_ld_32x16(tq + 3 * BWD_UNITS, p3);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int a = 1; a < 8; ++a) {
-                        float part[16];
-                        tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BWD_UNITS, part);
-                        tmem_ld_wait();
+                    for (int j = 0; j < 16; ++j) acc[j] += p1[j] + p2[j] + p3[j];
+                    float p0[16];
+                    tmem_ld_32x16(tq + 4 * BWD_UNITS, p0);
+                    tmem_ld_32x16(tq + 5 * BWD_UNITS, p1);
+                    tmem_ld_32x16(tq + 6 * BWD_UNITS, p2);
+                    tmem_ld_32x16(tq + 7 * BWD_UNITS, p3);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[j] += part[j];
-                    }
+                    for (int j = 0; j < 16; ++j) acc[j] += (p0[j] + p1[j]) + (p2[j] + p3[j]);
                     tc_fence_before();
                     float* dst = sAcc + (q * 32 + lane) * 17;
 #pragma unroll
@@ -498,7 +508,9 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
                 }
             }
             epi_bar();                                        // every dG_t store of this CTA precedes the releases
+            if (et == 0) FT_TRACE(p, t, 5);
             if (et < 4) red_release_add(&p.flags[t * BWD_NCH + et * 16 + cta / 4], 1);   // one release per gate chunk
+            if (et == 0) FT_TRACE(p, t, 7);
         }
     }
     tc_fence_before();
@@ -577,13 +589,14 @@ int launch_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void
     const int fixed = BWD_W_BYTES + 128 * 17 * 4 + 512 + 1024;
     const int avail = smem_optin() - fixed;
     int gs = 8;
+    { const char* e = getenv("FT_LSTM_BWD_GS"); if (e) { int v = atoi(e); if (v == 2 || v == 4 || v == 8 || v == 16) gs = v; } }
     while (gs > 2 && 2 * gs * slot > avail) gs >>= 1;          // at least a 2-deep ring of groups (gs stays even)
     int nring = avail / (gs * slot);
-    if (nring > 4) nring = 4;
+    if (nring > 8) nring = 8;
     if (nring < 2) return ft_set_error("lstm_bwd: not enough shared memory for the dG ring");
     p.gs = gs; p.ng = BWD_NCH / gs; p.nring = nring;
     p.dh_ext = dh_ext; p.ldd = ldd; p.gates = static_cast<const __half*>(gates16); p.cstate = cstate; p.lens = lens;
-    p.dG = static_cast<__half*>(dG16); p.flags = flags; p.status = ft_status_word(); p.trace = nullptr;
+    p.dG = static_cast<__half*>(dG16); p.flags = flags; p.status = ft_status_word(); p.trace = g_lstm_trace;
     CUtensorMap tmWT, tmG;
     if (make_tmap_2d(&tmWT, whhT16, FMT_F16, LH, LG, LG, KCH, BWD_UNITS)) return -1;
     if (make_tmap_chunks(&tmG, dG16, static_cast<long long>(T) * B, BWD_NCH, LG, p.Bbox, gs)) return -1;

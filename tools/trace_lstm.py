@@ -26,8 +26,32 @@ def main():
         torch.cuda.synchronize()
         print(f"run {it}: {e0.elapsed_time(e1) * 1e3 / T:.2f} us/step")
     L.ft_debug_set_lstm_trace(None)
+    report(trace, T, "forward", ["flags_seen", "tma_issued", "first_group_landed", "all_mma_issued", "accum_done(epi)",
+                                 "last_group_landed", "proxy_fence_done", "release_issued"])
+    # ---- backward
+    w = torch.randn(T, B, H, generator=g).cuda()
+    dG = torch.zeros(T, B, 4 * H, device="cuda", dtype=torch.float16)
+    whhT = whh.float().t().contiguous().half()
+    trace.zero_()
+    for it in range(3):
+        if it == 2:
+            L.ft_debug_set_lstm_trace(ctypes.c_void_p(trace.data_ptr()))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.lstm_bwd(w, whhT, gates, cst, None, dG)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"bwd run {it}: {e0.elapsed_time(e1) * 1e3 / T:.2f} us/step")
+    L.ft_debug_set_lstm_trace(None)
+    report(trace, T, "backward", ["flags_seen", "first_tma_issued", "first_group_landed", "all_mma_issued", "accum_done(epi)",
+                                  "dG_stored", "last_tma_issued", "release_issued"], reverse=True)
+
+
+def report(trace, T, title, names, reverse=False):
     tr = trace.cpu().double()[50:350]
-    names = ["flags_seen", "tma_issued", "first_group_landed", "all_mma_issued", "accum_done(epi)", "last_group_landed", "proxy_fence_done", "release_issued"]
+    if reverse:
+        tr = torch.flip(tr, (0,))
+    print(f"== {title}")
     period = (tr[1:, 0] - tr[:-1, 0]).mean().item()
     print(f"step period: {period:.0f} clk = {period / 1.965e3:.2f} us @1.965GHz")
     base = tr[:, 0:1]
