@@ -9,7 +9,7 @@ A step = H2D of one synthetic batch (e2e leg only) -> Flowtron.forward -> Flowtr
 bucketed NCCL gradient all-reduce (N>1) -> grad-norm clip -> RAdam step (train.py:281-331).
 `value` = valid mel frames (sum of out_lens over all ranks) per second with inputs resident in HBM;
 `e2e` = the same through the public module API with pinned-host inputs copied every step and the loss read back.
-Precision: fp16 tensor-core operands in forward, bf16 in backward, fp32 accumulation/state.
+Precision: fp16 tensor-core operands (backward on device-side loss-scaled gradients), fp32 accumulation/state.
 """
 from __future__ import annotations
 
@@ -264,7 +264,7 @@ def main():
     out = {
         "metric": "training mel-frames/sec", "value": value, "unit": "valid mel-frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f16 fwd / bf16 bwd operands, f32 accumulate+state", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16 tensor-core operands (loss-scaled in backward), f32 accumulate+state", "data": "synthetic",
         "config": {"workload": "configs[1]: LJS single-speaker 2-flow Flowtron train step, n_mel=80, per-GPU batch 32, T<=1000",
                    "per_gpu_batch": B, "global_batch": B * world, "max_frames": T, "max_text": L, "attn_prior": True,
                    "optimizer": "RAdam lr=1e-3 wd=1e-6 + clip_grad_norm 1.0", "parallelism": f"dp{world}",
