@@ -260,6 +260,10 @@ def main():
                 "= 2*B*1024*4096*(T-1) per launch"}
     kernel_table = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["count"] / args.steps,
                         "tflops": (v["flop"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 else None} for k, v in by_name.items()}
+    top_shapes = sorted(trep, key=lambda r: -r[5])[:14]
+    shape_table = [{"kernel": n_, "m": m_, "n": nn_, "k": k_, "launches_per_step": c_ / args.steps, "ms_per_launch": t_ / c_,
+                    "tflops": (2.0 * m_ * nn_ * k_ / (t_ / c_ / 1e3) / 1e12) if n_.startswith("gemm") else None}
+                   for n_, m_, nn_, k_, c_, t_ in top_shapes]
     flop_step = 3.0 * 2 * FLOP_PER_FRAME_FWD(L) * B * T * world       # fwd+bwd, 2 flows, padded frames
     out = {
         "metric": "training mel-frames/sec", "value": value, "unit": "valid mel-frames/s", "n_gpus": world,
@@ -272,7 +276,7 @@ def main():
                    "l2": "working set per step (>3 GB of activations) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e, "unit": "valid mel-frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernel_table,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernel_table, "top_launch_shapes": shape_table,
         "model_tflops": flop_step * args.steps / (ms / 1e3) / 1e12,
         "model_tensor_frac": flop_step * args.steps / (ms / 1e3) / 1e12 / (sustained * world),
     }

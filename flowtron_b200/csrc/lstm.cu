@@ -94,7 +94,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         mbar_init(accum_full, 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<128>(tmem_slot);
+    if (warp == 1) tmem_alloc<32>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -147,11 +147,9 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     uint64_t xa = da, xb = db;
 #pragma unroll
                     for (int c = 0; c < FWD_GS; ++c) {
-                        // the 4 k-steps of a chunk go to 4 independent TMEM accumulators (summed by the epilogue):
-                        // back-to-back MMAs into one accumulator serialise on its read-modify-write
 #pragma unroll
                         for (int k = 0; k < KCH / 16; ++k)
-                            umma_f16(tmem_d + k * FWD_N, xa + 2 * k, xb + 2 * k, idesc, (g | c) != 0);
+                            umma_f16(tmem_d, xa + 2 * k, xb + 2 * k, idesc, (g | c | k) != 0);
                         xa += a_chunk;
                         xb += b_chunk;
                     }
@@ -197,15 +195,8 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     mbar_wait(accum_full, (t - 1) & 1, p.status, 205);
                     tc_fence_after();
                     if (et == 64) FT_TRACE(p, t, 4);          // warp 4 == quadrant 0
-                    const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-                    float p1[32], p2[32], p3[32];             // the 4 partial accumulators, one wait
-                    tmem_ld_32x32(tq, acc);
-                    tmem_ld_32x32(tq + FWD_N, p1);
-                    tmem_ld_32x32(tq + 2 * FWD_N, p2);
-                    tmem_ld_32x32(tq + 3 * FWD_N, p3);
+                    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16), acc);
                     tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[j] = (acc[j] + p1[j]) + (p2[j] + p3[j]);
                     tc_fence_before();
                     float* dst = sAcc + (q * 32 + lane) * 33;
 #pragma unroll
@@ -271,7 +262,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<128>(tmem_base);
+    if (warp == 1) tmem_dealloc<32>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------- backward
@@ -320,7 +311,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
         mbar_init(accum_full, 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<128>(tmem_slot);
+    if (warp == 1) tmem_alloc<32>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -369,16 +360,14 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
                     if (g == 0) FT_TRACE(p, t, 2);
                     uint64_t xa = da_slot, xb = db;
                     uint32_t acc = g != 0;
-                    for (int c = 0; c < p.gs; c += 2) {       // 8 independent accumulators (see the forward kernel)
+                    for (int c = 0; c < p.gs; ++c) {
 #pragma unroll
-                        for (int cc = 0; cc < 2; ++cc) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_f16(tmem_d + (cc * 4 + k) * BWD_UNITS, xa + 2 * k, xb + 2 * k, idesc, acc);
-                            xa += a_chunk;
-                            xb += b_chunk;
+                        for (int k = 0; k < 4; ++k) {
+                            umma_f16(tmem_d, xa + 2 * k, xb + 2 * k, idesc, acc);
+                            acc = 1;
                         }
-                        acc = 1;
+                        xa += a_chunk;
+                        xb += b_chunk;
                     }
                     umma_commit(&empty[s]);
                     if (g == p.ng - 1) { FT_TRACE(p, t, 3); umma_commit(accum_full); }
@@ -439,23 +428,8 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
                     mbar_wait(accum_full, (step - 1) & 1, p.status, 215);
                     tc_fence_after();
                     if (et == 64) FT_TRACE(p, t, 4);
-                    const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-                    float p1[16], p2[16], p3[16];
-                    tmem_ld_32x16(tq, acc);                       // 8 partial accumulators, loaded 4 at a time
-                    tmem_ld_32x16(tq + 1 * BWD_UNITS, p1);
-                    tmem_ld_32x16(tq + 2 * BWD_UNITS, p2);
-                    tmem_ld_32x16(tq + 3 * BWD_UNITS, p3);
+                    tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16), acc);
                     tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] += p1[j] + p2[j] + p3[j];
-                    float p0[16];
-                    tmem_ld_32x16(tq + 4 * BWD_UNITS, p0);
-                    tmem_ld_32x16(tq + 5 * BWD_UNITS, p1);
-                    tmem_ld_32x16(tq + 6 * BWD_UNITS, p2);
-                    tmem_ld_32x16(tq + 7 * BWD_UNITS, p3);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] += (p0[j] + p1[j]) + (p2[j] + p3[j]);
                     tc_fence_before();
                     float* dst = sAcc + (q * 32 + lane) * 17;
 #pragma unroll
@@ -515,7 +489,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<128>(tmem_base);
+    if (warp == 1) tmem_dealloc<32>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------- backward, split-K cluster
@@ -559,7 +533,7 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
         mbar_init(&part_bar[0], B4_CLUSTER); mbar_init(&part_bar[1], B4_CLUSTER);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<256>(tmem_slot);
+    if (warp == 1) tmem_alloc<64>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -584,7 +558,6 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
                     mbar_expect_tx(&full[g], GS * slot_bytes);
                     tma_load_3d(sA + g * GS * slot_bytes, &tmG, &full[g], 0, (t + 1) * p.B, rank * B4_NCH + g * GS);
                 }
-                FT_TRACE(p, t, 1);
             }
             __syncwarp();
         }
@@ -608,8 +581,8 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
 #pragma unroll
                     for (int c = 0; c < GS; ++c) {
 #pragma unroll
-                        for (int k = 0; k < KCH / 16; ++k)       // 4 independent accumulators of 64 columns
-                            umma_f16(tmem_d + k * B4_UNITS, xa + 2 * k, xb + 2 * k, idesc, (g | c) != 0);
+                        for (int k = 0; k < KCH / 16; ++k)
+                            umma_f16(tmem_d, xa + 2 * k, xb + 2 * k, idesc, (g | c | k) != 0);
                         xa += a_chunk;
                         xb += b_chunk;
                     }
@@ -662,23 +635,20 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
                     mbar_wait(accum_full, (step - 1) & 1, p.status, 225);
                     tc_fence_after();
                     if (et == 64) FT_TRACE(p, t, 4);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {                 // 64 columns in two halves, 4 partial accumulators each
-                        float a0[32], a1[32], a2[32], a3[32];
-                        tmem_ld_32x32(tmem_base + h * 32, a0);
-                        tmem_ld_32x32(tmem_base + B4_UNITS + h * 32, a1);
-                        tmem_ld_32x32(tmem_base + 2 * B4_UNITS + h * 32, a2);
-                        tmem_ld_32x32(tmem_base + 3 * B4_UNITS + h * 32, a3);
+                    {
+                        float a0[32], a1[32];
+                        tmem_ld_32x32(tmem_base, a0);
+                        tmem_ld_32x32(tmem_base + 32, a1);
                         tmem_ld_wait();
-                        float* dst = mine + lane * B4_PP + h * 32;
+                        float* dst = mine + lane * B4_PP;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(dst + j) = make_float4((a0[j] + a1[j]) + (a2[j] + a3[j]),
-                                                                              (a0[j + 1] + a1[j + 1]) + (a2[j + 1] + a3[j + 1]),
-                                                                              (a0[j + 2] + a1[j + 2]) + (a2[j + 2] + a3[j + 2]),
-                                                                              (a0[j + 3] + a1[j + 3]) + (a2[j + 3] + a3[j + 3]));
+                        for (int j = 0; j < 32; j += 4) {
+                            *reinterpret_cast<float4*>(dst + j) = make_float4(a0[j], a0[j + 1], a0[j + 2], a0[j + 3]);
+                            *reinterpret_cast<float4*>(dst + 32 + j) = make_float4(a1[j], a1[j + 1], a1[j + 2], a1[j + 3]);
+                        }
                     }
                     tc_fence_before();
+                    if (et == 64) FT_TRACE(p, t, 6);
                 }
                 epi_bar();
                 if (et == 0) {                                    // publish: one release-arrive on every rank's barrier
@@ -686,6 +656,7 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
                     for (int rr = 0; rr < B4_CLUSTER; ++rr) mbar_arrive_cluster(mapa_shared(smem_u32(&part_bar[par]), rr));
                 }
                 mbar_wait_cluster(&part_bar[par], ((step - 1) >> 1) & 1, p.status, 226);
+                if (et == 0) FT_TRACE(p, t, 1 + 0 * 8 + 0);   // reuse slot 1: all partials visible
                 if (has_item) {
                     const uint32_t off = static_cast<uint32_t>((par * 32 * B4_PP + ib * B4_PP + B4_OWN * rank + 4 * uq) * 4);
 #pragma unroll
@@ -741,7 +712,7 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                          // nobody exits while a peer may still read its partials
-    if (warp == 1) tmem_dealloc<256>(tmem_base);
+    if (warp == 1) tmem_dealloc<64>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------- host

@@ -43,8 +43,8 @@ def main():
         torch.cuda.synchronize()
         print(f"bwd run {it}: {e0.elapsed_time(e1) * 1e3 / T:.2f} us/step")
     L.ft_debug_set_lstm_trace(None)
-    report(trace, T, "backward", ["flags_seen", "first_tma_issued", "first_group_landed", "all_mma_issued", "accum_done(epi)",
-                                  "dG_stored", "last_tma_issued", "release_issued"], reverse=True)
+    report(trace, T, "backward", ["flags_seen", "partials_visible(cluster)", "first_group_landed", "all_mma_issued", "accum_done(epi)",
+                                  "dG_stored", "own_partial_written", "release_issued"], reverse=True)
 
 
 def report(trace, T, title, names, reverse=False):
