@@ -127,83 +127,86 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
     } else {
         // ---------------------------------------------------- epilogue warps (TMEM lane quadrant = warp % 4)
+        // TMEM -> registers (lane = row) -> alpha/bias/tanh -> this warp's staging tile in the (now idle) pipeline
+        // buffers -> row-wise, fully coalesced global stores (one 512-byte row per warp instruction).  The first
+        // version stored straight from registers: 32 lanes x 16 B into 32 different rows per instruction, which
+        // capped the N=4096 projection GEMMs at ~0.64 TB/s of output bandwidth.
         const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const long long m = static_cast<long long>(tile_m) * BM + row;
-        mbar_wait(accum_full, 0, p.status, 103);
+        const int row0 = q * 32;
+        mbar_wait(accum_full, 0, p.status, 103);               // all MMAs retired: smem stages are free
         tc_fence_after();
-        const bool row_ok = m < p.M;
+        constexpr int SP = BN + 4;                             // staging pitch (floats)
+        float* stage = reinterpret_cast<float*>(smem) + q * 32 * SP;      // 4 x 32 x 132 x 4 B = 67.6 KB <= 96 KB
+        const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
+        const int ncols = min(BN, p.N - tile_n * BN);
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             const int n0 = tile_n * BN + c * 32;
-            if (n0 >= p.N) break;                        // warp-uniform
+            if (c * 32 >= ncols) break;                        // warp-uniform
             float v[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(row0) << 16) + c * 32, v);
             tmem_ld_wait();
-            if (!row_ok) continue;
-            const int nvalid = min(32, p.N - n0);
-            const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 float x = v[j] * alpha;
-                if (j < nvalid) {
+                if (c * 32 + j < ncols) {
                     if (p.bias) x += __ldg(p.bias + n0 + j);
                     if (p.bias2) x += __ldg(p.bias2 + n0 + j);
                 }
                 if (p.act == 1) x = tanh_f(x);
                 v[j] = x;
             }
-            if (p.act == 2) {
-                const __half* ax = p.aux16 + m * p.ldaux + n0;
+            float* dst = stage + lane * SP + c * 32;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (j < nvalid) {
-                        const float y = __half2float(ax[j]);
-                        v[j] *= (1.f - y * y);
-                    }
-                }
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        __syncwarp();
+        // write phase: each iteration handles one row of this warp's 32; lane l owns columns 4l..4l+3
+        const int col = 4 * lane;
+        const bool vec_ok = (ncols == BN);
+#pragma unroll 1
+        for (int r = 0; r < 32; ++r) {
+            const long long m = static_cast<long long>(tile_m) * BM + row0 + r;
+            if (m >= p.M) break;                               // warp-uniform
+            const float4 s4 = *reinterpret_cast<const float4*>(stage + r * SP + col);
+            float x[4] = {s4.x, s4.y, s4.z, s4.w};
+            const int nc = tile_n * BN + col;
+            if (p.act == 2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (col + j < ncols) { const float y = __half2float(p.aux16[m * p.ldaux + nc + j]); x[j] *= (1.f - y * y); }
             }
             if (p.C32) {
-                float* dst = p.C32 + m * p.ldc32 + n0;
-                if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                    float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        if (p.beta) { float4 c0 = d4[j]; o.x += c0.x; o.y += c0.y; o.z += c0.z; o.w += c0.w; }
-                        d4[j] = o;
-                        if (p.beta) { v[4 * j] = o.x; v[4 * j + 1] = o.y; v[4 * j + 2] = o.z; v[4 * j + 3] = o.w; }
-                    }
+                float* dst = p.C32 + m * p.ldc32 + nc;
+                if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                    float4 o = make_float4(x[0], x[1], x[2], x[3]);
+                    if (p.beta) { const float4 c0 = *reinterpret_cast<const float4*>(dst); o.x += c0.x; o.y += c0.y; o.z += c0.z; o.w += c0.w; }
+                    *reinterpret_cast<float4*>(dst) = o;
+                    x[0] = o.x; x[1] = o.y; x[2] = o.z; x[3] = o.w;
                 } else {
-                    for (int j = 0; j < nvalid; ++j) {
-                        float o = v[j];
-                        if (p.beta) o += dst[j];
-                        dst[j] = o;
-                        v[j] = o;
-                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (col + j < ncols) { if (p.beta) x[j] += dst[j]; dst[j] = x[j]; }
                 }
             }
             if (p.C16) {
-                uint16_t* dst = reinterpret_cast<uint16_t*>(p.C16) + m * p.ldc16 + n0;
-                uint32_t pk[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    if (p.c16_fmt == 0) {      // fp16: saturate instead of overflowing to inf
-                        __half2 h = __floats2half2_rn(fminf(fmaxf(v[2 * j], -65504.f), 65504.f),
-                                                      fminf(fmaxf(v[2 * j + 1], -65504.f), 65504.f));
-                        pk[j] = *reinterpret_cast<uint32_t*>(&h);
-                    } else {
-                        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                        pk[j] = *reinterpret_cast<uint32_t*>(&h);
-                    }
+                uint16_t* dst = reinterpret_cast<uint16_t*>(p.C16) + m * p.ldc16 + nc;
+                uint32_t pk[2];
+                if (p.c16_fmt == 0) {      // fp16: saturate instead of overflowing to inf
+                    __half2 h0 = __floats2half2_rn(fminf(fmaxf(x[0], -65504.f), 65504.f), fminf(fmaxf(x[1], -65504.f), 65504.f));
+                    __half2 h1 = __floats2half2_rn(fminf(fmaxf(x[2], -65504.f), 65504.f), fminf(fmaxf(x[3], -65504.f), 65504.f));
+                    pk[0] = *reinterpret_cast<uint32_t*>(&h0); pk[1] = *reinterpret_cast<uint32_t*>(&h1);
+                } else {
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(x[0], x[1]), h1 = __floats2bfloat162_rn(x[2], x[3]);
+                    pk[0] = *reinterpret_cast<uint32_t*>(&h0); pk[1] = *reinterpret_cast<uint32_t*>(&h1);
                 }
-                if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                    uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+                    *reinterpret_cast<uint2*>(dst) = make_uint2(pk[0], pk[1]);
                 } else {
                     const uint16_t* ps = reinterpret_cast<const uint16_t*>(pk);
-                    for (int j = 0; j < nvalid; ++j) dst[j] = ps[j];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (col + j < ncols) dst[j] = ps[j];
                 }
             }
         }
