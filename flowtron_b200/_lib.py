@@ -195,9 +195,13 @@ def lstm_bwd(dh_ext, whhT16, gates16, cstate, lens, dG16):
 _scratch = {}
 
 
+def set_lstm_half_sm(on: bool):
+    lib().ft_set_lstm_half_sm(1 if on else 0)
+
+
 def scratch_buffer(nbytes: int, device) -> torch.Tensor:
-    """Per-device transient work area shared by every flow (grown on demand, never shrunk)."""
-    key = (device.type, device.index)
+    """Per-(device, stream) transient work area shared by every flow on that stream (grown on demand)."""
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = None

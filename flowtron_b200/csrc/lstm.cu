@@ -50,8 +50,9 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
 
 // ------------------------------------------------------------------------------------------- forward
-constexpr int FWD_CTAS = 128, FWD_UNITS = 8, FWD_N = 32, FWD_NCH = LH / KCH;     // 16 chunks / step
-constexpr int FWD_W_BYTES = FWD_NCH * FWD_N * 128;                                 // 64 KB
+constexpr int FWD_NCH = LH / KCH;                  // 16 chunks / step
+// FWD_UNITS hidden units per CTA: 8 -> 128 CTAs (whole GPU, lowest latency), 16 -> 64 CTAs (two such launches on two
+// streams -- one per half batch -- run concurrently and hide each other's exchange latency)
 
 struct LstmFwdParams {
     int T, B, Bbox;
@@ -66,17 +67,20 @@ struct LstmFwdParams {
     long long* trace;          // optional [T][8] clock64 stamps of CTA 0 (debug/profiling), or null
 };
 
-template <int FWD_GS>
+template <int FWD_GS, int FWD_UNITS>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, LstmFwdParams p) {
     constexpr int FWD_NG = FWD_NCH / FWD_GS;                     // TMA groups per step
+    constexpr int FWD_N = 4 * FWD_UNITS, FWD_W_BYTES = FWD_NCH * FWD_N * 128, FWD_PROD = KCH / FWD_UNITS;
+    constexpr int AP = FWD_N + 1;                                // accumulator staging pitch
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int slot_bytes = p.Bbox * 128;
     uint8_t* sA = smem;                                          // [16 chunks][Bbox rows][128 B]
     uint8_t* sW = smem + FWD_NCH * slot_bytes;                   // the M=128 over-read of the last chunks lands here
-    float* sAcc = reinterpret_cast<float*>(sW + FWD_W_BYTES);    // [128 rows][33]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + 128 * 33);
+    float* sAcc = reinterpret_cast<float*>(sW + FWD_W_BYTES);    // [32 * nq rows][AP]
+    const int nq = (p.B + 31) / 32;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + ((nq * 32 * AP + 1) & ~1));
     uint64_t* full = bars;                       // [FWD_NG] (<= 16)
     uint64_t* wbar = bars + 16;
     uint64_t* accum_full = bars + 17;
@@ -84,7 +88,6 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x;
-    const int nq = (p.B + 31) / 32;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmW);
@@ -94,7 +97,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         mbar_init(accum_full, 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<32>(tmem_slot);
+    if (warp == 1) tmem_alloc<(FWD_N < 32 ? 32 : FWD_N)>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -102,17 +105,17 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 
     if (warp == 0) {
         if (lane == 0) {
-            // resident W_hh slice: chunk kc, gate g -> 8 rows x 128 B (one swizzle atom)
+            // resident W_hh slice: chunk kc, gate g -> FWD_UNITS rows x 128 B
             mbar_expect_tx(wbar, FWD_W_BYTES);
             for (int kc = 0; kc < FWD_NCH; ++kc)
                 for (int g = 0; g < 4; ++g)
-                    tma_load_2d(sW + kc * (FWD_N * 128) + g * 1024, &tmW, wbar, kc * KCH, g * LH + FWD_UNITS * cta);
+                    tma_load_2d(sW + kc * (FWD_N * 128) + g * (FWD_UNITS * 128), &tmW, wbar, kc * KCH, g * LH + FWD_UNITS * cta);
         }
         for (int t = 1; t < p.T; ++t) {
-            // the 16 chunk counters of step t-1 (8 producer CTAs each) are polled in parallel, one lane each.
+            // the 16 chunk counters of step t-1 (FWD_PROD producer CTAs each) are polled in parallel, one lane each.
             // Seeing them all also proves this CTA's own step t-1 retired (its release is among them), so the A
             // buffer is free: no empty-slot barrier is needed.
-            if (lane < FWD_NCH) wait_flag_ge(&p.flags[(t - 1) * FWD_NCH + lane], 8, p.status, 202);
+            if (lane < FWD_NCH) wait_flag_ge(&p.flags[(t - 1) * FWD_NCH + lane], FWD_PROD, p.status, 202);
             __syncwarp();
             if (elect_one()) {
                 FT_TRACE(p, t, 0);
@@ -164,14 +167,15 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         // ---------------------------------------------------------------- epilogue: 4 warps, 128 threads
         const int q = warp & 3;                               // TMEM lane quadrant this warp may read
         const int et = threadIdx.x - 64;                      // 0..127
-        // work items: (batch row b, unit pair up) -> item = b * 4 + up ; thread handles items et, et + 128
-        const int n_items = p.B * 4;
+        // work items: (batch row b, unit pair up) -> item = b * UP + up ; thread handles items et, et + 128
+        constexpr int UP = FWD_UNITS / 2;
+        const int n_items = p.B * UP;
         float c[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
         int len_i[2];
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             const int item = et + s * EPI_THREADS;
-            len_i[s] = (item < n_items && p.lens) ? p.lens[item >> 2] : p.T;
+            len_i[s] = (item < n_items && p.lens) ? p.lens[item / UP] : p.T;
         }
         const int u0 = FWD_UNITS * cta;
         for (int t = 0; t < p.T; ++t) {
@@ -180,7 +184,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             for (int s = 0; s < 2; ++s) {
                 const int item = et + s * EPI_THREADS;
                 if (item < n_items) {
-                    const int b = item >> 2, up = item & 3;
+                    const int b = item / UP, up = item % UP;
                     const float* src = p.xproj + (static_cast<long long>(t) * p.B + b) * LG + u0 + 2 * up;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -191,26 +195,29 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             }
             if (t > 0) {
                 if (q < nq) {                                 // this warp owns TMEM rows [32q, 32q+32)
-                    float acc[32];
                     mbar_wait(accum_full, (t - 1) & 1, p.status, 205);
                     tc_fence_after();
                     if (et == 64) FT_TRACE(p, t, 4);          // warp 4 == quadrant 0
-                    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16), acc);
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    float* dst = sAcc + (q * 32 + lane) * 33;
+                    float* dst = sAcc + (q * 32 + lane) * AP;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) dst[j] = acc[j];
+                    for (int h = 0; h < FWD_N / 32; ++h) {
+                        float acc[32];
+                        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 32, acc);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) dst[h * 32 + j] = acc[j];
+                    }
+                    tc_fence_before();
                 }
                 epi_bar();
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     const int item = et + s * EPI_THREADS;
                     if (item < n_items) {
-                        const int b = item >> 2, up = item & 3;
-                        const float* a = sAcc + b * 33 + 2 * up;
+                        const int b = item / UP, up = item % UP;
+                        const float* a = sAcc + b * AP + 2 * up;
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) { x[s][2 * g] += a[g * 8]; x[s][2 * g + 1] += a[g * 8 + 1]; }
+                        for (int g = 0; g < 4; ++g) { x[s][2 * g] += a[g * FWD_UNITS]; x[s][2 * g + 1] += a[g * FWD_UNITS + 1]; }
                     }
                 }
             }
@@ -219,7 +226,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             for (int s = 0; s < 2; ++s) {
                 const int item = et + s * EPI_THREADS;
                 if (item < n_items) {
-                    const int b = item >> 2, up = item & 3;
+                    const int b = item / UP, up = item % UP;
                     const bool valid = t < len_i[s];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
@@ -237,7 +244,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             }
             epi_bar();                                        // all h_t stores of this CTA precede the release
             if (et == 0) {
-                red_release_add(&p.flags[t * FWD_NCH + cta / 8], 1);      // cumulative release (gpu scope)
+                red_release_add(&p.flags[t * FWD_NCH + cta / FWD_PROD], 1);      // cumulative release (gpu scope)
                 FT_TRACE(p, t, 7);
             }
             // off the critical path: tensors only the backward pass reads
@@ -245,7 +252,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             for (int s = 0; s < 2; ++s) {
                 const int item = et + s * EPI_THREADS;
                 if (item < n_items) {
-                    const int b = item >> 2, up = item & 3;
+                    const int b = item / UP, up = item % UP;
                     const long long r = static_cast<long long>(t) * p.B + b;
                     if (p.h32) *reinterpret_cast<float2*>(p.h32 + r * p.ldh32 + u0 + 2 * up) = make_float2(hv[s][0], hv[s][1]);
                     if (p.gates) {
@@ -262,7 +269,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<32>(tmem_base);
+    if (warp == 1) tmem_dealloc<(FWD_N < 32 ? 32 : FWD_N)>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------- backward
@@ -746,33 +753,40 @@ static int make_tmap_chunks(CUtensorMap* out, const void* ptr, long long rows, i
     return 0;
 }
 
+static bool g_half_sm = false;       // 64-CTA forward kernel (for two concurrent half-batch launches)
+void set_lstm_half_sm(int on) { g_half_sm = on != 0; }
+
+template <int GS, int UNITS>
+static int launch_fwd_t(LstmFwdParams& p, const void* whh16, void* hseq16, long long ldh, int T, int B, int* flags, cudaStream_t st) {
+    constexpr int N = 4 * UNITS, W_BYTES = FWD_NCH * N * 128, CTAS = LH / UNITS;
+    const int slot = p.Bbox * 128, nq = (B + 31) / 32;
+    const int smem = FWD_NCH * slot + W_BYTES + nq * 32 * (N + 1) * 4 + 8 + 256 + 1024;
+    if (smem > smem_optin()) return ft_set_error("lstm_fwd: not enough shared memory");
+    CUtensorMap tmW, tmH;
+    if (make_tmap_2d(&tmW, whh16, FMT_F16, LG, LH, LH, KCH, UNITS)) return -1;
+    if (make_tmap_chunks(&tmH, hseq16, static_cast<long long>(T) * B, FWD_NCH, ldh, p.Bbox, GS)) return -1;
+    if (cudaMemsetAsync(flags, 0, sizeof(int) * T * FWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_fwd: memset failed");
+    void* fn = reinterpret_cast<void*>(lstm_fwd_kernel<GS, UNITS>);
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    TimeScope ts("lstm_fwd", T, B, 0, st);
+    void* args[] = {&tmW, &tmH, &p};
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(CTAS), dim3(LSTM_THREADS), args, smem, st);
+    if (e != cudaSuccess) return ft_set_error(cudaGetErrorString(e));
+    ft_count_launch(1);
+    return ft_check_launch("lstm_fwd_kernel");
+}
+
 int launch_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const int* lens, void* hseq16, long long ldh,
                     void* gates16, float* cstate, float* h32, long long ldh32, int* flags, cudaStream_t st) {
     if (T <= 0 || B <= 0) return 0;
     if (B > 64) return ft_set_error("lstm_fwd: batch > 64 per call not supported (split the batch)");
     LstmFwdParams p;
     p.T = T; p.B = B; p.Bbox = (B + 7) & ~7;
-    const int slot = p.Bbox * 128;
-    const int smem = FWD_NCH * slot + FWD_W_BYTES + 128 * 33 * 4 + 256 + 1024;
-    if (smem > smem_optin()) return ft_set_error("lstm_fwd: not enough shared memory");
     p.xproj = xproj; p.lens = lens; p.hseq = static_cast<__half*>(hseq16); p.ldh = ldh;
     p.gates = static_cast<__half*>(gates16); p.cstate = cstate; p.h32 = h32; p.ldh32 = ldh32;
     p.flags = flags; p.status = ft_status_word(); p.trace = g_lstm_trace;
-    CUtensorMap tmW, tmH;
-    if (make_tmap_2d(&tmW, whh16, FMT_F16, LG, LH, LH, KCH, FWD_UNITS)) return -1;
-    static int gs = 0;
-    if (!gs) { const char* e = getenv("FT_LSTM_GS"); gs = e ? atoi(e) : 8; if (gs != 2 && gs != 4 && gs != 8 && gs != 16) gs = 8; }
-    if (make_tmap_chunks(&tmH, hseq16, static_cast<long long>(T) * B, FWD_NCH, ldh, p.Bbox, gs)) return -1;
-    if (cudaMemsetAsync(flags, 0, sizeof(int) * T * FWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_fwd: memset failed");
-    void* fn = gs == 2 ? reinterpret_cast<void*>(lstm_fwd_kernel<2>) : gs == 4 ? reinterpret_cast<void*>(lstm_fwd_kernel<4>)
-             : gs == 16 ? reinterpret_cast<void*>(lstm_fwd_kernel<16>) : reinterpret_cast<void*>(lstm_fwd_kernel<8>);
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    TimeScope ts("lstm_fwd", T, B, 0, st);
-    void* args[] = {&tmW, &tmH, &p};
-    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(FWD_CTAS), dim3(LSTM_THREADS), args, smem, st);
-    if (e != cudaSuccess) return ft_set_error(cudaGetErrorString(e));
-    ft_count_launch(1);
-    return ft_check_launch("lstm_fwd_kernel");
+    if (g_half_sm && B <= 32) return launch_fwd_t<8, 16>(p, whh16, hseq16, ldh, T, B, flags, st);
+    return launch_fwd_t<8, 8>(p, whh16, hseq16, ldh, T, B, flags, st);
 }
 
 int launch_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void* whhT16, const void* gates16,

@@ -312,6 +312,21 @@ class Flowtron(nn.Module):
             self.flows.append(cls(n_mel_channels, n_speaker_dim, n_text_dim, n_mel_channels + n_speaker_dim, n_hidden,
                                   n_attn_channels, n_lstm_layers, add_gate, use_cumm_attention))
 
+    # Number of concurrent half-batch pipelines.  The recurrences are bound by a per-step exchange latency, not by
+    # throughput, so two independent half batches on two CUDA streams (each using a 64-SM persistent kernel) hide
+    # each other's latency, and one half's GEMMs / attention fill the SMs the other half's recurrence leaves idle.
+    n_streams = 2
+    min_split_batch = 8
+
+    def _run_flows(self, mel, encoder_outputs, mask, out_lens, attn_prior):
+        log_s_list, attns_list, attns_logprob_list, gate = [], [], [], None
+        for i, flow in enumerate(self.flows):
+            mel, log_s, gate, attn_out, attn_logprob_out = flow(mel, encoder_outputs, mask, out_lens, attn_prior)
+            log_s_list.append(log_s)
+            attns_list.append(attn_out)
+            attns_logprob_list.append(attn_logprob_out)
+        return mel, log_s_list, gate, attns_list, attns_logprob_list
+
     def forward(self, mel, speaker_ids, text, in_lens, out_lens, attn_prior=None):
         speaker_ids = speaker_ids * 0 if self.dummy_speaker_embedding else speaker_ids
         speaker_vecs = self.speaker_embedding(speaker_ids)
@@ -321,14 +336,39 @@ class Flowtron(nn.Module):
         text = text.transpose(0, 1)
         mel = mel.permute(2, 0, 1)
         encoder_outputs = torch.cat([text, speaker_vecs.expand(text.size(0), -1, -1)], 2)
-        log_s_list, attns_list, attns_logprob_list = [], [], []
         mask = ~get_mask_from_lengths(in_lens)[..., None]
-        gate = None
-        for i, flow in enumerate(self.flows):
-            mel, log_s, gate, attn_out, attn_logprob_out = flow(mel, encoder_outputs, mask, out_lens, attn_prior)
-            log_s_list.append(log_s)
-            attns_list.append(attn_out)
-            attns_logprob_list.append(attn_logprob_out)
+        B = mel.size(1)
+        split = self.n_streams > 1 and mel.is_cuda and B >= self.min_split_batch and out_lens is not None
+        if mel.is_cuda:
+            _lib.set_lstm_half_sm(split)
+        if not split:
+            mel, log_s_list, gate, attns_list, attns_logprob_list = self._run_flows(mel, encoder_outputs, mask, out_lens, attn_prior)
+            return (mel, log_s_list, gate, attns_list, attns_logprob_list, mean, log_var, prob)
+
+        cur = torch.cuda.current_stream()
+        if not hasattr(self, "_side_streams") or self._side_streams[0].device != mel.device:
+            self._side_streams = [torch.cuda.Stream(device=mel.device) for _ in range(2)]
+        bounds = [(0, B // 2), (B // 2, B)]
+        parts = []
+        for (b0, b1), s in zip(bounds, self._side_streams):
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                part = self._run_flows(mel[:, b0:b1], encoder_outputs[:, b0:b1], mask[b0:b1], out_lens[b0:b1],
+                                       None if attn_prior is None else attn_prior[b0:b1])
+            parts.append(part)
+        for s in self._side_streams:
+            cur.wait_stream(s)
+
+        def cat(ts, dim):
+            for t in ts:
+                t.record_stream(cur)
+            return torch.cat(ts, dim)
+        n_flows = len(self.flows)
+        mel = cat([p[0] for p in parts], 1)
+        log_s_list = [cat([p[1][i] for p in parts], 1) for i in range(n_flows)]
+        gate = None if parts[0][2] is None else cat([p[2] for p in parts], 1)
+        attns_list = [cat([p[3][i] for p in parts], 0) for i in range(n_flows)]
+        attns_logprob_list = [cat([p[4][i] for p in parts], 0) for i in range(n_flows)]
         return (mel, log_s_list, gate, attns_list, attns_logprob_list, mean, log_var, prob)
 
     def infer(self, residual, speaker_ids, text, temperature=1.0, gate_threshold=0.5, attns=None, attn_prior=None):

@@ -52,6 +52,10 @@ int ft_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const int* 
 /* debug/profiling: device buffer [T][8] that receives clock64 stamps of CTA 0 of later ft_lstm_fwd launches */
 void ft_debug_set_lstm_trace(long long* buf);
 
+/* Process-wide switch: 1 = ft_lstm_fwd (and ft_ar_step_fwd) use the 64-CTA recurrence kernel so two half-batch
+ * launches on two streams run concurrently (the BPTT kernel always uses 64 CTAs for B <= 32). */
+void ft_set_lstm_half_sm(int on);
+
 /* BPTT of the same layer (autograd of nn.LSTM).  dh_ext: gradient w.r.t. the layer outputs, fp32
  * [T*B, ldd] (ignored at t >= lens[b]; the caller may pre-multiply it by a power-of-two loss scale).  whhT16:
  * fp16 copy of weight_hh^T [1024,4096].  Writes dG (fp16 [T*B,4096], saturating), the gradient w.r.t. the gate

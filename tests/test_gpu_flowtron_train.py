@@ -140,3 +140,33 @@ def test_pad_independence():
     assert torch.equal(a[0][vm], b[0][vm])
     for x, y in zip(a[1], b[1]):
         assert torch.equal(x[vm], y[vm])
+
+
+def test_two_stream_half_batches_equal_single_stream():
+    """Flowtron.forward splits B >= 8 into two half batches on two CUDA streams (64-SM recurrence kernels running
+    concurrently).  Utterances are independent, so outputs and parameter gradients must equal the single-stream run."""
+    from flowtron_b200.flowtron import FlowtronLoss
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = dict(synth.DEFAULT_MODEL_CONFIG, n_flows=2)
+    batch = synth.synth_batch(8, 40, 14, cfg, 21, with_prior=True)
+    cu = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    res = []
+    for n_streams in (1, 2):
+        model = build_model(cfg, 31)
+        model.train()
+        model.encoder.p_dropout = 0.0
+        model.n_streams = n_streams
+        out = model(cu["mel"], cu["speaker_ids"], cu["text"], cu["in_lens"], cu["out_lens"], cu["attn_prior"])
+        nll, gl, _ = FlowtronLoss()(out, cu["gate_target"], cu["in_lens"], cu["out_lens"])
+        (nll + gl).sum().backward()
+        torch.cuda.synchronize()
+        res.append((out, float(nll), {n: p.grad.clone() for n, p in model.named_parameters()}))
+    (o1, n1, g1), (o2, n2, g2) = res
+    assert (o1[0] - o2[0]).abs().max().item() <= 1e-5 * o1[0].abs().max().item()
+    assert (o1[2] - o2[2]).abs().max().item() <= 1e-4
+    for a, b in zip(o1[3], o2[3]):
+        assert (a - b).abs().max().item() <= 1e-5
+    assert abs(n1 - n2) <= 1e-5 * abs(n1)
+    for k in g1:
+        d = (g1[k] - g2[k]).norm().item()
+        assert d <= 2e-3 * (g1[k].norm().item() + 1e-8), (k, d)      # wgrad sums are split differently (fp16 products, fp32 sums)
