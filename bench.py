@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=1, help="2 = two half-batch pipelines on two CUDA streams")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: no e2e leg, no CPU baseline, warm-up as given")
     return ap.parse_args()
 
@@ -163,6 +164,7 @@ def main():
     model = Flowtron(**cfg)
     model.load_state_dict(synth.synth_params(cfg, 1234), strict=True)
     model = model.to(dev).train()
+    model.n_streams = args.streams
     crit = FlowtronLoss(sigma=1.0, gate_loss=True, use_ctc_loss=False)
     if world > 1:
         ftd.apply_gradient_allreduce(model)
@@ -271,7 +273,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f16 tensor-core operands (loss-scaled in backward), f32 accumulate+state", "data": "synthetic",
         "config": {"workload": "configs[1]: LJS single-speaker 2-flow Flowtron train step, n_mel=80, per-GPU batch 32, T<=1000",
                    "per_gpu_batch": B, "global_batch": B * world, "max_frames": T, "max_text": L, "attn_prior": True,
-                   "optimizer": "RAdam lr=1e-3 wd=1e-6 + clip_grad_norm 1.0", "parallelism": f"dp{world}",
+                   "optimizer": "RAdam lr=1e-3 wd=1e-6 + clip_grad_norm 1.0", "parallelism": f"dp{world}", "streams_per_rank": args.streams,
                    "padded_frames_per_s": B * T * world * args.steps / (ms / 1e3),
                    "l2": "working set per step (>3 GB of activations) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e, "unit": "valid mel-frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,

@@ -167,6 +167,7 @@ def test_two_stream_half_batches_equal_single_stream():
     for a, b in zip(o1[3], o2[3]):
         assert (a - b).abs().max().item() <= 1e-5
     assert abs(n1 - n2) <= 1e-5 * abs(n1)
+    gmax = max(v.norm().item() for v in g1.values())
     for k in g1:
         d = (g1[k] - g2[k]).norm().item()
-        assert d <= 2e-3 * (g1[k].norm().item() + 1e-8), (k, d)      # wgrad sums are split differently (fp16 products, fp32 sums)
+        assert d <= 2e-3 * (g1[k].norm().item() + 1e-4 * gmax), (k, d)   # wgrad sums are split differently (fp32 sums of fp16 products)
