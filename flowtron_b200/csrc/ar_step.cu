@@ -6,7 +6,10 @@
 // Precision plan: forward tensor-core operands are fp16 (11-bit significand, same as tf32; every
 // forward operand is either a weight or a bounded activation); backward operands are fp16 too, on gradients
 // multiplied by a per-flow power-of-two loss scale chosen on the device (launch_grad_scale); accumulation, LSTM cell state, softmax, exp/log and all reductions are fp32.
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -104,13 +107,15 @@ struct FwdScratch {
 
 struct BwdScratch {
     W16 w;                      // fp16, natural layouts (w_hh* hold the TRANSPOSED recurrent weights [H, 4H])
-    uint16_t *dG, *do16, *dy2, *dy1, *dQ16, *dK16, *dV16;
+    uint16_t *dG1, *dG0, *dGa, *do16, *dy2, *dy1, *dQ16, *dK16, *dV16;
     float *dh, *dd, *dQ, *dK, *dV, *dmel_flow, *dmel_in, *scale;
     int* flags;
     void plan(Plan& p, const FtArStepDesc& d) {
         const Dims n(d);
         w.plan(p, n);
-        dG = p.get<uint16_t>("dG", n.R * G);
+        dG1 = p.get<uint16_t>("dG1", n.R * G);      // one per LSTM layer: the wgrad GEMMs of a layer run on the side
+        dG0 = p.get<uint16_t>("dG0", n.R * G);      // stream while the next BPTT already writes its own dG
+        dGa = p.get<uint16_t>("dGa", n.R * G);
         do16 = p.get<uint16_t>("do16", n.R * 2 * n.M);
         dy2 = p.get<uint16_t>("dy2", n.R * H);
         dy1 = p.get<uint16_t>("dy1", n.R * H);
@@ -172,6 +177,41 @@ int gemm_wgrad(cudaStream_t st, int N, int K, long long R, const void* dY, long 
     g.alpha_ptr = inv_scale;          // undo the loss scale on the way out
     g.C32 = dW; g.ldc32 = ldw;
     return launch_gemm(g, st);
+}
+
+// Side stream for work that is off the backward critical path (weight gradients, bias column sums): it runs under the
+// next persistent BPTT kernel, which occupies 64 of the 148 SMs.  One side stream + event per caller stream; ordering is
+// by events only (fork: side waits for "main so far"; join: main waits for "side so far").
+struct Side {
+    cudaStream_t s = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+};
+static std::map<cudaStream_t, Side> g_sides;
+static std::mutex g_side_mu;
+static bool g_side_enabled = true;
+
+static Side* get_side(cudaStream_t main) {
+    if (!g_side_enabled) return nullptr;
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    auto it = g_sides.find(main);
+    if (it != g_sides.end()) return &it->second;
+    Side sd;
+    if (cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&sd.ev_main, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&sd.ev_side, cudaEventDisableTiming);
+    g_sides[main] = sd;
+    return &g_sides[main];
+}
+static cudaStream_t fork_side(Side* sd, cudaStream_t main) {      // returns the stream to launch off-path work on
+    if (!sd) return main;
+    cudaEventRecord(sd->ev_main, main);
+    cudaStreamWaitEvent(sd->s, sd->ev_main, 0);
+    return sd->s;
+}
+static void join_side(Side* sd, cudaStream_t main) {
+    if (!sd) return;
+    cudaEventRecord(sd->ev_side, sd->s);
+    cudaStreamWaitEvent(main, sd->ev_side, 0);
 }
 
 int zero(void* p, size_t bytes, cudaStream_t st) {
@@ -282,39 +322,49 @@ int ar_step_bwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
     const float* S = F.scale;            // S[0] = scale, S[1] = 1/scale
     const float* iS = F.scale + 1;
 
+    static int side_env = -1;
+    if (side_env < 0) { const char* e = getenv("FT_SIDE_STREAM"); side_env = e ? atoi(e) : 1; g_side_enabled = side_env != 0; }
+    Side* sd = get_side(st);
+    cudaStream_t ss;
+
     // 1. affine coupling (scales the incoming gradients by S)
     FT_TRY(launch_affine_bwd(d_mel_out, d_log_s, S_.o32, mel_flow, out_lens, n.T, n.B, n.M, d.reversed, F.do16, F.dmel_flow, S, st));
 
-    // 2. 1x1 conv
-    FT_TRY(gemm_wgrad(st, 2 * n.M, H, R, F.do16, 2 * n.M, S_.y2_16, H, g.conv_w, H, iS));
-    FT_TRY(launch_colsum(F.do16, 0, 2 * n.M, R, 2 * n.M, g.conv_b, iS, st));
+    // 2. 1x1 conv     (weight / bias gradients go to the side stream, the dgrad chain stays on `st`)
+    ss = fork_side(sd, st);
+    FT_TRY(gemm_wgrad(ss, 2 * n.M, H, R, F.do16, 2 * n.M, S_.y2_16, H, g.conv_w, H, iS));
+    FT_TRY(launch_colsum(F.do16, 0, 2 * n.M, R, 2 * n.M, g.conv_b, iS, ss));
     FT_TRY(gemm_dgrad(st, R, H, 2 * n.M, F.do16, 2 * n.M, F.w.wc, H, 0, nullptr, 0, F.dy2, H, S_.y2_16, H));     // * (1 - y2^2)
 
     // 3. dense layer 1 (second linear)
-    FT_TRY(gemm_wgrad(st, H, H, R, F.dy2, H, S_.y1_16, H, g.dense_w1, H, iS));
-    FT_TRY(launch_colsum(F.dy2, 0, H, R, H, g.dense_b1, iS, st));
+    ss = fork_side(sd, st);
+    FT_TRY(gemm_wgrad(ss, H, H, R, F.dy2, H, S_.y1_16, H, g.dense_w1, H, iS));
+    FT_TRY(launch_colsum(F.dy2, 0, H, R, H, g.dense_b1, iS, ss));
     FT_TRY(gemm_dgrad(st, R, H, H, F.dy2, H, F.w.w2, H, 0, nullptr, 0, F.dy1, H, S_.y1_16, H));                   // * (1 - y1^2)
 
     // 4. dense layer 0
-    FT_TRY(gemm_wgrad(st, H, H, R, F.dy1, H, S_.h1_16, H, g.dense_w0, H, iS));
-    FT_TRY(launch_colsum(F.dy1, 0, H, R, H, g.dense_b0, iS, st));
+    ss = fork_side(sd, st);
+    FT_TRY(gemm_wgrad(ss, H, H, R, F.dy1, H, S_.h1_16, H, g.dense_w0, H, iS));
+    FT_TRY(launch_colsum(F.dy1, 0, H, R, H, g.dense_b0, iS, ss));
     FT_TRY(gemm_dgrad(st, R, H, H, F.dy1, H, F.w.w1, H, 0, F.dh, H, nullptr, 0, nullptr, 0));
 
     // 5. lstm layer 1
-    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dh, H, F.w.w_hh1, S_.gates1, S_.c1, out_lens, F.dG, F.flags, st));
-    FT_TRY(gemm_wgrad(st, G, H, Rm, F.dG + static_cast<size_t>(n.B) * G, G, S_.h1_16, H, g.lstm_w_hh1, H, iS));
-    FT_TRY(gemm_wgrad(st, G, H, R, F.dG, G, S_.h0_16, H, g.lstm_w_ih1, H, iS));
-    FT_TRY(launch_colsum(F.dG, 0, G, R, G, g.lstm_b_ih1, iS, st));
-    FT_TRY(copy_f32(g.lstm_b_hh1, g.lstm_b_ih1, G, st));
-    FT_TRY(gemm_dgrad(st, R, H, G, F.dG, G, F.w.w_ih1, H, 0, F.dh, H, nullptr, 0, nullptr, 0));
+    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dh, H, F.w.w_hh1, S_.gates1, S_.c1, out_lens, F.dG1, F.flags, st));
+    ss = fork_side(sd, st);
+    FT_TRY(gemm_wgrad(ss, G, H, Rm, F.dG1 + static_cast<size_t>(n.B) * G, G, S_.h1_16, H, g.lstm_w_hh1, H, iS));
+    FT_TRY(gemm_wgrad(ss, G, H, R, F.dG1, G, S_.h0_16, H, g.lstm_w_ih1, H, iS));
+    FT_TRY(launch_colsum(F.dG1, 0, G, R, G, g.lstm_b_ih1, iS, ss));
+    FT_TRY(copy_f32(g.lstm_b_hh1, g.lstm_b_ih1, G, ss));
+    FT_TRY(gemm_dgrad(st, R, H, G, F.dG1, G, F.w.w_ih1, H, 0, F.dh, H, nullptr, 0, nullptr, 0));
 
     // 6. lstm layer 0
-    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dh, H, F.w.w_hh0, S_.gates0, S_.c0, out_lens, F.dG, F.flags, st));
-    FT_TRY(gemm_wgrad(st, G, H, Rm, F.dG + static_cast<size_t>(n.B) * G, G, S_.h0_16, H, g.lstm_w_hh0, H, iS));
-    FT_TRY(gemm_wgrad(st, G, n.D, R, F.dG, G, S_.d16, n.D, g.lstm_w_ih0, n.D, iS));
-    FT_TRY(launch_colsum(F.dG, 0, G, R, G, g.lstm_b_ih0, iS, st));
-    FT_TRY(copy_f32(g.lstm_b_hh0, g.lstm_b_ih0, G, st));
-    FT_TRY(gemm_dgrad(st, R, n.D, G, F.dG, G, F.w.w_ih0, n.D, 0, F.dd, n.D, nullptr, 0, nullptr, 0));
+    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dh, H, F.w.w_hh0, S_.gates0, S_.c0, out_lens, F.dG0, F.flags, st));
+    ss = fork_side(sd, st);
+    FT_TRY(gemm_wgrad(ss, G, H, Rm, F.dG0 + static_cast<size_t>(n.B) * G, G, S_.h0_16, H, g.lstm_w_hh0, H, iS));
+    FT_TRY(gemm_wgrad(ss, G, n.D, R, F.dG0, G, S_.d16, n.D, g.lstm_w_ih0, n.D, iS));
+    FT_TRY(launch_colsum(F.dG0, 0, G, R, G, g.lstm_b_ih0, iS, ss));
+    FT_TRY(copy_f32(g.lstm_b_hh0, g.lstm_b_ih0, G, ss));
+    FT_TRY(gemm_dgrad(st, R, n.D, G, F.dG0, G, F.w.w_ih0, n.D, 0, F.dd, n.D, nullptr, 0, nullptr, 0));
 
     // 7. gate layer (last flow only): dd is in the scaled domain, the gate's own parameter gradients are not
     if (d.has_gate && g.gate_w) {
@@ -339,25 +389,28 @@ int ar_step_bwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
 
     // 9. Q/K/V projections  (d16 = [hA ; ctx] saved in fp16, row pitch D)
     FT_TRY(launch_cast(F.dQ, 2, F.dQ16, 0, R * n.A, st));
-    FT_TRY(gemm_wgrad(st, n.A, H, R, F.dQ16, n.A, S_.d16, n.D, g.att_query, H, iS));
-    FT_TRY(gemm_dgrad(st, R, H, n.A, F.dQ16, n.A, F.w.wq, H, 1, F.dd, n.D, nullptr, 0, nullptr, 0));   // dhA += dQ Wq
     FT_TRY(launch_cast(F.dK, 2, F.dK16, 0, RL * n.A, st));
     FT_TRY(launch_cast(F.dV, 2, F.dV16, 0, RL * n.A, st));
-    FT_TRY(gemm_wgrad(st, n.A, n.E, RL, F.dK16, n.A, S_.text16, n.E, g.att_key, n.E, iS));
-    FT_TRY(gemm_wgrad(st, n.A, n.E, RL, F.dV16, n.A, S_.text16, n.E, g.att_value, n.E, iS));
+    ss = fork_side(sd, st);
+    FT_TRY(gemm_wgrad(ss, n.A, H, R, F.dQ16, n.A, S_.d16, n.D, g.att_query, H, iS));
+    FT_TRY(gemm_wgrad(ss, n.A, n.E, RL, F.dK16, n.A, S_.text16, n.E, g.att_key, n.E, iS));
+    FT_TRY(gemm_wgrad(ss, n.A, n.E, RL, F.dV16, n.A, S_.text16, n.E, g.att_value, n.E, iS));
+    FT_TRY(gemm_dgrad(st, R, H, n.A, F.dQ16, n.A, F.w.wq, H, 1, F.dd, n.D, nullptr, 0, nullptr, 0));   // dhA += dQ Wq
     FT_TRY(gemm_dgrad(st, RL, n.E, n.A, F.dK16, n.A, F.w.wk, n.E, 0, d_text, n.E, nullptr, 0, nullptr, 0, iS));
     FT_TRY(gemm_dgrad(st, RL, n.E, n.A, F.dV16, n.A, F.w.wv, n.E, 1, d_text, n.E, nullptr, 0, nullptr, 0, iS));
 
     // 10. attention_lstm  (dhA = F.dd[:, 0:H], pitch D)
-    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dd, n.D, F.w.w_hh_a, S_.gatesA, S_.cA, out_lens, F.dG, F.flags, st));
-    FT_TRY(gemm_wgrad(st, G, H, Rm, F.dG + static_cast<size_t>(n.B) * G, G, S_.d16, n.D, g.attn_lstm_w_hh, H, iS));
-    FT_TRY(gemm_wgrad(st, G, n.M, R, F.dG, G, S_.mel_in16, n.M, g.attn_lstm_w_ih, n.M, iS));
-    FT_TRY(launch_colsum(F.dG, 0, G, R, G, g.attn_lstm_b_ih, iS, st));
-    FT_TRY(copy_f32(g.attn_lstm_b_hh, g.attn_lstm_b_ih, G, st));
-    FT_TRY(gemm_dgrad(st, R, n.M, G, F.dG, G, F.w.w_ih_a, n.M, 0, F.dmel_in, n.M, nullptr, 0, nullptr, 0));
+    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dd, n.D, F.w.w_hh_a, S_.gatesA, S_.cA, out_lens, F.dGa, F.flags, st));
+    ss = fork_side(sd, st);
+    FT_TRY(gemm_wgrad(ss, G, H, Rm, F.dGa + static_cast<size_t>(n.B) * G, G, S_.d16, n.D, g.attn_lstm_w_hh, H, iS));
+    FT_TRY(gemm_wgrad(ss, G, n.M, R, F.dGa, G, S_.mel_in16, n.M, g.attn_lstm_w_ih, n.M, iS));
+    FT_TRY(launch_colsum(F.dGa, 0, G, R, G, g.attn_lstm_b_ih, iS, ss));
+    FT_TRY(copy_f32(g.attn_lstm_b_hh, g.attn_lstm_b_ih, G, ss));
+    FT_TRY(gemm_dgrad(st, R, n.M, G, F.dGa, G, F.w.w_ih_a, n.M, 0, F.dmel_in, n.M, nullptr, 0, nullptr, 0));
 
     // 11. input gradient: coupling path + (shifted) attention_lstm path, back to natural time, loss scale undone
     if (d_mel) FT_TRY(launch_combine_dmel(F.dmel_flow, F.dmel_in, out_lens, n.T, n.B, n.M, d.reversed, d_mel, iS, st));
+    join_side(sd, st);                   // everything this call launched is ordered before what the caller enqueues next
     return 0;
 }
 
