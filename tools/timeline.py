@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""GPU-idle accounting of one training step with torch.profiler (kernel timeline): busy time vs wall, largest gaps."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torch.profiler import profile, ProfilerActivity
+sys.argv = [sys.argv[0]]
+import bench
+from flowtron_b200 import synth
+from flowtron_b200.flowtron import Flowtron, FlowtronLoss
+
+cfg = dict(synth.DEFAULT_MODEL_CONFIG)
+model = Flowtron(**cfg); model.load_state_dict(synth.synth_params(cfg, 1234), strict=True); model = model.cuda().train()
+crit = FlowtronLoss()
+opt = torch.optim.RAdam(model.parameters(), lr=1e-3, weight_decay=1e-6)
+batch, L = bench.make_batch(cfg, 32, 1000, 1234)
+d = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+def step():
+    opt.zero_grad(set_to_none=True)
+    out = model(d["mel"], d["speaker_ids"], d["text"], d["in_lens"], d["out_lens"], d["attn_prior"])
+    nll, gl, _ = crit(out, d["gate_target"], d["in_lens"], d["out_lens"])
+    (nll + gl).sum().backward()
+    torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+    opt.step()
+
+for _ in range(3): step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for _ in range(2): step()
+    torch.cuda.synchronize()
+ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None]
+ev.sort(key=lambda e: e.time_range.start)
+t0, t1 = ev[0].time_range.start, max(e.time_range.end for e in ev)
+busy, cur_end, gaps = 0.0, t0, []
+for e in ev:
+    s, en = e.time_range.start, e.time_range.end
+    if s > cur_end:
+        gaps.append((s - cur_end, e.name[:60]))
+        busy += en - s
+        cur_end = en
+    elif en > cur_end:
+        busy += en - cur_end
+        cur_end = en
+print(f"wall {(t1 - t0) / 1e3:.2f} ms for 2 steps, GPU busy (union of kernels) {busy / 1e3:.2f} ms, idle {(t1 - t0 - busy) / 1e3:.2f} ms, kernels {len(ev)}")
+gaps.sort(reverse=True)
+print("largest gaps (us, next kernel):", [(round(g, 1), n) for g, n in gaps[:12]])
+big = sum(g for g, _ in gaps if g > 20)
+print(f"gaps > 20 us sum {big / 1e3:.2f} ms ; count of gaps {len(gaps)}")
