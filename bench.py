@@ -252,11 +252,16 @@ def main():
             a["flop"] += (2.0 if name == "attn_fwd" else 6.0) * n * m * k * 640 * cnt
     top = max(by_name.items(), key=lambda kv: kv[1]["ms"]) if by_name else (None, None)
     roof = None
+    traffic_tab = {}
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")     # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tp):
+        traffic_tab = json.load(open(tp))
     if top[0]:
         t = top[1]
         ach = t["flop"] / (t["ms"] / 1e3) / 1e12
         roof = {"kernel": top[0], "bound": "tensor", "achieved": ach, "peak": sustained, "unit": "TFLOP/s", "frac": ach / sustained,
-                "traffic": None, "peak_source": f"{src} bf16 sustained (kernel timed inside a long step)",
+                "traffic": (traffic_tab.get(top[0]) or {}).get("dram_bytes_per_launch") if (B, T) == (32, 1000) else None,
+                "traffic_source": (traffic_tab.get(top[0]) or {}).get("source"), "peak_source": f"{src} bf16 sustained (kernel timed inside a long step)",
                 "launches": t["count"], "avg_ms": t["ms"] / t["count"],
                 "share_of_step": t["ms"] / ms, "note": "latency-bound T-step dependency chain (DESIGN.md): algorithmic FLOPs "
                 "= 2*B*1024*4096*(T-1) per launch"}

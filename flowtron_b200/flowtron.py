@@ -319,7 +319,21 @@ class Flowtron(nn.Module):
     n_streams = 1
     min_split_batch = 8
 
+    max_kernel_batch = 64        # the persistent recurrence kernels take up to 64 utterances per launch
+
     def _run_flows(self, mel, encoder_outputs, mask, out_lens, attn_prior):
+        B = mel.size(1)
+        if B > self.max_kernel_batch:          # larger batches run as consecutive chunks (utterances are independent)
+            outs = [self._run_flows(mel[:, b0:b0 + self.max_kernel_batch], encoder_outputs[:, b0:b0 + self.max_kernel_batch],
+                                    mask[b0:b0 + self.max_kernel_batch],
+                                    None if out_lens is None else out_lens[b0:b0 + self.max_kernel_batch],
+                                    None if attn_prior is None else attn_prior[b0:b0 + self.max_kernel_batch])
+                    for b0 in range(0, B, self.max_kernel_batch)]
+            n_flows = len(self.flows)
+            return (torch.cat([o[0] for o in outs], 1), [torch.cat([o[1][i] for o in outs], 1) for i in range(n_flows)],
+                    None if outs[0][2] is None else torch.cat([o[2] for o in outs], 1),
+                    [torch.cat([o[3][i] for o in outs], 0) for i in range(n_flows)],
+                    [torch.cat([o[4][i] for o in outs], 0) for i in range(n_flows)])
         log_s_list, attns_list, attns_logprob_list, gate = [], [], [], None
         for i, flow in enumerate(self.flows):
             mel, log_s, gate, attn_out, attn_logprob_out = flow(mel, encoder_outputs, mask, out_lens, attn_prior)

@@ -171,3 +171,18 @@ def test_two_stream_half_batches_equal_single_stream():
     for k in g1:
         d = (g1[k] - g2[k]).norm().item()
         assert d <= 2e-3 * (g1[k].norm().item() + 1e-4 * gmax), (k, d)   # wgrad sums are split differently (fp32 sums of fp16 products)
+
+
+def test_batches_larger_than_a_launch_are_chunked():
+    """B > 64 runs as consecutive <= 64-utterance launches; rows must equal the unchunked result."""
+    cfg = dict(synth.DEFAULT_MODEL_CONFIG, n_flows=2)
+    model = build_model(cfg, 13)
+    batch = synth.synth_batch(6, 24, 10, cfg, 3)
+    cu = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    with torch.no_grad():
+        a = model(cu["mel"], cu["speaker_ids"], cu["text"], cu["in_lens"], cu["out_lens"])
+        model.max_kernel_batch = 4
+        b = model(cu["mel"], cu["speaker_ids"], cu["text"], cu["in_lens"], cu["out_lens"])
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+    for x, y in zip(a[1] + a[3], b[1] + b[3]):
+        assert torch.equal(x, y)
