@@ -814,7 +814,9 @@ int launch_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void
         attrs[0].val.clusterDim.x = B4_CLUSTER; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
         attrs[1].id = cudaLaunchAttributeCooperative;
         attrs[1].val.cooperative = 1;
-        cfg.attrs = attrs; cfg.numAttrs = 2;
+        static int coop = -1;          // FT_BWD_COOP=0: plain cluster launch (ncu cannot replay cooperative + cluster launches)
+        if (coop < 0) { const char* e = getenv("FT_BWD_COOP"); coop = e ? atoi(e) : 1; }
+        cfg.attrs = attrs; cfg.numAttrs = coop ? 2 : 1;
         TimeScope ts("lstm_bwd", T, B, 0, st);
         cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_bwd4_kernel, tmWT, tmG, p);
         if (e != cudaSuccess) {                                  // co-residency is implied by 64 CTAs <= SMs; retry without the attribute
