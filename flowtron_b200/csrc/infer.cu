@@ -15,7 +15,7 @@
 namespace ft {
 
 constexpr int IH = 1024, IG = 4096;
-constexpr int IBT = 8;                 // batch tile
+// batch tile IBT is a template parameter (1, 2, 4 or 8): B = 1 must not pay for 8 rows of staging and FMAs
 constexpr int INF_THREADS = 256;
 constexpr int KMAX = 1664 + 1024;      // widest phase input: [d ; h0]
 
@@ -53,6 +53,7 @@ __device__ __forceinline__ void grid_sync(const InferParams& p, int& epoch) {
 }
 
 // stage x[b][0:K] (fp32 global, row pitch ld, batch rows b0..b0+IBT) as fp16 into smem at column offset c0
+template <int IBT>
 __device__ __forceinline__ void stage_x(__half* sx, int c0, const float* src, long long ld, int K, int b0, int B) {
     for (int i = threadIdx.x; i < IBT * K; i += INF_THREADS) {
         const int bb = i / K, k = i % K;
@@ -62,6 +63,7 @@ __device__ __forceinline__ void stage_x(__half* sx, int c0, const float* src, lo
 }
 
 // acc[r][bb] += sum_k W[rows[r], k] * x[bb][c0 + k]   (one warp; K multiple of 8)
+template <int IBT>
 __device__ __forceinline__ void rows4_dot(float (&acc)[4][IBT], const __half* W, int ldw, const int (&rows)[4], int K,
                                           const __half* sx, int c0, int lane) {
     for (int k = lane * 8; k < K; k += 256) {
@@ -94,6 +96,7 @@ __device__ __forceinline__ void rows4_dot(float (&acc)[4][IBT], const __half* W,
     }
 }
 
+template <int IBT>
 __device__ __forceinline__ void reduce_acc(float (&acc)[4][IBT]) {
 #pragma unroll
     for (int r = 0; r < 4; ++r)
@@ -107,6 +110,7 @@ __device__ __forceinline__ void reduce_acc(float (&acc)[4][IBT]) {
 }
 
 // One LSTM layer step for all hidden units: x = [xa (Ka) ; xb (IH)], weights W_ih [4H,Ka], W_hh [4H,IH]
+template <int IBT>
 __device__ void lstm_phase(const InferParams& p, __half* sx, const __half* W_ih, int Ka, const float* xa, long long lda,
                            const __half* W_hh, const float* hprev, const float* b_ih, const float* b_hh, float* c,
                            float* hnew) {
@@ -114,8 +118,8 @@ __device__ void lstm_phase(const InferParams& p, __half* sx, const __half* W_ih,
     const int gw = blockIdx.x * (INF_THREADS / 32) + warp, nw = gridDim.x * (INF_THREADS / 32);
     for (int b0 = 0; b0 < p.B; b0 += IBT) {
         __syncthreads();
-        stage_x(sx, 0, xa, lda, Ka, b0, p.B);
-        stage_x(sx, Ka, hprev, IH, IH, b0, p.B);
+        stage_x<IBT>(sx, 0, xa, lda, Ka, b0, p.B);
+        stage_x<IBT>(sx, Ka, hprev, IH, IH, b0, p.B);
         __syncthreads();
         for (int u = gw; u < IH; u += nw) {
             float acc[4][IBT];
@@ -124,9 +128,9 @@ __device__ void lstm_phase(const InferParams& p, __half* sx, const __half* W_ih,
 #pragma unroll
                 for (int bb = 0; bb < IBT; ++bb) acc[r][bb] = 0.f;
             const int rows[4] = {u, IH + u, 2 * IH + u, 3 * IH + u};
-            rows4_dot(acc, W_ih, Ka, rows, Ka, sx, 0, lane);
-            rows4_dot(acc, W_hh, IH, rows, IH, sx, Ka, lane);
-            reduce_acc(acc);
+            rows4_dot<IBT>(acc, W_ih, Ka, rows, Ka, sx, 0, lane);
+            rows4_dot<IBT>(acc, W_hh, IH, rows, IH, sx, Ka, lane);
+            reduce_acc<IBT>(acc);
             if (lane < IBT && b0 + lane < p.B) {
                 const int b = b0 + lane;
                 float a[4];
@@ -147,13 +151,14 @@ __device__ void lstm_phase(const InferParams& p, __half* sx, const __half* W_ih,
 }
 
 // y[b, r] = act(W[r,:] x[b,:] + bias[r]) for r < R (R multiple of 4), K multiple of 8
+template <int IBT>
 __device__ void dense_phase(const InferParams& p, __half* sx, const __half* W, int K, int R, const float* x, long long ldx,
                             const float* bias, int act, float* y, long long ldy) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * (INF_THREADS / 32) + warp, nw = gridDim.x * (INF_THREADS / 32);
     for (int b0 = 0; b0 < p.B; b0 += IBT) {
         __syncthreads();
-        stage_x(sx, 0, x, ldx, K, b0, p.B);
+        stage_x<IBT>(sx, 0, x, ldx, K, b0, p.B);
         __syncthreads();
         for (int t = gw; t < R / 4; t += nw) {
             float acc[4][IBT];
@@ -162,8 +167,8 @@ __device__ void dense_phase(const InferParams& p, __half* sx, const __half* W, i
 #pragma unroll
                 for (int bb = 0; bb < IBT; ++bb) acc[r][bb] = 0.f;
             const int rows[4] = {4 * t, 4 * t + 1, 4 * t + 2, 4 * t + 3};
-            rows4_dot(acc, W, K, rows, K, sx, 0, lane);
-            reduce_acc(acc);
+            rows4_dot<IBT>(acc, W, K, rows, K, sx, 0, lane);
+            reduce_acc<IBT>(acc);
             if (lane < IBT && b0 + lane < p.B) {
                 const int b = b0 + lane;
 #pragma unroll
@@ -180,6 +185,7 @@ __device__ void dense_phase(const InferParams& p, __half* sx, const __half* W, i
     }
 }
 
+template <int IBT>
 __global__ void __launch_bounds__(INF_THREADS, 1)
 infer_kernel(InferParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -196,10 +202,10 @@ infer_kernel(InferParams p) {
         if (!any) break;
 
         // ---- P1 attention_lstm step on the previous output frame (zeros at i == 0)
-        lstm_phase(p, sx, p.w_ih_a, p.M, p.xprev, p.M, p.w_hh_a, p.hA[prv], p.b_ih_a, p.b_hh_a, p.cA, p.hA[cur]);
+        lstm_phase<IBT>(p, sx, p.w_ih_a, p.M, p.xprev, p.M, p.w_hh_a, p.hA[prv], p.b_ih_a, p.b_hh_a, p.cA, p.hA[cur]);
         grid_sync(p, epoch);
         // ---- P2a query projection (no bias)
-        dense_phase(p, sx, p.wq, IH, p.A, p.hA[cur], IH, nullptr, 0, p.q, p.A);
+        dense_phase<IBT>(p, sx, p.wq, IH, p.A, p.hA[cur], IH, nullptr, 0, p.q, p.A);
         grid_sync(p, epoch);
         // ---- P2b scores e[b,l] = v . tanh(q[b] + K[l,b]) / temperature   (no key mask in inference, flowtron.py:800-803)
         for (int t = gw; t < p.B * p.L; t += nw) {
@@ -296,20 +302,20 @@ infer_kernel(InferParams p) {
         } else if (gw == 0 && lane < p.B) {
             p.n_frames[lane] = i + 1;
         }
-        lstm_phase(p, sx, p.w_ih0, p.D, p.d, p.D, p.w_hh0, p.h0[prv], p.b_ih0, p.b_hh0, p.c0, p.h0[cur]);
+        lstm_phase<IBT>(p, sx, p.w_ih0, p.D, p.d, p.D, p.w_hh0, p.h0[prv], p.b_ih0, p.b_hh0, p.c0, p.h0[cur]);
         grid_sync(p, epoch);
         // ---- P4 lstm layer 1
-        lstm_phase(p, sx, p.w_ih1, IH, p.h0[cur], IH, p.w_hh1, p.h1[prv], p.b_ih1, p.b_hh1, p.c1, p.h1[cur]);
+        lstm_phase<IBT>(p, sx, p.w_ih1, IH, p.h0[cur], IH, p.w_hh1, p.h1[prv], p.b_ih1, p.b_hh1, p.c1, p.h1[cur]);
         grid_sync(p, epoch);
         // ---- P5/P6 dense layers
-        dense_phase(p, sx, p.w1, IH, IH, p.h1[cur], IH, p.b1, 1, p.y1, IH);
+        dense_phase<IBT>(p, sx, p.w1, IH, IH, p.h1[cur], IH, p.b1, 1, p.y1, IH);
         grid_sync(p, epoch);
-        dense_phase(p, sx, p.w2, IH, IH, p.y1, IH, p.b2, 1, p.y2, IH);
+        dense_phase<IBT>(p, sx, p.w2, IH, IH, p.y1, IH, p.b2, 1, p.y2, IH);
         grid_sync(p, epoch);
         // ---- P7 conv + inverse affine: out = (residual - b) / exp(log_s)
         for (int b0 = 0; b0 < p.B; b0 += IBT) {
             __syncthreads();
-            stage_x(sx, 0, p.y2, IH, IH, b0, p.B);
+            stage_x<IBT>(sx, 0, p.y2, IH, IH, b0, p.B);
             __syncthreads();
             for (int t = gw; t < p.M / 2; t += nw) {
                 float acc[4][IBT];
@@ -318,8 +324,8 @@ infer_kernel(InferParams p) {
 #pragma unroll
                     for (int bb = 0; bb < IBT; ++bb) acc[r][bb] = 0.f;
                 const int rows[4] = {2 * t, 2 * t + 1, p.M + 2 * t, p.M + 2 * t + 1};
-                rows4_dot(acc, p.wc, IH, rows, IH, sx, 0, lane);
-                reduce_acc(acc);
+                rows4_dot<IBT>(acc, p.wc, IH, rows, IH, sx, 0, lane);
+                reduce_acc<IBT>(acc);
                 if (lane < IBT && b0 + lane < p.B) {
                     const int b = b0 + lane;
                     float o[4];
@@ -464,11 +470,14 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int smem = IBT * KMAX * 2;
-    cudaFuncSetAttribute(infer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int ibt = B == 1 ? 1 : (B == 2 ? 2 : (B <= 4 ? 4 : 8));
+    void* fn = ibt == 1 ? reinterpret_cast<void*>(infer_kernel<1>) : ibt == 2 ? reinterpret_cast<void*>(infer_kernel<2>)
+             : ibt == 4 ? reinterpret_cast<void*>(infer_kernel<4>) : reinterpret_cast<void*>(infer_kernel<8>);
+    const int smem = ibt * KMAX * 2;
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     TimeScope ts("infer", d->T, B, d->L, st);
     void* args[] = {&p};
-    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(infer_kernel), dim3(sms), dim3(INF_THREADS), args, smem, st);
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(sms), dim3(INF_THREADS), args, smem, st);
     if (e != cudaSuccess) return ft_set_error(cudaGetErrorString(e));
     ft_count_launch(1);
     return ft_check_launch("infer_kernel");
