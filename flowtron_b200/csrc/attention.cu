@@ -50,10 +50,14 @@ __device__ __forceinline__ float exp2x_clamped(float x) {               // e^{2x
     return fast_ex2(2.8853900817779268f * xc);
 }
 
-// score accumulation for one staged (query, key, channel) chunk; NJ = key columns per thread actually needed
+// score accumulation for one staged (query, key, channel) chunk; NJ = key columns per thread actually needed.
+// The MUFU (XU) pipe bounds this loop (ncu r1: 57 % XU, 25 % FMA), so two reciprocals share one MUFU.RCP:
+//   1/x0 = x1 * rcp(x0 x1),  1/x1 = x0 * rcp(x0 x1)      (x = e^{2q} e^{2k} + 1 >= 1)
+// x is clamped to 2^60 so the product stays finite (1/x < 1e-18 there: far below fp32 resolution of tanh = 1 - 2/x).
 template <int NJ>
 __device__ __forceinline__ void score_chunk(float (&acc)[4][8], const float* __restrict__ sQ, const float* __restrict__ sK,
                                             const float* __restrict__ sva, int na, int ty, int tx) {
+    constexpr float kBig = 1152921504606846976.f;     // 2^60
 #pragma unroll 2
     for (int a = 0; a < na; ++a) {
         const float4 q4 = *reinterpret_cast<const float4*>(&sQ[a * SQ_LD + 4 * ty]);
@@ -61,11 +65,16 @@ __device__ __forceinline__ void score_chunk(float (&acc)[4][8], const float* __r
         float k[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) k[j] = sK[a * SK_LD + tx + 16 * j];
-        const float q[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(va, fast_rcp(fmaf(q[i], k[j], 1.0f)), acc[i][j]);
+        for (int j = 0; j < NJ; ++j) {
+            const float x0 = fminf(fmaf(q4.x, k[j], 1.0f), kBig), x1 = fminf(fmaf(q4.y, k[j], 1.0f), kBig);
+            const float x2 = fminf(fmaf(q4.z, k[j], 1.0f), kBig), x3 = fminf(fmaf(q4.w, k[j], 1.0f), kBig);
+            const float w01 = va * fast_rcp(x0 * x1), w23 = va * fast_rcp(x2 * x3);
+            acc[0][j] = fmaf(x1, w01, acc[0][j]);
+            acc[1][j] = fmaf(x0, w01, acc[1][j]);
+            acc[2][j] = fmaf(x3, w23, acc[2][j]);
+            acc[3][j] = fmaf(x2, w23, acc[3][j]);
+        }
     }
 }
 
@@ -115,9 +124,12 @@ attn_fwd_kernel(AttnFwdParams p) {
     }
 
     const int ty = tid >> 4, tx = tid & 15;           // 16 x 16 thread grid: rows 4*ty.., keys tx + 16*j
-    const int nlb = (p.L + AT_LB - 1) / AT_LB;
+    // keys >= in_len are masked to probability exactly 0 (flowtron.py:545-553): their scores are never read, so the
+    // score and context loops stop at this utterance's text length instead of the batch maximum.
+    const int Lk = min(p.L, in_len);
+    const int nlb = (Lk + AT_LB - 1) / AT_LB;
     for (int lb = 0; lb < nlb; ++lb) {
-        const int nl = min(AT_LB, p.L - lb * AT_LB);
+        const int nl = min(AT_LB, Lk - lb * AT_LB);
         const int nj = (nl + 15) >> 4;                // key columns per thread that hold real keys (block-uniform)
         float acc[4][8];
 #pragma unroll
@@ -227,19 +239,19 @@ attn_fwd_kernel(AttnFwdParams p) {
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) c4[i][j] = 0.f;
-        for (int l0 = 0; l0 < p.L; l0 += 64) {
+        for (int l0 = 0; l0 < Lk; l0 += 64) {
             __syncthreads();
             {
                 const int aa = tid & 63;
                 for (int ll = tid >> 6; ll < 64; ll += AT_THREADS / 64) {
                     const int l = l0 + ll;
                     float x = 0.f;
-                    if (l < p.L && ac + aa < p.A) x = p.V[(static_cast<long long>(l) * p.B + b) * p.ldv + ac + aa];
+                    if (l < Lk && ac + aa < p.A) x = p.V[(static_cast<long long>(l) * p.B + b) * p.ldv + ac + aa];
                     sV[ll * SV_LD + aa] = x;
                 }
             }
             __syncthreads();
-            const int nl = min(64, p.L - l0);
+            const int nl = min(64, Lk - l0);
             for (int l = 0; l < nl; ++l) {
                 const float4 v4 = *reinterpret_cast<const float4*>(&sV[l * SV_LD + 4 * tx]);
 #pragma unroll
@@ -299,6 +311,7 @@ attn_bwd_kernel(AttnBwdParams p) {
     float* sD = sK + AT_AC * SK_LD;                   // [AT_TT][SE_LD]  dattn -> de
     float* sv = sD + AT_TT * SE_LD;                   // [A]
     float* sdv = sv + p.A;                            // [A]
+    __shared__ float s_sumde;                         // sum of de over the tile (dv needs sum de (1 - 2r) = sum de - 2 sum de r)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y, t0 = blockIdx.x * AT_TT;
@@ -316,7 +329,10 @@ attn_bwd_kernel(AttnBwdParams p) {
         return;
     }
     for (int i = tid; i < p.A; i += AT_THREADS) { sv[i] = p.v[i]; sdv[i] = 0.f; }
+    if (tid == 0) s_sumde = 0.f;
     const float S = p.scale ? p.scale[0] : 1.f, iS = p.scale ? p.scale[1] : 1.f;
+    // keys >= in_len: attn == 0 and de == 0 exactly (masked softmax), so every key loop below stops at the text length
+    const int Lk = min(p.L, in_len);
 
     // ---------------------------------------------------------------- 1. dattn[t,l] = dctx[t,:] . V[l,:]  (+ext);  dV += attn^T dctx
     for (int i = tid; i < AT_TT * SE_LD; i += AT_THREADS) sD[i] = 0.f;
@@ -336,14 +352,14 @@ attn_bwd_kernel(AttnBwdParams p) {
                 sC[tt * SC_LD + aa] = x;
             }
         }
-        for (int l0 = 0; l0 < p.L; l0 += 64) {
+        for (int l0 = 0; l0 < Lk; l0 += 64) {
             __syncthreads();
             {
                 const int aa = tid & 63;
                 for (int ll = tid >> 6; ll < 64; ll += AT_THREADS / 64) {
                     const int l = l0 + ll;
                     float x = 0.f;
-                    if (l < p.L && ac + aa < p.A) x = p.V[(static_cast<long long>(l) * p.B + b) * p.ldv + ac + aa];
+                    if (l < Lk && ac + aa < p.A) x = p.V[(static_cast<long long>(l) * p.B + b) * p.ldv + ac + aa];
                     sV[ll * SC_LD + aa] = x;
                 }
             }
@@ -384,7 +400,7 @@ attn_bwd_kernel(AttnBwdParams p) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int l = l0 + 4 * ty + i;
-                    const float w = (l < p.L) ? __ldg(attn_b + static_cast<long long>(tt) * p.L + l) : 0.f;
+                    const float w = (l < Lk) ? __ldg(attn_b + static_cast<long long>(tt) * p.L + l) : 0.f;
                     g[i][0] = fmaf(w, c.x, g[i][0]); g[i][1] = fmaf(w, c.y, g[i][1]);
                     g[i][2] = fmaf(w, c.z, g[i][2]); g[i][3] = fmaf(w, c.w, g[i][3]);
                 }
@@ -392,7 +408,7 @@ attn_bwd_kernel(AttnBwdParams p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int l = l0 + 4 * ty + i;
-                if (l < p.L && ac + 4 * tx < p.A) {
+                if (l < Lk && ac + 4 * tx < p.A) {
                     float* dst = p.dV + (static_cast<long long>(l) * p.B + b) * p.lddv + ac + 4 * tx;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) atomicAdd(dst + j, g[i][j]);
@@ -424,7 +440,15 @@ attn_bwd_kernel(AttnBwdParams p) {
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-            for (int l = lane; l < Lr; l += 32) d[l] = (l < in_len) ? at[l] * (d[l] - dot) * p.inv_temperature : 0.f;
+            float sde = 0.f;
+            for (int l = lane; l < Lr; l += 32) {
+                const float de = (l < in_len) ? at[l] * (d[l] - dot) * p.inv_temperature : 0.f;
+                d[l] = de;
+                sde += de;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) sde += __shfl_xor_sync(0xffffffffu, sde, o);
+            if (lane == 0) atomicAdd(&s_sumde, sde);
         } else {
             // attn = softmax(mask(lp)), lp = log(p+1e-20) + log(prior+1e-20), p = softmax(e)
             float dot = 0.f;
@@ -447,29 +471,42 @@ attn_bwd_kernel(AttnBwdParams p) {
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) dot2 += __shfl_xor_sync(0xffffffffu, dot2, o);
+            float sde = 0.f;
             for (int l = lane; l < Lr; l += 32) {
                 const float pr = (l < p.L) ? p.p_save[o0 + l] : 0.f;
-                d[l] = (l < in_len) ? pr * (d[l] - dot2) * p.inv_temperature : 0.f;
+                const float de = (l < in_len) ? pr * (d[l] - dot2) * p.inv_temperature : 0.f;
+                d[l] = de;
+                sde += de;
             }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) sde += __shfl_xor_sync(0xffffffffu, sde, o);
+            if (lane == 0) atomicAdd(&s_sumde, sde);
         }
     }
     __syncthreads();
 
     // ---------------------------------------------------------------- 3. score backward, tanh recomputed
-    // Two reduction-free passes per (channel chunk, key block): in pass A a thread owns (16 rows, 1 channel) and
-    // runs over the keys (-> dQ, dv); in pass B it owns (16 keys, 1 channel) and runs over the rows (-> dK).
-    // Each pass re-evaluates r = 1/(e^{2q} e^{2k} + 1) (tanh = 1 - 2r, 1 - tanh^2 = 4 r (1 - r)); the first version
-    // evaluated it once but paid ~30 shuffles + 8 shared atomics per 32 elements to reduce dQ/dK across threads.
+    // A thread owns (16 rows, 1 channel) and walks the keys: g = de * r (1 - r), r = 1/(e^{2q} e^{2k} + 1), feeds
+    // dQ[row] (register, summed over keys) and dK[key] (register, summed over the thread's 16 rows) from ONE reciprocal
+    // (tanh = 1 - 2r, 1 - tanh^2 = 4 r (1 - r)).  dK is then reduced over the four row groups through a 16 KB shared
+    // buffer once per 16 keys and leaves with one global atomic per (key, channel).  History: v1 evaluated r once but
+    // paid ~30 shuffles + 8 shared atomics per 32 elements; v2 ran two reduction-free passes (2 MUFU per element) and
+    // sat at the MUFU bound (ncu r1: XU 52 %, 2.5 ms); this version has 1 MUFU + 6 FMA-pipe ops per element.
     {
         constexpr int QP = 65;                        // [row][channel] pitch: lanes walk channels -> conflict-free
+        constexpr int KB3 = 64;                       // keys staged per block
+        constexpr int KS = 16;                        // keys per dK reduction round
         float* sQt = sQ;                              // [AT_TT][QP]
-        float* sKt = sK;                              // [AT_LB][QP]
-        const int a_l = tid & 63, grp = tid >> 6;     // channel lane; row group (pass A) / key group (pass B)
+        float* sKt = sK;                              // [KB3][QP]
+        float* sRed = sK + KB3 * QP;                  // [4 row groups][KS][64]   (4160 + 4096 floats <= AT_AC * SK_LD)
+        static_assert(KB3 * QP + 4 * KS * 64 <= AT_AC * SK_LD, "phase-3 buffers must fit in sK");
+        const int a_l = tid & 63, grp = tid >> 6;     // channel lane; row group
+        const float sumde = s_sumde;
         for (int ac = 0; ac < p.A; ac += AT_AC) {
             float dq[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) dq[i] = 0.f;
-            float dva = 0.f;
+            float dvr = 0.f;                          // sum de * r
             const bool a_ok = ac + a_l < p.A;
             __syncthreads();
             for (int i = tid; i < AT_TT * AT_AC; i += AT_THREADS) {
@@ -478,68 +515,59 @@ attn_bwd_kernel(AttnBwdParams p) {
                 if (tt < nrows && ac + aa < p.A) q = p.Q[(static_cast<long long>(t0 + tt) * p.B + b) * p.ldq + ac + aa];
                 sQt[tt * QP + aa] = exp2x_clamped(q);
             }
-            for (int lb = 0; lb < nlb; ++lb) {
-                const int nl = min(AT_LB, p.L - lb * AT_LB);
+            for (int l0 = 0; l0 < Lk; l0 += KB3) {
+                const int nl = min(KB3, Lk - l0);
+                const int nl4 = (nl + 3) & ~3;        // de is 0 in [Lk, Lr): padded keys only need finite e^{2k}
                 __syncthreads();
-                for (int i = tid; i < AT_LB * AT_AC; i += AT_THREADS) {
+                for (int i = tid; i < nl4 * AT_AC; i += AT_THREADS) {
                     const int ll = i >> 6, aa = i & 63;
-                    const int l = lb * AT_LB + ll;
+                    const int l = l0 + ll;
                     float k = 0.f;
-                    if (l < p.L && ac + aa < p.A) k = p.K[(static_cast<long long>(l) * p.B + b) * p.ldk + ac + aa];
+                    if (l < Lk && ac + aa < p.A) k = p.K[(static_cast<long long>(l) * p.B + b) * p.ldk + ac + aa];
                     sKt[ll * QP + aa] = exp2x_clamped(k);
                 }
                 __syncthreads();
-                {   // ---- pass A: dQ[t, a] += sum_l de[t,l] r (1 - r) ;  dv[a] += sum de (1 - 2 r)
-                    float eq[16];
+                float eq[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) eq[i] = sQt[(grp * 16 + i) * QP + a_l];
-                    const int nl4 = (nl + 3) & ~3;    // de is 0 in [L, Lr)
-                    for (int l = 0; l < nl4; l += 4) {
-                        float ek[4];
+                for (int i = 0; i < 16; ++i) eq[i] = sQt[(grp * 16 + i) * QP + a_l];
+                for (int s0 = 0; s0 < nl; s0 += KS) {
+                    const int ns = min(KS, nl - s0);
+                    float dk[KS];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) ek[j] = sKt[(l + j) * QP + a_l];
+                    for (int j = 0; j < KS; ++j) dk[j] = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float4 d4 = *reinterpret_cast<const float4*>(&sD[(grp * 16 + i) * SE_LD + lb * AT_LB + l]);
-                            const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+                    for (int j4 = 0; j4 < KS / 4; ++j4) {
+                        if (4 * j4 < ns) {            // block-uniform
+                            float ek[4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float r = fast_rcp(fmaf(eq[i], ek[j], 1.0f));
-                                dq[i] = fmaf(dd[j], fmaf(-r, r, r), dq[i]);
-                                dva = fmaf(dd[j], fmaf(-2.f, r, 1.f), dva);
+                            for (int e = 0; e < 4; ++e) ek[e] = sKt[(s0 + 4 * j4 + e) * QP + a_l];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float4 d4 = *reinterpret_cast<const float4*>(&sD[(grp * 16 + i) * SE_LD + l0 + s0 + 4 * j4]);
+                                const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float r = fast_rcp(fmaf(eq[i], ek[e], 1.0f));
+                                    const float m = dd[e] * fmaf(-r, r, r);
+                                    dq[i] += m;
+                                    dk[4 * j4 + e] += m;
+                                    dvr = fmaf(dd[e], r, dvr);
+                                }
                             }
                         }
                     }
-                }
-                // ---- pass B: dK[l, a] += sum_t de[t,l] r (1 - r)   (two 64-key halves, 16 keys per thread)
-                for (int half = 0; half < 2; ++half) {
-                    const int lo = half * 64 + grp * 16;
-                    if (lo >= nl) continue;           // warp-uniform
-                    float ek[16], dk[16];
+                    __syncthreads();                  // previous round's readers of sRed are done
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) { ek[j] = sKt[(lo + j) * QP + a_l]; dk[j] = 0.f; }
-                    for (int tt = 0; tt < nrows; ++tt) {
-                        const float eqv = sQt[tt * QP + a_l];
-                        const float* drow = sD + tt * SE_LD + lb * AT_LB + lo;
+                    for (int j = 0; j < KS; ++j) sRed[(grp * KS + j) * 64 + a_l] = dk[j];
+                    __syncthreads();
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const float4 d4 = *reinterpret_cast<const float4*>(drow + 4 * j4);
-                            const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float r = fast_rcp(fmaf(eqv, ek[4 * j4 + e], 1.0f));
-                                dk[4 * j4 + e] = fmaf(dd[e], fmaf(-r, r, r), dk[4 * j4 + e]);
-                            }
-                        }
-                    }
-                    if (a_ok) {
-                        const float s4 = 4.f * sv[ac + a_l];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int l = lb * AT_LB + lo + j;
-                            const float x = dk[j] * s4;
-                            if (l < p.L && x != 0.f) atomicAdd(p.dK + (static_cast<long long>(l) * p.B + b) * p.lddk + ac + a_l, x);
-                        }
+                    for (int k4 = 0; k4 < (KS * 64) / AT_THREADS; ++k4) {
+                        const int idx = tid + AT_THREADS * k4;
+                        const int j = idx >> 6, aa = idx & 63;
+                        const float x = (sRed[(0 * KS + j) * 64 + aa] + sRed[(1 * KS + j) * 64 + aa]) +
+                                        (sRed[(2 * KS + j) * 64 + aa] + sRed[(3 * KS + j) * 64 + aa]);
+                        if (j < ns && ac + aa < p.A && x != 0.f)
+                            atomicAdd(p.dK + (static_cast<long long>(l0 + s0 + j) * p.B + b) * p.lddk + ac + aa, x * 4.f * sv[ac + aa]);
                     }
                 }
             }
@@ -550,7 +578,7 @@ attn_bwd_kernel(AttnBwdParams p) {
                     const int tt = grp * 16 + i;
                     if (tt < nrows) p.dQ[(static_cast<long long>(t0 + tt) * p.B + b) * p.lddq + ac + a_l] = dq[i] * s4;
                 }
-                atomicAdd(&sdv[ac + a_l], dva);
+                atomicAdd(&sdv[ac + a_l], (grp == 0 ? sumde : 0.f) - 2.f * dvr);
             }
         }
     }

@@ -105,18 +105,34 @@ class Encoder(nn.Module):
         self.lstm = nn.LSTM(encoder_embedding_dim, int(encoder_embedding_dim / 2), 1, batch_first=True, bidirectional=True)
         self.p_dropout = 0.5        # flowtron.py:502 hard-codes 0.5; exposed so tests can run deterministic train-mode steps
 
+    def _lstm_dir(self, x, sfx):
+        """One direction of the BiLSTM on a padded [B, L, C] batch (cuDNN's persistent padded path)."""
+        w = [getattr(self.lstm, n + sfx) for n in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")]
+        h0 = x.new_zeros(1, x.size(0), self.lstm.hidden_size)
+        out, _, _ = torch._VF.lstm(x, (h0, h0), w, True, 1, 0.0, self.training, False, True)
+        return out
+
     def forward(self, x, in_lens):
-        mask = get_mask_from_lengths(in_lens).unsqueeze(1) if x.size(0) > 1 else None
+        """Same result as the reference's packed BiLSTM (flowtron.py:505-512) without packing: the forward direction is
+        causal, so running it over the padded batch and zeroing t >= len is identical; the reverse direction runs on
+        each utterance reversed inside its own length (one gather in, one gather out).  This replaces ~1500 per-time-step
+        cuDNN kernels (and the host sync of `in_lens.cpu()`) by two persistent-LSTM calls.  Requires the text batch to be
+        padded to max(in_lens), which DataCollate guarantees (data.py:200-208)."""
+        Bn, _, L = x.shape
+        ar = torch.arange(L, device=x.device)
+        valid = ar[None, :] < in_lens[:, None]                                   # [B, L]
+        mask = valid.unsqueeze(1) if Bn > 1 else None
         for conv, norm in self.convolutions:
             if mask is not None:
                 x = x.masked_fill(~mask, 0.)
             x = F.dropout(F.relu(norm(conv(x), mask=mask)), self.p_dropout, self.training)
-        x = x.transpose(1, 2)
-        x = nn.utils.rnn.pack_padded_sequence(x, in_lens.cpu(), batch_first=True)
-        self.lstm.flatten_parameters()
-        outputs, _ = self.lstm(x)
-        outputs, _ = nn.utils.rnn.pad_packed_sequence(outputs, batch_first=True)
-        return outputs
+        x = x.transpose(1, 2).contiguous()                                        # [B, L, C]
+        rev = torch.where(valid, in_lens[:, None] - 1 - ar[None, :], ar[None, :])   # per-utterance time reversal (involution)
+        fwd = self._lstm_dir(x, "")
+        gidx = rev[..., None].expand(-1, -1, x.size(2))
+        bwd = self._lstm_dir(torch.gather(x, 1, gidx), "_reverse")
+        bwd = torch.gather(bwd, 1, rev[..., None].expand(-1, -1, bwd.size(2)))
+        return torch.cat([fwd, bwd], -1) * valid[..., None].to(x.dtype)
 
     def infer(self, x):
         for conv in self.convolutions:
@@ -351,7 +367,8 @@ class Flowtron(nn.Module):
         text = text.transpose(0, 1)
         mel = mel.permute(2, 0, 1)
         encoder_outputs = torch.cat([text, speaker_vecs.expand(text.size(0), -1, -1)], 2)
-        mask = ~get_mask_from_lengths(in_lens)[..., None]
+        # key-padding mask from the padded text length (== max(in_lens) by the collate contract): no .item() host sync
+        mask = ~(torch.arange(text.size(0), device=in_lens.device)[None, :] < in_lens[:, None])[..., None]
         B = mel.size(1)
         split = self.n_streams > 1 and mel.is_cuda and B >= self.min_split_batch and out_lens is not None
         if mel.is_cuda:

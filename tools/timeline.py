@@ -32,18 +32,33 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None]
 ev.sort(key=lambda e: e.time_range.start)
 t0, t1 = ev[0].time_range.start, max(e.time_range.end for e in ev)
-busy, cur_end, gaps = 0.0, t0, []
+busy, cur_end, gaps, prev = 0.0, t0, [], ev[0]
 for e in ev:
     s, en = e.time_range.start, e.time_range.end
     if s > cur_end:
-        gaps.append((s - cur_end, e.name[:60]))
+        gaps.append((s - cur_end, prev.name[:40], e.name[:40]))
         busy += en - s
-        cur_end = en
+        cur_end, prev = en, e
     elif en > cur_end:
         busy += en - cur_end
-        cur_end = en
+        cur_end, prev = en, e
 print(f"wall {(t1 - t0) / 1e3:.2f} ms for 2 steps, GPU busy (union of kernels) {busy / 1e3:.2f} ms, idle {(t1 - t0 - busy) / 1e3:.2f} ms, kernels {len(ev)}")
 gaps.sort(reverse=True)
-print("largest gaps (us, next kernel):", [(round(g, 1), n) for g, n in gaps[:12]])
-big = sum(g for g, _ in gaps if g > 20)
-print(f"gaps > 20 us sum {big / 1e3:.2f} ms ; count of gaps {len(gaps)}")
+print("largest gaps (us, prev kernel -> next kernel):")
+for g, a, b in gaps[:25]:
+    print(f"  {g:8.1f}  {a}  ->  {b}")
+for thr in (5, 20, 100):
+    print(f"gaps > {thr} us: sum {sum(g for g, _, _ in gaps if g > thr) / 1e3:.2f} ms, count {sum(1 for g, _, _ in gaps if g > thr)}")
+print(f"gaps <= 5 us: sum {sum(g for g, _, _ in gaps if g <= 5) / 1e3:.2f} ms, count {sum(1 for g, _, _ in gaps if g <= 5)}")
+agg = {}
+for e in ev:
+    k = e.name[:48]
+    a = agg.setdefault(k, [0.0, 0]); a[0] += e.time_range.end - e.time_range.start; a[1] += 1
+print("per-kernel GPU time over 2 steps (ms, launches):")
+for k, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:30]:
+    print(f"  {t / 1e3:8.3f} {n:5d}  {k}")
+import time
+torch.cuda.synchronize(); c0 = time.perf_counter()
+for _ in range(3): step()
+c1 = time.perf_counter(); torch.cuda.synchronize(); c2 = time.perf_counter()
+print(f"host issue time per step {(c1 - c0) / 3 * 1e3:.1f} ms ; wall per step {(c2 - c0) / 3 * 1e3:.1f} ms")
