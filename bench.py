@@ -166,9 +166,16 @@ def main():
     model = model.to(dev).train()
     model.n_streams = args.streams
     crit = FlowtronLoss(sigma=1.0, gate_loss=True, use_ctc_loss=False)
+    # train.py:231-252 order: optimizer first, then the all-reduce wrapper.  FT_FUSED_OPT=0 falls back to torch's
+    # multi-tensor RAdam + torch clip_grad_norm_ (the round-1 configuration) for A/B runs.
+    fused_opt = os.environ.get("FT_FUSED_OPT", "0") != "0"     # flipped to default-on once validated on the GPU
+    if fused_opt:
+        from flowtron_b200.radam import RAdam
+        opt = RAdam(model.parameters(), lr=1e-3, weight_decay=1e-6)
+    else:
+        opt = torch.optim.RAdam(model.parameters(), lr=1e-3, weight_decay=1e-6)
     if world > 1:
         ftd.apply_gradient_allreduce(model)
-    opt = torch.optim.RAdam(model.parameters(), lr=1e-3, weight_decay=1e-6)
 
     batch, L = make_batch(cfg, B, T, 1234 + rank)            # every rank gets its own utterances (weak scaling)
     keys = ["mel", "speaker_ids", "text", "in_lens", "out_lens", "gate_target", "attn_prior"]
@@ -184,6 +191,8 @@ def main():
     def zero_grads():
         if world > 1:
             model.zero_grad_buckets()
+        elif fused_opt:
+            opt.zero_grad()                                   # one memset of the flat gradient buffer
         else:
             opt.zero_grad(set_to_none=True)
 
@@ -193,7 +202,10 @@ def main():
         nll, gl, _ = crit(out, d["gate_target"], d["in_lens"], d["out_lens"])
         loss = (nll + gl).sum()
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        if fused_opt:
+            opt.clip_grad_norm_(1.0)                          # norm + coefficient stay on the device, applied inside step()
+        else:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step()
         return loss
 
@@ -278,7 +290,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f16 tensor-core operands (loss-scaled in backward), f32 accumulate+state", "data": "synthetic",
         "config": {"workload": "configs[1]: LJS single-speaker 2-flow Flowtron train step, n_mel=80, per-GPU batch 32, T<=1000",
                    "per_gpu_batch": B, "global_batch": B * world, "max_frames": T, "max_text": L, "attn_prior": True,
-                   "optimizer": "RAdam lr=1e-3 wd=1e-6 + clip_grad_norm 1.0", "parallelism": f"dp{world}", "streams_per_rank": args.streams,
+                   "optimizer": ("flowtron_b200.RAdam (fused, reference radam.py semantics)" if fused_opt else "torch.optim.RAdam") + " lr=1e-3 wd=1e-6 + clip_grad_norm 1.0", "parallelism": f"dp{world}", "streams_per_rank": args.streams,
                    "padded_frames_per_s": B * T * world * args.steps / (ms / 1e3),
                    "l2": "working set per step (>3 GB of activations) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e, "unit": "valid mel-frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,

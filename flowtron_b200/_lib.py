@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
+from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 import torch
 
@@ -96,6 +96,13 @@ def _declare(L):
     L.ft_nll_grad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.ft_nll_grad.restype = c_int
+    L.ft_sumsq_partials.argtypes = [c_void_p, c_longlong, c_void_p, c_void_p]
+    L.ft_sumsq_partials.restype = c_int
+    L.ft_clip_coef.argtypes = [c_void_p, c_int, c_float, c_void_p, c_void_p]
+    L.ft_clip_coef.restype = c_int
+    L.ft_radam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_double, c_double, c_double, c_double,
+                                c_double, c_int, c_void_p, c_void_p]
+    L.ft_radam_step.restype = c_int
 
 
 def check(rc: int, what: str = ""):
@@ -256,6 +263,44 @@ def nll_grad(z, gate, gate_target, out_lens, sigma, sums, g_nll, g_gate, dz, dlo
     T, B, M = z.shape
     check(lib().ft_nll_grad(ptr(z), ptr(gate), ptr(gate_target), ptr(out_lens), T, B, M, float(sigma), ptr(sums),
                             ptr(g_nll), ptr(g_gate), ptr(dz), ptr(dlog_s), ptr(dgate), stream_ptr()), "ft_nll_grad")
+
+
+SUMSQ_PARTIALS = 1024
+
+
+def sumsq_partials(x, partials):
+    """x: flat f32 CUDA tensor; partials: f32 [1024] (written)."""
+    _need_cuda(x, partials)
+    assert x.dtype == torch.float32 and x.is_contiguous() and partials.numel() >= SUMSQ_PARTIALS
+    check(lib().ft_sumsq_partials(ptr(x), x.numel(), ptr(partials), stream_ptr()), "ft_sumsq_partials")
+
+
+def clip_coef(partials, n_partials, max_norm, norm_coef):
+    _need_cuda(partials, norm_coef)
+    check(lib().ft_clip_coef(ptr(partials), int(n_partials), float(max_norm), ptr(norm_coef), stream_ptr()), "ft_clip_coef")
+
+
+def radam_step(p, g, m, v, beta1, beta2, eps, weight_decay_lr, step_size, use_denom, grad_coef=None):
+    """In-place fused RAdam update of flat f32 CUDA tensors (radam.py:77-122)."""
+    _need_cuda(p, g, m, v)
+    n = p.numel()
+    assert g.numel() == n and m.numel() == n and v.numel() == n
+    for t in (p, g, m, v):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    check(lib().ft_radam_step(ptr(p), ptr(g), ptr(m), ptr(v), n, float(beta1), float(beta2), float(eps),
+                              float(weight_decay_lr), float(step_size), 1 if use_denom else 0, ptr(grad_coef), stream_ptr()),
+          "ft_radam_step")
+
+
+def sumsq_partials_raw(x_ptr: int, n: int, partials_ptr: int):
+    check(lib().ft_sumsq_partials(c_void_p(x_ptr), int(n), c_void_p(partials_ptr), stream_ptr()), "ft_sumsq_partials")
+
+
+def radam_step_raw(p_ptr, g_ptr, m_ptr, v_ptr, n, beta1, beta2, eps, weight_decay_lr, step_size, use_denom, coef_ptr=0):
+    """Raw-pointer form used by flowtron_b200.radam (runs of parameters inside flat buffers)."""
+    check(lib().ft_radam_step(c_void_p(p_ptr), c_void_p(g_ptr), c_void_p(m_ptr), c_void_p(v_ptr), int(n), float(beta1),
+                              float(beta2), float(eps), float(weight_decay_lr), float(step_size), 1 if use_denom else 0,
+                              c_void_p(coef_ptr) if coef_ptr else None, stream_ptr()), "ft_radam_step")
 
 
 def ar_step_infer(desc, weights, residual, text, prior, gate_threshold, out, attn_out, n_frames):

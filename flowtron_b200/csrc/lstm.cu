@@ -786,6 +786,11 @@ int launch_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const i
     p.gates = static_cast<__half*>(gates16); p.cstate = cstate; p.h32 = h32; p.ldh32 = ldh32;
     p.flags = flags; p.status = ft_status_word(); p.trace = g_lstm_trace;
     if (g_half_sm && B <= 32) return launch_fwd_t<8, 16>(p, whh16, hseq16, ldh, T, B, flags, st);
+    static int gs = -1;            // FT_LSTM_FWD_GS: K-chunks per TMA group (16 / gs groups per step), tuning knob
+    if (gs < 0) { const char* e = getenv("FT_LSTM_FWD_GS"); gs = e ? atoi(e) : 8; }
+    if (gs == 4) return launch_fwd_t<4, 8>(p, whh16, hseq16, ldh, T, B, flags, st);
+    if (gs == 2) return launch_fwd_t<2, 8>(p, whh16, hseq16, ldh, T, B, flags, st);
+    if (gs == 16) return launch_fwd_t<16, 8>(p, whh16, hseq16, ldh, T, B, flags, st);
     return launch_fwd_t<8, 8>(p, whh16, hseq16, ldh, T, B, flags, st);
 }
 

@@ -21,6 +21,16 @@ import torch.distributed as dist
 from torch.autograd import Variable
 
 
+def flat_offsets(tensors, align: int = 64):
+    """(offsets, total): tensors packed back to back, each start rounded up to `align` elements (== radam.flat_offsets;
+    duplicated here so this module keeps working without the CUDA library)."""
+    offs, off = [], 0
+    for t in tensors:
+        offs.append(off)
+        off += (t.numel() + align - 1) // align * align
+    return offs, off
+
+
 def reduce_tensor(tensor, num_gpus):
     rt = tensor.clone()
     dist.all_reduce(rt, op=dist.ReduceOp.SUM)
@@ -63,12 +73,15 @@ class _Bucket:
     def __init__(self, params):
         self.params = params
         dev = params[0].device
-        n = sum(p.numel() for p in params)
+        # same 256-byte-aligned packing as the fused optimizer's flat parameter buffer (radam.flat_offsets), so a bucket
+        # is one contiguous run for it; the padding stays zero (AVG of zeros)
+        self.offsets, n = flat_offsets(params)
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
-        off = 0
-        for p in params:
+        for p, off in zip(params, self.offsets):
+            old = p.grad
             p.grad = self.flat[off: off + p.numel()].view_as(p)     # autograd accumulates in place into the bucket
-            off += p.numel()
+            if old is not None:
+                p.grad.copy_(old)
         self.ready = 0
         self.work = None
 
@@ -116,12 +129,10 @@ def apply_gradient_allreduce(module):
                 Variable._execution_engine.queue_callback(finalize)
             if param.grad.data_ptr() < b.flat.data_ptr() or param.grad.data_ptr() >= b.flat.data_ptr() + b.flat.numel() * 4:
                 # someone replaced .grad (e.g. zero_grad(set_to_none=True)): fold it back into the bucket
-                off = 0
-                for q in b.params:
+                for q, off in zip(b.params, b.offsets):
                     if q is param:
                         b.flat[off: off + q.numel()].view_as(q).copy_(param.grad)
                         param.grad = b.flat[off: off + q.numel()].view_as(q)
-                    off += q.numel()
             b.ready += 1
             if b.ready == len(b.params):
                 launch(b)

@@ -124,6 +124,21 @@ int ft_nll_grad(const float* z, const float* gate, const float* gate_target, con
                 float sigma, const float* sums, const float* g_nll, const float* g_gate, float* dz, float* dlog_s,
                 float* dgate, void* stream);
 
+/* Optimizer step of the training loop around the hot path (SURVEY.md 8f "next"): torch.nn.utils.clip_grad_norm_
+ * (train.py:324-329) followed by RAdam.step (radam.py:44-122), on flat fp32 device buffers, no host sync.
+ *   ft_sumsq_partials: partials[0..1023] = per-block sums of x[i]^2 over x[0..n) (one call per contiguous gradient
+ *     segment, each into its own 1024 floats);
+ *   ft_clip_coef: norm_coef[0] = sqrt(sum partials) (the total gradient norm clip_grad_norm_ returns),
+ *     norm_coef[1] = min(1, max_norm / (norm + 1e-6)) (the factor it multiplies every gradient by);
+ *   ft_radam_step: p, m (exp_avg), v (exp_avg_sq) updated in place from g * grad_coef[0] (grad_coef NULL = 1):
+ *     v = beta2 v + (1-beta2) g^2; m = beta1 m + (1-beta1) g; p -= weight_decay_lr p (weight_decay*lr, radam.py:109);
+ *     use_denom (N_sma >= 5, radam.py:115): p -= step_size m / (sqrt(v) + eps), else p -= step_size m.
+ *     N_sma / step_size are the host scalars of radam.py:87-107. */
+int ft_sumsq_partials(const float* x, long long n, float* partials, void* stream);
+int ft_clip_coef(const float* partials, int n_partials, float max_norm, float* norm_coef, void* stream);
+int ft_radam_step(float* p, const float* g, float* m, float* v, long long n, double beta1, double beta2, double eps,
+                  double weight_decay_lr, double step_size, int use_denom, const float* grad_coef, void* stream);
+
 /* AR_Step.infer (flowtron.py:775-828): sequential inverse of one flow for all T frames in ONE persistent launch.
  *   residual [T,B,M] f32 in flow-time order (the caller flips for AR_Back_Step, :629-642), text [L,B,E] f32,
  *   attn_prior [B,T,L] or NULL (row i is used at frame i).  Uses d->T/B/L/n_*, has_gate, has_prior, temperature.

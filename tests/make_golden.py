@@ -6,7 +6,7 @@ Run in the build container only (the GPU box has no /root/reference):
 Weights come from oracle.synth.synth_params(cfg, seed), so fixtures carry outputs only.
 Reference entry points exercised: Flowtron.forward (flowtron.py:870-899), FlowtronLoss.forward
 (:200-243), autograd of both, Flowtron.infer (:901-930), TacotronSTFT.mel_spectrogram
-(audio_processing.py:117-134).
+(audio_processing.py:117-134), RAdam.step (radam.py:44-122) after clip_grad_norm_ (train.py:326).
 """
 from __future__ import annotations
 
@@ -103,6 +103,36 @@ def mel_case():
     print("mel: ", {k: tuple(rec[f'mel_{k}'].shape) for k in sigs})
 
 
+def radam_case():
+    """Trajectory of the UNMODIFIED reference optimizer (radam.py:25-122) preceded by train.py:326's clip, CPU fp32."""
+    import warnings
+    sys.path.insert(0, "/root/reference")
+    from radam import RAdam
+    g = torch.Generator().manual_seed(77)
+    shapes = [(7, 5), (33,), (1,)]
+    ps = [torch.nn.Parameter(torch.randn(*s, generator=g)) for s in shapes]
+    opt = RAdam(ps, lr=1e-3, weight_decay=1e-6)
+    rec = {"n_steps": np.int64(9), "max_norm": np.float32(1.0)}
+    for i, p in enumerate(ps):
+        rec[f"p0_{i}"] = p.detach().numpy().copy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for s in range(9):                       # steps 1-5 take the N_sma < 5 branch, 6+ the adaptive one
+            for i, p in enumerate(ps):
+                p.grad = torch.randn(*shapes[i], generator=g) * (3.0 if s % 2 else 0.05)
+                rec[f"g{s}_{i}"] = p.grad.numpy().copy()
+            total = torch.nn.utils.clip_grad_norm_(ps, 1.0)
+            rec[f"norm{s}"] = total.numpy().copy()
+            opt.step()
+            for i, p in enumerate(ps):
+                rec[f"p{s + 1}_{i}"] = p.detach().numpy().copy()
+    for i, p in enumerate(ps):
+        rec[f"m_{i}"] = opt.state[p]["exp_avg"].numpy().copy()
+        rec[f"v_{i}"] = opt.state[p]["exp_avg_sq"].numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "radam.npz"), **rec)
+    print("radam: 9 steps recorded")
+
+
 def main():
     assert ref_shims.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -115,7 +145,11 @@ def main():
     infer_case("b1gate", n_flows=2, B=1, T=48, L=20, seed=6, gate_bias=0.25)
     infer_case("b4nogate", n_flows=2, B=4, T=32, L=16, seed=8, gate_bias=0.0, use_gate=False)
     mel_case()
+    radam_case()
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "radam":     # regenerate only the optimizer fixture
+        radam_case()
+    else:
+        main()

@@ -136,3 +136,23 @@ def test_beta_binomial_prior_matches_scipy():
     ours = synth.beta_binomial_prior(P, M)
     ref = O.beta_binomial_prior(P, M)
     assert np.allclose(ours, ref, rtol=1e-9, atol=1e-12)
+
+
+def test_radam_oracle_matches_reference_trajectory():
+    """oracle.radam_oracle vs the unmodified reference RAdam + clip_grad_norm_ (tests/golden/radam.npz)."""
+    from oracle import radam_oracle as R
+    g = np.load(os.path.join(GOLDEN, "radam.npz"))
+    n = int(g["n_steps"])
+    ps = [torch.from_numpy(g[f"p0_{i}"]) for i in range(3)]
+    ms = [torch.zeros_like(p) for p in ps]
+    vs = [torch.zeros_like(p) for p in ps]
+    for s in range(n):
+        grads = [torch.from_numpy(g[f"g{s}_{i}"]) for i in range(3)]
+        total, coef = R.clip_coef(grads, float(g["max_norm"]))
+        assert abs(float(total) - float(g[f"norm{s}"])) <= 1e-6 * float(total)
+        for i in range(3):
+            ps[i], ms[i], vs[i] = R.radam_step(ps[i], grads[i] * coef, ms[i], vs[i], s + 1, lr=1e-3, weight_decay=1e-6)
+            torch.testing.assert_close(ps[i], torch.from_numpy(g[f"p{s + 1}_{i}"]), rtol=2e-6, atol=1e-7)
+    for i in range(3):
+        torch.testing.assert_close(ms[i], torch.from_numpy(g[f"m_{i}"]), rtol=2e-6, atol=1e-8)
+        torch.testing.assert_close(vs[i], torch.from_numpy(g[f"v_{i}"]), rtol=2e-6, atol=1e-10)
