@@ -96,6 +96,8 @@ def _declare(L):
     L.ft_nll_grad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.ft_nll_grad.restype = c_int
+    L.ft_ar_step_set_text_ready_event.argtypes = [c_void_p]
+    L.ft_ar_step_set_text_ready_event.restype = None
     L.ft_sumsq_partials.argtypes = [c_void_p, c_longlong, c_void_p, c_void_p]
     L.ft_sumsq_partials.restype = c_int
     L.ft_clip_coef.argtypes = [c_void_p, c_int, c_float, c_void_p, c_void_p]
@@ -244,6 +246,11 @@ def ar_step_fwd(desc, weights, mel, text, in_lens, out_lens, prior, mel_out, log
     check(lib().ft_ar_step_fwd(byref(desc), byref(weights), ptr(mel), ptr(text), ptr(in_lens), ptr(out_lens), ptr(prior),
                                ptr(mel_out), ptr(log_s), ptr(gates), ptr(attn), ptr(logprob), ptr(saved), ptr(scratch),
                                stream_ptr()), "ft_ar_step_fwd")
+
+
+def set_text_ready_event(event):
+    """event: a recorded torch.cuda.Event (or None).  Consumed by the next ar_step_fwd on this thread."""
+    lib().ft_ar_step_set_text_ready_event(c_void_p(event.cuda_event) if event is not None else None)
 
 
 def ar_step_bwd(desc, weights, mel, in_lens, out_lens, attn, d_mel_out, d_log_s, d_gates, d_attn, d_logprob, d_mel, d_text,

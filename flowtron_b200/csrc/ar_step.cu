@@ -224,9 +224,14 @@ int copy_f32(float* dst, const float* src, size_t n, cudaStream_t st) {
 }  // namespace
 
 // =================================================================================================== forward
+static thread_local cudaEvent_t g_text_ready = nullptr;
+void set_text_ready_event(void* ev) { g_text_ready = static_cast<cudaEvent_t>(ev); }
+
 int ar_step_fwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* mel, const float* text, const int* in_lens,
                 const int* out_lens, const float* prior, float* mel_out, float* log_s, float* gates, float* attn,
                 float* logprob, void* saved, void* scratch, cudaStream_t st) {
+    cudaEvent_t text_ready = g_text_ready;        // one-shot: consumed by this call whatever happens next
+    g_text_ready = nullptr;
     FT_TRY(check_desc(d));
     if (d.has_prior && !prior) return ft_set_error("ar_step_fwd: has_prior set but attn_prior is NULL");
     if (d.has_gate && (!gates || !w.gate_w)) return ft_set_error("ar_step_fwd: has_gate set but gate pointers are NULL");
@@ -259,6 +264,11 @@ int ar_step_fwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
     FT_TRY(launch_lstm_fwd(n.T, n.B, F.X, F.w.w_hh_a, out_lens, S.d16, n.D, S.gatesA, S.cA, nullptr, 0, F.flags, st));
 
     // attention: K/V/Q projections, fused score+softmax(+prior)+context; ctx lands in d16[:, H:H+A]
+    // First use of `text`: if the caller produced it on another stream it handed us the event to wait for, so the encoder
+    // ran underneath everything above (ft_ar_step_set_text_ready_event).
+    if (text_ready) {
+        if (cudaStreamWaitEvent(st, text_ready, 0) != cudaSuccess) return ft_set_error("ar_step_fwd: cudaStreamWaitEvent(text_ready) failed");
+    }
     FT_TRY(launch_cast(text, 2, S.text16, 0, n.RL * n.E, st));
     FT_TRY(gemm_fwd(st, n.RL, n.A, n.E, S.text16, n.E, F.w.wk, n.E, nullptr, nullptr, 0, S.Kp, n.A, nullptr, 0));
     FT_TRY(gemm_fwd(st, n.RL, n.A, n.E, S.text16, n.E, F.w.wv, n.E, nullptr, nullptr, 0, S.Vp, n.A, nullptr, 0));
@@ -436,6 +446,8 @@ int ft_ar_step_saved_lookup(const FtArStepDesc* d, const char* name, size_t* off
         if (std::strcmp(r.name, name) == 0) { *offset = r.off; *bytes = r.bytes; return 0; }
     return ft::ft_set_error("ft_ar_step_saved_lookup: unknown region");
 }
+
+void ft_ar_step_set_text_ready_event(void* cuda_event) { ft::set_text_ready_event(cuda_event); }
 
 int ft_ar_step_fwd(const FtArStepDesc* d, const FtArStepWeights* w, const float* mel, const float* text,
                    const int* in_lens, const int* out_lens, const float* attn_prior, float* mel_out, float* log_s,

@@ -197,38 +197,49 @@ __global__ void gate_bwd_kernel(const __half* __restrict__ d16, long long ldd, i
                                 const float* __restrict__ dgate, long long R, float* __restrict__ dd, long long lddd,
                                 float* __restrict__ dwg, float* __restrict__ dbg, const float* __restrict__ scale) {
     const float S = scale ? scale[0] : 1.f;      // dd lives in the loss-scaled domain, dwg / dbg do not
-    // block handles a slab of rows; thread k-strided accumulators for dwg
-    extern __shared__ float sacc[];                   // [K]
-    for (int k = threadIdx.x; k < K; k += blockDim.x) sacc[k] = 0.f;
-    __syncthreads();
+    // A block walks a slab of rows; thread t owns columns t, t+256, ... (<= GB_KJ of them): every row is one coalesced
+    // sweep with GB_KJ independent loads in flight per thread (the first version walked the rows per column: 0.44 ms
+    // for 0.5 GB of traffic, latency-bound).
+    constexpr int GB_KJ = 8;                          // K <= 2048 (checked by the launcher)
     const long long rows_per_block = (R + gridDim.x - 1) / gridDim.x;
     const long long r0 = blockIdx.x * rows_per_block, r1 = min(R, r0 + rows_per_block);
+    float acc[GB_KJ], w[GB_KJ];
+#pragma unroll
+    for (int j = 0; j < GB_KJ; ++j) {
+        const int k = threadIdx.x + 256 * j;
+        acc[j] = 0.f;
+        w[j] = k < K ? S * wg[k] : 0.f;
+    }
     float db = 0.f;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        float a = 0.f;
-        const float w = wg[k];
-        for (long long r = r0; r < r1; ++r) {
-            const float g = dgate[r];
-            if (g != 0.f) {
-                a = fmaf(g, __half2float(d16[r * ldd + k]), a);
-                dd[r * lddd + k] += S * g * w;
+    for (long long r = r0; r < r1; ++r) {
+        const float g = dgate[r];                     // block-uniform
+        if (g == 0.f) continue;                       // padded frames
+        db += g;
+        const __half* drow = d16 + r * ldd;
+        float* ddrow = dd + r * lddd;
+#pragma unroll
+        for (int j = 0; j < GB_KJ; ++j) {
+            const int k = threadIdx.x + 256 * j;
+            if (k < K) {
+                acc[j] = fmaf(g, __half2float(drow[k]), acc[j]);
+                ddrow[k] = fmaf(g, w[j], ddrow[k]);
             }
         }
-        sacc[k] = a;
     }
-    if (threadIdx.x == 0) {
-        for (long long r = r0; r < r1; ++r) db += dgate[r];
-        atomicAdd(dbg, db);
+    if (threadIdx.x == 0 && db != 0.f) atomicAdd(dbg, db);
+#pragma unroll
+    for (int j = 0; j < GB_KJ; ++j) {
+        const int k = threadIdx.x + 256 * j;
+        if (k < K && acc[j] != 0.f) atomicAdd(dwg + k, acc[j]);
     }
-    __syncthreads();
-    for (int k = threadIdx.x; k < K; k += blockDim.x) atomicAdd(dwg + k, sacc[k]);
 }
 int launch_gate_bwd(const void* d16, long long ldd, int K, const float* wg, const float* dgate, long long R, float* dd,
                     long long lddd, float* dwg, float* dbg, const float* scale, cudaStream_t st) {
     long long gl = (R + 15) / 16, gcap = static_cast<long long>(num_sms()) * 4;
     int g = static_cast<int>(gl > gcap ? gcap : gl);
     if (g < 1) g = 1;
-    gate_bwd_kernel<<<g, 256, K * sizeof(float), st>>>(static_cast<const __half*>(d16), ldd, K, wg, dgate, R, dd, lddd, dwg, dbg, scale);
+    if (K > 2048) return ft_set_error("gate_bwd: K > 2048 not supported");
+    gate_bwd_kernel<<<g, 256, 0, st>>>(static_cast<const __half*>(d16), ldd, K, wg, dgate, R, dd, lddd, dwg, dbg, scale);
     ft_count_launch(1);
     return ft_check_launch("gate_bwd_kernel");
 }

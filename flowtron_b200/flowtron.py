@@ -12,6 +12,8 @@ PyTorch modules, written device-agnostically.
 """
 from __future__ import annotations
 
+import os
+import warnings
 from typing import Optional
 
 import torch
@@ -90,6 +92,23 @@ class DenseLayer(nn.Module):
         return x
 
 
+_enc_streams = {}
+
+
+def _encoder_overlap_stream(device):
+    key = ("overlap", device.type, device.index)
+    if key not in _enc_streams:
+        _enc_streams[key] = torch.cuda.Stream(device=device)
+    return _enc_streams[key]
+
+
+def _encoder_side_stream(device):
+    key = (device.type, device.index)
+    if key not in _enc_streams:
+        _enc_streams[key] = torch.cuda.Stream(device=device)
+    return _enc_streams[key]
+
+
 class Encoder(nn.Module):
     """flowtron.py:467-525 (3 x conv+masked instance norm+relu+dropout, packed BiLSTM)."""
 
@@ -104,20 +123,30 @@ class Encoder(nn.Module):
         self.convolutions = nn.ModuleList(convolutions)
         self.lstm = nn.LSTM(encoder_embedding_dim, int(encoder_embedding_dim / 2), 1, batch_first=True, bidirectional=True)
         self.p_dropout = 0.5        # flowtron.py:502 hard-codes 0.5; exposed so tests can run deterministic train-mode steps
+        self.two_streams = os.environ.get("FT_ENC_STREAMS", "0") != "0"   # run the two LSTM directions concurrently
 
     def _lstm_dir(self, x, sfx):
-        """One direction of the BiLSTM on a padded [B, L, C] batch (cuDNN's persistent padded path)."""
+        """One direction of the BiLSTM on a padded [B, L, C] batch."""
         w = [getattr(self.lstm, n + sfx) for n in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")]
         h0 = x.new_zeros(1, x.size(0), self.lstm.hidden_size)
-        out, _, _ = torch._VF.lstm(x, (h0, h0), w, True, 1, 0.0, self.training, False, True)
+        with warnings.catch_warnings():           # "weights are not part of single contiguous chunk": one direction at a time
+            warnings.simplefilter("ignore", UserWarning)
+            out, _, _ = torch._VF.lstm(x, (h0, h0), w, True, 1, 0.0, self.training, False, True)
         return out
+
+    def _reverse_dir(self, x, rev):
+        gidx = rev[..., None].expand(-1, -1, x.size(2))
+        out = self._lstm_dir(torch.gather(x, 1, gidx), "_reverse")
+        return torch.gather(out, 1, rev[..., None].expand(-1, -1, out.size(2)))
 
     def forward(self, x, in_lens):
         """Same result as the reference's packed BiLSTM (flowtron.py:505-512) without packing: the forward direction is
         causal, so running it over the padded batch and zeroing t >= len is identical; the reverse direction runs on
-        each utterance reversed inside its own length (one gather in, one gather out).  This replaces ~1500 per-time-step
-        cuDNN kernels (and the host sync of `in_lens.cpu()`) by two persistent-LSTM calls.  Requires the text batch to be
-        padded to max(in_lens), which DataCollate guarantees (data.py:200-208)."""
+        each utterance reversed inside its own length (one gather in, one gather out).  No pack/unpack and no host sync
+        (`in_lens.cpu()`); cuDNN still launches its per-time-step fp32 kernels (measured: same GPU time as packed), and
+        they are latency-bound, so with ``two_streams`` the two directions run concurrently on two CUDA streams (autograd
+        replays each direction's backward on the stream its forward ran on).  Requires the text batch to be padded to
+        max(in_lens), which DataCollate guarantees (data.py:200-208)."""
         Bn, _, L = x.shape
         ar = torch.arange(L, device=x.device)
         valid = ar[None, :] < in_lens[:, None]                                   # [B, L]
@@ -128,10 +157,18 @@ class Encoder(nn.Module):
             x = F.dropout(F.relu(norm(conv(x), mask=mask)), self.p_dropout, self.training)
         x = x.transpose(1, 2).contiguous()                                        # [B, L, C]
         rev = torch.where(valid, in_lens[:, None] - 1 - ar[None, :], ar[None, :])   # per-utterance time reversal (involution)
-        fwd = self._lstm_dir(x, "")
-        gidx = rev[..., None].expand(-1, -1, x.size(2))
-        bwd = self._lstm_dir(torch.gather(x, 1, gidx), "_reverse")
-        bwd = torch.gather(bwd, 1, rev[..., None].expand(-1, -1, bwd.size(2)))
+        if self.two_streams and x.is_cuda:
+            cur = torch.cuda.current_stream(x.device)
+            side = _encoder_side_stream(x.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                bwd = self._reverse_dir(x, rev)
+            fwd = self._lstm_dir(x, "")
+            cur.wait_stream(side)
+            bwd.record_stream(cur)                # allocated from the side stream's pool, consumed on the caller's stream
+        else:
+            fwd = self._lstm_dir(x, "")
+            bwd = self._reverse_dir(x, rev)
         return torch.cat([fwd, bwd], -1) * valid[..., None].to(x.dtype)
 
     def infer(self, x):
@@ -197,6 +234,10 @@ class _ArStepFn(torch.autograd.Function):
         gates = torch.empty(T, B, 1, device=dev) if has_gate else None
         attn = torch.empty(B, T, L, device=dev)
         logprob = torch.empty(B, T, L, device=dev)
+        ev = getattr(step, "_text_event", None)
+        if ev is not None:                        # `text` was produced on another stream: wait inside the flow, not here
+            step._text_event = None
+            _lib.set_text_ready_event(ev)
         _lib.ar_step_fwd(desc, weights, mel_c, text_c, in_lens, out_lens, prior_c, mel_out, log_s, gates, attn, logprob,
                          saved, scratch)
         ctx.desc, ctx.saved_buf, ctx.plist = desc, saved, plist
@@ -333,6 +374,7 @@ class Flowtron(nn.Module):
     # many dependent steps as the full batch); it only lets one half's GEMMs / attention / launch gaps overlap the other
     # half's recurrences.  Measured on B200 (B=32, T=1000): 91.5 -> 89.1 ms/step (+2.7 %).  Off by default.
     n_streams = 1
+    overlap_encoder = os.environ.get("FT_ENC_OVERLAP", "0") != "0"   # run the Encoder underneath the first flow's attention LSTM
     min_split_batch = 8
 
     max_kernel_batch = 64        # the persistent recurrence kernels take up to 64 utterances per launch
@@ -352,24 +394,46 @@ class Flowtron(nn.Module):
                     [torch.cat([o[4][i] for o in outs], 0) for i in range(n_flows)])
         log_s_list, attns_list, attns_logprob_list, gate = [], [], [], None
         for i, flow in enumerate(self.flows):
+            flow._text_event = getattr(self, "_text_event", None) if i == 0 else None
             mel, log_s, gate, attn_out, attn_logprob_out = flow(mel, encoder_outputs, mask, out_lens, attn_prior)
             log_s_list.append(log_s)
             attns_list.append(attn_out)
             attns_logprob_list.append(attn_logprob_out)
         return mel, log_s_list, gate, attns_list, attns_logprob_list
 
-    def forward(self, mel, speaker_ids, text, in_lens, out_lens, attn_prior=None):
+    def _encode(self, speaker_ids, text, in_lens):
+        """flowtron.py:871-880: embeddings + Encoder + speaker vector concat -> [L, B, n_text + n_speaker]."""
         speaker_ids = speaker_ids * 0 if self.dummy_speaker_embedding else speaker_ids
         speaker_vecs = self.speaker_embedding(speaker_ids)
         text = self.embedding(text).transpose(1, 2)
         text = self.encoder(text, in_lens)
-        mean, log_var, prob = None, None, None
         text = text.transpose(0, 1)
+        return torch.cat([text, speaker_vecs.expand(text.size(0), -1, -1)], 2)
+
+    def forward(self, mel, speaker_ids, text, in_lens, out_lens, attn_prior=None):
+        mean, log_var, prob = None, None, None
+        n_text = text.size(1)
+        B = mel.size(0)
+        # The first flow needs the text encoding only after its attention LSTM (T dependent steps that read mel alone), so
+        # the encoder's ~700 small latency-bound kernels can run on a second stream underneath it; the flow's C entry
+        # point waits for `text_event` right before it first reads the encoding (ft_ar_step_set_text_ready_event).
+        overlap = self.overlap_encoder and mel.is_cuda and self.n_streams <= 1 and B <= self.max_kernel_batch
+        self._text_event = None
+        if overlap:
+            cur = torch.cuda.current_stream(mel.device)
+            es = _encoder_overlap_stream(mel.device)
+            es.wait_stream(cur)
+            with torch.cuda.stream(es):
+                encoder_outputs = self._encode(speaker_ids, text, in_lens)
+                ev = torch.cuda.Event()
+                ev.record(es)
+            encoder_outputs.record_stream(cur)
+            self._text_event = ev
+        else:
+            encoder_outputs = self._encode(speaker_ids, text, in_lens)
         mel = mel.permute(2, 0, 1)
-        encoder_outputs = torch.cat([text, speaker_vecs.expand(text.size(0), -1, -1)], 2)
         # key-padding mask from the padded text length (== max(in_lens) by the collate contract): no .item() host sync
-        mask = ~(torch.arange(text.size(0), device=in_lens.device)[None, :] < in_lens[:, None])[..., None]
-        B = mel.size(1)
+        mask = ~(torch.arange(n_text, device=in_lens.device)[None, :] < in_lens[:, None])[..., None]
         split = self.n_streams > 1 and mel.is_cuda and B >= self.min_split_batch and out_lens is not None
         if mel.is_cuda:
             _lib.set_lstm_half_sm(split)

@@ -107,6 +107,12 @@ int ft_ar_step_fwd(const FtArStepDesc* d, const FtArStepWeights* w, const float*
                    const int* in_lens, const int* out_lens, const float* attn_prior, float* mel_out, float* log_s,
                    float* gates, float* attn, float* attn_logprob, void* saved, void* scratch, void* stream);
 
+/* Optional, one-shot, per host thread: the NEXT ft_ar_step_fwd call on this thread waits for `cuda_event` (a
+ * cudaEvent_t recorded on whatever stream produced `text`) on its own stream right before it first reads `text` --
+ * i.e. after the attention LSTM, which depends on mel only -- so the caller can run the text encoder
+ * (flowtron.py:871-880) concurrently with the first third of the flow instead of in front of it.  NULL clears it. */
+void ft_ar_step_set_text_ready_event(void* cuda_event);
+
 /* Autograd of the above.  Incoming gradients (any may be NULL = zero): d_mel_out, d_log_s [T,B,M], d_gates [T,B],
  * d_attn, d_attn_logprob [B,T,L].  Outputs: d_mel [T,B,M], d_text [L,B,E] (overwritten), parameter gradients
  * into `g` (overwritten; same layouts as the weights). */
