@@ -394,7 +394,8 @@ class Flowtron(nn.Module):
                     [torch.cat([o[4][i] for o in outs], 0) for i in range(n_flows)])
         log_s_list, attns_list, attns_logprob_list, gate = [], [], [], None
         for i, flow in enumerate(self.flows):
-            flow._text_event = getattr(self, "_text_event", None) if i == 0 else None
+            # the module whose kernels run first gets the text-ready event (AR_Back_Step wraps its AR_Step as .ar_step)
+            getattr(flow, "ar_step", flow)._text_event = getattr(self, "_text_event", None) if i == 0 else None
             mel, log_s, gate, attn_out, attn_logprob_out = flow(mel, encoder_outputs, mask, out_lens, attn_prior)
             log_s_list.append(log_s)
             attns_list.append(attn_out)
