@@ -166,9 +166,12 @@ def main():
     model = model.to(dev).train()
     model.n_streams = args.streams
     crit = FlowtronLoss(sigma=1.0, gate_loss=True, use_ctc_loss=False)
-    # train.py:231-252 order: optimizer first, then the all-reduce wrapper.  FT_FUSED_OPT=0 falls back to torch's
-    # multi-tensor RAdam + torch clip_grad_norm_ (the round-1 configuration) for A/B runs.
-    fused_opt = os.environ.get("FT_FUSED_OPT", "0") != "0"     # flipped to default-on once validated on the GPU
+    # train.py:231-252 order: optimizer first, then the all-reduce wrapper.
+    # FT_FUSED_OPT=1: flowtron_b200.RAdam (fused clip + reference-semantics RAdam, parity-tested on the GPU).  Off by
+    # default: in this harness it measured SLOWER (145 vs 85.5 ms/step un-synced, 87.0 vs 86.1 ms with a sync per step;
+    # kernel times unchanged) -- an integration stall not yet profiled (DESIGN.md findings), so the headline keeps
+    # torch.optim.RAdam + torch clip_grad_norm_.
+    fused_opt = os.environ.get("FT_FUSED_OPT", "0") != "0"
     if fused_opt:
         from flowtron_b200.radam import RAdam
         opt = RAdam(model.parameters(), lr=1e-3, weight_decay=1e-6)
