@@ -10,6 +10,8 @@ bucketed NCCL gradient all-reduce (N>1) -> grad-norm clip -> RAdam step (train.p
 `value` = valid mel frames (sum of out_lens over all ranks) per second with inputs resident in HBM;
 `e2e` = the same through the public module API with pinned-host inputs copied every step and the loss read back.
 Precision: fp16 tensor-core operands (backward on device-side loss-scaled gradients), fp32 accumulation/state.
+Scheduling switches (environment): FT_ENC_OVERLAP (default 1), FT_ENC_STREAMS (0), FT_FUSED_OPT (0); the
+values in force are echoed in `config`.
 """
 from __future__ import annotations
 
@@ -294,6 +296,7 @@ def main():
         "config": {"workload": "configs[1]: LJS single-speaker 2-flow Flowtron train step, n_mel=80, per-GPU batch 32, T<=1000",
                    "per_gpu_batch": B, "global_batch": B * world, "max_frames": T, "max_text": L, "attn_prior": True,
                    "optimizer": ("flowtron_b200.RAdam (fused, reference radam.py semantics)" if fused_opt else "torch.optim.RAdam") + " lr=1e-3 wd=1e-6 + clip_grad_norm 1.0", "parallelism": f"dp{world}", "streams_per_rank": args.streams,
+                   "encoder_overlap": bool(model.overlap_encoder), "encoder_two_streams": bool(model.encoder.two_streams),
                    "padded_frames_per_s": B * T * world * args.steps / (ms / 1e3),
                    "l2": "working set per step (>3 GB of activations) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e, "unit": "valid mel-frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
