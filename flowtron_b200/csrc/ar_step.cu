@@ -93,15 +93,30 @@ struct W16 {
     }
 };
 
+// EXPERIMENTAL (not validated on hardware): FT_PIPE_FWD=1 runs lstm layers 0 and 1 of the forward pass as two
+// 64-CTA recurrences one chunk of FT_PIPE_CHUNK steps apart (lstm_fwd_chunk_kernel).  Off by default.
+static bool pipe_fwd_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FT_PIPE_FWD"); v = (e && atoi(e) != 0) ? 1 : 0; }
+    return v == 1;
+}
+static int pipe_chunk_steps() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FT_PIPE_CHUNK"); v = e ? atoi(e) : 100; if (v < 8) v = 8; }
+    return v;
+}
+
 struct FwdScratch {
     W16 w;
     float* X;
     int* flags;
+    float* X1 = nullptr;        // second input-projection buffer (pipelined layers only)
     void plan(Plan& p, const FtArStepDesc& d) {
         const Dims n(d);
         w.plan(p, n);
         X = p.get<float>("X", n.R * G);
         flags = p.get<int>("flags", static_cast<size_t>(n.T) * 64);
+        if (pipe_fwd_enabled()) X1 = p.get<float>("X1", n.R * G);
     }
 };
 
@@ -214,6 +229,27 @@ static void join_side(Side* sd, cudaStream_t main) {
     cudaStreamWaitEvent(main, sd->ev_side, 0);
 }
 
+// Streams of the experimental layer pipeline: sB runs the second recurrence, sC its per-chunk input-projection GEMMs.
+struct Pipe {
+    cudaStream_t sB = nullptr, sC = nullptr;
+    cudaEvent_t evA = nullptr, evG = nullptr, evB = nullptr, ev0 = nullptr;
+};
+static std::map<cudaStream_t, Pipe> g_pipes;
+static Pipe* get_pipe(cudaStream_t main) {
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    auto it = g_pipes.find(main);
+    if (it != g_pipes.end()) return &it->second;
+    Pipe pp;
+    if (cudaStreamCreateWithFlags(&pp.sB, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&pp.sC, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&pp.evA, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&pp.evG, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&pp.evB, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&pp.ev0, cudaEventDisableTiming);
+    g_pipes[main] = pp;
+    return &g_pipes[main];
+}
+
 int zero(void* p, size_t bytes, cudaStream_t st) {
     return cudaMemsetAsync(p, 0, bytes, st) == cudaSuccess ? 0 : ft_set_error("cudaMemsetAsync failed");
 }
@@ -285,10 +321,37 @@ int ar_step_fwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
     if (d.has_gate) FT_TRY(launch_gate_fwd(S.d16, n.D, n.D, w.gate_w, w.gate_b, n.R, gates, st));
 
     // 2-layer lstm
-    FT_TRY(gemm_fwd(st, n.R, G, n.D, S.d16, n.D, F.w.w_ih0, n.D, w.lstm_b_ih0, w.lstm_b_hh0, 0, F.X, G, nullptr, 0));
-    FT_TRY(launch_lstm_fwd(n.T, n.B, F.X, F.w.w_hh0, out_lens, S.h0_16, H, S.gates0, S.c0, nullptr, 0, F.flags, st));
-    FT_TRY(gemm_fwd(st, n.R, G, H, S.h0_16, H, F.w.w_ih1, H, w.lstm_b_ih1, w.lstm_b_hh1, 0, F.X, G, nullptr, 0));
-    FT_TRY(launch_lstm_fwd(n.T, n.B, F.X, F.w.w_hh1, out_lens, S.h1_16, H, S.gates1, S.c1, nullptr, 0, F.flags, st));
+    Pipe* pp = (F.X1 && n.B <= 32 && n.T > pipe_chunk_steps()) ? get_pipe(st) : nullptr;
+    if (pp) {
+        // EXPERIMENTAL: layer 1 at step t needs layer 0 only up to t, so the two recurrences run as two 64-CTA kernels
+        // one chunk apart: st = layer 0, sC = layer-1 input projection of a finished chunk, sB = layer 1.
+        const int S_ = pipe_chunk_steps();
+        int* flagsA = F.flags;
+        int* flagsB = F.flags + static_cast<size_t>(S_) * 16;
+        FT_TRY(gemm_fwd(st, n.R, G, n.D, S.d16, n.D, F.w.w_ih0, n.D, w.lstm_b_ih0, w.lstm_b_hh0, 0, F.X, G, nullptr, 0));
+        cudaEventRecord(pp->ev0, st);
+        cudaStreamWaitEvent(pp->sB, pp->ev0, 0);
+        cudaStreamWaitEvent(pp->sC, pp->ev0, 0);
+        for (int t0 = 0; t0 < n.T; t0 += S_) {
+            const int t1 = t0 + S_ < n.T ? t0 + S_ : n.T;
+            const long long r0 = static_cast<long long>(t0) * n.B, rows = static_cast<long long>(t1 - t0) * n.B;
+            FT_TRY(launch_lstm_fwd_chunk(n.T, n.B, t0, t1, F.X, F.w.w_hh0, out_lens, S.h0_16, H, S.gates0, S.c0, flagsA, st));
+            cudaEventRecord(pp->evA, st);
+            cudaStreamWaitEvent(pp->sC, pp->evA, 0);
+            FT_TRY(gemm_fwd(pp->sC, rows, G, H, S.h0_16 + r0 * H, H, F.w.w_ih1, H, w.lstm_b_ih1, w.lstm_b_hh1, 0,
+                            F.X1 + r0 * G, G, nullptr, 0));
+            cudaEventRecord(pp->evG, pp->sC);
+            cudaStreamWaitEvent(pp->sB, pp->evG, 0);
+            FT_TRY(launch_lstm_fwd_chunk(n.T, n.B, t0, t1, F.X1, F.w.w_hh1, out_lens, S.h1_16, H, S.gates1, S.c1, flagsB, pp->sB));
+        }
+        cudaEventRecord(pp->evB, pp->sB);
+        cudaStreamWaitEvent(st, pp->evB, 0);
+    } else {
+        FT_TRY(gemm_fwd(st, n.R, G, n.D, S.d16, n.D, F.w.w_ih0, n.D, w.lstm_b_ih0, w.lstm_b_hh0, 0, F.X, G, nullptr, 0));
+        FT_TRY(launch_lstm_fwd(n.T, n.B, F.X, F.w.w_hh0, out_lens, S.h0_16, H, S.gates0, S.c0, nullptr, 0, F.flags, st));
+        FT_TRY(gemm_fwd(st, n.R, G, H, S.h0_16, H, F.w.w_ih1, H, w.lstm_b_ih1, w.lstm_b_hh1, 0, F.X, G, nullptr, 0));
+        FT_TRY(launch_lstm_fwd(n.T, n.B, F.X, F.w.w_hh1, out_lens, S.h1_16, H, S.gates1, S.c1, nullptr, 0, F.flags, st));
+    }
 
     // dense x2 (tanh fused in the GEMM epilogue), 1x1 conv, affine coupling
     FT_TRY(gemm_fwd(st, n.R, H, H, S.h1_16, H, F.w.w1, H, w.dense_b0, nullptr, 1, nullptr, 0, S.y1_16, H));

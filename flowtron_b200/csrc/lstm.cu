@@ -721,6 +721,226 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
     if (warp == 1) tmem_dealloc<64>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------- forward, one chunk of steps
+// EXPERIMENTAL (round-2 groundwork; NOT validated on hardware yet, only reachable with FT_PIPE_FWD=1):
+// the same recurrence over steps [t0, t1) only, resuming h from the output tensor (row t0-1) and c from the saved cell
+// states, so that two layers can run as two 64-CTA kernels on two streams, chunk by chunk, one chunk apart.  A verbatim
+// copy of lstm_fwd_kernel with the loop bounds, the flag indexing (relative to t0), the mbarrier phases (relative to the
+// first step that has a recurrent term) and the cell-state resume changed; the default path does not use it.
+struct LstmFwdChunkParams : LstmFwdParams {
+    int t0, t1;                // steps [t0, t1); flags: [(t1 - t0) * 16] ints, zeroed by the launcher
+};
+
+template <int FWD_GS, int FWD_UNITS>
+__global__ void __launch_bounds__(LSTM_THREADS, 1)
+lstm_fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, LstmFwdChunkParams p) {
+    constexpr int FWD_NG = FWD_NCH / FWD_GS;                     // TMA groups per step
+    constexpr int FWD_N = 4 * FWD_UNITS, FWD_W_BYTES = FWD_NCH * FWD_N * 128, FWD_PROD = KCH / FWD_UNITS;
+    constexpr int AP = FWD_N + 1;                                // accumulator staging pitch
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int slot_bytes = p.Bbox * 128;
+    uint8_t* sA = smem;                                          // [16 chunks][Bbox rows][128 B]
+    uint8_t* sW = smem + FWD_NCH * slot_bytes;                   // the M=128 over-read of the last chunks lands here
+    float* sAcc = reinterpret_cast<float*>(sW + FWD_W_BYTES);    // [32 * nq rows][AP]
+    const int nq = (p.B + 31) / 32;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + ((nq * 32 * AP + 1) & ~1));
+    uint64_t* full = bars;                       // [FWD_NG] (<= 16)
+    uint64_t* wbar = bars + 16;
+    uint64_t* accum_full = bars + 17;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cta = blockIdx.x;
+    const int tm0 = p.t0 > 1 ? p.t0 : 1;                         // first step with a recurrent term
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmW);
+        tma_prefetch_desc(&tmH);
+        for (int g = 0; g < FWD_NG; ++g) mbar_init(&full[g], 1);
+        mbar_init(wbar, 1);
+        mbar_init(accum_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<(FWD_N < 32 ? 32 : FWD_N)>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // resident W_hh slice: chunk kc, gate g -> FWD_UNITS rows x 128 B
+            mbar_expect_tx(wbar, FWD_W_BYTES);
+            for (int kc = 0; kc < FWD_NCH; ++kc)
+                for (int g = 0; g < 4; ++g)
+                    tma_load_2d(sW + kc * (FWD_N * 128) + g * (FWD_UNITS * 128), &tmW, wbar, kc * KCH, g * LH + FWD_UNITS * cta);
+        }
+        for (int t = tm0; t < p.t1; ++t) {
+            // as in lstm_fwd_kernel; the first step of a chunk has nothing to wait for: h_{t0-1} was written by the
+            // previous launch on this stream (kernel boundary) and the A buffer is untouched
+            if (t > p.t0 && lane < FWD_NCH) wait_flag_ge(&p.flags[(t - 1 - p.t0) * FWD_NCH + lane], FWD_PROD, p.status, 212);
+            __syncwarp();
+            if (elect_one()) {
+                fence_proxy_async_global();        // generic-proxy writes of other SMs -> async-proxy (TMA) reads
+#pragma unroll
+                for (int g = 0; g < FWD_NG; ++g) {
+                    mbar_expect_tx(&full[g], FWD_GS * slot_bytes);
+                    tma_load_3d(sA + g * FWD_GS * slot_bytes, &tmH, &full[g], 0, (t - 1) * p.B, g * FWD_GS);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // warp-uniform loop, one elected lane issues (see gemm.cu: descriptors must be uniform-register operands)
+        mbar_wait(wbar, 0, p.status, 213);
+        const uint32_t idesc = umma_idesc(128, FWD_N, FMT_F16, FMT_F16, 0, 0);
+        const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint64_t da_base = umma_smem_desc(smem_u32(sA), 16, 1024), db_base = umma_smem_desc(smem_u32(sW), 16, 1024);
+        const uint64_t a_chunk = static_cast<uint64_t>(slot_bytes >> 4), b_chunk = (FWD_N * 128) >> 4;
+        for (int t = tm0; t < p.t1; ++t) {
+            const int ph = (t - tm0) & 1;
+            uint64_t da = da_base, db = db_base;
+#pragma unroll
+            for (int g = 0; g < FWD_NG; ++g) {
+                mbar_wait(&full[g], ph, p.status, 214);
+                tc_fence_after();
+                if (elect_one()) {
+                    uint64_t xa = da, xb = db;
+#pragma unroll
+                    for (int c = 0; c < FWD_GS; ++c) {
+#pragma unroll
+                        for (int k = 0; k < KCH / 16; ++k)
+                            umma_f16(tmem_d, xa + 2 * k, xb + 2 * k, idesc, (g | c | k) != 0);
+                        xa += a_chunk;
+                        xb += b_chunk;
+                    }
+                    if (g == FWD_NG - 1) umma_commit(accum_full);
+                }
+                __syncwarp();
+                da += FWD_GS * a_chunk;
+                db += FWD_GS * b_chunk;
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue: 4 warps, 128 threads
+        const int q = warp & 3;                               // TMEM lane quadrant this warp may read
+        const int et = threadIdx.x - 64;                      // 0..127
+        // work items: (batch row b, unit pair up) -> item = b * UP + up ; thread handles items et, et + 128
+        constexpr int UP = FWD_UNITS / 2;
+        const int n_items = p.B * UP;
+        float c[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        int len_i[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int item = et + s * EPI_THREADS;
+            len_i[s] = (item < n_items && p.lens) ? p.lens[item / UP] : p.T;
+        }
+        const int u0 = FWD_UNITS * cta;
+        if (p.t0 > 0) {                                       // resume the cell state saved by the previous chunk
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int item = et + s * EPI_THREADS;
+                if (item < n_items) {
+                    const int b = item / UP, up = item % UP;
+                    const float2 cv = *reinterpret_cast<const float2*>(p.cstate + (static_cast<long long>(p.t0 - 1) * p.B + b) * LH + u0 + 2 * up);
+                    c[s][0] = cv.x; c[s][1] = cv.y;
+                }
+            }
+        }
+        for (int t = p.t0; t < p.t1; ++t) {
+            float x[2][8];                                    // [item][gate*2 + e]
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int item = et + s * EPI_THREADS;
+                if (item < n_items) {
+                    const int b = item / UP, up = item % UP;
+                    const float* src = p.xproj + (static_cast<long long>(t) * p.B + b) * LG + u0 + 2 * up;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float2 v = __ldg(reinterpret_cast<const float2*>(src + g * LH));
+                        x[s][2 * g] = v.x; x[s][2 * g + 1] = v.y;
+                    }
+                }
+            }
+            if (t > 0) {
+                if (q < nq) {                                 // this warp owns TMEM rows [32q, 32q+32)
+                    mbar_wait(accum_full, (t - tm0) & 1, p.status, 215);
+                    tc_fence_after();
+                    float* dst = sAcc + (q * 32 + lane) * AP;
+#pragma unroll
+                    for (int h = 0; h < FWD_N / 32; ++h) {
+                        float acc[32];
+                        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 32, acc);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) dst[h * 32 + j] = acc[j];
+                    }
+                    tc_fence_before();
+                }
+                epi_bar();
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int item = et + s * EPI_THREADS;
+                    if (item < n_items) {
+                        const int b = item / UP, up = item % UP;
+                        const float* a = sAcc + b * AP + 2 * up;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) { x[s][2 * g] += a[g * FWD_UNITS]; x[s][2 * g + 1] += a[g * FWD_UNITS + 1]; }
+                    }
+                }
+            }
+            float gi[2][2], gf[2][2], gg[2][2], go[2][2], hv[2][2];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int item = et + s * EPI_THREADS;
+                if (item < n_items) {
+                    const int b = item / UP, up = item % UP;
+                    const bool valid = t < len_i[s];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        gi[s][e] = sigmoid_f(x[s][0 + e]);
+                        gf[s][e] = sigmoid_f(x[s][2 + e]);
+                        gg[s][e] = tanh_f(x[s][4 + e]);
+                        go[s][e] = sigmoid_f(x[s][6 + e]);
+                        c[s][e] = gf[s][e] * c[s][e] + gi[s][e] * gg[s][e];
+                        hv[s][e] = valid ? go[s][e] * tanh_f(c[s][e]) : 0.f;
+                    }
+                    const long long r = static_cast<long long>(t) * p.B + b;
+                    const __half2 h2 = __floats2half2_rn(hv[s][0], hv[s][1]);
+                    *reinterpret_cast<__half2*>(p.hseq + r * p.ldh + u0 + 2 * up) = h2;     // critical path: h_t first
+                }
+            }
+            epi_bar();                                        // all h_t stores of this CTA precede the release
+            if (et == 0) {
+                red_release_add(&p.flags[(t - p.t0) * FWD_NCH + cta / FWD_PROD], 1);      // cumulative release (gpu scope)
+            }
+            // off the critical path: tensors only the backward pass reads
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int item = et + s * EPI_THREADS;
+                if (item < n_items) {
+                    const int b = item / UP, up = item % UP;
+                    const long long r = static_cast<long long>(t) * p.B + b;
+                    if (p.h32) *reinterpret_cast<float2*>(p.h32 + r * p.ldh32 + u0 + 2 * up) = make_float2(hv[s][0], hv[s][1]);
+                    if (p.gates) {
+                        __half* gp = p.gates + r * LG + u0 + 2 * up;
+                        *reinterpret_cast<__half2*>(gp) = __floats2half2_rn(gi[s][0], gi[s][1]);
+                        *reinterpret_cast<__half2*>(gp + LH) = __floats2half2_rn(gf[s][0], gf[s][1]);
+                        *reinterpret_cast<__half2*>(gp + 2 * LH) = __floats2half2_rn(gg[s][0], gg[s][1]);
+                        *reinterpret_cast<__half2*>(gp + 3 * LH) = __floats2half2_rn(go[s][0], go[s][1]);
+                    }
+                    if (p.cstate) *reinterpret_cast<float2*>(p.cstate + r * LH + u0 + 2 * up) = make_float2(c[s][0], c[s][1]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<(FWD_N < 32 ? 32 : FWD_N)>(tmem_base);
+}
+
+
 // ------------------------------------------------------------------------------------------- host
 static int smem_optin() {
     static int v = -1;
@@ -792,6 +1012,35 @@ int launch_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const i
     if (gs == 2) return launch_fwd_t<2, 8>(p, whh16, hseq16, ldh, T, B, flags, st);
     if (gs == 16) return launch_fwd_t<16, 8>(p, whh16, hseq16, ldh, T, B, flags, st);
     return launch_fwd_t<8, 8>(p, whh16, hseq16, ldh, T, B, flags, st);
+}
+
+// EXPERIMENTAL (see lstm_fwd_chunk_kernel): steps [t0, t1) of a layer on 64 CTAs.  `flags` needs (t1 - t0) * 16 ints.
+int launch_lstm_fwd_chunk(int T, int B, int t0, int t1, const float* xproj, const void* whh16, const int* lens, void* hseq16,
+                          long long ldh, void* gates16, float* cstate, int* flags, cudaStream_t st) {
+    if (T <= 0 || B <= 0 || t1 <= t0) return 0;
+    if (B > 64 || t0 < 0 || t1 > T) return ft_set_error("lstm_fwd_chunk: bad batch or step range");
+    if (t0 > 0 && !cstate) return ft_set_error("lstm_fwd_chunk: resuming a chunk needs the saved cell states");
+    constexpr int GS = 8, UNITS = 16, N = 4 * UNITS, W_BYTES = FWD_NCH * N * 128, CTAS = LH / UNITS;
+    LstmFwdChunkParams p;
+    p.T = T; p.B = B; p.Bbox = (B + 7) & ~7; p.t0 = t0; p.t1 = t1;
+    p.xproj = xproj; p.lens = lens; p.hseq = static_cast<__half*>(hseq16); p.ldh = ldh;
+    p.gates = static_cast<__half*>(gates16); p.cstate = cstate; p.h32 = nullptr; p.ldh32 = 0;
+    p.flags = flags; p.status = ft_status_word(); p.trace = nullptr;
+    const int slot = p.Bbox * 128, nq = (B + 31) / 32;
+    const int smem = FWD_NCH * slot + W_BYTES + nq * 32 * (N + 1) * 4 + 8 + 256 + 1024;
+    if (smem > smem_optin()) return ft_set_error("lstm_fwd_chunk: not enough shared memory");
+    CUtensorMap tmW, tmH;
+    if (make_tmap_2d(&tmW, whh16, FMT_F16, LG, LH, LH, KCH, UNITS)) return -1;
+    if (make_tmap_chunks(&tmH, hseq16, static_cast<long long>(T) * B, FWD_NCH, ldh, p.Bbox, GS)) return -1;
+    if (cudaMemsetAsync(flags, 0, sizeof(int) * (t1 - t0) * FWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_fwd_chunk: memset failed");
+    void* fn = reinterpret_cast<void*>(lstm_fwd_chunk_kernel<GS, UNITS>);
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    TimeScope ts("lstm_fwd", t1 - t0, B, 0, st);
+    void* args[] = {&tmW, &tmH, &p};
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(CTAS), dim3(LSTM_THREADS), args, smem, st);
+    if (e != cudaSuccess) return ft_set_error(cudaGetErrorString(e));
+    ft_count_launch(1);
+    return ft_check_launch("lstm_fwd_chunk_kernel");
 }
 
 int launch_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void* whhT16, const void* gates16,
