@@ -100,6 +100,11 @@ static bool pipe_fwd_enabled() {
     if (v < 0) { const char* e = getenv("FT_PIPE_FWD"); v = (e && atoi(e) != 0) ? 1 : 0; }
     return v == 1;
 }
+static bool pipe_bwd_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FT_PIPE_BWD"); v = (e && atoi(e) != 0) ? 1 : 0; }
+    return v == 1;
+}
 static int pipe_chunk_steps() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("FT_PIPE_CHUNK"); v = e ? atoi(e) : 100; if (v < 8) v = 8; }
@@ -125,6 +130,7 @@ struct BwdScratch {
     uint16_t *dG1, *dG0, *dGa, *do16, *dy2, *dy1, *dQ16, *dK16, *dV16;
     float *dh, *dd, *dQ, *dK, *dV, *dmel_flow, *dmel_in, *scale;
     int* flags;
+    float *dcarry1 = nullptr, *dcarry0 = nullptr;      // dc*f hand-over between BPTT chunks (pipelined layers only)
     void plan(Plan& p, const FtArStepDesc& d) {
         const Dims n(d);
         w.plan(p, n);
@@ -146,6 +152,10 @@ struct BwdScratch {
         dmel_in = p.get<float>("dmel_in", n.R * n.M);
         scale = p.get<float>("scale", 8);
         flags = p.get<int>("flags", static_cast<size_t>(n.T) * 64);
+        if (pipe_bwd_enabled()) {
+            dcarry1 = p.get<float>("dcarry1", static_cast<size_t>(n.B) * H);
+            dcarry0 = p.get<float>("dcarry0", static_cast<size_t>(n.B) * H);
+        }
     }
 };
 
@@ -421,6 +431,38 @@ int ar_step_bwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
     FT_TRY(launch_colsum(F.dy1, 0, H, R, H, g.dense_b0, iS, ss));
     FT_TRY(gemm_dgrad(st, R, H, H, F.dy1, H, F.w.w1, H, 0, F.dh, H, nullptr, 0, nullptr, 0));
 
+    Pipe* pp = (F.dcarry1 && n.B <= 32 && 2 * pipe_chunk_steps() <= n.T) ? get_pipe(st) : nullptr;
+    if (pp) {
+        // EXPERIMENTAL 5+6: BPTT of layer 1 (st) and layer 0 (sB) one chunk apart; the layer-1 dgrad of a finished chunk
+        // (sC) turns dG1 rows into layer 0's incoming dh rows (F.dh is reused row-disjointly: layer 1 only reads rows
+        // below the chunk it has finished).  Highest chunk first.
+        const int S_c = pipe_chunk_steps();
+        int* flagsA = F.flags;
+        int* flagsB = F.flags + static_cast<size_t>(S_c) * 64;
+        cudaEventRecord(pp->ev0, st);
+        cudaStreamWaitEvent(pp->sB, pp->ev0, 0);
+        cudaStreamWaitEvent(pp->sC, pp->ev0, 0);
+        const int n_chunks = (n.T + S_c - 1) / S_c;
+        for (int c = n_chunks - 1; c >= 0; --c) {
+            const int t0 = c * S_c, t1 = t0 + S_c < n.T ? t0 + S_c : n.T;
+            const long long r0 = static_cast<long long>(t0) * n.B, rows = static_cast<long long>(t1 - t0) * n.B;
+            FT_TRY(launch_lstm_bwd_chunk(n.T, n.B, t0, t1, F.dh, H, F.w.w_hh1, S_.gates1, S_.c1, out_lens, F.dG1, F.dcarry1, flagsA, st));
+            cudaEventRecord(pp->evA, st);
+            cudaStreamWaitEvent(pp->sC, pp->evA, 0);
+            FT_TRY(gemm_dgrad(pp->sC, rows, H, G, F.dG1 + r0 * G, G, F.w.w_ih1, H, 0, F.dh + r0 * H, H, nullptr, 0, nullptr, 0));
+            cudaEventRecord(pp->evG, pp->sC);
+            cudaStreamWaitEvent(pp->sB, pp->evG, 0);
+            FT_TRY(launch_lstm_bwd_chunk(n.T, n.B, t0, t1, F.dh, H, F.w.w_hh0, S_.gates0, S_.c0, out_lens, F.dG0, F.dcarry0, flagsB, pp->sB));
+        }
+        // layer-1 weight gradients run under the tail of layer 0 (side stream forks from st = all of layer 1 done)
+        ss = fork_side(sd, st);
+        FT_TRY(gemm_wgrad(ss, G, H, Rm, F.dG1 + static_cast<size_t>(n.B) * G, G, S_.h1_16, H, g.lstm_w_hh1, H, iS));
+        FT_TRY(gemm_wgrad(ss, G, H, R, F.dG1, G, S_.h0_16, H, g.lstm_w_ih1, H, iS));
+        FT_TRY(launch_colsum(F.dG1, 0, G, R, G, g.lstm_b_ih1, iS, ss));
+        FT_TRY(copy_f32(g.lstm_b_hh1, g.lstm_b_ih1, G, ss));
+        cudaEventRecord(pp->evB, pp->sB);
+        cudaStreamWaitEvent(st, pp->evB, 0);
+    } else {
     // 5. lstm layer 1
     FT_TRY(launch_lstm_bwd(n.T, n.B, F.dh, H, F.w.w_hh1, S_.gates1, S_.c1, out_lens, F.dG1, F.flags, st));
     ss = fork_side(sd, st);
@@ -432,6 +474,7 @@ int ar_step_bwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
 
     // 6. lstm layer 0
     FT_TRY(launch_lstm_bwd(n.T, n.B, F.dh, H, F.w.w_hh0, S_.gates0, S_.c0, out_lens, F.dG0, F.flags, st));
+    }
     ss = fork_side(sd, st);
     FT_TRY(gemm_wgrad(ss, G, H, Rm, F.dG0 + static_cast<size_t>(n.B) * G, G, S_.h0_16, H, g.lstm_w_hh0, H, iS));
     FT_TRY(gemm_wgrad(ss, G, n.D, R, F.dG0, G, S_.d16, n.D, g.lstm_w_ih0, n.D, iS));

@@ -45,6 +45,8 @@ int launch_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const i
                     void* gates16, float* cstate, float* h32, long long ldh32, int* flags, cudaStream_t st);
 int launch_lstm_fwd_chunk(int T, int B, int t0, int t1, const float* xproj, const void* whh16, const int* lens, void* hseq16,
                           long long ldh, void* gates16, float* cstate, int* flags, cudaStream_t st);   // experimental
+int launch_lstm_bwd_chunk(int T, int B, int t0, int t1, const float* dh_ext, long long ldd, const void* whhT16, const void* gates16,
+                          const float* cstate, const int* lens, void* dG16, float* dc_carry, int* flags, cudaStream_t st);   // experimental
 int launch_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void* whhT16, const void* gates16,
                     const float* cstate, const int* lens, void* dG16, int* flags, cudaStream_t st);
 

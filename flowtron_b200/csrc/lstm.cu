@@ -721,6 +721,232 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
     if (warp == 1) tmem_dealloc<64>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------- backward, one chunk of steps
+// EXPERIMENTAL (round-2 groundwork; NOT validated on hardware yet, only reachable with FT_PIPE_BWD=1):
+// lstm_bwd4_kernel over steps [t0, t1), highest step first, resuming dc*f from `dc_carry` ([B,1024] fp32, written by the
+// chunk above) and dG_{t1} from the dG tensor.  A verbatim copy with the loop bounds, the flag indexing (relative to t0),
+// the mbarrier phases (counted over the steps that have a recurrent term) and the carry changed.
+struct LstmBwdChunkParams : LstmBwdParams {
+    int t0, t1;                // steps [t0, t1); flags: [(t1 - t0) * 64] ints, zeroed by the launcher
+    float* dc_carry;           // [B, 1024]
+};
+
+__global__ void __launch_bounds__(LSTM_THREADS, 1)
+lstm_bwd4_chunk_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant__ CUtensorMap tmG, LstmBwdChunkParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int slot_bytes = p.Bbox * 128;
+    uint8_t* sA = smem;                                          // [16 chunks][Bbox rows][128 B]
+    uint8_t* sW = smem + B4_NCH * slot_bytes;                    // [16 chunks][64 rows][128 B]
+    float* sPart = reinterpret_cast<float*>(sW + B4_W_BYTES);    // [2 parities][32 rows][B4_PP]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + 2 * 32 * B4_PP);
+    uint64_t* full = bars;                       // [2]
+    uint64_t* wbar = bars + 2;
+    uint64_t* accum_full = bars + 3;
+    uint64_t* part_bar = bars + 4;               // [2] : 4 cluster-scope arrivals each
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = static_cast<int>(cluster_ctarank());
+    const int cl = blockIdx.x / B4_CLUSTER;
+    constexpr int GS = 8, NG = B4_NCH / GS;
+    const bool top = p.t1 == p.T;                                // the chunk that holds the last time step
+    const int t_hi = top ? p.T - 2 : p.t1 - 1;                   // highest step that has a recurrent term (dG_{t+1} exists)
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmWT);
+        tma_prefetch_desc(&tmG);
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        mbar_init(wbar, 1);
+        mbar_init(accum_full, 1);
+        mbar_init(&part_bar[0], B4_CLUSTER); mbar_init(&part_bar[1], B4_CLUSTER);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<64>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    cluster_sync_all();                                          // every rank's barriers exist before any remote arrive
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(wbar, B4_W_BYTES);
+            for (int kc = 0; kc < B4_NCH; ++kc)                  // W_hh^T rows [64c, 64c+64), columns of gate `rank`
+                tma_load_2d(sW + kc * (B4_UNITS * 128), &tmWT, wbar, rank * LH + kc * KCH, B4_UNITS * cl);
+        }
+        for (int t = t_hi; t >= p.t0; --t) {
+            // gate `rank` of dG_{t+1}: 16 chunks, each released by the 4 ranks of one cluster.  dG_{t1} (first step of a
+            // lower chunk) was written by the previous launch on this stream: nothing to wait for.
+            if (t + 1 < p.t1 && lane < B4_NCH)
+                wait_flag_ge(&p.flags[(t + 1 - p.t0) * BWD_NCH + rank * B4_NCH + lane], 4, p.status, 232);
+            __syncwarp();
+            if (elect_one()) {
+                fence_proxy_async_global();
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    mbar_expect_tx(&full[g], GS * slot_bytes);
+                    tma_load_3d(sA + g * GS * slot_bytes, &tmG, &full[g], 0, (t + 1) * p.B, rank * B4_NCH + g * GS);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        mbar_wait(wbar, 0, p.status, 233);
+        const uint32_t idesc = umma_idesc(128, B4_UNITS, FMT_F16, FMT_F16, 0, 0);
+        const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint64_t da_base = umma_smem_desc(smem_u32(sA), 16, 1024), db_base = umma_smem_desc(smem_u32(sW), 16, 1024);
+        const uint64_t a_chunk = static_cast<uint64_t>(slot_bytes >> 4), b_chunk = (B4_UNITS * 128) >> 4;
+        int step = 0;
+        for (int t = t_hi; t >= p.t0; --t, ++step) {
+            const int ph = step & 1;
+            uint64_t da = da_base, db = db_base;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                mbar_wait(&full[g], ph, p.status, 234);
+                tc_fence_after();
+                if (elect_one()) {
+                    uint64_t xa = da, xb = db;
+#pragma unroll
+                    for (int c = 0; c < GS; ++c) {
+#pragma unroll
+                        for (int k = 0; k < KCH / 16; ++k)
+                            umma_f16(tmem_d, xa + 2 * k, xb + 2 * k, idesc, (g | c | k) != 0);
+                        xa += a_chunk;
+                        xb += b_chunk;
+                    }
+                    if (g == NG - 1) umma_commit(accum_full);
+                }
+                __syncwarp();
+                da += GS * a_chunk;
+                db += GS * b_chunk;
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int et = threadIdx.x - 64;
+        const int n_items = p.B * 4;                              // (batch row, quad of units) over this rank's 16 final units
+        const int u0 = B4_UNITS * cl + B4_OWN * rank;
+        const int item = et;
+        const bool has_item = item < n_items;
+        const int ib = item >> 2, uq = item & 3;
+        float dcs[4] = {0.f, 0.f, 0.f, 0.f};
+        const int len = (has_item && p.lens) ? p.lens[ib] : p.T;
+        if (!top && has_item) {                                   // resume dc * f carried out of the chunk above
+            const float4 cv = *reinterpret_cast<const float4*>(p.dc_carry + static_cast<long long>(ib) * LH + B4_UNITS * cl + B4_OWN * rank + 4 * uq);
+            dcs[0] = cv.x; dcs[1] = cv.y; dcs[2] = cv.z; dcs[3] = cv.w;
+        }
+        uint32_t part_remote[B4_CLUSTER];
+#pragma unroll
+        for (int r = 0; r < B4_CLUSTER; ++r) part_remote[r] = mapa_shared(smem_u32(sPart), r);
+        int step = 0;
+        for (int t = p.t1 - 1; t >= p.t0; --t, ++step) {
+            const int rs = top ? step - 1 : step;                 // index of this step among the steps with a recurrent term
+            float dh[4], ct[4], cp[4];
+            __half2 gt[4][2];
+            const bool valid = has_item && (t < len);
+            const long long r = static_cast<long long>(t) * p.B + ib;
+            const int uo = u0 + 4 * uq;
+            if (valid) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(p.dh_ext + r * p.ldd + uo));
+                dh[0] = v.x; dh[1] = v.y; dh[2] = v.z; dh[3] = v.w;
+                const float4 cc = __ldg(reinterpret_cast<const float4*>(p.cstate + r * LH + uo));
+                ct[0] = cc.x; ct[1] = cc.y; ct[2] = cc.z; ct[3] = cc.w;
+                float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t > 0) pp = __ldg(reinterpret_cast<const float4*>(p.cstate + (r - p.B) * LH + uo));
+                cp[0] = pp.x; cp[1] = pp.y; cp[2] = pp.z; cp[3] = pp.w;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint2 pk = __ldg(reinterpret_cast<const uint2*>(p.gates + r * LG + g * LH + uo));
+                    *reinterpret_cast<uint2*>(&gt[g][0]) = pk;
+                }
+            }
+            float rec[4] = {0.f, 0.f, 0.f, 0.f};                 // recurrent part of dh_t: sum over the 4 ranks' partials
+            if (rs >= 0) {
+                const int par = rs & 1;
+                float* mine = sPart + par * 32 * B4_PP;
+                if (q == 0) {                                     // B <= 32: TMEM rows 0..31 hold the batch rows
+                    mbar_wait(accum_full, rs & 1, p.status, 235);
+                    tc_fence_after();
+                    {
+                        float a0[32], a1[32];
+                        tmem_ld_32x32(tmem_base, a0);
+                        tmem_ld_32x32(tmem_base + 32, a1);
+                        tmem_ld_wait();
+                        float* dst = mine + lane * B4_PP;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            *reinterpret_cast<float4*>(dst + j) = make_float4(a0[j], a0[j + 1], a0[j + 2], a0[j + 3]);
+                            *reinterpret_cast<float4*>(dst + 32 + j) = make_float4(a1[j], a1[j + 1], a1[j + 2], a1[j + 3]);
+                        }
+                    }
+                    tc_fence_before();
+                }
+                epi_bar();
+                // publish: one release-arrive on every rank's barrier, issued by 4 different threads so the four
+                // cluster-scope releases overlap (issued serially by one thread they cost ~1.8 us per step)
+                if (et < B4_CLUSTER) mbar_arrive_cluster(mapa_shared(smem_u32(&part_bar[par]), et));
+                mbar_wait_cluster(&part_bar[par], (rs >> 1) & 1, p.status, 236);
+                if (has_item) {
+                    const uint32_t off = static_cast<uint32_t>((par * 32 * B4_PP + ib * B4_PP + B4_OWN * rank + 4 * uq) * 4);
+#pragma unroll
+                    for (int rr = 0; rr < B4_CLUSTER; ++rr) {
+                        const float4 v = ld_dsmem_f4(part_remote[rr] + off);
+                        rec[0] += v.x; rec[1] += v.y; rec[2] += v.z; rec[3] += v.w;
+                    }
+                }
+            }
+            if (has_item) {
+                __half2 out[4][2];
+                if (valid) {
+#pragma unroll
+                    for (int j2 = 0; j2 < 2; ++j2) {
+                        float da[4][2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int j = 2 * j2 + e;
+                            const float gi = e ? __high2float(gt[0][j2]) : __low2float(gt[0][j2]);
+                            const float gf = e ? __high2float(gt[1][j2]) : __low2float(gt[1][j2]);
+                            const float gg = e ? __high2float(gt[2][j2]) : __low2float(gt[2][j2]);
+                            const float go = e ? __high2float(gt[3][j2]) : __low2float(gt[3][j2]);
+                            const float dht = dh[j] + rec[j];
+                            const float tc = tanh_f(ct[j]);
+                            const float dc = dcs[j] + dht * go * (1.f - tc * tc);
+                            da[3][e] = dht * tc * go * (1.f - go);
+                            da[0][e] = dc * gg * gi * (1.f - gi);
+                            da[2][e] = dc * gi * (1.f - gg * gg);
+                            da[1][e] = dc * cp[j] * gf * (1.f - gf);
+                            dcs[j] = dc * gf;
+                        }
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            out[g][j2] = __floats2half2_rn(fminf(fmaxf(da[g][0], -65504.f), 65504.f),
+                                                           fminf(fmaxf(da[g][1], -65504.f), 65504.f));
+                    }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) { out[g][0] = __floats2half2_rn(0.f, 0.f); out[g][1] = out[g][0]; }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dcs[j] = 0.f;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    *reinterpret_cast<uint2*>(p.dG + r * LG + g * LH + uo) = *reinterpret_cast<uint2*>(&out[g][0]);
+            }
+            epi_bar();                                            // every dG_t store of this CTA precedes the releases
+            if (et < 4) red_release_add(&p.flags[(t - p.t0) * BWD_NCH + et * 16 + cl], 1);     // chunk (gate et, units 64cl..) : 4 ranks
+        }
+        if (p.t0 > 0 && has_item)                                 // hand dc * f to the chunk below
+            *reinterpret_cast<float4*>(p.dc_carry + static_cast<long long>(ib) * LH + B4_UNITS * cl + B4_OWN * rank + 4 * uq) =
+                make_float4(dcs[0], dcs[1], dcs[2], dcs[3]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                          // nobody exits while a peer may still read its partials
+    if (warp == 1) tmem_dealloc<64>(tmem_base);
+}
+
+
 // ------------------------------------------------------------------------------------------- forward, one chunk of steps
 // EXPERIMENTAL (round-2 groundwork; NOT validated on hardware yet, only reachable with FT_PIPE_FWD=1):
 // the same recurrence over steps [t0, t1) only, resuming h from the output tensor (row t0-1) and c from the saved cell
@@ -1041,6 +1267,42 @@ int launch_lstm_fwd_chunk(int T, int B, int t0, int t1, const float* xproj, cons
     if (e != cudaSuccess) return ft_set_error(cudaGetErrorString(e));
     ft_count_launch(1);
     return ft_check_launch("lstm_fwd_chunk_kernel");
+}
+
+// EXPERIMENTAL (see lstm_bwd4_chunk_kernel): steps [t0, t1) of a layer's BPTT, B <= 32.  `flags` needs (t1 - t0) * 64 ints.
+int launch_lstm_bwd_chunk(int T, int B, int t0, int t1, const float* dh_ext, long long ldd, const void* whhT16, const void* gates16,
+                          const float* cstate, const int* lens, void* dG16, float* dc_carry, int* flags, cudaStream_t st) {
+    if (T <= 0 || B <= 0 || t1 <= t0) return 0;
+    if (B > 32 || t0 < 0 || t1 > T || !dc_carry) return ft_set_error("lstm_bwd_chunk: bad batch, step range or carry buffer");
+    LstmBwdChunkParams p;
+    p.T = T; p.B = B; p.Bbox = (B + 7) & ~7; p.gs = 8; p.ng = 2; p.nring = 0; p.t0 = t0; p.t1 = t1; p.dc_carry = dc_carry;
+    const int slot = p.Bbox * 128;
+    p.dh_ext = dh_ext; p.ldd = ldd; p.gates = static_cast<const __half*>(gates16); p.cstate = cstate; p.lens = lens;
+    p.dG = static_cast<__half*>(dG16); p.flags = flags; p.status = ft_status_word(); p.trace = nullptr;
+    CUtensorMap tmWT, tmG;
+    if (make_tmap_2d(&tmWT, whhT16, FMT_F16, LH, LG, LG, KCH, B4_UNITS)) return -1;
+    if (make_tmap_chunks(&tmG, dG16, static_cast<long long>(T) * B, BWD_NCH, LG, p.Bbox, 8)) return -1;
+    if (cudaMemsetAsync(flags, 0, sizeof(int) * (t1 - t0) * BWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_bwd_chunk: memset failed");
+    const int smem = B4_NCH * slot + B4_W_BYTES + 2 * 32 * B4_PP * 4 + 256 + 1024;
+    cudaFuncSetAttribute(lstm_bwd4_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B4_CTAS); cfg.blockDim = dim3(LSTM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = B4_CLUSTER; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeCooperative;
+    attrs[1].val.cooperative = 1;
+    cfg.attrs = attrs; cfg.numAttrs = 2;
+    TimeScope ts("lstm_bwd", t1 - t0, B, 0, st);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_bwd4_chunk_kernel, tmWT, tmG, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, lstm_bwd4_chunk_kernel, tmWT, tmG, p);
+    }
+    if (e != cudaSuccess) return ft_set_error(cudaGetErrorString(e));
+    ft_count_launch(1);
+    return ft_check_launch("lstm_bwd4_chunk_kernel");
 }
 
 int launch_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void* whhT16, const void* gates16,

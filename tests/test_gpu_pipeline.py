@@ -1,5 +1,5 @@
-"""GPU, EXPERIMENTAL and therefore opt-in (FT_TEST_EXPERIMENTAL=1): the chunk-pipelined forward of lstm layers 0/1
-(FT_PIPE_FWD=1) must reproduce the default schedule bit for bit -- same kernels' arithmetic, different
+"""GPU, EXPERIMENTAL and therefore opt-in (FT_TEST_EXPERIMENTAL=1): the chunk-pipelined forward and BPTT of lstm layers 0/1
+(FT_PIPE_FWD=1 / FT_PIPE_BWD=1) must reproduce the default schedule bit for bit -- same kernels' arithmetic, different
 launch granularity.  The switch is read once per process by the library, so the pipelined run happens in a child process."""
 import os
 import subprocess
@@ -19,12 +19,18 @@ sys.path.insert(0, sys.argv[1])
 from flowtron_b200 import synth
 from flowtron_b200.flowtron import Flowtron
 cfg = dict(synth.DEFAULT_MODEL_CONFIG, n_flows=2)
-model = Flowtron(**cfg); model.load_state_dict(synth.synth_params(cfg, 5), strict=True); model = model.cuda().eval()
+model = Flowtron(**cfg); model.load_state_dict(synth.synth_params(cfg, 5), strict=True); model = model.cuda()
 b = synth.synth_batch(5, 77, 12, cfg, 9, with_prior=True)
 d = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
-with torch.no_grad():
-    out = model(d["mel"], d["speaker_ids"], d["text"], d["in_lens"], d["out_lens"], d["attn_prior"])
-torch.save({"z": out[0].cpu(), "log_s": [x.cpu() for x in out[1]], "gate": out[2].cpu()}, sys.argv[2])
+from flowtron_b200.flowtron import FlowtronLoss
+model.train(); model.encoder.p_dropout = 0.0
+torch.backends.cudnn.allow_tf32 = False
+out = model(d["mel"], d["speaker_ids"], d["text"], d["in_lens"], d["out_lens"], d["attn_prior"])
+nll, gl, _ = FlowtronLoss()(out, d["gate_target"], d["in_lens"], d["out_lens"])
+(nll + gl).sum().backward()
+torch.cuda.synchronize()
+torch.save({"z": out[0].detach().cpu(), "log_s": [x.detach().cpu() for x in out[1]], "gate": out[2].detach().cpu(),
+            "grads": {n: p.grad.cpu() for n, p in model.named_parameters()}}, sys.argv[2])
 '''
 
 
@@ -37,8 +43,12 @@ def _run(tmp_path, name, env):
 
 
 def test_pipelined_layers_equal_default_schedule(tmp_path):
-    a = _run(tmp_path, "default", {"FT_PIPE_FWD": "0"})
-    b = _run(tmp_path, "pipe", {"FT_PIPE_FWD": "1", "FT_PIPE_CHUNK": "16"})      # 77 steps -> 5 chunks, ragged tail
+    a = _run(tmp_path, "default", {"FT_PIPE_FWD": "0", "FT_PIPE_BWD": "0"})
+    b = _run(tmp_path, "pipe", {"FT_PIPE_FWD": "1", "FT_PIPE_BWD": "1", "FT_PIPE_CHUNK": "16"})   # 77 steps -> 5 chunks, ragged tail
     assert torch.equal(a["z"], b["z"]) and torch.equal(a["gate"], b["gate"])
     for x, y in zip(a["log_s"], b["log_s"]):
         assert torch.equal(x, y)
+    gmax = max(v.norm().item() for v in a["grads"].values())
+    for k in a["grads"]:
+        d = (a["grads"][k] - b["grads"][k]).norm().item()
+        assert d <= 1e-4 * (a["grads"][k].norm().item() + 1e-4 * gmax), (k, d)     # atomics / wgrad split order only
