@@ -12,16 +12,27 @@ from flowtron_b200.flowtron import Flowtron, FlowtronLoss
 cfg = dict(synth.DEFAULT_MODEL_CONFIG)
 model = Flowtron(**cfg); model.load_state_dict(synth.synth_params(cfg, 1234), strict=True); model = model.cuda().train()
 crit = FlowtronLoss()
-opt = torch.optim.RAdam(model.parameters(), lr=1e-3, weight_decay=1e-6)
+FUSED = os.environ.get("FT_FUSED_OPT", "0") != "0"        # same switch as bench.py: profile the fused optimizer's stall
+if FUSED:
+    from flowtron_b200.radam import RAdam
+    opt = RAdam(model.parameters(), lr=1e-3, weight_decay=1e-6)
+else:
+    opt = torch.optim.RAdam(model.parameters(), lr=1e-3, weight_decay=1e-6)
 batch, L = bench.make_batch(cfg, 32, 1000, 1234)
 d = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
 
 def step():
-    opt.zero_grad(set_to_none=True)
+    if FUSED:
+        opt.zero_grad()
+    else:
+        opt.zero_grad(set_to_none=True)
     out = model(d["mel"], d["speaker_ids"], d["text"], d["in_lens"], d["out_lens"], d["attn_prior"])
     nll, gl, _ = crit(out, d["gate_target"], d["in_lens"], d["out_lens"])
     (nll + gl).sum().backward()
-    torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+    if FUSED:
+        opt.clip_grad_norm_(1.0)
+    else:
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
     opt.step()
 
 for _ in range(3): step()
