@@ -88,3 +88,18 @@ def test_encoder_matches_oracle_restatement():
         ours_i = m.encoder.infer(x[:1])
         ref_i = O.encoder_forward(p, x[:1], None, infer=True)
         assert (ours_i - ref_i).abs().max().item() < 1e-5
+
+
+def test_default_switches_are_the_validated_configuration(monkeypatch):
+    """The round-1 GPU validation (profiles/r1_final2_*) ran with: encoder overlap ON, two-stream BiLSTM OFF, fused
+    optimizer OFF, layer pipeline OFF.  Anything else is opt-in through the environment."""
+    import flowtron_b200.flowtron as F
+    if "FT_ENC_OVERLAP" not in os.environ:                 # class attribute, read at import
+        assert F.Flowtron.overlap_encoder is True
+    monkeypatch.delenv("FT_ENC_STREAMS", raising=False)
+    assert F.Encoder().two_streams is False
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert 'os.environ.get("FT_FUSED_OPT", "0")' in src
+    csrc = open(os.path.join(ROOT, "flowtron_b200", "csrc", "ar_step.cu")).read()
+    assert 'getenv("FT_PIPE_FWD"); v = (e && atoi(e) != 0) ? 1 : 0' in csrc
+    assert 'getenv("FT_PIPE_BWD"); v = (e && atoi(e) != 0) ? 1 : 0' in csrc
