@@ -319,7 +319,6 @@ attn_bwd_kernel(AttnBwdParams p) {
     const int in_len = p.in_lens ? p.in_lens[b] : p.L;
     const int nrows = min(AT_TT, p.T - t0);
     const int ty = tid >> 4, tx = tid & 15;
-    const int nlb = (p.L + AT_LB - 1) / AT_LB;
 
     if (t0 >= out_len) {                              // forward wrote constants here: no gradient
         for (int i = tid; i < nrows * p.A; i += AT_THREADS) {
