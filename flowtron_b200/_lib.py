@@ -83,14 +83,29 @@ def _declare(L):
     L.ft_ar_step_bwd.restype = c_int
     L.ft_ar_step_infer_scratch_bytes.argtypes = [POINTER(FtArStepDesc)]
     L.ft_ar_step_infer_scratch_bytes.restype = c_size_t
-    L.ft_ar_step_infer.argtypes = [POINTER(FtArStepDesc), POINTER(FtArStepWeights), c_void_p, c_void_p, c_void_p, c_float,
-                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.ft_ar_step_infer.argtypes = [POINTER(FtArStepDesc), POINTER(FtArStepWeights), c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.ft_ar_step_infer.restype = c_int
     L.ft_mel_scratch_bytes.argtypes = [c_int, c_longlong]
     L.ft_mel_scratch_bytes.restype = c_size_t
     L.ft_mel_spectrogram.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_longlong, c_void_p]
     L.ft_mel_spectrogram.restype = c_int
+    L.ft_mel_spectrogram_fused.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]
+    L.ft_mel_spectrogram_fused.restype = c_int
+    L.ft_stft_transform.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p]
+    L.ft_stft_transform.restype = c_int
+    L.ft_attn_prior.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]
+    L.ft_attn_prior.restype = c_int
+    L.ft_collate_mel.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.ft_collate_mel.restype = c_int
+    L.ft_attn_ctc_scratch_bytes.argtypes = [c_int, c_int, c_int]
+    L.ft_attn_ctc_scratch_bytes.restype = c_size_t
+    L.ft_attn_ctc_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                   c_void_p]
+    L.ft_attn_ctc_loss.restype = c_int
     L.ft_nll_reduce.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
     L.ft_nll_reduce.restype = c_int
     L.ft_nll_grad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
@@ -310,11 +325,12 @@ def radam_step_raw(p_ptr, g_ptr, m_ptr, v_ptr, n, beta1, beta2, eps, weight_deca
                               c_void_p(coef_ptr) if coef_ptr else None, stream_ptr()), "ft_radam_step")
 
 
-def ar_step_infer(desc, weights, residual, text, prior, gate_threshold, out, attn_out, n_frames):
+def ar_step_infer(desc, weights, residual, text, prior, attn_forced, gate_threshold, out, attn_out, n_frames):
     nbytes = int(lib().ft_ar_step_infer_scratch_bytes(byref(desc)))
     scratch = scratch_buffer(nbytes, residual.device)
-    check(lib().ft_ar_step_infer(byref(desc), byref(weights), ptr(residual), ptr(text), ptr(prior), float(gate_threshold),
-                                 ptr(out), ptr(attn_out), ptr(n_frames), ptr(scratch), stream_ptr()), "ft_ar_step_infer")
+    check(lib().ft_ar_step_infer(byref(desc), byref(weights), ptr(residual), ptr(text), ptr(prior), ptr(attn_forced),
+                                 float(gate_threshold), ptr(out), ptr(attn_out), ptr(n_frames), ptr(scratch), stream_ptr()),
+          "ft_ar_step_infer")
 
 
 def mel_spectrogram(wav, sample_offsets, frame_offsets, n_utt, total_frames, window, basis, band_lo, band_hi, n_fft, hop,
@@ -324,3 +340,44 @@ def mel_spectrogram(wav, sample_offsets, frame_offsets, n_utt, total_frames, win
     check(lib().ft_mel_spectrogram(ptr(wav), ptr(sample_offsets), ptr(frame_offsets), n_utt, total_frames, ptr(window),
                                    ptr(basis), ptr(band_lo), ptr(band_hi), basis.shape[0], n_fft, hop, float(clip),
                                    ptr(mel_out), ptr(scratch), chunk, stream_ptr()), "ft_mel_spectrogram")
+
+
+def mel_spectrogram_fused(wav, sample_offsets, frame_offsets, n_utt, total_frames, window, basis, band_lo, band_hi, n_fft, hop,
+                          clip, mel_out):
+    """wav: flat f32 (in [-1,1]) or int16 PCM CUDA tensor.  One kernel, no scratch (csrc/mel_fused.cu)."""
+    _need_cuda(wav, mel_out)
+    fmt = {torch.float32: 0, torch.int16: 1}[wav.dtype]
+    check(lib().ft_mel_spectrogram_fused(ptr(wav), fmt, ptr(sample_offsets), ptr(frame_offsets), int(n_utt), int(total_frames),
+                                         ptr(window), ptr(basis), ptr(band_lo), ptr(band_hi), basis.shape[0], int(n_fft),
+                                         int(hop), float(clip), ptr(mel_out), stream_ptr()), "ft_mel_spectrogram_fused")
+
+
+def stft_transform(wav, sample_offsets, frame_offsets, n_utt, total_frames, window, n_fft, hop, magnitude, phase):
+    _need_cuda(wav, magnitude, phase)
+    check(lib().ft_stft_transform(ptr(wav), ptr(sample_offsets), ptr(frame_offsets), int(n_utt), int(total_frames), ptr(window),
+                                  int(n_fft), int(hop), ptr(magnitude), ptr(phase), stream_ptr()), "ft_stft_transform")
+
+
+def attn_prior(in_lens, out_lens, T, L, scaling, threshold, prior):
+    """in_lens / out_lens: int32 CUDA [B]; prior: f32 CUDA [B,T,L] (written)."""
+    _need_cuda(in_lens, out_lens, prior)
+    assert in_lens.dtype == torch.int32 and out_lens.dtype == torch.int32 and prior.is_contiguous()
+    check(lib().ft_attn_prior(ptr(in_lens), ptr(out_lens), in_lens.numel(), int(T), int(L), float(scaling), float(threshold),
+                              ptr(prior), stream_ptr()), "ft_attn_prior")
+
+
+def collate_mel(mel_packed, frame_offsets, order, n_mel, T, mel_padded, gate_padded, out_lens):
+    _need_cuda(mel_packed, frame_offsets, order, mel_padded, gate_padded, out_lens)
+    assert order.dtype == torch.int32 and out_lens.dtype == torch.int32 and frame_offsets.dtype == torch.int64
+    check(lib().ft_collate_mel(ptr(mel_packed), ptr(frame_offsets), ptr(order), order.numel(), int(n_mel), int(T),
+                               ptr(mel_padded), ptr(gate_padded), ptr(out_lens), stream_ptr()), "ft_collate_mel")
+
+
+def attn_ctc_loss(logprob, in_lens, out_lens, time_reversed, blank_logprob, cost, dlogprob):
+    """logprob [B,T,L] f32 CUDA (one flow), in_lens / out_lens int32 CUDA [B]; cost [B], dlogprob [B,T,L] written."""
+    _need_cuda(logprob, in_lens, out_lens, cost, dlogprob)
+    B, T, L = logprob.shape
+    assert logprob.is_contiguous() and dlogprob.is_contiguous() and in_lens.dtype == torch.int32 and out_lens.dtype == torch.int32
+    scratch = scratch_buffer(int(lib().ft_attn_ctc_scratch_bytes(B, T, L)), logprob.device)
+    check(lib().ft_attn_ctc_loss(ptr(logprob), ptr(in_lens), ptr(out_lens), B, T, L, 1 if time_reversed else 0,
+                                 float(blank_logprob), ptr(cost), ptr(dlogprob), ptr(scratch), stream_ptr()), "ft_attn_ctc_loss")

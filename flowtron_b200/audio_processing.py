@@ -1,8 +1,11 @@
 """Mel front-end with the reference's API (audio_processing.py: TacotronSTFT :96-134, STFT :172-270).
 
-``TacotronSTFT.mel_spectrogram(y[B,N]) -> [B,80,F]`` runs on the GPU (framing kernel + batched cuFFT + fused
-magnitude / sparse filterbank / log kernel, csrc/mel.cu).  ``mel_spectrogram_ragged`` is the batched form for a
-whole dataset shard (what data.py:149-155 does one utterance at a time on a CPU worker).
+``TacotronSTFT.mel_spectrogram(y[B,N]) -> [B,80,F]`` runs on the GPU: for the shipped filter_length 1024 as ONE fused
+kernel (csrc/mel_fused.cu: reflect pad + window on the load, per-warp 1024-point FFT in shared memory, |X|, sparse
+filterbank, log; waveform read once, mel written once), for other sizes as framing kernel + batched cuFFT + fused
+magnitude / filterbank / log (csrc/mel.cu).  ``mel_spectrogram_packed`` / ``mel_spectrogram_ragged`` are the batched
+forms for a whole dataset shard (what data.py:149-155 does one utterance at a time on a CPU worker); int16 PCM input is
+scaled by 1/32768 on load (data.py:150).  ``STFT.transform`` returns (magnitude, phase) like the reference.
 Buffers ``mel_basis``, ``stft_fn.forward_basis``, ``stft_fn.inverse_basis`` keep the reference's state_dict layout.
 The inverse STFT / Griffin-Lim are not called by training or inference and are not provided.
 """
@@ -59,8 +62,26 @@ class STFT(torch.nn.Module):
         self.register_buffer('_window', w, persistent=False)
 
     def transform(self, input_data):
-        raise NotImplementedError("STFT.transform's (magnitude, phase) pair is only used by Griffin-Lim / the denoiser, "
-                                  "outside the hot path; use TacotronSTFT.mel_spectrogram")
+        """audio_processing.py:207-235: input [B, N] -> (magnitude [B, n_fft/2+1, F], phase [B, n_fft/2+1, F]),
+        F = 1 + N // hop, phase = atan2(imag, real).  CUDA only (fused FFT kernel, filter_length 1024)."""
+        if not input_data.is_cuda:
+            raise FlowtronB200Error("STFT.transform needs CUDA tensors: the sm_100a path is the only implementation")
+        if self.filter_length != 1024:
+            raise NotImplementedError("STFT.transform is built for filter_length 1024 (config.json:31)")
+        B, N = input_data.shape
+        if N <= self.filter_length // 2:
+            raise ValueError("input shorter than the reflect padding")
+        self.num_samples = N
+        F = 1 + N // self.hop_length
+        dev = input_data.device
+        so = torch.arange(B + 1, device=dev, dtype=torch.int64) * N
+        fo = torch.arange(B + 1, device=dev, dtype=torch.int64) * F
+        cutoff = self.filter_length // 2 + 1
+        magnitude = torch.empty(B, cutoff, F, device=dev)
+        phase = torch.empty(B, cutoff, F, device=dev)
+        _lib.stft_transform(input_data.detach().float().contiguous(), so, fo, B, B * F, self._window, self.filter_length,
+                            self.hop_length, magnitude, phase)
+        return magnitude, phase
 
     def inverse(self, magnitude, phase):
         raise NotImplementedError("inverse STFT is not on the Flowtron training/inference path")
@@ -86,22 +107,47 @@ class TacotronSTFT(torch.nn.Module):
     def spectral_de_normalize(self, magnitudes):
         return torch.exp(magnitudes)
 
+    def _run(self, flat, so, fo, n_utt, total, out):
+        hop, n_fft = self.stft_fn.hop_length, self.stft_fn.filter_length
+        if n_fft == 1024:
+            _lib.mel_spectrogram_fused(flat, so, fo, n_utt, total, self.stft_fn._window, self.mel_basis, self._band_lo,
+                                       self._band_hi, n_fft, hop, 1e-5, out)
+        else:
+            if flat.dtype != torch.float32:
+                flat = flat.float() / 32768.0
+            _lib.mel_spectrogram(flat, so, fo, n_utt, total, self.stft_fn._window, self.mel_basis, self._band_lo,
+                                 self._band_hi, n_fft, hop, 1e-5, out)
+
+    def mel_spectrogram_packed(self, flat, lengths, out=None):
+        """Whole-shard form: ``flat`` = the utterances concatenated (f32 in [-1, 1] or int16 PCM, CUDA), ``lengths`` = their
+        sample counts (host sequence; each > filter_length/2).  Returns (mel_packed, frame_offsets): per-utterance
+        [n_mel, 1 + N_u // hop] blocks concatenated (utterance u = mel_packed[fo[u]*n_mel : fo[u+1]*n_mel].view(n_mel, -1))
+        and the host int64 prefix sums fo.  One kernel launch for the whole shard; no host sync."""
+        if not flat.is_cuda:
+            raise FlowtronB200Error("TacotronSTFT needs CUDA tensors: the sm_100a path is the only implementation")
+        if flat.dtype not in (torch.float32, torch.int16):
+            raise TypeError("waveform must be float32 in [-1, 1] or int16 PCM")
+        hop, n_fft = self.stft_fn.hop_length, self.stft_fn.filter_length
+        lens = np.asarray(lengths, dtype=np.int64)
+        if lens.min() <= n_fft // 2:
+            raise ValueError("utterance shorter than the reflect padding (torch's reflect pad raises too)")
+        so = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        fo = np.concatenate([[0], np.cumsum(1 + lens // hop)]).astype(np.int64)
+        assert int(so[-1]) == flat.numel(), "lengths do not add up to the packed waveform"
+        dev = flat.device
+        total = int(fo[-1])
+        if out is None:
+            out = torch.empty(total * self.n_mel_channels, device=dev)
+        self._run(flat.contiguous(), torch.from_numpy(so).to(dev, non_blocking=True), torch.from_numpy(fo).to(dev, non_blocking=True),
+                  len(lens), total, out)
+        return out, fo
+
     def mel_spectrogram_ragged(self, wavs):
         """wavs: list of 1-D float tensors in [-1, 1] (any lengths > filter_length/2) -> list of [n_mel, 1 + N//hop]."""
         if not wavs[0].is_cuda:
-            raise FlowtronB200Error("TacotronSTFT needs CUDA tensors: the cuFFT/sm_100a path is the only implementation")
-        dev = wavs[0].device
-        hop, n_fft = self.stft_fn.hop_length, self.stft_fn.filter_length
-        lens = [int(w.numel()) for w in wavs]
-        if min(lens) <= n_fft // 2:
-            raise ValueError("utterance shorter than the reflect padding (torch's reflect pad raises too)")
-        so = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-        fo = np.concatenate([[0], np.cumsum([1 + n // hop for n in lens])]).astype(np.int64)
+            raise FlowtronB200Error("TacotronSTFT needs CUDA tensors: the sm_100a path is the only implementation")
         flat = torch.cat([w.reshape(-1).float() for w in wavs]) if len(wavs) > 1 else wavs[0].reshape(-1).float().contiguous()
-        total = int(fo[-1])
-        out = torch.empty(total * self.n_mel_channels, device=dev)
-        _lib.mel_spectrogram(flat, torch.from_numpy(so).to(dev), torch.from_numpy(fo).to(dev), len(wavs), total,
-                             self.stft_fn._window, self.mel_basis, self._band_lo, self._band_hi, n_fft, hop, 1e-5, out)
+        out, fo = self.mel_spectrogram_packed(flat, [int(w.numel()) for w in wavs])
         return [out[fo[i] * self.n_mel_channels: fo[i + 1] * self.n_mel_channels].view(self.n_mel_channels, -1)
                 for i in range(len(wavs))]
 
@@ -120,6 +166,5 @@ class TacotronSTFT(torch.nn.Module):
         so = torch.arange(B + 1, device=dev, dtype=torch.int64) * N
         fo = torch.arange(B + 1, device=dev, dtype=torch.int64) * F
         out = torch.empty(B, self.n_mel_channels, F, device=dev)
-        _lib.mel_spectrogram(y.detach().float().contiguous(), so, fo, B, B * F, self.stft_fn._window, self.mel_basis,
-                             self._band_lo, self._band_hi, n_fft, hop, 1e-5, out)
+        self._run(y.detach().float().contiguous(), so, fo, B, B * F, out)
         return out

@@ -401,7 +401,9 @@ int ar_step_bwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
 
     // 0. loss scale for this flow's backward: S = 2^k with S * max|incoming grad| ~ 64 (device-side, no host sync)
     const long long RM = R * n.M;
-    FT_TRY(launch_grad_scale(d_mel_out, d_mel_out ? RM : 0, d_log_s, d_log_s ? RM : 0, d_gates, d_gates ? R : 0, 64.f, F.scale, st));
+    const long long BTL = static_cast<long long>(n.B) * n.T * n.L;
+    FT_TRY(launch_grad_scale(d_mel_out, d_mel_out ? RM : 0, d_log_s, d_log_s ? RM : 0, d_gates, d_gates ? R : 0, 64.f, F.scale, st,
+                             d_attn, d_attn ? BTL : 0, d_logprob, d_logprob ? BTL : 0));
     const float* S = F.scale;            // S[0] = scale, S[1] = 1/scale
     const float* iS = F.scale + 1;
 

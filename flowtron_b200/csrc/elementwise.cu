@@ -115,14 +115,18 @@ __global__ void scale_finalize_kernel(const unsigned int* __restrict__ mx, float
     scale2[1] = 1.f / s;
 }
 int launch_grad_scale(const float* a, long long na, const float* b, long long nb, const float* c, long long nc, float target,
-                      float* scale2, cudaStream_t st) {
+                      float* scale2, cudaStream_t st, const float* d, long long nd, const float* e, long long ne) {
     unsigned int* mx = reinterpret_cast<unsigned int*>(scale2 + 2);
     if (cudaMemsetAsync(mx, 0, sizeof(unsigned int), st) != cudaSuccess) return ft_set_error("grad_scale: memset failed");
     long long n = na > nb ? na : nb;
     n = n > nc ? n : nc;
-    absmax_kernel<<<grid_for(n, 256, 4), 256, 0, st>>>(a, na, b, nb, c, nc, mx);
+    if (n > 0) absmax_kernel<<<grid_for(n, 256, 4), 256, 0, st>>>(a, na, b, nb, c, nc, mx);
+    // the attention-side external gradients (CTC loss path: d_attn, d_attn_logprob) are multiplied by the same S inside
+    // attn_bwd and their products are cast to fp16 too, so they take part in choosing S
+    const long long n2 = nd > ne ? nd : ne;
+    if (n2 > 0 && (d || e)) absmax_kernel<<<grid_for(n2, 256, 4), 256, 0, st>>>(d, d ? nd : 0, e, e ? ne : 0, nullptr, 0, mx);
     scale_finalize_kernel<<<1, 1, 0, st>>>(mx, target, scale2);
-    ft_count_launch(2);
+    ft_count_launch(3);
     return ft_check_launch("grad_scale");
 }
 

@@ -53,7 +53,8 @@ int launch_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void
 int launch_cast(const void* src, int src_fmt, void* dst, int dst_fmt, long long n, cudaStream_t st);   // 0 f16, 1 bf16, 2 f32
 int launch_transpose_cast_f16(const float* src, void* dst, int rows, int cols, cudaStream_t st);
 int launch_grad_scale(const float* a, long long na, const float* b, long long nb, const float* c, long long nc, float target,
-                      float* scale2, cudaStream_t st);   // scale2[0] = S (power of two), scale2[1] = 1/S
+                      float* scale2, cudaStream_t st, const float* d = nullptr, long long nd = 0, const float* e = nullptr,
+                      long long ne = 0);   // scale2[0] = S (power of two) from max|a..e|, scale2[1] = 1/S
 int launch_prep_mel(const float* mel, const int* lens, int T, int B, int M, int reversed, void* mel_in16, float* mel_flow, cudaStream_t st);
 int launch_gate_fwd(const void* d16, long long ldd, int K, const float* wg, const float* bg, long long R, float* gate, cudaStream_t st);
 int launch_gate_bwd(const void* d16, long long ldd, int K, const float* wg, const float* dgate, long long R, float* dd,

@@ -28,6 +28,7 @@ struct InferParams {
     const float* Kp; const float* Vp;      // [L*B, A] projected once
     const float* residual;                 // [T,B,M] flow-time order
     const float* prior;                    // [B,T,L] (row i used at frame i) or null
+    const float* attn_forced;              // [T,B,L] forced alignments (flowtron.py:585-588, 797): scoring is skipped
     float inv_temperature, gate_threshold;
     int has_gate;
     // outputs
@@ -204,11 +205,15 @@ infer_kernel(InferParams p) {
         // ---- P1 attention_lstm step on the previous output frame (zeros at i == 0)
         lstm_phase<IBT>(p, sx, p.w_ih_a, p.M, p.xprev, p.M, p.w_hh_a, p.hA[prv], p.b_ih_a, p.b_hh_a, p.cA, p.hA[cur]);
         grid_sync(p, epoch);
+        // forced alignments (`attn` given, flowtron.py:585-588): no query / score / softmax / prior, context = attn . V
+        const bool forced = p.attn_forced != nullptr;
         // ---- P2a query projection (no bias)
+        if (!forced) {
         dense_phase<IBT>(p, sx, p.wq, IH, p.A, p.hA[cur], IH, nullptr, 0, p.q, p.A);
         grid_sync(p, epoch);
+        }
         // ---- P2b scores e[b,l] = v . tanh(q[b] + K[l,b]) / temperature   (no key mask in inference, flowtron.py:800-803)
-        for (int t = gw; t < p.B * p.L; t += nw) {
+        for (int t = gw; t < p.B * p.L && !forced; t += nw) {
             const int b = t / p.L, l = t % p.L;
             const float* kr = p.Kp + (static_cast<long long>(l) * p.B + b) * p.A;
             float s = 0.f;
@@ -217,7 +222,7 @@ infer_kernel(InferParams p) {
             for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0) p.e[b * p.L + l] = s * p.inv_temperature;
         }
-        grid_sync(p, epoch);
+        if (!forced) grid_sync(p, epoch);
         // ---- P2c softmax (+ prior posterior) and context; d = [hA ; ctx]
         {
             const int chunks = (p.A + 31) / 32;
@@ -226,6 +231,13 @@ infer_kernel(InferParams p) {
                 // softmax over L in registers: lane holds l = lane + 32 j
                 float w[8];
                 float m = -INFINITY;
+                if (forced) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int l = lane + 32 * j;
+                        w[j] = (l < p.L) ? p.attn_forced[(static_cast<long long>(i) * p.B + b) * p.L + l] : 0.f;
+                    }
+                } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int l = lane + 32 * j;
@@ -242,7 +254,8 @@ infer_kernel(InferParams p) {
                 const float inv = 1.f / s;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) w[j] *= inv;
-                if (p.prior) {
+                }
+                if (p.prior && !forced) {
                     float m2 = -INFINITY;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -397,8 +410,8 @@ extern "C" {
 size_t ft_ar_step_infer_scratch_bytes(const FtArStepDesc* d) { return ft::plan_infer(*d, nullptr).total + 256; }
 
 int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const float* residual, const float* text,
-                     const float* attn_prior, float gate_threshold, float* out, float* attn_out, int* n_frames,
-                     void* scratch, void* stream) {
+                     const float* attn_prior, const float* attn_forced, float gate_threshold, float* out, float* attn_out,
+                     int* n_frames, void* scratch, void* stream) {
     using namespace ft;
     if (!d || !w || !residual || !text || !out || !attn_out || !n_frames || !scratch) return ft_set_error("ft_ar_step_infer: NULL argument");
     if (d->n_hidden != IH) return ft_set_error("infer: n_hidden must be 1024");
@@ -448,6 +461,7 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
     p.b_ih1 = w->lstm_b_ih1; p.b_hh1 = w->lstm_b_hh1; p.b1 = w->dense_b0; p.b2 = w->dense_b1; p.bc = w->conv_b;
     p.v = w->att_v; p.wg = w->gate_w; p.bg = w->gate_b;
     p.Kp = s.Kp; p.Vp = s.Vp; p.residual = residual; p.prior = d->has_prior ? attn_prior : nullptr;
+    p.attn_forced = attn_forced;
     p.inv_temperature = 1.0f / d->temperature; p.gate_threshold = gate_threshold;
     p.has_gate = d->has_gate && w->gate_w;
     p.out = out; p.attn_out = attn_out; p.n_frames = n_frames;

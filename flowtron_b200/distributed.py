@@ -99,10 +99,27 @@ def apply_gradient_allreduce(module):
     avg_ok = dist.get_backend() == "nccl"
     state = {"callback_queued": False}
 
+    def reset(*_):
+        """Forward pre-hook (the reference re-arms `needs_reduction` in a forward hook, distributed.py:126-131): a backward
+        that raised never ran finalize(), which would leave callback_queued set (every later backward would then skip
+        the join and the optimizer would read un-averaged gradients) and stale ready counts / work handles."""
+        state["callback_queued"] = False
+        for b in buckets:
+            if b.work is not None:
+                try:
+                    b.work.wait()
+                except Exception:
+                    pass
+                b.work = None
+            b.ready = 0
+
     def finalize():
         state["callback_queued"] = False
         for b in buckets:
-            if b.ready and b.work is None:                            # a bucket whose params did not all get grads
+            # every bucket is reduced on every rank every step, whether or not all (or any) of its parameters received a
+            # gradient on THIS rank (untouched gradients are the zeros of zero_grad_buckets): the set and order of
+            # collectives is then identical everywhere, so ranks cannot issue mismatched all-reduces and hang
+            if b.work is None:
                 launch(b)
         for b in buckets:
             if b.work is not None:
@@ -141,6 +158,7 @@ def apply_gradient_allreduce(module):
     for b in buckets:
         for p in b.params:
             p.register_post_accumulate_grad_hook(make_hook(b))
+    module.register_forward_pre_hook(reset)
 
     def zero_grad_buckets():
         for b in buckets:

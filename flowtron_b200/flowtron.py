@@ -176,8 +176,11 @@ class Encoder(nn.Module):
         for conv in self.convolutions:
             x = F.dropout(F.relu(conv(x)), self.p_dropout, self.training)
         x = x.transpose(1, 2)
-        self.lstm.flatten_parameters()
-        outputs, _ = self.lstm(x)
+        # no self.lstm.flatten_parameters() (flowtron.py:521): on cuDNN it moves the weights into a new buffer (param.set_),
+        # which would detach them from a flat-buffer optimizer / all-reduce bucket built earlier
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)
+            outputs, _ = self.lstm(x)
         return outputs
 
 
@@ -258,6 +261,9 @@ class _ArStepFn(torch.autograd.Function):
             d_gates = None
         c = lambda g: None if g is None else g.float().contiguous()
         d_mel_out, d_log_s, d_gates, d_attn, d_lp = map(c, (d_mel_out, d_log_s, d_gates, d_attn, d_lp))
+        if ctx.saved_buf is None:
+            raise FlowtronB200Error("AR_Step backward ran twice: the flow's saved activations are released after the first "
+                                    "backward (retain_graph is not supported on the CUDA path)")
         desc = ctx.desc
         dev = ctx.mel_c.device
         d_mel = torch.empty_like(ctx.mel_c)
@@ -268,7 +274,8 @@ class _ArStepFn(torch.autograd.Function):
         scratch = _lib.scratch_buffer(scratch_bytes, dev)
         _lib.ar_step_bwd(desc, weights, ctx.mel_c, ctx.in_lens, ctx.out_lens, ctx.attn, d_mel_out, d_log_s, d_gates, d_attn,
                          d_lp, d_mel, d_text, grads_s, ctx.saved_buf, scratch)
-        ctx.saved_buf = None
+        # release everything the node holds (saved activations, the output `attn` -> ctx reference cycle) right away
+        ctx.saved_buf = ctx.attn = ctx.mel_c = ctx.plist = ctx.in_lens = ctx.out_lens = None
         return (None, None, d_mel, d_text, None, None, None, *gl)
 
 
@@ -531,9 +538,32 @@ class _NllGateFn(torch.autograd.Function):
         return (None, dz, dgate, None, None, *([dls] * ctx.n_flows))
 
 
+class _AttnCtcFn(torch.autograd.Function):
+    """Batched attention-CTC cost per utterance and its gradient in one launch (ft_attn_ctc_loss, csrc/ctc.cu)."""
+
+    @staticmethod
+    def forward(ctx, attn_logprob, in_lens, out_lens, time_reversed, blank_logprob):
+        if not attn_logprob.is_cuda:
+            raise FlowtronB200Error("AttentionCTCLoss needs CUDA tensors: the sm_100a kernel is the only implementation")
+        lp = attn_logprob.detach().float().contiguous()
+        dev = lp.device
+        cost = torch.empty(lp.size(0), device=dev)
+        dlp = torch.empty_like(lp)
+        _lib.attn_ctc_loss(lp, _lens_i32(in_lens, dev), _lens_i32(out_lens, dev), time_reversed, blank_logprob, cost, dlp)
+        ctx.save_for_backward(dlp)
+        return cost
+
+    @staticmethod
+    def backward(ctx, g_cost):
+        (dlp,) = ctx.saved_tensors
+        return dlp * g_cost.reshape(-1, 1, 1), None, None, None, None
+
+
 class AttentionCTCLoss(nn.Module):
-    """flowtron.py:155-182 — out of the kernel scope (SURVEY §2 row 2): plain torch over the kernels' attn_logprob;
-    its gradient re-enters the CUDA path through ft_ar_step_bwd's d_attn_logprob."""
+    """flowtron.py:155-182.  Same constructor and call signature; the per-utterance Python loop (blank padding, slicing,
+    log_softmax, nn.CTCLoss, `.item()` host syncs) is ONE kernel launch for the whole batch.
+    ``time_reversed=True`` consumes an AR_Back_Step's attn_logprob in its flipped time directly, replacing the
+    reference's in-place roll + flip (flowtron.py:250-256, 266-270)."""
 
     def __init__(self, blank_logprob=-1):
         super().__init__()
@@ -541,18 +571,11 @@ class AttentionCTCLoss(nn.Module):
         self.blank_logprob = blank_logprob
         self.CTCLoss = nn.CTCLoss(zero_infinity=True)
 
-    def forward(self, attn, in_lens, out_lens, attn_logprob):
+    def forward(self, attn, in_lens, out_lens, attn_logprob, time_reversed=False):
         assert attn_logprob is not None
-        key_lens, query_lens = in_lens, out_lens
-        attn_logprob_padded = F.pad(input=attn_logprob, pad=(1, 0, 0, 0, 0, 0, 0, 0), value=self.blank_logprob)
-        cost_total = 0.0
-        for bid in range(attn_logprob.shape[0]):
-            target_seq = torch.arange(1, int(key_lens[bid]) + 1).unsqueeze(0)
-            curr_logprob = attn_logprob_padded[bid].permute(1, 0, 2)[:int(query_lens[bid]), :, :int(key_lens[bid]) + 1]
-            curr_logprob = self.log_softmax(curr_logprob[None])[0]
-            cost_total += self.CTCLoss(curr_logprob, target_seq, input_lengths=query_lens[bid:bid + 1],
-                                       target_lengths=key_lens[bid:bid + 1])
-        return cost_total / attn_logprob.shape[0]
+        lp = attn_logprob[:, 0] if attn_logprob.dim() == 4 else attn_logprob          # [B, 1, T, L] like the reference
+        cost = _AttnCtcFn.apply(lp, in_lens, out_lens, bool(time_reversed), float(self.blank_logprob))
+        return cost.sum() / lp.shape[0]
 
 
 class FlowtronLoss(nn.Module):
@@ -579,10 +602,10 @@ class FlowtronLoss(nn.Module):
         if self.use_ctc_loss:
             for cur_flow_idx, flow_attn in enumerate(attn_list):
                 cur = attn_logprob_list[cur_flow_idx]
-                if cur_flow_idx % 2 != 0:       # back steps return flipped time (flowtron.py:250-256): un-roll, un-flip
-                    cur = torch.stack([cur[k].roll(-int(out_lengths[k]), dims=0) for k in range(cur.size(0))])
-                    cur = torch.flip(cur, (1,))
+                # back steps return flipped time; the reference un-rolls / un-flips in place (flowtron.py:250-256) and
+                # restores afterwards (:266-270) -- here the kernel indexes the flipped tensor directly
                 loss_ctc = loss_ctc + self.attention_loss(flow_attn.unsqueeze(1), in_lengths, out_lengths,
-                                                          attn_logprob=cur.unsqueeze(1))
+                                                          attn_logprob=cur.unsqueeze(1),
+                                                          time_reversed=(cur_flow_idx % 2 != 0))
             loss_ctc = loss_ctc / float(len(attn_list))
         return loss, gate_loss, loss_ctc

@@ -11,9 +11,11 @@ def ar_step_infer(step, residual, text, attns, attn_prior=None, reversed_flag=Fa
     """residual [T,B,M], text [L,B,E] -> (total_output [T',B,M], [attention_weight [B,1,L]] * T').
 
     B == 1: T' is where the gate fired (the reference's `break`); B > 1: per-sample stop (rows emit zeros after
-    their own gate fires), T' = the longest row.  AR_Back_Step flips time on the way in and out (:629-642)."""
-    if attns is not None:
-        raise NotImplementedError("forced alignments (attns=...) are outside the B200 hot-path scope")
+    their own gate fires), T' = the longest row.  AR_Back_Step flips time on the way in and out (:629-642).
+
+    ``attns`` (forced alignments, flowtron.py:585-588, 797): frame i uses ``attns[i]`` instead of scoring -- a [T, L] tensor
+    (B == 1, the reference's ``attns[i][None, None]``), a [T, B, L] tensor, or the list of T per-frame weights this
+    function returns ([B, 1, L] each).  Like the reference, a back step consumes them in its own (flipped) time order."""
     if not residual.is_cuda:
         raise FlowtronB200Error("AR_Step.infer needs CUDA tensors: the sm_100a kernel is the only implementation")
     T, B, M = residual.shape
@@ -30,13 +32,21 @@ def ar_step_infer(step, residual, text, attns, attn_prior=None, reversed_flag=Fa
     has_gate = hasattr(step, 'gate_layer')
     desc = _lib.FtArStepDesc(T, B, L, M, step.lstm.hidden_size, step.attention_layer.query.linear_layer.out_features, E, 0,
                              int(has_gate), int(prior is not None), float(step.attention_layer.temperature))
+    forced = None
+    if attns is not None:
+        if isinstance(attns, (list, tuple)):
+            attns = torch.stack([a.reshape(B, L) for a in attns], 0)
+        forced = attns.detach().float().reshape(-1, B, L)
+        if forced.size(0) < T:
+            raise ValueError(f"attns covers {forced.size(0)} frames, residual has {T}")
+        forced = forced[:T].contiguous().to(dev)
     plist = [None if p is None else p.detach().contiguous() for p in step._param_list()]
     weights = _lib.make_weights(plist)
     out = torch.empty(T, B, M, device=dev)
     attn_out = torch.empty(T, B, L, device=dev)
     n_frames = torch.empty(B, dtype=torch.int32, device=dev)
     thr = float(getattr(step, 'gate_threshold', 0.5))
-    _lib.ar_step_infer(desc, weights, res, text.detach().float().contiguous(), prior, thr, out, attn_out, n_frames)
+    _lib.ar_step_infer(desc, weights, res, text.detach().float().contiguous(), prior, forced, thr, out, attn_out, n_frames)
     n = int(n_frames.max().item())                      # one host sync per flow (the reference syncs every frame)
     if has_gate and n < T:
         print("Hitting gate limit")

@@ -74,10 +74,14 @@ class _Flat:
         return buf[off: off + p.numel()].view_as(p)
 
     def install_grads(self):
-        """Point every .grad at the own flat buffer (keeps values of existing gradients)."""
+        """Point the .grad of every TRAINABLE parameter at the own flat buffer (keeps values of existing gradients).
+        Frozen parameters (requires_grad=False, train.py's finetune_layers) keep .grad = None, so step() skips them like
+        the reference does (radam.py:53-54): no weight decay, no step count."""
         if self.g is None:
             self.g = torch.zeros(self.total, dtype=torch.float32, device=self.p.device)
         for i, p in enumerate(self.params):
+            if not p.requires_grad:
+                continue
             gv = self.view(self.g, i)
             if p.grad is not None and p.grad.data_ptr() != gv.data_ptr():
                 gv.copy_(p.grad)
@@ -87,7 +91,24 @@ class _Flat:
         if self.g is None:
             return False
         base = self.g.data_ptr()
-        return all(p.grad is not None and p.grad.data_ptr() == base + 4 * off for p, off in zip(self.params, self.offsets))
+        return all((not p.requires_grad and p.grad is None) or (p.grad is not None and p.grad.data_ptr() == base + 4 * off)
+                   for p, off in zip(self.params, self.offsets))
+
+    def rehome(self):
+        """Re-attach parameters whose storage was moved out of the flat buffer after construction -- cuDNN's
+        ``nn.LSTM.flatten_parameters()`` (``param.set_``), ``module.to()`` / ``.half()`` -- which would otherwise make
+        step() update a dead copy while the live weights silently stop training.  The live values win."""
+        base, moved = self.p.data_ptr(), 0
+        for p, off in zip(self.params, self.offsets):
+            if p.data_ptr() != base + 4 * off:
+                if p.dtype != torch.float32 or p.device != self.p.device:
+                    raise FlowtronB200Error("flowtron_b200.RAdam: a parameter changed dtype/device after the optimizer was "
+                                            "built; rebuild the optimizer")
+                view = self.p[off: off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                moved += 1
+        return moved
 
 
 class RAdam(Optimizer):
@@ -105,7 +126,7 @@ class RAdam(Optimizer):
                     raise RuntimeError('RAdam does not support sparse gradients')      # radam.py:57-60
             _lib.lib()                                   # fail loudly now if the native library is missing
             flat = _Flat(ps)
-            if all(p.grad is None for p in ps):
+            if all(p.grad is None for p in ps) and any(p.requires_grad for p in ps):
                 flat.install_grads()
             self._flats.append(flat)
             for i, p in enumerate(ps):
@@ -113,6 +134,15 @@ class RAdam(Optimizer):
         self._partials = None
         self._norm_coef = None
         self._pending_coef = None
+        self._built = True
+
+    def add_param_group(self, param_group):
+        """Groups are fixed at construction (each owns flat buffers); adding one later would be silently ignored by
+        step(), so it is refused."""
+        if getattr(self, "_built", False):
+            raise FlowtronB200Error("flowtron_b200.RAdam: add_param_group after construction is not supported; "
+                                    "build a new optimizer with all groups")
+        super().add_param_group(param_group)
 
     @staticmethod
     def _require_cuda(p):
@@ -128,9 +158,13 @@ class RAdam(Optimizer):
         bucket laid out with the same flat_offsets); two gradients merge only if they are views of one base tensor or
         there is no padding between them, and the trailing padding of a run is never touched.  Cached on the tuple of
         (gradient pointer, step)."""
-        key = tuple((p.grad.data_ptr() if p.grad is not None else 0, self.state[p]['step']) for p in flat.params)
+        # the parameter pointer is part of the key: a parameter that left the flat buffer invalidates the cache and is
+        # re-homed before any kernel sees a stale pointer
+        key = tuple((p.grad.data_ptr() if p.grad is not None else 0, self.state[p]['step'], p.data_ptr()) for p in flat.params)
         if key == flat.seg_key:
             return flat.segs
+        if flat.rehome():
+            key = tuple((p.grad.data_ptr() if p.grad is not None else 0, self.state[p]['step'], p.data_ptr()) for p in flat.params)
         if flat.g is not None:                            # own gradient buffer no longer referenced (buckets took over): free it
             lo, hi = flat.g.data_ptr(), flat.g.data_ptr() + 4 * flat.total
             if not any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in flat.params):
@@ -221,7 +255,7 @@ class RAdam(Optimizer):
                 if p.grad is not None:
                     self.state[p]['step'] += 1
             if flat.seg_key is not None:                 # keep the cache valid across the uniform step increment
-                flat.seg_key = tuple((gp, s + 1 if gp else s) for gp, s in flat.seg_key)
+                flat.seg_key = tuple((gp, s + 1 if gp else s, pp) for gp, s, pp in flat.seg_key)
                 flat.segs = [(o, gp, n, s + 1) for o, gp, n, s in flat.segs]
         self._pending_coef = None
         return loss

@@ -147,15 +147,17 @@ int ft_radam_step(float* p, const float* g, float* m, float* v, long long n, dou
 
 /* AR_Step.infer (flowtron.py:775-828): sequential inverse of one flow for all T frames in ONE persistent launch.
  *   residual [T,B,M] f32 in flow-time order (the caller flips for AR_Back_Step, :629-642), text [L,B,E] f32,
- *   attn_prior [B,T,L] or NULL (row i is used at frame i).  Uses d->T/B/L/n_*, has_gate, has_prior, temperature.
+ *   attn_prior [B,T,L] or NULL (row i is used at frame i); attn_forced [T,B,L] or NULL: forced alignments (the `attns`
+ *   argument, flowtron.py:585-588, 797: scoring, softmax and the prior are skipped, context = attn_forced[i] . V).
+ *   Uses d->T/B/L/n_*, has_gate, has_prior, temperature.
  *   out [T,B,M]: generated frames (zeros after a sample's gate fired; the frame that trips the gate is emitted),
  *   attn_out [T,B,L]: per-frame attention weights, n_frames [B] int32: frames emitted per sample.
  *   With B == 1 this is exactly the reference's loop-with-break; B > 1 with a gate is the per-sample-stop
  *   extension (the reference raises there). */
 size_t ft_ar_step_infer_scratch_bytes(const FtArStepDesc* d);
 int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const float* residual, const float* text,
-                     const float* attn_prior, float gate_threshold, float* out, float* attn_out, int* n_frames,
-                     void* scratch, void* stream);
+                     const float* attn_prior, const float* attn_forced, float gate_threshold, float* out, float* attn_out,
+                     int* n_frames, void* scratch, void* stream);
 
 /* TacotronSTFT.mel_spectrogram (audio_processing.py:117-134) for a ragged batch.  wav: concatenated utterances
  * (f32 in [-1,1]); sample_offsets / frame_offsets: device int64 [n_utt+1] prefix sums (frames of utterance u =
@@ -167,6 +169,42 @@ int ft_mel_spectrogram(const float* wav, const long long* sample_offsets, const 
                        long long total_frames, const float* window, const float* mel_basis, const int* band_lo,
                        const int* band_hi, int n_mel, int n_fft, int hop, float clip, float* mel_out, void* scratch,
                        long long chunk_frames, void* stream);
+
+/* Fused form for n_fft == 1024 (the shipped configuration, config.json:31-33): ONE kernel -- reflect pad + window on the
+ * load, a 1024-point real FFT per warp in shared memory, |X|, sparse filterbank, log -- reads the waveform once and writes
+ * the mel once (no frames / spectrum round trip, no scratch).  wav_fmt: 0 = f32 in [-1,1], 1 = int16 PCM scaled by
+ * 1/32768 on load (data.py:150 `audio / max_wav_value`).  Same output layout as ft_mel_spectrogram. */
+int ft_mel_spectrogram_fused(const void* wav, int wav_fmt, const long long* sample_offsets, const long long* frame_offsets,
+                             int n_utt, long long total_frames, const float* window, const float* mel_basis, const int* band_lo,
+                             const int* band_hi, int n_mel, int n_fft, int hop, float clip, float* mel_out, void* stream);
+
+/* STFT.transform (audio_processing.py:207-235), n_fft == 1024: magnitude and phase (atan2(imag, real)) as per-utterance
+ * [n_fft/2+1, F_u] blocks (== [B, 513, F] for equal lengths), same kernel as above without the filterbank. */
+int ft_stft_transform(const float* wav, const long long* sample_offsets, const long long* frame_offsets, int n_utt,
+                      long long total_frames, const float* window, int n_fft, int hop, float* magnitude, float* phase,
+                      void* stream);
+
+/* Data layer on the device.
+ * ft_attn_prior: beta_binomial_prior_distribution (data.py:31-41) for a whole batch directly in DataCollate's zero-padded
+ *   [B,T,L] layout (data.py:222-243): prior[b,i-1,k] = BetaBinomial(k; n=in_lens[b]-1, a=s*i, b=s*(out_lens[b]+1-i)) for
+ *   i <= out_lens[b], k < in_lens[b], else 0; values < threshold are zeroed when threshold > 0 (data.py:137-139).
+ *   fp64 log-gamma evaluation, fp32 output.
+ * ft_collate_mel: DataCollate's mel / gate padding (data.py:214-236) from ft_mel_spectrogram's packed output: row i of
+ *   mel_padded [B,n_mel,T] is utterance order[i]; gate_padded [B,T] = 1 from its last frame on; out_lens[i] = its frames. */
+int ft_attn_prior(const int* in_lens, const int* out_lens, int B, int T, int L, float scaling, float threshold, float* prior,
+                  void* stream);
+int ft_collate_mel(const float* mel_packed, const long long* frame_offsets, const int* order, int B, int n_mel, int T,
+                   float* mel_padded, float* gate_padded, int* out_lens, void* stream);
+
+/* AttentionCTCLoss (flowtron.py:155-182) for a whole batch, with its gradient, in one launch (the
+ * reference loops over utterances in Python).  attn_logprob [B,T,L] f32 of ONE flow; classes = blank (constant logit
+ * blank_logprob) + the utterance's in_lens[b] tokens, log_softmax over them, CTC against the target 1..in_lens[b] over
+ * out_lens[b] frames, reduction 'mean' (nll / in_lens[b]), zero_infinity.  time_reversed = 1: the tensor is in an
+ * AR_Back_Step's flipped time (flowtron.py:250-256).  cost [B]; d_attn_logprob [B,T,L] = d cost[b] / d attn_logprob (zeros
+ * outside the utterance's frames / tokens).  scratch: ft_attn_ctc_scratch_bytes(B, T, L). */
+size_t ft_attn_ctc_scratch_bytes(int B, int T, int L);
+int ft_attn_ctc_loss(const float* attn_logprob, const int* in_lens, const int* out_lens, int B, int T, int L, int time_reversed,
+                     float blank_logprob, float* cost, float* d_attn_logprob, void* scratch, void* stream);
 
 #ifdef __cplusplus
 }

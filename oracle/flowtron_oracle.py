@@ -239,12 +239,13 @@ def ar_step_infer(p: Params, pre: str, residual: Tensor, text: Tensor, temperatu
 
 
 def ar_back_step_infer(p, pre, residual, text, temperature=1.0, gate_threshold=0.5, attn_prior=None,
-                       per_sample_stop=False):
-    """AR_Back_Step.infer, flowtron.py:629-642: flip in time, run, flip back (no roll)."""
+                       per_sample_stop=False, attns=None):
+    """AR_Back_Step.infer, flowtron.py:629-642: flip in time, run, flip back (no roll); `attns` is passed through
+    unflipped (:634-635), i.e. consumed in the back step's own time order."""
     if attn_prior is not None:
         attn_prior = torch.flip(attn_prior, (1,))
     out, attns = ar_step_infer(p, f"{pre}.ar_step", torch.flip(residual, (0,)), text, temperature,
-                               gate_threshold, attn_prior, per_sample_stop=per_sample_stop)
+                               gate_threshold, attn_prior, attns=attns, per_sample_stop=per_sample_stop)
     return torch.flip(out, (0,)), attns
 
 
@@ -330,8 +331,9 @@ def flowtron_forward(p: Params, mel: Tensor, speaker_ids: Tensor, text: Tensor, 
 
 def flowtron_infer(p: Params, residual: Tensor, speaker_ids: Tensor, text: Tensor,
                    temperature: float = 1.0, gate_threshold: float = 0.5,
-                   per_sample_stop: bool = False):
-    """Flowtron.infer, flowtron.py:901-930."""
+                   per_sample_stop: bool = False, attns=None):
+    """Flowtron.infer, flowtron.py:901-930.  `attns`: per-flow forced alignments [T,L] indexed by flow (the reference's
+    `reversed(attns)[i]` at :924 is not subscriptable; the evident intent -- flow k gets attns[k] -- is restated)."""
     spk = F.embedding(speaker_ids, p["speaker_embedding.weight"])
     t = F.embedding(text, p["embedding.weight"]).transpose(1, 2)
     t = encoder_forward(p, t, None, infer=True).transpose(0, 1)
@@ -339,12 +341,13 @@ def flowtron_infer(p: Params, residual: Tensor, speaker_ids: Tensor, text: Tenso
     residual = residual.permute(2, 0, 1)
     attn_all = []
     for i in reversed(range(n_flows_of(p))):
+        forced = None if attns is None else attns[i]
         if i % 2 == 0:
             residual, a = ar_step_infer(p, flow_prefix(i), residual, enc, temperature, gate_threshold,
-                                        per_sample_stop=per_sample_stop)
+                                        attns=forced, per_sample_stop=per_sample_stop)
         else:
             residual, a = ar_back_step_infer(p, flow_prefix(i), residual, enc, temperature,
-                                             gate_threshold, per_sample_stop=per_sample_stop)
+                                             gate_threshold, per_sample_stop=per_sample_stop, attns=forced)
         attn_all.append(a)
     return residual.permute(1, 2, 0), attn_all
 
@@ -364,6 +367,34 @@ def flowtron_loss(model_output, gate_target: Tensor, in_lens: Tensor, out_lens: 
         gl = F.binary_cross_entropy_with_logits(gp, gate_target, reduction="none")
         gl = (gl.permute(1, 0) * mask[:, :, 0]).sum() / n
     return nll, gl
+
+
+def attention_ctc_loss(attn_logprob: Tensor, in_lens: Tensor, out_lens: Tensor, blank_logprob: float = -1.0) -> Tensor:
+    """AttentionCTCLoss.forward, flowtron.py:162-182: attn_logprob [B,T,L] (natural time) -> scalar."""
+    padded = F.pad(attn_logprob[:, None], (1, 0, 0, 0, 0, 0, 0, 0), value=blank_logprob)     # blank column in front, :166-168
+    ctc = torch.nn.CTCLoss(zero_infinity=True)
+    total = 0.0
+    for b in range(attn_logprob.shape[0]):
+        K, Tq = int(in_lens[b]), int(out_lens[b])
+        cur = padded[b].permute(1, 0, 2)[:Tq, :, :K + 1]                                    # :172-175
+        cur = torch.log_softmax(cur[None], dim=3)[0]
+        total = total + ctc(cur, torch.arange(1, K + 1)[None], input_lengths=torch.tensor([Tq]),
+                            target_lengths=torch.tensor([K]))
+    return total / attn_logprob.shape[0]
+
+
+def flowtron_ctc_loss(model_output, in_lens: Tensor, out_lens: Tensor, blank_logprob: float = -1.0) -> Tensor:
+    """The use_ctc_loss branch of FlowtronLoss.forward, flowtron.py:245-274: back-step flows are un-rolled and
+    un-flipped to natural time first (index map instead of the reference's in-place roll/flip/restore)."""
+    lps = model_output[4]
+    T = lps[0].shape[1]
+    total = 0.0
+    for i, lp in enumerate(lps):
+        if i % 2 != 0:
+            idx = back_step_index(out_lens, T)                        # [T, B]: natural t -> flow-time row
+            lp = torch.stack([lp[b][idx[:, b]] for b in range(lp.shape[0])])
+        total = total + attention_ctc_loss(lp, in_lens, out_lens, blank_logprob)
+    return total / float(len(lps))
 
 
 # --------------------------------------------------------------------------- attention prior

@@ -1,8 +1,7 @@
-"""Import the UNMODIFIED reference modules from /root/reference on CPU (build container only).
-
-Used by tests/make_golden.py to generate fixtures and by tests marked ``needs_reference``.
-/root/reference does not exist on the GPU box: nothing in ``-m gpu`` tests, smoke() or bench.py
-may call this.  Shims:
+"""Import the UNMODIFIED reference modules on CPU: from /root/reference in the build container (used by
+tests/make_golden.py to generate fixtures and by tests marked ``needs_reference``), or from their byte-compiled staging
+in oracle/_ref/ (oracle/build_ref.py) on the GPU box, where ONLY bench.py's reference arm / cpu_baseline leg may use it
+(nothing in ``-m gpu`` tests or smoke() reads the reference).  Shims:
   1. flowtron.get_mask_from_lengths hard-codes torch.cuda.LongTensor (flowtron.py:48) -> arange version;
   2. AR_Step.infer allocates torch.cuda.FloatTensor (flowtron.py:785) -> alias to torch.FloatTensor;
   3. audio_processing imports librosa (absent here) -> stub providing filters.mel / util.pad_center /
@@ -17,11 +16,21 @@ import types
 import numpy as np
 import torch
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("FLOWTRON_REFERENCE", "/root/reference")
+if not os.path.isfile(os.path.join(REF, "flowtron.py")):
+    # GPU box: the byte-compiled reference modules staged by oracle/build_ref.py (bench.py's reference arm only)
+    REF = os.path.join(_HERE, "_ref")
 
 
 def available() -> bool:
+    """The reference tree itself (build container): fixtures may only be generated from this."""
     return os.path.isfile(os.path.join(REF, "flowtron.py"))
+
+
+def runnable() -> bool:
+    """The reference modules can be imported: the tree, or its byte-compiled staging in oracle/_ref/."""
+    return available() or os.path.isfile(os.path.join(REF, "flowtron.pyc"))
 
 
 def import_flowtron():

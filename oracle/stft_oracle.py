@@ -93,3 +93,13 @@ def mel_spectrogram(y: torch.Tensor, filter_length=1024, hop_length=256, win_len
         mel_basis = slaney_mel_basis(sampling_rate, filter_length, n_mel_channels, mel_fmin, mel_fmax)
     mel = torch.matmul(torch.from_numpy(mel_basis), mag)               # :132
     return torch.log(torch.clamp(mel, min=1e-5))                       # :84
+
+
+def stft_transform(y: torch.Tensor, filter_length=1024, hop_length=256, win_length=1024):
+    """STFT.transform (audio_processing.py:207-235): y [B,N] -> (magnitude, phase) each [B, N/2+1, 1+N//hop]."""
+    basis = torch.from_numpy(forward_basis(filter_length, win_length))[:, None, :]
+    x = F.pad(y[:, None, None, :], (filter_length // 2, filter_length // 2, 0, 0), mode="reflect")[:, 0]
+    ft = F.conv1d(x, basis, stride=hop_length)
+    cutoff = filter_length // 2 + 1
+    re, im = ft[:, :cutoff], ft[:, cutoff:]
+    return torch.sqrt(re ** 2 + im ** 2), torch.atan2(im, re)

@@ -21,3 +21,16 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords and not has_gpu:
             item.add_marker(pytest.mark.skip(reason="no CUDA device"))
+
+
+def record_parity(test: str, values: dict) -> None:
+    """Append the measured parity errors of a GPU test to gpurun_out/parity.jsonl (scratch, merged back by gpurun) so the
+    numbers behind a green run can be committed under profiles/."""
+    import json
+    d = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, os.environ.get("FT_PARITY_LOG", "parity.jsonl")), "a") as f:
+            f.write(json.dumps({"test": test, **{k: (float(v) if isinstance(v, (int, float)) else v) for k, v in values.items()}}) + "\n")
+    except OSError:
+        pass

@@ -30,12 +30,14 @@ def grad_sample_index(name: str, numel: int) -> np.ndarray:
     return torch.randint(0, numel, (N_GRAD_SAMPLES,), generator=g).numpy()
 
 
-def train_case(tag, n_flows, B, T, L, out_lens, with_prior, seed):
+def train_case(tag, n_flows, B, T, L, out_lens, with_prior, seed, in_lens=None, logmel_stats=False, store_attn=True,
+               ctc_weight=0.0):
     cfg = dict(synth.DEFAULT_MODEL_CONFIG, n_flows=n_flows)
     params = synth.synth_params(cfg, seed)
     F, model = ref_shims.reference_model(cfg, params)
-    batch = synth.synth_batch(B, T, L, cfg, seed, out_lens=out_lens, with_prior=with_prior)
-    crit = F.FlowtronLoss(sigma=1.0, gm_loss=False, gate_loss=True, use_ctc_loss=False)
+    batch = synth.synth_batch(B, T, L, cfg, seed, out_lens=out_lens, in_lens=in_lens, with_prior=with_prior,
+                              logmel_stats=logmel_stats)
+    crit = F.FlowtronLoss(sigma=1.0, gm_loss=False, gate_loss=True, use_ctc_loss=ctc_weight > 0, ctc_loss_weight=ctc_weight)
     for p in model.parameters():
         p.requires_grad_(True)
     # Encoder dropout (flowtron.py:502) is random in train mode, and in eval mode F.dropout returns
@@ -45,16 +47,19 @@ def train_case(tag, n_flows, B, T, L, out_lens, with_prior, seed):
     out = model(batch["mel"], batch["speaker_ids"], batch["text"], batch["in_lens"], batch["out_lens"],
                 batch["attn_prior"])
     z, log_s_list, gate, attns, lps = out[:5]
-    nll, gl, _ = crit(out, batch["gate_target"], batch["in_lens"], batch["out_lens"])
-    (nll + gl).sum().backward()
-    rec = dict(cfg_n_flows=n_flows, B=B, T=T, L=L, seed=seed, with_prior=int(with_prior),
+    nll, gl, ctc = crit(out, batch["gate_target"], batch["in_lens"], batch["out_lens"])
+    (nll + gl + ctc * ctc_weight).sum().backward()        # train.py:301-304
+    rec = dict(ctc_weight=np.float32(ctc_weight), loss_ctc=ctc.detach().numpy(),cfg_n_flows=n_flows, B=B, T=T, L=L, seed=seed, with_prior=int(with_prior), logmel_stats=int(logmel_stats),
                out_lens=batch["out_lens"].numpy(), in_lens=batch["in_lens"].numpy(),
                z=z.detach().numpy(), gate=gate.detach().numpy(),
                nll=nll.detach().numpy(), gate_loss=gl.detach().numpy())
     for i in range(n_flows):
         rec[f"log_s_{i}"] = log_s_list[i].detach().numpy()
-        rec[f"attn_{i}"] = attns[i].detach().numpy()
-        rec[f"attn_logprob_{i}"] = lps[i].detach().numpy()
+        if store_attn:
+            rec[f"attn_{i}"] = attns[i].detach().numpy()
+            rec[f"attn_logprob_{i}"] = lps[i].detach().numpy()
+        else:                                   # BASELINE-size cases: keep the fixture to a few MB (one utterance's attention)
+            rec[f"attn_{i}_b0"] = attns[i][0].detach().numpy()
     for name, p in model.named_parameters():
         gflat = p.grad.detach().reshape(-1)
         rec[f"gnorm::{name}"] = np.float64(gflat.double().norm().item())
@@ -133,6 +138,16 @@ def radam_case():
     print("radam: 9 steps recorded")
 
 
+def big_cases():
+    """BASELINE-shape fixtures: a T=1000 training step (cfg 2 shapes at the largest B the CPU reference
+    finishes in minutes) and cfg-4 inference requests (T=400 default, T=1000), all 2-flow."""
+    train_case("t1000", n_flows=2, B=4, T=1000, L=150, out_lens=[1000, 873, 640, 512], in_lens=[150, 134, 98, 79],
+               with_prior=True, seed=2024, logmel_stats=True, store_attn=False)
+    infer_case("b1_t400", n_flows=2, B=1, T=400, L=100, seed=11, gate_bias=-10.0)
+    infer_case("b1_t1000", n_flows=2, B=1, T=1000, L=100, seed=12, gate_bias=-10.0)
+    infer_case("b4nogate_t400", n_flows=2, B=4, T=400, L=100, seed=13, gate_bias=0.0, use_gate=False)
+
+
 def main():
     assert ref_shims.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -141,15 +156,25 @@ def main():
     train_case("cfg1", n_flows=1, B=2, T=128, L=32, out_lens=[128, 100], with_prior=False, seed=1234)
     train_case("f2prior", n_flows=2, B=3, T=96, L=24, out_lens=[96, 61, 80], with_prior=True, seed=4321)
     train_case("f2ragged", n_flows=2, B=5, T=64, L=20, out_lens=[64, 1, 33, 64, 17], with_prior=False, seed=99)
+    train_case("f2ctc", n_flows=2, B=3, T=80, L=20, out_lens=[80, 47, 66], with_prior=True, seed=777, ctc_weight=1.0)
     infer_case("b1", n_flows=2, B=1, T=48, L=20, seed=5, gate_bias=-10.0)
     infer_case("b1gate", n_flows=2, B=1, T=48, L=20, seed=6, gate_bias=0.25)
     infer_case("b4nogate", n_flows=2, B=4, T=32, L=16, seed=8, gate_bias=0.0, use_gate=False)
     mel_case()
     radam_case()
+    big_cases()
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "radam":     # regenerate only the optimizer fixture
         radam_case()
+    elif len(sys.argv) > 1 and sys.argv[1] == "ctc":     # only the CTC-loss fixture
+        torch.manual_seed(0)
+        torch.set_num_threads(8)
+        train_case("f2ctc", n_flows=2, B=3, T=80, L=20, out_lens=[80, 47, 66], with_prior=True, seed=777, ctc_weight=1.0)
+    elif len(sys.argv) > 1 and sys.argv[1] == "big":     # only the BASELINE-shape fixtures (minutes of CPU time)
+        torch.manual_seed(0)
+        torch.set_num_threads(8)
+        big_cases()
     else:
         main()

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN
+from conftest import GOLDEN, record_parity
 from oracle import synth
 
 pytestmark = pytest.mark.gpu
@@ -76,6 +76,7 @@ def test_forward_loss_backward_match_reference_goldens(tag):
     errs["nll"] = abs(float(nll) - float(gold["nll"])) / abs(float(gold["nll"]))
     errs["gate_loss"] = abs(float(gl) - float(gold["gate_loss"])) / abs(float(gold["gate_loss"]))
     print("forward errors:", {k: f"{v:.2e}" for k, v in errs.items()})
+    record_parity(f"train_{tag}_forward", errs)
     bad = {k: v for k, v in errs.items() if not v <= 1e-3}
     assert not bad, bad
 
@@ -103,6 +104,8 @@ def test_forward_loss_backward_match_reference_goldens(tag):
         if not (e_norm <= 1e-2 and rel_l2 <= 4e-2 and cos >= 0.999):   # tightened once the fp16-scaled backward landed
             bad[name] = (e_norm, rel_l2, cos)
     rows.sort(key=lambda x: -x[2])
+    record_parity(f"train_{tag}_grads", {"norm_err_worst": max(r[1] for r in rows), "rel_l2_worst": max(r[2] for r in rows),
+                                         "cos_worst": min(r[3] for r in rows), "worst_tensor": rows[0][0]})
     print("worst grads (name, norm err, rel L2, cosine):", [(n, f"{a:.1e}", f"{b:.1e}", f"{c:.5f}") for n, a, b, c in rows[:8]])
     assert not bad, bad
 

@@ -69,7 +69,53 @@ def test_train_forward_loss_grads_match_reference(tag):
         assert (samp - ref).abs().max().item() <= 2e-3 * (ref.abs().max().item() + gn / np.sqrt(g.numel())) + 1e-8, name
 
 
-@pytest.mark.parametrize("tag", ["b1", "b1gate", "b4nogate"])
+def test_train_forward_matches_reference_at_baseline_shape():
+    """cfg-2 shape (T=1000, L=150, prior on, log-mel statistics): oracle forward + losses vs the reference fixture."""
+    gold = _load("train_t1000.npz")
+    n_flows, B, T, L = (int(gold[k]) for k in ("cfg_n_flows", "B", "T", "L"))
+    cfg = dict(synth.DEFAULT_MODEL_CONFIG, n_flows=n_flows)
+    p = synth.synth_params(cfg, int(gold["seed"]))
+    batch = synth.synth_batch(B, T, L, cfg, int(gold["seed"]), out_lens=[1000, 873, 640, 512], in_lens=[150, 134, 98, 79],
+                              with_prior=True, logmel_stats=True)
+    assert np.array_equal(batch["out_lens"].numpy(), gold["out_lens"]) and np.array_equal(batch["in_lens"].numpy(), gold["in_lens"])
+    with torch.no_grad():
+        out = O.flowtron_forward(p, batch["mel"], batch["speaker_ids"], batch["text"], batch["in_lens"], batch["out_lens"],
+                                 batch["attn_prior"], fast=True)
+        nll, gl = O.flowtron_loss(out, batch["gate_target"], batch["in_lens"], batch["out_lens"])
+    vm = _valid_mask_T(batch["out_lens"], T)
+    for name, a, b in [("z", out[0], gold["z"]), ("gate", out[2], gold["gate"]), ("log_s_0", out[1][0], gold["log_s_0"]),
+                       ("log_s_1", out[1][1], gold["log_s_1"])]:
+        b = torch.from_numpy(b)
+        err = (a[vm] - b[vm]).abs().max().item() / max(1.0, b[vm].abs().max().item())
+        assert err <= 5e-5, (name, err)
+    for i in range(n_flows):
+        n0 = int(batch["out_lens"][0])
+        assert (out[3][i][0, :n0] - torch.from_numpy(gold[f"attn_{i}_b0"])[:n0]).abs().max().item() <= 5e-5
+    assert abs(float(nll) - float(gold["nll"])) < 1e-4 * abs(float(gold["nll"]))
+    assert abs(float(gl) - float(gold["gate_loss"])) < 1e-4
+
+
+def test_ctc_branch_matches_reference():
+    """FlowtronLoss with use_ctc_loss (flowtron.py:245-274, 155-182): oracle loss_ctc and the gradients of
+    nll + gate + ctc vs the reference fixture (2 flows: one forward, one back step; prior on)."""
+    gold = _load("train_f2ctc.npz")
+    n_flows, B, T, L = (int(gold[k]) for k in ("cfg_n_flows", "B", "T", "L"))
+    cfg = dict(synth.DEFAULT_MODEL_CONFIG, n_flows=n_flows)
+    p = {k: v.requires_grad_(True) for k, v in synth.synth_params(cfg, int(gold["seed"])).items()}
+    batch = synth.synth_batch(B, T, L, cfg, int(gold["seed"]), out_lens=[80, 47, 66], with_prior=True)
+    out = O.flowtron_forward(p, batch["mel"], batch["speaker_ids"], batch["text"], batch["in_lens"], batch["out_lens"],
+                             batch["attn_prior"])
+    nll, gl = O.flowtron_loss(out, batch["gate_target"], batch["in_lens"], batch["out_lens"])
+    ctc = O.flowtron_ctc_loss(out, batch["in_lens"], batch["out_lens"])
+    assert abs(float(ctc.detach()) - float(gold["loss_ctc"])) <= 1e-5 * abs(float(gold["loss_ctc"]))
+    (nll + gl + float(gold["ctc_weight"]) * ctc).sum().backward()
+    for name, t in p.items():
+        g = t.grad.reshape(-1)
+        gn = float(gold[f"gnorm::{name}"])
+        assert abs(float(g.double().norm()) - gn) <= 2e-3 * gn + 1e-7, name
+
+
+@pytest.mark.parametrize("tag", ["b1", "b1gate", "b4nogate", "b1_t400", "b4nogate_t400"])
 def test_infer_matches_reference(tag):
     gold = _load(f"infer_{tag}.npz")
     cfg = dict(synth.DEFAULT_MODEL_CONFIG, n_flows=int(gold["cfg_n_flows"]), use_gate_layer=bool(gold["use_gate"]))
