@@ -275,9 +275,11 @@ def ar_step_bwd(desc, weights, mel, in_lens, out_lens, attn, d_mel_out, d_log_s,
                                ptr(d_text), byref(grads), ptr(saved), ptr(scratch), stream_ptr()), "ft_ar_step_bwd")
 
 
-def nll_reduce(z, log_s_ptrs, n_flows, gate, gate_target, out_lens, sums):
+def nll_reduce(z, log_s_list, gate, gate_target, out_lens, sums):
+    """log_s_list: list of f32 CUDA tensors [T,B,M] (one per flow); their pointers travel as a host array."""
     T, B, M = z.shape
-    check(lib().ft_nll_reduce(ptr(z), ptr(log_s_ptrs), n_flows, ptr(gate), ptr(gate_target), ptr(out_lens), T, B, M,
+    arr = (c_void_p * len(log_s_list))(*[t.data_ptr() for t in log_s_list])
+    check(lib().ft_nll_reduce(ptr(z), arr, len(log_s_list), ptr(gate), ptr(gate_target), ptr(out_lens), T, B, M,
                               ptr(sums), stream_ptr()), "ft_nll_reduce")
 
 

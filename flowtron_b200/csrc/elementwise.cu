@@ -374,7 +374,9 @@ int launch_colsum(const void* src, int fmt, long long ld, long long R, int C, fl
 // ------------------------------------------------------------------------------------------------ loss reductions
 // FlowtronLoss default branch (flowtron.py:205-243).  sums[0] = sum (z*m)^2, sums[1] = sum_flows sum log_s*m,
 // sums[2] = sum m * BCEWithLogits(gate*m, target), sums[3] = n = sum m.   z/log_s: [T,B,M]; gate [T,B]; target [B,T].
-__global__ void nll_reduce_kernel(const float* __restrict__ z, const float* const* __restrict__ log_s_list, int n_flows,
+constexpr int NLL_MAX_FLOWS = 16;
+struct LogSList { const float* p[NLL_MAX_FLOWS]; };      // passed BY VALUE: no device-side pointer table, nothing to upload
+__global__ void nll_reduce_kernel(const float* __restrict__ z, const LogSList log_s_list, int n_flows,
                                   const float* __restrict__ gate, const float* __restrict__ gate_target,
                                   const int* __restrict__ lens, int T, int B, int M, float* __restrict__ sums) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -387,7 +389,7 @@ __global__ void nll_reduce_kernel(const float* __restrict__ z, const float* cons
         if (t < lens[b]) {
             const float zz = z[i];
             a0 = fmaf(zz, zz, a0);
-            for (int f = 0; f < n_flows; ++f) a1 += log_s_list[f][i];
+            for (int f = 0; f < n_flows; ++f) a1 += log_s_list.p[f][i];
             if (m == 0) {
                 a3 += 1.f;
                 if (gate) {
@@ -416,11 +418,14 @@ __global__ void nll_reduce_kernel(const float* __restrict__ z, const float* cons
         }
     }
 }
-int launch_nll_reduce(const float* z, const float* const* log_s_list_dev, int n_flows, const float* gate,
+int launch_nll_reduce(const float* z, const float* const* log_s_list_host, int n_flows, const float* gate,
                       const float* gate_target, const int* lens, int T, int B, int M, float* sums, cudaStream_t st) {
+    if (n_flows < 0 || n_flows > NLL_MAX_FLOWS) return ft_set_error("nll_reduce: more than 16 flows not supported");
     if (cudaMemsetAsync(sums, 0, sizeof(float) * 4, st) != cudaSuccess) return ft_set_error("nll: memset failed");
+    LogSList ls;
+    for (int f = 0; f < NLL_MAX_FLOWS; ++f) ls.p[f] = f < n_flows ? log_s_list_host[f] : nullptr;
     const long long n = static_cast<long long>(T) * B * M;
-    nll_reduce_kernel<<<grid_for(n, 256, 4), 256, 0, st>>>(z, log_s_list_dev, n_flows, gate, gate_target, lens, T, B, M, sums);
+    nll_reduce_kernel<<<grid_for(n, 256, 4), 256, 0, st>>>(z, ls, n_flows, gate, gate_target, lens, T, B, M, sums);
     ft_count_launch(1);
     return ft_check_launch("nll_reduce_kernel");
 }

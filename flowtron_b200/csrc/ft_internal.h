@@ -66,7 +66,7 @@ int launch_affine_bwd(const float* dz, const float* dlog_s_ext, const float* o, 
 int launch_combine_dmel(const float* dmel_flow, const float* dmel_in, const int* lens, int T, int B, int M, int reversed,
                         float* dmel, const float* inv_scale, cudaStream_t st);
 int launch_colsum(const void* src, int fmt, long long ld, long long R, int C, float* out, const float* out_scale, cudaStream_t st);
-int launch_nll_reduce(const float* z, const float* const* log_s_list_dev, int n_flows, const float* gate,
+int launch_nll_reduce(const float* z, const float* const* log_s_list_host, int n_flows, const float* gate,
                       const float* gate_target, const int* lens, int T, int B, int M, float* sums, cudaStream_t st);
 int launch_nll_grad(const float* z, const float* gate, const float* gate_target, const int* lens, int T, int B, int M,
                     float sigma, const float* sums, const float* g_nll, const float* g_gate, float* dz, float* dlog_s,

@@ -67,211 +67,6 @@ struct LstmFwdParams {
     long long* trace;          // optional [T][8] clock64 stamps of CTA 0 (debug/profiling), or null
 };
 
-template <int FWD_GS, int FWD_UNITS>
-__global__ void __launch_bounds__(LSTM_THREADS, 1)
-lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, LstmFwdParams p) {
-    constexpr int FWD_NG = FWD_NCH / FWD_GS;                     // TMA groups per step
-    constexpr int FWD_N = 4 * FWD_UNITS, FWD_W_BYTES = FWD_NCH * FWD_N * 128, FWD_PROD = KCH / FWD_UNITS;
-    constexpr int AP = FWD_N + 1;                                // accumulator staging pitch
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int slot_bytes = p.Bbox * 128;
-    uint8_t* sA = smem;                                          // [16 chunks][Bbox rows][128 B]
-    uint8_t* sW = smem + FWD_NCH * slot_bytes;                   // the M=128 over-read of the last chunks lands here
-    float* sAcc = reinterpret_cast<float*>(sW + FWD_W_BYTES);    // [32 * nq rows][AP]
-    const int nq = (p.B + 31) / 32;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + ((nq * 32 * AP + 1) & ~1));
-    uint64_t* full = bars;                       // [FWD_NG] (<= 16)
-    uint64_t* wbar = bars + 16;
-    uint64_t* accum_full = bars + 17;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cta = blockIdx.x;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmW);
-        tma_prefetch_desc(&tmH);
-        for (int g = 0; g < FWD_NG; ++g) mbar_init(&full[g], 1);
-        mbar_init(wbar, 1);
-        mbar_init(accum_full, 1);
-        fence_mbar_init();
-    }
-    if (warp == 1) tmem_alloc<(FWD_N < 32 ? 32 : FWD_N)>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // resident W_hh slice: chunk kc, gate g -> FWD_UNITS rows x 128 B
-            mbar_expect_tx(wbar, FWD_W_BYTES);
-            for (int kc = 0; kc < FWD_NCH; ++kc)
-                for (int g = 0; g < 4; ++g)
-                    tma_load_2d(sW + kc * (FWD_N * 128) + g * (FWD_UNITS * 128), &tmW, wbar, kc * KCH, g * LH + FWD_UNITS * cta);
-        }
-        for (int t = 1; t < p.T; ++t) {
-            // the 16 chunk counters of step t-1 (FWD_PROD producer CTAs each) are polled in parallel, one lane each.
-            // Seeing them all also proves this CTA's own step t-1 retired (its release is among them), so the A
-            // buffer is free: no empty-slot barrier is needed.
-            if (lane < FWD_NCH) wait_flag_ge(&p.flags[(t - 1) * FWD_NCH + lane], FWD_PROD, p.status, 202);
-            __syncwarp();
-            if (elect_one()) {
-                FT_TRACE(p, t, 0);
-                fence_proxy_async_global();        // generic-proxy writes of other SMs -> async-proxy (TMA) reads
-                FT_TRACE(p, t, 6);
-#pragma unroll
-                for (int g = 0; g < FWD_NG; ++g) {
-                    mbar_expect_tx(&full[g], FWD_GS * slot_bytes);
-                    tma_load_3d(sA + g * FWD_GS * slot_bytes, &tmH, &full[g], 0, (t - 1) * p.B, g * FWD_GS);
-                }
-                FT_TRACE(p, t, 1);
-            }
-            __syncwarp();
-        }
-    } else if (warp == 1) {
-        // warp-uniform loop, one elected lane issues (see gemm.cu: descriptors must be uniform-register operands)
-        mbar_wait(wbar, 0, p.status, 203);
-        const uint32_t idesc = umma_idesc(128, FWD_N, FMT_F16, FMT_F16, 0, 0);
-        const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
-        const uint64_t da_base = umma_smem_desc(smem_u32(sA), 16, 1024), db_base = umma_smem_desc(smem_u32(sW), 16, 1024);
-        const uint64_t a_chunk = static_cast<uint64_t>(slot_bytes >> 4), b_chunk = (FWD_N * 128) >> 4;
-        for (int t = 1; t < p.T; ++t) {
-            const int ph = (t - 1) & 1;
-            uint64_t da = da_base, db = db_base;
-#pragma unroll
-            for (int g = 0; g < FWD_NG; ++g) {
-                mbar_wait(&full[g], ph, p.status, 204);
-                tc_fence_after();
-                if (elect_one()) {
-                    if (g == 0) FT_TRACE(p, t, 2);
-                    if (g == FWD_NG - 1) FT_TRACE(p, t, 5);
-                    uint64_t xa = da, xb = db;
-#pragma unroll
-                    for (int c = 0; c < FWD_GS; ++c) {
-#pragma unroll
-                        for (int k = 0; k < KCH / 16; ++k)
-                            umma_f16(tmem_d, xa + 2 * k, xb + 2 * k, idesc, (g | c | k) != 0);
-                        xa += a_chunk;
-                        xb += b_chunk;
-                    }
-                    if (g == FWD_NG - 1) { FT_TRACE(p, t, 3); umma_commit(accum_full); }
-                }
-                __syncwarp();
-                da += FWD_GS * a_chunk;
-                db += FWD_GS * b_chunk;
-            }
-        }
-    } else {
-        // ---------------------------------------------------------------- epilogue: 4 warps, 128 threads
-        const int q = warp & 3;                               // TMEM lane quadrant this warp may read
-        const int et = threadIdx.x - 64;                      // 0..127
-        // work items: (batch row b, unit pair up) -> item = b * UP + up ; thread handles items et, et + 128
-        constexpr int UP = FWD_UNITS / 2;
-        const int n_items = p.B * UP;
-        float c[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-        int len_i[2];
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const int item = et + s * EPI_THREADS;
-            len_i[s] = (item < n_items && p.lens) ? p.lens[item / UP] : p.T;
-        }
-        const int u0 = FWD_UNITS * cta;
-        for (int t = 0; t < p.T; ++t) {
-            float x[2][8];                                    // [item][gate*2 + e]
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int item = et + s * EPI_THREADS;
-                if (item < n_items) {
-                    const int b = item / UP, up = item % UP;
-                    const float* src = p.xproj + (static_cast<long long>(t) * p.B + b) * LG + u0 + 2 * up;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const float2 v = __ldg(reinterpret_cast<const float2*>(src + g * LH));
-                        x[s][2 * g] = v.x; x[s][2 * g + 1] = v.y;
-                    }
-                }
-            }
-            if (t > 0) {
-                if (q < nq) {                                 // this warp owns TMEM rows [32q, 32q+32)
-                    mbar_wait(accum_full, (t - 1) & 1, p.status, 205);
-                    tc_fence_after();
-                    if (et == 64) FT_TRACE(p, t, 4);          // warp 4 == quadrant 0
-                    float* dst = sAcc + (q * 32 + lane) * AP;
-#pragma unroll
-                    for (int h = 0; h < FWD_N / 32; ++h) {
-                        float acc[32];
-                        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 32, acc);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) dst[h * 32 + j] = acc[j];
-                    }
-                    tc_fence_before();
-                }
-                epi_bar();
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const int item = et + s * EPI_THREADS;
-                    if (item < n_items) {
-                        const int b = item / UP, up = item % UP;
-                        const float* a = sAcc + b * AP + 2 * up;
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) { x[s][2 * g] += a[g * FWD_UNITS]; x[s][2 * g + 1] += a[g * FWD_UNITS + 1]; }
-                    }
-                }
-            }
-            float gi[2][2], gf[2][2], gg[2][2], go[2][2], hv[2][2];
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int item = et + s * EPI_THREADS;
-                if (item < n_items) {
-                    const int b = item / UP, up = item % UP;
-                    const bool valid = t < len_i[s];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        gi[s][e] = sigmoid_f(x[s][0 + e]);
-                        gf[s][e] = sigmoid_f(x[s][2 + e]);
-                        gg[s][e] = tanh_f(x[s][4 + e]);
-                        go[s][e] = sigmoid_f(x[s][6 + e]);
-                        c[s][e] = gf[s][e] * c[s][e] + gi[s][e] * gg[s][e];
-                        hv[s][e] = valid ? go[s][e] * tanh_f(c[s][e]) : 0.f;
-                    }
-                    const long long r = static_cast<long long>(t) * p.B + b;
-                    const __half2 h2 = __floats2half2_rn(hv[s][0], hv[s][1]);
-                    *reinterpret_cast<__half2*>(p.hseq + r * p.ldh + u0 + 2 * up) = h2;     // critical path: h_t first
-                }
-            }
-            epi_bar();                                        // all h_t stores of this CTA precede the release
-            if (et == 0) {
-                red_release_add(&p.flags[t * FWD_NCH + cta / FWD_PROD], 1);      // cumulative release (gpu scope)
-                FT_TRACE(p, t, 7);
-            }
-            // off the critical path: tensors only the backward pass reads
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int item = et + s * EPI_THREADS;
-                if (item < n_items) {
-                    const int b = item / UP, up = item % UP;
-                    const long long r = static_cast<long long>(t) * p.B + b;
-                    if (p.h32) *reinterpret_cast<float2*>(p.h32 + r * p.ldh32 + u0 + 2 * up) = make_float2(hv[s][0], hv[s][1]);
-                    if (p.gates) {
-                        __half* gp = p.gates + r * LG + u0 + 2 * up;
-                        *reinterpret_cast<__half2*>(gp) = __floats2half2_rn(gi[s][0], gi[s][1]);
-                        *reinterpret_cast<__half2*>(gp + LH) = __floats2half2_rn(gf[s][0], gf[s][1]);
-                        *reinterpret_cast<__half2*>(gp + 2 * LH) = __floats2half2_rn(gg[s][0], gg[s][1]);
-                        *reinterpret_cast<__half2*>(gp + 3 * LH) = __floats2half2_rn(go[s][0], go[s][1]);
-                    }
-                    if (p.cstate) *reinterpret_cast<float2*>(p.cstate + r * LH + u0 + 2 * up) = make_float2(c[s][0], c[s][1]);
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc<(FWD_N < 32 ? 32 : FWD_N)>(tmem_base);
-}
-
 // ------------------------------------------------------------------------------------------- backward
 constexpr int BWD_CTAS = 64, BWD_UNITS = 16, BWD_NCH = LG / KCH;                   // 64 chunks / step
 constexpr int BWD_W_BYTES = BWD_NCH * BWD_UNITS * 128;                              // 128 KB
@@ -511,228 +306,17 @@ constexpr int B4_CTAS = 64, B4_CLUSTER = 4, B4_UNITS = 64, B4_OWN = 16, B4_NCH =
 constexpr int B4_W_BYTES = B4_NCH * B4_UNITS * 128;                                               // 128 KB
 constexpr int B4_PP = 68;                                                                          // partial row pitch (floats)
 
-__global__ void __launch_bounds__(LSTM_THREADS, 1)
-lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant__ CUtensorMap tmG, LstmBwdParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int slot_bytes = p.Bbox * 128;
-    uint8_t* sA = smem;                                          // [16 chunks][Bbox rows][128 B]
-    uint8_t* sW = smem + B4_NCH * slot_bytes;                    // [16 chunks][64 rows][128 B]
-    float* sPart = reinterpret_cast<float*>(sW + B4_W_BYTES);    // [2 parities][32 rows][B4_PP]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + 2 * 32 * B4_PP);
-    uint64_t* full = bars;                       // [2]
-    uint64_t* wbar = bars + 2;
-    uint64_t* accum_full = bars + 3;
-    uint64_t* part_bar = bars + 4;               // [2] : 4 cluster-scope arrivals each
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rank = static_cast<int>(cluster_ctarank());
-    const int cl = blockIdx.x / B4_CLUSTER;
-    constexpr int GS = 8, NG = B4_NCH / GS;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmWT);
-        tma_prefetch_desc(&tmG);
-        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-        mbar_init(wbar, 1);
-        mbar_init(accum_full, 1);
-        mbar_init(&part_bar[0], B4_CLUSTER); mbar_init(&part_bar[1], B4_CLUSTER);
-        fence_mbar_init();
-    }
-    if (warp == 1) tmem_alloc<64>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    cluster_sync_all();                                          // every rank's barriers exist before any remote arrive
-
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_expect_tx(wbar, B4_W_BYTES);
-            for (int kc = 0; kc < B4_NCH; ++kc)                  // W_hh^T rows [64c, 64c+64), columns of gate `rank`
-                tma_load_2d(sW + kc * (B4_UNITS * 128), &tmWT, wbar, rank * LH + kc * KCH, B4_UNITS * cl);
-        }
-        for (int t = p.T - 2; t >= 0; --t) {
-            // gate `rank` of dG_{t+1}: 16 chunks, each released by the 4 ranks of one cluster
-            if (lane < B4_NCH) wait_flag_ge(&p.flags[(t + 1) * BWD_NCH + rank * B4_NCH + lane], 4, p.status, 222);
-            __syncwarp();
-            if (elect_one()) {
-                FT_TRACE(p, t, 0);
-                fence_proxy_async_global();
-#pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    mbar_expect_tx(&full[g], GS * slot_bytes);
-                    tma_load_3d(sA + g * GS * slot_bytes, &tmG, &full[g], 0, (t + 1) * p.B, rank * B4_NCH + g * GS);
-                }
-            }
-            __syncwarp();
-        }
-    } else if (warp == 1) {
-        mbar_wait(wbar, 0, p.status, 223);
-        const uint32_t idesc = umma_idesc(128, B4_UNITS, FMT_F16, FMT_F16, 0, 0);
-        const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
-        const uint64_t da_base = umma_smem_desc(smem_u32(sA), 16, 1024), db_base = umma_smem_desc(smem_u32(sW), 16, 1024);
-        const uint64_t a_chunk = static_cast<uint64_t>(slot_bytes >> 4), b_chunk = (B4_UNITS * 128) >> 4;
-        int step = 0;
-        for (int t = p.T - 2; t >= 0; --t, ++step) {
-            const int ph = step & 1;
-            uint64_t da = da_base, db = db_base;
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                mbar_wait(&full[g], ph, p.status, 224);
-                tc_fence_after();
-                if (elect_one()) {
-                    if (g == 0) FT_TRACE(p, t, 2);
-                    uint64_t xa = da, xb = db;
-#pragma unroll
-                    for (int c = 0; c < GS; ++c) {
-#pragma unroll
-                        for (int k = 0; k < KCH / 16; ++k)
-                            umma_f16(tmem_d, xa + 2 * k, xb + 2 * k, idesc, (g | c | k) != 0);
-                        xa += a_chunk;
-                        xb += b_chunk;
-                    }
-                    if (g == NG - 1) { FT_TRACE(p, t, 3); umma_commit(accum_full); }
-                }
-                __syncwarp();
-                da += GS * a_chunk;
-                db += GS * b_chunk;
-            }
-        }
-    } else {
-        const int q = warp & 3;
-        const int et = threadIdx.x - 64;
-        const int n_items = p.B * 4;                              // (batch row, quad of units) over this rank's 16 final units
-        const int u0 = B4_UNITS * cl + B4_OWN * rank;
-        const int item = et;
-        const bool has_item = item < n_items;
-        const int ib = item >> 2, uq = item & 3;
-        float dcs[4] = {0.f, 0.f, 0.f, 0.f};
-        const int len = (has_item && p.lens) ? p.lens[ib] : p.T;
-        uint32_t part_remote[B4_CLUSTER];
-#pragma unroll
-        for (int r = 0; r < B4_CLUSTER; ++r) part_remote[r] = mapa_shared(smem_u32(sPart), r);
-        int step = 0;
-        for (int t = p.T - 1; t >= 0; --t, ++step) {
-            float dh[4], ct[4], cp[4];
-            __half2 gt[4][2];
-            const bool valid = has_item && (t < len);
-            const long long r = static_cast<long long>(t) * p.B + ib;
-            const int uo = u0 + 4 * uq;
-            if (valid) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(p.dh_ext + r * p.ldd + uo));
-                dh[0] = v.x; dh[1] = v.y; dh[2] = v.z; dh[3] = v.w;
-                const float4 cc = __ldg(reinterpret_cast<const float4*>(p.cstate + r * LH + uo));
-                ct[0] = cc.x; ct[1] = cc.y; ct[2] = cc.z; ct[3] = cc.w;
-                float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t > 0) pp = __ldg(reinterpret_cast<const float4*>(p.cstate + (r - p.B) * LH + uo));
-                cp[0] = pp.x; cp[1] = pp.y; cp[2] = pp.z; cp[3] = pp.w;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const uint2 pk = __ldg(reinterpret_cast<const uint2*>(p.gates + r * LG + g * LH + uo));
-                    *reinterpret_cast<uint2*>(&gt[g][0]) = pk;
-                }
-            }
-            float rec[4] = {0.f, 0.f, 0.f, 0.f};                 // recurrent part of dh_t: sum over the 4 ranks' partials
-            if (step > 0) {
-                const int par = (step - 1) & 1;
-                float* mine = sPart + par * 32 * B4_PP;
-                if (q == 0) {                                     // B <= 32: TMEM rows 0..31 hold the batch rows
-                    mbar_wait(accum_full, (step - 1) & 1, p.status, 225);
-                    tc_fence_after();
-                    if (et == 64) FT_TRACE(p, t, 4);
-                    {
-                        float a0[32], a1[32];
-                        tmem_ld_32x32(tmem_base, a0);
-                        tmem_ld_32x32(tmem_base + 32, a1);
-                        tmem_ld_wait();
-                        float* dst = mine + lane * B4_PP;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            *reinterpret_cast<float4*>(dst + j) = make_float4(a0[j], a0[j + 1], a0[j + 2], a0[j + 3]);
-                            *reinterpret_cast<float4*>(dst + 32 + j) = make_float4(a1[j], a1[j + 1], a1[j + 2], a1[j + 3]);
-                        }
-                    }
-                    tc_fence_before();
-                    if (et == 64) FT_TRACE(p, t, 6);
-                }
-                epi_bar();
-                // publish: one release-arrive on every rank's barrier, issued by 4 different threads so the four
-                // cluster-scope releases overlap (issued serially by one thread they cost ~1.8 us per step)
-                if (et < B4_CLUSTER) mbar_arrive_cluster(mapa_shared(smem_u32(&part_bar[par]), et));
-                mbar_wait_cluster(&part_bar[par], ((step - 1) >> 1) & 1, p.status, 226);
-                if (et == 0) FT_TRACE(p, t, 1 + 0 * 8 + 0);   // reuse slot 1: all partials visible
-                if (has_item) {
-                    const uint32_t off = static_cast<uint32_t>((par * 32 * B4_PP + ib * B4_PP + B4_OWN * rank + 4 * uq) * 4);
-#pragma unroll
-                    for (int rr = 0; rr < B4_CLUSTER; ++rr) {
-                        const float4 v = ld_dsmem_f4(part_remote[rr] + off);
-                        rec[0] += v.x; rec[1] += v.y; rec[2] += v.z; rec[3] += v.w;
-                    }
-                }
-            }
-            if (has_item) {
-                __half2 out[4][2];
-                if (valid) {
-#pragma unroll
-                    for (int j2 = 0; j2 < 2; ++j2) {
-                        float da[4][2];
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int j = 2 * j2 + e;
-                            const float gi = e ? __high2float(gt[0][j2]) : __low2float(gt[0][j2]);
-                            const float gf = e ? __high2float(gt[1][j2]) : __low2float(gt[1][j2]);
-                            const float gg = e ? __high2float(gt[2][j2]) : __low2float(gt[2][j2]);
-                            const float go = e ? __high2float(gt[3][j2]) : __low2float(gt[3][j2]);
-                            const float dht = dh[j] + rec[j];
-                            const float tc = tanh_f(ct[j]);
-                            const float dc = dcs[j] + dht * go * (1.f - tc * tc);
-                            da[3][e] = dht * tc * go * (1.f - go);
-                            da[0][e] = dc * gg * gi * (1.f - gi);
-                            da[2][e] = dc * gi * (1.f - gg * gg);
-                            da[1][e] = dc * cp[j] * gf * (1.f - gf);
-                            dcs[j] = dc * gf;
-                        }
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            out[g][j2] = __floats2half2_rn(fminf(fmaxf(da[g][0], -65504.f), 65504.f),
-                                                           fminf(fmaxf(da[g][1], -65504.f), 65504.f));
-                    }
-                } else {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) { out[g][0] = __floats2half2_rn(0.f, 0.f); out[g][1] = out[g][0]; }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dcs[j] = 0.f;
-                }
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    *reinterpret_cast<uint2*>(p.dG + r * LG + g * LH + uo) = *reinterpret_cast<uint2*>(&out[g][0]);
-            }
-            epi_bar();                                            // every dG_t store of this CTA precedes the releases
-            if (et == 0) FT_TRACE(p, t, 5);
-            if (et < 4) red_release_add(&p.flags[t * BWD_NCH + et * 16 + cl], 1);     // chunk (gate et, units 64cl..) : 4 ranks
-            if (et == 0) FT_TRACE(p, t, 7);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();                                          // nobody exits while a peer may still read its partials
-    if (warp == 1) tmem_dealloc<64>(tmem_base);
-}
-
-// ------------------------------------------------------------------------------------------- backward, one chunk of steps
-// EXPERIMENTAL (round-2 groundwork; NOT validated on hardware yet, only reachable with FT_PIPE_BWD=1):
-// lstm_bwd4_kernel over steps [t0, t1), highest step first, resuming dc*f from `dc_carry` ([B,1024] fp32, written by the
-// chunk above) and dG_{t1} from the dG tensor.  A verbatim copy with the loop bounds, the flag indexing (relative to t0),
-// the mbarrier phases (counted over the steps that have a recurrent term) and the carry changed.
+// The kernel runs steps [t0, t1) of the sequence, highest step first: the whole sequence in one launch (t0 = 0, t1 = T), or
+// one chunk of the layer pipeline (ar_step.cu), resuming dc*f from `dc_carry` ([B,1024] fp32, written by the chunk above) and
+// dG_{t1} from the dG tensor.  Flags are indexed relative to t0, mbarrier phases are counted over the steps that have a
+// recurrent term.
 struct LstmBwdChunkParams : LstmBwdParams {
     int t0, t1;                // steps [t0, t1); flags: [(t1 - t0) * 64] ints, zeroed by the launcher
     float* dc_carry;           // [B, 1024]
 };
 
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
-lstm_bwd4_chunk_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant__ CUtensorMap tmG, LstmBwdChunkParams p) {
+lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant__ CUtensorMap tmG, LstmBwdChunkParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int slot_bytes = p.Bbox * 128;
@@ -782,6 +366,7 @@ lstm_bwd4_chunk_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_co
                 wait_flag_ge(&p.flags[(t + 1 - p.t0) * BWD_NCH + rank * B4_NCH + lane], 4, p.status, 232);
             __syncwarp();
             if (elect_one()) {
+                FT_TRACE(p, t, 0);
                 fence_proxy_async_global();
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
@@ -806,6 +391,7 @@ lstm_bwd4_chunk_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_co
                 mbar_wait(&full[g], ph, p.status, 234);
                 tc_fence_after();
                 if (elect_one()) {
+                    if (g == 0) FT_TRACE(p, t, 2);
                     uint64_t xa = da, xb = db;
 #pragma unroll
                     for (int c = 0; c < GS; ++c) {
@@ -815,7 +401,7 @@ lstm_bwd4_chunk_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_co
                         xa += a_chunk;
                         xb += b_chunk;
                     }
-                    if (g == NG - 1) umma_commit(accum_full);
+                    if (g == NG - 1) { FT_TRACE(p, t, 3); umma_commit(accum_full); }
                 }
                 __syncwarp();
                 da += GS * a_chunk;
@@ -868,6 +454,7 @@ lstm_bwd4_chunk_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_co
                 if (q == 0) {                                     // B <= 32: TMEM rows 0..31 hold the batch rows
                     mbar_wait(accum_full, rs & 1, p.status, 235);
                     tc_fence_after();
+                    if (et == 64) FT_TRACE(p, t, 4);
                     {
                         float a0[32], a1[32];
                         tmem_ld_32x32(tmem_base, a0);
@@ -881,12 +468,14 @@ lstm_bwd4_chunk_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_co
                         }
                     }
                     tc_fence_before();
+                    if (et == 64) FT_TRACE(p, t, 6);
                 }
                 epi_bar();
                 // publish: one release-arrive on every rank's barrier, issued by 4 different threads so the four
                 // cluster-scope releases overlap (issued serially by one thread they cost ~1.8 us per step)
                 if (et < B4_CLUSTER) mbar_arrive_cluster(mapa_shared(smem_u32(&part_bar[par]), et));
                 mbar_wait_cluster(&part_bar[par], (rs >> 1) & 1, p.status, 236);
+                if (et == 0) FT_TRACE(p, t, 1);               // all partials visible
                 if (has_item) {
                     const uint32_t off = static_cast<uint32_t>((par * 32 * B4_PP + ib * B4_PP + B4_OWN * rank + 4 * uq) * 4);
 #pragma unroll
@@ -934,7 +523,9 @@ lstm_bwd4_chunk_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_co
                     *reinterpret_cast<uint2*>(p.dG + r * LG + g * LH + uo) = *reinterpret_cast<uint2*>(&out[g][0]);
             }
             epi_bar();                                            // every dG_t store of this CTA precedes the releases
+            if (et == 0) FT_TRACE(p, t, 5);
             if (et < 4) red_release_add(&p.flags[(t - p.t0) * BWD_NCH + et * 16 + cl], 1);     // chunk (gate et, units 64cl..) : 4 ranks
+            if (et == 0) FT_TRACE(p, t, 7);
         }
         if (p.t0 > 0 && has_item)                                 // hand dc * f to the chunk below
             *reinterpret_cast<float4*>(p.dc_carry + static_cast<long long>(ib) * LH + B4_UNITS * cl + B4_OWN * rank + 4 * uq) =
@@ -947,19 +538,18 @@ lstm_bwd4_chunk_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_co
 }
 
 
-// ------------------------------------------------------------------------------------------- forward, one chunk of steps
-// EXPERIMENTAL (round-2 groundwork; NOT validated on hardware yet, only reachable with FT_PIPE_FWD=1):
-// the same recurrence over steps [t0, t1) only, resuming h from the output tensor (row t0-1) and c from the saved cell
-// states, so that two layers can run as two 64-CTA kernels on two streams, chunk by chunk, one chunk apart.  A verbatim
-// copy of lstm_fwd_kernel with the loop bounds, the flag indexing (relative to t0), the mbarrier phases (relative to the
-// first step that has a recurrent term) and the cell-state resume changed; the default path does not use it.
+// ------------------------------------------------------------------------------------------- forward kernel
+// Steps [t0, t1) of the recurrence: the whole sequence in one launch (t0 = 0, t1 = T), or one chunk of the layer pipeline
+// (ar_step.cu: two layers run as two 64-CTA kernels on two streams, chunk by chunk, one chunk apart), resuming h from the
+// output tensor (row t0-1) and c from the saved cell states.  Flags are indexed relative to t0, mbarrier phases relative to
+// the first step that has a recurrent term.
 struct LstmFwdChunkParams : LstmFwdParams {
     int t0, t1;                // steps [t0, t1); flags: [(t1 - t0) * 16] ints, zeroed by the launcher
 };
 
 template <int FWD_GS, int FWD_UNITS>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
-lstm_fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, LstmFwdChunkParams p) {
+lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, LstmFwdChunkParams p) {
     constexpr int FWD_NG = FWD_NCH / FWD_GS;                     // TMA groups per step
     constexpr int FWD_N = 4 * FWD_UNITS, FWD_W_BYTES = FWD_NCH * FWD_N * 128, FWD_PROD = KCH / FWD_UNITS;
     constexpr int AP = FWD_N + 1;                                // accumulator staging pitch
@@ -1008,12 +598,15 @@ lstm_fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             if (t > p.t0 && lane < FWD_NCH) wait_flag_ge(&p.flags[(t - 1 - p.t0) * FWD_NCH + lane], FWD_PROD, p.status, 212);
             __syncwarp();
             if (elect_one()) {
+                FT_TRACE(p, t, 0);
                 fence_proxy_async_global();        // generic-proxy writes of other SMs -> async-proxy (TMA) reads
+                FT_TRACE(p, t, 6);
 #pragma unroll
                 for (int g = 0; g < FWD_NG; ++g) {
                     mbar_expect_tx(&full[g], FWD_GS * slot_bytes);
                     tma_load_3d(sA + g * FWD_GS * slot_bytes, &tmH, &full[g], 0, (t - 1) * p.B, g * FWD_GS);
                 }
+                FT_TRACE(p, t, 1);
             }
             __syncwarp();
         }
@@ -1032,6 +625,8 @@ lstm_fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
                 mbar_wait(&full[g], ph, p.status, 214);
                 tc_fence_after();
                 if (elect_one()) {
+                    if (g == 0) FT_TRACE(p, t, 2);
+                    if (g == FWD_NG - 1) FT_TRACE(p, t, 5);
                     uint64_t xa = da, xb = db;
 #pragma unroll
                     for (int c = 0; c < FWD_GS; ++c) {
@@ -1041,7 +636,7 @@ lstm_fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
                         xa += a_chunk;
                         xb += b_chunk;
                     }
-                    if (g == FWD_NG - 1) umma_commit(accum_full);
+                    if (g == FWD_NG - 1) { FT_TRACE(p, t, 3); umma_commit(accum_full); }
                 }
                 __syncwarp();
                 da += FWD_GS * a_chunk;
@@ -1093,6 +688,7 @@ lstm_fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
                 if (q < nq) {                                 // this warp owns TMEM rows [32q, 32q+32)
                     mbar_wait(accum_full, (t - tm0) & 1, p.status, 215);
                     tc_fence_after();
+                    if (et == 64) FT_TRACE(p, t, 4);          // warp 4 == quadrant 0
                     float* dst = sAcc + (q * 32 + lane) * AP;
 #pragma unroll
                     for (int h = 0; h < FWD_N / 32; ++h) {
@@ -1140,6 +736,7 @@ lstm_fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             epi_bar();                                        // all h_t stores of this CTA precede the release
             if (et == 0) {
                 red_release_add(&p.flags[(t - p.t0) * FWD_NCH + cta / FWD_PROD], 1);      // cumulative release (gpu scope)
+                FT_TRACE(p, t, 7);
             }
             // off the critical path: tensors only the backward pass reads
 #pragma unroll
@@ -1202,19 +799,26 @@ static int make_tmap_chunks(CUtensorMap* out, const void* ptr, long long rows, i
 static bool g_half_sm = false;       // 64-CTA forward kernel (for two concurrent half-batch launches)
 void set_lstm_half_sm(int on) { g_half_sm = on != 0; }
 
+// Steps [t0, t1) of one layer's forward recurrence on 1024 / UNITS CTAs.  `flags` needs (t1 - t0) * 16 ints.
 template <int GS, int UNITS>
-static int launch_fwd_t(LstmFwdParams& p, const void* whh16, void* hseq16, long long ldh, int T, int B, int* flags, cudaStream_t st) {
+static int launch_fwd_t(int T, int B, int t0, int t1, const float* xproj, const void* whh16, const int* lens, void* hseq16,
+                        long long ldh, void* gates16, float* cstate, float* h32, long long ldh32, int* flags, cudaStream_t st) {
     constexpr int N = 4 * UNITS, W_BYTES = FWD_NCH * N * 128, CTAS = LH / UNITS;
+    LstmFwdChunkParams p;
+    p.T = T; p.B = B; p.Bbox = (B + 7) & ~7; p.t0 = t0; p.t1 = t1;
+    p.xproj = xproj; p.lens = lens; p.hseq = static_cast<__half*>(hseq16); p.ldh = ldh;
+    p.gates = static_cast<__half*>(gates16); p.cstate = cstate; p.h32 = h32; p.ldh32 = ldh32;
+    p.flags = flags; p.status = ft_status_word(); p.trace = (t0 == 0 && t1 == T) ? g_lstm_trace : nullptr;
     const int slot = p.Bbox * 128, nq = (B + 31) / 32;
     const int smem = FWD_NCH * slot + W_BYTES + nq * 32 * (N + 1) * 4 + 8 + 256 + 1024;
     if (smem > smem_optin()) return ft_set_error("lstm_fwd: not enough shared memory");
     CUtensorMap tmW, tmH;
     if (make_tmap_2d(&tmW, whh16, FMT_F16, LG, LH, LH, KCH, UNITS)) return -1;
     if (make_tmap_chunks(&tmH, hseq16, static_cast<long long>(T) * B, FWD_NCH, ldh, p.Bbox, GS)) return -1;
-    if (cudaMemsetAsync(flags, 0, sizeof(int) * T * FWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_fwd: memset failed");
+    if (cudaMemsetAsync(flags, 0, sizeof(int) * (t1 - t0) * FWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_fwd: memset failed");
     void* fn = reinterpret_cast<void*>(lstm_fwd_kernel<GS, UNITS>);
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    TimeScope ts("lstm_fwd", T, B, 0, st);
+    TimeScope ts("lstm_fwd", t1 - t0, B, 0, st);
     void* args[] = {&tmW, &tmH, &p};
     cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(CTAS), dim3(LSTM_THREADS), args, smem, st);
     if (e != cudaSuccess) return ft_set_error(cudaGetErrorString(e));
@@ -1226,65 +830,39 @@ int launch_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const i
                     void* gates16, float* cstate, float* h32, long long ldh32, int* flags, cudaStream_t st) {
     if (T <= 0 || B <= 0) return 0;
     if (B > 64) return ft_set_error("lstm_fwd: batch > 64 per call not supported (split the batch)");
-    LstmFwdParams p;
-    p.T = T; p.B = B; p.Bbox = (B + 7) & ~7;
-    p.xproj = xproj; p.lens = lens; p.hseq = static_cast<__half*>(hseq16); p.ldh = ldh;
-    p.gates = static_cast<__half*>(gates16); p.cstate = cstate; p.h32 = h32; p.ldh32 = ldh32;
-    p.flags = flags; p.status = ft_status_word(); p.trace = g_lstm_trace;
-    if (g_half_sm && B <= 32) return launch_fwd_t<8, 16>(p, whh16, hseq16, ldh, T, B, flags, st);
+    if (g_half_sm && B <= 32) return launch_fwd_t<8, 16>(T, B, 0, T, xproj, whh16, lens, hseq16, ldh, gates16, cstate, h32, ldh32, flags, st);
     static int gs = -1;            // FT_LSTM_FWD_GS: K-chunks per TMA group (16 / gs groups per step), tuning knob
     if (gs < 0) { const char* e = getenv("FT_LSTM_FWD_GS"); gs = e ? atoi(e) : 8; }
-    if (gs == 4) return launch_fwd_t<4, 8>(p, whh16, hseq16, ldh, T, B, flags, st);
-    if (gs == 2) return launch_fwd_t<2, 8>(p, whh16, hseq16, ldh, T, B, flags, st);
-    if (gs == 16) return launch_fwd_t<16, 8>(p, whh16, hseq16, ldh, T, B, flags, st);
-    return launch_fwd_t<8, 8>(p, whh16, hseq16, ldh, T, B, flags, st);
+    if (gs == 4) return launch_fwd_t<4, 8>(T, B, 0, T, xproj, whh16, lens, hseq16, ldh, gates16, cstate, h32, ldh32, flags, st);
+    if (gs == 16) return launch_fwd_t<16, 8>(T, B, 0, T, xproj, whh16, lens, hseq16, ldh, gates16, cstate, h32, ldh32, flags, st);
+    return launch_fwd_t<8, 8>(T, B, 0, T, xproj, whh16, lens, hseq16, ldh, gates16, cstate, h32, ldh32, flags, st);
 }
 
-// EXPERIMENTAL (see lstm_fwd_chunk_kernel): steps [t0, t1) of a layer on 64 CTAs.  `flags` needs (t1 - t0) * 16 ints.
+// Steps [t0, t1) of a layer on 64 CTAs (layer pipeline, ar_step.cu).  `flags` needs (t1 - t0) * 16 ints.
 int launch_lstm_fwd_chunk(int T, int B, int t0, int t1, const float* xproj, const void* whh16, const int* lens, void* hseq16,
                           long long ldh, void* gates16, float* cstate, int* flags, cudaStream_t st) {
     if (T <= 0 || B <= 0 || t1 <= t0) return 0;
     if (B > 64 || t0 < 0 || t1 > T) return ft_set_error("lstm_fwd_chunk: bad batch or step range");
     if (t0 > 0 && !cstate) return ft_set_error("lstm_fwd_chunk: resuming a chunk needs the saved cell states");
-    constexpr int GS = 8, UNITS = 16, N = 4 * UNITS, W_BYTES = FWD_NCH * N * 128, CTAS = LH / UNITS;
-    LstmFwdChunkParams p;
-    p.T = T; p.B = B; p.Bbox = (B + 7) & ~7; p.t0 = t0; p.t1 = t1;
-    p.xproj = xproj; p.lens = lens; p.hseq = static_cast<__half*>(hseq16); p.ldh = ldh;
-    p.gates = static_cast<__half*>(gates16); p.cstate = cstate; p.h32 = nullptr; p.ldh32 = 0;
-    p.flags = flags; p.status = ft_status_word(); p.trace = nullptr;
-    const int slot = p.Bbox * 128, nq = (B + 31) / 32;
-    const int smem = FWD_NCH * slot + W_BYTES + nq * 32 * (N + 1) * 4 + 8 + 256 + 1024;
-    if (smem > smem_optin()) return ft_set_error("lstm_fwd_chunk: not enough shared memory");
-    CUtensorMap tmW, tmH;
-    if (make_tmap_2d(&tmW, whh16, FMT_F16, LG, LH, LH, KCH, UNITS)) return -1;
-    if (make_tmap_chunks(&tmH, hseq16, static_cast<long long>(T) * B, FWD_NCH, ldh, p.Bbox, GS)) return -1;
-    if (cudaMemsetAsync(flags, 0, sizeof(int) * (t1 - t0) * FWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_fwd_chunk: memset failed");
-    void* fn = reinterpret_cast<void*>(lstm_fwd_chunk_kernel<GS, UNITS>);
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    TimeScope ts("lstm_fwd", t1 - t0, B, 0, st);
-    void* args[] = {&tmW, &tmH, &p};
-    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(CTAS), dim3(LSTM_THREADS), args, smem, st);
-    if (e != cudaSuccess) return ft_set_error(cudaGetErrorString(e));
-    ft_count_launch(1);
-    return ft_check_launch("lstm_fwd_chunk_kernel");
+    return launch_fwd_t<8, 16>(T, B, t0, t1, xproj, whh16, lens, hseq16, ldh, gates16, cstate, nullptr, 0, flags, st);
 }
 
-// EXPERIMENTAL (see lstm_bwd4_chunk_kernel): steps [t0, t1) of a layer's BPTT, B <= 32.  `flags` needs (t1 - t0) * 64 ints.
-int launch_lstm_bwd_chunk(int T, int B, int t0, int t1, const float* dh_ext, long long ldd, const void* whhT16, const void* gates16,
-                          const float* cstate, const int* lens, void* dG16, float* dc_carry, int* flags, cudaStream_t st) {
-    if (T <= 0 || B <= 0 || t1 <= t0) return 0;
-    if (B > 32 || t0 < 0 || t1 > T || !dc_carry) return ft_set_error("lstm_bwd_chunk: bad batch, step range or carry buffer");
+// Steps [t0, t1) of a layer's BPTT with the split-K cluster kernel, B <= 32.  `flags` needs (t1 - t0) * 64 ints; `dc_carry`
+// ([B,1024] fp32) is only touched when the range is a proper chunk.
+static int launch_bwd4(int T, int B, int t0, int t1, const float* dh_ext, long long ldd, const void* whhT16, const void* gates16,
+                       const float* cstate, const int* lens, void* dG16, float* dc_carry, int* flags, cudaStream_t st) {
     LstmBwdChunkParams p;
     p.T = T; p.B = B; p.Bbox = (B + 7) & ~7; p.gs = 8; p.ng = 2; p.nring = 0; p.t0 = t0; p.t1 = t1; p.dc_carry = dc_carry;
     const int slot = p.Bbox * 128;
     p.dh_ext = dh_ext; p.ldd = ldd; p.gates = static_cast<const __half*>(gates16); p.cstate = cstate; p.lens = lens;
-    p.dG = static_cast<__half*>(dG16); p.flags = flags; p.status = ft_status_word(); p.trace = nullptr;
+    p.dG = static_cast<__half*>(dG16); p.flags = flags; p.status = ft_status_word();
+    p.trace = (t0 == 0 && t1 == T) ? g_lstm_trace : nullptr;
     CUtensorMap tmWT, tmG;
     if (make_tmap_2d(&tmWT, whhT16, FMT_F16, LH, LG, LG, KCH, B4_UNITS)) return -1;
     if (make_tmap_chunks(&tmG, dG16, static_cast<long long>(T) * B, BWD_NCH, LG, p.Bbox, 8)) return -1;
-    if (cudaMemsetAsync(flags, 0, sizeof(int) * (t1 - t0) * BWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_bwd_chunk: memset failed");
+    if (cudaMemsetAsync(flags, 0, sizeof(int) * (t1 - t0) * BWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_bwd: memset failed");
     const int smem = B4_NCH * slot + B4_W_BYTES + 2 * 32 * B4_PP * 4 + 256 + 1024;
-    cudaFuncSetAttribute(lstm_bwd4_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(lstm_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(B4_CTAS); cfg.blockDim = dim3(LSTM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attrs[2];
@@ -1292,17 +870,26 @@ int launch_lstm_bwd_chunk(int T, int B, int t0, int t1, const float* dh_ext, lon
     attrs[0].val.clusterDim.x = B4_CLUSTER; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
     attrs[1].id = cudaLaunchAttributeCooperative;
     attrs[1].val.cooperative = 1;
-    cfg.attrs = attrs; cfg.numAttrs = 2;
+    static int coop = -1;          // FT_BWD_COOP=0: plain cluster launch (ncu cannot replay cooperative + cluster launches)
+    if (coop < 0) { const char* e = getenv("FT_BWD_COOP"); coop = e ? atoi(e) : 1; }
+    cfg.attrs = attrs; cfg.numAttrs = coop ? 2 : 1;
     TimeScope ts("lstm_bwd", t1 - t0, B, 0, st);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_bwd4_chunk_kernel, tmWT, tmG, p);
-    if (e != cudaSuccess) {
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_bwd4_kernel, tmWT, tmG, p);
+    if (e != cudaSuccess) {                                  // co-residency is implied by 64 CTAs <= SMs; retry without the attribute
         cudaGetLastError();
         cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, lstm_bwd4_chunk_kernel, tmWT, tmG, p);
+        e = cudaLaunchKernelEx(&cfg, lstm_bwd4_kernel, tmWT, tmG, p);
     }
     if (e != cudaSuccess) return ft_set_error(cudaGetErrorString(e));
     ft_count_launch(1);
-    return ft_check_launch("lstm_bwd4_chunk_kernel");
+    return ft_check_launch("lstm_bwd4_kernel");
+}
+
+int launch_lstm_bwd_chunk(int T, int B, int t0, int t1, const float* dh_ext, long long ldd, const void* whhT16, const void* gates16,
+                          const float* cstate, const int* lens, void* dG16, float* dc_carry, int* flags, cudaStream_t st) {
+    if (T <= 0 || B <= 0 || t1 <= t0) return 0;
+    if (B > 32 || t0 < 0 || t1 > T || !dc_carry) return ft_set_error("lstm_bwd_chunk: bad batch, step range or carry buffer");
+    return launch_bwd4(T, B, t0, t1, dh_ext, ldd, whhT16, gates16, cstate, lens, dG16, dc_carry, flags, st);
 }
 
 int launch_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void* whhT16, const void* gates16,
@@ -1311,39 +898,8 @@ int launch_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void
     if (B > 64) return ft_set_error("lstm_bwd: batch > 64 per call not supported (split the batch)");
     static int use_cluster = -1;
     if (use_cluster < 0) { const char* e = getenv("FT_LSTM_BWD_CLUSTER"); use_cluster = e ? atoi(e) : 1; }
-    if (B <= 32 && use_cluster) {
-        LstmBwdParams p;
-        p.T = T; p.B = B; p.Bbox = (B + 7) & ~7; p.gs = 8; p.ng = 2; p.nring = 0;
-        const int slot = p.Bbox * 128;
-        p.dh_ext = dh_ext; p.ldd = ldd; p.gates = static_cast<const __half*>(gates16); p.cstate = cstate; p.lens = lens;
-        p.dG = static_cast<__half*>(dG16); p.flags = flags; p.status = ft_status_word(); p.trace = g_lstm_trace;
-        CUtensorMap tmWT, tmG;
-        if (make_tmap_2d(&tmWT, whhT16, FMT_F16, LH, LG, LG, KCH, B4_UNITS)) return -1;
-        if (make_tmap_chunks(&tmG, dG16, static_cast<long long>(T) * B, BWD_NCH, LG, p.Bbox, 8)) return -1;
-        if (cudaMemsetAsync(flags, 0, sizeof(int) * T * BWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_bwd: memset failed");
-        const int smem = B4_NCH * slot + B4_W_BYTES + 2 * 32 * B4_PP * 4 + 256 + 1024;
-        cudaFuncSetAttribute(lstm_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(B4_CTAS); cfg.blockDim = dim3(LSTM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute attrs[2];
-        attrs[0].id = cudaLaunchAttributeClusterDimension;
-        attrs[0].val.clusterDim.x = B4_CLUSTER; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
-        attrs[1].id = cudaLaunchAttributeCooperative;
-        attrs[1].val.cooperative = 1;
-        static int coop = -1;          // FT_BWD_COOP=0: plain cluster launch (ncu cannot replay cooperative + cluster launches)
-        if (coop < 0) { const char* e = getenv("FT_BWD_COOP"); coop = e ? atoi(e) : 1; }
-        cfg.attrs = attrs; cfg.numAttrs = coop ? 2 : 1;
-        TimeScope ts("lstm_bwd", T, B, 0, st);
-        cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_bwd4_kernel, tmWT, tmG, p);
-        if (e != cudaSuccess) {                                  // co-residency is implied by 64 CTAs <= SMs; retry without the attribute
-            cudaGetLastError();
-            cfg.numAttrs = 1;
-            e = cudaLaunchKernelEx(&cfg, lstm_bwd4_kernel, tmWT, tmG, p);
-        }
-        if (e != cudaSuccess) return ft_set_error(cudaGetErrorString(e));
-        ft_count_launch(1);
-        return ft_check_launch("lstm_bwd4_kernel");
-    }
+    if (B <= 32 && use_cluster)
+        return launch_bwd4(T, B, 0, T, dh_ext, ldd, whhT16, gates16, cstate, lens, dG16, nullptr, flags, st);
     LstmBwdParams p;
     p.T = T; p.B = B; p.Bbox = (B + 7) & ~7;
     const int slot = p.Bbox * 128;

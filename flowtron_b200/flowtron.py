@@ -513,12 +513,11 @@ class _NllGateFn(torch.autograd.Function):
         dev = z.device
         zc = z.detach().float().contiguous()
         lsl = [ls.detach().float().contiguous() for ls in log_s_list]
-        ptrs = torch.tensor([t.data_ptr() for t in lsl], dtype=torch.int64, device=dev)
         gp = None if gate_pred is None else gate_pred.detach().float().contiguous()
         gt = None if gate_pred is None else gate_target.detach().float().contiguous()
         lens = out_lens.to(device=dev, dtype=torch.int32).contiguous()
         sums = torch.empty(4, device=dev)
-        _lib.nll_reduce(zc, ptrs, len(lsl), gp, gt, lens, sums)
+        _lib.nll_reduce(zc, lsl, gp, gt, lens, sums)
         n = sums[3]
         nll = (sums[0] / (2 * sigma * sigma) - sums[1]) / (n * M)
         gate_loss = (sums[2] / n).reshape(1)

@@ -122,7 +122,8 @@ int ft_ar_step_bwd(const FtArStepDesc* d, const FtArStepWeights* w, const float*
                    const FtArStepWeights* g, void* saved, void* scratch, void* stream);
 
 /* FlowtronLoss default branch (flowtron.py:205-243): sums[0]=sum (z m)^2, [1]=sum_flows sum log_s m,
- * [2]=sum m BCEWithLogits(gate m, target), [3]=n=sum m.  log_s_list: device array of n_flows device pointers. */
+ * [2]=sum m BCEWithLogits(gate m, target), [3]=n=sum m.  log_s_list: HOST array of n_flows (<= 16) device pointers (passed
+ * to the kernel by value: no upload, so the call can be captured in a CUDA graph). */
 int ft_nll_reduce(const float* z, const float* const* log_s_list, int n_flows, const float* gate,
                   const float* gate_target, const int* out_lens, int T, int B, int M, float* sums, void* stream);
 /* Gradients of g_nll*nll + g_gate*gate_loss w.r.t. z, every log_s (identical tensor), gate logits. */

@@ -1,6 +1,6 @@
-"""GPU, EXPERIMENTAL and therefore opt-in (FT_TEST_EXPERIMENTAL=1): the chunk-pipelined forward and BPTT of lstm layers 0/1
-(FT_PIPE_FWD=1 / FT_PIPE_BWD=1) must reproduce the default schedule bit for bit -- same kernels' arithmetic, different
-launch granularity.  The switch is read once per process by the library, so the pipelined run happens in a child process."""
+"""GPU: the chunk-pipelined forward and BPTT of lstm layers 0/1 (FT_PIPE_FWD=1 / FT_PIPE_BWD=1, DESIGN.md 4.2: two 64-CTA
+recurrences one chunk apart) must reproduce the one-launch-per-layer schedule bit for bit -- same kernel, same arithmetic,
+different step ranges per launch.  The switch is read once per process by the library, so each run is a child process."""
 import os
 import subprocess
 import sys
@@ -10,8 +10,7 @@ import torch
 
 from conftest import ROOT
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FT_TEST_EXPERIMENTAL") != "1", reason="experimental path: set FT_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 CHILD = r'''
 import sys, torch

@@ -4,8 +4,6 @@ import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import profile, ProfilerActivity
-sys.argv = [sys.argv[0]]
-import bench
 from flowtron_b200 import synth
 from flowtron_b200.flowtron import Flowtron, FlowtronLoss
 
@@ -18,7 +16,9 @@ if FUSED:
     opt = RAdam(model.parameters(), lr=1e-3, weight_decay=1e-6)
 else:
     opt = torch.optim.RAdam(model.parameters(), lr=1e-3, weight_decay=1e-6)
-batch, L = bench.make_batch(cfg, 32, 1000, 1234)
+_ol, _il = synth.ljs_like_lengths(32, 1000, 1234)
+L = int(_il.max())
+batch = synth.synth_batch(32, 1000, L, cfg, 1234, out_lens=_ol.tolist(), in_lens=_il.tolist(), with_prior=True, logmel_stats=True)
 d = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
 
 def step():
