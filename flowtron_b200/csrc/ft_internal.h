@@ -57,6 +57,8 @@ int launch_grad_scale(const float* a, long long na, const float* b, long long nb
                       long long ne = 0);   // scale2[0] = S (power of two) from max|a..e|, scale2[1] = 1/S
 int launch_prep_mel(const float* mel, const int* lens, int T, int B, int M, int reversed, void* mel_in16, float* mel_flow, cudaStream_t st);
 int launch_gate_fwd(const void* d16, long long ldd, int K, const float* wg, const float* bg, long long R, float* gate, cudaStream_t st);
+int launch_gate_fwd_f32(const float* h32, long long ldh, int H, const float* c32, long long ldc, int A, const float* wg,
+                        const float* bg, long long R, float* gate, cudaStream_t st);
 int launch_gate_bwd(const void* d16, long long ldd, int K, const float* wg, const float* dgate, long long R, float* dd,
                     long long lddd, float* dwg, float* dbg, const float* scale, cudaStream_t st);
 int launch_affine_fwd(const float* o, const float* mel_flow, const int* lens, int T, int B, int M, int reversed, float* z,

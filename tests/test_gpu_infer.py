@@ -101,7 +101,9 @@ def test_forced_alignments_attns_argument():
         # attention_weights are returned in flow-application order (last flow first); attns is indexed per flow
         attns = [torch.stack([a[0, 0] for a in aw]) for aw in reversed(attn0)]          # per flow [T, L]
         mel1, attn1 = m.infer(res.cuda(), spk.cuda(), text.cuda(), attns=attns)
-        rolled = [a.roll(1, dims=1) for a in attns]
+        rolled = [torch.zeros_like(a) for a in attns]               # a very different alignment: everything on the last token
+        for a in rolled:
+            a[:, -1] = 1.0
         mel2, _ = m.infer(res.cuda(), spk.cuda(), text.cuda(), attns=rolled)
         ref2, _ = O.flowtron_infer(synth.synth_params(cfg, 17), res, spk, text, attns=[a.cpu() for a in rolled])
     torch.cuda.synchronize()
@@ -109,7 +111,8 @@ def test_forced_alignments_attns_argument():
     assert (mel1 - mel0).abs().max().item() <= 1e-5 * mel0.abs().max().item()
     for a, b in zip(attn0, attn1):
         assert torch.equal(torch.stack(a), torch.stack(b))
-    assert (mel2 - mel0).abs().max().item() > 1e-3
     err = (mel2.cpu() - ref2).abs().max().item() / ref2.abs().max().item()
-    record_parity("infer_forced_attns", {"mel": err})
+    moved = (mel2 - mel0).abs().max().item() / ref2.abs().max().item()
+    record_parity("infer_forced_attns", {"mel": err, "changed_by": moved})
     assert err <= 1e-3, err
+    assert moved > 3 * err, (moved, err)            # the forced alignment is really used
