@@ -91,8 +91,9 @@ def test_encoder_matches_oracle_restatement():
 
 
 def test_default_switches_are_the_validated_configuration(monkeypatch):
-    """The round-1 GPU validation (profiles/r1_final2_*) ran with: encoder overlap ON, two-stream BiLSTM OFF, fused
-    optimizer OFF, layer pipeline OFF.  Anything else is opt-in through the environment."""
+    """The GPU validation of record (profiles/r2_*) ran with: encoder overlap ON, two-stream BiLSTM OFF, fused optimizer
+    OFF, layer pipeline ON (forward and BPTT), CUDA-graph step ON in bench.py.  Anything else is opt-in through the
+    environment."""
     import flowtron_b200.flowtron as F
     if "FT_ENC_OVERLAP" not in os.environ:                 # class attribute, read at import
         assert F.Flowtron.overlap_encoder is True
@@ -101,5 +102,6 @@ def test_default_switches_are_the_validated_configuration(monkeypatch):
     src = open(os.path.join(ROOT, "bench.py")).read()
     assert 'os.environ.get("FT_FUSED_OPT", "0")' in src
     csrc = open(os.path.join(ROOT, "flowtron_b200", "csrc", "ar_step.cu")).read()
-    assert 'getenv("FT_PIPE_FWD"); v = (e && atoi(e) != 0) ? 1 : 0' in csrc
-    assert 'getenv("FT_PIPE_BWD"); v = (e && atoi(e) != 0) ? 1 : 0' in csrc
+    assert 'getenv("FT_PIPE_FWD"); v = (!e || atoi(e) != 0) ? 1 : 0' in csrc
+    assert 'getenv("FT_PIPE_BWD"); v = (!e || atoi(e) != 0) ? 1 : 0' in csrc
+    assert 'os.environ.get("FT_GRAPH", "1")' in src
