@@ -13,6 +13,8 @@
 // Used for every non-recurrent contraction on the Flowtron hot path (LSTM input projections
 // flowtron.py:654-655, attention Q/K/V projections :568-571, DenseLayer :461-464, 1x1 conv :768, and
 // all their dgrad/wgrad counterparts).
+#include <cstdlib>
+
 #include "ptx.cuh"
 #include "ft_internal.h"
 
@@ -216,6 +218,184 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (warp == 1) tmem_dealloc<BN>(tmem_base);
 }
 
+// ================================================================================================ v2: persistent kernel
+// One CTA per SM walks a static list of 128 x BN output tiles (BN = 256, or 128 for narrow outputs):
+//   * a 4-stage (BN = 256: 48 KB per stage) / 6-stage (BN = 128) TMA ring feeds one elected thread issuing
+//     tcgen05.mma 128 x BN x 16: one stage is 512 (256) tensor-core clocks, so the ring covers ~2000 clocks of TMA latency
+//     (the 3-stage 128x128 ring of v1 covered 768: its K <= 1024 shapes ran at 24-43 % of peak), and a 128 x 256 tile reads
+//     96 B of shared memory per tensor-core clock instead of the 128 B (the SM's whole bandwidth) of a 128 x 128 tile;
+//   * TWO accumulators in TMEM (2 x BN columns): the four epilogue warps drain tile i while the MMA warp already
+//     accumulates tile i+1, so the epilogue (and the per-CTA start-up v1 paid on every tile) leaves the critical path;
+//   * epilogue: tcgen05.ld 32 columns -> a 32x33 shared-memory transpose per warp -> lane = column: alpha, bias(es), tanh /
+//     tanh' , beta and the stores are issued row by row, 128 contiguous bytes per warp instruction.
+constexpr int G2_THREADS = 192;
+constexpr int G2_STAGE_FLOATS = 32 * 33;                       // per-warp transpose tile
+template <int BN_> struct G2Cfg {
+    static constexpr int STAGE_BYTES = (BM + BN_) * 128;
+    static constexpr int STAGES = BN_ == 256 ? 4 : 6;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 4 * G2_STAGE_FLOATS * 4 + 256 + 1024;
+};
+
+template <bool kTf32, int BN_>
+__global__ void __launch_bounds__(G2_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p, int tiles_n, int n_tiles) {
+    using C = G2Cfg<BN_>;
+    constexpr int ST = C::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* stage_all = reinterpret_cast<float*>(smem + ST * C::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + 4 * G2_STAGE_FLOATS);
+    uint64_t* full = bars;                 // [ST]
+    uint64_t* empty = bars + ST;           // [ST]
+    uint64_t* tfull = bars + 2 * ST;       // [2] accumulator ready
+    uint64_t* tempty = bars + 2 * ST + 2;  // [2] accumulator drained (4 arrivals: one per epilogue warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int ELT = kTf32 ? 4 : 2;
+    constexpr int BK = 128 / ELT;
+    constexpr int UK = 32 / ELT;
+    const int num_kb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
+        mbar_init(&tempty[0], 4); mbar_init(&tempty[1], 4);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<2 * BN_>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer (warp-uniform loop, one elected lane issues)
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % ST, ph = (it / ST) & 1;
+                mbar_wait(&empty[s], ph ^ 1, p.status, 111);
+                uint8_t* a = smem + s * C::STAGE_BYTES;
+                uint8_t* b = a + TILE_BYTES;
+                if (elect_one()) {
+                    mbar_expect_tx(&full[s], C::STAGE_BYTES);
+                    if (!p.a_mn) {
+                        tma_load_2d(a, &tmA, &full[s], kb * BK, tile_m * BM);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / BK; ++j)
+                            tma_load_2d(a + j * (BK * 128), &tmA, &full[s], tile_m * BM + j * BK, kb * BK);
+                    }
+                    if (!p.b_mn) {
+                        tma_load_2d(b, &tmB, &full[s], kb * BK, tile_n * BN_);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN_ / BK; ++j)
+                            tma_load_2d(b + j * (BK * 128), &tmB, &full[s], tile_n * BN_ + j * BK, kb * BK);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer
+        const uint32_t idesc = umma_idesc(BM, BN_, p.a_fmt, p.b_fmt, p.a_mn, p.b_mn);
+        const uint32_t tmem_d0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint64_t da0 = p.a_mn ? umma_smem_desc(smem_u32(smem), BK * 128, 1024) : umma_smem_desc(smem_u32(smem), 16, 1024);
+        const uint64_t db0 = p.b_mn ? umma_smem_desc(smem_u32(smem + TILE_BYTES), BK * 128, 1024)
+                                    : umma_smem_desc(smem_u32(smem + TILE_BYTES), 16, 1024);
+        const uint64_t ka = p.a_mn ? (UK * 128) >> 4 : 2, kbs = p.b_mn ? (UK * 128) >> 4 : 2;
+        int it = 0, tc = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tc) {
+            const int buf = tc & 1, bph = (tc >> 1) & 1;
+            mbar_wait(&tempty[buf], bph ^ 1, p.status, 112);          // the epilogue drained this accumulator (first use: free)
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_d0 + buf * BN_;
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % ST, ph = (it / ST) & 1;
+                mbar_wait(&full[s], ph, p.status, 113);
+                tc_fence_after();
+                const uint64_t so = static_cast<uint64_t>(s) * (C::STAGE_BYTES >> 4);
+                const uint64_t da = da0 + so, db = db0 + so;
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k) {
+                        const uint32_t acc = (kb | k) != 0;
+                        if (kTf32) umma_tf32(tmem_d, da + k * ka, db + k * kbs, idesc, acc);
+                        else       umma_f16(tmem_d, da + k * ka, db + k * kbs, idesc, acc);
+                    }
+                    umma_commit(&empty[s]);
+                    if (kb == num_kb - 1) umma_commit(&tfull[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
+        const int q = warp & 3;
+        float* stg = stage_all + q * G2_STAGE_FLOATS;
+        const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
+        int tc = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tc) {
+            const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+            const int buf = tc & 1, bph = (tc >> 1) & 1;
+            mbar_wait(&tfull[buf], bph, p.status, 114);
+            tc_fence_after();
+            const int ncols = min(BN_, p.N - tile_n * BN_);
+            const long long m0 = static_cast<long long>(tile_m) * BM + q * 32;
+            const int rows = static_cast<int>(min(static_cast<long long>(32), p.M - m0));     // may be <= 0
+            const int nchunks = (ncols + 31) >> 5;
+#pragma unroll 1
+            for (int c = 0; c < nchunks; ++c) {
+                float v[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN_ + c * 32, v);
+                tmem_ld_wait();
+                if (c == nchunks - 1) {                              // everything this warp needs is in registers: hand the
+                    tc_fence_before();                               // accumulator back to the MMA warp before the stores
+                    if (lane == 0) mbar_arrive(&tempty[buf]);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+                __syncwarp();
+                const int n = tile_n * BN_ + c * 32 + lane;           // lane = column
+                const bool col_ok = c * 32 + lane < ncols;
+                float bsum = 0.f;
+                if (col_ok) {
+                    if (p.bias) bsum += __ldg(p.bias + n);
+                    if (p.bias2) bsum += __ldg(p.bias2 + n);
+                }
+#pragma unroll 4
+                for (int r = 0; r < rows; ++r) {
+                    const long long m = m0 + r;
+                    float x = fmaf(stg[r * 33 + lane], alpha, bsum);
+                    if (p.act == 1) x = tanh_f(x);
+                    if (col_ok) {
+                        if (p.act == 2) { const float y = __half2float(p.aux16[m * p.ldaux + n]); x *= (1.f - y * y); }
+                        if (p.C32) {
+                            float* dst = p.C32 + m * p.ldc32 + n;
+                            if (p.beta) x += *dst;
+                            *dst = x;
+                        }
+                        if (p.C16) {
+                            if (p.c16_fmt == 0) reinterpret_cast<__half*>(p.C16)[m * p.ldc16 + n] = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+                            else reinterpret_cast<__nv_bfloat16*>(p.C16)[m * p.ldc16 + n] = __float2bfloat16_rn(x);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            if (nchunks == 0) { tc_fence_before(); if (lane == 0) mbar_arrive(&tempty[buf]); }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<2 * BN_>(tmem_base);
+}
+
 // ------------------------------------------------------------------------------------------------ host
 static PFN_encodeTiled g_encode = nullptr;
 
@@ -270,6 +450,39 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
     p.bias = g.bias; p.bias2 = g.bias2; p.act = g.act; p.alpha_ptr = g.alpha_ptr; p.aux16 = static_cast<const __half*>(g.aux16); p.ldaux = g.ldaux; p.beta = g.beta; p.alpha = g.alpha;
     p.C32 = g.C32; p.ldc32 = g.ldc32; p.C16 = g.C16; p.ldc16 = g.ldc16; p.c16_fmt = g.c16_fmt;
     p.status = ft_status_word();
+    static int use_v1 = -1;              // FT_GEMM_V1=1: the round-1 non-persistent 128x128 kernel (A/B comparisons)
+    if (use_v1 < 0) { const char* e = getenv("FT_GEMM_V1"); use_v1 = (e && atoi(e) != 0) ? 1 : 0; }
+    if (!use_v1) {
+        static int sms = 0;
+        if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+        const bool wide = (g.N % 256 == 0) || g.N > 1024;
+        const int bn = wide ? 256 : 128;
+        const int tiles_n = (g.N + bn - 1) / bn, tiles_m = (g.M + BM - 1) / BM;
+        const long long n_tiles_ll = static_cast<long long>(tiles_n) * tiles_m;
+        if (n_tiles_ll > 0x7fffffff) return ft_set_error("gemm: too many tiles");
+        const int n_tiles = static_cast<int>(n_tiles_ll);
+        const int grid2 = n_tiles < sms ? n_tiles : sms;
+        // operand boxes: K-major A {BK, 128}; K-major B {BK, bn}; MN-major boxes are {BK, BK} as in v1
+        if (!g.b_mn && bn == 256) { if (make_tmap_2d(&tmB, g.B, g.b_fmt, g.N, g.K, g.ldb, BK, 256)) return -1; }
+        static bool attr2 = false;
+        if (!attr2) {
+            cudaFuncSetAttribute(gemm2_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<256>::SMEM);
+            cudaFuncSetAttribute(gemm2_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<128>::SMEM);
+            cudaFuncSetAttribute(gemm2_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<256>::SMEM);
+            cudaFuncSetAttribute(gemm2_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<128>::SMEM);
+            attr2 = true;
+        }
+        TimeScope ts(g.a_mn ? "gemm_wgrad" : (g.b_mn ? "gemm_dgrad" : "gemm_fwd"), g.M, g.N, g.K, st);
+        if (tf32) {
+            if (wide) gemm2_kernel<true, 256><<<grid2, G2_THREADS, G2Cfg<256>::SMEM, st>>>(tmA, tmB, p, tiles_n, n_tiles);
+            else      gemm2_kernel<true, 128><<<grid2, G2_THREADS, G2Cfg<128>::SMEM, st>>>(tmA, tmB, p, tiles_n, n_tiles);
+        } else {
+            if (wide) gemm2_kernel<false, 256><<<grid2, G2_THREADS, G2Cfg<256>::SMEM, st>>>(tmA, tmB, p, tiles_n, n_tiles);
+            else      gemm2_kernel<false, 128><<<grid2, G2_THREADS, G2Cfg<128>::SMEM, st>>>(tmA, tmB, p, tiles_n, n_tiles);
+        }
+        ft_count_launch(1);
+        return ft_check_launch("gemm2_kernel");
+    }
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
     static bool attr_set = false;
     if (!attr_set) {

@@ -45,8 +45,9 @@ def import_flowtron():
 
     F.get_mask_from_lengths = _mask
     F.get_gate_mask_from_lengths = _mask
-    if not torch.cuda.is_available():
-        torch.cuda.FloatTensor = torch.FloatTensor
+    # the reference is only ever RUN ON THE CPU here (fixtures, CPU baseline): AR_Step.infer allocates its first frame as
+    # torch.cuda.FloatTensor (flowtron.py:785), which on a GPU box would land on cuda:0 while the model sits on the host
+    torch.cuda.FloatTensor = torch.FloatTensor
     return F
 
 
