@@ -224,11 +224,11 @@ def run_train(args):
     model.n_streams = args.streams
     crit = FlowtronLoss(sigma=1.0, gate_loss=True, use_ctc_loss=False)
     use_graph = os.environ.get("FT_GRAPH", "1") != "0" and not args.profile and args.streams == 1
-    fused_opt = os.environ.get("FT_FUSED_OPT", "0") != "0" and not use_graph
+    fused_opt = os.environ.get("FT_FUSED_OPT", "0") != "0"
     # train.py:231-252 order: optimizer first, then the all-reduce wrapper
     if fused_opt:
         from flowtron_b200.radam import RAdam
-        opt = RAdam(model.parameters(), lr=1e-3, weight_decay=1e-6)
+        opt = RAdam(model.parameters(), lr=1e-3, weight_decay=1e-6, capturable=use_graph)
     else:
         opt = torch.optim.RAdam(model.parameters(), lr=1e-3, weight_decay=1e-6, capturable=use_graph, foreach=True)
     if world > 1:

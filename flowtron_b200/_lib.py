@@ -120,6 +120,11 @@ def _declare(L):
     L.ft_radam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_double, c_double, c_double, c_double,
                                 c_double, c_int, c_void_p, c_void_p]
     L.ft_radam_step.restype = c_int
+    L.ft_radam_step_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_double, c_double, c_double, c_double,
+                                    c_double, c_void_p, c_void_p, c_void_p]
+    L.ft_radam_step_dev.restype = c_int
+    L.ft_step_increment.argtypes = [c_void_p, c_void_p]
+    L.ft_step_increment.restype = c_int
 
 
 def check(rc: int, what: str = ""):
@@ -383,3 +388,14 @@ def attn_ctc_loss(logprob, in_lens, out_lens, time_reversed, blank_logprob, cost
     scratch = scratch_buffer(int(lib().ft_attn_ctc_scratch_bytes(B, T, L)), logprob.device)
     check(lib().ft_attn_ctc_loss(ptr(logprob), ptr(in_lens), ptr(out_lens), B, T, L, 1 if time_reversed else 0,
                                  float(blank_logprob), ptr(cost), ptr(dlogprob), ptr(scratch), stream_ptr()), "ft_attn_ctc_loss")
+
+
+def radam_step_dev_raw(p_ptr, g_ptr, m_ptr, v_ptr, n, beta1, beta2, eps, weight_decay, lr, step_dev, coef_ptr=0):
+    """Capturable update: the step count is read from the int32 CUDA tensor ``step_dev`` by the kernel."""
+    check(lib().ft_radam_step_dev(c_void_p(p_ptr), c_void_p(g_ptr), c_void_p(m_ptr), c_void_p(v_ptr), int(n), float(beta1),
+                                  float(beta2), float(eps), float(weight_decay), float(lr), ptr(step_dev),
+                                  c_void_p(coef_ptr) if coef_ptr else None, stream_ptr()), "ft_radam_step_dev")
+
+
+def step_increment(step_dev):
+    check(lib().ft_step_increment(ptr(step_dev), stream_ptr()), "ft_step_increment")

@@ -104,6 +104,64 @@ radam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     }
 }
 
+// Capturable form (CUDA graphs): the step count lives on the device, so N_sma / step_size (radam.py:87-107) are evaluated by
+// the kernel (one thread per block, fp64 like the Python floats of the reference) instead of being baked into the launch.
+struct RAdamHyper { double beta1, beta2, eps, wd, lr; };
+
+__global__ void __launch_bounds__(OPT_THREADS)
+radam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                 RAdamHyper h, const int* __restrict__ step_dev, const float* __restrict__ grad_coef) {
+    __shared__ RAdamScalars sa;
+    if (threadIdx.x == 0) {
+        const double t = static_cast<double>(step_dev[0] + 1);           // this update is step t (state['step'] += 1 first, :81)
+        const double beta2_t = pow(h.beta2, t);
+        const double n_sma_max = 2.0 / (1.0 - h.beta2) - 1.0;
+        const double n_sma = n_sma_max - 2.0 * t * beta2_t / (1.0 - beta2_t);
+        double step_size;
+        if (n_sma >= 5.0)
+            step_size = h.lr * sqrt((1.0 - beta2_t) * (n_sma - 4.0) / (n_sma_max - 4.0) * (n_sma - 2.0) / n_sma * n_sma_max /
+                                    (n_sma_max - 2.0)) / (1.0 - pow(h.beta1, t));
+        else
+            step_size = h.lr / (1.0 - pow(h.beta1, t));
+        RAdamScalars a;
+        a.beta1 = static_cast<float>(h.beta1); a.beta2 = static_cast<float>(h.beta2);
+        a.omb1 = static_cast<float>(1.0 - h.beta1); a.omb2 = static_cast<float>(1.0 - h.beta2); a.eps = static_cast<float>(h.eps);
+        a.wd_lr = static_cast<float>(h.wd * h.lr); a.step_size = static_cast<float>(step_size); a.use_denom = n_sma >= 5.0;
+        sa = a;
+    }
+    __syncthreads();
+    const RAdamScalars a = sa;
+    const float gc = grad_coef ? grad_coef[0] : 1.0f;
+    const long long stride = static_cast<long long>(gridDim.x) * OPT_THREADS;
+    const long long i0 = static_cast<long long>(blockIdx.x) * OPT_THREADS + threadIdx.x;
+    const bool al = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                      reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+    long long done = 0;
+    if (al) {
+        const long long n4 = n >> 2;
+        float4* p4 = reinterpret_cast<float4*>(p);
+        const float4* g4 = reinterpret_cast<const float4*>(g);
+        float4* m4 = reinterpret_cast<float4*>(m);
+        float4* v4 = reinterpret_cast<float4*>(v);
+        for (long long i = i0; i < n4; i += stride) {
+            float4 pp = p4[i], mm = m4[i], vv = v4[i];
+            const float4 gg = g4[i];
+            radam_one(pp.x, gg.x * gc, mm.x, vv.x, a);
+            radam_one(pp.y, gg.y * gc, mm.y, vv.y, a);
+            radam_one(pp.z, gg.z * gc, mm.z, vv.z, a);
+            radam_one(pp.w, gg.w * gc, mm.w, vv.w, a);
+            p4[i] = pp; m4[i] = mm; v4[i] = vv;
+        }
+        done = n4 << 2;
+    }
+    for (long long i = done + i0; i < n; i += stride) {
+        float pp = p[i], mm = m[i], vv = v[i];
+        radam_one(pp, g[i] * gc, mm, vv, a);
+        p[i] = pp; m[i] = mm; v[i] = vv;
+    }
+}
+__global__ void step_increment_kernel(int* step_dev) { step_dev[0] += 1; }
+
 static int grid_1d(long long work_items, int cap) {
     long long b = (work_items + OPT_THREADS - 1) / OPT_THREADS;
     if (b < 1) b = 1;
@@ -146,6 +204,30 @@ int ft_radam_step(float* p, const float* g, float* m, float* v, long long n, dou
     ft::radam_kernel<<<ft::grid_1d((n + 3) / 4, 148 * 8), ft::OPT_THREADS, 0, st>>>(p, g, m, v, n, a, grad_coef);
     ft::ft_count_launch(1);
     return ft::ft_check_launch("radam_kernel");
+}
+
+}  // extern "C"
+
+extern "C" {
+
+/* RAdam update with the step count on the device (graph-capturable): uses step_dev[0] + 1 as this update's step; the caller
+ * bumps the counter once per optimizer step with ft_step_increment after every segment has been updated. */
+int ft_radam_step_dev(float* p, const float* g, float* m, float* v, long long n, double beta1, double beta2, double eps,
+                      double weight_decay, double lr, const int* step_dev, const float* grad_coef, void* stream) {
+    if (!p || !g || !m || !v || !step_dev || n < 0) return ft::ft_set_error("ft_radam_step_dev: bad argument");
+    if (n == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ft::RAdamHyper h{beta1, beta2, eps, weight_decay, lr};
+    ft::radam_dev_kernel<<<ft::grid_1d((n + 3) / 4, 148 * 8), ft::OPT_THREADS, 0, st>>>(p, g, m, v, n, h, step_dev, grad_coef);
+    ft::ft_count_launch(1);
+    return ft::ft_check_launch("radam_dev_kernel");
+}
+
+int ft_step_increment(int* step_dev, void* stream) {
+    if (!step_dev) return ft::ft_set_error("ft_step_increment: NULL argument");
+    ft::step_increment_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(step_dev);
+    ft::ft_count_launch(1);
+    return ft::ft_check_launch("step_increment_kernel");
 }
 
 }  // extern "C"

@@ -114,9 +114,13 @@ class _Flat:
 class RAdam(Optimizer):
     """RAdam optimizer (fused, flat-buffer).  Signature: radam.py:28-29."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, capturable=False):
+        """``capturable=True`` (extension, like torch.optim's): the step count lives on the device and the kernels derive
+        N_sma / step_size from it, so ``step()`` can be captured in a CUDA graph and replayed; requires that every
+        trainable parameter of a group receives a gradient every step (one step count per group)."""
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
+        self.capturable = bool(capturable)
         self._flats = []
         for group in self.param_groups:
             ps = list(group['params'])
@@ -134,6 +138,7 @@ class RAdam(Optimizer):
         self._partials = None
         self._norm_coef = None
         self._pending_coef = None
+        self._step_dev = [torch.zeros(1, dtype=torch.int32, device=f.p.device) for f in self._flats] if self.capturable else None
         self._built = True
 
     def add_param_group(self, param_group):
@@ -241,6 +246,22 @@ class RAdam(Optimizer):
             with torch.enable_grad():
                 loss = closure()
         coef_ptr = self._pending_coef.data_ptr() + 4 if self._pending_coef is not None else 0
+        if self.capturable:
+            for gi, (group, flat) in enumerate(zip(self.param_groups, self._flats)):
+                segs = self._segments(flat)
+                if not segs:
+                    continue
+                if len({st for _, _, _, st in segs}) != 1 or any(p.grad is None for p in flat.params if p.requires_grad):
+                    raise FlowtronB200Error("flowtron_b200.RAdam(capturable=True) needs one step count per group: every "
+                                            "trainable parameter must receive a gradient every step")
+                beta1, beta2 = group['betas']
+                for off, gptr, n, _ in segs:
+                    _lib.radam_step_dev_raw(flat.p.data_ptr() + 4 * off, gptr, flat.m.data_ptr() + 4 * off,
+                                            flat.v.data_ptr() + 4 * off, n, beta1, beta2, group['eps'], group['weight_decay'],
+                                            group['lr'], self._step_dev[gi], coef_ptr)
+                _lib.step_increment(self._step_dev[gi])
+            self._pending_coef = None
+            return loss
         for group, flat in zip(self.param_groups, self._flats):
             segs = self._segments(flat)
             if not segs:
@@ -260,6 +281,22 @@ class RAdam(Optimizer):
         self._pending_coef = None
         return loss
 
+    def _sync_steps(self):
+        """capturable: bring the Python-side ``state[p]['step']`` in line with the device counters (one host sync; only
+        when the state is inspected or saved -- graph replays advance the device counter without running Python)."""
+        if not self.capturable:
+            return
+        for sd, flat in zip(self._step_dev, self._flats):
+            n = int(sd.item())
+            for p in flat.params:
+                if p.requires_grad:
+                    self.state[p]['step'] = n
+            flat.seg_key = None
+
+    def state_dict(self):
+        self._sync_steps()
+        return super().state_dict()
+
     def load_state_dict(self, state_dict):
         """Accepts the reference's optimizer checkpoints (train.py:123): moments are copied into the flat buffers."""
         super().load_state_dict(state_dict)
@@ -275,3 +312,7 @@ class RAdam(Optimizer):
                 st['exp_avg'], st['exp_avg_sq'] = mv, vv
                 st['step'] = int(st['step'])
             flat.seg_key = None
+        if self.capturable:
+            for sd, flat in zip(self._step_dev, self._flats):
+                steps = {self.state[p]['step'] for p in flat.params if p.requires_grad}
+                sd.fill_(max(steps) if steps else 0)

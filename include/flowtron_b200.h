@@ -145,6 +145,12 @@ int ft_sumsq_partials(const float* x, long long n, float* partials, void* stream
 int ft_clip_coef(const float* partials, int n_partials, float max_norm, float* norm_coef, void* stream);
 int ft_radam_step(float* p, const float* g, float* m, float* v, long long n, double beta1, double beta2, double eps,
                   double weight_decay_lr, double step_size, int use_denom, const float* grad_coef, void* stream);
+/* CUDA-graph-capturable form: the step count lives on the device (step_dev[0] = updates done so far); the kernel derives
+ * N_sma / step_size from step_dev[0] + 1 itself (fp64), so a captured step replays with the right schedule.  Call
+ * ft_step_increment once after all segments of an optimizer step. */
+int ft_radam_step_dev(float* p, const float* g, float* m, float* v, long long n, double beta1, double beta2, double eps,
+                      double weight_decay, double lr, const int* step_dev, const float* grad_coef, void* stream);
+int ft_step_increment(int* step_dev, void* stream);
 
 /* AR_Step.infer (flowtron.py:775-828): sequential inverse of one flow for all T frames in ONE persistent launch.
  *   residual [T,B,M] f32 in flow-time order (the caller flips for AR_Back_Step, :629-642), text [L,B,E] f32,

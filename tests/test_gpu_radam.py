@@ -83,3 +83,62 @@ def test_radam_on_flowtron_model_matches_oracle():
         for n, p in model.named_parameters():
             torch.testing.assert_close(p.detach().cpu(), ref_p[n], rtol=1e-5, atol=1e-7, msg=lambda m, n=n: f"{n}: {m}")
     assert torch.isfinite(nll).all()
+
+
+def test_radam_capturable_replayed_from_a_cuda_graph_matches_reference():
+    """capturable=True: clip + step captured ONCE in a CUDA graph and replayed for every step of the reference trajectory
+    (steps 1-5 take the N_sma < 5 branch, 6+ the adaptive one: the kernel must derive both from the device step count)."""
+    from flowtron_b200.radam import RAdam
+    g = _golden()
+    ps = [torch.nn.Parameter(torch.from_numpy(g[f"p0_{i}"]).cuda()) for i in range(3)]
+    opt = RAdam(ps, lr=1e-3, weight_decay=1e-6, capturable=True)
+    norm_out = torch.zeros((), device="cuda")
+
+    def body():
+        total = opt.clip_grad_norm_(float(g["max_norm"]))
+        opt.step()
+        norm_out.copy_(total)
+
+    s_ = torch.cuda.Stream()
+    s_.wait_stream(torch.cuda.current_stream())
+    graph = None
+    for s in range(int(g["n_steps"])):
+        for i, p in enumerate(ps):
+            p.grad.copy_(torch.from_numpy(g[f"g{s}_{i}"]).cuda())
+        if s == 0:                                   # eager first step (warm-up), then capture, then replays only
+            body()
+        elif graph is None:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body()
+            graph.replay()
+        else:
+            graph.replay()
+        torch.cuda.synchronize()
+        assert abs(float(norm_out) - float(g[f"norm{s}"])) <= 1e-5 * float(g[f"norm{s}"])
+        for i, p in enumerate(ps):
+            torch.testing.assert_close(p.detach().cpu(), torch.from_numpy(g[f"p{s + 1}_{i}"]), rtol=1e-5, atol=1e-7)
+    sd = opt.state_dict()
+    assert all(int(v["step"]) == int(g["n_steps"]) for v in sd["state"].values())
+
+
+def test_radam_survives_parameter_rehoming_by_cudnn():
+    """nn.LSTM.flatten_parameters() (called by cuDNN paths, e.g. Encoder.infer in the reference) moves weights
+    out of the flat buffer; the optimizer must re-home them instead of updating a dead copy."""
+    from flowtron_b200.radam import RAdam
+    torch.manual_seed(0)
+    lstm = torch.nn.LSTM(16, 8, 1, batch_first=True, bidirectional=True).cuda()
+    opt = RAdam(lstm.parameters(), lr=1e-2)
+    x = torch.randn(4, 5, 16, device="cuda")
+
+    def one_step():
+        opt.zero_grad()
+        lstm(x)[0].pow(2).sum().backward()
+        opt.step()
+    one_step()
+    w0 = lstm.weight_hh_l0.detach().clone()
+    lstm.flatten_parameters()                          # cuDNN re-packs: p.data now lives in a fresh buffer
+    one_step()
+    assert not torch.equal(lstm.weight_hh_l0.detach(), w0), "the live weights must keep training"
+    base = opt._flats[0].p.data_ptr()
+    assert all(p.data_ptr() == base + 4 * off for p, off in zip(opt._flats[0].params, opt._flats[0].offsets))

@@ -31,12 +31,16 @@ for s in $SECS; do case $s in
 tests)
   timeout 900 python -m pytest tests -q -m gpu -rfE --tb=short -p no:cacheprovider > $O/${TAG}_tests.txt 2>&1; echo "pytest rc=$?"; tail -25 $O/${TAG}_tests.txt ;;
 train)
-  bench train_eager FT_GRAPH=0 -- --steps 5 --warmup 3 --no-cpu-baseline
-  bench train_graph FT_GRAPH=1 -- --steps 5 --warmup 3 --no-cpu-baseline
-  bench train_pipe FT_GRAPH=0 FT_PIPE_FWD=1 FT_PIPE_BWD=1 -- --steps 5 --warmup 3 --no-cpu-baseline
-  bench train_pipe_graph FT_GRAPH=1 FT_PIPE_FWD=1 FT_PIPE_BWD=1 -- --steps 5 --warmup 3 --no-cpu-baseline
-  bench train_pipe200 FT_GRAPH=0 FT_PIPE_FWD=1 FT_PIPE_BWD=1 FT_PIPE_CHUNK=200 -- --steps 5 --warmup 3 --no-cpu-baseline
-  bench train_pipefwd FT_GRAPH=0 FT_PIPE_FWD=1 FT_PIPE_BWD=0 -- --steps 5 --warmup 3 --no-cpu-baseline ;;
+  bench train_default X=1 -- --steps 5 --warmup 3 --no-cpu-baseline
+  bench train_gemm_v1 FT_GEMM_V1=1 -- --steps 5 --warmup 3 --no-cpu-baseline
+  bench train_fused_opt FT_FUSED_OPT=1 -- --steps 5 --warmup 3 --no-cpu-baseline
+  bench train_chunk50 FT_PIPE_CHUNK=50 -- --steps 5 --warmup 3 --no-cpu-baseline
+  bench train_chunk150 FT_PIPE_CHUNK=150 -- --steps 5 --warmup 3 --no-cpu-baseline
+  bench train_eager FT_GRAPH=0 -- --steps 5 --warmup 3 --no-cpu-baseline ;;
+cfg3)
+  bench train_cfg3 X=1 -- --config 3 --steps 5 --warmup 3 --no-cpu-baseline ;;
+tlgraph)
+  timeout 300 python tools/timeline_graph.py > $O/${TAG}_timeline_graph.txt 2>&1; echo "timeline_graph rc=$?"; grep -v Warn $O/${TAG}_timeline_graph.txt | head -60 ;;
 infer)
   bench infer_b1 X=1 -- --workload infer --batch 1 --steps 3 --warmup 3 --no-cpu-baseline
   bench infer_b16 X=1 -- --workload infer --batch 16 --steps 3 --warmup 3 --no-cpu-baseline ;;
