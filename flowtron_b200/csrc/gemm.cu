@@ -39,6 +39,7 @@ struct GemmParams {
     float* C32; long long ldc32;
     void* C16; long long ldc16; int c16_fmt;   // 0 f16, 1 bf16
     int* status;
+    int splitk = 1;            // v2 only: K is cut into `splitk` ranges, partial tiles are atomically added into a zeroed C32
 };
 
 template <bool kTf32>
@@ -226,10 +227,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 //     96 B of shared memory per tensor-core clock instead of the 128 B (the SM's whole bandwidth) of a 128 x 128 tile;
 //   * TWO accumulators in TMEM (2 x BN columns): the four epilogue warps drain tile i while the MMA warp already
 //     accumulates tile i+1, so the epilogue (and the per-CTA start-up v1 paid on every tile) leaves the critical path;
-//   * epilogue: tcgen05.ld 32 columns -> a 32x33 shared-memory transpose per warp -> lane = column: alpha, bias(es), tanh /
-//     tanh' , beta and the stores are issued row by row, 128 contiguous bytes per warp instruction.
+//   * epilogue: tcgen05.ld 32 columns -> a 32x36 shared-memory transpose per warp -> float4 per lane, 4 rows x 128 contiguous
+//     bytes per warp instruction, all loads of a chunk hoisted in front of the arithmetic (details at the epilogue).
 constexpr int G2_THREADS = 192;
-constexpr int G2_STAGE_FLOATS = 32 * 33;                       // per-warp transpose tile
+constexpr int G2_PITCH = 36;                                   // floats: 16-byte aligned rows, conflict-free float4 access
+constexpr int G2_STAGE_FLOATS = 32 * G2_PITCH;                 // per-warp transpose tile
 template <int BN_> struct G2Cfg {
     static constexpr int STAGE_BYTES = (BM + BN_) * 128;
     static constexpr int STAGES = BN_ == 256 ? 4 : 6;
@@ -255,7 +257,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     constexpr int ELT = kTf32 ? 4 : 2;
     constexpr int BK = 128 / ELT;
     constexpr int UK = 32 / ELT;
-    const int num_kb = (p.K + BK - 1) / BK;
+    const int num_kb_all = (p.K + BK - 1) / BK;
+    const int kb_per_split = (num_kb_all + p.splitk - 1) / p.splitk;     // work item w = split * n_tiles + tile
+    const int n_work = n_tiles * p.splitk;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -274,9 +278,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (warp == 0) {
         // ------------------------------------------------ TMA producer (warp-uniform loop, one elected lane issues)
         int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int split = w / n_tiles, tile = w - split * n_tiles;
             const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const int kb0 = split * kb_per_split, kb1 = min(num_kb_all, kb0 + kb_per_split);
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % ST, ph = (it / ST) & 1;
                 mbar_wait(&empty[s], ph ^ 1, p.status, 111);
                 uint8_t* a = smem + s * C::STAGE_BYTES;
@@ -310,12 +316,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                     : umma_smem_desc(smem_u32(smem + TILE_BYTES), 16, 1024);
         const uint64_t ka = p.a_mn ? (UK * 128) >> 4 : 2, kbs = p.b_mn ? (UK * 128) >> 4 : 2;
         int it = 0, tc = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tc) {
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tc) {
+            const int split = w / n_tiles;
+            const int kb0 = split * kb_per_split, kb1 = min(num_kb_all, kb0 + kb_per_split);
             const int buf = tc & 1, bph = (tc >> 1) & 1;
             mbar_wait(&tempty[buf], bph ^ 1, p.status, 112);          // the epilogue drained this accumulator (first use: free)
             tc_fence_after();
             const uint32_t tmem_d = tmem_d0 + buf * BN_;
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % ST, ph = (it / ST) & 1;
                 mbar_wait(&full[s], ph, p.status, 113);
                 tc_fence_after();
@@ -324,23 +332,35 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BK / UK; ++k) {
-                        const uint32_t acc = (kb | k) != 0;
+                        const uint32_t acc = ((kb - kb0) | k) != 0;
                         if (kTf32) umma_tf32(tmem_d, da + k * ka, db + k * kbs, idesc, acc);
                         else       umma_f16(tmem_d, da + k * ka, db + k * kbs, idesc, acc);
                     }
                     umma_commit(&empty[s]);
-                    if (kb == num_kb - 1) umma_commit(&tfull[buf]);
+                    if (kb == kb1 - 1) umma_commit(&tfull[buf]);
                 }
                 __syncwarp();
             }
         }
     } else {
         // ------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
+        // Per 32-column chunk: tcgen05.ld (lane = row) -> 32x36 shared-memory tile (16-byte vector stores, conflict-free per
+        // quarter warp) -> re-read as float4 with lane = (row within a group of 4, 4-column group): one warp instruction
+        // covers 4 rows x 128 contiguous bytes.  All global loads of a chunk (tanh' operand, beta accumulate) are issued
+        // before any arithmetic (8 independent 8/16-byte loads per lane in flight), then alpha / bias / activation and the
+        // 16-byte (fp32) / 8-byte (16-bit) stores.  The first version walked rows with scalar loads and stores (a 600-clock
+        // load latency per row iteration, 256 iterations per tile): 13-43 TFLOP/s on the K <= 640 dgrad shapes.
         const int q = warp & 3;
         float* stg = stage_all + q * G2_STAGE_FLOATS;
         const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
+        const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+        const bool vec_ok = (p.N % 4 == 0) &&
+                            (!p.C32 || (((reinterpret_cast<uintptr_t>(p.C32) & 15) == 0) && (p.ldc32 % 4 == 0))) &&
+                            (!p.C16 || (((reinterpret_cast<uintptr_t>(p.C16) & 7) == 0) && (p.ldc16 % 4 == 0))) &&
+                            (p.act != 2 || (((reinterpret_cast<uintptr_t>(p.aux16) & 7) == 0) && (p.ldaux % 4 == 0)));
         int tc = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tc) {
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tc) {
+            const int tile = w % n_tiles;
             const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
             const int buf = tc & 1, bph = (tc >> 1) & 1;
             mbar_wait(&tfull[buf], bph, p.status, 114);
@@ -359,30 +379,89 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     if (lane == 0) mbar_arrive(&tempty[buf]);
                 }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * G2_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 __syncwarp();
-                const int n = tile_n * BN_ + c * 32 + lane;           // lane = column
-                const bool col_ok = c * 32 + lane < ncols;
-                float bsum = 0.f;
-                if (col_ok) {
-                    if (p.bias) bsum += __ldg(p.bias + n);
-                    if (p.bias2) bsum += __ldg(p.bias2 + n);
-                }
-#pragma unroll 4
-                for (int r = 0; r < rows; ++r) {
-                    const long long m = m0 + r;
-                    float x = fmaf(stg[r * 33 + lane], alpha, bsum);
-                    if (p.act == 1) x = tanh_f(x);
+                const int nb = tile_n * BN_ + c * 32;                 // first column of the chunk
+                if (vec_ok) {
+                    const int n = nb + c4;
+                    const bool col_ok = c * 32 + c4 < ncols;          // N % 4 == 0: the whole 4-group is in or out
+                    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (col_ok) {
-                        if (p.act == 2) { const float y = __half2float(p.aux16[m * p.ldaux + n]); x *= (1.f - y * y); }
-                        if (p.C32) {
-                            float* dst = p.C32 + m * p.ldc32 + n;
-                            if (p.beta) x += *dst;
-                            *dst = x;
+                        if (p.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n)); bsum = t; }
+                        if (p.bias2) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias2 + n)); bsum.x += t.x; bsum.y += t.y; bsum.z += t.z; bsum.w += t.w; }
+                    }
+                    uint2 aux[8];
+                    float4 old[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = rsub + 4 * i;
+                        const long long m = m0 + r;
+                        aux[i] = make_uint2(0u, 0u);
+                        old[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (col_ok && r < rows) {
+                            if (p.act == 2) aux[i] = *reinterpret_cast<const uint2*>(p.aux16 + m * p.ldaux + n);
+                            if (p.beta && p.C32) old[i] = *reinterpret_cast<const float4*>(p.C32 + m * p.ldc32 + n);
                         }
-                        if (p.C16) {
-                            if (p.c16_fmt == 0) reinterpret_cast<__half*>(p.C16)[m * p.ldc16 + n] = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
-                            else reinterpret_cast<__nv_bfloat16*>(p.C16)[m * p.ldc16 + n] = __float2bfloat16_rn(x);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = rsub + 4 * i;
+                        const long long m = m0 + r;
+                        const float4 s4 = *reinterpret_cast<const float4*>(stg + r * G2_PITCH + c4);
+                        float x[4] = {fmaf(s4.x, alpha, bsum.x), fmaf(s4.y, alpha, bsum.y), fmaf(s4.z, alpha, bsum.z), fmaf(s4.w, alpha, bsum.w)};
+                        if (p.act == 1) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) x[j] = tanh_f(x[j]);
+                        } else if (p.act == 2) {
+                            const __half2* h = reinterpret_cast<const __half2*>(&aux[i]);
+                            const float2 y0 = __half22float2(h[0]), y1 = __half22float2(h[1]);
+                            x[0] *= (1.f - y0.x * y0.x); x[1] *= (1.f - y0.y * y0.y); x[2] *= (1.f - y1.x * y1.x); x[3] *= (1.f - y1.y * y1.y);
+                        }
+                        if (p.beta) { x[0] += old[i].x; x[1] += old[i].y; x[2] += old[i].z; x[3] += old[i].w; }
+                        if (col_ok && r < rows) {
+                            if (p.C32) {
+                                if (p.splitk > 1) atomicAdd(reinterpret_cast<float4*>(p.C32 + m * p.ldc32 + n), make_float4(x[0], x[1], x[2], x[3]));
+                                else *reinterpret_cast<float4*>(p.C32 + m * p.ldc32 + n) = make_float4(x[0], x[1], x[2], x[3]);
+                            }
+                            if (p.C16) {
+                                uint2 pk;
+                                if (p.c16_fmt == 0) {      // fp16: saturate instead of overflowing to inf
+                                    const __half2 h0 = __floats2half2_rn(fminf(fmaxf(x[0], -65504.f), 65504.f), fminf(fmaxf(x[1], -65504.f), 65504.f));
+                                    const __half2 h1 = __floats2half2_rn(fminf(fmaxf(x[2], -65504.f), 65504.f), fminf(fmaxf(x[3], -65504.f), 65504.f));
+                                    pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                                } else {
+                                    const __nv_bfloat162 h0 = __floats2bfloat162_rn(x[0], x[1]), h1 = __floats2bfloat162_rn(x[2], x[3]);
+                                    pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                                }
+                                *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.C16) + m * p.ldc16 + n) = pk;
+                            }
+                        }
+                    }
+                } else {
+                    // unaligned / N % 4 != 0 outputs: lane = column, one row per iteration (rare: no shape on the hot path)
+                    const int n = nb + lane;
+                    const bool col_ok = c * 32 + lane < ncols;
+                    float bsum = 0.f;
+                    if (col_ok) {
+                        if (p.bias) bsum += __ldg(p.bias + n);
+                        if (p.bias2) bsum += __ldg(p.bias2 + n);
+                    }
+                    for (int r = 0; r < rows; ++r) {
+                        const long long m = m0 + r;
+                        float x = fmaf(stg[r * G2_PITCH + lane], alpha, bsum);
+                        if (p.act == 1) x = tanh_f(x);
+                        if (col_ok) {
+                            if (p.act == 2) { const float y = __half2float(p.aux16[m * p.ldaux + n]); x *= (1.f - y * y); }
+                            if (p.C32) {
+                                float* dst = p.C32 + m * p.ldc32 + n;
+                                if (p.beta) x += *dst;
+                                *dst = x;
+                            }
+                            if (p.C16) {
+                                if (p.c16_fmt == 0) reinterpret_cast<__half*>(p.C16)[m * p.ldc16 + n] = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+                                else reinterpret_cast<__nv_bfloat16*>(p.C16)[m * p.ldc16 + n] = __float2bfloat16_rn(x);
+                            }
                         }
                     }
                 }
@@ -455,13 +534,30 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
     if (!use_v1) {
         static int sms = 0;
         if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-        const bool wide = (g.N % 256 == 0) || g.N > 1024;
+        bool wide = (g.N % 256 == 0) || g.N > 1024;
+        if (wide && static_cast<long long>((g.N + 255) / 256) * ((g.M + BM - 1) / BM) < sms) wide = false;   // few tiles: prefer more CTAs
         const int bn = wide ? 256 : 128;
         const int tiles_n = (g.N + bn - 1) / bn, tiles_m = (g.M + BM - 1) / BM;
         const long long n_tiles_ll = static_cast<long long>(tiles_n) * tiles_m;
         if (n_tiles_ll > 0x7fffffff) return ft_set_error("gemm: too many tiles");
         const int n_tiles = static_cast<int>(n_tiles_ll);
-        const int grid2 = n_tiles < sms ? n_tiles : sms;
+        // split-K: long reductions with few output tiles (the dense / projection weight gradients: K = T*B rows, 8-64 tiles)
+        // would leave most SMs idle; each K range is reduced by its own CTA and added atomically into a zeroed C32
+        const int num_kb_all = (g.K + BK - 1) / BK;
+        int splitk = 1;
+        const bool splittable = g.C32 && !g.C16 && !g.beta && !g.bias && !g.bias2 && g.act == 0 && (g.N % 4 == 0) &&
+                                g.ldc32 == g.N && ((reinterpret_cast<uintptr_t>(g.C32) & 15) == 0);
+        if (splittable && n_tiles * 2 <= sms && num_kb_all >= 64) {
+            splitk = sms / n_tiles;
+            if (splitk > 16) splitk = 16;
+            while (splitk > 1 && num_kb_all / splitk < 16) --splitk;
+        }
+        if (splitk > 1) {
+            if (cudaMemsetAsync(g.C32, 0, sizeof(float) * static_cast<size_t>(g.M) * g.N, st) != cudaSuccess) return ft_set_error("gemm: memset failed");
+        }
+        p.splitk = splitk;
+        const long long n_work = static_cast<long long>(n_tiles) * splitk;
+        const int grid2 = n_work < sms ? static_cast<int>(n_work) : sms;
         // operand boxes: K-major A {BK, 128}; K-major B {BK, bn}; MN-major boxes are {BK, BK} as in v1
         if (!g.b_mn && bn == 256) { if (make_tmap_2d(&tmB, g.B, g.b_fmt, g.N, g.K, g.ldb, BK, 256)) return -1; }
         static bool attr2 = false;

@@ -79,3 +79,19 @@ def test_gemm_epilogue_tanh_beta_alpha_strided():
     assert (C.double() - ref).abs().max().item() < 1e-4
     assert (out16.double() - ref).abs().max().item() < 2e-2
     assert _lib.device_status() == 0
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 1024, 8192), (640, 1024, 128 * 70 + 24), (128, 80, 4096 * 3)])
+def test_gemm_split_k_weight_gradient_shapes(M, N, K):
+    """dW = dY^T X with few output tiles and a long reduction: the persistent kernel splits K over the idle SMs and adds
+    the partial tiles atomically into a zeroed fp32 output (alpha is applied per partial: the result stays alpha * sum)."""
+    from flowtron_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(K)
+    A = (torch.randn(K, M, device="cuda", generator=g) * 0.5).half()
+    B = (torch.randn(K, N, device="cuda", generator=g) * 0.5).half()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    _lib.gemm(A, B, a_mn=True, b_mn=True, alpha=0.25, out32=out)
+    torch.cuda.synchronize()
+    assert _lib.device_status() == 0
+    ref = 0.25 * (A.double().t() @ B.double())
+    assert (out.double() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
