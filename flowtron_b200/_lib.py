@@ -81,6 +81,14 @@ def _declare(L):
     L.ft_ar_step_bwd.argtypes = [POINTER(FtArStepDesc), POINTER(FtArStepWeights)] + [c_void_p] * 11 + \
         [POINTER(FtArStepWeights), c_void_p, c_void_p, c_void_p]
     L.ft_ar_step_bwd.restype = c_int
+    L.ft_ar_step_bwd_carry_bytes.argtypes = [POINTER(FtArStepDesc)]
+    L.ft_ar_step_bwd_carry_bytes.restype = c_size_t
+    L.ft_ar_step_bwd_main.argtypes = [POINTER(FtArStepDesc), POINTER(FtArStepWeights)] + [c_void_p] * 10 + \
+        [POINTER(FtArStepWeights), c_void_p, c_void_p, c_void_p, c_void_p]
+    L.ft_ar_step_bwd_main.restype = c_int
+    L.ft_ar_step_bwd_attn_lstm.argtypes = [POINTER(FtArStepDesc), POINTER(FtArStepWeights), c_void_p, c_void_p,
+                                           POINTER(FtArStepWeights), c_void_p, c_void_p, c_void_p, c_void_p]
+    L.ft_ar_step_bwd_attn_lstm.restype = c_int
     L.ft_ar_step_infer_scratch_bytes.argtypes = [POINTER(FtArStepDesc)]
     L.ft_ar_step_infer_scratch_bytes.restype = c_size_t
     L.ft_ar_step_infer.argtypes = [POINTER(FtArStepDesc), POINTER(FtArStepWeights), c_void_p, c_void_p, c_void_p, c_void_p,
@@ -278,6 +286,22 @@ def ar_step_bwd(desc, weights, mel, in_lens, out_lens, attn, d_mel_out, d_log_s,
     check(lib().ft_ar_step_bwd(byref(desc), byref(weights), ptr(mel), ptr(in_lens), ptr(out_lens), ptr(attn),
                                ptr(d_mel_out), ptr(d_log_s), ptr(d_gates), ptr(d_attn), ptr(d_logprob), ptr(d_mel),
                                ptr(d_text), byref(grads), ptr(saved), ptr(scratch), stream_ptr()), "ft_ar_step_bwd")
+
+
+def ar_step_bwd_carry_bytes(desc) -> int:
+    return int(lib().ft_ar_step_bwd_carry_bytes(byref(desc)))
+
+
+def ar_step_bwd_main(desc, weights, mel, in_lens, out_lens, attn, d_mel_out, d_log_s, d_gates, d_attn, d_logprob, d_text, grads,
+                     saved, scratch, carry):
+    check(lib().ft_ar_step_bwd_main(byref(desc), byref(weights), ptr(mel), ptr(in_lens), ptr(out_lens), ptr(attn), ptr(d_mel_out),
+                                    ptr(d_log_s), ptr(d_gates), ptr(d_attn), ptr(d_logprob), ptr(d_text), byref(grads), ptr(saved),
+                                    ptr(scratch), ptr(carry), stream_ptr()), "ft_ar_step_bwd_main")
+
+
+def ar_step_bwd_attn_lstm(desc, weights, out_lens, d_mel, grads, saved, scratch, carry):
+    check(lib().ft_ar_step_bwd_attn_lstm(byref(desc), byref(weights), ptr(out_lens), ptr(d_mel), byref(grads), ptr(saved),
+                                         ptr(scratch), ptr(carry), stream_ptr()), "ft_ar_step_bwd_attn_lstm")
 
 
 def nll_reduce(z, log_s_list, gate, gate_target, out_lens, sums):

@@ -131,10 +131,23 @@ struct FwdScratch {
     }
 };
 
+// What the attention-LSTM part of the backward (ar_step_bwd_attn) needs from the main part (ar_step_bwd_main): the two are
+// separate entry points so that the caller's autograd can run whatever depends only on d_text (the text encoder's backward)
+// concurrently with the attention LSTM's BPTT, a 64-SM kernel.  Lives in caller memory (`carry`), not in the shared scratch.
+struct BwdCarry {
+    float *dd, *dmel_flow, *scale;
+    void plan(Plan& p, const FtArStepDesc& d) {
+        const Dims n(d);
+        dd = p.get<float>("dd", n.R * n.D);                 // [R, D]: cols 0:H = dhA (attention-LSTM output gradient), H: = dctx
+        dmel_flow = p.get<float>("dmel_flow", n.R * n.M);
+        scale = p.get<float>("scale", 8);
+    }
+};
+
 struct BwdScratch {
     W16 w;                      // fp16, natural layouts (w_hh* hold the TRANSPOSED recurrent weights [H, 4H])
     uint16_t *dG1, *dG0, *dGa, *do16, *dy2, *dy1, *dQ16, *dK16, *dV16;
-    float *dh, *dd, *dQ, *dK, *dV, *dmel_flow, *dmel_in, *scale;
+    float *dh, *dQ, *dK, *dV, *dmel_in;
     int* flags;
     float *dcarry1 = nullptr, *dcarry0 = nullptr;      // dc*f hand-over between BPTT chunks (pipelined layers only)
     void plan(Plan& p, const FtArStepDesc& d) {
@@ -150,13 +163,10 @@ struct BwdScratch {
         dK16 = p.get<uint16_t>("dK16", n.RL * n.A);
         dV16 = p.get<uint16_t>("dV16", n.RL * n.A);
         dh = p.get<float>("dh", n.R * H);
-        dd = p.get<float>("dd", n.R * n.D);
         dQ = p.get<float>("dQ", n.R * n.A);
         dK = p.get<float>("dK", n.RL * n.A);
         dV = p.get<float>("dV", n.RL * n.A);
-        dmel_flow = p.get<float>("dmel_flow", n.R * n.M);
         dmel_in = p.get<float>("dmel_in", n.R * n.M);
-        scale = p.get<float>("scale", 8);
         flags = p.get<int>("flags", static_cast<size_t>(n.T) * 64);
         if (pipe_bwd_enabled()) {
             dcarry1 = p.get<float>("dcarry1", static_cast<size_t>(n.B) * H);
@@ -378,21 +388,24 @@ int ar_step_fwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
 }
 
 // =================================================================================================== backward
-int ar_step_bwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* mel, const int* in_lens, const int* out_lens,
-                const float* attn, const float* d_mel_out, const float* d_log_s, const float* d_gates, const float* d_attn,
-                const float* d_logprob, float* d_mel, float* d_text, const FtArStepWeights& g, void* saved, void* scratch,
-                cudaStream_t st) {
+// Main part: everything except the attention LSTM.  Outputs d_text and every parameter gradient but attention_lstm's; leaves
+// dhA / dmel_flow / the loss scale in `carry` for ar_step_bwd_attn.
+int ar_step_bwd_main(const FtArStepDesc& d, const FtArStepWeights& w, const float* mel, const int* in_lens, const int* out_lens,
+                     const float* attn, const float* d_mel_out, const float* d_log_s, const float* d_gates, const float* d_attn,
+                     const float* d_logprob, float* d_text, const FtArStepWeights& g, void* saved, void* scratch, void* carry,
+                     cudaStream_t st) {
     FT_TRY(check_desc(d));
     const Dims n(d);
     Plan ps; ps.base = static_cast<uint8_t*>(saved);
     Saved S_; S_.plan(ps, d);
     Plan pb; pb.base = static_cast<uint8_t*>(scratch);
     BwdScratch F; F.plan(pb, d);
+    Plan pc; pc.base = static_cast<uint8_t*>(carry);
+    BwdCarry C; C.plan(pc, d);
     const float* mel_flow = d.reversed ? S_.mel_flow : mel;
     const long long R = n.R, RL = n.RL, Rm = n.R - n.B;     // Rm: rows with a predecessor step
 
     // fp16 operand copies: natural layouts for dgrad (B operand MN-major), transposed recurrent weights for BPTT
-    FT_TRY(launch_cast(w.attn_lstm_w_ih, 2, F.w.w_ih_a, 0, static_cast<long long>(G) * n.M, st));
     FT_TRY(launch_cast(w.lstm_w_ih0, 2, F.w.w_ih0, 0, static_cast<long long>(G) * n.D, st));
     FT_TRY(launch_cast(w.lstm_w_ih1, 2, F.w.w_ih1, 0, static_cast<long long>(G) * H, st));
     FT_TRY(launch_cast(w.att_query, 2, F.w.wq, 0, static_cast<long long>(n.A) * H, st));
@@ -401,17 +414,16 @@ int ar_step_bwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
     FT_TRY(launch_cast(w.dense_w0, 2, F.w.w1, 0, static_cast<long long>(H) * H, st));
     FT_TRY(launch_cast(w.dense_w1, 2, F.w.w2, 0, static_cast<long long>(H) * H, st));
     FT_TRY(launch_cast(w.conv_w, 2, F.w.wc, 0, static_cast<long long>(2 * n.M) * H, st));
-    FT_TRY(launch_transpose_cast_f16(w.attn_lstm_w_hh, F.w.w_hh_a, G, H, st));
     FT_TRY(launch_transpose_cast_f16(w.lstm_w_hh0, F.w.w_hh0, G, H, st));
     FT_TRY(launch_transpose_cast_f16(w.lstm_w_hh1, F.w.w_hh1, G, H, st));
 
     // 0. loss scale for this flow's backward: S = 2^k with S * max|incoming grad| ~ 64 (device-side, no host sync)
     const long long RM = R * n.M;
     const long long BTL = static_cast<long long>(n.B) * n.T * n.L;
-    FT_TRY(launch_grad_scale(d_mel_out, d_mel_out ? RM : 0, d_log_s, d_log_s ? RM : 0, d_gates, d_gates ? R : 0, 64.f, F.scale, st,
+    FT_TRY(launch_grad_scale(d_mel_out, d_mel_out ? RM : 0, d_log_s, d_log_s ? RM : 0, d_gates, d_gates ? R : 0, 64.f, C.scale, st,
                              d_attn, d_attn ? BTL : 0, d_logprob, d_logprob ? BTL : 0));
-    const float* S = F.scale;            // S[0] = scale, S[1] = 1/scale
-    const float* iS = F.scale + 1;
+    const float* S = C.scale;            // S[0] = scale, S[1] = 1/scale
+    const float* iS = C.scale + 1;
 
     static int side_env = -1;
     if (side_env < 0) { const char* e = getenv("FT_SIDE_STREAM"); side_env = e ? atoi(e) : 1; g_side_enabled = side_env != 0; }
@@ -419,7 +431,7 @@ int ar_step_bwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
     cudaStream_t ss;
 
     // 1. affine coupling (scales the incoming gradients by S)
-    FT_TRY(launch_affine_bwd(d_mel_out, d_log_s, S_.o32, mel_flow, out_lens, n.T, n.B, n.M, d.reversed, F.do16, F.dmel_flow, S, st));
+    FT_TRY(launch_affine_bwd(d_mel_out, d_log_s, S_.o32, mel_flow, out_lens, n.T, n.B, n.M, d.reversed, F.do16, C.dmel_flow, S, st));
 
     // 2. 1x1 conv     (weight / bias gradients go to the side stream, the dgrad chain stays on `st`)
     ss = fork_side(sd, st);
@@ -483,18 +495,15 @@ int ar_step_bwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
     // 6. lstm layer 0
     FT_TRY(launch_lstm_bwd(n.T, n.B, F.dh, H, F.w.w_hh0, S_.gates0, S_.c0, out_lens, F.dG0, F.flags, st));
     }
-    ss = fork_side(sd, st);
-    FT_TRY(gemm_wgrad(ss, G, H, Rm, F.dG0 + static_cast<size_t>(n.B) * G, G, S_.h0_16, H, g.lstm_w_hh0, H, iS));
-    FT_TRY(gemm_wgrad(ss, G, n.D, R, F.dG0, G, S_.d16, n.D, g.lstm_w_ih0, n.D, iS));
-    FT_TRY(launch_colsum(F.dG0, 0, G, R, G, g.lstm_b_ih0, iS, ss));
-    FT_TRY(copy_f32(g.lstm_b_hh0, g.lstm_b_ih0, G, ss));
-    FT_TRY(gemm_dgrad(st, R, n.D, G, F.dG0, G, F.w.w_ih0, n.D, 0, F.dd, n.D, nullptr, 0, nullptr, 0));
+    // (the weight gradients of lstm layer 0 and of the attention projections are launched by ar_step_bwd_attn, on the side
+    //  stream underneath the attention LSTM's BPTT: dG0, dQ16, dK16, dV16 stay in the scratch area until then)
+    FT_TRY(gemm_dgrad(st, R, n.D, G, F.dG0, G, F.w.w_ih0, n.D, 0, C.dd, n.D, nullptr, 0, nullptr, 0));
 
     // 7. gate layer (last flow only): dd is in the scaled domain, the gate's own parameter gradients are not
     if (d.has_gate && g.gate_w) {
         FT_TRY(zero(g.gate_w, sizeof(float) * n.D, st));
         FT_TRY(zero(g.gate_b, sizeof(float), st));
-        if (d_gates) FT_TRY(launch_gate_bwd(S_.d16, n.D, n.D, w.gate_w, d_gates, R, F.dd, n.D, g.gate_w, g.gate_b, S, st));
+        if (d_gates) FT_TRY(launch_gate_bwd(S_.d16, n.D, n.D, w.gate_w, d_gates, R, C.dd, n.D, g.gate_w, g.gate_b, S, st));
     }
 
     // 8. attention (score/softmax/context) with tanh recompute
@@ -506,7 +515,7 @@ int ar_step_bwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
         a.T = n.T; a.B = n.B; a.L = n.L; a.A = n.A;
         a.Q = S_.Q; a.ldq = n.A; a.K = S_.Kp; a.ldk = n.A; a.V = S_.Vp; a.ldv = n.A; a.v = w.att_v;
         a.in_lens = in_lens; a.out_lens = out_lens; a.attn = attn; a.p_save = S_.p_save; a.temperature = d.temperature;
-        a.dctx = F.dd + H; a.lddc = n.D; a.dattn_ext = d_attn; a.dlp_ext = d_logprob; a.scale = S;
+        a.dctx = C.dd + H; a.lddc = n.D; a.dattn_ext = d_attn; a.dlp_ext = d_logprob; a.scale = S;
         a.dQ = F.dQ; a.lddq = n.A; a.dK = F.dK; a.lddk = n.A; a.dV = F.dV; a.lddv = n.A; a.dv = g.att_v;
         FT_TRY(launch_attn_bwd(a, st));
     }
@@ -515,16 +524,47 @@ int ar_step_bwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
     FT_TRY(launch_cast(F.dQ, 2, F.dQ16, 0, R * n.A, st));
     FT_TRY(launch_cast(F.dK, 2, F.dK16, 0, RL * n.A, st));
     FT_TRY(launch_cast(F.dV, 2, F.dV16, 0, RL * n.A, st));
-    ss = fork_side(sd, st);
-    FT_TRY(gemm_wgrad(ss, n.A, H, R, F.dQ16, n.A, S_.d16, n.D, g.att_query, H, iS));
-    FT_TRY(gemm_wgrad(ss, n.A, n.E, RL, F.dK16, n.A, S_.text16, n.E, g.att_key, n.E, iS));
-    FT_TRY(gemm_wgrad(ss, n.A, n.E, RL, F.dV16, n.A, S_.text16, n.E, g.att_value, n.E, iS));
-    FT_TRY(gemm_dgrad(st, R, H, n.A, F.dQ16, n.A, F.w.wq, H, 1, F.dd, n.D, nullptr, 0, nullptr, 0));   // dhA += dQ Wq
+    FT_TRY(gemm_dgrad(st, R, H, n.A, F.dQ16, n.A, F.w.wq, H, 1, C.dd, n.D, nullptr, 0, nullptr, 0));   // dhA += dQ Wq
     FT_TRY(gemm_dgrad(st, RL, n.E, n.A, F.dK16, n.A, F.w.wk, n.E, 0, d_text, n.E, nullptr, 0, nullptr, 0, iS));
     FT_TRY(gemm_dgrad(st, RL, n.E, n.A, F.dV16, n.A, F.w.wv, n.E, 1, d_text, n.E, nullptr, 0, nullptr, 0, iS));
 
-    // 10. attention_lstm  (dhA = F.dd[:, 0:H], pitch D)
-    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dd, n.D, F.w.w_hh_a, S_.gatesA, S_.cA, out_lens, F.dGa, F.flags, st));
+    join_side(sd, st);                   // everything this call launched is ordered before what the caller enqueues next
+    return 0;
+}
+
+// Attention-LSTM part: BPTT over dhA (carry), its weight gradients, and the input gradient d_mel (coupling path from carry +
+// the shifted attention-LSTM path, back to natural time, loss scale undone).
+int ar_step_bwd_attn(const FtArStepDesc& d, const FtArStepWeights& w, const int* out_lens, float* d_mel, const FtArStepWeights& g,
+                     void* saved, void* scratch, void* carry, cudaStream_t st) {
+    FT_TRY(check_desc(d));
+    const Dims n(d);
+    Plan ps; ps.base = static_cast<uint8_t*>(saved);
+    Saved S_; S_.plan(ps, d);
+    Plan pb; pb.base = static_cast<uint8_t*>(scratch);
+    BwdScratch F; F.plan(pb, d);
+    Plan pc; pc.base = static_cast<uint8_t*>(carry);
+    BwdCarry C; C.plan(pc, d);
+    const long long R = n.R, Rm = n.R - n.B;
+    const float* iS = C.scale + 1;
+    Side* sd = get_side(st);
+    cudaStream_t ss;
+    const long long RL = n.RL;
+    FT_TRY(launch_cast(w.attn_lstm_w_ih, 2, F.w.w_ih_a, 0, static_cast<long long>(G) * n.M, st));
+    FT_TRY(launch_transpose_cast_f16(w.attn_lstm_w_hh, F.w.w_hh_a, G, H, st));
+
+    // deferred from ar_step_bwd_main: weight gradients of lstm layer 0 and of the attention projections, on the side stream,
+    // underneath the BPTT kernel below (64 of the 148 SMs)
+    ss = fork_side(sd, st);
+    FT_TRY(gemm_wgrad(ss, G, H, Rm, F.dG0 + static_cast<size_t>(n.B) * G, G, S_.h0_16, H, g.lstm_w_hh0, H, iS));
+    FT_TRY(gemm_wgrad(ss, G, n.D, R, F.dG0, G, S_.d16, n.D, g.lstm_w_ih0, n.D, iS));
+    FT_TRY(launch_colsum(F.dG0, 0, G, R, G, g.lstm_b_ih0, iS, ss));
+    FT_TRY(copy_f32(g.lstm_b_hh0, g.lstm_b_ih0, G, ss));
+    FT_TRY(gemm_wgrad(ss, n.A, H, R, F.dQ16, n.A, S_.d16, n.D, g.att_query, H, iS));
+    FT_TRY(gemm_wgrad(ss, n.A, n.E, RL, F.dK16, n.A, S_.text16, n.E, g.att_key, n.E, iS));
+    FT_TRY(gemm_wgrad(ss, n.A, n.E, RL, F.dV16, n.A, S_.text16, n.E, g.att_value, n.E, iS));
+
+    // 10. attention_lstm  (dhA = C.dd[:, 0:H], pitch D)
+    FT_TRY(launch_lstm_bwd(n.T, n.B, C.dd, n.D, F.w.w_hh_a, S_.gatesA, S_.cA, out_lens, F.dGa, F.flags, st));
     ss = fork_side(sd, st);
     FT_TRY(gemm_wgrad(ss, G, H, Rm, F.dGa + static_cast<size_t>(n.B) * G, G, S_.d16, n.D, g.attn_lstm_w_hh, H, iS));
     FT_TRY(gemm_wgrad(ss, G, n.M, R, F.dGa, G, S_.mel_in16, n.M, g.attn_lstm_w_ih, n.M, iS));
@@ -533,7 +573,7 @@ int ar_step_bwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
     FT_TRY(gemm_dgrad(st, R, n.M, G, F.dGa, G, F.w.w_ih_a, n.M, 0, F.dmel_in, n.M, nullptr, 0, nullptr, 0));
 
     // 11. input gradient: coupling path + (shifted) attention_lstm path, back to natural time, loss scale undone
-    if (d_mel) FT_TRY(launch_combine_dmel(F.dmel_flow, F.dmel_in, out_lens, n.T, n.B, n.M, d.reversed, d_mel, iS, st));
+    if (d_mel) FT_TRY(launch_combine_dmel(C.dmel_flow, F.dmel_in, out_lens, n.T, n.B, n.M, d.reversed, d_mel, iS, st));
     join_side(sd, st);                   // everything this call launched is ordered before what the caller enqueues next
     return 0;
 }
@@ -547,10 +587,16 @@ size_t ft_ar_step_saved_bytes(const FtArStepDesc* d) {
     ft::Plan p; ft::Saved s; s.plan(p, *d);
     return p.off + 256;
 }
+size_t ft_ar_step_bwd_carry_bytes(const FtArStepDesc* d) {
+    ft::Plan pc; ft::BwdCarry c; c.plan(pc, *d);
+    return pc.off + 256;
+}
 size_t ft_ar_step_scratch_bytes(const FtArStepDesc* d) {
     ft::Plan pf; ft::FwdScratch f; f.plan(pf, *d);
     ft::Plan pb; ft::BwdScratch b; b.plan(pb, *d);
-    return (pf.off > pb.off ? pf.off : pb.off) + 256;
+    // the one-call backward (ft_ar_step_bwd) places its carry area behind the backward scratch
+    const size_t bwd = ((pb.off + 255) & ~static_cast<size_t>(255)) + ft_ar_step_bwd_carry_bytes(d);
+    return (pf.off > bwd ? pf.off : bwd) + 256;
 }
 int ft_ar_step_saved_lookup(const FtArStepDesc* d, const char* name, size_t* offset, size_t* bytes) {
     std::vector<ft::Region> regs;
@@ -577,8 +623,26 @@ int ft_ar_step_bwd(const FtArStepDesc* d, const FtArStepWeights* w, const float*
                    const float* d_gates, const float* d_attn, const float* d_attn_logprob, float* d_mel, float* d_text,
                    const FtArStepWeights* g, void* saved, void* scratch, void* stream) {
     if (!d || !w || !mel || !attn || !d_text || !g || !saved || !scratch) return ft::ft_set_error("ft_ar_step_bwd: NULL argument");
-    return ft::ar_step_bwd(*d, *w, mel, in_lens, out_lens, attn, d_mel_out, d_log_s, d_gates, d_attn, d_attn_logprob,
-                           d_mel, d_text, *g, saved, scratch, static_cast<cudaStream_t>(stream));
+    ft::Plan pb; ft::BwdScratch b; b.plan(pb, *d);
+    void* carry = static_cast<uint8_t*>(scratch) + ((pb.off + 255) & ~static_cast<size_t>(255));
+    if (ft::ar_step_bwd_main(*d, *w, mel, in_lens, out_lens, attn, d_mel_out, d_log_s, d_gates, d_attn, d_attn_logprob, d_text, *g,
+                             saved, scratch, carry, static_cast<cudaStream_t>(stream)) != 0) return -1;
+    return ft::ar_step_bwd_attn(*d, *w, out_lens, d_mel, *g, saved, scratch, carry, static_cast<cudaStream_t>(stream));
+}
+
+int ft_ar_step_bwd_main(const FtArStepDesc* d, const FtArStepWeights* w, const float* mel, const int* in_lens,
+                        const int* out_lens, const float* attn, const float* d_mel_out, const float* d_log_s,
+                        const float* d_gates, const float* d_attn, const float* d_attn_logprob, float* d_text,
+                        const FtArStepWeights* g, void* saved, void* scratch, void* carry, void* stream) {
+    if (!d || !w || !mel || !attn || !d_text || !g || !saved || !scratch || !carry) return ft::ft_set_error("ft_ar_step_bwd_main: NULL argument");
+    return ft::ar_step_bwd_main(*d, *w, mel, in_lens, out_lens, attn, d_mel_out, d_log_s, d_gates, d_attn, d_attn_logprob, d_text,
+                                *g, saved, scratch, carry, static_cast<cudaStream_t>(stream));
+}
+
+int ft_ar_step_bwd_attn_lstm(const FtArStepDesc* d, const FtArStepWeights* w, const int* out_lens, float* d_mel,
+                             const FtArStepWeights* g, void* saved, void* scratch, void* carry, void* stream) {
+    if (!d || !w || !g || !saved || !scratch || !carry) return ft::ft_set_error("ft_ar_step_bwd_attn_lstm: NULL argument");
+    return ft::ar_step_bwd_attn(*d, *w, out_lens, d_mel, *g, saved, scratch, carry, static_cast<cudaStream_t>(stream));
 }
 
 int ft_nll_reduce(const float* z, const float* const* log_s_list, int n_flows, const float* gate,

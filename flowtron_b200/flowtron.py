@@ -210,11 +210,56 @@ def _lens_i32(lens: Optional[Tensor], device) -> Optional[Tensor]:
     return lens.to(device=device, dtype=torch.int32).contiguous()
 
 
-class _ArStepFn(torch.autograd.Function):
-    """autograd wrapper around ft_ar_step_fwd / ft_ar_step_bwd."""
+# Parameters whose gradients are produced by the attention-LSTM half of the backward (ft_ar_step_bwd_attn_lstm: the
+# attention LSTM itself, plus lstm layer 0 and the attention query/key/value projections, whose weight-gradient GEMMs are
+# deferred so they run underneath that BPTT kernel); indices into AR_Step._param_list() / _lib.AR_WEIGHT_FIELDS.
+_ATTN_HALF = (0, 1, 2, 3, 4, 5, 6, 7, 12, 13, 14)
+_MAIN_HALF = tuple(i for i in range(24) if i not in _ATTN_HALF)
+
+
+class _FlowState:
+    """What the two autograd nodes of one flow step share between forward and the two backward calls."""
+    __slots__ = ("desc", "saved", "plist", "mel_c", "in_lens", "out_lens", "attn", "carry", "grads", "text_shape", "has_gate")
+
+    def clear(self):
+        for k in self.__slots__:
+            setattr(self, k, None)
+
+
+class _ArStepAttnLstmFn(torch.autograd.Function):
+    """Autograd node A of a flow step: owns `mel` and the _ATTN_HALF parameters.  Its forward does nothing (the whole
+    forward pass is ONE C call, issued by node B); it returns a token that node B consumes, so that A.backward runs after
+    B.backward.  Splitting the backward in two nodes lets the autograd engine run everything that depends only on d_text
+    (the text encoder's backward, on its own stream) concurrently with the attention LSTM's BPTT of the first flow."""
 
     @staticmethod
-    def forward(ctx, step, reversed_flag, mel, text, in_lens, out_lens, attn_prior, *params):
+    def forward(ctx, state, mel, *params_a):
+        ctx.state = state
+        return mel.new_zeros(1)
+
+    @staticmethod
+    def backward(ctx, g_token):
+        st = ctx.state
+        if st is None or st.saved is None or st.carry is None:
+            raise FlowtronB200Error("AR_Step backward ran twice: the flow's saved activations are released after the first "
+                                    "backward (retain_graph is not supported on the CUDA path)")
+        dev = st.mel_c.device
+        d_mel = torch.empty_like(st.mel_c)
+        _, scratch_bytes = _lib.ar_step_sizes(st.desc)
+        scratch = _lib.scratch_buffer(scratch_bytes, dev)
+        _lib.ar_step_bwd_attn_lstm(st.desc, _lib.make_weights(st.plist), st.out_lens, d_mel, _lib.make_weights(st.grads),
+                                   st.saved, scratch, st.carry)
+        grads_a = [st.grads[i] for i in _ATTN_HALF]
+        st.clear()                                   # saved activations, carry, the output `attn` -> ctx reference cycle
+        ctx.state = None
+        return (None, d_mel, *grads_a)
+
+
+class _ArStepFn(torch.autograd.Function):
+    """Autograd node B: ft_ar_step_fwd (the whole forward) / ft_ar_step_bwd_main."""
+
+    @staticmethod
+    def forward(ctx, state, step, reversed_flag, token, mel, text, in_lens, out_lens, attn_prior, *params_b):
         if not mel.is_cuda:
             raise FlowtronB200Error("AR_Step needs CUDA tensors: the sm_100a kernels are the only implementation")
         T, B, M = mel.shape
@@ -227,7 +272,7 @@ class _ArStepFn(torch.autograd.Function):
         mel_c = mel.detach().float().contiguous()
         text_c = text.detach().float().contiguous()
         prior_c = None if attn_prior is None else attn_prior.detach().float().contiguous()
-        plist = [p.detach() if p is not None else None for p in params]
+        plist = [p.detach() if p is not None else None for p in step._param_list()]
         plist = [p if (p is None or p.is_contiguous()) else p.contiguous() for p in plist]
         weights = _lib.make_weights(plist)
         saved_bytes, scratch_bytes = _lib.ar_step_sizes(desc)
@@ -244,9 +289,10 @@ class _ArStepFn(torch.autograd.Function):
             _lib.set_text_ready_event(ev)
         _lib.ar_step_fwd(desc, weights, mel_c, text_c, in_lens, out_lens, prior_c, mel_out, log_s, gates, attn, logprob,
                          saved, scratch)
-        ctx.desc, ctx.saved_buf, ctx.plist = desc, saved, plist
-        ctx.mel_c, ctx.in_lens, ctx.out_lens, ctx.attn = mel_c, in_lens, out_lens, attn
-        ctx.text_shape = text.shape
+        state.desc, state.saved, state.plist = desc, saved, plist
+        state.mel_c, state.in_lens, state.out_lens, state.attn = mel_c, in_lens, out_lens, attn
+        state.text_shape, state.has_gate = text.shape, has_gate
+        ctx.state = state
         ctx.has_gate = has_gate
         if has_gate:
             return mel_out, log_s, gates, attn, logprob
@@ -261,22 +307,23 @@ class _ArStepFn(torch.autograd.Function):
             d_gates = None
         c = lambda g: None if g is None else g.float().contiguous()
         d_mel_out, d_log_s, d_gates, d_attn, d_lp = map(c, (d_mel_out, d_log_s, d_gates, d_attn, d_lp))
-        if ctx.saved_buf is None:
+        st = ctx.state
+        if st is None or st.saved is None:
             raise FlowtronB200Error("AR_Step backward ran twice: the flow's saved activations are released after the first "
                                     "backward (retain_graph is not supported on the CUDA path)")
-        desc = ctx.desc
-        dev = ctx.mel_c.device
-        d_mel = torch.empty_like(ctx.mel_c)
-        d_text = torch.empty(ctx.text_shape, device=dev, dtype=torch.float32)
-        gl = [None if p is None else torch.empty_like(p) for p in ctx.plist]
-        weights, grads_s = _lib.make_weights(ctx.plist), _lib.make_weights(gl)
+        desc = st.desc
+        dev = st.mel_c.device
+        d_text = torch.empty(st.text_shape, device=dev, dtype=torch.float32)
+        st.grads = [None if p is None else torch.empty_like(p) for p in st.plist]
+        st.carry = torch.empty(_lib.ar_step_bwd_carry_bytes(desc), dtype=torch.uint8, device=dev)
         _, scratch_bytes = _lib.ar_step_sizes(desc)
         scratch = _lib.scratch_buffer(scratch_bytes, dev)
-        _lib.ar_step_bwd(desc, weights, ctx.mel_c, ctx.in_lens, ctx.out_lens, ctx.attn, d_mel_out, d_log_s, d_gates, d_attn,
-                         d_lp, d_mel, d_text, grads_s, ctx.saved_buf, scratch)
-        # release everything the node holds (saved activations, the output `attn` -> ctx reference cycle) right away
-        ctx.saved_buf = ctx.attn = ctx.mel_c = ctx.plist = ctx.in_lens = ctx.out_lens = None
-        return (None, None, d_mel, d_text, None, None, None, *gl)
+        _lib.ar_step_bwd_main(desc, _lib.make_weights(st.plist), st.mel_c, st.in_lens, st.out_lens, st.attn, d_mel_out, d_log_s,
+                              d_gates, d_attn, d_lp, d_text, _lib.make_weights(st.grads), st.saved, scratch, st.carry)
+        grads_b = [st.grads[i] for i in _MAIN_HALF]
+        ctx.state = None
+        # (state, step, reversed, token, mel, text, in_lens, out_lens, prior, *params_b): mel's gradient comes out of node A
+        return (None, None, None, torch.zeros(1, device=dev), None, d_text, None, None, None, *grads_b)
 
 
 class AR_Step(nn.Module):
@@ -320,8 +367,12 @@ class AR_Step(nn.Module):
         in_lens = None
         if mask is not None:
             in_lens = (~mask[..., 0]).sum(1).to(torch.int32).contiguous()
-        out = _ArStepFn.apply(self, reversed_flag, mel, text, in_lens, _lens_i32(out_lens, dev), attn_prior,
-                              *self._param_list())
+        plist = self._param_list()
+        state = _FlowState()
+        state.clear()
+        token = _ArStepAttnLstmFn.apply(state, mel, *[plist[i] for i in _ATTN_HALF])
+        out = _ArStepFn.apply(state, self, reversed_flag, token, mel, text, in_lens, _lens_i32(out_lens, dev), attn_prior,
+                              *[plist[i] for i in _MAIN_HALF])
         if hasattr(self, 'gate_layer'):
             mel_out, log_s, gates, attn, lp = out
         else:

@@ -121,6 +121,23 @@ int ft_ar_step_bwd(const FtArStepDesc* d, const FtArStepWeights* w, const float*
                    const float* d_gates, const float* d_attn, const float* d_attn_logprob, float* d_mel, float* d_text,
                    const FtArStepWeights* g, void* saved, void* scratch, void* stream);
 
+/* The same backward as two calls, so that the caller's autograd can overlap work that depends only on d_text (the text
+ * encoder's backward) with the attention LSTM's BPTT (a 64-SM kernel):
+ *   ft_ar_step_bwd_main      : everything but the attention LSTM.  Writes d_text and the gradients of conv, dense_layer,
+ *                              lstm layer 1 and the gate; leaves dhA / the coupling-path input gradient / the loss scale in
+ *                              `carry` (ft_ar_step_bwd_carry_bytes, caller-owned, must survive until the second call) and
+ *                              dG0 / dQ / dK / dV in `scratch` (nothing else may use `scratch` in between).
+ *   ft_ar_step_bwd_attn_lstm : attention-LSTM BPTT; writes d_mel and the gradients of attention_lstm, lstm layer 0 and the
+ *                              attention query / key / value projections (their GEMMs run underneath the BPTT kernel).
+ * ft_ar_step_bwd == the two back to back. */
+size_t ft_ar_step_bwd_carry_bytes(const FtArStepDesc* d);
+int ft_ar_step_bwd_main(const FtArStepDesc* d, const FtArStepWeights* w, const float* mel, const int* in_lens,
+                        const int* out_lens, const float* attn, const float* d_mel_out, const float* d_log_s,
+                        const float* d_gates, const float* d_attn, const float* d_attn_logprob, float* d_text,
+                        const FtArStepWeights* g, void* saved, void* scratch, void* carry, void* stream);
+int ft_ar_step_bwd_attn_lstm(const FtArStepDesc* d, const FtArStepWeights* w, const int* out_lens, float* d_mel,
+                             const FtArStepWeights* g, void* saved, void* scratch, void* carry, void* stream);
+
 /* FlowtronLoss default branch (flowtron.py:205-243): sums[0]=sum (z m)^2, [1]=sum_flows sum log_s m,
  * [2]=sum m BCEWithLogits(gate m, target), [3]=n=sum m.  log_s_list: HOST array of n_flows (<= 16) device pointers (passed
  * to the kernel by value: no upload, so the call can be captured in a CUDA graph). */

@@ -34,8 +34,7 @@ train)
   bench train_default X=1 -- --steps 5 --warmup 3 --no-cpu-baseline
   bench train_gemm_v1 FT_GEMM_V1=1 -- --steps 5 --warmup 3 --no-cpu-baseline
   bench train_fused_opt FT_FUSED_OPT=1 -- --steps 5 --warmup 3 --no-cpu-baseline
-  bench train_chunk50 FT_PIPE_CHUNK=50 -- --steps 5 --warmup 3 --no-cpu-baseline
-  bench train_chunk150 FT_PIPE_CHUNK=150 -- --steps 5 --warmup 3 --no-cpu-baseline
+  bench train_fused_v1 FT_FUSED_OPT=1 FT_GEMM_V1=1 -- --steps 5 --warmup 3 --no-cpu-baseline
   bench train_eager FT_GRAPH=0 -- --steps 5 --warmup 3 --no-cpu-baseline ;;
 cfg3)
   bench train_cfg3 X=1 -- --config 3 --steps 5 --warmup 3 --no-cpu-baseline ;;
