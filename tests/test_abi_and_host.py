@@ -92,7 +92,7 @@ def test_encoder_matches_oracle_restatement():
 
 def test_default_switches_are_the_validated_configuration(monkeypatch):
     """The GPU validation of record (profiles/r2_*) ran with: encoder overlap ON, two-stream BiLSTM OFF, fused optimizer
-    OFF, layer pipeline ON (forward and BPTT), CUDA-graph step ON in bench.py.  Anything else is opt-in through the
+    ON (capturable), layer pipeline ON (forward and BPTT), CUDA-graph step ON in bench.py.  Anything else is opt-in through the
     environment."""
     import flowtron_b200.flowtron as F
     if "FT_ENC_OVERLAP" not in os.environ:                 # class attribute, read at import
@@ -100,7 +100,7 @@ def test_default_switches_are_the_validated_configuration(monkeypatch):
     monkeypatch.delenv("FT_ENC_STREAMS", raising=False)
     assert F.Encoder().two_streams is False
     src = open(os.path.join(ROOT, "bench.py")).read()
-    assert 'os.environ.get("FT_FUSED_OPT", "0")' in src
+    assert 'os.environ.get("FT_FUSED_OPT", "1")' in src
     csrc = open(os.path.join(ROOT, "flowtron_b200", "csrc", "ar_step.cu")).read()
     assert 'getenv("FT_PIPE_FWD"); v = (!e || atoi(e) != 0) ? 1 : 0' in csrc
     assert 'getenv("FT_PIPE_BWD"); v = (!e || atoi(e) != 0) ? 1 : 0' in csrc
