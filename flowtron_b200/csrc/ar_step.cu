@@ -321,9 +321,17 @@ int ar_step_fwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
     FT_TRY(launch_prep_mel(mel, out_lens, n.T, n.B, n.M, d.reversed, S.mel_in16, S.mel_flow, st));
     const float* mel_flow = d.reversed ? S.mel_flow : mel;
 
-    // attention_lstm: input projection GEMM, then the persistent recurrence; h lands in d16[:, 0:H]
-    FT_TRY(gemm_fwd(st, n.R, G, n.M, S.mel_in16, n.M, F.w.w_ih_a, n.M, w.attn_lstm_b_ih, w.attn_lstm_b_hh, 0, F.X, G, nullptr, 0));
-    FT_TRY(launch_lstm_fwd(n.T, n.B, F.X, F.w.w_hh_a, out_lens, S.d16, n.D, S.gatesA, S.cA, F.hA32, H, F.flags, st));
+    // attention_lstm: the 80-channel input projection is folded into the persistent recurrence (no [R,4096] projection
+    // tensor: -0.5 ms GEMM, -1 GB of HBM traffic per flow); h lands in d16[:, 0:H].  FT_LSTM_XIN=0: separate GEMM (r1 path).
+    static int xin = -1;
+    if (xin < 0) { const char* e = getenv("FT_LSTM_XIN"); xin = (!e || atoi(e) != 0) ? 1 : 0; }
+    if (xin && n.M <= 128) {
+        FT_TRY(launch_lstm_fwd_xin(n.T, n.B, S.mel_in16, n.M, n.M, F.w.w_ih_a, w.attn_lstm_b_ih, w.attn_lstm_b_hh, F.w.w_hh_a, out_lens,
+                                   S.d16, n.D, S.gatesA, S.cA, F.hA32, H, F.flags, st));
+    } else {
+        FT_TRY(gemm_fwd(st, n.R, G, n.M, S.mel_in16, n.M, F.w.w_ih_a, n.M, w.attn_lstm_b_ih, w.attn_lstm_b_hh, 0, F.X, G, nullptr, 0));
+        FT_TRY(launch_lstm_fwd(n.T, n.B, F.X, F.w.w_hh_a, out_lens, S.d16, n.D, S.gatesA, S.cA, F.hA32, H, F.flags, st));
+    }
 
     // attention: K/V/Q projections, fused score+softmax(+prior)+context; ctx lands in d16[:, H:H+A]
     // First use of `text`: if the caller produced it on another stream it handed us the event to wait for, so the encoder

@@ -43,6 +43,9 @@ void set_lstm_trace(long long* p);
 void set_lstm_half_sm(int on);
 int launch_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const int* lens, void* hseq16, long long ldh,
                     void* gates16, float* cstate, float* h32, long long ldh32, int* flags, cudaStream_t st);
+int launch_lstm_fwd_xin(int T, int B, const void* x16, long long ldx, int kx, const void* wih16, const float* b_ih, const float* b_hh,
+                        const void* whh16, const int* lens, void* hseq16, long long ldh, void* gates16, float* cstate, float* h32,
+                        long long ldh32, int* flags, cudaStream_t st);    // input projection folded into the recurrence (kx <= 128)
 int launch_lstm_fwd_chunk(int T, int B, int t0, int t1, const float* xproj, const void* whh16, const int* lens, void* hseq16,
                           long long ldh, void* gates16, float* cstate, int* flags, cudaStream_t st);   // experimental
 int launch_lstm_bwd_chunk(int T, int B, int t0, int t1, const float* dh_ext, long long ldd, const void* whhT16, const void* gates16,

@@ -56,7 +56,8 @@ constexpr int FWD_NCH = LH / KCH;                  // 16 chunks / step
 
 struct LstmFwdParams {
     int T, B, Bbox;
-    const float* xproj;        // [T*B, 4096] input projection + both biases
+    const float* xproj;        // [T*B, 4096] input projection + both biases (null when the projection is folded in)
+    const float* b_ih; const float* b_hh;   // folded-projection form only: the two bias vectors [4096]
     const int* lens;           // [B] or null
     __half* hseq; long long ldh;   // [T*B, ldh] output (fp16), also the recurrent exchange buffer
     __half* gates;             // [T*B, 4096] post-activation i,f,g,o (fp16) or null
@@ -304,7 +305,9 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
 //   * pointwise LSTM backward + dG_t stores + per-chunk release flags exactly as in the single-CTA kernel.
 constexpr int B4_CTAS = 64, B4_CLUSTER = 4, B4_UNITS = 64, B4_OWN = 16, B4_NCH = LH / KCH;     // 16 chunks / step / rank
 constexpr int B4_W_BYTES = B4_NCH * B4_UNITS * 128;                                               // 128 KB
-constexpr int B4_PP = 68;                                                                          // partial row pitch (floats)
+constexpr int B4_PP = 68;                                                                          // partial row pitch (floats), pull form
+constexpr int B4_RP = 20;                                                                          // received-slice row pitch (floats), push form
+constexpr int B4_XCHG_FLOATS = 2 * 4 * 32 * B4_RP;                                                 // [2 parities][4 sources][32 rows][B4_RP] >= 2*32*B4_PP
 
 // The kernel runs steps [t0, t1) of the sequence, highest step first: the whole sequence in one launch (t0 = 0, t1 = T), or
 // one chunk of the layer pipeline (ar_step.cu), resuming dc*f from `dc_carry` ([B,1024] fp32, written by the chunk above) and
@@ -313,6 +316,7 @@ constexpr int B4_PP = 68;                                                       
 struct LstmBwdChunkParams : LstmBwdParams {
     int t0, t1;                // steps [t0, t1); flags: [(t1 - t0) * 64] ints, zeroed by the launcher
     float* dc_carry;           // [B, 1024]
+    int push;                  // 1: partial sums are pushed into the finishing rank's shared memory (default); 0: pulled over DSMEM
 };
 
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
@@ -322,8 +326,8 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
     const int slot_bytes = p.Bbox * 128;
     uint8_t* sA = smem;                                          // [16 chunks][Bbox rows][128 B]
     uint8_t* sW = smem + B4_NCH * slot_bytes;                    // [16 chunks][64 rows][128 B]
-    float* sPart = reinterpret_cast<float*>(sW + B4_W_BYTES);    // [2 parities][32 rows][B4_PP]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + 2 * 32 * B4_PP);
+    float* sPart = reinterpret_cast<float*>(sW + B4_W_BYTES);    // pull: [2 parities][32 rows][B4_PP]; push: [2][4 sources][32 rows][B4_RP]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + B4_XCHG_FLOATS);
     uint64_t* full = bars;                       // [2]
     uint64_t* wbar = bars + 2;
     uint64_t* accum_full = bars + 3;
@@ -460,11 +464,25 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
                         tmem_ld_32x32(tmem_base, a0);
                         tmem_ld_32x32(tmem_base + 32, a1);
                         tmem_ld_wait();
-                        float* dst = mine + lane * B4_PP;
+                        if (p.push) {
+                            // PUSH: the 16 columns rank r' finishes go straight into r's shared memory (slot of THIS source
+                            // rank), so after the barrier every rank sums four LOCAL slices: one DSMEM hop (store + arrive)
+                            // on the critical path instead of three (arrive, then a remote load round trip)
+                            const uint32_t base = smem_u32(sPart) + static_cast<uint32_t>((((par * 4 + rank) * 32 + lane) * B4_RP) * 4);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            *reinterpret_cast<float4*>(dst + j) = make_float4(a0[j], a0[j + 1], a0[j + 2], a0[j + 3]);
-                            *reinterpret_cast<float4*>(dst + 32 + j) = make_float4(a1[j], a1[j + 1], a1[j + 2], a1[j + 3]);
+                            for (int r2 = 0; r2 < B4_CLUSTER; ++r2) {
+                                const uint32_t dst = mapa_shared(base, r2);
+                                const float* src = (r2 < 2) ? (a0 + 16 * r2) : (a1 + 16 * (r2 - 2));
+#pragma unroll
+                                for (int j = 0; j < 16; j += 4) st_dsmem_f4(dst + j * 4, src[j], src[j + 1], src[j + 2], src[j + 3]);
+                            }
+                        } else {
+                            float* dst = mine + lane * B4_PP;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                *reinterpret_cast<float4*>(dst + j) = make_float4(a0[j], a0[j + 1], a0[j + 2], a0[j + 3]);
+                                *reinterpret_cast<float4*>(dst + 32 + j) = make_float4(a1[j], a1[j + 1], a1[j + 2], a1[j + 3]);
+                            }
                         }
                     }
                     tc_fence_before();
@@ -477,11 +495,19 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
                 mbar_wait_cluster(&part_bar[par], (rs >> 1) & 1, p.status, 236);
                 if (et == 0) FT_TRACE(p, t, 1);               // all partials visible
                 if (has_item) {
-                    const uint32_t off = static_cast<uint32_t>((par * 32 * B4_PP + ib * B4_PP + B4_OWN * rank + 4 * uq) * 4);
+                    if (p.push) {
 #pragma unroll
-                    for (int rr = 0; rr < B4_CLUSTER; ++rr) {
-                        const float4 v = ld_dsmem_f4(part_remote[rr] + off);
-                        rec[0] += v.x; rec[1] += v.y; rec[2] += v.z; rec[3] += v.w;
+                        for (int rr = 0; rr < B4_CLUSTER; ++rr) {
+                            const float4 v = *reinterpret_cast<const float4*>(sPart + ((par * 4 + rr) * 32 + ib) * B4_RP + 4 * uq);
+                            rec[0] += v.x; rec[1] += v.y; rec[2] += v.z; rec[3] += v.w;
+                        }
+                    } else {
+                        const uint32_t off = static_cast<uint32_t>((par * 32 * B4_PP + ib * B4_PP + B4_OWN * rank + 4 * uq) * 4);
+#pragma unroll
+                        for (int rr = 0; rr < B4_CLUSTER; ++rr) {
+                            const float4 v = ld_dsmem_f4(part_remote[rr] + off);
+                            rec[0] += v.x; rec[1] += v.y; rec[2] += v.z; rec[3] += v.w;
+                        }
                     }
                 }
             }
@@ -547,17 +573,26 @@ struct LstmFwdChunkParams : LstmFwdParams {
     int t0, t1;                // steps [t0, t1); flags: [(t1 - t0) * 16] ints, zeroed by the launcher
 };
 
-template <int FWD_GS, int FWD_UNITS>
+// kXIn: the layer's INPUT projection is folded into the recurrent contraction (narrow inputs: the attention LSTM's 80 mel
+// channels).  The step's input row block x_t ([B, <=128] fp16, zero-filled by TMA beyond the real width) is loaded next to
+// h_{t-1} as XCH more K chunks, W_ih's slice sits next to W_hh's in shared memory, and b_ih + b_hh are added in the epilogue:
+// no [T*B, 4096] fp32 projection tensor is written (0.5 ms GEMM + 524 MB write + 524 MB read per flow at B=32, T=1000).
+// Requires x_0 == 0 (the teacher-forcing shift guarantees it): step 0 has no contraction at all.
+constexpr int XCH = 2;                                           // extra K chunks (128 input channels max)
+
+template <int FWD_GS, int FWD_UNITS, bool kXIn>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
-lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, LstmFwdChunkParams p) {
+lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmWx,
+                const __grid_constant__ CUtensorMap tmX, LstmFwdChunkParams p) {
     constexpr int FWD_NG = FWD_NCH / FWD_GS;                     // TMA groups per step
-    constexpr int FWD_N = 4 * FWD_UNITS, FWD_W_BYTES = FWD_NCH * FWD_N * 128, FWD_PROD = KCH / FWD_UNITS;
+    constexpr int NCHT = FWD_NCH + (kXIn ? XCH : 0);             // K chunks per step: h (16) [+ x (2)]
+    constexpr int FWD_N = 4 * FWD_UNITS, FWD_W_BYTES = NCHT * FWD_N * 128, FWD_PROD = KCH / FWD_UNITS;
     constexpr int AP = FWD_N + 1;                                // accumulator staging pitch
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int slot_bytes = p.Bbox * 128;
-    uint8_t* sA = smem;                                          // [16 chunks][Bbox rows][128 B]
-    uint8_t* sW = smem + FWD_NCH * slot_bytes;                   // the M=128 over-read of the last chunks lands here
+    uint8_t* sA = smem;                                          // [16 (+2) chunks][Bbox rows][128 B]: h chunks, then x chunks
+    uint8_t* sW = smem + NCHT * slot_bytes;                      // the M=128 over-read of the last chunks lands here
     float* sAcc = reinterpret_cast<float*>(sW + FWD_W_BYTES);    // [32 * nq rows][AP]
     const int nq = (p.B + 31) / 32;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + ((nq * 32 * AP + 1) & ~1));
@@ -573,6 +608,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmW);
         tma_prefetch_desc(&tmH);
+        if (kXIn) { tma_prefetch_desc(&tmWx); tma_prefetch_desc(&tmX); }
         for (int g = 0; g < FWD_NG; ++g) mbar_init(&full[g], 1);
         mbar_init(wbar, 1);
         mbar_init(accum_full, 1);
@@ -591,6 +627,10 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             for (int kc = 0; kc < FWD_NCH; ++kc)
                 for (int g = 0; g < 4; ++g)
                     tma_load_2d(sW + kc * (FWD_N * 128) + g * (FWD_UNITS * 128), &tmW, wbar, kc * KCH, g * LH + FWD_UNITS * cta);
+            if (kXIn)                                          // W_ih slice behind it: chunks 16, 17 (columns beyond the input width: 0)
+                for (int kc = 0; kc < XCH; ++kc)
+                    for (int g = 0; g < 4; ++g)
+                        tma_load_2d(sW + (FWD_NCH + kc) * (FWD_N * 128) + g * (FWD_UNITS * 128), &tmWx, wbar, kc * KCH, g * LH + FWD_UNITS * cta);
         }
         for (int t = tm0; t < p.t1; ++t) {
             // as in lstm_fwd_kernel; the first step of a chunk has nothing to wait for: h_{t0-1} was written by the
@@ -603,8 +643,13 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 FT_TRACE(p, t, 6);
 #pragma unroll
                 for (int g = 0; g < FWD_NG; ++g) {
-                    mbar_expect_tx(&full[g], FWD_GS * slot_bytes);
+                    mbar_expect_tx(&full[g], (FWD_GS + ((kXIn && g == 0) ? XCH : 0)) * slot_bytes);
                     tma_load_3d(sA + g * FWD_GS * slot_bytes, &tmH, &full[g], 0, (t - 1) * p.B, g * FWD_GS);
+                }
+                if (kXIn) {                                    // x_t rides on the first group's barrier
+#pragma unroll
+                    for (int kc = 0; kc < XCH; ++kc)
+                        tma_load_2d(sA + (FWD_NCH + kc) * slot_bytes, &tmX, &full[0], kc * KCH, t * p.B);
                 }
                 FT_TRACE(p, t, 1);
             }
@@ -627,12 +672,23 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 if (elect_one()) {
                     if (g == 0) FT_TRACE(p, t, 2);
                     if (g == FWD_NG - 1) FT_TRACE(p, t, 5);
+                    if (kXIn && g == 0) {                       // the input chunks arrived with group 0: they open the accumulation
+                        uint64_t ya = da_base + FWD_NCH * a_chunk, yb = db_base + FWD_NCH * b_chunk;
+#pragma unroll
+                        for (int c = 0; c < XCH; ++c) {
+#pragma unroll
+                            for (int k = 0; k < KCH / 16; ++k)
+                                umma_f16(tmem_d, ya + 2 * k, yb + 2 * k, idesc, (c | k) != 0);
+                            ya += a_chunk;
+                            yb += b_chunk;
+                        }
+                    }
                     uint64_t xa = da, xb = db;
 #pragma unroll
                     for (int c = 0; c < FWD_GS; ++c) {
 #pragma unroll
                         for (int k = 0; k < KCH / 16; ++k)
-                            umma_f16(tmem_d, xa + 2 * k, xb + 2 * k, idesc, (g | c | k) != 0);
+                            umma_f16(tmem_d, xa + 2 * k, xb + 2 * k, idesc, kXIn || (g | c | k) != 0);
                         xa += a_chunk;
                         xb += b_chunk;
                     }
@@ -669,12 +725,33 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 }
             }
         }
+        float bias[2][8];                                     // kXIn: b_ih + b_hh of this thread's (gate, unit) pairs
+        if (kXIn) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int item = et + s * EPI_THREADS;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bias[s][j] = 0.f;
+                if (item < n_items) {
+                    const int up = item % UP;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int r = g * LH + u0 + 2 * up;
+                        bias[s][2 * g] = p.b_ih[r] + p.b_hh[r];
+                        bias[s][2 * g + 1] = p.b_ih[r + 1] + p.b_hh[r + 1];
+                    }
+                }
+            }
+        }
         for (int t = p.t0; t < p.t1; ++t) {
             float x[2][8];                                    // [item][gate*2 + e]
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 const int item = et + s * EPI_THREADS;
-                if (item < n_items) {
+                if (kXIn) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[s][j] = bias[s][j];
+                } else if (item < n_items) {
                     const int b = item / UP, up = item % UP;
                     const float* src = p.xproj + (static_cast<long long>(t) * p.B + b) * LG + u0 + 2 * up;
 #pragma unroll
@@ -800,26 +877,37 @@ static bool g_half_sm = false;       // 64-CTA forward kernel (for two concurren
 void set_lstm_half_sm(int on) { g_half_sm = on != 0; }
 
 // Steps [t0, t1) of one layer's forward recurrence on 1024 / UNITS CTAs.  `flags` needs (t1 - t0) * 16 ints.
-template <int GS, int UNITS>
+// x16 != null: folded input projection (kXIn): x16 [T*B, kx] fp16 (row pitch ldx), wih16 [4096, kx] fp16, biases fp32.
+template <int GS, int UNITS, bool kXIn>
 static int launch_fwd_t(int T, int B, int t0, int t1, const float* xproj, const void* whh16, const int* lens, void* hseq16,
-                        long long ldh, void* gates16, float* cstate, float* h32, long long ldh32, int* flags, cudaStream_t st) {
-    constexpr int N = 4 * UNITS, W_BYTES = FWD_NCH * N * 128, CTAS = LH / UNITS;
+                        long long ldh, void* gates16, float* cstate, float* h32, long long ldh32, int* flags, cudaStream_t st,
+                        const void* x16 = nullptr, long long ldx = 0, int kx = 0, const void* wih16 = nullptr,
+                        const float* b_ih = nullptr, const float* b_hh = nullptr) {
+    constexpr int NCHT = FWD_NCH + (kXIn ? XCH : 0);
+    constexpr int N = 4 * UNITS, W_BYTES = NCHT * N * 128, CTAS = LH / UNITS;
     LstmFwdChunkParams p;
     p.T = T; p.B = B; p.Bbox = (B + 7) & ~7; p.t0 = t0; p.t1 = t1;
-    p.xproj = xproj; p.lens = lens; p.hseq = static_cast<__half*>(hseq16); p.ldh = ldh;
+    p.xproj = xproj; p.b_ih = b_ih; p.b_hh = b_hh; p.lens = lens; p.hseq = static_cast<__half*>(hseq16); p.ldh = ldh;
     p.gates = static_cast<__half*>(gates16); p.cstate = cstate; p.h32 = h32; p.ldh32 = ldh32;
     p.flags = flags; p.status = ft_status_word(); p.trace = (t0 == 0 && t1 == T) ? g_lstm_trace : nullptr;
     const int slot = p.Bbox * 128, nq = (B + 31) / 32;
-    const int smem = FWD_NCH * slot + W_BYTES + nq * 32 * (N + 1) * 4 + 8 + 256 + 1024;
+    const int smem = NCHT * slot + W_BYTES + nq * 32 * (N + 1) * 4 + 8 + 256 + 1024;
     if (smem > smem_optin()) return ft_set_error("lstm_fwd: not enough shared memory");
-    CUtensorMap tmW, tmH;
+    CUtensorMap tmW, tmH, tmWx, tmX;
     if (make_tmap_2d(&tmW, whh16, FMT_F16, LG, LH, LH, KCH, UNITS)) return -1;
     if (make_tmap_chunks(&tmH, hseq16, static_cast<long long>(T) * B, FWD_NCH, ldh, p.Bbox, GS)) return -1;
+    if (kXIn) {
+        if (kx <= 0 || kx > XCH * KCH) return ft_set_error("lstm_fwd: folded input width must be in (0, 128]");
+        if (make_tmap_2d(&tmWx, wih16, FMT_F16, LG, kx, kx, KCH, UNITS)) return -1;
+        if (make_tmap_2d(&tmX, x16, FMT_F16, static_cast<long long>(T) * B, kx, ldx, KCH, p.Bbox)) return -1;
+    } else {
+        tmWx = tmW; tmX = tmH;                                   // unused
+    }
     if (cudaMemsetAsync(flags, 0, sizeof(int) * (t1 - t0) * FWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_fwd: memset failed");
-    void* fn = reinterpret_cast<void*>(lstm_fwd_kernel<GS, UNITS>);
+    void* fn = reinterpret_cast<void*>(lstm_fwd_kernel<GS, UNITS, kXIn>);
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     TimeScope ts("lstm_fwd", t1 - t0, B, 0, st);
-    void* args[] = {&tmW, &tmH, &p};
+    void* args[] = {&tmW, &tmH, &tmWx, &tmX, &p};
     cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(CTAS), dim3(LSTM_THREADS), args, smem, st);
     if (e != cudaSuccess) return ft_set_error(cudaGetErrorString(e));
     ft_count_launch(1);
@@ -830,12 +918,25 @@ int launch_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const i
                     void* gates16, float* cstate, float* h32, long long ldh32, int* flags, cudaStream_t st) {
     if (T <= 0 || B <= 0) return 0;
     if (B > 64) return ft_set_error("lstm_fwd: batch > 64 per call not supported (split the batch)");
-    if (g_half_sm && B <= 32) return launch_fwd_t<8, 16>(T, B, 0, T, xproj, whh16, lens, hseq16, ldh, gates16, cstate, h32, ldh32, flags, st);
+    if (g_half_sm && B <= 32) return launch_fwd_t<8, 16, false>(T, B, 0, T, xproj, whh16, lens, hseq16, ldh, gates16, cstate, h32, ldh32, flags, st);
     static int gs = -1;            // FT_LSTM_FWD_GS: K-chunks per TMA group (16 / gs groups per step), tuning knob
     if (gs < 0) { const char* e = getenv("FT_LSTM_FWD_GS"); gs = e ? atoi(e) : 8; }
-    if (gs == 4) return launch_fwd_t<4, 8>(T, B, 0, T, xproj, whh16, lens, hseq16, ldh, gates16, cstate, h32, ldh32, flags, st);
-    if (gs == 16) return launch_fwd_t<16, 8>(T, B, 0, T, xproj, whh16, lens, hseq16, ldh, gates16, cstate, h32, ldh32, flags, st);
-    return launch_fwd_t<8, 8>(T, B, 0, T, xproj, whh16, lens, hseq16, ldh, gates16, cstate, h32, ldh32, flags, st);
+    if (gs == 4) return launch_fwd_t<4, 8, false>(T, B, 0, T, xproj, whh16, lens, hseq16, ldh, gates16, cstate, h32, ldh32, flags, st);
+    if (gs == 16) return launch_fwd_t<16, 8, false>(T, B, 0, T, xproj, whh16, lens, hseq16, ldh, gates16, cstate, h32, ldh32, flags, st);
+    return launch_fwd_t<8, 8, false>(T, B, 0, T, xproj, whh16, lens, hseq16, ldh, gates16, cstate, h32, ldh32, flags, st);
+}
+
+// Whole sequence with the input projection folded in (narrow inputs, kx <= 128; x16 row 0..B-1 must be zero: step 0 skips the
+// contraction).  128 CTAs (or 64 with the half-SM switch).
+int launch_lstm_fwd_xin(int T, int B, const void* x16, long long ldx, int kx, const void* wih16, const float* b_ih, const float* b_hh,
+                        const void* whh16, const int* lens, void* hseq16, long long ldh, void* gates16, float* cstate, float* h32,
+                        long long ldh32, int* flags, cudaStream_t st) {
+    if (T <= 0 || B <= 0) return 0;
+    if (B > 64) return ft_set_error("lstm_fwd: batch > 64 per call not supported (split the batch)");
+    if (!x16 || !wih16 || !b_ih || !b_hh) return ft_set_error("lstm_fwd_xin: NULL argument");
+    if (g_half_sm && B <= 32)
+        return launch_fwd_t<8, 16, true>(T, B, 0, T, nullptr, whh16, lens, hseq16, ldh, gates16, cstate, h32, ldh32, flags, st, x16, ldx, kx, wih16, b_ih, b_hh);
+    return launch_fwd_t<8, 8, true>(T, B, 0, T, nullptr, whh16, lens, hseq16, ldh, gates16, cstate, h32, ldh32, flags, st, x16, ldx, kx, wih16, b_ih, b_hh);
 }
 
 // Steps [t0, t1) of a layer on 64 CTAs (layer pipeline, ar_step.cu).  `flags` needs (t1 - t0) * 16 ints.
@@ -844,7 +945,7 @@ int launch_lstm_fwd_chunk(int T, int B, int t0, int t1, const float* xproj, cons
     if (T <= 0 || B <= 0 || t1 <= t0) return 0;
     if (B > 64 || t0 < 0 || t1 > T) return ft_set_error("lstm_fwd_chunk: bad batch or step range");
     if (t0 > 0 && !cstate) return ft_set_error("lstm_fwd_chunk: resuming a chunk needs the saved cell states");
-    return launch_fwd_t<8, 16>(T, B, t0, t1, xproj, whh16, lens, hseq16, ldh, gates16, cstate, nullptr, 0, flags, st);
+    return launch_fwd_t<8, 16, false>(T, B, t0, t1, xproj, whh16, lens, hseq16, ldh, gates16, cstate, nullptr, 0, flags, st);
 }
 
 // Steps [t0, t1) of a layer's BPTT with the split-K cluster kernel, B <= 32.  `flags` needs (t1 - t0) * 64 ints; `dc_carry`
@@ -861,7 +962,10 @@ static int launch_bwd4(int T, int B, int t0, int t1, const float* dh_ext, long l
     if (make_tmap_2d(&tmWT, whhT16, FMT_F16, LH, LG, LG, KCH, B4_UNITS)) return -1;
     if (make_tmap_chunks(&tmG, dG16, static_cast<long long>(T) * B, BWD_NCH, LG, p.Bbox, 8)) return -1;
     if (cudaMemsetAsync(flags, 0, sizeof(int) * (t1 - t0) * BWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_bwd: memset failed");
-    const int smem = B4_NCH * slot + B4_W_BYTES + 2 * 32 * B4_PP * 4 + 256 + 1024;
+    static int push = -1;          // FT_BWD_PUSH=0: the round-1 pull exchange (A/B)
+    if (push < 0) { const char* e = getenv("FT_BWD_PUSH"); push = (!e || atoi(e) != 0) ? 1 : 0; }
+    p.push = push;
+    const int smem = B4_NCH * slot + B4_W_BYTES + B4_XCHG_FLOATS * 4 + 256 + 1024;
     cudaFuncSetAttribute(lstm_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(B4_CTAS); cfg.blockDim = dim3(LSTM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;

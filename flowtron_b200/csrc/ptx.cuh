@@ -116,6 +116,10 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cluster_addr) {
     return v;
 }
 
+__device__ __forceinline__ void st_dsmem_f4(uint32_t cluster_addr, float a, float b, float c, float d) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ------------------------------------------------------------------------------------ fences
 __device__ __forceinline__ void fence_proxy_async() {          // generic <-> async proxy (all spaces)
     asm volatile("fence.proxy.async;" ::: "memory");
