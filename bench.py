@@ -577,7 +577,8 @@ def run_mel(args):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
-        traffic = (json.load(open(tp)).get("mel_fused") or {}).get("dram_bytes_per_launch")
+        per_frame = (json.load(open(tp)).get("mel_fused") or {}).get("dram_bytes_per_frame")
+        traffic = per_frame * frames if per_frame and fmt == "f32" else None     # captured on a 2000-utterance launch, scaled by frames
     res = {
         "metric": "mel front-end mel-frames/sec", "value": fps, "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
