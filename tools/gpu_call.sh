@@ -32,10 +32,11 @@ tests)
   timeout 900 python -m pytest tests -q -m gpu -rfE --tb=short -p no:cacheprovider > $O/${TAG}_tests.txt 2>&1; echo "pytest rc=$?"; tail -25 $O/${TAG}_tests.txt ;;
 train)
   bench train_default X=1 -- --steps 5 --warmup 3 --no-cpu-baseline
-  bench train_gemm_v1 FT_GEMM_V1=1 -- --steps 5 --warmup 3 --no-cpu-baseline
-  bench train_fused_opt FT_FUSED_OPT=1 -- --steps 5 --warmup 3 --no-cpu-baseline
-  bench train_fused_v1 FT_FUSED_OPT=1 FT_GEMM_V1=1 -- --steps 5 --warmup 3 --no-cpu-baseline
-  bench train_eager FT_GRAPH=0 -- --steps 5 --warmup 3 --no-cpu-baseline ;;
+  bench train_noxin FT_LSTM_XIN=0 -- --steps 5 --warmup 3 --no-cpu-baseline
+  bench train_pull FT_BWD_PUSH=0 -- --steps 5 --warmup 3 --no-cpu-baseline ;;
+trace)
+  timeout 120 python tools/trace_lstm.py 32 > $O/${TAG}_trace_lstm.txt 2>&1; echo "trace rc=$?"; cat $O/${TAG}_trace_lstm.txt
+  FT_BWD_PUSH=0 timeout 120 python tools/trace_lstm.py 32 > $O/${TAG}_trace_lstm_pull.txt 2>&1; grep -A12 "== backward" $O/${TAG}_trace_lstm_pull.txt ;;
 cfg3)
   bench train_cfg3 X=1 -- --config 3 --steps 5 --warmup 3 --no-cpu-baseline ;;
 tlgraph)
