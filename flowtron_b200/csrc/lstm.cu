@@ -305,9 +305,8 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant_
 //   * pointwise LSTM backward + dG_t stores + per-chunk release flags exactly as in the single-CTA kernel.
 constexpr int B4_CTAS = 64, B4_CLUSTER = 4, B4_UNITS = 64, B4_OWN = 16, B4_NCH = LH / KCH;     // 16 chunks / step / rank
 constexpr int B4_W_BYTES = B4_NCH * B4_UNITS * 128;                                               // 128 KB
-constexpr int B4_PP = 68;                                                                          // partial row pitch (floats), pull form
-constexpr int B4_RP = 20;                                                                          // received-slice row pitch (floats), push form
-constexpr int B4_XCHG_FLOATS = 2 * 4 * 32 * B4_RP;                                                 // [2 parities][4 sources][32 rows][B4_RP] >= 2*32*B4_PP
+constexpr int B4_UP = 36;                                                                          // received-slice row pitch (floats): 32 batch columns, 16-byte aligned rows
+constexpr int B4_XCHG_FLOATS = 2 * 4 * 16 * B4_UP;                                                 // [2 parities][4 source ranks][16 units][B4_UP]
 
 // The kernel runs steps [t0, t1) of the sequence, highest step first: the whole sequence in one launch (t0 = 0, t1 = T), or
 // one chunk of the layer pipeline (ar_step.cu), resuming dc*f from `dc_carry` ([B,1024] fp32, written by the chunk above) and
@@ -316,7 +315,6 @@ constexpr int B4_XCHG_FLOATS = 2 * 4 * 32 * B4_RP;                              
 struct LstmBwdChunkParams : LstmBwdParams {
     int t0, t1;                // steps [t0, t1); flags: [(t1 - t0) * 64] ints, zeroed by the launcher
     float* dc_carry;           // [B, 1024]
-    int push;                  // 1: partial sums are pushed into the finishing rank's shared memory (default); 0: pulled over DSMEM
 };
 
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
@@ -326,7 +324,7 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
     const int slot_bytes = p.Bbox * 128;
     uint8_t* sA = smem;                                          // [16 chunks][Bbox rows][128 B]
     uint8_t* sW = smem + B4_NCH * slot_bytes;                    // [16 chunks][64 rows][128 B]
-    float* sPart = reinterpret_cast<float*>(sW + B4_W_BYTES);    // pull: [2 parities][32 rows][B4_PP]; push: [2][4 sources][32 rows][B4_RP]
+    float* sPart = reinterpret_cast<float*>(sW + B4_W_BYTES);    // received partial sums: [2 parities][4 source ranks][16 units][B4_UP]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + B4_XCHG_FLOATS);
     uint64_t* full = bars;                       // [2]
     uint64_t* wbar = bars + 2;
@@ -350,7 +348,7 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
         mbar_init(&part_bar[0], B4_CLUSTER); mbar_init(&part_bar[1], B4_CLUSTER);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<64>(tmem_slot);
+    if (warp == 1) tmem_alloc<32>(tmem_slot);                    // accumulator: 64 lanes (units) x Bbox <= 32 columns
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -382,10 +380,11 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
         }
     } else if (warp == 1) {
         mbar_wait(wbar, 0, p.status, 233);
-        const uint32_t idesc = umma_idesc(128, B4_UNITS, FMT_F16, FMT_F16, 0, 0);
+        // swapped operands (see lstm_fwd_kernel): A = resident W_hh^T block (M = 64 units), B = dG_{t+1} quarter (N = Bbox rows)
+        const uint32_t idesc = umma_idesc(64, p.Bbox, FMT_F16, FMT_F16, 0, 0);
         const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
-        const uint64_t da_base = umma_smem_desc(smem_u32(sA), 16, 1024), db_base = umma_smem_desc(smem_u32(sW), 16, 1024);
-        const uint64_t a_chunk = static_cast<uint64_t>(slot_bytes >> 4), b_chunk = (B4_UNITS * 128) >> 4;
+        const uint64_t da_base = umma_smem_desc(smem_u32(sW), 16, 1024), db_base = umma_smem_desc(smem_u32(sA), 16, 1024);
+        const uint64_t a_chunk = (B4_UNITS * 128) >> 4, b_chunk = static_cast<uint64_t>(slot_bytes >> 4);
         int step = 0;
         for (int t = t_hi; t >= p.t0; --t, ++step) {
             const int ph = step & 1;
@@ -426,9 +425,6 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
             const float4 cv = *reinterpret_cast<const float4*>(p.dc_carry + static_cast<long long>(ib) * LH + B4_UNITS * cl + B4_OWN * rank + 4 * uq);
             dcs[0] = cv.x; dcs[1] = cv.y; dcs[2] = cv.z; dcs[3] = cv.w;
         }
-        uint32_t part_remote[B4_CLUSTER];
-#pragma unroll
-        for (int r = 0; r < B4_CLUSTER; ++r) part_remote[r] = mapa_shared(smem_u32(sPart), r);
         int step = 0;
         for (int t = p.t1 - 1; t >= p.t0; --t, ++step) {
             const int rs = top ? step - 1 : step;                 // index of this step among the steps with a recurrent term
@@ -454,40 +450,26 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
             float rec[4] = {0.f, 0.f, 0.f, 0.f};                 // recurrent part of dh_t: sum over the 4 ranks' partials
             if (rs >= 0) {
                 const int par = rs & 1;
-                float* mine = sPart + par * 32 * B4_PP;
-                if (q == 0) {                                     // B <= 32: TMEM rows 0..31 hold the batch rows
-                    mbar_wait(accum_full, rs & 1, p.status, 235);
-                    tc_fence_after();
-                    if (et == 64) FT_TRACE(p, t, 4);
-                    {
-                        float a0[32], a1[32];
-                        tmem_ld_32x32(tmem_base, a0);
-                        tmem_ld_32x32(tmem_base + 32, a1);
-                        tmem_ld_wait();
-                        if (p.push) {
-                            // PUSH: the 16 columns rank r' finishes go straight into r's shared memory (slot of THIS source
-                            // rank), so after the barrier every rank sums four LOCAL slices: one DSMEM hop (store + arrive)
-                            // on the critical path instead of three (arrive, then a remote load round trip)
-                            const uint32_t base = smem_u32(sPart) + static_cast<uint32_t>((((par * 4 + rank) * 32 + lane) * B4_RP) * 4);
+                // Accumulator rows = the cluster block's 64 units: quadrant q (= this warp) holds units [16q, 16q+16), exactly the
+                // units rank q finishes.  PUSH: each warp sends its 16 x Bbox partial sums straight into rank q's shared memory
+                // (slot of THIS source rank, [unit][batch] rows of 32 floats), then one release-arrive per rank publishes them
+                // and every rank sums four LOCAL slices -- one DSMEM hop on the critical path (r1 pulled: arrive, then a remote
+                // load round trip), and all four epilogue warps move data instead of one.
+                mbar_wait(accum_full, rs & 1, p.status, 235);
+                tc_fence_after();
+                if (et == 64) FT_TRACE(p, t, 4);
+                {
+                    float acc[32];
+                    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16), acc);
+                    tmem_ld_wait();
+                    if (lane < 16) {
+                        const uint32_t dst = mapa_shared(smem_u32(sPart) + static_cast<uint32_t>((((par * 4 + rank) * 16 + lane) * B4_UP) * 4), q);
 #pragma unroll
-                            for (int r2 = 0; r2 < B4_CLUSTER; ++r2) {
-                                const uint32_t dst = mapa_shared(base, r2);
-                                const float* src = (r2 < 2) ? (a0 + 16 * r2) : (a1 + 16 * (r2 - 2));
-#pragma unroll
-                                for (int j = 0; j < 16; j += 4) st_dsmem_f4(dst + j * 4, src[j], src[j + 1], src[j + 2], src[j + 3]);
-                            }
-                        } else {
-                            float* dst = mine + lane * B4_PP;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                *reinterpret_cast<float4*>(dst + j) = make_float4(a0[j], a0[j + 1], a0[j + 2], a0[j + 3]);
-                                *reinterpret_cast<float4*>(dst + 32 + j) = make_float4(a1[j], a1[j + 1], a1[j + 2], a1[j + 3]);
-                            }
-                        }
+                        for (int j = 0; j < 32; j += 4) st_dsmem_f4(dst + j * 4, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
                     }
-                    tc_fence_before();
-                    if (et == 64) FT_TRACE(p, t, 6);
                 }
+                tc_fence_before();
+                if (et == 64) FT_TRACE(p, t, 6);
                 epi_bar();
                 // publish: one release-arrive on every rank's barrier, issued by 4 different threads so the four
                 // cluster-scope releases overlap (issued serially by one thread they cost ~1.8 us per step)
@@ -495,19 +477,11 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
                 mbar_wait_cluster(&part_bar[par], (rs >> 1) & 1, p.status, 236);
                 if (et == 0) FT_TRACE(p, t, 1);               // all partials visible
                 if (has_item) {
-                    if (p.push) {
 #pragma unroll
-                        for (int rr = 0; rr < B4_CLUSTER; ++rr) {
-                            const float4 v = *reinterpret_cast<const float4*>(sPart + ((par * 4 + rr) * 32 + ib) * B4_RP + 4 * uq);
-                            rec[0] += v.x; rec[1] += v.y; rec[2] += v.z; rec[3] += v.w;
-                        }
-                    } else {
-                        const uint32_t off = static_cast<uint32_t>((par * 32 * B4_PP + ib * B4_PP + B4_OWN * rank + 4 * uq) * 4);
+                    for (int rr = 0; rr < B4_CLUSTER; ++rr) {
+                        const float* src = sPart + ((par * 4 + rr) * 16 + 4 * uq) * B4_UP + ib;
 #pragma unroll
-                        for (int rr = 0; rr < B4_CLUSTER; ++rr) {
-                            const float4 v = ld_dsmem_f4(part_remote[rr] + off);
-                            rec[0] += v.x; rec[1] += v.y; rec[2] += v.z; rec[3] += v.w;
-                        }
+                        for (int j = 0; j < 4; ++j) rec[j] += src[j * B4_UP];
                     }
                 }
             }
@@ -560,7 +534,7 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                          // nobody exits while a peer may still read its partials
-    if (warp == 1) tmem_dealloc<64>(tmem_base);
+    if (warp == 1) tmem_dealloc<32>(tmem_base);
 }
 
 
@@ -586,20 +560,22 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmX, LstmFwdChunkParams p) {
     constexpr int FWD_NG = FWD_NCH / FWD_GS;                     // TMA groups per step
     constexpr int NCHT = FWD_NCH + (kXIn ? XCH : 0);             // K chunks per step: h (16) [+ x (2)]
+    constexpr int A_SLOTS = FWD_NCH + (kXIn ? 2 * XCH : 0);      // x_t is double-buffered: it is prefetched one step ahead
     constexpr int FWD_N = 4 * FWD_UNITS, FWD_W_BYTES = NCHT * FWD_N * 128, FWD_PROD = KCH / FWD_UNITS;
     constexpr int AP = FWD_N + 1;                                // accumulator staging pitch
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int slot_bytes = p.Bbox * 128;
-    uint8_t* sA = smem;                                          // [16 (+2) chunks][Bbox rows][128 B]: h chunks, then x chunks
-    uint8_t* sW = smem + NCHT * slot_bytes;                      // the M=128 over-read of the last chunks lands here
+    uint8_t* sA = smem;                                          // [16 (+2x2) chunks][Bbox rows][128 B]: h chunks, then two x buffers
+    uint8_t* sW = smem + A_SLOTS * slot_bytes;
     float* sAcc = reinterpret_cast<float*>(sW + FWD_W_BYTES);    // [32 * nq rows][AP]
     const int nq = (p.B + 31) / 32;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + ((nq * 32 * AP + 1) & ~1));
     uint64_t* full = bars;                       // [FWD_NG] (<= 16)
     uint64_t* wbar = bars + 16;
     uint64_t* accum_full = bars + 17;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t* xfull = bars + 18;                 // [2] (kXIn)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x;
@@ -612,9 +588,10 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         for (int g = 0; g < FWD_NG; ++g) mbar_init(&full[g], 1);
         mbar_init(wbar, 1);
         mbar_init(accum_full, 1);
+        mbar_init(&xfull[0], 1); mbar_init(&xfull[1], 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<(FWD_N < 32 ? 32 : FWD_N)>(tmem_slot);
+    if (warp == 1) tmem_alloc<64>(tmem_slot);             // accumulator: 64 lanes (W rows) x Bbox <= 64 columns
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -632,9 +609,15 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     for (int g = 0; g < 4; ++g)
                         tma_load_2d(sW + (FWD_NCH + kc) * (FWD_N * 128) + g * (FWD_UNITS * 128), &tmWx, wbar, kc * KCH, g * LH + FWD_UNITS * cta);
         }
+        if (kXIn && tm0 < p.t1 && elect_one()) {               // x of the first contraction step: no dependency, load it now
+            mbar_expect_tx(&xfull[0], XCH * slot_bytes);
+#pragma unroll
+            for (int kc = 0; kc < XCH; ++kc) tma_load_2d(sA + (FWD_NCH + kc) * slot_bytes, &tmX, &xfull[0], kc * KCH, tm0 * p.B);
+        }
+        __syncwarp();
         for (int t = tm0; t < p.t1; ++t) {
-            // as in lstm_fwd_kernel; the first step of a chunk has nothing to wait for: h_{t0-1} was written by the
-            // previous launch on this stream (kernel boundary) and the A buffer is untouched
+            // the first step of a chunk has nothing to wait for: h_{t0-1} was written by the previous launch on this stream
+            // (kernel boundary) and the A buffer is untouched
             if (t > p.t0 && lane < FWD_NCH) wait_flag_ge(&p.flags[(t - 1 - p.t0) * FWD_NCH + lane], FWD_PROD, p.status, 212);
             __syncwarp();
             if (elect_one()) {
@@ -643,13 +626,18 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 FT_TRACE(p, t, 6);
 #pragma unroll
                 for (int g = 0; g < FWD_NG; ++g) {
-                    mbar_expect_tx(&full[g], (FWD_GS + ((kXIn && g == 0) ? XCH : 0)) * slot_bytes);
+                    mbar_expect_tx(&full[g], FWD_GS * slot_bytes);
                     tma_load_3d(sA + g * FWD_GS * slot_bytes, &tmH, &full[g], 0, (t - 1) * p.B, g * FWD_GS);
                 }
-                if (kXIn) {                                    // x_t rides on the first group's barrier
+                if (kXIn && t + 1 < p.t1) {
+                    // x_{t+1} does not depend on the recurrence: prefetch it one step ahead (it comes from HBM, not from L2
+                    // like h: riding on this step's barrier cost 0.6 us per step).  Its buffer was last read by step t-1's MMAs,
+                    // which have retired (all flags of step t-1, ours included, were seen above).
+                    const int xs = (t + 1 - tm0) & 1;
+                    mbar_expect_tx(&xfull[xs], XCH * slot_bytes);
 #pragma unroll
                     for (int kc = 0; kc < XCH; ++kc)
-                        tma_load_2d(sA + (FWD_NCH + kc) * slot_bytes, &tmX, &full[0], kc * KCH, t * p.B);
+                        tma_load_2d(sA + (FWD_NCH + xs * XCH + kc) * slot_bytes, &tmX, &xfull[xs], kc * KCH, (t + 1) * p.B);
                 }
                 FT_TRACE(p, t, 1);
             }
@@ -658,22 +646,29 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     } else if (warp == 1) {
         // warp-uniform loop, one elected lane issues (see gemm.cu: descriptors must be uniform-register operands)
         mbar_wait(wbar, 0, p.status, 213);
-        const uint32_t idesc = umma_idesc(128, FWD_N, FMT_F16, FMT_F16, 0, 0);
+        // SWAPPED operands (r2): A = the resident W slice (M = 64 accumulator rows: the CTA's 4*UNITS gate rows, plus -- for
+        // UNITS = 8 -- 32 don't-care rows read from the next chunk), B = h_{t-1} (N = Bbox batch rows, exactly what TMA
+        // delivered).  The r1 form (A = h padded to M = 128, B = W) made every instruction read 128 rows x 32 B of A from
+        // shared memory, 3/4 of it padding: 5-6 KB per MMA against the SM's 128 B/clk = 40-48 clk per instruction instead of the
+        // 16-clk tensor floor (trace: 64 MMAs took 1.2-1.5 us of a 4-5 us step).  Now 2 KB + 1 KB per instruction.
+        const uint32_t idesc = umma_idesc(64, p.Bbox, FMT_F16, FMT_F16, 0, 0);
         const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
-        const uint64_t da_base = umma_smem_desc(smem_u32(sA), 16, 1024), db_base = umma_smem_desc(smem_u32(sW), 16, 1024);
-        const uint64_t a_chunk = static_cast<uint64_t>(slot_bytes >> 4), b_chunk = (FWD_N * 128) >> 4;
+        const uint64_t da_base = umma_smem_desc(smem_u32(sW), 16, 1024), db_base = umma_smem_desc(smem_u32(sA), 16, 1024);
+        const uint64_t a_chunk = (FWD_N * 128) >> 4, b_chunk = static_cast<uint64_t>(slot_bytes >> 4);
         for (int t = tm0; t < p.t1; ++t) {
             const int ph = (t - tm0) & 1;
             uint64_t da = da_base, db = db_base;
 #pragma unroll
+            if (kXIn) mbar_wait(&xfull[(t - tm0) & 1], ((t - tm0) >> 1) & 1, p.status, 216);
             for (int g = 0; g < FWD_NG; ++g) {
                 mbar_wait(&full[g], ph, p.status, 214);
                 tc_fence_after();
                 if (elect_one()) {
                     if (g == 0) FT_TRACE(p, t, 2);
                     if (g == FWD_NG - 1) FT_TRACE(p, t, 5);
-                    if (kXIn && g == 0) {                       // the input chunks arrived with group 0: they open the accumulation
-                        uint64_t ya = da_base + FWD_NCH * a_chunk, yb = db_base + FWD_NCH * b_chunk;
+                    if (kXIn && g == 0) {                       // the (prefetched) input chunks open the accumulation
+                        const int xs = (t - tm0) & 1;
+                        uint64_t ya = da_base + FWD_NCH * a_chunk, yb = db_base + (FWD_NCH + xs * XCH) * b_chunk;
 #pragma unroll
                         for (int c = 0; c < XCH; ++c) {
 #pragma unroll
@@ -762,18 +757,19 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 }
             }
             if (t > 0) {
-                if (q < nq) {                                 // this warp owns TMEM rows [32q, 32q+32)
-                    mbar_wait(accum_full, (t - tm0) & 1, p.status, 215);
+                if (q < FWD_N / 16) {                         // M = 64 accumulator: row r lives in TMEM lane 32 (r / 16) + r % 16
+                    mbar_wait(accum_full, (t - tm0) & 1, p.status, 215);     // (measured on B200: tools/probe/m64_layout.cu)
                     tc_fence_after();
                     if (et == 64) FT_TRACE(p, t, 4);          // warp 4 == quadrant 0
-                    float* dst = sAcc + (q * 32 + lane) * AP;
-#pragma unroll
-                    for (int h = 0; h < FWD_N / 32; ++h) {
+                    const int r = 16 * q + lane;              // W-slice row = gate * UNITS + unit (lanes 16..31 hold nothing)
+                    for (int h = 0; h < nq; ++h) {            // 32 batch columns at a time
                         float acc[32];
                         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 32, acc);
                         tmem_ld_wait();
+                        if (lane < 16) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) dst[h * 32 + j] = acc[j];
+                            for (int j = 0; j < 32; ++j) sAcc[(h * 32 + j) * AP + r] = acc[j];   // [batch][row]: readers unchanged
+                        }
                     }
                     tc_fence_before();
                 }
@@ -837,7 +833,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<(FWD_N < 32 ? 32 : FWD_N)>(tmem_base);
+    if (warp == 1) tmem_dealloc<64>(tmem_base);
 }
 
 
@@ -891,7 +887,7 @@ static int launch_fwd_t(int T, int B, int t0, int t1, const float* xproj, const 
     p.gates = static_cast<__half*>(gates16); p.cstate = cstate; p.h32 = h32; p.ldh32 = ldh32;
     p.flags = flags; p.status = ft_status_word(); p.trace = (t0 == 0 && t1 == T) ? g_lstm_trace : nullptr;
     const int slot = p.Bbox * 128, nq = (B + 31) / 32;
-    const int smem = NCHT * slot + W_BYTES + nq * 32 * (N + 1) * 4 + 8 + 256 + 1024;
+    const int smem = (FWD_NCH + (kXIn ? 2 * XCH : 0)) * slot + W_BYTES + nq * 32 * (N + 1) * 4 + 8 + 256 + 1024;
     if (smem > smem_optin()) return ft_set_error("lstm_fwd: not enough shared memory");
     CUtensorMap tmW, tmH, tmWx, tmX;
     if (make_tmap_2d(&tmW, whh16, FMT_F16, LG, LH, LH, KCH, UNITS)) return -1;
@@ -962,9 +958,6 @@ static int launch_bwd4(int T, int B, int t0, int t1, const float* dh_ext, long l
     if (make_tmap_2d(&tmWT, whhT16, FMT_F16, LH, LG, LG, KCH, B4_UNITS)) return -1;
     if (make_tmap_chunks(&tmG, dG16, static_cast<long long>(T) * B, BWD_NCH, LG, p.Bbox, 8)) return -1;
     if (cudaMemsetAsync(flags, 0, sizeof(int) * (t1 - t0) * BWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_bwd: memset failed");
-    static int push = -1;          // FT_BWD_PUSH=0: the round-1 pull exchange (A/B)
-    if (push < 0) { const char* e = getenv("FT_BWD_PUSH"); push = (!e || atoi(e) != 0) ? 1 : 0; }
-    p.push = push;
     const int smem = B4_NCH * slot + B4_W_BYTES + B4_XCHG_FLOATS * 4 + 256 + 1024;
     cudaFuncSetAttribute(lstm_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaLaunchConfig_t cfg = {};

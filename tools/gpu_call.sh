@@ -33,10 +33,10 @@ tests)
 train)
   bench train_default X=1 -- --steps 5 --warmup 3 --no-cpu-baseline
   bench train_noxin FT_LSTM_XIN=0 -- --steps 5 --warmup 3 --no-cpu-baseline
-  bench train_pull FT_BWD_PUSH=0 -- --steps 5 --warmup 3 --no-cpu-baseline ;;
+  ;;
 trace)
   timeout 120 python tools/trace_lstm.py 32 > $O/${TAG}_trace_lstm.txt 2>&1; echo "trace rc=$?"; cat $O/${TAG}_trace_lstm.txt
-  FT_BWD_PUSH=0 timeout 120 python tools/trace_lstm.py 32 > $O/${TAG}_trace_lstm_pull.txt 2>&1; grep -A12 "== backward" $O/${TAG}_trace_lstm_pull.txt ;;
+  ;;
 cfg3)
   bench train_cfg3 X=1 -- --config 3 --steps 5 --warmup 3 --no-cpu-baseline ;;
 tlgraph)
