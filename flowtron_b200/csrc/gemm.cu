@@ -1,18 +1,17 @@
-// tcgen05 + TMA GEMM for sm_100a:  C[M,N] = act(A[M,K] * B[N,K]^T + bias (+bias2)) (+ C if beta)
+// tcgen05 + TMA GEMM for sm_100a:  C[M,N] = act(alpha * A[M,K] * B[N,K]^T + bias (+bias2)) (+ C if beta)
 //
-//  * operands 16-bit (f16 / bf16, kind::f16, UMMA_K=16) or tf32 (fp32 storage, kind::tf32, UMMA_K=8),
-//    fp32 accumulation in TMEM;
-//  * operand tiles staged by TMA (SWIZZLE_128B) into a 3-stage mbarrier ring; 2 CTAs/SM so one CTA's
-//    epilogue overlaps the other's main loop;
-//  * each operand may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows], i.e. the
-//    transposed view of a natural activation/gradient tensor) -- this is what lets dW = dY^T X and
-//    dX = dY W run on the tensors exactly as the forward pass left them (no transposes);
-//  * warp roles: w0 = TMA producer, w1 = TMEM alloc + single-thread MMA issue, w2..w5 = epilogue
-//    (TMEM -> registers -> bias/tanh/accumulate -> 128-bit global stores, fp32 and/or 16-bit copy).
+//  * operands 16-bit (f16 / bf16, kind::f16, UMMA_K=16) or tf32 (fp32 storage, kind::tf32, UMMA_K=8), fp32 accumulation in
+//    TMEM; each operand may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows], i.e. the transposed view of a
+//    natural activation / gradient tensor) -- this is what lets dW = dY^T X and dX = dY W run on the tensors exactly as the
+//    forward pass left them (no transposes anywhere);
+//  * persistent: one CTA per SM walks a static tile list; 4/6-stage TMA ring (SWIZZLE_128B), double-buffered TMEM
+//    accumulators, epilogue overlapped with the next tile's main loop, optional split-K (details at gemm2_kernel).
+//  * warp roles: w0 = TMA producer, w1 = TMEM alloc + single-thread MMA issue, w2..w5 = epilogue.
 //
-// Used for every non-recurrent contraction on the Flowtron hot path (LSTM input projections
-// flowtron.py:654-655, attention Q/K/V projections :568-571, DenseLayer :461-464, 1x1 conv :768, and
-// all their dgrad/wgrad counterparts).
+// Used for every non-recurrent contraction on the Flowtron hot path (LSTM input projections flowtron.py:654-655, attention
+// Q/K/V projections :568-571, DenseLayer :461-464, 1x1 conv :768, and all their dgrad/wgrad counterparts).
+// The round-1 kernel (non-persistent 128x128 tiles, 3 stages, 2 CTAs/SM) was measured against this one on the training step
+// (profiles/r2_c3_train_gemm_v1.json: 60.7 vs 60.3 ms/step, GEMM kernel time 19.0 vs 15.8 ms) and removed.
 #include <cstdlib>
 
 #include "ptx.cuh"
@@ -20,10 +19,8 @@
 
 namespace ft {
 
-constexpr int BM = 128, BN = 128, STAGES = 3;
-constexpr int TILE_BYTES = BM * 128;               // 128 rows x 128 B (one SW128 row per matrix row)
-constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_SMEM = STAGES * 2 * TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int BM = 128;
+constexpr int TILE_BYTES = BM * 128;               // A tile of one stage: 128 rows x 128 B (one SW128 row per matrix row)
 
 struct GemmParams {
     int M, N, K;
@@ -42,184 +39,6 @@ struct GemmParams {
     int splitk = 1;            // v2 only: K is cut into `splitk` ranges, partial tiles are atomically added into a zeroed C32
 };
 
-template <bool kTf32>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * TILE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGES * TILE_BYTES);
-    uint64_t* full = bars;                 // [STAGES]
-    uint64_t* empty = bars + STAGES;       // [STAGES]
-    uint64_t* accum_full = bars + 2 * STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile_n = blockIdx.x, tile_m = blockIdx.y;
-    constexpr int ELT = kTf32 ? 4 : 2;
-    constexpr int BK = 128 / ELT;          // elements per 128-byte swizzle row
-    constexpr int UK = 32 / ELT;           // K per tcgen05.mma
-    const int num_kb = (p.K + BK - 1) / BK;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(accum_full, 1);
-        fence_mbar_init();
-    }
-    if (warp == 1) tmem_alloc<BN>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    // Producer / MMA warps run their loops warp-uniformly and only the instruction issue is predicated on one elected
-    // lane: operands of UTMALDG / UTCHMMA must live in uniform registers, and computing them inside an `if (lane == 0)`
-    // region makes the compiler wrap every issue in an R2UR + ELECT "waterfall" loop (~60 clk per MMA, measured).
-    if (warp == 0) {
-        // ------------------------------------------------ TMA producer
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-            mbar_wait(&empty[s], ph ^ 1, p.status, 101);
-            uint8_t* a = sA + s * TILE_BYTES;
-            uint8_t* b = sB + s * TILE_BYTES;
-            if (elect_one()) {
-                mbar_expect_tx(&full[s], 2 * TILE_BYTES);
-                if (!p.a_mn) {
-                    tma_load_2d(a, &tmA, &full[s], kb * BK, tile_m * BM);             // box {BK, 128 rows}
-                } else {                                                                // box {BK mn-elems, BK k-rows} x (BM/BK)
-                    for (int j = 0; j < BM / BK; ++j)
-                        tma_load_2d(a + j * (BK * 128), &tmA, &full[s], tile_m * BM + j * BK, kb * BK);
-                }
-                if (!p.b_mn) {
-                    tma_load_2d(b, &tmB, &full[s], kb * BK, tile_n * BN);
-                } else {
-                    for (int j = 0; j < BN / BK; ++j)
-                        tma_load_2d(b + j * (BK * 128), &tmB, &full[s], tile_n * BN + j * BK, kb * BK);
-                }
-            }
-            __syncwarp();
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer (one elected lane issues)
-        const uint32_t idesc = umma_idesc(BM, BN, p.a_fmt, p.b_fmt, p.a_mn, p.b_mn);
-        const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
-        // K-major : rows 128 B apart, 8-row groups 1024 B apart (SBO); K step = 32 B inside the row.
-        // MN-major: k-rows 128 B apart, 8-k-row groups 1024 B apart (SBO), MN atoms BK*128 B apart (LBO); K step = UK k-rows.
-        const uint64_t da0 = p.a_mn ? umma_smem_desc(smem_u32(sA), BK * 128, 1024) : umma_smem_desc(smem_u32(sA), 16, 1024);
-        const uint64_t db0 = p.b_mn ? umma_smem_desc(smem_u32(sB), BK * 128, 1024) : umma_smem_desc(smem_u32(sB), 16, 1024);
-        const uint64_t ka = p.a_mn ? (UK * 128) >> 4 : 2, kbs = p.b_mn ? (UK * 128) >> 4 : 2;   // per-MMA K advance (16-byte units)
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-            mbar_wait(&full[s], ph, p.status, 102);
-            tc_fence_after();
-            const uint64_t da = da0 + static_cast<uint64_t>(s * (TILE_BYTES >> 4)), db = db0 + static_cast<uint64_t>(s * (TILE_BYTES >> 4));
-            if (elect_one()) {
-#pragma unroll
-                for (int k = 0; k < BK / UK; ++k) {
-                    const uint32_t acc = (kb | k) != 0;
-                    if (kTf32) umma_tf32(tmem_d, da + k * ka, db + k * kbs, idesc, acc);
-                    else       umma_f16(tmem_d, da + k * ka, db + k * kbs, idesc, acc);
-                }
-                umma_commit(&empty[s]);                 // frees the smem slot once these MMAs retire
-                if (kb == num_kb - 1) umma_commit(accum_full);
-            }
-            __syncwarp();
-        }
-    } else {
-        // ---------------------------------------------------- epilogue warps (TMEM lane quadrant = warp % 4)
-        // TMEM -> registers (lane = row) -> alpha/bias/tanh -> this warp's staging tile in the (now idle) pipeline
-        // buffers -> row-wise, fully coalesced global stores (one 512-byte row per warp instruction).  The first
-        // version stored straight from registers: 32 lanes x 16 B into 32 different rows per instruction, which
-        // capped the N=4096 projection GEMMs at ~0.64 TB/s of output bandwidth.
-        const int q = warp & 3;
-        const int row0 = q * 32;
-        mbar_wait(accum_full, 0, p.status, 103);               // all MMAs retired: smem stages are free
-        tc_fence_after();
-        constexpr int SP = BN + 4;                             // staging pitch (floats)
-        float* stage = reinterpret_cast<float*>(smem) + q * 32 * SP;      // 4 x 32 x 132 x 4 B = 67.6 KB <= 96 KB
-        const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
-        const int ncols = min(BN, p.N - tile_n * BN);
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            const int n0 = tile_n * BN + c * 32;
-            if (c * 32 >= ncols) break;                        // warp-uniform
-            float v[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(row0) << 16) + c * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float x = v[j] * alpha;
-                if (c * 32 + j < ncols) {
-                    if (p.bias) x += __ldg(p.bias + n0 + j);
-                    if (p.bias2) x += __ldg(p.bias2 + n0 + j);
-                }
-                if (p.act == 1) x = tanh_f(x);
-                v[j] = x;
-            }
-            float* dst = stage + lane * SP + c * 32;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-        __syncwarp();
-        // write phase: each iteration handles one row of this warp's 32; lane l owns columns 4l..4l+3
-        const int col = 4 * lane;
-        const bool vec_ok = (ncols == BN);
-#pragma unroll 1
-        for (int r = 0; r < 32; ++r) {
-            const long long m = static_cast<long long>(tile_m) * BM + row0 + r;
-            if (m >= p.M) break;                               // warp-uniform
-            const float4 s4 = *reinterpret_cast<const float4*>(stage + r * SP + col);
-            float x[4] = {s4.x, s4.y, s4.z, s4.w};
-            const int nc = tile_n * BN + col;
-            if (p.act == 2) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (col + j < ncols) { const float y = __half2float(p.aux16[m * p.ldaux + nc + j]); x[j] *= (1.f - y * y); }
-            }
-            if (p.C32) {
-                float* dst = p.C32 + m * p.ldc32 + nc;
-                if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                    float4 o = make_float4(x[0], x[1], x[2], x[3]);
-                    if (p.beta) { const float4 c0 = *reinterpret_cast<const float4*>(dst); o.x += c0.x; o.y += c0.y; o.z += c0.z; o.w += c0.w; }
-                    *reinterpret_cast<float4*>(dst) = o;
-                    x[0] = o.x; x[1] = o.y; x[2] = o.z; x[3] = o.w;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (col + j < ncols) { if (p.beta) x[j] += dst[j]; dst[j] = x[j]; }
-                }
-            }
-            if (p.C16) {
-                uint16_t* dst = reinterpret_cast<uint16_t*>(p.C16) + m * p.ldc16 + nc;
-                uint32_t pk[2];
-                if (p.c16_fmt == 0) {      // fp16: saturate instead of overflowing to inf
-                    __half2 h0 = __floats2half2_rn(fminf(fmaxf(x[0], -65504.f), 65504.f), fminf(fmaxf(x[1], -65504.f), 65504.f));
-                    __half2 h1 = __floats2half2_rn(fminf(fmaxf(x[2], -65504.f), 65504.f), fminf(fmaxf(x[3], -65504.f), 65504.f));
-                    pk[0] = *reinterpret_cast<uint32_t*>(&h0); pk[1] = *reinterpret_cast<uint32_t*>(&h1);
-                } else {
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(x[0], x[1]), h1 = __floats2bfloat162_rn(x[2], x[3]);
-                    pk[0] = *reinterpret_cast<uint32_t*>(&h0); pk[1] = *reinterpret_cast<uint32_t*>(&h1);
-                }
-                if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
-                    *reinterpret_cast<uint2*>(dst) = make_uint2(pk[0], pk[1]);
-                } else {
-                    const uint16_t* ps = reinterpret_cast<const uint16_t*>(pk);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (col + j < ncols) dst[j] = ps[j];
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc<BN>(tmem_base);
-}
-
-// ================================================================================================ v2: persistent kernel
 // One CTA per SM walks a static list of 128 x BN output tiles (BN = 256, or 128 for narrow outputs):
 //   * a 4-stage (BN = 256: 48 KB per stage) / 6-stage (BN = 128) TMA ring feeds one elected thread issuing
 //     tcgen05.mma 128 x BN x 16: one stage is 512 (256) tensor-core clocks, so the ring covers ~2000 clocks of TMA latency
@@ -521,7 +340,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
     if (!g.a_mn) rc = make_tmap_2d(&tmA, g.A, g.a_fmt, g.M, g.K, g.lda, BK, BM);
     else         rc = make_tmap_2d(&tmA, g.A, g.a_fmt, g.K, g.M, g.lda, BK, BK);
     if (rc) return rc;
-    if (!g.b_mn) rc = make_tmap_2d(&tmB, g.B, g.b_fmt, g.N, g.K, g.ldb, BK, BN);
+    if (!g.b_mn) rc = make_tmap_2d(&tmB, g.B, g.b_fmt, g.N, g.K, g.ldb, BK, 128);
     else         rc = make_tmap_2d(&tmB, g.B, g.b_fmt, g.K, g.N, g.ldb, BK, BK);
     if (rc) return rc;
     GemmParams p;
@@ -529,9 +348,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
     p.bias = g.bias; p.bias2 = g.bias2; p.act = g.act; p.alpha_ptr = g.alpha_ptr; p.aux16 = static_cast<const __half*>(g.aux16); p.ldaux = g.ldaux; p.beta = g.beta; p.alpha = g.alpha;
     p.C32 = g.C32; p.ldc32 = g.ldc32; p.C16 = g.C16; p.ldc16 = g.ldc16; p.c16_fmt = g.c16_fmt;
     p.status = ft_status_word();
-    static int use_v1 = -1;              // FT_GEMM_V1=1: the round-1 non-persistent 128x128 kernel (A/B comparisons)
-    if (use_v1 < 0) { const char* e = getenv("FT_GEMM_V1"); use_v1 = (e && atoi(e) != 0) ? 1 : 0; }
-    if (!use_v1) {
+    {
         static int sms = 0;
         if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
         bool wide = (g.N % 256 == 0) || g.N > 1024;
@@ -579,18 +396,6 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
         ft_count_launch(1);
         return ft_check_launch("gemm2_kernel");
     }
-    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-        cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-        attr_set = true;
-    }
-    TimeScope ts(g.a_mn ? "gemm_wgrad" : (g.b_mn ? "gemm_dgrad" : "gemm_fwd"), g.M, g.N, g.K, st);
-    if (tf32) gemm_kernel<true><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmB, p);
-    else      gemm_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmB, p);
-    ft_count_launch(1);
-    return ft_check_launch("gemm_kernel");
 }
 
 }  // namespace ft

@@ -42,10 +42,12 @@ struct InferParams {
     int* status;
 };
 
+// Grid barrier: one release-add per CTA on a monotonic counter, one acquiring poller per CTA.  The release (gpu scope) after the
+// CTA barrier is cumulative over every thread's earlier writes, so no separate __threadfence() is needed (r1 had one: a second
+// full fence on the critical path of each of the 9 barriers per frame).
 __device__ __forceinline__ void grid_sync(const InferParams& p, int& epoch) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
         ++epoch;
         red_release_add(p.barrier, 1);
         wait_flag_ge(p.barrier, epoch * static_cast<int>(gridDim.x), p.status, 301);
