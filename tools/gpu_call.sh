@@ -37,6 +37,9 @@ train)
 trace)
   timeout 120 python tools/trace_lstm.py 32 > $O/${TAG}_trace_lstm.txt 2>&1; echo "trace rc=$?"; cat $O/${TAG}_trace_lstm.txt
   ;;
+driver)
+  bench bench_default X=1 -- 
+  bench bench_reference X=1 -- --impl reference ;;
 cfg3)
   bench train_cfg3 X=1 -- --config 3 --steps 5 --warmup 3 --no-cpu-baseline ;;
 tlgraph)
