@@ -325,7 +325,7 @@ int ar_step_fwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
     // tensor: -0.5 ms GEMM, -1 GB of HBM traffic per flow); h lands in d16[:, 0:H].  FT_LSTM_XIN=0: separate GEMM (r1 path).
     static int xin = -1;
     if (xin < 0) { const char* e = getenv("FT_LSTM_XIN"); xin = (!e || atoi(e) != 0) ? 1 : 0; }
-    if (xin && n.M <= 128) {
+    if (xin && n.M <= 128 && n.B <= 32) {      // B > 32: the double-buffered x tile no longer fits next to a 64-row h tile
         FT_TRY(launch_lstm_fwd_xin(n.T, n.B, S.mel_in16, n.M, n.M, F.w.w_ih_a, w.attn_lstm_b_ih, w.attn_lstm_b_hh, F.w.w_hh_a, out_lens,
                                    S.d16, n.D, S.gatesA, S.cA, F.hA32, H, F.flags, st));
     } else {
