@@ -228,3 +228,42 @@ def test_encoder_streams_and_overlap_equal_serial():
                 # schedules differ only in the order of fp32 atomic accumulation (attention reductions, split-K weight
                 # gradients); tensors that are small sums of large partials see a few 1e-4 of their own norm
                 assert d <= 1e-3 * (g1[k].norm().item() + 1e-4 * gmax), (flags, k, d)
+
+
+def test_batch_above_32_uses_the_wide_paths_and_matches_split_runs():
+    """B in (32, 64] takes different kernels (no folded attention-LSTM projection, no layer pipeline, single-CTA-ownership
+    BPTT): rows must equal the same utterances run as two B = 20 batches, and the backward must produce the same gradients
+    as the sum of the two halves (cfg 3 runs B = 64 per GPU)."""
+    from flowtron_b200 import _lib
+    from flowtron_b200.flowtron import FlowtronLoss
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = dict(synth.DEFAULT_MODEL_CONFIG, n_flows=2)
+    batch = synth.synth_batch(40, 150, 16, cfg, 41, with_prior=True)
+    cu = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+    def run(sl):
+        model = build_model(cfg, 43)
+        model.train()
+        model.encoder.p_dropout = 0.0
+        Lp = int(cu["in_lens"][sl].max())
+        out = model(cu["mel"][sl], cu["speaker_ids"][sl], cu["text"][sl][:, :Lp].contiguous(), cu["in_lens"][sl], cu["out_lens"][sl],
+                    cu["attn_prior"][sl][:, :, :Lp].contiguous())
+        nll, gl, _ = FlowtronLoss()(out, cu["gate_target"][sl], cu["in_lens"][sl], cu["out_lens"][sl])
+        n = cu["out_lens"][sl].sum().float()
+        ((nll + gl).sum() * n).backward()                       # un-normalised: the two halves' gradients add up to the whole
+        torch.cuda.synchronize()
+        return out, {k: p.grad.clone() for k, p in model.named_parameters()}
+
+    full, gf = run(slice(0, 40))
+    a, ga = run(slice(0, 20))
+    b, gb = run(slice(20, 40))
+    assert _lib.device_status() == 0
+    T = 150
+    vm = (torch.arange(T, device="cuda")[:, None] < cu["out_lens"][None, :])
+    for part, sl in ((a, slice(0, 20)), (b, slice(20, 40))):
+        ez = (full[0][:, sl] - part[0])[vm[:, sl]].abs().max().item() / full[0].abs().max().item()
+        assert ez <= 1e-3, ez
+    gmax = max(v.norm().item() for v in gf.values())
+    for k in gf:
+        d = (gf[k] - (ga[k] + gb[k])).norm().item()
+        assert d <= 2e-2 * (gf[k].norm().item() + 1e-3 * gmax), (k, d, gf[k].norm().item())
