@@ -3,11 +3,22 @@
 // (z - b)/exp(log_s) -> gate  runs for all T frames without returning to the host (the reference issues ~25
 // launches and one host sync per frame, and re-projects K/V every frame; here K/V are projected once).
 //
-// Parallelisation: every matrix-vector phase is split into warp tasks of 4 weight rows (for the LSTMs: the 4
-// gates of one hidden unit, so the cell update happens in the same warp); a task streams its rows from L2
-// (fp16, 128-bit loads), the activations of the phase are staged once per CTA in shared memory (fp16, batch
-// tile of 8), accumulation is fp32, and 9 grid-wide barriers per frame order the phases.  Same operand
-// precision as the training kernels (fp16 operands, fp32 state), so forward(infer(z)) closes to ~1e-3.
+// Round-2 design (r1 was warp-per-4-rows CUDA-core FMAs: B=16 cost 2.9x B=1, 9 grid barriers per frame, loads issued one
+// dependent iteration at a time):
+//   * every matrix-vector phase runs on the TENSOR CORES with the batch as the M = 16 rows of mma.sync.m16n8k16 and 8 weight
+//     rows as N, so batches up to 16 cost what B = 1 costs.  Why warp-level mma.sync and not tcgen05: a tcgen05 instruction
+//     needs M >= 64 rows and BOTH operands in shared memory -- for an N <= 16 matvec that is 2.5-3 KB of shared-memory operand
+//     reads (20+ clk) per K = 16 plus a shared-memory staging pass for 54 MB of weights per frame, while mma.sync takes the
+//     weights straight from L2 into registers (one 16-byte load per lane per 32 k) with no padding rows.  The phase is bound
+//     by L2 latency/bandwidth, not by tensor throughput, either way;
+//   * weights are re-packed ONCE per call into the order the lanes consume them: [task (8 rows)][k-block of 32][row][32 k]
+//     fp16, input and recurrent matrices of an LSTM fused along K (zero padded), so a warp instruction reads 512 contiguous
+//     bytes and issues 8 of them back to back (4 KB in flight per warp, 16 warps per SM);
+//   * a task's K range is split over the warps of a CTA (partial accumulators meet in shared memory), so all 16 warps of
+//     every SM stream weights in every phase;
+//   * score + softmax (+ prior posterior) + context + gate of one utterance run inside ONE CTA (block barriers only):
+//     8 software grid barriers per frame instead of 9 (6 with forced alignments), without the redundant fence.
+// Same operand precision as the training kernels (fp16 operands, fp32 accumulate/state).
 #include "ptx.cuh"
 #include "ft_internal.h"
 #include "../../include/flowtron_b200.h"
@@ -15,16 +26,18 @@
 namespace ft {
 
 constexpr int IH = 1024, IG = 4096;
-// batch tile IBT is a template parameter (1, 2, 4 or 8): B = 1 must not pay for 8 rows of staging and FMAs
-constexpr int INF_THREADS = 256;
-constexpr int KMAX = 1664 + 1024;      // widest phase input: [d ; h0]
+constexpr int INF_THREADS = 512, INF_WARPS = 16;
+constexpr int KMAX = 1664 + 1024;              // widest phase input: [d ; h0]
+constexpr int KP = KMAX + 32;                  // activation row pitch (halfs): 5440 B = 64 mod 128 -> conflict-free 16-byte reads
+constexpr int XPAD = 96;                       // the 80 mel channels of the attention LSTM's input, padded to 3 k-blocks
+constexpr int LMAX = 256;
 
 struct InferParams {
     int T, B, L, M, A, E, D;
-    // fp16 weights (row-major, PyTorch layouts)
-    const __half *w_ih_a, *w_hh_a, *w_ih0, *w_hh0, *w_ih1, *w_hh1, *wq, *w1, *w2, *wc;
-    // fp32 biases / small vectors
-    const float *b_ih_a, *b_hh_a, *b_ih0, *b_hh0, *b_ih1, *b_hh1, *b1, *b2, *bc, *v, *wg, *bg;
+    // packed fp16 weights ([task][k-block][8 rows][32 k]) and packed fp32 biases ([task][8])
+    const __half *wA, *w0, *w1, *wq, *wd1, *wd2, *wc;
+    const float *bA, *b0, *b1, *bd1, *bd2, *bc;
+    const float *v, *wg, *bg;
     const float* Kp; const float* Vp;      // [L*B, A] projected once
     const float* residual;                 // [T,B,M] flow-time order
     const float* prior;                    // [B,T,L] (row i used at frame i) or null
@@ -36,15 +49,14 @@ struct InferParams {
     float* attn_out;                       // [T,B,L]
     int* n_frames;                         // [B]
     // state (global scratch, zero-initialised by the launcher)
-    float *hA[2], *cA, *h0[2], *c0, *h1[2], *c1, *xprev, *q, *e, *d, *y1, *y2;
+    float *hA[2], *cA, *h0[2], *c0, *h1[2], *c1, *xprev, *q, *d, *y1, *y2;
     int* alive;                            // [B] 1 while the sample is still generating
     int* barrier;                          // monotonic grid barrier counter
     int* status;
 };
 
 // Grid barrier: one release-add per CTA on a monotonic counter, one acquiring poller per CTA.  The release (gpu scope) after the
-// CTA barrier is cumulative over every thread's earlier writes, so no separate __threadfence() is needed (r1 had one: a second
-// full fence on the critical path of each of the 9 barriers per frame).
+// CTA barrier is cumulative over every thread's earlier writes, so no separate __threadfence() is needed.
 __device__ __forceinline__ void grid_sync(const InferParams& p, int& epoch) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -55,96 +67,93 @@ __device__ __forceinline__ void grid_sync(const InferParams& p, int& epoch) {
     __syncthreads();
 }
 
-// stage x[b][0:K] (fp32 global, row pitch ld, batch rows b0..b0+IBT) as fp16 into smem at column offset c0
-template <int IBT>
-__device__ __forceinline__ void stage_x(__half* sx, int c0, const float* src, long long ld, int K, int b0, int B) {
-    for (int i = threadIdx.x; i < IBT * K; i += INF_THREADS) {
-        const int bb = i / K, k = i % K;
-        const int b = b0 + bb;
-        sx[bb * KMAX + c0 + k] = __float2half_rn(b < B ? src[static_cast<long long>(b) * ld + k] : 0.f);
+// activations of a phase: fp32 global [B, K] (row pitch ld) -> fp16 shared [16][KP] at column c0 (batch rows >= B stay zero)
+__device__ __forceinline__ void stage_x(__half* sx, int c0, const float* src, long long ld, int K, int B) {
+    for (int i = threadIdx.x; i < B * K; i += INF_THREADS) {
+        const int b = i / K, k = i - b * K;
+        sx[b * KP + c0 + k] = __float2half_rn(src[static_cast<long long>(b) * ld + k]);
     }
 }
 
-// acc[r][bb] += sum_k W[rows[r], k] * x[bb][c0 + k]   (one warp; K multiple of 8)
-template <int IBT>
-__device__ __forceinline__ void rows4_dot(float (&acc)[4][IBT], const __half* W, int ldw, const int (&rows)[4], int K,
-                                          const __half* sx, int c0, int lane) {
-    for (int k = lane * 8; k < K; k += 256) {
-        float wf[4][8];
+__device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// d[16 batch x 8 rows] += sum over k-blocks [m0, m1) of  x[batch][k] * W[row][k].  Wt: this task's packed weights
+// ([k-block][8 rows][32 k]); lane (n = lane/4, j = lane%4) owns row n and the 8 k values 8j..8j+7 of every block; the k order
+// inside a block is a fixed permutation shared by both operands (any bijection is a valid contraction order):
+// MMA step s in {0,1} of a block uses halfs 4s..4s+3 of the lane's chunk as its (k, k+1, k+8, k+9) slots.
+template <bool kB16>
+__device__ __forceinline__ void mv_partial(const __half* __restrict__ Wt, int m0, int m1, const __half* sx, int lane, float (&d)[4]) {
+    constexpr int U = 8;
+    const uint4* wp = reinterpret_cast<const uint4*>(Wt) + lane;             // block m: + 32 m   (lane = 4 n + j: 16 bytes each)
+    const __half* a_lo = sx + (lane >> 2) * KP + 8 * (lane & 3);
+    const __half* a_hi = a_lo + 8 * KP;
+    for (int m = m0; m < m1; m += U) {
+        uint4 w[U];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const uint4 pk = __ldg(reinterpret_cast<const uint4*>(W + static_cast<long long>(rows[r]) * ldw + k));
-            const __half2* h = reinterpret_cast<const __half2*>(&pk);
+        for (int u = 0; u < U; ++u) w[u] = (m + u < m1) ? __ldg(wp + 32 * (m + u)) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h[j]);
-                wf[r][2 * j] = f.x; wf[r][2 * j + 1] = f.y;
+        for (int u = 0; u < U; ++u) {
+            if (m + u < m1) {
+                const uint4 lo = *reinterpret_cast<const uint4*>(a_lo + 32 * (m + u));
+                uint4 hi = make_uint4(0u, 0u, 0u, 0u);
+                if (kB16) hi = *reinterpret_cast<const uint4*>(a_hi + 32 * (m + u));
+                mma_16816(d, lo.x, hi.x, lo.y, hi.y, w[u].x, w[u].y);
+                mma_16816(d, lo.z, hi.z, lo.w, hi.w, w[u].z, w[u].w);
             }
-        }
-#pragma unroll
-        for (int bb = 0; bb < IBT; ++bb) {
-            const uint4 pk = *reinterpret_cast<const uint4*>(sx + bb * KMAX + c0 + k);
-            const __half2* h = reinterpret_cast<const __half2*>(&pk);
-            float xf[8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h[j]);
-                xf[2 * j] = f.x; xf[2 * j + 1] = f.y;
-            }
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[r][bb] = fmaf(wf[r][j], xf[j], acc[r][bb]);
         }
     }
 }
 
-template <int IBT>
-__device__ __forceinline__ void reduce_acc(float (&acc)[4][IBT]) {
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int bb = 0; bb < IBT; ++bb) {
-            float x = acc[r][bb];
-#pragma unroll
-            for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            acc[r][bb] = x;
-        }
-}
-
-// One LSTM layer step for all hidden units: x = [xa (Ka) ; xb (IH)], weights W_ih [4H,Ka], W_hh [4H,IH]
-template <int IBT>
-__device__ void lstm_phase(const InferParams& p, __half* sx, const __half* W_ih, int Ka, const float* xa, long long lda,
-                           const __half* W_hh, const float* hprev, const float* b_ih, const float* b_hh, float* c,
-                           float* hnew) {
+// One matrix-vector phase: n_tasks tasks of 8 rows, nm k-blocks, each task split over S warps of a CTA.  epi(task, d) is
+// called by the task's first warp (all 32 lanes) with the complete accumulator fragment:
+//   d[0], d[1] = batch row lane/4, rows 2j, 2j+1 of the task (j = lane%4);  d[2], d[3] = batch row lane/4 + 8, same rows.
+template <bool kB16, class Epi>
+__device__ __forceinline__ void mv_phase(const __half* __restrict__ W, int n_tasks, int nm, int S, float* spart, const __half* sx, Epi epi) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gw = blockIdx.x * (INF_THREADS / 32) + warp, nw = gridDim.x * (INF_THREADS / 32);
-    for (int b0 = 0; b0 < p.B; b0 += IBT) {
-        __syncthreads();
-        stage_x<IBT>(sx, 0, xa, lda, Ka, b0, p.B);
-        stage_x<IBT>(sx, Ka, hprev, IH, IH, b0, p.B);
-        __syncthreads();
-        for (int u = gw; u < IH; u += nw) {
-            float acc[4][IBT];
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int bb = 0; bb < IBT; ++bb) acc[r][bb] = 0.f;
-            const int rows[4] = {u, IH + u, 2 * IH + u, 3 * IH + u};
-            rows4_dot<IBT>(acc, W_ih, Ka, rows, Ka, sx, 0, lane);
-            rows4_dot<IBT>(acc, W_hh, IH, rows, IH, sx, Ka, lane);
-            reduce_acc<IBT>(acc);
-            if (lane < IBT && b0 + lane < p.B) {
-                const int b = b0 + lane;
-                float a[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    float s = 0.f;
-#pragma unroll
-                    for (int bb = 0; bb < IBT; ++bb) s = (bb == lane) ? acc[r][bb] : s;
-                    a[r] = s + b_ih[rows[r]] + b_hh[rows[r]];
+    const int tpc = INF_WARPS / S;
+    const int tl = warp / S, split = warp - tl * S;
+    for (int base = blockIdx.x * tpc; base < n_tasks; base += gridDim.x * tpc) {       // CTA-uniform trip count
+        const int task = base + tl;
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        if (task < n_tasks) {
+            const int m0 = nm * split / S, m1 = nm * (split + 1) / S;
+            mv_partial<kB16>(W + static_cast<long long>(task) * nm * 256, m0, m1, sx, lane, d);
+            if (S > 1) *reinterpret_cast<float4*>(spart + (warp * 32 + lane) * 4) = make_float4(d[0], d[1], d[2], d[3]);
+        }
+        if (S > 1) {
+            __syncthreads();
+            if (task < n_tasks && split == 0) {
+                for (int s2 = 1; s2 < S; ++s2) {
+                    const float4 v = *reinterpret_cast<const float4*>(spart + ((warp + s2) * 32 + lane) * 4);
+                    d[0] += v.x; d[1] += v.y; d[2] += v.z; d[3] += v.w;
                 }
-                const float gi = sigmoid_f(a[0]), gf = sigmoid_f(a[1]), gg = tanh_f(a[2]), go = sigmoid_f(a[3]);
+            }
+        }
+        if (task < n_tasks && split == 0) epi(task, d);
+        if (S > 1) __syncthreads();
+    }
+}
+
+// LSTM cell for task = 2 units x 4 gates (rows i0,f0,g0,o0,i1,f1,g1,o1): lane j holds (i,f) [j even] or (g,o) [j odd] of unit j/2
+__device__ __forceinline__ void lstm_epi(const InferParams& p, int task, float (&d)[4], const float* bias, float* c, float* hnew) {
+    const int lane = threadIdx.x & 31, j = lane & 3, r = lane >> 2;
+    const float b0 = bias[task * 8 + 2 * j], b1 = bias[task * 8 + 2 * j + 1];
+    float v[4] = {d[0] + b0, d[1] + b1, d[2] + b0, d[3] + b1};
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = __shfl_xor_sync(0xffffffffu, v[i], 1);          // partner lane holds the other gate pair
+    if ((j & 1) == 0) {
+        const int u = 2 * task + (j >> 1);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int b = r + 8 * half;
+            if (b < p.B) {
+                const float gi = sigmoid_f(v[2 * half]), gf = sigmoid_f(v[2 * half + 1]);
+                const float gg = tanh_f(o[2 * half]), go = sigmoid_f(o[2 * half + 1]);
                 const float cn = gf * c[b * IH + u] + gi * gg;
                 c[b * IH + u] = cn;
                 hnew[b * IH + u] = go * tanh_f(cn);
@@ -153,225 +162,227 @@ __device__ void lstm_phase(const InferParams& p, __half* sx, const __half* W_ih,
     }
 }
 
-// y[b, r] = act(W[r,:] x[b,:] + bias[r]) for r < R (R multiple of 4), K multiple of 8
-template <int IBT>
-__device__ void dense_phase(const InferParams& p, __half* sx, const __half* W, int K, int R, const float* x, long long ldx,
-                            const float* bias, int act, float* y, long long ldy) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gw = blockIdx.x * (INF_THREADS / 32) + warp, nw = gridDim.x * (INF_THREADS / 32);
-    for (int b0 = 0; b0 < p.B; b0 += IBT) {
-        __syncthreads();
-        stage_x<IBT>(sx, 0, x, ldx, K, b0, p.B);
-        __syncthreads();
-        for (int t = gw; t < R / 4; t += nw) {
-            float acc[4][IBT];
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int bb = 0; bb < IBT; ++bb) acc[r][bb] = 0.f;
-            const int rows[4] = {4 * t, 4 * t + 1, 4 * t + 2, 4 * t + 3};
-            rows4_dot<IBT>(acc, W, K, rows, K, sx, 0, lane);
-            reduce_acc<IBT>(acc);
-            if (lane < IBT && b0 + lane < p.B) {
-                const int b = b0 + lane;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    float s = 0.f;
-#pragma unroll
-                    for (int bb = 0; bb < IBT; ++bb) s = (bb == lane) ? acc[r][bb] : s;
-                    s += bias ? bias[rows[r]] : 0.f;
-                    if (act) s = tanh_f(s);
-                    y[static_cast<long long>(b) * ldy + rows[r]] = s;
-                }
-            }
-        }
-    }
-}
-
-template <int IBT>
+template <bool kB16>
 __global__ void __launch_bounds__(INF_THREADS, 1)
 infer_kernel(InferParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __half* sx = reinterpret_cast<__half*>(smem_raw);          // [IBT][KMAX] fp16
+    __half* sx = reinterpret_cast<__half*>(smem_raw);                          // [16][KP] fp16 activations of the phase
+    float* spart = reinterpret_cast<float*>(sx + 16 * KP);                     // [16 warps][32 lanes][4] partial accumulators
+    float* sf = spart + INF_WARPS * 128;                                       // attention scratch: q[A] e[LMAX] d[D]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gw = blockIdx.x * (INF_THREADS / 32) + warp, nw = gridDim.x * (INF_THREADS / 32);
     int epoch = 0;
+    for (int i = threadIdx.x; i < 16 * KP; i += INF_THREADS) sx[i] = __float2half_rn(0.f);     // batch rows >= B and pads: zero forever
+    __syncthreads();
 
     for (int i = 0; i < p.T; ++i) {
         const int cur = i & 1, prv = cur ^ 1;
-        // all samples stopped?  (alive is only written in phase 3 of the previous frame, ordered by grid barriers)
+        // all samples stopped?  (alive is only written in the attention phase of the previous frame, ordered by grid barriers)
         bool any = false;
         for (int b = 0; b < p.B; ++b) any |= (ld_acquire(&p.alive[b]) != 0);
         if (!any) break;
 
-        // ---- P1 attention_lstm step on the previous output frame (zeros at i == 0)
-        lstm_phase<IBT>(p, sx, p.w_ih_a, p.M, p.xprev, p.M, p.w_hh_a, p.hA[prv], p.b_ih_a, p.b_hh_a, p.cA, p.hA[cur]);
+        // ---- P1 attention_lstm step on the previous output frame (zeros at i == 0): x = [out_{i-1} (80 -> 96) ; hA_{i-1}]
+        __syncthreads();
+        stage_x(sx, 0, p.xprev, p.M, p.M, p.B);
+        for (int i2 = threadIdx.x; i2 < p.B * (XPAD - p.M); i2 += INF_THREADS)         // pad columns (later phases stage over them)
+            sx[(i2 / (XPAD - p.M)) * KP + p.M + (i2 % (XPAD - p.M))] = __float2half_rn(0.f);
+        stage_x(sx, XPAD, p.hA[prv], IH, IH, p.B);
+        __syncthreads();
+        mv_phase<kB16>(p.wA, IH / 2, (XPAD + IH) / 32, 4, spart, sx,
+                       [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.bA, p.cA, p.hA[cur]); });
         grid_sync(p, epoch);
-        // forced alignments (`attn` given, flowtron.py:585-588): no query / score / softmax / prior, context = attn . V
-        const bool forced = p.attn_forced != nullptr;
-        // ---- P2a query projection (no bias)
+
+        const bool forced = p.attn_forced != nullptr;    // `attn` given (flowtron.py:585-588): no query / score / softmax / prior
+        // ---- P2 query projection (no bias)
         if (!forced) {
-        dense_phase<IBT>(p, sx, p.wq, IH, p.A, p.hA[cur], IH, nullptr, 0, p.q, p.A);
-        grid_sync(p, epoch);
+            stage_x(sx, 0, p.hA[cur], IH, IH, p.B);
+            __syncthreads();
+            mv_phase<kB16>(p.wq, p.A / 8, IH / 32, INF_WARPS, spart, sx, [&](int task, float (&d)[4]) {
+                const int j = lane & 3, r = lane >> 2;
+                if (r < p.B) { p.q[r * p.A + 8 * task + 2 * j] = d[0]; p.q[r * p.A + 8 * task + 2 * j + 1] = d[1]; }
+                if (kB16 && r + 8 < p.B) { p.q[(r + 8) * p.A + 8 * task + 2 * j] = d[2]; p.q[(r + 8) * p.A + 8 * task + 2 * j + 1] = d[3]; }
+            });
+            grid_sync(p, epoch);
         }
-        // ---- P2b scores e[b,l] = v . tanh(q[b] + K[l,b]) / temperature   (no key mask in inference, flowtron.py:800-803)
-        for (int t = gw; t < p.B * p.L && !forced; t += nw) {
-            const int b = t / p.L, l = t % p.L;
-            const float* kr = p.Kp + (static_cast<long long>(l) * p.B + b) * p.A;
-            float s = 0.f;
-            for (int a = lane; a < p.A; a += 32) s = fmaf(p.v[a], tanh_f(p.q[b * p.A + a] + kr[a]), s);
+        // ---- P3 attention of utterance b inside CTA b: scores e[l] = v . tanh(q + K[l]) / temperature (no key mask in
+        //      inference, flowtron.py:800-803), softmax (+ prior posterior), context, d = [hA ; ctx], gate decision
+        if (static_cast<int>(blockIdx.x) < p.B) {
+            const int b = blockIdx.x;
+            float* sq = sf; float* se = sf + p.A; float* sd = se + LMAX;
+            if (!forced) {
+                for (int a = threadIdx.x; a < p.A; a += INF_THREADS) sq[a] = p.q[b * p.A + a];
+                __syncthreads();
+                for (int l = warp; l < p.L; l += INF_WARPS) {
+                    const float* kr = p.Kp + (static_cast<long long>(l) * p.B + b) * p.A;
+                    float s = 0.f;
+                    for (int a = lane; a < p.A; a += 32) s = fmaf(p.v[a], tanh_f(sq[a] + kr[a]), s);
 #pragma unroll
-            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) p.e[b * p.L + l] = s * p.inv_temperature;
-        }
-        if (!forced) grid_sync(p, epoch);
-        // ---- P2c softmax (+ prior posterior) and context; d = [hA ; ctx]
-        {
-            const int chunks = (p.A + 31) / 32;
-            for (int t = gw; t < p.B * (chunks + 1); t += nw) {
-                const int b = t / (chunks + 1), ch = t % (chunks + 1);
-                // softmax over L in registers: lane holds l = lane + 32 j
-                float w[8];
-                float m = -INFINITY;
-                if (forced) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int l = lane + 32 * j;
-                        w[j] = (l < p.L) ? p.attn_forced[(static_cast<long long>(i) * p.B + b) * p.L + l] : 0.f;
-                    }
-                } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int l = lane + 32 * j;
-                    w[j] = (l < p.L) ? p.e[b * p.L + l] : -INFINITY;
-                    m = fmaxf(m, w[j]);
+                    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    if (lane == 0) se[l] = s * p.inv_temperature;
                 }
+                __syncthreads();
+                if (warp == 0) {                         // softmax over L in registers: lane holds l = lane + 32 jj
+                    float w[8];
+                    float mx = -INFINITY;
 #pragma unroll
-                for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                float s = 0.f;
+                    for (int jj = 0; jj < 8; ++jj) { const int l = lane + 32 * jj; w[jj] = (l < p.L) ? se[l] : -INFINITY; mx = fmaxf(mx, w[jj]); }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { w[j] = (lane + 32 * j < p.L) ? expf(w[j] - m) : 0.f; s += w[j]; }
+                    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    float s = 0.f;
 #pragma unroll
-                for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                const float inv = 1.f / s;
+                    for (int jj = 0; jj < 8; ++jj) { w[jj] = (lane + 32 * jj < p.L) ? expf(w[jj] - mx) : 0.f; s += w[jj]; }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) w[j] *= inv;
-                }
-                if (p.prior && !forced) {
-                    float m2 = -INFINITY;
+                    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    const float inv = 1.f / s;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int l = lane + 32 * j;
-                        if (l < p.L) {
-                            const float pr = p.prior[(static_cast<long long>(b) * p.T + i) * p.L + l];
-                            w[j] = logf(w[j] + 1e-20f) + logf(pr + 1e-20f);
-                            m2 = fmaxf(m2, w[j]);
+                    for (int jj = 0; jj < 8; ++jj) w[jj] *= inv;
+                    if (p.prior) {
+                        float m2 = -INFINITY;
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const int l = lane + 32 * jj;
+                            if (l < p.L) {
+                                const float pr = p.prior[(static_cast<long long>(b) * p.T + i) * p.L + l];
+                                w[jj] = logf(w[jj] + 1e-20f) + logf(pr + 1e-20f);
+                                m2 = fmaxf(m2, w[jj]);
+                            }
                         }
+#pragma unroll
+                        for (int o = 16; o; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+                        float s2 = 0.f;
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) { w[jj] = (lane + 32 * jj < p.L) ? expf(w[jj] - m2) : 0.f; s2 += w[jj]; }
+#pragma unroll
+                        for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                        const float inv2 = 1.f / s2;
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) w[jj] *= inv2;
                     }
 #pragma unroll
-                    for (int o = 16; o; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
-                    float s2 = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { w[j] = (lane + 32 * j < p.L) ? expf(w[j] - m2) : 0.f; s2 += w[j]; }
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                    const float inv2 = 1.f / s2;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) w[j] *= inv2;
+                    for (int jj = 0; jj < 8; ++jj) { const int l = lane + 32 * jj; if (l < p.L) se[l] = w[jj]; }
                 }
-                if (ch == chunks) {                      // this task publishes the attention weights and the hA half of d
+            } else {
+                for (int l = threadIdx.x; l < p.L; l += INF_THREADS) se[l] = p.attn_forced[(static_cast<long long>(i) * p.B + b) * p.L + l];
+            }
+            __syncthreads();
+            for (int l = threadIdx.x; l < p.L; l += INF_THREADS) p.attn_out[(static_cast<long long>(i) * p.B + b) * p.L + l] = se[l];
+            for (int k = threadIdx.x; k < IH; k += INF_THREADS) sd[k] = p.hA[cur][b * IH + k];
+            for (int a = threadIdx.x; a < p.A; a += INF_THREADS) {
+                float c = 0.f;
+                for (int l = 0; l < p.L; ++l) c = fmaf(se[l], p.Vp[(static_cast<long long>(l) * p.B + b) * p.A + a], c);
+                sd[IH + a] = c;
+            }
+            __syncthreads();
+            for (int k = threadIdx.x; k < p.D; k += INF_THREADS) p.d[b * p.D + k] = sd[k];
+            if (warp == 0) {                             // gate decision for this frame (the frame that trips the gate IS emitted, :823-826)
+                if (p.has_gate) {
+                    float s = 0.f;
+                    for (int k = lane; k < p.D; k += 32) s = fmaf(p.wg[k], sd[k], s);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int l = lane + 32 * j;
-                        if (l < p.L) p.attn_out[(static_cast<long long>(i) * p.B + b) * p.L + l] = w[j];
+                    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    if (lane == 0 && p.alive[b]) {
+                        p.n_frames[b] = i + 1;
+                        if (sigmoid_f(s + p.bg[0]) > p.gate_threshold) p.alive[b] = 0;
                     }
-                    for (int k = lane; k < IH; k += 32) p.d[b * p.D + k] = p.hA[cur][b * IH + k];
-                } else {
-                    const int a = ch * 32 + lane;
-                    float c = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int lmax = min(32, p.L - 32 * j);                 // warp-uniform
-                        for (int ll = 0; ll < lmax; ++ll) {
-                            const float wl = __shfl_sync(0xffffffffu, w[j], ll);
-                            if (a < p.A) c = fmaf(wl, p.Vp[(static_cast<long long>(32 * j + ll) * p.B + b) * p.A + a], c);
-                        }
-                    }
-                    if (a < p.A) p.d[b * p.D + IH + a] = c;
+                } else if (lane == 0) {
+                    p.n_frames[b] = i + 1;
                 }
             }
         }
         grid_sync(p, epoch);
-        // ---- P3 lstm layer 0 on d; the gate decision for this frame rides along (one warp per sample)
-        if (p.has_gate) {
-            for (int b = gw; b < p.B; b += nw) {
-                float s = 0.f;
-                for (int k = lane; k < p.D; k += 32) s = fmaf(p.wg[k], p.d[b * p.D + k], s);
-#pragma unroll
-                for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == 0 && p.alive[b]) {
-                    p.n_frames[b] = i + 1;                               // the frame that trips the gate IS emitted (:823-826)
-                    if (sigmoid_f(s + p.bg[0]) > p.gate_threshold) p.alive[b] = 0;
-                }
-            }
-        } else if (gw == 0 && lane < p.B) {
-            p.n_frames[lane] = i + 1;
-        }
-        lstm_phase<IBT>(p, sx, p.w_ih0, p.D, p.d, p.D, p.w_hh0, p.h0[prv], p.b_ih0, p.b_hh0, p.c0, p.h0[cur]);
+        // ---- P4 lstm layer 0 on [d ; h0_{i-1}]
+        stage_x(sx, 0, p.d, p.D, p.D, p.B);
+        stage_x(sx, p.D, p.h0[prv], IH, IH, p.B);
+        __syncthreads();
+        mv_phase<kB16>(p.w0, IH / 2, (p.D + IH) / 32, 4, spart, sx,
+                       [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.b0, p.c0, p.h0[cur]); });
         grid_sync(p, epoch);
-        // ---- P4 lstm layer 1
-        lstm_phase<IBT>(p, sx, p.w_ih1, IH, p.h0[cur], IH, p.w_hh1, p.h1[prv], p.b_ih1, p.b_hh1, p.c1, p.h1[cur]);
+        // ---- P5 lstm layer 1 on [h0 ; h1_{i-1}]
+        stage_x(sx, 0, p.h0[cur], IH, IH, p.B);
+        stage_x(sx, IH, p.h1[prv], IH, IH, p.B);
+        __syncthreads();
+        mv_phase<kB16>(p.w1, IH / 2, 2 * IH / 32, 4, spart, sx,
+                       [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.b1, p.c1, p.h1[cur]); });
         grid_sync(p, epoch);
-        // ---- P5/P6 dense layers
-        dense_phase<IBT>(p, sx, p.w1, IH, IH, p.h1[cur], IH, p.b1, 1, p.y1, IH);
-        grid_sync(p, epoch);
-        dense_phase<IBT>(p, sx, p.w2, IH, IH, p.y1, IH, p.b2, 1, p.y2, IH);
-        grid_sync(p, epoch);
-        // ---- P7 conv + inverse affine: out = (residual - b) / exp(log_s)
-        for (int b0 = 0; b0 < p.B; b0 += IBT) {
+        // ---- P6/P7 dense layers (tanh)
+        auto dense = [&](const __half* W, const float* bias, const float* x, float* y) {
+            stage_x(sx, 0, x, IH, IH, p.B);
             __syncthreads();
-            stage_x<IBT>(sx, 0, p.y2, IH, IH, b0, p.B);
-            __syncthreads();
-            for (int t = gw; t < p.M / 2; t += nw) {
-                float acc[4][IBT];
+            mv_phase<kB16>(W, IH / 8, IH / 32, INF_WARPS, spart, sx, [&](int task, float (&d)[4]) {
+                const int j = lane & 3, r = lane >> 2;
+                const float b0 = bias[task * 8 + 2 * j], b1 = bias[task * 8 + 2 * j + 1];
+                if (r < p.B) { y[r * IH + 8 * task + 2 * j] = tanh_f(d[0] + b0); y[r * IH + 8 * task + 2 * j + 1] = tanh_f(d[1] + b1); }
+                if (kB16 && r + 8 < p.B) { y[(r + 8) * IH + 8 * task + 2 * j] = tanh_f(d[2] + b0); y[(r + 8) * IH + 8 * task + 2 * j + 1] = tanh_f(d[3] + b1); }
+            });
+        };
+        dense(p.wd1, p.bd1, p.h1[cur], p.y1);
+        grid_sync(p, epoch);
+        dense(p.wd2, p.bd2, p.y1, p.y2);
+        grid_sync(p, epoch);
+        // ---- P8 conv + inverse affine: out = (residual - b) / exp(log_s); task rows = (log_s, b) of 4 consecutive channels
+        stage_x(sx, 0, p.y2, IH, IH, p.B);
+        __syncthreads();
+        mv_phase<kB16>(p.wc, p.M / 4, IH / 32, INF_WARPS, spart, sx, [&](int task, float (&d)[4]) {
+            const int j = lane & 3, r = lane >> 2;
+            const int m = 4 * task + j;
+            const float bl = p.bc[task * 8 + 2 * j], bb = p.bc[task * 8 + 2 * j + 1];
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int bb = 0; bb < IBT; ++bb) acc[r][bb] = 0.f;
-                const int rows[4] = {2 * t, 2 * t + 1, p.M + 2 * t, p.M + 2 * t + 1};
-                rows4_dot<IBT>(acc, p.wc, IH, rows, IH, sx, 0, lane);
-                reduce_acc<IBT>(acc);
-                if (lane < IBT && b0 + lane < p.B) {
-                    const int b = b0 + lane;
-                    float o[4];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        float s = 0.f;
-#pragma unroll
-                        for (int bb = 0; bb < IBT; ++bb) s = (bb == lane) ? acc[r][bb] : s;
-                        o[r] = s + p.bc[rows[r]];
-                    }
+            for (int half = 0; half < 2; ++half) {
+                const int b = r + 8 * half;
+                if (b < p.B && (half == 0 || kB16)) {
                     const long long ro = (static_cast<long long>(i) * p.B + b) * p.M;
-                    // a sample that stopped at an earlier frame emits zeros; the frame that trips the gate is
-                    // still emitted, which n_frames (written in P3, ordered by the barriers since) encodes
+                    // a sample that stopped at an earlier frame emits zeros; the frame that trips the gate is still emitted,
+                    // which n_frames (written in P3, ordered by the barriers since) encodes
                     const bool emit = (i < p.n_frames[b]);
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int m = 2 * t + e;
-                        const float val = (p.residual[ro + m] - o[2 + e]) / expf(o[e]);
-                        p.out[ro + m] = emit ? val : 0.f;
-                        p.xprev[b * p.M + m] = val;
-                    }
+                    const float val = (p.residual[ro + m] - (d[2 * half + 1] + bb)) / expf(d[2 * half] + bl);
+                    p.out[ro + m] = emit ? val : 0.f;
+                    p.xprev[b * p.M + m] = val;
                 }
             }
-        }
+        });
         grid_sync(p, epoch);
     }
 }
 
+// ------------------------------------------------------------------------------------------------ weight packing
+// dst[task][m][n][kk] (fp16) <- W[row(task, n)][32 m + kk] over the virtual K = [A part (Ka real columns, padded to Kap) ; B part]
+//   kind 0: LSTM      row = (n % 4) * 1024 + 2 task + n / 4        (rows i0,f0,g0,o0,i1,f1,g1,o1)
+//   kind 1: dense     row = 8 task + n
+//   kind 2: conv pair row = (n % 2) * M + 4 task + n / 2           (log_s, b of 4 consecutive channels)
+// bias_dst[task][n] = b1[row] (+ b2[row])
+__global__ void pack_weights_kernel(__half* __restrict__ dst, float* __restrict__ bias_dst, const float* __restrict__ WA, int Ka, int Kap,
+                                    const float* __restrict__ WB, int Kb, const float* __restrict__ b1, const float* __restrict__ b2,
+                                    int n_tasks, int nm, int kind, int M) {
+    const long long total = static_cast<long long>(n_tasks) * nm * 256;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int kk = static_cast<int>(i & 31), n = static_cast<int>((i >> 5) & 7);
+        const long long tm = i >> 8;
+        const int m = static_cast<int>(tm % nm), task = static_cast<int>(tm / nm);
+        const int row = kind == 0 ? (n & 3) * IH + 2 * task + (n >> 2) : kind == 1 ? 8 * task + n : (n & 1) * M + 4 * task + (n >> 1);
+        const int k = 32 * m + kk;
+        float v = 0.f;
+        if (k < Kap) { if (k < Ka) v = WA[static_cast<long long>(row) * Ka + k]; }
+        else if (WB && k - Kap < Kb) v = WB[static_cast<long long>(row) * Kb + (k - Kap)];
+        dst[i] = __float2half_rn(v);
+        if (m == 0 && kk == 0 && bias_dst) bias_dst[task * 8 + n] = (b1 ? b1[row] : 0.f) + (b2 ? b2[row] : 0.f);
+    }
+}
+
+static int pack(__half* dst, float* bias_dst, const float* WA, int Ka, int Kap, const float* WB, int Kb, const float* b1, const float* b2,
+                int n_tasks, int nm, int kind, int M, cudaStream_t st) {
+    const long long total = static_cast<long long>(n_tasks) * nm * 256;
+    int blocks = static_cast<int>((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pack_weights_kernel<<<blocks, 256, 0, st>>>(dst, bias_dst, WA, Ka, Kap, WB, Kb, b1, b2, n_tasks, nm, kind, M);
+    ft_count_launch(1);
+    return ft_check_launch("pack_weights_kernel");
+}
+
 // ------------------------------------------------------------------------------------------------ host
 struct InferScratch {
-    uint16_t *w_ih_a, *w_hh_a, *w_ih0, *w_hh0, *w_ih1, *w_hh1, *wq, *wk, *wv, *w1, *w2, *wc, *text16;
+    __half *wA, *w0, *w1, *wq, *wd1, *wd2, *wc;
+    float *bA, *b0, *b1, *bd1, *bd2, *bc;
+    uint16_t *wk, *wv, *text16;
     float *Kp, *Vp, *state;
     int* ints;
     size_t state_floats, total;
@@ -382,23 +393,23 @@ static InferScratch plan_infer(const FtArStepDesc& d, uint8_t* base) {
     size_t off = 0;
     auto get = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return base ? base + o : nullptr; };
     const int M = d.n_mel, A = d.n_attn, E = d.n_text, D = IH + A;
-    s.w_ih_a = reinterpret_cast<uint16_t*>(get(size_t(IG) * M * 2));
-    s.w_hh_a = reinterpret_cast<uint16_t*>(get(size_t(IG) * IH * 2));
-    s.w_ih0 = reinterpret_cast<uint16_t*>(get(size_t(IG) * D * 2));
-    s.w_hh0 = reinterpret_cast<uint16_t*>(get(size_t(IG) * IH * 2));
-    s.w_ih1 = reinterpret_cast<uint16_t*>(get(size_t(IG) * IH * 2));
-    s.w_hh1 = reinterpret_cast<uint16_t*>(get(size_t(IG) * IH * 2));
-    s.wq = reinterpret_cast<uint16_t*>(get(size_t(A) * IH * 2));
+    auto wbytes = [](size_t tasks, size_t nm) { return tasks * nm * 256 * 2; };
+    s.wA = reinterpret_cast<__half*>(get(wbytes(IH / 2, (XPAD + IH) / 32)));
+    s.w0 = reinterpret_cast<__half*>(get(wbytes(IH / 2, (D + IH) / 32)));
+    s.w1 = reinterpret_cast<__half*>(get(wbytes(IH / 2, 2 * IH / 32)));
+    s.wq = reinterpret_cast<__half*>(get(wbytes(A / 8, IH / 32)));
+    s.wd1 = reinterpret_cast<__half*>(get(wbytes(IH / 8, IH / 32)));
+    s.wd2 = reinterpret_cast<__half*>(get(wbytes(IH / 8, IH / 32)));
+    s.wc = reinterpret_cast<__half*>(get(wbytes(M / 4, IH / 32)));
+    s.bA = reinterpret_cast<float*>(get(IG * 4)); s.b0 = reinterpret_cast<float*>(get(IG * 4)); s.b1 = reinterpret_cast<float*>(get(IG * 4));
+    s.bd1 = reinterpret_cast<float*>(get(IH * 4)); s.bd2 = reinterpret_cast<float*>(get(IH * 4)); s.bc = reinterpret_cast<float*>(get(2 * M * 4));
     s.wk = reinterpret_cast<uint16_t*>(get(size_t(A) * E * 2));
     s.wv = reinterpret_cast<uint16_t*>(get(size_t(A) * E * 2));
-    s.w1 = reinterpret_cast<uint16_t*>(get(size_t(IH) * IH * 2));
-    s.w2 = reinterpret_cast<uint16_t*>(get(size_t(IH) * IH * 2));
-    s.wc = reinterpret_cast<uint16_t*>(get(size_t(2 * M) * IH * 2));
     s.text16 = reinterpret_cast<uint16_t*>(get(size_t(d.L) * d.B * E * 2));
     s.Kp = reinterpret_cast<float*>(get(size_t(d.L) * d.B * A * 4));
     s.Vp = reinterpret_cast<float*>(get(size_t(d.L) * d.B * A * 4));
-    // state: hA[2], cA, h0[2], c0, h1[2], c1 (9 x B*IH), xprev (B*M), q (B*A), e (B*L), d (B*D), y1, y2 (B*IH)
-    s.state_floats = size_t(d.B) * (9 * IH + M + A + d.L + D + 2 * IH);
+    // state: hA[2], cA, h0[2], c0, h1[2], c1 (9 x B*IH), xprev (B*M), q (B*A), d (B*D), y1, y2 (B*IH)
+    s.state_floats = size_t(d.B) * (9 * IH + M + A + D + 2 * IH);
     s.state = reinterpret_cast<float*>(get(s.state_floats * 4));
     s.ints = reinterpret_cast<int*>(get((size_t(d.B) + 64) * 4));
     s.total = off;
@@ -417,26 +428,24 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
     using namespace ft;
     if (!d || !w || !residual || !text || !out || !attn_out || !n_frames || !scratch) return ft_set_error("ft_ar_step_infer: NULL argument");
     if (d->n_hidden != IH) return ft_set_error("infer: n_hidden must be 1024");
-    if (d->L > 256) return ft_set_error("infer: L > 256 not supported");
-    if (d->B > 64) return ft_set_error("infer: batch > 64 not supported");
-    if (d->n_mel % 8 || d->n_attn % 8 || d->n_text % 8) return ft_set_error("infer: channel counts must be multiples of 8");
+    if (d->L > LMAX) return ft_set_error("infer: L > 256 not supported");
+    if (d->B > 16) return ft_set_error("infer: batch > 16 per call not supported (run the batch in slices of 16)");
+    if (d->n_mel > XPAD || d->n_mel % 8 || d->n_attn % 32 || d->n_text % 8) return ft_set_error("infer: n_mel <= 96 and %8, n_attn %32, n_text %8 required");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     InferScratch s = plan_infer(*d, static_cast<uint8_t*>(scratch));
     const int M = d->n_mel, A = d->n_attn, E = d->n_text, D = IH + A, B = d->B;
     const long long RL = static_cast<long long>(d->L) * B;
 #define FT_TRYX(x) do { if ((x) != 0) return -1; } while (0)
-    FT_TRYX(launch_cast(w->attn_lstm_w_ih, 2, s.w_ih_a, 0, static_cast<long long>(IG) * M, st));
-    FT_TRYX(launch_cast(w->attn_lstm_w_hh, 2, s.w_hh_a, 0, static_cast<long long>(IG) * IH, st));
-    FT_TRYX(launch_cast(w->lstm_w_ih0, 2, s.w_ih0, 0, static_cast<long long>(IG) * D, st));
-    FT_TRYX(launch_cast(w->lstm_w_hh0, 2, s.w_hh0, 0, static_cast<long long>(IG) * IH, st));
-    FT_TRYX(launch_cast(w->lstm_w_ih1, 2, s.w_ih1, 0, static_cast<long long>(IG) * IH, st));
-    FT_TRYX(launch_cast(w->lstm_w_hh1, 2, s.w_hh1, 0, static_cast<long long>(IG) * IH, st));
-    FT_TRYX(launch_cast(w->att_query, 2, s.wq, 0, static_cast<long long>(A) * IH, st));
+    // weights in consumption order (fp16), LSTM input + recurrent matrices fused along K, biases pre-added
+    FT_TRYX(pack(s.wA, s.bA, w->attn_lstm_w_ih, M, XPAD, w->attn_lstm_w_hh, IH, w->attn_lstm_b_ih, w->attn_lstm_b_hh, IH / 2, (XPAD + IH) / 32, 0, M, st));
+    FT_TRYX(pack(s.w0, s.b0, w->lstm_w_ih0, D, D, w->lstm_w_hh0, IH, w->lstm_b_ih0, w->lstm_b_hh0, IH / 2, (D + IH) / 32, 0, M, st));
+    FT_TRYX(pack(s.w1, s.b1, w->lstm_w_ih1, IH, IH, w->lstm_w_hh1, IH, w->lstm_b_ih1, w->lstm_b_hh1, IH / 2, 2 * IH / 32, 0, M, st));
+    FT_TRYX(pack(s.wq, nullptr, w->att_query, IH, IH, nullptr, 0, nullptr, nullptr, A / 8, IH / 32, 1, M, st));
+    FT_TRYX(pack(s.wd1, s.bd1, w->dense_w0, IH, IH, nullptr, 0, w->dense_b0, nullptr, IH / 8, IH / 32, 1, M, st));
+    FT_TRYX(pack(s.wd2, s.bd2, w->dense_w1, IH, IH, nullptr, 0, w->dense_b1, nullptr, IH / 8, IH / 32, 1, M, st));
+    FT_TRYX(pack(s.wc, s.bc, w->conv_w, IH, IH, nullptr, 0, w->conv_b, nullptr, M / 4, IH / 32, 2, M, st));
     FT_TRYX(launch_cast(w->att_key, 2, s.wk, 0, static_cast<long long>(A) * E, st));
     FT_TRYX(launch_cast(w->att_value, 2, s.wv, 0, static_cast<long long>(A) * E, st));
-    FT_TRYX(launch_cast(w->dense_w0, 2, s.w1, 0, static_cast<long long>(IH) * IH, st));
-    FT_TRYX(launch_cast(w->dense_w1, 2, s.w2, 0, static_cast<long long>(IH) * IH, st));
-    FT_TRYX(launch_cast(w->conv_w, 2, s.wc, 0, static_cast<long long>(2 * M) * IH, st));
     FT_TRYX(launch_cast(text, 2, s.text16, 0, RL * E, st));
     {   // K / V projections once per utterance (the reference recomputes them every frame, flowtron.py:568-570)
         GemmArgs g;
@@ -454,13 +463,8 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
 
     InferParams p;
     p.T = d->T; p.B = B; p.L = d->L; p.M = M; p.A = A; p.E = E; p.D = D;
-    p.w_ih_a = reinterpret_cast<const __half*>(s.w_ih_a); p.w_hh_a = reinterpret_cast<const __half*>(s.w_hh_a);
-    p.w_ih0 = reinterpret_cast<const __half*>(s.w_ih0); p.w_hh0 = reinterpret_cast<const __half*>(s.w_hh0);
-    p.w_ih1 = reinterpret_cast<const __half*>(s.w_ih1); p.w_hh1 = reinterpret_cast<const __half*>(s.w_hh1);
-    p.wq = reinterpret_cast<const __half*>(s.wq); p.w1 = reinterpret_cast<const __half*>(s.w1);
-    p.w2 = reinterpret_cast<const __half*>(s.w2); p.wc = reinterpret_cast<const __half*>(s.wc);
-    p.b_ih_a = w->attn_lstm_b_ih; p.b_hh_a = w->attn_lstm_b_hh; p.b_ih0 = w->lstm_b_ih0; p.b_hh0 = w->lstm_b_hh0;
-    p.b_ih1 = w->lstm_b_ih1; p.b_hh1 = w->lstm_b_hh1; p.b1 = w->dense_b0; p.b2 = w->dense_b1; p.bc = w->conv_b;
+    p.wA = s.wA; p.w0 = s.w0; p.w1 = s.w1; p.wq = s.wq; p.wd1 = s.wd1; p.wd2 = s.wd2; p.wc = s.wc;
+    p.bA = s.bA; p.b0 = s.b0; p.b1 = s.b1; p.bd1 = s.bd1; p.bd2 = s.bd2; p.bc = s.bc;
     p.v = w->att_v; p.wg = w->gate_w; p.bg = w->gate_b;
     p.Kp = s.Kp; p.Vp = s.Vp; p.residual = residual; p.prior = d->has_prior ? attn_prior : nullptr;
     p.attn_forced = attn_forced;
@@ -473,12 +477,11 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
     p.hA[0] = take(BH); p.hA[1] = take(BH); p.cA = take(BH);
     p.h0[0] = take(BH); p.h0[1] = take(BH); p.c0 = take(BH);
     p.h1[0] = take(BH); p.h1[1] = take(BH); p.c1 = take(BH);
-    p.xprev = take(static_cast<size_t>(B) * M); p.q = take(static_cast<size_t>(B) * A); p.e = take(static_cast<size_t>(B) * d->L);
+    p.xprev = take(static_cast<size_t>(B) * M); p.q = take(static_cast<size_t>(B) * A);
     p.d = take(static_cast<size_t>(B) * D); p.y1 = take(BH); p.y2 = take(BH);
     p.alive = s.ints; p.barrier = s.ints + B + 32;
     p.status = ft_status_word();
-    // alive[b] = 1
-    {
+    {   // alive[b] = 1
         static int ones[64];
         for (int i = 0; i < 64; ++i) ones[i] = 1;
         if (cudaMemcpyAsync(p.alive, ones, sizeof(int) * B, cudaMemcpyHostToDevice, st) != cudaSuccess) return ft_set_error("infer: memcpy failed");
@@ -486,10 +489,9 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int ibt = B == 1 ? 1 : (B == 2 ? 2 : (B <= 4 ? 4 : 8));
-    void* fn = ibt == 1 ? reinterpret_cast<void*>(infer_kernel<1>) : ibt == 2 ? reinterpret_cast<void*>(infer_kernel<2>)
-             : ibt == 4 ? reinterpret_cast<void*>(infer_kernel<4>) : reinterpret_cast<void*>(infer_kernel<8>);
-    const int smem = ibt * KMAX * 2;
+    if (sms < B) return ft_set_error("infer: fewer SMs than utterances");
+    void* fn = B > 8 ? reinterpret_cast<void*>(infer_kernel<true>) : reinterpret_cast<void*>(infer_kernel<false>);
+    const int smem = 16 * KP * 2 + INF_WARPS * 128 * 4 + (A + LMAX + D + 64) * 4;
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     TimeScope ts("infer", d->T, B, d->L, st);
     void* args[] = {&p};

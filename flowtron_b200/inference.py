@@ -21,6 +21,24 @@ def ar_step_infer(step, residual, text, attns, attn_prior=None, reversed_flag=Fa
     T, B, M = residual.shape
     L, _, E = text.shape
     dev = residual.device
+    if B > 16:                                            # the kernel takes up to 16 utterances (one mma M tile): run slices
+        outs, attns_o = [], []
+        for b0 in range(0, B, 16):
+            sl = slice(b0, min(B, b0 + 16))
+            a_sl = attns
+            if attns is not None:
+                a_sl = torch.stack([a.reshape(B, L) for a in attns], 0)[:, sl] if isinstance(attns, (list, tuple)) \
+                    else attns.reshape(-1, B, L)[:, sl]
+            o, a = ar_step_infer(step, residual[:, sl], text[:, sl], a_sl, None if attn_prior is None else attn_prior[sl], reversed_flag)
+            outs.append(o)
+            attns_o.append(torch.stack(a, 0) if a else residual.new_zeros(0, sl.stop - sl.start, 1, L))
+        n = max(o.size(0) for o in outs)
+        pad = lambda t: t if t.size(0) == n else torch.cat([t, t.new_zeros(n - t.size(0), *t.shape[1:])], 0)
+        if reversed_flag:       # slices that stopped earlier are left-padded in the flipped-back time order
+            pad = lambda t: t if t.size(0) == n else torch.cat([t.new_zeros(n - t.size(0), *t.shape[1:]), t], 0)
+        out = torch.cat([pad(o) for o in outs], 1)
+        att = torch.cat([t if t.size(0) == n else torch.cat([t, t.new_zeros(n - t.size(0), *t.shape[1:])], 0) for t in attns_o], 1)
+        return out, [a for a in att]
     res = residual.detach().float()
     prior = None if attn_prior is None else attn_prior.detach().float()
     if reversed_flag:
