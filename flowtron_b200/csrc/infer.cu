@@ -53,7 +53,11 @@ struct InferParams {
     int* alive;                            // [B] 1 while the sample is still generating
     int* barrier;                          // monotonic grid barrier counter
     int* status;
+    long long* trace;                      // debug: [T][32] clock64 stamps of CTA 0 (tools/trace_infer.py), or null
 };
+
+static long long* g_infer_trace = nullptr;
+#define IT_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[i * 32 + (slot)] = clock64(); } while (0)
 
 // Grid barrier: one release-add per CTA on a monotonic counter, one acquiring poller per CTA.  The release (gpu scope) after the
 // CTA barrier is cumulative over every thread's earlier writes, so no separate __threadfence() is needed.
@@ -183,26 +187,33 @@ infer_kernel(InferParams p) {
 
         // ---- P1 attention_lstm step on the previous output frame (zeros at i == 0): x = [out_{i-1} (80 -> 96) ; hA_{i-1}]
         __syncthreads();
+        IT_TRACE(0);
         stage_x(sx, 0, p.xprev, p.M, p.M, p.B);
         for (int i2 = threadIdx.x; i2 < p.B * (XPAD - p.M); i2 += INF_THREADS)         // pad columns (later phases stage over them)
             sx[(i2 / (XPAD - p.M)) * KP + p.M + (i2 % (XPAD - p.M))] = __float2half_rn(0.f);
         stage_x(sx, XPAD, p.hA[prv], IH, IH, p.B);
         __syncthreads();
+        IT_TRACE(1);
         mv_phase<kB16>(p.wA, IH / 2, (XPAD + IH) / 32, 4, spart, sx,
                        [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.bA, p.cA, p.hA[cur]); });
+        IT_TRACE(2);
         grid_sync(p, epoch);
+        IT_TRACE(3);
 
         const bool forced = p.attn_forced != nullptr;    // `attn` given (flowtron.py:585-588): no query / score / softmax / prior
         // ---- P2 query projection (no bias)
         if (!forced) {
             stage_x(sx, 0, p.hA[cur], IH, IH, p.B);
             __syncthreads();
+            IT_TRACE(4);
             mv_phase<kB16>(p.wq, p.A / 8, IH / 32, INF_WARPS, spart, sx, [&](int task, float (&d)[4]) {
                 const int j = lane & 3, r = lane >> 2;
                 if (r < p.B) { p.q[r * p.A + 8 * task + 2 * j] = d[0]; p.q[r * p.A + 8 * task + 2 * j + 1] = d[1]; }
                 if (kB16 && r + 8 < p.B) { p.q[(r + 8) * p.A + 8 * task + 2 * j] = d[2]; p.q[(r + 8) * p.A + 8 * task + 2 * j + 1] = d[3]; }
             });
+            IT_TRACE(5);
             grid_sync(p, epoch);
+            IT_TRACE(6);
         }
         // ---- P3 attention of utterance b inside CTA b: scores e[l] = v . tanh(q + K[l]) / temperature (no key mask in
         //      inference, flowtron.py:800-803), softmax (+ prior posterior), context, d = [hA ; ctx], gate decision
@@ -289,21 +300,29 @@ infer_kernel(InferParams p) {
                 }
             }
         }
+        IT_TRACE(7);
         grid_sync(p, epoch);
+        IT_TRACE(8);
         // ---- P4 lstm layer 0 on [d ; h0_{i-1}]
         stage_x(sx, 0, p.d, p.D, p.D, p.B);
         stage_x(sx, p.D, p.h0[prv], IH, IH, p.B);
         __syncthreads();
+        IT_TRACE(9);
         mv_phase<kB16>(p.w0, IH / 2, (p.D + IH) / 32, 4, spart, sx,
                        [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.b0, p.c0, p.h0[cur]); });
+        IT_TRACE(10);
         grid_sync(p, epoch);
+        IT_TRACE(11);
         // ---- P5 lstm layer 1 on [h0 ; h1_{i-1}]
         stage_x(sx, 0, p.h0[cur], IH, IH, p.B);
         stage_x(sx, IH, p.h1[prv], IH, IH, p.B);
         __syncthreads();
+        IT_TRACE(12);
         mv_phase<kB16>(p.w1, IH / 2, 2 * IH / 32, 4, spart, sx,
                        [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.b1, p.c1, p.h1[cur]); });
+        IT_TRACE(13);
         grid_sync(p, epoch);
+        IT_TRACE(14);
         // ---- P6/P7 dense layers (tanh)
         auto dense = [&](const __half* W, const float* bias, const float* x, float* y) {
             stage_x(sx, 0, x, IH, IH, p.B);
@@ -316,9 +335,13 @@ infer_kernel(InferParams p) {
             });
         };
         dense(p.wd1, p.bd1, p.h1[cur], p.y1);
+        IT_TRACE(15);
         grid_sync(p, epoch);
+        IT_TRACE(16);
         dense(p.wd2, p.bd2, p.y1, p.y2);
+        IT_TRACE(17);
         grid_sync(p, epoch);
+        IT_TRACE(18);
         // ---- P8 conv + inverse affine: out = (residual - b) / exp(log_s); task rows = (log_s, b) of 4 consecutive channels
         stage_x(sx, 0, p.y2, IH, IH, p.B);
         __syncthreads();
@@ -340,7 +363,9 @@ infer_kernel(InferParams p) {
                 }
             }
         });
+        IT_TRACE(19);
         grid_sync(p, epoch);
+        IT_TRACE(20);
     }
 }
 
@@ -420,6 +445,9 @@ static InferScratch plan_infer(const FtArStepDesc& d, uint8_t* base) {
 
 extern "C" {
 
+/* debug: device buffer [T][32] receiving clock64 stamps of CTA 0 of the next ft_ar_step_infer launches (NULL disables) */
+void ft_debug_set_infer_trace(long long* buf) { ft::g_infer_trace = buf; }
+
 size_t ft_ar_step_infer_scratch_bytes(const FtArStepDesc* d) { return ft::plan_infer(*d, nullptr).total + 256; }
 
 int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const float* residual, const float* text,
@@ -481,6 +509,7 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
     p.d = take(static_cast<size_t>(B) * D); p.y1 = take(BH); p.y2 = take(BH);
     p.alive = s.ints; p.barrier = s.ints + B + 32;
     p.status = ft_status_word();
+    p.trace = g_infer_trace;
     {   // alive[b] = 1
         static int ones[64];
         for (int i = 0; i < 64; ++i) ones[i] = 1;

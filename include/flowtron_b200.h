@@ -51,6 +51,8 @@ int ft_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const int* 
 
 /* debug/profiling: device buffer [T][8] that receives clock64 stamps of CTA 0 of later ft_lstm_fwd launches */
 void ft_debug_set_lstm_trace(long long* buf);
+/* same for ft_ar_step_infer: [T][32] stamps of CTA 0 (phase boundaries, tools/trace_infer.py) */
+void ft_debug_set_infer_trace(long long* buf);
 
 /* Process-wide switch: 1 = ft_lstm_fwd (and ft_ar_step_fwd) use the 64-CTA recurrence kernel so two half-batch
  * launches on two streams run concurrently (the BPTT kernel always uses 64 CTAs for B <= 32). */
