@@ -16,8 +16,10 @@
 //     bytes and issues 8 of them back to back (4 KB in flight per warp, 16 warps per SM);
 //   * a task's K range is split over the warps of a CTA (partial accumulators meet in shared memory), so all 16 warps of
 //     every SM stream weights in every phase;
-//   * score + softmax (+ prior posterior) + context + gate of one utterance run inside ONE CTA (block barriers only):
-//     8 software grid barriers per frame instead of 9 (6 with forced alignments), without the redundant fence.
+//   * a warp's share of the NEXT phase's weights is prefetched into registers before each grid barrier (weights do not depend
+//     on what the barrier waits for); scores run over all warps of the grid, softmax (+ prior posterior) + context + gate of
+//     one utterance inside one CTA; 9 software grid barriers per frame (6 with forced alignments), ~1.2 us each
+//     (tools/trace_infer.py prints the phase table).
 // Same operand precision as the training kernels (fp16 operands, fp32 accumulate/state).
 #include "ptx.cuh"
 #include "ft_internal.h"
@@ -49,7 +51,7 @@ struct InferParams {
     float* attn_out;                       // [T,B,L]
     int* n_frames;                         // [B]
     // state (global scratch, zero-initialised by the launcher)
-    float *hA[2], *cA, *h0[2], *c0, *h1[2], *c1, *xprev, *q, *d, *y1, *y2;
+    float *hA[2], *cA, *h0[2], *c0, *h1[2], *c1, *xprev, *q, *e, *d, *y1, *y2;
     int* alive;                            // [B] 1 while the sample is still generating
     int* barrier;                          // monotonic grid barrier counter
     int* status;
@@ -72,10 +74,19 @@ __device__ __forceinline__ void grid_sync(const InferParams& p, int& epoch) {
 }
 
 // activations of a phase: fp32 global [B, K] (row pitch ld) -> fp16 shared [16][KP] at column c0 (batch rows >= B stay zero)
+// (K, ld, c0 multiples of 4: 16-byte loads, 8-byte stores)
 __device__ __forceinline__ void stage_x(__half* sx, int c0, const float* src, long long ld, int K, int B) {
-    for (int i = threadIdx.x; i < B * K; i += INF_THREADS) {
-        const int b = i / K, k = i - b * K;
-        sx[b * KP + c0 + k] = __float2half_rn(src[static_cast<long long>(b) * ld + k]);
+    const int k4 = K >> 2;
+    for (int b = 0; b < B; ++b) {
+        const float4* s4 = reinterpret_cast<const float4*>(src + static_cast<long long>(b) * ld);
+        __half* dst = sx + b * KP + c0;
+        for (int i = threadIdx.x; i < k4; i += INF_THREADS) {
+            const float4 v = s4[i];
+            const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(dst + 4 * i) = pk;
+        }
     }
 }
 
@@ -91,7 +102,7 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a
 // MMA step s in {0,1} of a block uses halfs 4s..4s+3 of the lane's chunk as its (k, k+1, k+8, k+9) slots.
 template <bool kB16>
 __device__ __forceinline__ void mv_partial(const __half* __restrict__ Wt, int m0, int m1, const __half* sx, int lane, float (&d)[4]) {
-    constexpr int U = 8;
+    constexpr int U = 10;
     const uint4* wp = reinterpret_cast<const uint4*>(Wt) + lane;             // block m: + 32 m   (lane = 4 n + j: 16 bytes each)
     const __half* a_lo = sx + (lane >> 2) * KP + 8 * (lane & 3);
     const __half* a_hi = a_lo + 8 * KP;
@@ -112,19 +123,54 @@ __device__ __forceinline__ void mv_partial(const __half* __restrict__ Wt, int m0
     }
 }
 
-// One matrix-vector phase: n_tasks tasks of 8 rows, nm k-blocks, each task split over S warps of a CTA.  epi(task, d) is
-// called by the task's first warp (all 32 lanes) with the complete accumulator fragment:
-//   d[0], d[1] = batch row lane/4, rows 2j, 2j+1 of the task (j = lane%4);  d[2], d[3] = batch row lane/4 + 8, same rows.
-template <bool kB16, class Epi>
-__device__ __forceinline__ void mv_phase(const __half* __restrict__ W, int n_tasks, int nm, int S, float* spart, const __half* sx, Epi epi) {
+// Weights do not depend on the activations a phase waits for: the first PFN k-blocks of a warp's share of the NEXT phase are
+// loaded into registers BEFORE the grid barrier and land while the CTA waits (trace: a phase spent 1-3 load round trips of
+// ~1.2 us each after its barrier).
+constexpr int PFN = 11;
+struct Prefetch { uint4 w[PFN]; };
+__device__ __forceinline__ void mv_prefetch(Prefetch& pf, const __half* __restrict__ W, int n_tasks, int nm, int S) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tpc = INF_WARPS / S;
     const int tl = warp / S, split = warp - tl * S;
+    const int task = blockIdx.x * tpc + tl;
+    const int m0 = nm * split / S, m1 = nm * (split + 1) / S;
+    const uint4* wp = reinterpret_cast<const uint4*>(W + static_cast<long long>(task) * nm * 256) + lane;
+#pragma unroll
+    for (int u = 0; u < PFN; ++u) pf.w[u] = (task < n_tasks && m0 + u < m1) ? __ldg(wp + 32 * (m0 + u)) : make_uint4(0u, 0u, 0u, 0u);
+}
+
+// One matrix-vector phase: n_tasks tasks of 8 rows, nm k-blocks, each task split over S warps of a CTA.  epi(task, d) is
+// called by the task's first warp (all 32 lanes) with the complete accumulator fragment:
+//   d[0], d[1] = batch row lane/4, rows 2j, 2j+1 of the task (j = lane%4);  d[2], d[3] = batch row lane/4 + 8, same rows.
+// pf: the prefetched first PFN blocks of this warp's share of the FIRST pass (mv_prefetch with the same arguments).
+template <bool kB16, class Epi>
+__device__ __forceinline__ void mv_phase(const __half* __restrict__ W, int n_tasks, int nm, int S, float* spart, const __half* sx,
+                                         const Prefetch& pf, Epi epi) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tpc = INF_WARPS / S;
+    const int tl = warp / S, split = warp - tl * S;
+    bool first = true;
     for (int base = blockIdx.x * tpc; base < n_tasks; base += gridDim.x * tpc) {       // CTA-uniform trip count
         const int task = base + tl;
         float d[4] = {0.f, 0.f, 0.f, 0.f};
         if (task < n_tasks) {
-            const int m0 = nm * split / S, m1 = nm * (split + 1) / S;
+            int m0 = nm * split / S;
+            const int m1 = nm * (split + 1) / S;
+            if (first) {
+                const __half* a_lo = sx + (lane >> 2) * KP + 8 * (lane & 3);
+                const __half* a_hi = a_lo + 8 * KP;
+#pragma unroll
+                for (int u = 0; u < PFN; ++u) {
+                    if (m0 + u < m1) {
+                        const uint4 lo = *reinterpret_cast<const uint4*>(a_lo + 32 * (m0 + u));
+                        uint4 hi = make_uint4(0u, 0u, 0u, 0u);
+                        if (kB16) hi = *reinterpret_cast<const uint4*>(a_hi + 32 * (m0 + u));
+                        mma_16816(d, lo.x, hi.x, lo.y, hi.y, pf.w[u].x, pf.w[u].y);
+                        mma_16816(d, lo.z, hi.z, lo.w, hi.w, pf.w[u].z, pf.w[u].w);
+                    }
+                }
+                m0 = (m0 + PFN < m1) ? m0 + PFN : m1;
+            }
             mv_partial<kB16>(W + static_cast<long long>(task) * nm * 256, m0, m1, sx, lane, d);
             if (S > 1) *reinterpret_cast<float4*>(spart + (warp * 32 + lane) * 4) = make_float4(d[0], d[1], d[2], d[3]);
         }
@@ -139,6 +185,7 @@ __device__ __forceinline__ void mv_phase(const __half* __restrict__ W, int n_tas
         }
         if (task < n_tasks && split == 0) epi(task, d);
         if (S > 1) __syncthreads();
+        first = false;
     }
 }
 
@@ -172,18 +219,23 @@ infer_kernel(InferParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __half* sx = reinterpret_cast<__half*>(smem_raw);                          // [16][KP] fp16 activations of the phase
     float* spart = reinterpret_cast<float*>(sx + 16 * KP);                     // [16 warps][32 lanes][4] partial accumulators
-    float* sf = spart + INF_WARPS * 128;                                       // attention scratch: q[A] e[LMAX] d[D]
+    float* sf = spart + INF_WARPS * 128;                                       // attention scratch: e[LMAX] d[D] partials[4][A]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int epoch = 0;
     for (int i = threadIdx.x; i < 16 * KP; i += INF_THREADS) sx[i] = __float2half_rn(0.f);     // batch rows >= B and pads: zero forever
     __syncthreads();
 
+    const int nmA = (XPAD + IH) / 32, nm0 = (p.D + IH) / 32, nm1 = 2 * IH / 32, nmd = IH / 32;
+    const int gw = blockIdx.x * INF_WARPS + warp, nw = gridDim.x * INF_WARPS;
+    Prefetch pf;
+    mv_prefetch(pf, p.wA, IH / 2, nmA, 4);
     for (int i = 0; i < p.T; ++i) {
         const int cur = i & 1, prv = cur ^ 1;
         // all samples stopped?  (alive is only written in the attention phase of the previous frame, ordered by grid barriers)
         bool any = false;
         for (int b = 0; b < p.B; ++b) any |= (ld_acquire(&p.alive[b]) != 0);
         if (!any) break;
+        const bool forced = p.attn_forced != nullptr;    // `attn` given (flowtron.py:585-588): no query / score / softmax / prior
 
         // ---- P1 attention_lstm step on the previous output frame (zeros at i == 0): x = [out_{i-1} (80 -> 96) ; hA_{i-1}]
         __syncthreads();
@@ -194,49 +246,57 @@ infer_kernel(InferParams p) {
         stage_x(sx, XPAD, p.hA[prv], IH, IH, p.B);
         __syncthreads();
         IT_TRACE(1);
-        mv_phase<kB16>(p.wA, IH / 2, (XPAD + IH) / 32, 4, spart, sx,
+        mv_phase<kB16>(p.wA, IH / 2, nmA, 4, spart, sx, pf,
                        [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.bA, p.cA, p.hA[cur]); });
+        if (forced) mv_prefetch(pf, p.w0, IH / 2, nm0, 4); else mv_prefetch(pf, p.wq, p.A / 8, nmd, INF_WARPS);
         IT_TRACE(2);
         grid_sync(p, epoch);
         IT_TRACE(3);
 
-        const bool forced = p.attn_forced != nullptr;    // `attn` given (flowtron.py:585-588): no query / score / softmax / prior
-        // ---- P2 query projection (no bias)
         if (!forced) {
+            // ---- P2 query projection (no bias)
             stage_x(sx, 0, p.hA[cur], IH, IH, p.B);
             __syncthreads();
             IT_TRACE(4);
-            mv_phase<kB16>(p.wq, p.A / 8, IH / 32, INF_WARPS, spart, sx, [&](int task, float (&d)[4]) {
+            mv_phase<kB16>(p.wq, p.A / 8, nmd, INF_WARPS, spart, sx, pf, [&](int task, float (&d)[4]) {
                 const int j = lane & 3, r = lane >> 2;
                 if (r < p.B) { p.q[r * p.A + 8 * task + 2 * j] = d[0]; p.q[r * p.A + 8 * task + 2 * j + 1] = d[1]; }
                 if (kB16 && r + 8 < p.B) { p.q[(r + 8) * p.A + 8 * task + 2 * j] = d[2]; p.q[(r + 8) * p.A + 8 * task + 2 * j + 1] = d[3]; }
             });
+            mv_prefetch(pf, p.w0, IH / 2, nm0, 4);       // lstm layer 0's weights ride through the two attention phases
             IT_TRACE(5);
             grid_sync(p, epoch);
             IT_TRACE(6);
+            // ---- P3a scores e[b,l] = v . tanh(q[b] + K[l,b]) / temperature over ALL warps of the grid (no key mask in
+            //      inference, flowtron.py:800-803).  (Inside one CTA per utterance this took 19 of the frame's 49 us.)
+            for (int t = gw; t < p.B * p.L; t += nw) {
+                const int b = t / p.L, l = t - b * p.L;
+                const float* kr = p.Kp + (static_cast<long long>(l) * p.B + b) * p.A;
+                const float* qr = p.q + b * p.A;
+                float s = 0.f;
+                for (int a0 = 0; a0 < p.A; a0 += 128) {                      // 4 independent loads per operand in flight
+                    float kv[4], qv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const int a = a0 + 32 * u + lane; kv[u] = a < p.A ? kr[a] : 0.f; qv[u] = a < p.A ? qr[a] : 0.f; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const int a = a0 + 32 * u + lane; if (a < p.A) s = fmaf(p.v[a], tanh_f(qv[u] + kv[u]), s); }
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) p.e[t] = s * p.inv_temperature;
+            }
+            grid_sync(p, epoch);
         }
-        // ---- P3 attention of utterance b inside CTA b: scores e[l] = v . tanh(q + K[l]) / temperature (no key mask in
-        //      inference, flowtron.py:800-803), softmax (+ prior posterior), context, d = [hA ; ctx], gate decision
+        // ---- P3b utterance b inside CTA b: softmax (+ prior posterior) or the forced alignment, context, d = [hA ; ctx], gate
         if (static_cast<int>(blockIdx.x) < p.B) {
             const int b = blockIdx.x;
-            float* sq = sf; float* se = sf + p.A; float* sd = se + LMAX;
+            float* se = sf; float* sd = sf + LMAX; float* sp = sd + p.D;          // e / attn [LMAX], d [D], context partials [4][A]
             if (!forced) {
-                for (int a = threadIdx.x; a < p.A; a += INF_THREADS) sq[a] = p.q[b * p.A + a];
-                __syncthreads();
-                for (int l = warp; l < p.L; l += INF_WARPS) {
-                    const float* kr = p.Kp + (static_cast<long long>(l) * p.B + b) * p.A;
-                    float s = 0.f;
-                    for (int a = lane; a < p.A; a += 32) s = fmaf(p.v[a], tanh_f(sq[a] + kr[a]), s);
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    if (lane == 0) se[l] = s * p.inv_temperature;
-                }
-                __syncthreads();
                 if (warp == 0) {                         // softmax over L in registers: lane holds l = lane + 32 jj
                     float w[8];
                     float mx = -INFINITY;
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) { const int l = lane + 32 * jj; w[jj] = (l < p.L) ? se[l] : -INFINITY; mx = fmaxf(mx, w[jj]); }
+                    for (int jj = 0; jj < 8; ++jj) { const int l = lane + 32 * jj; w[jj] = (l < p.L) ? p.e[b * p.L + l] : -INFINITY; mx = fmaxf(mx, w[jj]); }
 #pragma unroll
                     for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                     float s = 0.f;
@@ -275,12 +335,26 @@ infer_kernel(InferParams p) {
             } else {
                 for (int l = threadIdx.x; l < p.L; l += INF_THREADS) se[l] = p.attn_forced[(static_cast<long long>(i) * p.B + b) * p.L + l];
             }
+            for (int k = threadIdx.x; k < IH; k += INF_THREADS) sd[k] = p.hA[cur][b * IH + k];
             __syncthreads();
             for (int l = threadIdx.x; l < p.L; l += INF_THREADS) p.attn_out[(static_cast<long long>(i) * p.B + b) * p.L + l] = se[l];
-            for (int k = threadIdx.x; k < IH; k += INF_THREADS) sd[k] = p.hA[cur][b * IH + k];
+            const int a4n = p.A >> 2, ngrp = INF_THREADS / a4n < 4 ? INF_THREADS / a4n : 4;       // A = 640: 3 groups of 160 threads
+            {   // context: `ngrp` groups of keys x (A/4) groups of 4 channels, 16-byte loads of V, partial sums meet in shared memory
+                const int lg = threadIdx.x / a4n, a4 = threadIdx.x - lg * a4n;
+                if (lg < ngrp) {
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int l = lg; l < p.L; l += ngrp) {
+                        const float4 v = *reinterpret_cast<const float4*>(p.Vp + (static_cast<long long>(l) * p.B + b) * p.A + 4 * a4);
+                        const float w = se[l];
+                        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                    }
+                    *reinterpret_cast<float4*>(sp + lg * p.A + 4 * a4) = acc;
+                }
+            }
+            __syncthreads();
             for (int a = threadIdx.x; a < p.A; a += INF_THREADS) {
                 float c = 0.f;
-                for (int l = 0; l < p.L; ++l) c = fmaf(se[l], p.Vp[(static_cast<long long>(l) * p.B + b) * p.A + a], c);
+                for (int g2 = 0; g2 < ngrp; ++g2) c += sp[g2 * p.A + a];
                 sd[IH + a] = c;
             }
             __syncthreads();
@@ -308,8 +382,9 @@ infer_kernel(InferParams p) {
         stage_x(sx, p.D, p.h0[prv], IH, IH, p.B);
         __syncthreads();
         IT_TRACE(9);
-        mv_phase<kB16>(p.w0, IH / 2, (p.D + IH) / 32, 4, spart, sx,
+        mv_phase<kB16>(p.w0, IH / 2, nm0, 4, spart, sx, pf,
                        [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.b0, p.c0, p.h0[cur]); });
+        mv_prefetch(pf, p.w1, IH / 2, nm1, 4);
         IT_TRACE(10);
         grid_sync(p, epoch);
         IT_TRACE(11);
@@ -318,8 +393,9 @@ infer_kernel(InferParams p) {
         stage_x(sx, IH, p.h1[prv], IH, IH, p.B);
         __syncthreads();
         IT_TRACE(12);
-        mv_phase<kB16>(p.w1, IH / 2, 2 * IH / 32, 4, spart, sx,
+        mv_phase<kB16>(p.w1, IH / 2, nm1, 4, spart, sx, pf,
                        [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.b1, p.c1, p.h1[cur]); });
+        mv_prefetch(pf, p.wd1, IH / 8, nmd, INF_WARPS);
         IT_TRACE(13);
         grid_sync(p, epoch);
         IT_TRACE(14);
@@ -327,7 +403,7 @@ infer_kernel(InferParams p) {
         auto dense = [&](const __half* W, const float* bias, const float* x, float* y) {
             stage_x(sx, 0, x, IH, IH, p.B);
             __syncthreads();
-            mv_phase<kB16>(W, IH / 8, IH / 32, INF_WARPS, spart, sx, [&](int task, float (&d)[4]) {
+            mv_phase<kB16>(W, IH / 8, nmd, INF_WARPS, spart, sx, pf, [&](int task, float (&d)[4]) {
                 const int j = lane & 3, r = lane >> 2;
                 const float b0 = bias[task * 8 + 2 * j], b1 = bias[task * 8 + 2 * j + 1];
                 if (r < p.B) { y[r * IH + 8 * task + 2 * j] = tanh_f(d[0] + b0); y[r * IH + 8 * task + 2 * j + 1] = tanh_f(d[1] + b1); }
@@ -335,17 +411,19 @@ infer_kernel(InferParams p) {
             });
         };
         dense(p.wd1, p.bd1, p.h1[cur], p.y1);
+        mv_prefetch(pf, p.wd2, IH / 8, nmd, INF_WARPS);
         IT_TRACE(15);
         grid_sync(p, epoch);
         IT_TRACE(16);
         dense(p.wd2, p.bd2, p.y1, p.y2);
+        mv_prefetch(pf, p.wc, p.M / 4, nmd, INF_WARPS);
         IT_TRACE(17);
         grid_sync(p, epoch);
         IT_TRACE(18);
         // ---- P8 conv + inverse affine: out = (residual - b) / exp(log_s); task rows = (log_s, b) of 4 consecutive channels
         stage_x(sx, 0, p.y2, IH, IH, p.B);
         __syncthreads();
-        mv_phase<kB16>(p.wc, p.M / 4, IH / 32, INF_WARPS, spart, sx, [&](int task, float (&d)[4]) {
+        mv_phase<kB16>(p.wc, p.M / 4, nmd, INF_WARPS, spart, sx, pf, [&](int task, float (&d)[4]) {
             const int j = lane & 3, r = lane >> 2;
             const int m = 4 * task + j;
             const float bl = p.bc[task * 8 + 2 * j], bb = p.bc[task * 8 + 2 * j + 1];
@@ -363,6 +441,7 @@ infer_kernel(InferParams p) {
                 }
             }
         });
+        mv_prefetch(pf, p.wA, IH / 2, nmA, 4);           // next frame's attention LSTM
         IT_TRACE(19);
         grid_sync(p, epoch);
         IT_TRACE(20);
@@ -433,8 +512,8 @@ static InferScratch plan_infer(const FtArStepDesc& d, uint8_t* base) {
     s.text16 = reinterpret_cast<uint16_t*>(get(size_t(d.L) * d.B * E * 2));
     s.Kp = reinterpret_cast<float*>(get(size_t(d.L) * d.B * A * 4));
     s.Vp = reinterpret_cast<float*>(get(size_t(d.L) * d.B * A * 4));
-    // state: hA[2], cA, h0[2], c0, h1[2], c1 (9 x B*IH), xprev (B*M), q (B*A), d (B*D), y1, y2 (B*IH)
-    s.state_floats = size_t(d.B) * (9 * IH + M + A + D + 2 * IH);
+    // state: hA[2], cA, h0[2], c0, h1[2], c1 (9 x B*IH), xprev (B*M), q (B*A), e (B*L), d (B*D), y1, y2 (B*IH)
+    s.state_floats = size_t(d.B) * (9 * IH + M + A + d.L + D + 2 * IH);
     s.state = reinterpret_cast<float*>(get(s.state_floats * 4));
     s.ints = reinterpret_cast<int*>(get((size_t(d.B) + 64) * 4));
     s.total = off;
@@ -458,7 +537,8 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
     if (d->n_hidden != IH) return ft_set_error("infer: n_hidden must be 1024");
     if (d->L > LMAX) return ft_set_error("infer: L > 256 not supported");
     if (d->B > 16) return ft_set_error("infer: batch > 16 per call not supported (run the batch in slices of 16)");
-    if (d->n_mel > XPAD || d->n_mel % 8 || d->n_attn % 32 || d->n_text % 8) return ft_set_error("infer: n_mel <= 96 and %8, n_attn %32, n_text %8 required");
+    if (d->n_mel > XPAD || d->n_mel % 8 || d->n_attn % 32 || d->n_text % 8 || d->n_attn > 4 * INF_THREADS)
+        return ft_set_error("infer: n_mel <= 96 and %8, n_attn %32 and <= 2048, n_text %8 required");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     InferScratch s = plan_infer(*d, static_cast<uint8_t*>(scratch));
     const int M = d->n_mel, A = d->n_attn, E = d->n_text, D = IH + A, B = d->B;
@@ -505,7 +585,7 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
     p.hA[0] = take(BH); p.hA[1] = take(BH); p.cA = take(BH);
     p.h0[0] = take(BH); p.h0[1] = take(BH); p.c0 = take(BH);
     p.h1[0] = take(BH); p.h1[1] = take(BH); p.c1 = take(BH);
-    p.xprev = take(static_cast<size_t>(B) * M); p.q = take(static_cast<size_t>(B) * A);
+    p.xprev = take(static_cast<size_t>(B) * M); p.q = take(static_cast<size_t>(B) * A); p.e = take(static_cast<size_t>(B) * d->L);
     p.d = take(static_cast<size_t>(B) * D); p.y1 = take(BH); p.y2 = take(BH);
     p.alive = s.ints; p.barrier = s.ints + B + 32;
     p.status = ft_status_word();
@@ -520,7 +600,7 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms < B) return ft_set_error("infer: fewer SMs than utterances");
     void* fn = B > 8 ? reinterpret_cast<void*>(infer_kernel<true>) : reinterpret_cast<void*>(infer_kernel<false>);
-    const int smem = 16 * KP * 2 + INF_WARPS * 128 * 4 + (A + LMAX + D + 64) * 4;
+    const int smem = 16 * KP * 2 + INF_WARPS * 128 * 4 + (LMAX + D + 4 * A + 64) * 4;
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     TimeScope ts("infer", d->T, B, d->L, st);
     void* args[] = {&p};
