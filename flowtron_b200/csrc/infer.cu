@@ -76,16 +76,25 @@ __device__ __forceinline__ void grid_sync(const InferParams& p, int& epoch) {
 // activations of a phase: fp32 global [B, K] (row pitch ld) -> fp16 shared [16][KP] at column c0 (batch rows >= B stay zero)
 // (K, ld, c0 multiples of 4: 16-byte loads, 8-byte stores)
 __device__ __forceinline__ void stage_x(__half* sx, int c0, const float* src, long long ld, int K, int B) {
-    const int k4 = K >> 2;
-    for (int b = 0; b < B; ++b) {
-        const float4* s4 = reinterpret_cast<const float4*>(src + static_cast<long long>(b) * ld);
-        __half* dst = sx + b * KP + c0;
-        for (int i = threadIdx.x; i < k4; i += INF_THREADS) {
-            const float4 v = s4[i];
-            const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-            *reinterpret_cast<uint2*>(dst + 4 * i) = pk;
+    const int k4 = K >> 2, total = B * k4;
+    constexpr int SU = 2;                                                     // independent 16-byte loads in flight per thread
+    for (int i0 = threadIdx.x; i0 < total; i0 += SU * INF_THREADS) {
+        float4 v[SU];
+        int bb[SU], ii[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int idx = i0 + u * INF_THREADS;
+            bb[u] = idx / k4; ii[u] = idx - bb[u] * k4;
+            if (idx < total) v[u] = *reinterpret_cast<const float4*>(src + static_cast<long long>(bb[u]) * ld + 4 * ii[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            if (i0 + u * INF_THREADS < total) {
+                const __half2 h0 = __floats2half2_rn(v[u].x, v[u].y), h1 = __floats2half2_rn(v[u].z, v[u].w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(sx + bb[u] * KP + c0 + 4 * ii[u]) = pk;
+            }
         }
     }
 }
@@ -102,7 +111,7 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a
 // MMA step s in {0,1} of a block uses halfs 4s..4s+3 of the lane's chunk as its (k, k+1, k+8, k+9) slots.
 template <bool kB16>
 __device__ __forceinline__ void mv_partial(const __half* __restrict__ Wt, int m0, int m1, const __half* sx, int lane, float (&d)[4]) {
-    constexpr int U = 10;
+    constexpr int U = 8;
     const uint4* wp = reinterpret_cast<const uint4*>(Wt) + lane;             // block m: + 32 m   (lane = 4 n + j: 16 bytes each)
     const __half* a_lo = sx + (lane >> 2) * KP + 8 * (lane & 3);
     const __half* a_hi = a_lo + 8 * KP;
@@ -126,7 +135,7 @@ __device__ __forceinline__ void mv_partial(const __half* __restrict__ Wt, int m0
 // Weights do not depend on the activations a phase waits for: the first PFN k-blocks of a warp's share of the NEXT phase are
 // loaded into registers BEFORE the grid barrier and land while the CTA waits (trace: a phase spent 1-3 load round trips of
 // ~1.2 us each after its barrier).
-constexpr int PFN = 11;
+constexpr int PFN = 8;
 struct Prefetch { uint4 w[PFN]; };
 __device__ __forceinline__ void mv_prefetch(Prefetch& pf, const __half* __restrict__ W, int n_tasks, int nm, int S) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -213,6 +222,106 @@ __device__ __forceinline__ void lstm_epi(const InferParams& p, int task, float (
     }
 }
 
+// Utterance b inside CTA b: softmax (+ prior posterior) or the forced alignment, context, d = [hA ; ctx], gate decision.
+// Not inlined: it runs on B of the 148 CTAs only and must not push the weight-prefetch registers of the frame loop into spills.
+__device__ __noinline__ void attend_one(const InferParams& p, float* sf, int i, int cur, bool forced) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x;
+    float* se = sf; float* sd = sf + LMAX; float* sp = sd + p.D;          // e / attn [LMAX], d [D], context partials [4][A]
+    if (!forced) {
+        if (warp == 0) {                         // softmax over L in registers: lane holds l = lane + 32 jj
+            float w[8];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) { const int l = lane + 32 * jj; w[jj] = (l < p.L) ? p.e[b * p.L + l] : -INFINITY; mx = fmaxf(mx, w[jj]); }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float s = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) { w[jj] = (lane + 32 * jj < p.L) ? expf(w[jj] - mx) : 0.f; s += w[jj]; }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float inv = 1.f / s;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) w[jj] *= inv;
+            if (p.prior) {
+                float m2 = -INFINITY;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int l = lane + 32 * jj;
+                    if (l < p.L) {
+                        const float pr = p.prior[(static_cast<long long>(b) * p.T + i) * p.L + l];
+                        w[jj] = logf(w[jj] + 1e-20f) + logf(pr + 1e-20f);
+                        m2 = fmaxf(m2, w[jj]);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+                float s2 = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) { w[jj] = (lane + 32 * jj < p.L) ? expf(w[jj] - m2) : 0.f; s2 += w[jj]; }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                const float inv2 = 1.f / s2;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) w[jj] *= inv2;
+            }
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) { const int l = lane + 32 * jj; if (l < p.L) se[l] = w[jj]; }
+        }
+    } else {
+        for (int l = threadIdx.x; l < p.L; l += INF_THREADS) se[l] = p.attn_forced[(static_cast<long long>(i) * p.B + b) * p.L + l];
+    }
+    for (int k = threadIdx.x; k < IH; k += INF_THREADS) sd[k] = p.hA[cur][b * IH + k];
+    __syncthreads();
+    for (int l = threadIdx.x; l < p.L; l += INF_THREADS) p.attn_out[(static_cast<long long>(i) * p.B + b) * p.L + l] = se[l];
+    const int a4n = p.A >> 2, ngrp = INF_THREADS / a4n < 4 ? INF_THREADS / a4n : 4;       // A = 640: 3 groups of 160 threads
+    {   // context: `ngrp` groups of keys x (A/4) groups of 4 channels, 16-byte loads of V, partial sums meet in shared memory
+        const int lg = threadIdx.x / a4n, a4 = threadIdx.x - lg * a4n;
+        if (lg < ngrp) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int l0 = lg; l0 < p.L; l0 += 6 * ngrp) {             // 6 independent 16-byte loads in flight per thread
+                float4 v[6];
+#pragma unroll
+                for (int u = 0; u < 6; ++u) {
+                    const int l = l0 + u * ngrp;
+                    v[u] = l < p.L ? *reinterpret_cast<const float4*>(p.Vp + (static_cast<long long>(l) * p.B + b) * p.A + 4 * a4)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 6; ++u) {
+                    const int l = l0 + u * ngrp;
+                    const float w = l < p.L ? se[l] : 0.f;
+                    acc.x = fmaf(w, v[u].x, acc.x); acc.y = fmaf(w, v[u].y, acc.y); acc.z = fmaf(w, v[u].z, acc.z); acc.w = fmaf(w, v[u].w, acc.w);
+                }
+            }
+            *reinterpret_cast<float4*>(sp + lg * p.A + 4 * a4) = acc;
+        }
+    }
+    __syncthreads();
+    for (int a = threadIdx.x; a < p.A; a += INF_THREADS) {
+        float c = 0.f;
+        for (int g2 = 0; g2 < ngrp; ++g2) c += sp[g2 * p.A + a];
+        sd[IH + a] = c;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < p.D; k += INF_THREADS) p.d[b * p.D + k] = sd[k];
+    if (warp == 0) {                             // gate decision for this frame (the frame that trips the gate IS emitted, :823-826)
+        if (p.has_gate) {
+            float s = 0.f;
+            for (int k = lane; k < p.D; k += 32) s = fmaf(p.wg[k], sd[k], s);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0 && p.alive[b]) {
+                p.n_frames[b] = i + 1;
+                if (sigmoid_f(s + p.bg[0]) > p.gate_threshold) p.alive[b] = 0;
+            }
+        } else if (lane == 0) {
+            p.n_frames[b] = i + 1;
+        }
+    }
+}
+
 template <bool kB16>
 __global__ void __launch_bounds__(INF_THREADS, 1)
 infer_kernel(InferParams p) {
@@ -287,93 +396,8 @@ infer_kernel(InferParams p) {
             }
             grid_sync(p, epoch);
         }
-        // ---- P3b utterance b inside CTA b: softmax (+ prior posterior) or the forced alignment, context, d = [hA ; ctx], gate
-        if (static_cast<int>(blockIdx.x) < p.B) {
-            const int b = blockIdx.x;
-            float* se = sf; float* sd = sf + LMAX; float* sp = sd + p.D;          // e / attn [LMAX], d [D], context partials [4][A]
-            if (!forced) {
-                if (warp == 0) {                         // softmax over L in registers: lane holds l = lane + 32 jj
-                    float w[8];
-                    float mx = -INFINITY;
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) { const int l = lane + 32 * jj; w[jj] = (l < p.L) ? p.e[b * p.L + l] : -INFINITY; mx = fmaxf(mx, w[jj]); }
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                    float s = 0.f;
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) { w[jj] = (lane + 32 * jj < p.L) ? expf(w[jj] - mx) : 0.f; s += w[jj]; }
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    const float inv = 1.f / s;
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) w[jj] *= inv;
-                    if (p.prior) {
-                        float m2 = -INFINITY;
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) {
-                            const int l = lane + 32 * jj;
-                            if (l < p.L) {
-                                const float pr = p.prior[(static_cast<long long>(b) * p.T + i) * p.L + l];
-                                w[jj] = logf(w[jj] + 1e-20f) + logf(pr + 1e-20f);
-                                m2 = fmaxf(m2, w[jj]);
-                            }
-                        }
-#pragma unroll
-                        for (int o = 16; o; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
-                        float s2 = 0.f;
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) { w[jj] = (lane + 32 * jj < p.L) ? expf(w[jj] - m2) : 0.f; s2 += w[jj]; }
-#pragma unroll
-                        for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                        const float inv2 = 1.f / s2;
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) w[jj] *= inv2;
-                    }
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) { const int l = lane + 32 * jj; if (l < p.L) se[l] = w[jj]; }
-                }
-            } else {
-                for (int l = threadIdx.x; l < p.L; l += INF_THREADS) se[l] = p.attn_forced[(static_cast<long long>(i) * p.B + b) * p.L + l];
-            }
-            for (int k = threadIdx.x; k < IH; k += INF_THREADS) sd[k] = p.hA[cur][b * IH + k];
-            __syncthreads();
-            for (int l = threadIdx.x; l < p.L; l += INF_THREADS) p.attn_out[(static_cast<long long>(i) * p.B + b) * p.L + l] = se[l];
-            const int a4n = p.A >> 2, ngrp = INF_THREADS / a4n < 4 ? INF_THREADS / a4n : 4;       // A = 640: 3 groups of 160 threads
-            {   // context: `ngrp` groups of keys x (A/4) groups of 4 channels, 16-byte loads of V, partial sums meet in shared memory
-                const int lg = threadIdx.x / a4n, a4 = threadIdx.x - lg * a4n;
-                if (lg < ngrp) {
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int l = lg; l < p.L; l += ngrp) {
-                        const float4 v = *reinterpret_cast<const float4*>(p.Vp + (static_cast<long long>(l) * p.B + b) * p.A + 4 * a4);
-                        const float w = se[l];
-                        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
-                    }
-                    *reinterpret_cast<float4*>(sp + lg * p.A + 4 * a4) = acc;
-                }
-            }
-            __syncthreads();
-            for (int a = threadIdx.x; a < p.A; a += INF_THREADS) {
-                float c = 0.f;
-                for (int g2 = 0; g2 < ngrp; ++g2) c += sp[g2 * p.A + a];
-                sd[IH + a] = c;
-            }
-            __syncthreads();
-            for (int k = threadIdx.x; k < p.D; k += INF_THREADS) p.d[b * p.D + k] = sd[k];
-            if (warp == 0) {                             // gate decision for this frame (the frame that trips the gate IS emitted, :823-826)
-                if (p.has_gate) {
-                    float s = 0.f;
-                    for (int k = lane; k < p.D; k += 32) s = fmaf(p.wg[k], sd[k], s);
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    if (lane == 0 && p.alive[b]) {
-                        p.n_frames[b] = i + 1;
-                        if (sigmoid_f(s + p.bg[0]) > p.gate_threshold) p.alive[b] = 0;
-                    }
-                } else if (lane == 0) {
-                    p.n_frames[b] = i + 1;
-                }
-            }
-        }
+        // ---- P3b utterance b inside CTA b (attend_one)
+        if (static_cast<int>(blockIdx.x) < p.B) attend_one(p, sf, i, cur, forced);
         IT_TRACE(7);
         grid_sync(p, epoch);
         IT_TRACE(8);
@@ -513,7 +537,7 @@ static InferScratch plan_infer(const FtArStepDesc& d, uint8_t* base) {
     s.Kp = reinterpret_cast<float*>(get(size_t(d.L) * d.B * A * 4));
     s.Vp = reinterpret_cast<float*>(get(size_t(d.L) * d.B * A * 4));
     // state: hA[2], cA, h0[2], c0, h1[2], c1 (9 x B*IH), xprev (B*M), q (B*A), e (B*L), d (B*D), y1, y2 (B*IH)
-    s.state_floats = size_t(d.B) * (9 * IH + M + A + d.L + D + 2 * IH);
+    s.state_floats = size_t(d.B) * (9 * IH + M + A + d.L + D + 2 * IH) + 64;
     s.state = reinterpret_cast<float*>(get(s.state_floats * 4));
     s.ints = reinterpret_cast<int*>(get((size_t(d.B) + 64) * 4));
     s.total = off;
@@ -580,7 +604,7 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
     p.has_gate = d->has_gate && w->gate_w;
     p.out = out; p.attn_out = attn_out; p.n_frames = n_frames;
     float* f = s.state;
-    auto take = [&](size_t n) { float* r = f; f += n; return r; };
+    auto take = [&](size_t n) { float* r = f; f += (n + 3) & ~size_t(3); return r; };     // 16-byte aligned pieces (float4 staging loads)
     const size_t BH = static_cast<size_t>(B) * IH;
     p.hA[0] = take(BH); p.hA[1] = take(BH); p.cA = take(BH);
     p.h0[0] = take(BH); p.h0[1] = take(BH); p.c0 = take(BH);
