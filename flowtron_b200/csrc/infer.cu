@@ -51,7 +51,8 @@ struct InferParams {
     float* attn_out;                       // [T,B,L]
     int* n_frames;                         // [B]
     // state (global scratch, zero-initialised by the launcher)
-    float *hA[2], *cA, *h0[2], *c0, *h1[2], *c1, *xprev, *q, *e, *d, *y1, *y2;
+    float *hA[2], *cA, *c0, *c1, *q, *e;   // fp32: attention-LSTM output (gate / d), cell states, query, scores
+    __half *hA16[2], *h016[2], *h116[2], *d16, *y116, *y216, *x16;   // fp16 mirrors in staging layout [B][K]: what the next phases consume
     int* alive;                            // [B] 1 while the sample is still generating
     int* barrier;                          // monotonic grid barrier counter
     int* status;
@@ -73,30 +74,21 @@ __device__ __forceinline__ void grid_sync(const InferParams& p, int& epoch) {
     __syncthreads();
 }
 
-// activations of a phase: fp32 global [B, K] (row pitch ld) -> fp16 shared [16][KP] at column c0 (batch rows >= B stay zero)
-// (K, ld, c0 multiples of 4: 16-byte loads, 8-byte stores)
-__device__ __forceinline__ void stage_x(__half* sx, int c0, const float* src, long long ld, int K, int B) {
-    const int k4 = K >> 2, total = B * k4;
-    constexpr int SU = 2;                                                     // independent 16-byte loads in flight per thread
-    for (int i0 = threadIdx.x; i0 < total; i0 += SU * INF_THREADS) {
-        float4 v[SU];
-        int bb[SU], ii[SU];
-#pragma unroll
-        for (int u = 0; u < SU; ++u) {
-            const int idx = i0 + u * INF_THREADS;
-            bb[u] = idx / k4; ii[u] = idx - bb[u] * k4;
-            if (idx < total) v[u] = *reinterpret_cast<const float4*>(src + static_cast<long long>(bb[u]) * ld + 4 * ii[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < SU; ++u) {
-            if (i0 + u * INF_THREADS < total) {
-                const __half2 h0 = __floats2half2_rn(v[u].x, v[u].y), h1 = __floats2half2_rn(v[u].z, v[u].w);
-                uint2 pk;
-                pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-                *reinterpret_cast<uint2*>(sx + bb[u] * KP + c0 + 4 * ii[u]) = pk;
-            }
-        }
+// activations of a phase: fp16 global mirror [B, K] (written by the producing phase's epilogue) -> shared [16][KP] at column c0
+// with 16-byte cp.async copies: no registers, every copy of the phase in flight at once (batch rows >= B stay zero).
+// (K and c0 multiples of 8.)  Callers finish with stage_wait().
+__device__ __forceinline__ void stage16(__half* sx, int c0, const __half* src, int K, int B) {
+    const int k8 = K >> 3, total = B * k8;
+    for (int idx = threadIdx.x; idx < total; idx += INF_THREADS) {
+        const int b = idx / k8, i8 = idx - b * k8;
+        const uint32_t dst = smem_u32(sx + b * KP + c0 + 8 * i8);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + static_cast<long long>(b) * K + 8 * i8) : "memory");
     }
+}
+__device__ __forceinline__ void stage_wait() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
 }
 
 __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -111,7 +103,7 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a
 // MMA step s in {0,1} of a block uses halfs 4s..4s+3 of the lane's chunk as its (k, k+1, k+8, k+9) slots.
 template <bool kB16>
 __device__ __forceinline__ void mv_partial(const __half* __restrict__ Wt, int m0, int m1, const __half* sx, int lane, float (&d)[4]) {
-    constexpr int U = 8;
+    constexpr int U = 10;
     const uint4* wp = reinterpret_cast<const uint4*>(Wt) + lane;             // block m: + 32 m   (lane = 4 n + j: 16 bytes each)
     const __half* a_lo = sx + (lane >> 2) * KP + 8 * (lane & 3);
     const __half* a_hi = a_lo + 8 * KP;
@@ -135,7 +127,7 @@ __device__ __forceinline__ void mv_partial(const __half* __restrict__ Wt, int m0
 // Weights do not depend on the activations a phase waits for: the first PFN k-blocks of a warp's share of the NEXT phase are
 // loaded into registers BEFORE the grid barrier and land while the CTA waits (trace: a phase spent 1-3 load round trips of
 // ~1.2 us each after its barrier).
-constexpr int PFN = 8;
+constexpr int PFN = 11;
 struct Prefetch { uint4 w[PFN]; };
 __device__ __forceinline__ void mv_prefetch(Prefetch& pf, const __half* __restrict__ W, int n_tasks, int nm, int S) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -199,7 +191,7 @@ __device__ __forceinline__ void mv_phase(const __half* __restrict__ W, int n_tas
 }
 
 // LSTM cell for task = 2 units x 4 gates (rows i0,f0,g0,o0,i1,f1,g1,o1): lane j holds (i,f) [j even] or (g,o) [j odd] of unit j/2
-__device__ __forceinline__ void lstm_epi(const InferParams& p, int task, float (&d)[4], const float* bias, float* c, float* hnew) {
+__device__ __forceinline__ void lstm_epi(const InferParams& p, int task, float (&d)[4], const float* bias, float* c, float* hnew, __half* h16) {
     const int lane = threadIdx.x & 31, j = lane & 3, r = lane >> 2;
     const float b0 = bias[task * 8 + 2 * j], b1 = bias[task * 8 + 2 * j + 1];
     float v[4] = {d[0] + b0, d[1] + b1, d[2] + b0, d[3] + b1};
@@ -216,15 +208,18 @@ __device__ __forceinline__ void lstm_epi(const InferParams& p, int task, float (
                 const float gg = tanh_f(o[2 * half]), go = sigmoid_f(o[2 * half + 1]);
                 const float cn = gf * c[b * IH + u] + gi * gg;
                 c[b * IH + u] = cn;
-                hnew[b * IH + u] = go * tanh_f(cn);
+                const float h = go * tanh_f(cn);
+                if (hnew) hnew[b * IH + u] = h;
+                h16[b * IH + u] = __float2half_rn(h);
             }
         }
     }
 }
 
 // Utterance b inside CTA b: softmax (+ prior posterior) or the forced alignment, context, d = [hA ; ctx], gate decision.
-// Not inlined: it runs on B of the 148 CTAs only and must not push the weight-prefetch registers of the frame loop into spills.
-__device__ __noinline__ void attend_one(const InferParams& p, float* sf, int i, int cur, bool forced) {
+// (Must stay inlined: taking the address of the kernel's parameter struct for a real call moves it to local memory and
+//  turns every p.field access of the frame loop into a local load -- measured: 40 -> 57 us per frame.)
+__device__ __forceinline__ void attend_one(const InferParams& p, float* sf, int i, int cur, bool forced) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.x;
     float* se = sf; float* sd = sf + LMAX; float* sp = sd + p.D;          // e / attn [LMAX], d [D], context partials [4][A]
@@ -280,16 +275,17 @@ __device__ __noinline__ void attend_one(const InferParams& p, float* sf, int i, 
         const int lg = threadIdx.x / a4n, a4 = threadIdx.x - lg * a4n;
         if (lg < ngrp) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int l0 = lg; l0 < p.L; l0 += 6 * ngrp) {             // 6 independent 16-byte loads in flight per thread
-                float4 v[6];
+            constexpr int CU = 6;                                     // independent 16-byte loads in flight per thread
+            for (int l0 = lg; l0 < p.L; l0 += CU * ngrp) {
+                float4 v[CU];
 #pragma unroll
-                for (int u = 0; u < 6; ++u) {
+                for (int u = 0; u < CU; ++u) {
                     const int l = l0 + u * ngrp;
                     v[u] = l < p.L ? *reinterpret_cast<const float4*>(p.Vp + (static_cast<long long>(l) * p.B + b) * p.A + 4 * a4)
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
-                for (int u = 0; u < 6; ++u) {
+                for (int u = 0; u < CU; ++u) {
                     const int l = l0 + u * ngrp;
                     const float w = l < p.L ? se[l] : 0.f;
                     acc.x = fmaf(w, v[u].x, acc.x); acc.y = fmaf(w, v[u].y, acc.y); acc.z = fmaf(w, v[u].z, acc.z); acc.w = fmaf(w, v[u].w, acc.w);
@@ -305,7 +301,7 @@ __device__ __noinline__ void attend_one(const InferParams& p, float* sf, int i, 
         sd[IH + a] = c;
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < p.D; k += INF_THREADS) p.d[b * p.D + k] = sd[k];
+    for (int k = threadIdx.x; k < p.D; k += INF_THREADS) p.d16[b * p.D + k] = __float2half_rn(sd[k]);
     if (warp == 0) {                             // gate decision for this frame (the frame that trips the gate IS emitted, :823-826)
         if (p.has_gate) {
             float s = 0.f;
@@ -349,14 +345,12 @@ infer_kernel(InferParams p) {
         // ---- P1 attention_lstm step on the previous output frame (zeros at i == 0): x = [out_{i-1} (80 -> 96) ; hA_{i-1}]
         __syncthreads();
         IT_TRACE(0);
-        stage_x(sx, 0, p.xprev, p.M, p.M, p.B);
-        for (int i2 = threadIdx.x; i2 < p.B * (XPAD - p.M); i2 += INF_THREADS)         // pad columns (later phases stage over them)
-            sx[(i2 / (XPAD - p.M)) * KP + p.M + (i2 % (XPAD - p.M))] = __float2half_rn(0.f);
-        stage_x(sx, XPAD, p.hA[prv], IH, IH, p.B);
-        __syncthreads();
+        stage16(sx, 0, p.x16, XPAD, p.B);                 // [B][96]: 80 channels + 16 zero pads
+        stage16(sx, XPAD, p.hA16[prv], IH, p.B);
+        stage_wait();
         IT_TRACE(1);
         mv_phase<kB16>(p.wA, IH / 2, nmA, 4, spart, sx, pf,
-                       [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.bA, p.cA, p.hA[cur]); });
+                       [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.bA, p.cA, p.hA[cur], p.hA16[cur]); });
         if (forced) mv_prefetch(pf, p.w0, IH / 2, nm0, 4); else mv_prefetch(pf, p.wq, p.A / 8, nmd, INF_WARPS);
         IT_TRACE(2);
         grid_sync(p, epoch);
@@ -364,8 +358,8 @@ infer_kernel(InferParams p) {
 
         if (!forced) {
             // ---- P2 query projection (no bias)
-            stage_x(sx, 0, p.hA[cur], IH, IH, p.B);
-            __syncthreads();
+            stage16(sx, 0, p.hA16[cur], IH, p.B);
+            stage_wait();
             IT_TRACE(4);
             mv_phase<kB16>(p.wq, p.A / 8, nmd, INF_WARPS, spart, sx, pf, [&](int task, float (&d)[4]) {
                 const int j = lane & 3, r = lane >> 2;
@@ -402,51 +396,51 @@ infer_kernel(InferParams p) {
         grid_sync(p, epoch);
         IT_TRACE(8);
         // ---- P4 lstm layer 0 on [d ; h0_{i-1}]
-        stage_x(sx, 0, p.d, p.D, p.D, p.B);
-        stage_x(sx, p.D, p.h0[prv], IH, IH, p.B);
-        __syncthreads();
+        stage16(sx, 0, p.d16, p.D, p.B);
+        stage16(sx, p.D, p.h016[prv], IH, p.B);
+        stage_wait();
         IT_TRACE(9);
         mv_phase<kB16>(p.w0, IH / 2, nm0, 4, spart, sx, pf,
-                       [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.b0, p.c0, p.h0[cur]); });
+                       [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.b0, p.c0, nullptr, p.h016[cur]); });
         mv_prefetch(pf, p.w1, IH / 2, nm1, 4);
         IT_TRACE(10);
         grid_sync(p, epoch);
         IT_TRACE(11);
         // ---- P5 lstm layer 1 on [h0 ; h1_{i-1}]
-        stage_x(sx, 0, p.h0[cur], IH, IH, p.B);
-        stage_x(sx, IH, p.h1[prv], IH, IH, p.B);
-        __syncthreads();
+        stage16(sx, 0, p.h016[cur], IH, p.B);
+        stage16(sx, IH, p.h116[prv], IH, p.B);
+        stage_wait();
         IT_TRACE(12);
         mv_phase<kB16>(p.w1, IH / 2, nm1, 4, spart, sx, pf,
-                       [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.b1, p.c1, p.h1[cur]); });
+                       [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.b1, p.c1, nullptr, p.h116[cur]); });
         mv_prefetch(pf, p.wd1, IH / 8, nmd, INF_WARPS);
         IT_TRACE(13);
         grid_sync(p, epoch);
         IT_TRACE(14);
         // ---- P6/P7 dense layers (tanh)
-        auto dense = [&](const __half* W, const float* bias, const float* x, float* y) {
-            stage_x(sx, 0, x, IH, IH, p.B);
-            __syncthreads();
+        auto dense = [&](const __half* W, const float* bias, const __half* x, __half* y) {
+            stage16(sx, 0, x, IH, p.B);
+            stage_wait();
             mv_phase<kB16>(W, IH / 8, nmd, INF_WARPS, spart, sx, pf, [&](int task, float (&d)[4]) {
                 const int j = lane & 3, r = lane >> 2;
                 const float b0 = bias[task * 8 + 2 * j], b1 = bias[task * 8 + 2 * j + 1];
-                if (r < p.B) { y[r * IH + 8 * task + 2 * j] = tanh_f(d[0] + b0); y[r * IH + 8 * task + 2 * j + 1] = tanh_f(d[1] + b1); }
-                if (kB16 && r + 8 < p.B) { y[(r + 8) * IH + 8 * task + 2 * j] = tanh_f(d[2] + b0); y[(r + 8) * IH + 8 * task + 2 * j + 1] = tanh_f(d[3] + b1); }
+                if (r < p.B) *reinterpret_cast<__half2*>(y + r * IH + 8 * task + 2 * j) = __floats2half2_rn(tanh_f(d[0] + b0), tanh_f(d[1] + b1));
+                if (kB16 && r + 8 < p.B) *reinterpret_cast<__half2*>(y + (r + 8) * IH + 8 * task + 2 * j) = __floats2half2_rn(tanh_f(d[2] + b0), tanh_f(d[3] + b1));
             });
         };
-        dense(p.wd1, p.bd1, p.h1[cur], p.y1);
+        dense(p.wd1, p.bd1, p.h116[cur], p.y116);
         mv_prefetch(pf, p.wd2, IH / 8, nmd, INF_WARPS);
         IT_TRACE(15);
         grid_sync(p, epoch);
         IT_TRACE(16);
-        dense(p.wd2, p.bd2, p.y1, p.y2);
+        dense(p.wd2, p.bd2, p.y116, p.y216);
         mv_prefetch(pf, p.wc, p.M / 4, nmd, INF_WARPS);
         IT_TRACE(17);
         grid_sync(p, epoch);
         IT_TRACE(18);
         // ---- P8 conv + inverse affine: out = (residual - b) / exp(log_s); task rows = (log_s, b) of 4 consecutive channels
-        stage_x(sx, 0, p.y2, IH, IH, p.B);
-        __syncthreads();
+        stage16(sx, 0, p.y216, IH, p.B);
+        stage_wait();
         mv_phase<kB16>(p.wc, p.M / 4, nmd, INF_WARPS, spart, sx, pf, [&](int task, float (&d)[4]) {
             const int j = lane & 3, r = lane >> 2;
             const int m = 4 * task + j;
@@ -461,7 +455,7 @@ infer_kernel(InferParams p) {
                     const bool emit = (i < p.n_frames[b]);
                     const float val = (p.residual[ro + m] - (d[2 * half + 1] + bb)) / expf(d[2 * half] + bl);
                     p.out[ro + m] = emit ? val : 0.f;
-                    p.xprev[b * p.M + m] = val;
+                    p.x16[b * XPAD + m] = __float2half_rn(val);
                 }
             }
         });
@@ -536,8 +530,9 @@ static InferScratch plan_infer(const FtArStepDesc& d, uint8_t* base) {
     s.text16 = reinterpret_cast<uint16_t*>(get(size_t(d.L) * d.B * E * 2));
     s.Kp = reinterpret_cast<float*>(get(size_t(d.L) * d.B * A * 4));
     s.Vp = reinterpret_cast<float*>(get(size_t(d.L) * d.B * A * 4));
-    // state: hA[2], cA, h0[2], c0, h1[2], c1 (9 x B*IH), xprev (B*M), q (B*A), e (B*L), d (B*D), y1, y2 (B*IH)
-    s.state_floats = size_t(d.B) * (9 * IH + M + A + d.L + D + 2 * IH) + 64;
+    // state (fp32): hA[2], cA, c0, c1 (5 x B*IH), q (B*A), e (B*L); (fp16 mirrors, counted in floats): hA16[2], h016[2], h116[2],
+    // y116, y216 (8 x B*IH halfs), d16 (B*D), x16 (B*96)
+    s.state_floats = size_t(d.B) * (5 * IH + A + d.L) + (size_t(d.B) * (8 * IH + D + XPAD) + 1) / 2 + 256;
     s.state = reinterpret_cast<float*>(get(s.state_floats * 4));
     s.ints = reinterpret_cast<int*>(get((size_t(d.B) + 64) * 4));
     s.total = off;
@@ -606,11 +601,12 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
     float* f = s.state;
     auto take = [&](size_t n) { float* r = f; f += (n + 3) & ~size_t(3); return r; };     // 16-byte aligned pieces (float4 staging loads)
     const size_t BH = static_cast<size_t>(B) * IH;
-    p.hA[0] = take(BH); p.hA[1] = take(BH); p.cA = take(BH);
-    p.h0[0] = take(BH); p.h0[1] = take(BH); p.c0 = take(BH);
-    p.h1[0] = take(BH); p.h1[1] = take(BH); p.c1 = take(BH);
-    p.xprev = take(static_cast<size_t>(B) * M); p.q = take(static_cast<size_t>(B) * A); p.e = take(static_cast<size_t>(B) * d->L);
-    p.d = take(static_cast<size_t>(B) * D); p.y1 = take(BH); p.y2 = take(BH);
+    auto take16 = [&](size_t n) { return reinterpret_cast<__half*>(take((n + 1) / 2)); };
+    p.hA[0] = take(BH); p.hA[1] = take(BH); p.cA = take(BH); p.c0 = take(BH); p.c1 = take(BH);
+    p.q = take(static_cast<size_t>(B) * A); p.e = take(static_cast<size_t>(B) * d->L);
+    p.hA16[0] = take16(BH); p.hA16[1] = take16(BH); p.h016[0] = take16(BH); p.h016[1] = take16(BH);
+    p.h116[0] = take16(BH); p.h116[1] = take16(BH); p.y116 = take16(BH); p.y216 = take16(BH);
+    p.d16 = take16(static_cast<size_t>(B) * D); p.x16 = take16(static_cast<size_t>(B) * XPAD);
     p.alive = s.ints; p.barrier = s.ints + B + 32;
     p.status = ft_status_word();
     p.trace = g_infer_trace;
