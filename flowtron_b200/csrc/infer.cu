@@ -16,9 +16,16 @@
 //     bytes and issues 8 of them back to back (4 KB in flight per warp, 16 warps per SM);
 //   * a task's K range is split over the warps of a CTA (partial accumulators meet in shared memory), so all 16 warps of
 //     every SM stream weights in every phase;
-//   * a warp's share of the NEXT phase's weights is prefetched into registers before each grid barrier (weights do not depend
-//     on what the barrier waits for); scores run over all warps of the grid, softmax (+ prior posterior) + context + gate of
-//     one utterance inside one CTA; 9 software grid barriers per frame (6 with forced alignments), ~1.2 us each
+//   * a warp's share of the NEXT phase's weights is prefetched into registers before it waits for that phase's inputs (weights
+//     do not depend on them); scores run over all warps of the grid, softmax (+ prior posterior) + context + gate of one
+//     utterance inside one CTA;
+//   * NO grid barriers (r2 call 7 trace: 9 barriers x 1.4 us + 9 staging round trips x 0.6 us = 18 of a frame's 39 us): the
+//     DATA IS THE FLAG.  Every exchanged activation lives in a ring of 3 frame slots pre-filled with a sentinel (0xFFFF per
+//     fp16, 0xFFFFFFFF per fp32 word: bit patterns no conversion produces); producers store results with st.relaxed.gpu and
+//     reset the same elements of the NEXT slot to the sentinel; consumers spin with ld.relaxed.gpu on the very words they need
+//     until no sentinel is left and copy them to shared memory.  A phase hand-over costs one L2 store + one L2 load instead of
+//     membar + atomic + poll + barrier + load.  A slot is reset two frames after its last reader: every read is followed by a
+//     store that all CTAs consume within one frame, and one gpu-scope fence per thread per frame makes that chain formal
 //     (tools/trace_infer.py prints the phase table).
 // Same operand precision as the training kernels (fp16 operands, fp32 accumulate/state).
 #include "ptx.cuh"
@@ -50,11 +57,15 @@ struct InferParams {
     float* out;                            // [T,B,M]
     float* attn_out;                       // [T,B,L]
     int* n_frames;                         // [B]
-    // state (global scratch, zero-initialised by the launcher)
-    float *hA[2], *cA, *c0, *c1, *q, *e;   // fp32: attention-LSTM output (gate / d), cell states, query, scores
-    __half *hA16[2], *h016[2], *h116[2], *d16, *y116, *y216, *x16;   // fp16 mirrors in staging layout [B][K]: what the next phases consume
-    int* alive;                            // [B] 1 while the sample is still generating
-    int* barrier;                          // monotonic grid barrier counter
+    // state (global scratch).  Exchanged tensors are rings of 3 frame slots (slot = frame % 3) initialised to the sentinel
+    // (slot 2 of the recurrent ones to zero: the state before frame 0); cell states are private to their producing lanes.
+    float *cA, *c0, *c1;
+    // (slot-0 pointers; slot k of every ring lies k * slot_bytes further: no dynamically indexed arrays in the parameter struct,
+    //  which would move it to local memory)
+    long long slot_bytes;
+    float *hA, *q, *e;                     // fp32: attention-LSTM output (gate), query, scores
+    __half *hA16, *h016, *h116, *d16, *y116, *y216, *x16;   // fp16 [B][K]: what the next phases consume
+    uint32_t* alive;                       // [B] per slot: 1 while the sample keeps generating after this frame, 0 once stopped
     int* status;
     long long* trace;                      // debug: [T][32] clock64 stamps of CTA 0 (tools/trace_infer.py), or null
 };
@@ -62,33 +73,89 @@ struct InferParams {
 static long long* g_infer_trace = nullptr;
 #define IT_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[i * 32 + (slot)] = clock64(); } while (0)
 
-// Grid barrier: one release-add per CTA on a monotonic counter, one acquiring poller per CTA.  The release (gpu scope) after the
-// CTA barrier is cumulative over every thread's earlier writes, so no separate __threadfence() is needed.
-__device__ __forceinline__ void grid_sync(const InferParams& p, int& epoch) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        ++epoch;
-        red_release_add(p.barrier, 1);
-        wait_flag_ge(p.barrier, epoch * static_cast<int>(gridDim.x), p.status, 301);
+constexpr uint32_t SENT = 0xFFFFFFFFu;
+#define SL(ptr, k) (reinterpret_cast<decltype(ptr)>(reinterpret_cast<char*>(ptr) + (k)))     /* ring slot: k = slot index * slot_bytes */
+__device__ __forceinline__ uint4 ld_rlx_v4(const void* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_rlx_u32(const void* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_rlx_u32(void* p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_rlx_u16(void* p, uint16_t v) { asm volatile("st.relaxed.gpu.global.u16 [%0], %1;" ::"l"(p), "h"(v) : "memory"); }
+__device__ __forceinline__ void st_rlx_f32(float* p, float v) { st_rlx_u32(p, __float_as_uint(v)); }
+__device__ __forceinline__ void st_rlx_h(__half* p, float v) { st_rlx_u16(p, __half_as_ushort(__float2half_rn(v))); }
+__device__ __forceinline__ void st_rlx_h2(__half* p, float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    st_rlx_u32(p, *reinterpret_cast<const uint32_t*>(&h));
+}
+// any fp16 element of the 16-byte packet still the sentinel?
+__device__ __forceinline__ bool sent16(const uint4& v) { return (__vcmpeq2(v.x, SENT) | __vcmpeq2(v.y, SENT) | __vcmpeq2(v.z, SENT) | __vcmpeq2(v.w, SENT)) != 0u; }
+__device__ __forceinline__ uint4 poll16(const void* g, int* status, int code) {
+    uint4 v = ld_rlx_v4(g);
+    if (sent16(v)) {
+        const long long t0 = clock64();
+        do {
+            v = ld_rlx_v4(g);
+            if (clock64() - t0 > FT_WATCHDOG_CYCLES) watchdog_fail(status, code);
+        } while (sent16(v));
     }
-    __syncthreads();
+    return v;
+}
+__device__ __forceinline__ float poll_f32(const float* g, int* status, int code) {
+    uint32_t v = ld_rlx_u32(g);
+    if (v == SENT) {
+        const long long t0 = clock64();
+        do {
+            v = ld_rlx_u32(g);
+            if (clock64() - t0 > FT_WATCHDOG_CYCLES) watchdog_fail(status, code);
+        } while (v == SENT);
+    }
+    return __uint_as_float(v);
 }
 
-// activations of a phase: fp16 global mirror [B, K] (written by the producing phase's epilogue) -> shared [16][KP] at column c0
-// with 16-byte cp.async copies: no registers, every copy of the phase in flight at once (batch rows >= B stay zero).
-// (K and c0 multiples of 8.)  Callers finish with stage_wait().
-__device__ __forceinline__ void stage16(__half* sx, int c0, const __half* src, int K, int B) {
-    const int k8 = K >> 3, total = B * k8;
-    for (int idx = threadIdx.x; idx < total; idx += INF_THREADS) {
-        const int b = idx / k8, i8 = idx - b * k8;
-        const uint32_t dst = smem_u32(sx + b * KP + c0 + 8 * i8);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + static_cast<long long>(b) * K + 8 * i8) : "memory");
+// activations of a phase: up to two fp16 ring-slot tensors [B, pitch] (written by the producing phases' epilogues on other SMs)
+// -> shared [16][KP] at columns cA / cB.  Round = every still-pending 16-byte packet of this thread is fetched with cp.async.cg
+// (L2, no registers, all in flight at once), then checked in shared memory; packets that still hold a sentinel element are
+// fetched again next round.  Batch rows >= B stay zero.  K, pitch and column offsets are multiples of 8.  Callers finish with
+// __syncthreads().
+__device__ __forceinline__ void stage2(__half* sx, int cA, const __half* srcA, int KA, int pitchA, int cB, const __half* srcB, int KB, int pitchB,
+                                       int B, int* status) {
+    const int k8A = KA >> 3, k8B = KB >> 3, totA = B * k8A, total = totA + B * k8B;
+    uint32_t pend = 0;                                            // bit u: packet threadIdx.x + u * INF_THREADS not valid yet
+    for (int u = 0, idx = threadIdx.x; idx < total; ++u, idx += INF_THREADS) pend |= 1u << u;
+    long long t0 = 0;
+    while (pend) {
+        for (int u = 0, idx = threadIdx.x; idx < total; ++u, idx += INF_THREADS) {
+            if (pend >> u & 1u) {
+                const bool inA = idx < totA;
+                const int j = inA ? idx : idx - totA, k8 = inA ? k8A : k8B;
+                const int b = j / k8, i8 = j - b * k8;
+                const __half* g = (inA ? srcA + static_cast<long long>(b) * pitchA : srcB + static_cast<long long>(b) * pitchB) + 8 * i8;
+                const uint32_t dst = smem_u32(sx + b * KP + (inA ? cA : cB) + 8 * i8);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        for (int u = 0, idx = threadIdx.x; idx < total; ++u, idx += INF_THREADS) {
+            if (pend >> u & 1u) {
+                const bool inA = idx < totA;
+                const int j = inA ? idx : idx - totA, k8 = inA ? k8A : k8B;
+                const int b = j / k8, i8 = j - b * k8;
+                const uint4 v = *reinterpret_cast<const uint4*>(sx + b * KP + (inA ? cA : cB) + 8 * i8);
+                if (!sent16(v)) pend &= ~(1u << u);
+            }
+        }
+        if (pend) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > FT_WATCHDOG_CYCLES) watchdog_fail(status, 302);
+        }
     }
-}
-__device__ __forceinline__ void stage_wait() {
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
 }
 
 __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -190,8 +257,10 @@ __device__ __forceinline__ void mv_phase(const __half* __restrict__ W, int n_tas
     }
 }
 
-// LSTM cell for task = 2 units x 4 gates (rows i0,f0,g0,o0,i1,f1,g1,o1): lane j holds (i,f) [j even] or (g,o) [j odd] of unit j/2
-__device__ __forceinline__ void lstm_epi(const InferParams& p, int task, float (&d)[4], const float* bias, float* c, float* hnew, __half* h16) {
+// LSTM cell for task = 2 units x 4 gates (rows i0,f0,g0,o0,i1,f1,g1,o1): lane j holds (i,f) [j even] or (g,o) [j odd] of unit j/2.
+// h goes to ring slot `h16` (and `hnew`, fp32, when given); the same elements of the next slot are reset to the sentinel.
+__device__ __forceinline__ void lstm_epi(const InferParams& p, int task, float (&d)[4], const float* bias, float* c, float* hnew, float* hnew_next,
+                                         __half* h16, __half* h16_next) {
     const int lane = threadIdx.x & 31, j = lane & 3, r = lane >> 2;
     const float b0 = bias[task * 8 + 2 * j], b1 = bias[task * 8 + 2 * j + 1];
     float v[4] = {d[0] + b0, d[1] + b1, d[2] + b0, d[3] + b1};
@@ -209,8 +278,9 @@ __device__ __forceinline__ void lstm_epi(const InferParams& p, int task, float (
                 const float cn = gf * c[b * IH + u] + gi * gg;
                 c[b * IH + u] = cn;
                 const float h = go * tanh_f(cn);
-                if (hnew) hnew[b * IH + u] = h;
-                h16[b * IH + u] = __float2half_rn(h);
+                st_rlx_h(h16 + b * IH + u, h);
+                st_rlx_u16(h16_next + b * IH + u, 0xFFFFu);
+                if (hnew) { st_rlx_f32(hnew + b * IH + u, h); st_rlx_u32(hnew_next + b * IH + u, SENT); }
             }
         }
     }
@@ -219,7 +289,7 @@ __device__ __forceinline__ void lstm_epi(const InferParams& p, int task, float (
 // Utterance b inside CTA b: softmax (+ prior posterior) or the forced alignment, context, d = [hA ; ctx], gate decision.
 // (Must stay inlined: taking the address of the kernel's parameter struct for a real call moves it to local memory and
 //  turns every p.field access of the frame loop into a local load -- measured: 40 -> 57 us per frame.)
-__device__ __forceinline__ void attend_one(const InferParams& p, float* sf, int i, int cur, bool forced) {
+__device__ __forceinline__ void attend_one(const InferParams& p, float* sf, int i, long long cur, long long nxt, bool forced, bool was_alive) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.x;
     float* se = sf; float* sd = sf + LMAX; float* sp = sd + p.D;          // e / attn [LMAX], d [D], context partials [4][A]
@@ -228,7 +298,12 @@ __device__ __forceinline__ void attend_one(const InferParams& p, float* sf, int 
             float w[8];
             float mx = -INFINITY;
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) { const int l = lane + 32 * jj; w[jj] = (l < p.L) ? p.e[b * p.L + l] : -INFINITY; mx = fmaxf(mx, w[jj]); }
+            for (int jj = 0; jj < 8; ++jj) {
+                const int l = lane + 32 * jj;
+                w[jj] = -INFINITY;
+                if (l < p.L) w[jj] = poll_f32(SL(p.e, cur) + b * p.L + l, p.status, 303);
+                mx = fmaxf(mx, w[jj]);
+            }
 #pragma unroll
             for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             float s = 0.f;
@@ -267,7 +342,9 @@ __device__ __forceinline__ void attend_one(const InferParams& p, float* sf, int 
     } else {
         for (int l = threadIdx.x; l < p.L; l += INF_THREADS) se[l] = p.attn_forced[(static_cast<long long>(i) * p.B + b) * p.L + l];
     }
-    for (int k = threadIdx.x; k < IH; k += INF_THREADS) sd[k] = p.hA[cur][b * IH + k];
+    // fp32 attention-LSTM output of this frame (exchanged: written by the P1 epilogues of other CTAs).  Warp 0 is busy with
+    // the softmax above, the other warps wait here.
+    for (int k = threadIdx.x; k < IH; k += INF_THREADS) sd[k] = poll_f32(SL(p.hA, cur) + b * IH + k, p.status, 304);
     __syncthreads();
     for (int l = threadIdx.x; l < p.L; l += INF_THREADS) p.attn_out[(static_cast<long long>(i) * p.B + b) * p.L + l] = se[l];
     const int a4n = p.A >> 2, ngrp = INF_THREADS / a4n < 4 ? INF_THREADS / a4n : 4;       // A = 640: 3 groups of 160 threads
@@ -301,19 +378,23 @@ __device__ __forceinline__ void attend_one(const InferParams& p, float* sf, int 
         sd[IH + a] = c;
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < p.D; k += INF_THREADS) p.d16[b * p.D + k] = __float2half_rn(sd[k]);
+    for (int k = 2 * threadIdx.x; k < p.D; k += 2 * INF_THREADS) {       // d = [hA ; ctx] (fp16) for lstm layer 0 (D even)
+        st_rlx_h2(SL(p.d16, cur) + b * p.D + k, sd[k], sd[k + 1]);
+        st_rlx_u32(SL(p.d16, nxt) + b * p.D + k, SENT);
+    }
     if (warp == 0) {                             // gate decision for this frame (the frame that trips the gate IS emitted, :823-826)
+        bool alive = was_alive;
         if (p.has_gate) {
             float s = 0.f;
             for (int k = lane; k < p.D; k += 32) s = fmaf(p.wg[k], sd[k], s);
 #pragma unroll
             for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0 && p.alive[b]) {
-                p.n_frames[b] = i + 1;
-                if (sigmoid_f(s + p.bg[0]) > p.gate_threshold) p.alive[b] = 0;
-            }
-        } else if (lane == 0) {
-            p.n_frames[b] = i + 1;
+            if (was_alive && sigmoid_f(s + p.bg[0]) > p.gate_threshold) alive = false;
+        }
+        if (lane == 0) {
+            if (was_alive) p.n_frames[b] = i + 1;
+            st_rlx_u32(SL(p.alive, cur) + b, alive ? 1u : 0u);
+            st_rlx_u32(SL(p.alive, nxt) + b, SENT);
         }
     }
 }
@@ -325,122 +406,146 @@ infer_kernel(InferParams p) {
     __half* sx = reinterpret_cast<__half*>(smem_raw);                          // [16][KP] fp16 activations of the phase
     float* spart = reinterpret_cast<float*>(sx + 16 * KP);                     // [16 warps][32 lanes][4] partial accumulators
     float* sf = spart + INF_WARPS * 128;                                       // attention scratch: e[LMAX] d[D] partials[4][A]
+    __shared__ int s_alive[16], s_nfr[16];                                     // every CTA tracks every sample's gate state
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int epoch = 0;
-    for (int i = threadIdx.x; i < 16 * KP; i += INF_THREADS) sx[i] = __float2half_rn(0.f);     // batch rows >= B and pads: zero forever
+    for (int i = threadIdx.x; i < 16 * KP; i += INF_THREADS) sx[i] = __float2half_rn(0.f);     // batch rows >= B: zero forever
+    if (threadIdx.x < 16) { s_alive[threadIdx.x] = threadIdx.x < p.B; s_nfr[threadIdx.x] = 0; }
     __syncthreads();
 
     const int nmA = (XPAD + IH) / 32, nm0 = (p.D + IH) / 32, nm1 = 2 * IH / 32, nmd = IH / 32;
     const int gw = blockIdx.x * INF_WARPS + warp, nw = gridDim.x * INF_WARPS;
+    // which phases this CTA has tasks in (CTAs without a task skip the phase's staging: nothing they read would be followed
+    // by a store, and the ring-slot reuse argument relies on read -> store chains)
+    const bool act_lstm = static_cast<int>(blockIdx.x) * 4 < IH / 2, act_q = static_cast<int>(blockIdx.x) < p.A / 8;
+    const bool act_dense = static_cast<int>(blockIdx.x) < IH / 8, act_conv = static_cast<int>(blockIdx.x) < p.M / 4;
+    const bool forced = p.attn_forced != nullptr;    // `attn` given (flowtron.py:585-588): no query / score / softmax / prior
     Prefetch pf;
     mv_prefetch(pf, p.wA, IH / 2, nmA, 4);
     for (int i = 0; i < p.T; ++i) {
-        const int cur = i & 1, prv = cur ^ 1;
-        // all samples stopped?  (alive is only written in the attention phase of the previous frame, ordered by grid barriers)
+        const long long cur = (i % 3) * p.slot_bytes, prv = ((i + 2) % 3) * p.slot_bytes, nxt = ((i + 1) % 3) * p.slot_bytes;
+        // all samples stopped?  (s_alive: the flags every CTA read in the previous frame's P4 -- identical everywhere)
         bool any = false;
-        for (int b = 0; b < p.B; ++b) any |= (ld_acquire(&p.alive[b]) != 0);
+        for (int b = 0; b < p.B; ++b) any |= (s_alive[b] != 0);
         if (!any) break;
-        const bool forced = p.attn_forced != nullptr;    // `attn` given (flowtron.py:585-588): no query / score / softmax / prior
+        __threadfence();                         // one gpu-scope fence per thread per frame: see the header (slot reuse)
 
         // ---- P1 attention_lstm step on the previous output frame (zeros at i == 0): x = [out_{i-1} (80 -> 96) ; hA_{i-1}]
-        __syncthreads();
         IT_TRACE(0);
-        stage16(sx, 0, p.x16, XPAD, p.B);                 // [B][96]: 80 channels + 16 zero pads
-        stage16(sx, XPAD, p.hA16[prv], IH, p.B);
-        stage_wait();
+        if (act_lstm) {
+            if (threadIdx.x < 16 * 2) *reinterpret_cast<uint4*>(sx + (threadIdx.x >> 1) * KP + p.M + 8 * (threadIdx.x & 1)) = make_uint4(0u, 0u, 0u, 0u);
+            stage2(sx, 0, SL(p.x16, prv), p.M, XPAD, XPAD, SL(p.hA16, prv), IH, IH, p.B, p.status);
+        }
+        __syncthreads();
         IT_TRACE(1);
-        mv_phase<kB16>(p.wA, IH / 2, nmA, 4, spart, sx, pf,
-                       [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.bA, p.cA, p.hA[cur], p.hA16[cur]); });
+        mv_phase<kB16>(p.wA, IH / 2, nmA, 4, spart, sx, pf, [&](int task, float (&d)[4]) {
+            lstm_epi(p, task, d, p.bA, p.cA, SL(p.hA, cur), SL(p.hA, nxt), SL(p.hA16, cur), SL(p.hA16, nxt));
+        });
         if (forced) mv_prefetch(pf, p.w0, IH / 2, nm0, 4); else mv_prefetch(pf, p.wq, p.A / 8, nmd, INF_WARPS);
         IT_TRACE(2);
-        grid_sync(p, epoch);
-        IT_TRACE(3);
 
         if (!forced) {
             // ---- P2 query projection (no bias)
-            stage16(sx, 0, p.hA16[cur], IH, p.B);
-            stage_wait();
+            if (act_q) stage2(sx, 0, SL(p.hA16, cur), IH, IH, 0, nullptr, 0, 0, p.B, p.status);
+            __syncthreads();
             IT_TRACE(4);
             mv_phase<kB16>(p.wq, p.A / 8, nmd, INF_WARPS, spart, sx, pf, [&](int task, float (&d)[4]) {
                 const int j = lane & 3, r = lane >> 2;
-                if (r < p.B) { p.q[r * p.A + 8 * task + 2 * j] = d[0]; p.q[r * p.A + 8 * task + 2 * j + 1] = d[1]; }
-                if (kB16 && r + 8 < p.B) { p.q[(r + 8) * p.A + 8 * task + 2 * j] = d[2]; p.q[(r + 8) * p.A + 8 * task + 2 * j + 1] = d[3]; }
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int b = r + 8 * half;
+                    if (b < p.B && (half == 0 || kB16)) {
+                        const int o = b * p.A + 8 * task + 2 * j;
+                        st_rlx_f32(SL(p.q, cur) + o, d[2 * half]); st_rlx_f32(SL(p.q, cur) + o + 1, d[2 * half + 1]);
+                        st_rlx_u32(SL(p.q, nxt) + o, SENT); st_rlx_u32(SL(p.q, nxt) + o + 1, SENT);
+                    }
+                }
             });
             mv_prefetch(pf, p.w0, IH / 2, nm0, 4);       // lstm layer 0's weights ride through the two attention phases
             IT_TRACE(5);
-            grid_sync(p, epoch);
-            IT_TRACE(6);
             // ---- P3a scores e[b,l] = v . tanh(q[b] + K[l,b]) / temperature over ALL warps of the grid (no key mask in
-            //      inference, flowtron.py:800-803).  (Inside one CTA per utterance this took 19 of the frame's 49 us.)
+            //      inference, flowtron.py:800-803); every warp polls the query row it needs
             for (int t = gw; t < p.B * p.L; t += nw) {
                 const int b = t / p.L, l = t - b * p.L;
                 const float* kr = p.Kp + (static_cast<long long>(l) * p.B + b) * p.A;
-                const float* qr = p.q + b * p.A;
+                const float* qr = SL(p.q, cur) + b * p.A;
                 float s = 0.f;
                 for (int a0 = 0; a0 < p.A; a0 += 128) {                      // 4 independent loads per operand in flight
-                    float kv[4], qv[4];
+                    float kv[4]; uint32_t qv[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) { const int a = a0 + 32 * u + lane; kv[u] = a < p.A ? kr[a] : 0.f; qv[u] = a < p.A ? qr[a] : 0.f; }
+                    for (int u = 0; u < 4; ++u) { const int a = a0 + 32 * u + lane; kv[u] = a < p.A ? kr[a] : 0.f; qv[u] = a < p.A ? ld_rlx_u32(qr + a) : 0u; }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) { const int a = a0 + 32 * u + lane; if (a < p.A) s = fmaf(p.v[a], tanh_f(qv[u] + kv[u]), s); }
+                    for (int u = 0; u < 4; ++u) {
+                        const int a = a0 + 32 * u + lane;
+                        if (a < p.A) {
+                            const float qf = qv[u] == SENT ? poll_f32(qr + a, p.status, 305) : __uint_as_float(qv[u]);
+                            s = fmaf(p.v[a], tanh_f(qf + kv[u]), s);
+                        }
+                    }
                 }
 #pragma unroll
                 for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == 0) p.e[t] = s * p.inv_temperature;
+                if (lane == 0) { st_rlx_f32(SL(p.e, cur) + t, s * p.inv_temperature); st_rlx_u32(SL(p.e, nxt) + t, SENT); }
             }
-            grid_sync(p, epoch);
+            IT_TRACE(6);
         }
         // ---- P3b utterance b inside CTA b (attend_one)
-        if (static_cast<int>(blockIdx.x) < p.B) attend_one(p, sf, i, cur, forced);
+        if (static_cast<int>(blockIdx.x) < p.B) attend_one(p, sf, i, cur, nxt, forced, s_alive[blockIdx.x] != 0);
         IT_TRACE(7);
-        grid_sync(p, epoch);
-        IT_TRACE(8);
-        // ---- P4 lstm layer 0 on [d ; h0_{i-1}]
-        stage16(sx, 0, p.d16, p.D, p.B);
-        stage16(sx, p.D, p.h016[prv], IH, p.B);
-        stage_wait();
+        // ---- P4 lstm layer 0 on [d ; h0_{i-1}]; every CTA reads the samples' gate flags of this frame
+        if (act_lstm) {
+            stage2(sx, 0, SL(p.d16, cur), p.D, p.D, p.D, SL(p.h016, prv), IH, IH, p.B, p.status);
+        }
+        if (threadIdx.x < p.B) {
+            const float fl = poll_f32(reinterpret_cast<const float*>(SL(p.alive, cur)) + threadIdx.x, p.status, 306);
+            if (s_alive[threadIdx.x]) s_nfr[threadIdx.x] = i + 1;
+            s_alive[threadIdx.x] = __float_as_uint(fl) != 0u;
+        }
+        __syncthreads();
         IT_TRACE(9);
-        mv_phase<kB16>(p.w0, IH / 2, nm0, 4, spart, sx, pf,
-                       [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.b0, p.c0, nullptr, p.h016[cur]); });
+        mv_phase<kB16>(p.w0, IH / 2, nm0, 4, spart, sx, pf, [&](int task, float (&d)[4]) {
+            lstm_epi(p, task, d, p.b0, p.c0, nullptr, nullptr, SL(p.h016, cur), SL(p.h016, nxt));
+        });
         mv_prefetch(pf, p.w1, IH / 2, nm1, 4);
         IT_TRACE(10);
-        grid_sync(p, epoch);
-        IT_TRACE(11);
         // ---- P5 lstm layer 1 on [h0 ; h1_{i-1}]
-        stage16(sx, 0, p.h016[cur], IH, p.B);
-        stage16(sx, IH, p.h116[prv], IH, p.B);
-        stage_wait();
+        if (act_lstm) {
+            stage2(sx, 0, SL(p.h016, cur), IH, IH, IH, SL(p.h116, prv), IH, IH, p.B, p.status);
+        }
+        __syncthreads();
         IT_TRACE(12);
-        mv_phase<kB16>(p.w1, IH / 2, nm1, 4, spart, sx, pf,
-                       [&](int task, float (&d)[4]) { lstm_epi(p, task, d, p.b1, p.c1, nullptr, p.h116[cur]); });
+        mv_phase<kB16>(p.w1, IH / 2, nm1, 4, spart, sx, pf, [&](int task, float (&d)[4]) {
+            lstm_epi(p, task, d, p.b1, p.c1, nullptr, nullptr, SL(p.h116, cur), SL(p.h116, nxt));
+        });
         mv_prefetch(pf, p.wd1, IH / 8, nmd, INF_WARPS);
         IT_TRACE(13);
-        grid_sync(p, epoch);
-        IT_TRACE(14);
         // ---- P6/P7 dense layers (tanh)
-        auto dense = [&](const __half* W, const float* bias, const __half* x, __half* y) {
-            stage16(sx, 0, x, IH, p.B);
-            stage_wait();
+        auto dense = [&](const __half* W, const float* bias, const __half* x, __half* y, __half* y_next) {
+            if (act_dense) stage2(sx, 0, x, IH, IH, 0, nullptr, 0, 0, p.B, p.status);
+            __syncthreads();
             mv_phase<kB16>(W, IH / 8, nmd, INF_WARPS, spart, sx, pf, [&](int task, float (&d)[4]) {
                 const int j = lane & 3, r = lane >> 2;
                 const float b0 = bias[task * 8 + 2 * j], b1 = bias[task * 8 + 2 * j + 1];
-                if (r < p.B) *reinterpret_cast<__half2*>(y + r * IH + 8 * task + 2 * j) = __floats2half2_rn(tanh_f(d[0] + b0), tanh_f(d[1] + b1));
-                if (kB16 && r + 8 < p.B) *reinterpret_cast<__half2*>(y + (r + 8) * IH + 8 * task + 2 * j) = __floats2half2_rn(tanh_f(d[2] + b0), tanh_f(d[3] + b1));
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int b = r + 8 * half;
+                    if (b < p.B && (half == 0 || kB16)) {
+                        const int o = b * IH + 8 * task + 2 * j;
+                        st_rlx_h2(y + o, tanh_f(d[2 * half] + b0), tanh_f(d[2 * half + 1] + b1));
+                        st_rlx_u32(y_next + o, SENT);
+                    }
+                }
             });
         };
-        dense(p.wd1, p.bd1, p.h116[cur], p.y116);
+        dense(p.wd1, p.bd1, SL(p.h116, cur), SL(p.y116, cur), SL(p.y116, nxt));
         mv_prefetch(pf, p.wd2, IH / 8, nmd, INF_WARPS);
         IT_TRACE(15);
-        grid_sync(p, epoch);
-        IT_TRACE(16);
-        dense(p.wd2, p.bd2, p.y116, p.y216);
+        dense(p.wd2, p.bd2, SL(p.y116, cur), SL(p.y216, cur), SL(p.y216, nxt));
         mv_prefetch(pf, p.wc, p.M / 4, nmd, INF_WARPS);
         IT_TRACE(17);
-        grid_sync(p, epoch);
-        IT_TRACE(18);
         // ---- P8 conv + inverse affine: out = (residual - b) / exp(log_s); task rows = (log_s, b) of 4 consecutive channels
-        stage16(sx, 0, p.y216, IH, p.B);
-        stage_wait();
+        if (act_conv) stage2(sx, 0, SL(p.y216, cur), IH, IH, 0, nullptr, 0, 0, p.B, p.status);
+        __syncthreads();
+        IT_TRACE(18);
         mv_phase<kB16>(p.wc, p.M / 4, nmd, INF_WARPS, spart, sx, pf, [&](int task, float (&d)[4]) {
             const int j = lane & 3, r = lane >> 2;
             const int m = 4 * task + j;
@@ -450,19 +555,18 @@ infer_kernel(InferParams p) {
                 const int b = r + 8 * half;
                 if (b < p.B && (half == 0 || kB16)) {
                     const long long ro = (static_cast<long long>(i) * p.B + b) * p.M;
-                    // a sample that stopped at an earlier frame emits zeros; the frame that trips the gate is still emitted,
-                    // which n_frames (written in P3, ordered by the barriers since) encodes
-                    const bool emit = (i < p.n_frames[b]);
+                    // a sample that stopped at an earlier frame emits zeros; the frame that trips the gate is still emitted
+                    // (s_nfr: updated in this frame's P4 from the flags every CTA read)
+                    const bool emit = (i < s_nfr[b]);
                     const float val = (p.residual[ro + m] - (d[2 * half + 1] + bb)) / expf(d[2 * half] + bl);
                     p.out[ro + m] = emit ? val : 0.f;
-                    p.x16[b * XPAD + m] = __float2half_rn(val);
+                    st_rlx_h(SL(p.x16, cur) + b * XPAD + m, val);
+                    st_rlx_u16(SL(p.x16, nxt) + b * XPAD + m, 0xFFFFu);
                 }
             }
         });
         mv_prefetch(pf, p.wA, IH / 2, nmA, 4);           // next frame's attention LSTM
         IT_TRACE(19);
-        grid_sync(p, epoch);
-        IT_TRACE(20);
     }
 }
 
@@ -530,11 +634,13 @@ static InferScratch plan_infer(const FtArStepDesc& d, uint8_t* base) {
     s.text16 = reinterpret_cast<uint16_t*>(get(size_t(d.L) * d.B * E * 2));
     s.Kp = reinterpret_cast<float*>(get(size_t(d.L) * d.B * A * 4));
     s.Vp = reinterpret_cast<float*>(get(size_t(d.L) * d.B * A * 4));
-    // state (fp32): hA[2], cA, c0, c1 (5 x B*IH), q (B*A), e (B*L); (fp16 mirrors, counted in floats): hA16[2], h016[2], h116[2],
-    // y116, y216 (8 x B*IH halfs), d16 (B*D), x16 (B*96)
-    s.state_floats = size_t(d.B) * (5 * IH + A + d.L) + (size_t(d.B) * (8 * IH + D + XPAD) + 1) / 2 + 256;
+    // state: cell states cA, c0, c1 (3 x B*IH fp32), then the exchange rings (3 frame slots each): hA32 (B*IH), q (B*A), e (B*L),
+    // alive (B) as 32-bit words; hA16, h016, h116, y116, y216 (B*IH), d16 (B*D), x16 (B*96) as fp16 (counted in floats, each piece
+    // padded to 16 bytes)
+    s.state_floats = size_t(d.B) * 3 * IH + 3 * (size_t(d.B) * (IH + A + d.L + 1) + 16) +
+                     3 * ((size_t(d.B) * (5 * IH + D + XPAD) + 1) / 2 + 32) + 256;
     s.state = reinterpret_cast<float*>(get(s.state_floats * 4));
-    s.ints = reinterpret_cast<int*>(get((size_t(d.B) + 64) * 4));
+    s.ints = nullptr;
     s.total = off;
     return s;
 }
@@ -582,8 +688,6 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
         g.B = s.wv; g.C32 = s.Vp;
         FT_TRYX(launch_gemm(g, st));
     }
-    if (cudaMemsetAsync(s.state, 0, s.state_floats * 4, st) != cudaSuccess) return ft_set_error("infer: memset failed");
-    if (cudaMemsetAsync(s.ints, 0, (static_cast<size_t>(B) + 64) * 4, st) != cudaSuccess) return ft_set_error("infer: memset failed");
     if (cudaMemsetAsync(out, 0, sizeof(float) * d->T * B * M, st) != cudaSuccess) return ft_set_error("infer: memset failed");
     if (cudaMemsetAsync(attn_out, 0, sizeof(float) * d->T * B * d->L, st) != cudaSuccess) return ft_set_error("infer: memset failed");
     if (cudaMemsetAsync(n_frames, 0, sizeof(int) * B, st) != cudaSuccess) return ft_set_error("infer: memset failed");
@@ -599,22 +703,27 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
     p.has_gate = d->has_gate && w->gate_w;
     p.out = out; p.attn_out = attn_out; p.n_frames = n_frames;
     float* f = s.state;
-    auto take = [&](size_t n) { float* r = f; f += (n + 3) & ~size_t(3); return r; };     // 16-byte aligned pieces (float4 staging loads)
+    auto take = [&](size_t n) { float* r = f; f += (n + 3) & ~size_t(3); return r; };     // 16-byte aligned pieces (16-byte polls)
     const size_t BH = static_cast<size_t>(B) * IH;
     auto take16 = [&](size_t n) { return reinterpret_cast<__half*>(take((n + 1) / 2)); };
-    p.hA[0] = take(BH); p.hA[1] = take(BH); p.cA = take(BH); p.c0 = take(BH); p.c1 = take(BH);
-    p.q = take(static_cast<size_t>(B) * A); p.e = take(static_cast<size_t>(B) * d->L);
-    p.hA16[0] = take16(BH); p.hA16[1] = take16(BH); p.h016[0] = take16(BH); p.h016[1] = take16(BH);
-    p.h116[0] = take16(BH); p.h116[1] = take16(BH); p.y116 = take16(BH); p.y216 = take16(BH);
+    p.cA = take(BH); p.c0 = take(BH); p.c1 = take(BH);
+    float* ring0 = f;                                            // everything from here on is exchanged: sentinel-filled
+    p.hA = take(BH); p.q = take(static_cast<size_t>(B) * A); p.e = take(static_cast<size_t>(B) * d->L);
+    p.alive = reinterpret_cast<uint32_t*>(take(B));
+    p.hA16 = take16(BH); p.h016 = take16(BH); p.h116 = take16(BH); p.y116 = take16(BH); p.y216 = take16(BH);
     p.d16 = take16(static_cast<size_t>(B) * D); p.x16 = take16(static_cast<size_t>(B) * XPAD);
-    p.alive = s.ints; p.barrier = s.ints + B + 32;
+    p.slot_bytes = (f - ring0) * static_cast<long long>(sizeof(float));
+    f = ring0 + 3 * (f - ring0);
+    if (static_cast<size_t>(f - s.state) > s.state_floats) return ft_set_error("infer: scratch plan overflow");
+    if (cudaMemsetAsync(s.state, 0, (ring0 - s.state) * sizeof(float), st) != cudaSuccess) return ft_set_error("infer: memset failed");
+    if (cudaMemsetAsync(ring0, 0xFF, (f - ring0) * sizeof(float), st) != cudaSuccess) return ft_set_error("infer: memset failed");
+    // the state before frame 0 (slot 2 = frame -1): zero hidden states and a zero previous output frame
+    auto slot2 = [&](void* ptr) { return static_cast<char*>(ptr) + 2 * p.slot_bytes; };
+    if (cudaMemsetAsync(slot2(p.hA16), 0, BH * 2, st) != cudaSuccess || cudaMemsetAsync(slot2(p.h016), 0, BH * 2, st) != cudaSuccess ||
+        cudaMemsetAsync(slot2(p.h116), 0, BH * 2, st) != cudaSuccess || cudaMemsetAsync(slot2(p.x16), 0, static_cast<size_t>(B) * XPAD * 2, st) != cudaSuccess)
+        return ft_set_error("infer: memset failed");
     p.status = ft_status_word();
     p.trace = g_infer_trace;
-    {   // alive[b] = 1
-        static int ones[64];
-        for (int i = 0; i < 64; ++i) ones[i] = 1;
-        if (cudaMemcpyAsync(p.alive, ones, sizeof(int) * B, cudaMemcpyHostToDevice, st) != cudaSuccess) return ft_set_error("infer: memcpy failed");
-    }
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

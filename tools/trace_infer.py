@@ -22,13 +22,13 @@ with torch.no_grad():
     torch.cuda.synchronize()
     Lb.ft_debug_set_infer_trace(None)
 tr = trace.cpu().double()[20:180]
-names = ["frame start", "P1 staged", "P1 matvec+cell", "P1 barrier", "P2 staged", "P2 matvec", "P2 barrier", "P3 attention", "P3 barrier",
-         "P4 staged", "P4 matvec+cell", "P4 barrier", "P5 staged", "P5 matvec+cell", "P5 barrier", "P6 dense", "P6 barrier", "P7 dense",
-         "P7 barrier", "P8 conv+out", "P8 barrier"]
+names = {0: "frame start", 1: "P1 inputs staged", 2: "P1 matvec+cell", 4: "P2 input staged", 5: "P2 matvec (q)", 6: "P3a scores",
+         7: "P3b softmax+ctx+gate", 9: "P4 inputs staged", 10: "P4 matvec+cell", 12: "P5 inputs staged", 13: "P5 matvec+cell",
+         15: "P6 dense", 17: "P7 dense", 18: "P8 input staged", 19: "P8 conv+out"}
 period = (tr[1:, 0] - tr[:-1, 0]).mean().item()
 print(f"B={B}: frame period {period:.0f} clk = {period / 1965:.2f} us")
 prev = 0.0
-for k, n in enumerate(names):
+for k in sorted(names):
     v = (tr[:, k] - tr[:, 0]).mean().item()
-    print(f"  {n:18s} +{v / 1965:7.2f} us   (d {(v - prev) / 1965:5.2f})")
+    print(f"  {names[k]:22s} +{v / 1965:7.2f} us   (d {(v - prev) / 1965:5.2f})")
     prev = v
