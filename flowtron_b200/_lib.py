@@ -37,6 +37,22 @@ class FtArStepWeights(Structure):
     _fields_ = [(n, c_void_p) for n in AR_WEIGHT_FIELDS]
 
 
+class FtEncoderDesc(Structure):
+    _fields_ = [("B", c_int), ("L", c_int), ("C", c_int), ("n_convs", c_int), ("ksize", c_int), ("masked", c_int),
+                ("dropout_p", c_float), ("eps", c_float)]
+
+
+ENC_PARAM_FIELDS = [("conv_w", 3), ("conv_b", 3), ("norm_w", 3), ("norm_b", 3), ("w_ih", 2), ("w_hh", 2), ("b_ih", 2), ("b_hh", 2)]
+
+
+class FtEncoderWeights(Structure):
+    _fields_ = [(n, c_void_p * k) for n, k in ENC_PARAM_FIELDS]
+
+
+class FtEncoderGrads(Structure):
+    _fields_ = [("d_" + n, c_void_p * k) for n, k in ENC_PARAM_FIELDS]
+
+
 class FlowtronB200Error(RuntimeError):
     pass
 
@@ -133,6 +149,15 @@ def _declare(L):
     L.ft_radam_step_dev.restype = c_int
     L.ft_step_increment.argtypes = [c_void_p, c_void_p]
     L.ft_step_increment.restype = c_int
+    for fn in ("ft_encoder_saved_bytes", "ft_encoder_fwd_scratch_bytes", "ft_encoder_bwd_scratch_bytes"):
+        getattr(L, fn).argtypes = [POINTER(FtEncoderDesc)]
+        getattr(L, fn).restype = c_size_t
+    L.ft_encoder_fwd.argtypes = [POINTER(FtEncoderDesc), POINTER(FtEncoderWeights), c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_longlong, c_longlong, c_void_p, c_void_p, c_void_p]
+    L.ft_encoder_fwd.restype = c_int
+    L.ft_encoder_bwd.argtypes = [POINTER(FtEncoderDesc), POINTER(FtEncoderWeights), c_void_p, c_longlong, c_longlong, c_void_p,
+                                 c_void_p, POINTER(FtEncoderGrads), c_void_p, c_void_p]
+    L.ft_encoder_bwd.restype = c_int
 
 
 def check(rc: int, what: str = ""):
@@ -423,3 +448,44 @@ def radam_step_dev_raw(p_ptr, g_ptr, m_ptr, v_ptr, n, beta1, beta2, eps, weight_
 
 def step_increment(step_dev):
     check(lib().ft_step_increment(ptr(step_dev), stream_ptr()), "ft_step_increment")
+
+
+# ------------------------------------------------------------------------------------------------ text encoder
+def encoder_desc(B, L, masked, dropout_p, eps=1e-5):
+    return FtEncoderDesc(B=B, L=L, C=512, n_convs=3, ksize=5, masked=1 if masked else 0, dropout_p=float(dropout_p), eps=float(eps))
+
+
+def _enc_struct(cls, prefix, tensors):
+    """tensors: dict name -> list of tensors, in ENC_PARAM_FIELDS order."""
+    st = cls()
+    for n, k in ENC_PARAM_FIELDS:
+        arr = (c_void_p * k)(*[c_void_p(t.data_ptr()) for t in tensors[n]])
+        setattr(st, prefix + n, arr)
+    return st
+
+
+def encoder_fwd(desc, params, x, in_lens_i32, rng_state, out, out_stride_b, out_stride_l):
+    """ft_encoder_fwd.  params: dict name -> list of fp32 CUDA tensors (ENC_PARAM_FIELDS).  Returns the `saved` buffer."""
+    _need_cuda(x, out)
+    L = lib()
+    saved = torch.empty(L.ft_encoder_saved_bytes(byref(desc)), dtype=torch.uint8, device=x.device)
+    scratch = torch.empty(L.ft_encoder_fwd_scratch_bytes(byref(desc)), dtype=torch.uint8, device=x.device)
+    w = _enc_struct(FtEncoderWeights, "", params)
+    check(L.ft_encoder_fwd(byref(desc), byref(w), ptr(x), ptr(in_lens_i32), ptr(rng_state), ptr(out), out_stride_b, out_stride_l,
+                           ptr(saved), ptr(scratch), stream_ptr()), "ft_encoder_fwd")
+    return saved
+
+
+def encoder_bwd(desc, params, d_out, saved, need_dx=True):
+    """ft_encoder_bwd.  Returns (d_x [B,512,L] or None, dict of gradient tensors like `params`)."""
+    _need_cuda(d_out, saved)
+    L = lib()
+    dev = d_out.device
+    grads = {n: [torch.empty_like(t) for t in params[n]] for n, _ in ENC_PARAM_FIELDS}
+    d_x = torch.empty(desc.B, 512, desc.L, dtype=torch.float32, device=dev) if need_dx else None
+    scratch = torch.empty(L.ft_encoder_bwd_scratch_bytes(byref(desc)), dtype=torch.uint8, device=dev)
+    w = _enc_struct(FtEncoderWeights, "", params)
+    g = _enc_struct(FtEncoderGrads, "d_", grads)
+    check(L.ft_encoder_bwd(byref(desc), byref(w), ptr(d_out), d_out.stride(0), d_out.stride(1), ptr(saved), ptr(d_x), byref(g),
+                           ptr(scratch), stream_ptr()), "ft_encoder_bwd")
+    return d_x, grads

@@ -321,6 +321,73 @@ int ar_step_fwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
     FT_TRY(launch_prep_mel(mel, out_lens, n.T, n.B, n.M, d.reversed, S.mel_in16, S.mel_flow, st));
     const float* mel_flow = d.reversed ? S.mel_flow : mel;
 
+    // Attention-LSTM / attention overlap (OFF by default, FT_ATT_OVERLAP=N enables it with chunks of N steps, N % 64 == 0; measured
+    // r2 call 12 on B200, B=32, T=1000: 53.1 ms/step with N=128 against 51.1 serial -- the 64-CTA chunked recurrence with a separate
+    // projection GEMM and the chunk launches cost more than hiding 1.6 ms of attention + GEMMs per flow gains): the attention
+    // LSTM runs as a 64-CTA recurrence in chunks of 128 steps; as soon as a chunk's h is there, a second stream runs that chunk's
+    // query projection, fused attention, gate logits and lstm layer 0's input projection on the 84 free SMs, underneath the next
+    // chunk's recurrence.  Only the last chunk's share of that work stays exposed (r2: attention 0.93 ms + GEMMs 0.7 ms per flow
+    // were serial).  The 64-CTA kernel has no room for the folded 80-channel projection next to its 128 KB weight slice, so the
+    // projection is a per-chunk GEMM on a third stream, one chunk ahead.
+    static int att_chunk = -1;
+    if (att_chunk < 0) { const char* e = getenv("FT_ATT_OVERLAP"); att_chunk = e ? atoi(e) : 0; if (att_chunk % 64) att_chunk = 0; }
+    Pipe* pa = (att_chunk > 0 && F.X1 && n.B <= 32 && n.T > 2 * att_chunk) ? get_pipe(st) : nullptr;
+    bool xproj0_done = false;
+    auto attention_rows = [&](cudaStream_t s2, int t0, int t1) -> int {      // Q projection, attention, gate logits of steps [t0, t1)
+        const long long r0 = static_cast<long long>(t0) * n.B, rows = static_cast<long long>(t1 - t0) * n.B;
+        FT_TRY(gemm_fwd(s2, rows, n.A, H, S.d16 + r0 * n.D, n.D, F.w.wq, H, nullptr, nullptr, 0, S.Q + r0 * n.A, n.A, nullptr, 0));
+        AttnFwdArgs a;
+        a.T = n.T; a.B = n.B; a.L = n.L; a.A = n.A;
+        a.Q = S.Q; a.ldq = n.A; a.K = S.Kp; a.ldk = n.A; a.V = S.Vp; a.ldv = n.A; a.v = w.att_v;
+        a.in_lens = in_lens; a.out_lens = out_lens; a.prior = d.has_prior ? prior : nullptr; a.reversed = d.reversed;
+        a.temperature = d.temperature; a.attn = attn; a.logprob = logprob; a.p_save = S.p_save;
+        a.ctx16 = S.d16 + H; a.ldc = n.D; a.ctx32 = F.ctx32; a.ldc32 = n.A;
+        a.t_begin = t0; a.t_end = t1;
+        FT_TRY(launch_attn_fwd(a, s2));
+        if (d.has_gate) FT_TRY(launch_gate_fwd_f32(F.hA32 + r0 * H, H, H, F.ctx32 + r0 * n.A, n.A, n.A, w.gate_w, w.gate_b, rows, gates + r0, s2));
+        return 0;
+    };
+    auto kv_projections = [&](cudaStream_t s2) -> int {
+        // First use of `text`: if the caller produced it on another stream it handed us the event to wait for, so the encoder
+        // ran underneath everything above (ft_ar_step_set_text_ready_event).
+        if (text_ready) {
+            if (cudaStreamWaitEvent(s2, text_ready, 0) != cudaSuccess) return ft_set_error("ar_step_fwd: cudaStreamWaitEvent(text_ready) failed");
+        }
+        FT_TRY(launch_cast(text, 2, S.text16, 0, n.RL * n.E, s2));
+        FT_TRY(gemm_fwd(s2, n.RL, n.A, n.E, S.text16, n.E, F.w.wk, n.E, nullptr, nullptr, 0, S.Kp, n.A, nullptr, 0));
+        FT_TRY(gemm_fwd(s2, n.RL, n.A, n.E, S.text16, n.E, F.w.wv, n.E, nullptr, nullptr, 0, S.Vp, n.A, nullptr, 0));
+        return 0;
+    };
+    if (pa) {
+        const int CH = att_chunk;
+        auto xa = [&](cudaStream_t s2, int t0, int t1) {              // attention-LSTM input projection of steps [t0, t1) -> F.X1 rows
+            const long long r0 = static_cast<long long>(t0) * n.B, rows = static_cast<long long>(t1 - t0) * n.B;
+            return gemm_fwd(s2, rows, G, n.M, S.mel_in16 + r0 * n.M, n.M, F.w.w_ih_a, n.M, w.attn_lstm_b_ih, w.attn_lstm_b_hh, 0,
+                            F.X1 + r0 * G, G, nullptr, 0);
+        };
+        cudaEventRecord(pa->ev0, st);
+        cudaStreamWaitEvent(pa->sB, pa->ev0, 0);
+        cudaStreamWaitEvent(pa->sC, pa->ev0, 0);
+        FT_TRY(kv_projections(pa->sC));
+        FT_TRY(xa(st, 0, CH < n.T ? CH : n.T));
+        for (int t0 = 0; t0 < n.T; t0 += CH) {
+            const int t1 = t0 + CH < n.T ? t0 + CH : n.T;
+            if (t1 < n.T) {                                            // next chunk's projection, one chunk ahead, on sB
+                FT_TRY(xa(pa->sB, t1, t1 + CH < n.T ? t1 + CH : n.T));
+                cudaEventRecord(pa->evB, pa->sB);
+            }
+            FT_TRY(launch_lstm_fwd_chunk(n.T, n.B, t0, t1, F.X1, F.w.w_hh_a, out_lens, S.d16, n.D, S.gatesA, S.cA, F.flags, st, F.hA32, H));
+            cudaEventRecord(pa->evA, st);
+            if (t1 < n.T) cudaStreamWaitEvent(st, pa->evB, 0);        // the next launch on st needs its projection
+            cudaStreamWaitEvent(pa->sC, pa->evA, 0);
+            FT_TRY(attention_rows(pa->sC, t0, t1));
+            const long long r0 = static_cast<long long>(t0) * n.B, rows = static_cast<long long>(t1 - t0) * n.B;
+            FT_TRY(gemm_fwd(pa->sC, rows, G, n.D, S.d16 + r0 * n.D, n.D, F.w.w_ih0, n.D, w.lstm_b_ih0, w.lstm_b_hh0, 0, F.X + r0 * G, G, nullptr, 0));
+        }
+        cudaEventRecord(pa->evG, pa->sC);
+        cudaStreamWaitEvent(st, pa->evG, 0);
+        xproj0_done = true;
+    } else {
     // attention_lstm: the 80-channel input projection is folded into the persistent recurrence (no [R,4096] projection
     // tensor: -0.5 ms GEMM, -1 GB of HBM traffic per flow); h lands in d16[:, 0:H].  FT_LSTM_XIN=0: separate GEMM (r1 path).
     static int xin = -1;
@@ -332,27 +399,10 @@ int ar_step_fwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
         FT_TRY(gemm_fwd(st, n.R, G, n.M, S.mel_in16, n.M, F.w.w_ih_a, n.M, w.attn_lstm_b_ih, w.attn_lstm_b_hh, 0, F.X, G, nullptr, 0));
         FT_TRY(launch_lstm_fwd(n.T, n.B, F.X, F.w.w_hh_a, out_lens, S.d16, n.D, S.gatesA, S.cA, F.hA32, H, F.flags, st));
     }
-
     // attention: K/V/Q projections, fused score+softmax(+prior)+context; ctx lands in d16[:, H:H+A]
-    // First use of `text`: if the caller produced it on another stream it handed us the event to wait for, so the encoder
-    // ran underneath everything above (ft_ar_step_set_text_ready_event).
-    if (text_ready) {
-        if (cudaStreamWaitEvent(st, text_ready, 0) != cudaSuccess) return ft_set_error("ar_step_fwd: cudaStreamWaitEvent(text_ready) failed");
+    FT_TRY(kv_projections(st));
+    FT_TRY(attention_rows(st, 0, n.T));
     }
-    FT_TRY(launch_cast(text, 2, S.text16, 0, n.RL * n.E, st));
-    FT_TRY(gemm_fwd(st, n.RL, n.A, n.E, S.text16, n.E, F.w.wk, n.E, nullptr, nullptr, 0, S.Kp, n.A, nullptr, 0));
-    FT_TRY(gemm_fwd(st, n.RL, n.A, n.E, S.text16, n.E, F.w.wv, n.E, nullptr, nullptr, 0, S.Vp, n.A, nullptr, 0));
-    FT_TRY(gemm_fwd(st, n.R, n.A, H, S.d16, n.D, F.w.wq, H, nullptr, nullptr, 0, S.Q, n.A, nullptr, 0));
-    {
-        AttnFwdArgs a;
-        a.T = n.T; a.B = n.B; a.L = n.L; a.A = n.A;
-        a.Q = S.Q; a.ldq = n.A; a.K = S.Kp; a.ldk = n.A; a.V = S.Vp; a.ldv = n.A; a.v = w.att_v;
-        a.in_lens = in_lens; a.out_lens = out_lens; a.prior = d.has_prior ? prior : nullptr; a.reversed = d.reversed;
-        a.temperature = d.temperature; a.attn = attn; a.logprob = logprob; a.p_save = S.p_save;
-        a.ctx16 = S.d16 + H; a.ldc = n.D; a.ctx32 = F.ctx32; a.ldc32 = n.A;
-        FT_TRY(launch_attn_fwd(a, st));
-    }
-    if (d.has_gate) FT_TRY(launch_gate_fwd_f32(F.hA32, H, H, F.ctx32, n.A, n.A, w.gate_w, w.gate_b, n.R, gates, st));
 
     // 2-layer lstm
     Pipe* pp = (F.X1 && n.B <= 32 && n.T > pipe_chunk_steps()) ? get_pipe(st) : nullptr;
@@ -362,7 +412,7 @@ int ar_step_fwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
         const int S_ = pipe_chunk_steps();
         int* flagsA = F.flags;
         int* flagsB = F.flags + static_cast<size_t>(S_) * 16;
-        FT_TRY(gemm_fwd(st, n.R, G, n.D, S.d16, n.D, F.w.w_ih0, n.D, w.lstm_b_ih0, w.lstm_b_hh0, 0, F.X, G, nullptr, 0));
+        if (!xproj0_done) FT_TRY(gemm_fwd(st, n.R, G, n.D, S.d16, n.D, F.w.w_ih0, n.D, w.lstm_b_ih0, w.lstm_b_hh0, 0, F.X, G, nullptr, 0));
         cudaEventRecord(pp->ev0, st);
         cudaStreamWaitEvent(pp->sB, pp->ev0, 0);
         cudaStreamWaitEvent(pp->sC, pp->ev0, 0);
@@ -381,7 +431,7 @@ int ar_step_fwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
         cudaEventRecord(pp->evB, pp->sB);
         cudaStreamWaitEvent(st, pp->evB, 0);
     } else {
-        FT_TRY(gemm_fwd(st, n.R, G, n.D, S.d16, n.D, F.w.w_ih0, n.D, w.lstm_b_ih0, w.lstm_b_hh0, 0, F.X, G, nullptr, 0));
+        if (!xproj0_done) FT_TRY(gemm_fwd(st, n.R, G, n.D, S.d16, n.D, F.w.w_ih0, n.D, w.lstm_b_ih0, w.lstm_b_hh0, 0, F.X, G, nullptr, 0));
         FT_TRY(launch_lstm_fwd(n.T, n.B, F.X, F.w.w_hh0, out_lens, S.h0_16, H, S.gates0, S.c0, nullptr, 0, F.flags, st));
         FT_TRY(gemm_fwd(st, n.R, G, H, S.h0_16, H, F.w.w_ih1, H, w.lstm_b_ih1, w.lstm_b_hh1, 0, F.X, G, nullptr, 0));
         FT_TRY(launch_lstm_fwd(n.T, n.B, F.X, F.w.w_hh1, out_lens, S.h1_16, H, S.gates1, S.c1, nullptr, 0, F.flags, st));

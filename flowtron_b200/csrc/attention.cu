@@ -25,6 +25,7 @@ constexpr int SQ_LD = AT_TT + 4;     // 68: keeps float4 rows 16-byte aligned, s
 constexpr int SK_LD = AT_LB + 4;     // 132
 
 struct AttnFwdParams {
+    int t_begin, t_end;                  // query rows [t_begin, t_end) of this launch (t_begin a multiple of the tile height)
     int T, B, L, A;
     const float* Q; long long ldq;       // [T*B, A] row = t*B + b
     const float* K; long long ldk;       // [L*B, A] row = l*B + b
@@ -90,10 +91,10 @@ attn_fwd_kernel(AttnFwdParams p) {
     const int SE_LD = Lr + 4;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.y, t0 = blockIdx.x * AT_TT;
+    const int b = blockIdx.y, t0 = p.t_begin + blockIdx.x * AT_TT;
     const int out_len = p.out_lens ? p.out_lens[b] : p.T;
     const int in_len = p.in_lens ? p.in_lens[b] : p.L;
-    const int nrows = min(AT_TT, p.T - t0);
+    const int nrows = min(AT_TT, p.t_end - t0);
 
     if (t0 >= out_len) {      // tile entirely in the padded region: values there are outside the contract; keep them finite
         const float lp0 = logf(1e-8f);
@@ -610,8 +611,10 @@ int launch_attn_fwd(const AttnFwdArgs& a, cudaStream_t st) {
     p.ctx16 = static_cast<__half*>(a.ctx16); p.ldc = a.ldc; p.ctx32 = a.ctx32; p.ldc32 = a.ldc32;
     const size_t smem = attn_fwd_smem(a.L, a.A);
     cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    dim3 grid((a.T + AT_TT - 1) / AT_TT, a.B);
-    TimeScope ts("attn_fwd", a.T, a.B, a.L, st);
+    p.t_begin = a.t_begin; p.t_end = a.t_end > 0 ? a.t_end : a.T;
+    if (p.t_begin % AT_TT || p.t_begin < 0 || p.t_end > a.T || p.t_end <= p.t_begin) return ft_set_error("attention: bad query range");
+    dim3 grid((p.t_end - p.t_begin + AT_TT - 1) / AT_TT, a.B);
+    TimeScope ts("attn_fwd", p.t_end - p.t_begin, a.B, a.L, st);
     attn_fwd_kernel<<<grid, AT_THREADS, smem, st>>>(p);
     ft_count_launch(1);
     return ft_check_launch("attn_fwd_kernel");

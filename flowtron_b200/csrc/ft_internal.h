@@ -47,7 +47,8 @@ int launch_lstm_fwd_xin(int T, int B, const void* x16, long long ldx, int kx, co
                         const void* whh16, const int* lens, void* hseq16, long long ldh, void* gates16, float* cstate, float* h32,
                         long long ldh32, int* flags, cudaStream_t st);    // input projection folded into the recurrence (kx <= 128)
 int launch_lstm_fwd_chunk(int T, int B, int t0, int t1, const float* xproj, const void* whh16, const int* lens, void* hseq16,
-                          long long ldh, void* gates16, float* cstate, int* flags, cudaStream_t st);   // experimental
+                          long long ldh, void* gates16, float* cstate, int* flags, cudaStream_t st, float* h32 = nullptr,
+                          long long ldh32 = 0);
 int launch_lstm_bwd_chunk(int T, int B, int t0, int t1, const float* dh_ext, long long ldd, const void* whhT16, const void* gates16,
                           const float* cstate, const int* lens, void* dG16, float* dc_carry, int* flags, cudaStream_t st);   // experimental
 int launch_lstm_bwd(int T, int B, const float* dh_ext, long long ldd, const void* whhT16, const void* gates16,
@@ -82,6 +83,7 @@ struct AttnFwdArgs {
     const float* Q; long long ldq; const float* K; long long ldk; const float* V; long long ldv; const float* v;
     const int* in_lens; const int* out_lens; const float* prior; int reversed; float temperature;
     float* attn; float* logprob; float* p_save; void* ctx16; long long ldc; float* ctx32; long long ldc32;
+    int t_begin = 0, t_end = 0;          // query rows of this launch (t_end == 0: all T; t_begin a multiple of 64)
 };
 struct AttnBwdArgs {
     int T, B, L, A;

@@ -62,9 +62,10 @@ struct InferParams {
     float *cA, *c0, *c1;
     // (slot-0 pointers; slot k of every ring lies k * slot_bytes further: no dynamically indexed arrays in the parameter struct,
     //  which would move it to local memory)
-    long long slot_bytes;
+    long long slot_bytes, rep_bytes;       // the tensors every CTA reads exist in NREP replicas (rep_bytes apart): see the header
     float *hA, *q, *e;                     // fp32: attention-LSTM output (gate), query, scores
-    __half *hA16, *h016, *h116, *d16, *y116, *y216, *x16;   // fp16 [B][K]: what the next phases consume
+    __half *hA16, *h016, *h116, *ctx16, *y116, *y216, *x16;   // fp16 [B][K]: what the next phases consume
+    float* ctx32;                          // fp32 context (gate)
     uint32_t* alive;                       // [B] per slot: 1 while the sample keeps generating after this frame, 0 once stopped
     int* status;
     long long* trace;                      // debug: [T][32] clock64 stamps of CTA 0 (tools/trace_infer.py), or null
@@ -74,6 +75,8 @@ static long long* g_infer_trace = nullptr;
 #define IT_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[i * 32 + (slot)] = clock64(); } while (0)
 
 constexpr uint32_t SENT = 0xFFFFFFFFu;
+constexpr int NREP = 1;                        // replicas of the all-to-all exchanged tensors (CTA c reads replica c % NREP); r2 call 11: 8 replicas
+                                               // (to spread the 128-CTA reads of the same lines over more L2 slices) were SLOWER: 26.6 -> 29.9 us/frame
 #define SL(ptr, k) (reinterpret_cast<decltype(ptr)>(reinterpret_cast<char*>(ptr) + (k)))     /* ring slot: k = slot index * slot_bytes */
 __device__ __forceinline__ uint4 ld_rlx_v4(const void* p) {
     uint4 v;
@@ -118,37 +121,47 @@ __device__ __forceinline__ float poll_f32(const float* g, int* status, int code)
     return __uint_as_float(v);
 }
 
-// activations of a phase: up to two fp16 ring-slot tensors [B, pitch] (written by the producing phases' epilogues on other SMs)
-// -> shared [16][KP] at columns cA / cB.  Round = every still-pending 16-byte packet of this thread is fetched with cp.async.cg
-// (L2, no registers, all in flight at once), then checked in shared memory; packets that still hold a sentinel element are
-// fetched again next round.  Batch rows >= B stay zero.  K, pitch and column offsets are multiples of 8.  Callers finish with
-// __syncthreads().
-__device__ __forceinline__ void stage2(__half* sx, int cA, const __half* srcA, int KA, int pitchA, int cB, const __half* srcB, int KB, int pitchB,
-                                       int B, int* status) {
-    const int k8A = KA >> 3, k8B = KB >> 3, totA = B * k8A, total = totA + B * k8B;
+// Inputs of a phase: up to three ring-slot tensors [B, pitch] (written by the producing phases' epilogues on other SMs) -> shared
+// memory rows of KP halfs at element columns cA / cB / cC (kF32: fp32 elements, rows of KP / 2 floats).  Round = every pending
+// 16-byte packet of this thread is fetched with cp.async.cg (L2, no registers, all in flight at once), then checked in shared
+// memory; packets that still hold a sentinel element are fetched again next round.  While a thread's FIRST packet is not valid
+// it is the only one fetched (a failed round of everything moves B x K x 2 bytes per CTA for nothing: 11 MB over the grid at
+// B = 16); the 512 first packets of a CTA sample all producers.  Batch rows >= B stay zero.  K, pitch, columns: multiples of
+// the 16-byte packet.  Callers finish with __syncthreads().
+// B <= 8 variant: a thread has at most ~3 packets, so plain index arithmetic is cheapest (the shift / mask set-up of the variant
+// below costs more than it saves: 26.6 vs 31.2 us per frame at B = 1, r2 calls 10 / 12).
+template <bool kF32>
+__device__ __forceinline__ void stage3_small(__half* sx, int cA, const void* srcA, int KA, int pitchA, int cB, const void* srcB, int KB, int pitchB,
+                                             int cC, const void* srcC, int KC, int pitchC, int B, int* status) {
+    constexpr int EPP = kF32 ? 4 : 8, EB = kF32 ? 4 : 2;          // elements per packet, bytes per element
+    const int k8A = KA / EPP, k8B = KB / EPP, k8C = KC / EPP, totA = B * k8A, totB = totA + B * k8B, total = totB + B * k8C;
     uint32_t pend = 0;                                            // bit u: packet threadIdx.x + u * INF_THREADS not valid yet
     for (int u = 0, idx = threadIdx.x; idx < total; ++u, idx += INF_THREADS) pend |= 1u << u;
     long long t0 = 0;
     while (pend) {
-        for (int u = 0, idx = threadIdx.x; idx < total; ++u, idx += INF_THREADS) {
-            if (pend >> u & 1u) {
-                const bool inA = idx < totA;
-                const int j = inA ? idx : idx - totA, k8 = inA ? k8A : k8B;
-                const int b = j / k8, i8 = j - b * k8;
-                const __half* g = (inA ? srcA + static_cast<long long>(b) * pitchA : srcB + static_cast<long long>(b) * pitchB) + 8 * i8;
-                const uint32_t dst = smem_u32(sx + b * KP + (inA ? cA : cB) + 8 * i8);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g) : "memory");
+        const uint32_t want = (pend & 1u) ? 1u : pend;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int u = 0, idx = threadIdx.x; idx < total; ++u, idx += INF_THREADS) {
+                if (want >> u & 1u) {
+                    const int q = idx < totA ? 0 : (idx < totB ? 1 : 2);
+                    const int j = idx - (q == 0 ? 0 : (q == 1 ? totA : totB)), k8 = q == 0 ? k8A : (q == 1 ? k8B : k8C);
+                    const int b = j / k8, i8 = j - b * k8;
+                    uint8_t* dst = reinterpret_cast<uint8_t*>(sx) + b * (KP * 2) + (q == 0 ? cA : (q == 1 ? cB : cC)) * EB + 16 * i8;
+                    if (pass == 0) {
+                        const uint8_t* g = static_cast<const uint8_t*>(q == 0 ? srcA : (q == 1 ? srcB : srcC)) +
+                                           static_cast<long long>(b) * (q == 0 ? pitchA : (q == 1 ? pitchB : pitchC)) * EB + 16 * i8;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(g) : "memory");
+                    } else {
+                        const uint4 v = *reinterpret_cast<const uint4*>(dst);
+                        const bool bad = kF32 ? (v.x == SENT || v.y == SENT || v.z == SENT || v.w == SENT) : sent16(v);
+                        if (!bad) pend &= ~(1u << u);
+                    }
+                }
             }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        for (int u = 0, idx = threadIdx.x; idx < total; ++u, idx += INF_THREADS) {
-            if (pend >> u & 1u) {
-                const bool inA = idx < totA;
-                const int j = inA ? idx : idx - totA, k8 = inA ? k8A : k8B;
-                const int b = j / k8, i8 = j - b * k8;
-                const uint4 v = *reinterpret_cast<const uint4*>(sx + b * KP + (inA ? cA : cB) + 8 * i8);
-                if (!sent16(v)) pend &= ~(1u << u);
+            if (pass == 0) {
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
         }
         if (pend) {
@@ -156,6 +169,77 @@ __device__ __forceinline__ void stage2(__half* sx, int cA, const __half* srcA, i
             else if (clock64() - t0 > FT_WATCHDOG_CYCLES) watchdog_fail(status, 302);
         }
     }
+}
+
+template <bool kF32>
+__device__ __forceinline__ void stage3_big(__half* sx, int cA, const void* srcA, int KA, int pitchA, int cB, const void* srcB, int KB, int pitchB,
+                                           int cC, const void* srcC, int KC, int pitchC, int B, int* status) {
+    constexpr int EPP = kF32 ? 4 : 8, EB = kF32 ? 4 : 2;          // elements per packet, bytes per element
+    // thread -> (packet column i8 = tid & (kp - 1), row group tid / kp) per source, kp = packets per row rounded up to a power of
+    // two (shift / mask arithmetic only: with divisions a round of the B = 16 loops cost 2.6 us of instruction issue); a source
+    // needs `it` = ceil(B / (512 / kp)) iterations, pending bit = 4 * source + iteration (B <= 16, kp <= 512: it <= 4 when kp <= 128;
+    // wider rows use up to 8 bits, sources are then limited to what fits in 32 bits)
+    const void* src[3] = {srcA, srcB, srcC};
+    const int col[3] = {cA, cB, cC}, pitch[3] = {pitchA, pitchB, pitchC};
+    int k8[3] = {KA / EPP, KB / EPP, KC / EPP}, sh[3], nit[3], bit0[3];
+    uint32_t pend = 0;
+    int nb = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        int kp = 1, s2 = 0;
+        while (kp < k8[q]) { kp <<= 1; ++s2; }
+        sh[q] = s2;
+        const int rows_per = INF_THREADS >> s2;                   // rows covered per iteration
+        nit[q] = k8[q] ? (B + rows_per - 1) / rows_per : 0;
+        bit0[q] = nb;
+        for (int it = 0; it < nit[q]; ++it) {
+            const int b = (threadIdx.x >> s2) + it * rows_per, i8 = threadIdx.x & (kp - 1);
+            if (b < B && i8 < k8[q]) pend |= 1u << (nb + it);
+        }
+        nb += nit[q];
+    }
+    long long t0 = 0;
+    const uint32_t canary = pend & (0u - pend);                   // the thread's first packet: fetched alone until it is valid
+    while (pend) {
+        const uint32_t want = (pend & canary) ? canary : pend;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int rows_per = INF_THREADS >> sh[q], i8 = threadIdx.x & ((1 << sh[q]) - 1);
+                for (int it = 0; it < nit[q]; ++it) {
+                    const uint32_t bit = 1u << (bit0[q] + it);
+                    if (want & bit) {
+                        const int b = (threadIdx.x >> sh[q]) + it * rows_per;
+                        uint8_t* dst = reinterpret_cast<uint8_t*>(sx) + b * (KP * 2) + col[q] * EB + 16 * i8;
+                        if (pass == 0) {
+                            const uint8_t* g = static_cast<const uint8_t*>(src[q]) + static_cast<long long>(b) * pitch[q] * EB + 16 * i8;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(g) : "memory");
+                        } else {
+                            const uint4 v = *reinterpret_cast<const uint4*>(dst);
+                            const bool bad = kF32 ? (v.x == SENT || v.y == SENT || v.z == SENT || v.w == SENT) : sent16(v);
+                            if (!bad) pend &= ~bit;
+                        }
+                    }
+                }
+            }
+            if (pass == 0) {
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+        }
+        if (pend) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > FT_WATCHDOG_CYCLES) watchdog_fail(status, 302);
+        }
+    }
+}
+
+template <bool kF32, bool kBig>
+__device__ __forceinline__ void stage3(__half* sx, int cA, const void* srcA, int KA, int pitchA, int cB, const void* srcB, int KB, int pitchB,
+                                       int cC, const void* srcC, int KC, int pitchC, int B, int* status) {
+    if (kBig) stage3_big<kF32>(sx, cA, srcA, KA, pitchA, cB, srcB, KB, pitchB, cC, srcC, KC, pitchC, B, status);
+    else stage3_small<kF32>(sx, cA, srcA, KA, pitchA, cB, srcB, KB, pitchB, cC, srcC, KC, pitchC, B, status);
 }
 
 __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -251,7 +335,7 @@ __device__ __forceinline__ void mv_phase(const __half* __restrict__ W, int n_tas
                 }
             }
         }
-        if (task < n_tasks && split == 0) epi(task, d);
+        if (task < n_tasks && split == 0) epi(task, d, first);
         if (S > 1) __syncthreads();
         first = false;
     }
@@ -259,10 +343,11 @@ __device__ __forceinline__ void mv_phase(const __half* __restrict__ W, int n_tas
 
 // LSTM cell for task = 2 units x 4 gates (rows i0,f0,g0,o0,i1,f1,g1,o1): lane j holds (i,f) [j even] or (g,o) [j odd] of unit j/2.
 // h goes to ring slot `h16` (and `hnew`, fp32, when given); the same elements of the next slot are reset to the sentinel.
+// cpre / bpre: the lane's cell states and biases, loaded before the phase waited for its inputs (first pass only).
 __device__ __forceinline__ void lstm_epi(const InferParams& p, int task, float (&d)[4], const float* bias, float* c, float* hnew, float* hnew_next,
-                                         __half* h16, __half* h16_next) {
+                                         __half* h16, __half* h16_next, bool first, const float (&cpre)[2], const float (&bpre)[2]) {
     const int lane = threadIdx.x & 31, j = lane & 3, r = lane >> 2;
-    const float b0 = bias[task * 8 + 2 * j], b1 = bias[task * 8 + 2 * j + 1];
+    const float b0 = first ? bpre[0] : bias[task * 8 + 2 * j], b1 = first ? bpre[1] : bias[task * 8 + 2 * j + 1];
     float v[4] = {d[0] + b0, d[1] + b1, d[2] + b0, d[3] + b1};
     float o[4];
 #pragma unroll
@@ -275,27 +360,46 @@ __device__ __forceinline__ void lstm_epi(const InferParams& p, int task, float (
             if (b < p.B) {
                 const float gi = sigmoid_f(v[2 * half]), gf = sigmoid_f(v[2 * half + 1]);
                 const float gg = tanh_f(o[2 * half]), go = sigmoid_f(o[2 * half + 1]);
-                const float cn = gf * c[b * IH + u] + gi * gg;
-                c[b * IH + u] = cn;
+                const float cn = gf * (first ? cpre[half] : c[b * IH + u]) + gi * gg;
                 const float h = go * tanh_f(cn);
-                st_rlx_h(h16 + b * IH + u, h);
-                st_rlx_u16(h16_next + b * IH + u, 0xFFFFu);
+#pragma unroll
+                for (int rr = 0; rr < NREP; ++rr) {
+                    st_rlx_h(SL(h16, rr * p.rep_bytes) + b * IH + u, h);
+                    st_rlx_u16(SL(h16_next, rr * p.rep_bytes) + b * IH + u, 0xFFFFu);
+                }
                 if (hnew) { st_rlx_f32(hnew + b * IH + u, h); st_rlx_u32(hnew_next + b * IH + u, SENT); }
+                c[b * IH + u] = cn;
             }
         }
     }
 }
+// the loads lstm_epi wants early: this lane's biases and cell states for the first task of its warp (S = 4: 4 tasks per CTA)
+__device__ __forceinline__ void lstm_pre(const InferParams& p, const float* bias, const float* c, float (&cpre)[2], float (&bpre)[2]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, j = lane & 3, r = lane >> 2;
+    const int task = blockIdx.x * 4 + (warp >> 2);
+    cpre[0] = cpre[1] = bpre[0] = bpre[1] = 0.f;
+    if ((warp & 3) == 0 && task < IH / 2) {
+        bpre[0] = bias[task * 8 + 2 * j]; bpre[1] = bias[task * 8 + 2 * j + 1];
+        if ((j & 1) == 0) {
+            const int u = 2 * task + (j >> 1);
+            if (r < p.B) cpre[0] = c[r * IH + u];
+            if (r + 8 < p.B) cpre[1] = c[(r + 8) * IH + u];
+        }
+    }
+}
 
-// Utterance b inside CTA b: softmax (+ prior posterior) or the forced alignment, context, d = [hA ; ctx], gate decision.
-// (Must stay inlined: taking the address of the kernel's parameter struct for a real call moves it to local memory and
-//  turns every p.field access of the frame loop into a local load -- measured: 40 -> 57 us per frame.)
-__device__ __forceinline__ void attend_one(const InferParams& p, float* sf, int i, long long cur, long long nxt, bool forced, bool was_alive) {
+// Context of utterance b, channels [CW s, CW s + CW) (CW = 64 or 128), inside one CTA: warp 0 turns the scores into attention weights (softmax,
+// prior posterior -- or the forced alignment), all 16 warps then take L/16 keys each (every V load of the CTA in flight at
+// once), partial sums meet in shared memory.  Writes ctx (fp16 for lstm layer 0, fp32 for the gate) and, from slice 0, the
+// attention weights.  (r2 call 8: one CTA per utterance doing all 640 channels pulled 256 KB through one SM: 7.4 us.)
+template <int CW>
+__device__ __forceinline__ void context_item(const InferParams& p, float* sf, int i, int b, int s, long long cur, long long nxt, bool forced) {
+    constexpr int NV = CW / 32;                                    // channels per lane
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.x;
-    float* se = sf; float* sd = sf + LMAX; float* sp = sd + p.D;          // e / attn [LMAX], d [D], context partials [4][A]
-    if (!forced) {
-        if (warp == 0) {                         // softmax over L in registers: lane holds l = lane + 32 jj
-            float w[8];
+    float* se = sf; float* sp = sf + LMAX;                         // attn [LMAX], partials [16 warps][CW]
+    if (warp == 0) {
+        float w[8];
+        if (!forced) {                                            // softmax over L in registers: lane holds l = lane + 32 jj
             float mx = -INFINITY;
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
@@ -306,12 +410,12 @@ __device__ __forceinline__ void attend_one(const InferParams& p, float* sf, int 
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            float s = 0.f;
+            float sum = 0.f;
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) { w[jj] = (lane + 32 * jj < p.L) ? expf(w[jj] - mx) : 0.f; s += w[jj]; }
+            for (int jj = 0; jj < 8; ++jj) { w[jj] = (lane + 32 * jj < p.L) ? expf(w[jj] - mx) : 0.f; sum += w[jj]; }
 #pragma unroll
-            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            const float inv = 1.f / s;
+            for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float inv = 1.f / sum;
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) w[jj] *= inv;
             if (p.prior) {
@@ -336,67 +440,58 @@ __device__ __forceinline__ void attend_one(const InferParams& p, float* sf, int 
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) w[jj] *= inv2;
             }
+        } else {
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) { const int l = lane + 32 * jj; if (l < p.L) se[l] = w[jj]; }
+            for (int jj = 0; jj < 8; ++jj) { const int l = lane + 32 * jj; w[jj] = l < p.L ? p.attn_forced[(static_cast<long long>(i) * p.B + b) * p.L + l] : 0.f; }
         }
-    } else {
-        for (int l = threadIdx.x; l < p.L; l += INF_THREADS) se[l] = p.attn_forced[(static_cast<long long>(i) * p.B + b) * p.L + l];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int l = lane + 32 * jj;
+            if (l < p.L) { se[l] = w[jj]; if (s == 0) p.attn_out[(static_cast<long long>(i) * p.B + b) * p.L + l] = w[jj]; }
+        }
     }
-    // fp32 attention-LSTM output of this frame (exchanged: written by the P1 epilogues of other CTAs).  Warp 0 is busy with
-    // the softmax above, the other warps wait here.
-    for (int k = threadIdx.x; k < IH; k += INF_THREADS) sd[k] = poll_f32(SL(p.hA, cur) + b * IH + k, p.status, 304);
     __syncthreads();
-    for (int l = threadIdx.x; l < p.L; l += INF_THREADS) p.attn_out[(static_cast<long long>(i) * p.B + b) * p.L + l] = se[l];
-    const int a4n = p.A >> 2, ngrp = INF_THREADS / a4n < 4 ? INF_THREADS / a4n : 4;       // A = 640: 3 groups of 160 threads
-    {   // context: `ngrp` groups of keys x (A/4) groups of 4 channels, 16-byte loads of V, partial sums meet in shared memory
-        const int lg = threadIdx.x / a4n, a4 = threadIdx.x - lg * a4n;
-        if (lg < ngrp) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            constexpr int CU = 6;                                     // independent 16-byte loads in flight per thread
-            for (int l0 = lg; l0 < p.L; l0 += CU * ngrp) {
-                float4 v[CU];
+    {   // warp w: keys w, w + 16, ...; lane: channels CW s + NV lane .. + NV - 1
+        float acc[NV];
 #pragma unroll
-                for (int u = 0; u < CU; ++u) {
-                    const int l = l0 + u * ngrp;
-                    v[u] = l < p.L ? *reinterpret_cast<const float4*>(p.Vp + (static_cast<long long>(l) * p.B + b) * p.A + 4 * a4)
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+        for (int e = 0; e < NV; ++e) acc[e] = 0.f;
+        constexpr int CU = 8;
+        for (int l0 = warp; l0 < p.L; l0 += CU * INF_WARPS) {
+            float v[CU][NV];
 #pragma unroll
-                for (int u = 0; u < CU; ++u) {
-                    const int l = l0 + u * ngrp;
-                    const float w = l < p.L ? se[l] : 0.f;
-                    acc.x = fmaf(w, v[u].x, acc.x); acc.y = fmaf(w, v[u].y, acc.y); acc.z = fmaf(w, v[u].z, acc.z); acc.w = fmaf(w, v[u].w, acc.w);
+            for (int u = 0; u < CU; ++u) {
+                const int l = l0 + u * INF_WARPS;
+                const float* vr = p.Vp + (static_cast<long long>(l) * p.B + b) * p.A + CW * s + NV * lane;
+                if (l < p.L) {
+                    if (NV == 2) { const float2 t = *reinterpret_cast<const float2*>(vr); v[u][0] = t.x; v[u][1] = t.y; }
+                    else { const float4 t = *reinterpret_cast<const float4*>(vr); v[u][0] = t.x; v[u][1] = t.y; v[u][NV - 2] = t.z; v[u][NV - 1] = t.w; }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < NV; ++e) v[u][e] = 0.f;
                 }
             }
-            *reinterpret_cast<float4*>(sp + lg * p.A + 4 * a4) = acc;
-        }
-    }
-    __syncthreads();
-    for (int a = threadIdx.x; a < p.A; a += INF_THREADS) {
-        float c = 0.f;
-        for (int g2 = 0; g2 < ngrp; ++g2) c += sp[g2 * p.A + a];
-        sd[IH + a] = c;
-    }
-    __syncthreads();
-    for (int k = 2 * threadIdx.x; k < p.D; k += 2 * INF_THREADS) {       // d = [hA ; ctx] (fp16) for lstm layer 0 (D even)
-        st_rlx_h2(SL(p.d16, cur) + b * p.D + k, sd[k], sd[k + 1]);
-        st_rlx_u32(SL(p.d16, nxt) + b * p.D + k, SENT);
-    }
-    if (warp == 0) {                             // gate decision for this frame (the frame that trips the gate IS emitted, :823-826)
-        bool alive = was_alive;
-        if (p.has_gate) {
-            float s = 0.f;
-            for (int k = lane; k < p.D; k += 32) s = fmaf(p.wg[k], sd[k], s);
 #pragma unroll
-            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (was_alive && sigmoid_f(s + p.bg[0]) > p.gate_threshold) alive = false;
+            for (int u = 0; u < CU; ++u) {
+                const int l = l0 + u * INF_WARPS;
+                const float w = l < p.L ? se[l] : 0.f;
+#pragma unroll
+                for (int e = 0; e < NV; ++e) acc[e] = fmaf(w, v[u][e], acc[e]);
+            }
         }
-        if (lane == 0) {
-            if (was_alive) p.n_frames[b] = i + 1;
-            st_rlx_u32(SL(p.alive, cur) + b, alive ? 1u : 0u);
-            st_rlx_u32(SL(p.alive, nxt) + b, SENT);
-        }
+#pragma unroll
+        for (int e = 0; e < NV; ++e) sp[warp * CW + NV * lane + e] = acc[e];
     }
+    __syncthreads();
+    if (threadIdx.x < CW) {
+        float c = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < INF_WARPS; ++w2) c += sp[w2 * CW + threadIdx.x];
+        const int o = b * p.A + CW * s + threadIdx.x;
+#pragma unroll
+        for (int rr = 0; rr < NREP; ++rr) { st_rlx_h(SL(p.ctx16, cur + rr * p.rep_bytes) + o, c); st_rlx_u16(SL(p.ctx16, nxt + rr * p.rep_bytes) + o, 0xFFFFu); }
+        st_rlx_f32(SL(p.ctx32, cur) + o, c); st_rlx_u32(SL(p.ctx32, nxt) + o, SENT);
+    }
+    __syncthreads();
 }
 
 template <bool kB16>
@@ -405,7 +500,7 @@ infer_kernel(InferParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __half* sx = reinterpret_cast<__half*>(smem_raw);                          // [16][KP] fp16 activations of the phase
     float* spart = reinterpret_cast<float*>(sx + 16 * KP);                     // [16 warps][32 lanes][4] partial accumulators
-    float* sf = spart + INF_WARPS * 128;                                       // attention scratch: e[LMAX] d[D] partials[4][A]
+    float* sf = spart + INF_WARPS * 128;                                       // attention scratch: attn[LMAX], partials[16][128]
     __shared__ int s_alive[16], s_nfr[16];                                     // every CTA tracks every sample's gate state
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 16 * KP; i += INF_THREADS) sx[i] = __float2half_rn(0.f);     // batch rows >= B: zero forever
@@ -419,149 +514,203 @@ infer_kernel(InferParams p) {
     const bool act_lstm = static_cast<int>(blockIdx.x) * 4 < IH / 2, act_q = static_cast<int>(blockIdx.x) < p.A / 8;
     const bool act_dense = static_cast<int>(blockIdx.x) < IH / 8, act_conv = static_cast<int>(blockIdx.x) < p.M / 4;
     const bool forced = p.attn_forced != nullptr;    // `attn` given (flowtron.py:585-588): no query / score / softmax / prior
+    // context work items: (utterance, channel slice); 64-channel slices unless that needs a second pass over the grid
+    const bool wide_ctx = (p.A % 128 == 0) && p.B * (p.A / 64) > static_cast<int>(gridDim.x);
     Prefetch pf;
     mv_prefetch(pf, p.wA, IH / 2, nmA, 4);
     for (int i = 0; i < p.T; ++i) {
         const long long cur = (i % 3) * p.slot_bytes, prv = ((i + 2) % 3) * p.slot_bytes, nxt = ((i + 1) % 3) * p.slot_bytes;
-        // all samples stopped?  (s_alive: the flags every CTA read in the previous frame's P4 -- identical everywhere)
+        // all samples stopped?  (s_alive: the flags every CTA read before the previous frame's last phase -- identical everywhere)
         bool any = false;
         for (int b = 0; b < p.B; ++b) any |= (s_alive[b] != 0);
         if (!any) break;
         __threadfence();                         // one gpu-scope fence per thread per frame: see the header (slot reuse)
+        float cpre[2], bpre[2];
+        const long long cur_r = cur + (blockIdx.x % NREP) * p.rep_bytes, prv_r = prv + (blockIdx.x % NREP) * p.rep_bytes;   // this CTA's replica
 
         // ---- P1 attention_lstm step on the previous output frame (zeros at i == 0): x = [out_{i-1} (80 -> 96) ; hA_{i-1}]
         IT_TRACE(0);
+        lstm_pre(p, p.bA, p.cA, cpre, bpre);
         if (act_lstm) {
             if (threadIdx.x < 16 * 2) *reinterpret_cast<uint4*>(sx + (threadIdx.x >> 1) * KP + p.M + 8 * (threadIdx.x & 1)) = make_uint4(0u, 0u, 0u, 0u);
-            stage2(sx, 0, SL(p.x16, prv), p.M, XPAD, XPAD, SL(p.hA16, prv), IH, IH, p.B, p.status);
+            stage3<false, kB16>(sx, 0, SL(p.x16, prv_r), p.M, XPAD, XPAD, SL(p.hA16, prv_r), IH, IH, 0, nullptr, 0, 0, p.B, p.status);
         }
         __syncthreads();
         IT_TRACE(1);
-        mv_phase<kB16>(p.wA, IH / 2, nmA, 4, spart, sx, pf, [&](int task, float (&d)[4]) {
-            lstm_epi(p, task, d, p.bA, p.cA, SL(p.hA, cur), SL(p.hA, nxt), SL(p.hA16, cur), SL(p.hA16, nxt));
+        mv_phase<kB16>(p.wA, IH / 2, nmA, 4, spart, sx, pf, [&](int task, float (&d)[4], bool first) {
+            lstm_epi(p, task, d, p.bA, p.cA, SL(p.hA, cur), SL(p.hA, nxt), SL(p.hA16, cur), SL(p.hA16, nxt), first, cpre, bpre);
         });
         if (forced) mv_prefetch(pf, p.w0, IH / 2, nm0, 4); else mv_prefetch(pf, p.wq, p.A / 8, nmd, INF_WARPS);
         IT_TRACE(2);
 
         if (!forced) {
             // ---- P2 query projection (no bias)
-            if (act_q) stage2(sx, 0, SL(p.hA16, cur), IH, IH, 0, nullptr, 0, 0, p.B, p.status);
+            if (act_q) stage3<false, kB16>(sx, 0, SL(p.hA16, cur_r), IH, IH, 0, nullptr, 0, 0, 0, nullptr, 0, 0, p.B, p.status);
             __syncthreads();
             IT_TRACE(4);
-            mv_phase<kB16>(p.wq, p.A / 8, nmd, INF_WARPS, spart, sx, pf, [&](int task, float (&d)[4]) {
+            mv_phase<kB16>(p.wq, p.A / 8, nmd, INF_WARPS, spart, sx, pf, [&](int task, float (&d)[4], bool) {
                 const int j = lane & 3, r = lane >> 2;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int b = r + 8 * half;
                     if (b < p.B && (half == 0 || kB16)) {
                         const int o = b * p.A + 8 * task + 2 * j;
-                        st_rlx_f32(SL(p.q, cur) + o, d[2 * half]); st_rlx_f32(SL(p.q, cur) + o + 1, d[2 * half + 1]);
-                        st_rlx_u32(SL(p.q, nxt) + o, SENT); st_rlx_u32(SL(p.q, nxt) + o + 1, SENT);
-                    }
-                }
-            });
-            mv_prefetch(pf, p.w0, IH / 2, nm0, 4);       // lstm layer 0's weights ride through the two attention phases
-            IT_TRACE(5);
-            // ---- P3a scores e[b,l] = v . tanh(q[b] + K[l,b]) / temperature over ALL warps of the grid (no key mask in
-            //      inference, flowtron.py:800-803); every warp polls the query row it needs
-            for (int t = gw; t < p.B * p.L; t += nw) {
-                const int b = t / p.L, l = t - b * p.L;
-                const float* kr = p.Kp + (static_cast<long long>(l) * p.B + b) * p.A;
-                const float* qr = SL(p.q, cur) + b * p.A;
-                float s = 0.f;
-                for (int a0 = 0; a0 < p.A; a0 += 128) {                      // 4 independent loads per operand in flight
-                    float kv[4]; uint32_t qv[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) { const int a = a0 + 32 * u + lane; kv[u] = a < p.A ? kr[a] : 0.f; qv[u] = a < p.A ? ld_rlx_u32(qr + a) : 0u; }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int a = a0 + 32 * u + lane;
-                        if (a < p.A) {
-                            const float qf = qv[u] == SENT ? poll_f32(qr + a, p.status, 305) : __uint_as_float(qv[u]);
-                            s = fmaf(p.v[a], tanh_f(qf + kv[u]), s);
+                        for (int rr = 0; rr < NREP; ++rr) {
+                            const long long ro = rr * p.rep_bytes;
+                            st_rlx_f32(SL(p.q, cur + ro) + o, d[2 * half]); st_rlx_f32(SL(p.q, cur + ro) + o + 1, d[2 * half + 1]);
+                            st_rlx_u32(SL(p.q, nxt + ro) + o, SENT); st_rlx_u32(SL(p.q, nxt + ro) + o + 1, SENT);
                         }
                     }
                 }
+            });
+            mv_prefetch(pf, p.w0, IH / 2, nm0, 4);       // lstm layer 0's weights ride through the attention phases
+            IT_TRACE(5);
+            // ---- P3a scores e[b,l] = v . tanh(q[b] + K[l,b]) / temperature over ALL warps of the grid (no key mask in
+            //      inference, flowtron.py:800-803); the query rows are staged in shared memory first (fp32, rows of KP/2 floats)
+            if (static_cast<int>(blockIdx.x) * INF_WARPS < p.B * p.L)
+                stage3<true, kB16>(sx, 0, SL(p.q, cur_r), p.A, p.A, 0, nullptr, 0, 0, 0, nullptr, 0, 0, p.B, p.status);
+            __syncthreads();
+            {
+                const float* sq = reinterpret_cast<const float*>(sx);
+                for (int t = gw; t < p.B * p.L; t += nw) {
+                    const int b = t / p.L, l = t - b * p.L;
+                    const float* kr = p.Kp + (static_cast<long long>(l) * p.B + b) * p.A;
+                    const float* qr = sq + b * (KP / 2);
+                    float sc = 0.f;
+                    for (int a0 = 0; a0 < p.A; a0 += 256) {                      // 8 independent loads in flight
+                        float kv[8];
 #pragma unroll
-                for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == 0) { st_rlx_f32(SL(p.e, cur) + t, s * p.inv_temperature); st_rlx_u32(SL(p.e, nxt) + t, SENT); }
+                        for (int u = 0; u < 8; ++u) { const int a = a0 + 32 * u + lane; kv[u] = a < p.A ? kr[a] : 0.f; }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { const int a = a0 + 32 * u + lane; if (a < p.A) sc = fmaf(p.v[a], tanh_f(qr[a] + kv[u]), sc); }
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+                    if (lane == 0) { st_rlx_f32(SL(p.e, cur) + t, sc * p.inv_temperature); st_rlx_u32(SL(p.e, nxt) + t, SENT); }
+                }
             }
+            __syncthreads();                         // sx is re-staged below
             IT_TRACE(6);
         }
-        // ---- P3b utterance b inside CTA b (attend_one)
-        if (static_cast<int>(blockIdx.x) < p.B) attend_one(p, sf, i, cur, nxt, forced, s_alive[blockIdx.x] != 0);
+        // ---- P3b softmax + context, one (utterance, channel slice) item per CTA
+        if (wide_ctx) { for (int it = blockIdx.x; it < p.B * (p.A / 128); it += gridDim.x) context_item<128>(p, sf, i, it / (p.A / 128), it % (p.A / 128), cur, nxt, forced); }
+        else          { for (int it = blockIdx.x; it < p.B * (p.A / 64); it += gridDim.x) context_item<64>(p, sf, i, it / (p.A / 64), it % (p.A / 64), cur, nxt, forced); }
         IT_TRACE(7);
-        // ---- P4 lstm layer 0 on [d ; h0_{i-1}]; every CTA reads the samples' gate flags of this frame
-        if (act_lstm) {
-            stage2(sx, 0, SL(p.d16, cur), p.D, p.D, p.D, SL(p.h016, prv), IH, IH, p.B, p.status);
-        }
-        if (threadIdx.x < p.B) {
-            const float fl = poll_f32(reinterpret_cast<const float*>(SL(p.alive, cur)) + threadIdx.x, p.status, 306);
-            if (s_alive[threadIdx.x]) s_nfr[threadIdx.x] = i + 1;
-            s_alive[threadIdx.x] = __float_as_uint(fl) != 0u;
-        }
+        // ---- P4 lstm layer 0 on [hA ; ctx ; h0_{i-1}]
+        lstm_pre(p, p.b0, p.c0, cpre, bpre);
+        if (act_lstm) stage3<false, kB16>(sx, 0, SL(p.hA16, cur_r), IH, IH, IH, SL(p.ctx16, cur_r), p.A, p.A, p.D, SL(p.h016, prv_r), IH, IH, p.B, p.status);
         __syncthreads();
         IT_TRACE(9);
-        mv_phase<kB16>(p.w0, IH / 2, nm0, 4, spart, sx, pf, [&](int task, float (&d)[4]) {
-            lstm_epi(p, task, d, p.b0, p.c0, nullptr, nullptr, SL(p.h016, cur), SL(p.h016, nxt));
+        mv_phase<kB16>(p.w0, IH / 2, nm0, 4, spart, sx, pf, [&](int task, float (&d)[4], bool first) {
+            lstm_epi(p, task, d, p.b0, p.c0, nullptr, nullptr, SL(p.h016, cur), SL(p.h016, nxt), first, cpre, bpre);
         });
         mv_prefetch(pf, p.w1, IH / 2, nm1, 4);
         IT_TRACE(10);
-        // ---- P5 lstm layer 1 on [h0 ; h1_{i-1}]
-        if (act_lstm) {
-            stage2(sx, 0, SL(p.h016, cur), IH, IH, IH, SL(p.h116, prv), IH, IH, p.B, p.status);
+        if (static_cast<int>(blockIdx.x) < p.B) {
+            // gate decision of utterance b = blockIdx.x for this frame, off the critical path (consumed before the conv phase):
+            // w_g . [hA ; ctx] in fp32 (the frame that trips the gate IS emitted, flowtron.py:823-826)
+            const int b = blockIdx.x;
+            if (p.has_gate) {
+                float sg = 0.f;
+                for (int kk = threadIdx.x; kk < p.D; kk += INF_THREADS) {
+                    const float x = kk < IH ? poll_f32(SL(p.hA, cur) + b * IH + kk, p.status, 304)
+                                            : poll_f32(SL(p.ctx32, cur) + b * p.A + (kk - IH), p.status, 307);
+                    sg = fmaf(p.wg[kk], x, sg);
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) sg += __shfl_xor_sync(0xffffffffu, sg, o);
+                if (lane == 0) sf[warp] = sg;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const bool was_alive = s_alive[b] != 0;
+                bool alive = was_alive;
+                if (p.has_gate) {
+                    float tot = 0.f;
+                    for (int w2 = 0; w2 < INF_WARPS; ++w2) tot += sf[w2];
+                    if (was_alive && sigmoid_f(tot + p.bg[0]) > p.gate_threshold) alive = false;
+                }
+                if (was_alive) p.n_frames[b] = i + 1;
+                st_rlx_u32(SL(p.alive, cur) + b, alive ? 1u : 0u);
+                st_rlx_u32(SL(p.alive, nxt) + b, SENT);
+            }
+            __syncthreads();
         }
+        // ---- P5 lstm layer 1 on [h0 ; h1_{i-1}]
+        lstm_pre(p, p.b1, p.c1, cpre, bpre);
+        if (act_lstm) stage3<false, kB16>(sx, 0, SL(p.h016, cur_r), IH, IH, IH, SL(p.h116, prv_r), IH, IH, 0, nullptr, 0, 0, p.B, p.status);
         __syncthreads();
         IT_TRACE(12);
-        mv_phase<kB16>(p.w1, IH / 2, nm1, 4, spart, sx, pf, [&](int task, float (&d)[4]) {
-            lstm_epi(p, task, d, p.b1, p.c1, nullptr, nullptr, SL(p.h116, cur), SL(p.h116, nxt));
+        mv_phase<kB16>(p.w1, IH / 2, nm1, 4, spart, sx, pf, [&](int task, float (&d)[4], bool first) {
+            lstm_epi(p, task, d, p.b1, p.c1, nullptr, nullptr, SL(p.h116, cur), SL(p.h116, nxt), first, cpre, bpre);
         });
         mv_prefetch(pf, p.wd1, IH / 8, nmd, INF_WARPS);
         IT_TRACE(13);
         // ---- P6/P7 dense layers (tanh)
         auto dense = [&](const __half* W, const float* bias, const __half* x, __half* y, __half* y_next) {
-            if (act_dense) stage2(sx, 0, x, IH, IH, 0, nullptr, 0, 0, p.B, p.status);
+            const int j = lane & 3;
+            const float pb0 = act_dense ? bias[blockIdx.x * 8 + 2 * j] : 0.f, pb1 = act_dense ? bias[blockIdx.x * 8 + 2 * j + 1] : 0.f;   // S = 16: task == CTA
+            if (act_dense) stage3<false, kB16>(sx, 0, x, IH, IH, 0, nullptr, 0, 0, 0, nullptr, 0, 0, p.B, p.status);
             __syncthreads();
-            mv_phase<kB16>(W, IH / 8, nmd, INF_WARPS, spart, sx, pf, [&](int task, float (&d)[4]) {
-                const int j = lane & 3, r = lane >> 2;
-                const float b0 = bias[task * 8 + 2 * j], b1 = bias[task * 8 + 2 * j + 1];
+            mv_phase<kB16>(W, IH / 8, nmd, INF_WARPS, spart, sx, pf, [&](int task, float (&d)[4], bool first) {
+                const int r = lane >> 2;
+                const float b0 = first ? pb0 : bias[task * 8 + 2 * j], b1 = first ? pb1 : bias[task * 8 + 2 * j + 1];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int b = r + 8 * half;
                     if (b < p.B && (half == 0 || kB16)) {
                         const int o = b * IH + 8 * task + 2 * j;
-                        st_rlx_h2(y + o, tanh_f(d[2 * half] + b0), tanh_f(d[2 * half + 1] + b1));
-                        st_rlx_u32(y_next + o, SENT);
+                        const float y0 = tanh_f(d[2 * half] + b0), y1 = tanh_f(d[2 * half + 1] + b1);
+#pragma unroll
+                        for (int rr = 0; rr < NREP; ++rr) { st_rlx_h2(SL(y, rr * p.rep_bytes) + o, y0, y1); st_rlx_u32(SL(y_next, rr * p.rep_bytes) + o, SENT); }
                     }
                 }
             });
         };
-        dense(p.wd1, p.bd1, SL(p.h116, cur), SL(p.y116, cur), SL(p.y116, nxt));
+        dense(p.wd1, p.bd1, SL(p.h116, cur_r), SL(p.y116, cur), SL(p.y116, nxt));
         mv_prefetch(pf, p.wd2, IH / 8, nmd, INF_WARPS);
         IT_TRACE(15);
-        dense(p.wd2, p.bd2, SL(p.y116, cur), SL(p.y216, cur), SL(p.y216, nxt));
+        dense(p.wd2, p.bd2, SL(p.y116, cur_r), SL(p.y216, cur), SL(p.y216, nxt));
         mv_prefetch(pf, p.wc, p.M / 4, nmd, INF_WARPS);
         IT_TRACE(17);
         // ---- P8 conv + inverse affine: out = (residual - b) / exp(log_s); task rows = (log_s, b) of 4 consecutive channels
-        if (act_conv) stage2(sx, 0, SL(p.y216, cur), IH, IH, 0, nullptr, 0, 0, p.B, p.status);
+        if (threadIdx.x < p.B) {
+            // the samples' gate decisions of this frame (written by CTA b after lstm layer 0, long ago)
+            const float fl = poll_f32(reinterpret_cast<const float*>(SL(p.alive, cur)) + threadIdx.x, p.status, 306);
+            if (s_alive[threadIdx.x]) s_nfr[threadIdx.x] = i + 1;
+            s_alive[threadIdx.x] = __float_as_uint(fl) != 0u;
+        }
+        float rpre[2] = {0.f, 0.f}, cb0 = 0.f, cb1 = 0.f;                 // residual and conv biases of this lane's outputs (S = 16: task == CTA)
+        if (act_conv && warp == 0) {
+            const int j = lane & 3, r = lane >> 2, m = 4 * blockIdx.x + j;
+            cb0 = p.bc[blockIdx.x * 8 + 2 * j]; cb1 = p.bc[blockIdx.x * 8 + 2 * j + 1];
+            if (r < p.B) rpre[0] = p.residual[(static_cast<long long>(i) * p.B + r) * p.M + m];
+            if (kB16 && r + 8 < p.B) rpre[1] = p.residual[(static_cast<long long>(i) * p.B + r + 8) * p.M + m];
+        }
+        if (act_conv) stage3<false, kB16>(sx, 0, SL(p.y216, cur_r), IH, IH, 0, nullptr, 0, 0, 0, nullptr, 0, 0, p.B, p.status);
         __syncthreads();
         IT_TRACE(18);
-        mv_phase<kB16>(p.wc, p.M / 4, nmd, INF_WARPS, spart, sx, pf, [&](int task, float (&d)[4]) {
+        mv_phase<kB16>(p.wc, p.M / 4, nmd, INF_WARPS, spart, sx, pf, [&](int task, float (&d)[4], bool first) {
             const int j = lane & 3, r = lane >> 2;
             const int m = 4 * task + j;
-            const float bl = p.bc[task * 8 + 2 * j], bb = p.bc[task * 8 + 2 * j + 1];
+            const float bl = first ? cb0 : p.bc[task * 8 + 2 * j], bb = first ? cb1 : p.bc[task * 8 + 2 * j + 1];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int b = r + 8 * half;
                 if (b < p.B && (half == 0 || kB16)) {
                     const long long ro = (static_cast<long long>(i) * p.B + b) * p.M;
                     // a sample that stopped at an earlier frame emits zeros; the frame that trips the gate is still emitted
-                    // (s_nfr: updated in this frame's P4 from the flags every CTA read)
+                    // (s_nfr: updated above from the flags every CTA read)
                     const bool emit = (i < s_nfr[b]);
-                    const float val = (p.residual[ro + m] - (d[2 * half + 1] + bb)) / expf(d[2 * half] + bl);
+                    const float res = first ? rpre[half] : p.residual[ro + m];
+                    const float val = (res - (d[2 * half + 1] + bb)) / expf(d[2 * half] + bl);
                     p.out[ro + m] = emit ? val : 0.f;
-                    st_rlx_h(SL(p.x16, cur) + b * XPAD + m, val);
-                    st_rlx_u16(SL(p.x16, nxt) + b * XPAD + m, 0xFFFFu);
+#pragma unroll
+                    for (int rr = 0; rr < NREP; ++rr) {
+                        st_rlx_h(SL(p.x16, cur + rr * p.rep_bytes) + b * XPAD + m, val);
+                        st_rlx_u16(SL(p.x16, nxt + rr * p.rep_bytes) + b * XPAD + m, 0xFFFFu);
+                    }
                 }
             }
         });
@@ -637,8 +786,8 @@ static InferScratch plan_infer(const FtArStepDesc& d, uint8_t* base) {
     // state: cell states cA, c0, c1 (3 x B*IH fp32), then the exchange rings (3 frame slots each): hA32 (B*IH), q (B*A), e (B*L),
     // alive (B) as 32-bit words; hA16, h016, h116, y116, y216 (B*IH), d16 (B*D), x16 (B*96) as fp16 (counted in floats, each piece
     // padded to 16 bytes)
-    s.state_floats = size_t(d.B) * 3 * IH + 3 * (size_t(d.B) * (IH + A + d.L + 1) + 16) +
-                     3 * ((size_t(d.B) * (5 * IH + D + XPAD) + 1) / 2 + 32) + 256;
+    s.state_floats = size_t(d.B) * 3 * IH + 3 * (size_t(d.B) * (IH + A + d.L + 1) + 24) +
+                     3 * 8 /* NREP */ * ((size_t(d.B) * (5 * IH + A + XPAD) + 1) / 2 + size_t(d.B) * A + 40) + 256;
     s.state = reinterpret_cast<float*>(get(s.state_floats * 4));
     s.ints = nullptr;
     s.total = off;
@@ -662,8 +811,8 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
     if (d->n_hidden != IH) return ft_set_error("infer: n_hidden must be 1024");
     if (d->L > LMAX) return ft_set_error("infer: L > 256 not supported");
     if (d->B > 16) return ft_set_error("infer: batch > 16 per call not supported (run the batch in slices of 16)");
-    if (d->n_mel > XPAD || d->n_mel % 8 || d->n_attn % 32 || d->n_text % 8 || d->n_attn > 4 * INF_THREADS)
-        return ft_set_error("infer: n_mel <= 96 and %8, n_attn %32 and <= 2048, n_text %8 required");
+    if (d->n_mel > XPAD || d->n_mel % 8 || d->n_attn % 64 || d->n_text % 8 || d->n_attn > 4 * INF_THREADS)
+        return ft_set_error("infer: n_mel <= 96 and %8, n_attn %64 and <= 2048, n_text %8 required");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     InferScratch s = plan_infer(*d, static_cast<uint8_t*>(scratch));
     const int M = d->n_mel, A = d->n_attn, E = d->n_text, D = IH + A, B = d->B;
@@ -708,20 +857,25 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
     auto take16 = [&](size_t n) { return reinterpret_cast<__half*>(take((n + 1) / 2)); };
     p.cA = take(BH); p.c0 = take(BH); p.c1 = take(BH);
     float* ring0 = f;                                            // everything from here on is exchanged: sentinel-filled
-    p.hA = take(BH); p.q = take(static_cast<size_t>(B) * A); p.e = take(static_cast<size_t>(B) * d->L);
-    p.alive = reinterpret_cast<uint32_t*>(take(B));
+    // slot layout: [replicated tensors] x NREP, then the tensors only a few CTAs read
     p.hA16 = take16(BH); p.h016 = take16(BH); p.h116 = take16(BH); p.y116 = take16(BH); p.y216 = take16(BH);
-    p.d16 = take16(static_cast<size_t>(B) * D); p.x16 = take16(static_cast<size_t>(B) * XPAD);
+    p.ctx16 = take16(static_cast<size_t>(B) * A); p.x16 = take16(static_cast<size_t>(B) * XPAD); p.q = take(static_cast<size_t>(B) * A);
+    p.rep_bytes = (f - ring0) * static_cast<long long>(sizeof(float));
+    f = ring0 + NREP * (f - ring0);
+    p.hA = take(BH); p.e = take(static_cast<size_t>(B) * d->L); p.ctx32 = take(static_cast<size_t>(B) * A);
+    p.alive = reinterpret_cast<uint32_t*>(take(B));
     p.slot_bytes = (f - ring0) * static_cast<long long>(sizeof(float));
     f = ring0 + 3 * (f - ring0);
     if (static_cast<size_t>(f - s.state) > s.state_floats) return ft_set_error("infer: scratch plan overflow");
     if (cudaMemsetAsync(s.state, 0, (ring0 - s.state) * sizeof(float), st) != cudaSuccess) return ft_set_error("infer: memset failed");
     if (cudaMemsetAsync(ring0, 0xFF, (f - ring0) * sizeof(float), st) != cudaSuccess) return ft_set_error("infer: memset failed");
     // the state before frame 0 (slot 2 = frame -1): zero hidden states and a zero previous output frame
-    auto slot2 = [&](void* ptr) { return static_cast<char*>(ptr) + 2 * p.slot_bytes; };
-    if (cudaMemsetAsync(slot2(p.hA16), 0, BH * 2, st) != cudaSuccess || cudaMemsetAsync(slot2(p.h016), 0, BH * 2, st) != cudaSuccess ||
-        cudaMemsetAsync(slot2(p.h116), 0, BH * 2, st) != cudaSuccess || cudaMemsetAsync(slot2(p.x16), 0, static_cast<size_t>(B) * XPAD * 2, st) != cudaSuccess)
-        return ft_set_error("infer: memset failed");
+    for (int rr = 0; rr < NREP; ++rr) {
+        auto slot2 = [&](void* ptr) { return static_cast<char*>(ptr) + 2 * p.slot_bytes + rr * p.rep_bytes; };
+        if (cudaMemsetAsync(slot2(p.hA16), 0, BH * 2, st) != cudaSuccess || cudaMemsetAsync(slot2(p.h016), 0, BH * 2, st) != cudaSuccess ||
+            cudaMemsetAsync(slot2(p.h116), 0, BH * 2, st) != cudaSuccess || cudaMemsetAsync(slot2(p.x16), 0, static_cast<size_t>(B) * XPAD * 2, st) != cudaSuccess)
+            return ft_set_error("infer: memset failed");
+    }
     p.status = ft_status_word();
     p.trace = g_infer_trace;
     int dev = 0, sms = 0;
@@ -729,7 +883,7 @@ int ft_ar_step_infer(const FtArStepDesc* d, const FtArStepWeights* w, const floa
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms < B) return ft_set_error("infer: fewer SMs than utterances");
     void* fn = B > 8 ? reinterpret_cast<void*>(infer_kernel<true>) : reinterpret_cast<void*>(infer_kernel<false>);
-    const int smem = 16 * KP * 2 + INF_WARPS * 128 * 4 + (LMAX + D + 4 * A + 64) * 4;
+    const int smem = 16 * KP * 2 + INF_WARPS * 128 * 4 + (LMAX + INF_WARPS * 128 + 64) * 4;
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     TimeScope ts("infer", d->T, B, d->L, st);
     void* args[] = {&p};

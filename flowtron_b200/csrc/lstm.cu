@@ -937,11 +937,11 @@ int launch_lstm_fwd_xin(int T, int B, const void* x16, long long ldx, int kx, co
 
 // Steps [t0, t1) of a layer on 64 CTAs (layer pipeline, ar_step.cu).  `flags` needs (t1 - t0) * 16 ints.
 int launch_lstm_fwd_chunk(int T, int B, int t0, int t1, const float* xproj, const void* whh16, const int* lens, void* hseq16,
-                          long long ldh, void* gates16, float* cstate, int* flags, cudaStream_t st) {
+                          long long ldh, void* gates16, float* cstate, int* flags, cudaStream_t st, float* h32, long long ldh32) {
     if (T <= 0 || B <= 0 || t1 <= t0) return 0;
     if (B > 64 || t0 < 0 || t1 > T) return ft_set_error("lstm_fwd_chunk: bad batch or step range");
     if (t0 > 0 && !cstate) return ft_set_error("lstm_fwd_chunk: resuming a chunk needs the saved cell states");
-    return launch_fwd_t<8, 16, false>(T, B, t0, t1, xproj, whh16, lens, hseq16, ldh, gates16, cstate, nullptr, 0, flags, st);
+    return launch_fwd_t<8, 16, false>(T, B, t0, t1, xproj, whh16, lens, hseq16, ldh, gates16, cstate, h32, ldh32, flags, st);
 }
 
 // Steps [t0, t1) of a layer's BPTT with the split-K cluster kernel, B <= 32.  `flags` needs (t1 - t0) * 64 ints; `dc_carry`

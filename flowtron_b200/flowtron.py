@@ -109,8 +109,43 @@ def _encoder_side_stream(device):
     return _enc_streams[key]
 
 
+class _EncoderFn(torch.autograd.Function):
+    """Encoder.forward / Encoder.infer on the CUDA kernels (ft_encoder_fwd / ft_encoder_bwd)."""
+
+    @staticmethod
+    def forward(ctx, enc, x, in_lens, masked, dropout_p, *flat_params):
+        B, C, L = x.shape
+        names = [n for n, _ in _lib.ENC_PARAM_FIELDS]
+        counts = [k for _, k in _lib.ENC_PARAM_FIELDS]
+        params, i = {}, 0
+        for n, k in zip(names, counts):
+            params[n] = [t.detach().contiguous() for t in flat_params[i:i + k]]
+            i += k
+        desc = _lib.encoder_desc(B, L, masked, dropout_p, enc.convolutions[0][1].eps)
+        lens32 = in_lens.to(torch.int32) if masked else None
+        x = x.detach().contiguous().float()
+        out = torch.empty(B, L, C, dtype=torch.float32, device=x.device)
+        rng = enc._rng_state(x.device) if dropout_p > 0 else None
+        saved = _lib.encoder_fwd(desc, params, x, lens32, rng, out, out.stride(0), out.stride(1))
+        ctx.desc, ctx.params, ctx.saved = desc, params, saved
+        ctx.need_dx = x.requires_grad or ctx.needs_input_grad[1]
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        if ctx.saved is None:
+            raise RuntimeError("Encoder backward called twice (the saved activations were released)")
+        d_x, grads = _lib.encoder_bwd(ctx.desc, ctx.params, d_out.contiguous().float(), ctx.saved, need_dx=ctx.need_dx)
+        ctx.saved = None
+        flat = []
+        for n, _ in _lib.ENC_PARAM_FIELDS:
+            flat += grads[n]
+        return (None, d_x, None, None, None, *flat)
+
+
 class Encoder(nn.Module):
-    """flowtron.py:467-525 (3 x conv+masked instance norm+relu+dropout, packed BiLSTM)."""
+    """flowtron.py:467-525 (3 x conv+masked instance norm+relu+dropout, packed BiLSTM).  CUDA tensors run on the encoder kernels
+    (csrc/encoder.cu); the torch code below is the module's CPU mirror (host-logic tests) and the FT_ENC_KERNELS=0 A/B path."""
 
     def __init__(self, encoder_n_convolutions=3, encoder_embedding_dim=512, encoder_kernel_size=5, norm_fn=nn.BatchNorm1d):
         super().__init__()
@@ -125,6 +160,25 @@ class Encoder(nn.Module):
         self.p_dropout = 0.5        # flowtron.py:502 hard-codes 0.5; exposed so tests can run deterministic train-mode steps
         # FT_ENC_STREAMS=1: run the two LSTM directions concurrently (parity-tested; measured r1: only -0.4 ms/step, so off)
         self.two_streams = os.environ.get("FT_ENC_STREAMS", "0") != "0"
+        self.use_kernels = os.environ.get("FT_ENC_KERNELS", "1") != "0"
+        self._rng = None
+
+    def _rng_state(self, device):
+        """device uint64[2] = {seed, call counter} of the dropout masks (advanced on the device by every training forward)."""
+        if self._rng is None or self._rng.device != device:
+            self._rng = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=device)
+        return self._rng
+
+    def _kernel_params(self):
+        cs = self.convolutions
+        flat = [c[0].conv.weight for c in cs] + [c[0].conv.bias for c in cs] + [c[1].weight for c in cs] + [c[1].bias for c in cs]
+        for n in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"):
+            flat += [getattr(self.lstm, n), getattr(self.lstm, n + "_reverse")]
+        return flat
+
+    def _kernels_ok(self, x):
+        return (self.use_kernels and x.is_cuda and x.size(1) == 512 and len(self.convolutions) == 3 and x.size(0) <= 64
+                and self.convolutions[0][0].conv.kernel_size[0] == 5 and isinstance(self.convolutions[0][1], MaskedInstanceNorm1d))
 
     def _lstm_dir(self, x, sfx):
         """One direction of the BiLSTM on a padded [B, L, C] batch."""
@@ -148,6 +202,8 @@ class Encoder(nn.Module):
         they are latency-bound, so with ``two_streams`` the two directions run concurrently on two CUDA streams (autograd
         replays each direction's backward on the stream its forward ran on).  Requires the text batch to be padded to
         max(in_lens), which DataCollate guarantees (data.py:200-208)."""
+        if self._kernels_ok(x):
+            return _EncoderFn.apply(self, x, in_lens, x.size(0) > 1, self.p_dropout if self.training else 0.0, *self._kernel_params())
         Bn, _, L = x.shape
         ar = torch.arange(L, device=x.device)
         valid = ar[None, :] < in_lens[:, None]                                   # [B, L]
@@ -173,6 +229,8 @@ class Encoder(nn.Module):
         return torch.cat([fwd, bwd], -1) * valid[..., None].to(x.dtype)
 
     def infer(self, x):
+        if self._kernels_ok(x):
+            return _EncoderFn.apply(self, x, None, False, self.p_dropout if self.training else 0.0, *self._kernel_params())
         for conv in self.convolutions:
             x = F.dropout(F.relu(conv(x)), self.p_dropout, self.training)
         x = x.transpose(1, 2)

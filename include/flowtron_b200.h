@@ -232,6 +232,52 @@ size_t ft_attn_ctc_scratch_bytes(int B, int T, int L);
 int ft_attn_ctc_loss(const float* attn_logprob, const int* in_lens, const int* out_lens, int B, int T, int L, int time_reversed,
                      float blank_logprob, float* cost, float* d_attn_logprob, void* scratch, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------------
+ * Text Encoder (flowtron.py:467-525): 3 x [Conv1d(512, 512, k=5) -> MaskedInstanceNorm1d(affine) -> relu -> dropout(0.5)],
+ * then a packed bidirectional LSTM(512 -> 2 x 256); forward + backward.
+ * Replaces Encoder.forward (masked = 1: tokens at l >= in_lens[b] are zeroed before every convolution, statistics run over
+ * the utterance's own tokens, the BiLSTM behaves as on a packed sequence, outputs are zero at l >= in_lens[b]) and
+ * Encoder.infer / the B == 1 case (masked = 0: no lengths).  Weights in PyTorch layouts; index 1 of the LSTM arrays is the
+ * `_reverse` direction.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int B, L;           /* utterances (1..64), padded text length                               */
+    int C;              /* 512 (encoder_embedding_dim; must be 512 in this build)               */
+    int n_convs, ksize; /* 3, 5                                                                 */
+    int masked;         /* 1: use in_lens (Encoder.forward, B > 1); 0: every token valid        */
+    float dropout_p;    /* 0 (eval) or the training probability (flowtron.py:502 hard-codes 0.5) */
+    float eps;          /* instance-norm eps (1e-5)                                             */
+} FtEncoderDesc;
+
+typedef struct {
+    const float* conv_w[3]; const float* conv_b[3];    /* [512,512,5], [512] */
+    const float* norm_w[3]; const float* norm_b[3];    /* [512]              */
+    const float* w_ih[2]; const float* w_hh[2];        /* [1024,512], [1024,256] */
+    const float* b_ih[2]; const float* b_hh[2];        /* [1024]             */
+} FtEncoderWeights;
+
+typedef struct {                                       /* gradients, same shapes, OVERWRITTEN */
+    float* d_conv_w[3]; float* d_conv_b[3];
+    float* d_norm_w[3]; float* d_norm_b[3];
+    float* d_w_ih[2]; float* d_w_hh[2];
+    float* d_b_ih[2]; float* d_b_hh[2];
+} FtEncoderGrads;
+
+size_t ft_encoder_saved_bytes(const FtEncoderDesc* d);          /* forward -> backward tensors */
+size_t ft_encoder_fwd_scratch_bytes(const FtEncoderDesc* d);
+size_t ft_encoder_bwd_scratch_bytes(const FtEncoderDesc* d);
+/* x [B, 512, L] fp32 (embedding output, channels first, as Encoder.forward receives it); in_lens int32 [B] (masked only);
+ * rng_state: device uint64[2] = {seed, call counter} for the dropout masks (advanced by the call; NULL when dropout_p == 0);
+ * out: fp32, element (b, l, c) at out[b * out_stride_b + l * out_stride_l + c], c < 512 (forward direction first) -- lets the
+ * caller write straight into the [L, B, 640] text tensor the flows read. */
+int ft_encoder_fwd(const FtEncoderDesc* d, const FtEncoderWeights* w, const float* x, const int* in_lens,
+                   unsigned long long* rng_state, float* out, long long out_stride_b, long long out_stride_l, void* saved,
+                   void* scratch, void* stream);
+/* d_out: dense [B, L, 512] fp32; d_x [B, 512, L] fp32 (may be NULL). */
+int ft_encoder_bwd(const FtEncoderDesc* d, const FtEncoderWeights* w, const float* d_out, long long d_stride_b,
+                   long long d_stride_l, const void* saved, float* d_x, const FtEncoderGrads* grads, void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
