@@ -495,12 +495,16 @@ class Flowtron(nn.Module):
     overlap_encoder = os.environ.get("FT_ENC_OVERLAP", "1") != "0"
     min_split_batch = 8
 
-    max_kernel_batch = 64        # the persistent recurrence kernels take up to 64 utterances per launch
+    # Utterances per kernel launch.  The kernels take up to 64, but the fast paths (cluster BPTT, layer pipeline, folded input
+    # projection) are B <= 32 paths: a B = 64 batch (configs[2]) runs faster as two consecutive 32-utterance launches than as
+    # one 64-utterance launch on the fallback kernels (r2: 118.8 ms/step as one launch).  FT_MAX_KERNEL_BATCH overrides.
+    max_kernel_batch = int(os.environ.get("FT_MAX_KERNEL_BATCH", "32"))
 
     def _run_flows(self, mel, encoder_outputs, mask, out_lens, attn_prior):
         B = mel.size(1)
         if B > self.max_kernel_batch:          # larger batches run as consecutive chunks (utterances are independent)
-            outs = [self._run_flows(mel[:, b0:b0 + self.max_kernel_batch], encoder_outputs[:, b0:b0 + self.max_kernel_batch],
+            ech = getattr(self, "_enc_chunks", None) or {}      # contiguous text slices made on the encoder's stream (forward())
+            outs = [self._run_flows(mel[:, b0:b0 + self.max_kernel_batch], ech.get(b0, encoder_outputs[:, b0:b0 + self.max_kernel_batch]),
                                     mask[b0:b0 + self.max_kernel_batch],
                                     None if out_lens is None else out_lens[b0:b0 + self.max_kernel_batch],
                                     None if attn_prior is None else attn_prior[b0:b0 + self.max_kernel_batch])
@@ -536,19 +540,28 @@ class Flowtron(nn.Module):
         # The first flow needs the text encoding only after its attention LSTM (T dependent steps that read mel alone), so
         # the encoder's ~700 small latency-bound kernels can run on a second stream underneath it; the flow's C entry
         # point waits for `text_event` right before it first reads the encoding (ft_ar_step_set_text_ready_event).
-        overlap = self.overlap_encoder and mel.is_cuda and self.n_streams <= 1 and B <= self.max_kernel_batch
+        overlap = self.overlap_encoder and mel.is_cuda and self.n_streams <= 1 and B <= 64
         self._text_event = None
         if overlap:
             cur = torch.cuda.current_stream(mel.device)
             es = _encoder_overlap_stream(mel.device)
             es.wait_stream(cur)
+            self._enc_chunks = None
             with torch.cuda.stream(es):
                 encoder_outputs = self._encode(speaker_ids, text, in_lens)
+                if B > self.max_kernel_batch:
+                    # the flows will run on slices of the batch: make them contiguous HERE, on the encoder's stream, in front of
+                    # the event (a .contiguous() issued later on the caller's stream would read the encoding before it exists)
+                    mkb = self.max_kernel_batch
+                    self._enc_chunks = {b0: encoder_outputs[:, b0:b0 + mkb].contiguous() for b0 in range(0, B, mkb)}
+                    for t in self._enc_chunks.values():
+                        t.record_stream(cur)
                 ev = torch.cuda.Event()
                 ev.record(es)
             encoder_outputs.record_stream(cur)
             self._text_event = ev
         else:
+            self._enc_chunks = None
             encoder_outputs = self._encode(speaker_ids, text, in_lens)
         mel = mel.permute(2, 0, 1)
         # key-padding mask from the padded text length (== max(in_lens) by the collate contract): no .item() host sync

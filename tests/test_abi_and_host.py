@@ -105,3 +105,21 @@ def test_default_switches_are_the_validated_configuration(monkeypatch):
     assert 'getenv("FT_PIPE_FWD"); v = (!e || atoi(e) != 0) ? 1 : 0' in csrc
     assert 'getenv("FT_PIPE_BWD"); v = (!e || atoi(e) != 0) ? 1 : 0' in csrc
     assert 'os.environ.get("FT_GRAPH", "1")' in src
+
+
+def test_encoder_abi_host_side():
+    """ft_encoder_*_bytes are pure host functions: sizes grow with the batch, an unsupported descriptor gives 0 and an error
+    string (no GPU needed)."""
+    from ctypes import byref
+    from flowtron_b200 import _lib
+    L = _lib.lib()
+    small, big = _lib.encoder_desc(2, 16, True, 0.0), _lib.encoder_desc(32, 160, True, 0.5)
+    for fn in (L.ft_encoder_saved_bytes, L.ft_encoder_fwd_scratch_bytes, L.ft_encoder_bwd_scratch_bytes):
+        a, b = fn(byref(small)), fn(byref(big))
+        assert 0 < a < b
+    bad = _lib.encoder_desc(2, 16, True, 0.0)
+    bad.C = 256
+    assert L.ft_encoder_saved_bytes(byref(bad)) == 0
+    assert b"512" in L.ft_last_error()
+    # the weight / gradient structs have one pointer per reference parameter of Encoder (flowtron.py:473-490)
+    assert sum(k for _, k in _lib.ENC_PARAM_FIELDS) == 20
