@@ -17,13 +17,14 @@
 //   * a task's K range is split over the warps of a CTA (partial accumulators meet in shared memory), so all 16 warps of
 //     every SM stream weights in every phase;
 //   * a warp's share of the NEXT phase's weights is prefetched into registers before it waits for that phase's inputs (weights
-//     do not depend on them); scores run over all warps of the grid, softmax (+ prior posterior) + context + gate of one
-//     utterance inside one CTA;
+//     do not depend on them), and so are the lane's biases, cell states and residual frame; scores run over all warps of the
+//     grid (query rows staged in shared memory), then one (utterance, 64- or 128-channel slice) context item per CTA with the
+//     softmax (+ prior posterior) recomputed per item; the gate logit of utterance b is computed by CTA b off the critical path;
 //   * NO grid barriers (r2 call 7 trace: 9 barriers x 1.4 us + 9 staging round trips x 0.6 us = 18 of a frame's 39 us): the
 //     DATA IS THE FLAG.  Every exchanged activation lives in a ring of 3 frame slots pre-filled with a sentinel (0xFFFF per
 //     fp16, 0xFFFFFFFF per fp32 word: bit patterns no conversion produces); producers store results with st.relaxed.gpu and
-//     reset the same elements of the NEXT slot to the sentinel; consumers spin with ld.relaxed.gpu on the very words they need
-//     until no sentinel is left and copy them to shared memory.  A phase hand-over costs one L2 store + one L2 load instead of
+//     reset the same elements of the NEXT slot to the sentinel; consumers fetch the very words they need into shared memory
+//     (cp.async.cg rounds) and re-fetch the packets that still contain a sentinel.  A hand-over costs one L2 store + one L2 load instead of
 //     membar + atomic + poll + barrier + load.  A slot is reset two frames after its last reader: every read is followed by a
 //     store that all CTAs consume within one frame, and one gpu-scope fence per thread per frame makes that chain formal
 //     (tools/trace_infer.py prints the phase table).
