@@ -208,6 +208,11 @@ def _need_cuda(*ts):
             raise FlowtronB200Error("flowtron_b200 kernels need CUDA tensors (no CPU fallback exists)")
 
 
+def set_gemm_pair_mode(mode: int):
+    """0 = single-CTA tiles, 1 = CTA pairs for big contractions (default), 2 = CTA pairs whenever eligible."""
+    lib().ft_set_gemm_pair_mode(int(mode))
+
+
 def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, bias2=None, act=0, beta=0, alpha=1.0,
          out32=None, out16=None):
     """C = act(alpha * A @ B^T + bias + bias2) (+ out32 if beta).  A:[M,K] (or [K,M] if a_mn), B:[N,K] (or [K,N])."""

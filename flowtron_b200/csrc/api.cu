@@ -127,6 +127,7 @@ void ft_debug_set_lstm_trace(long long* buf) { ft::set_lstm_trace(buf); }
 /* 1: ft_lstm_fwd uses its 64-CTA variant (16 units per CTA) so that two launches -- one per half batch, on two
  * streams -- are co-resident on the 148 SMs and hide each other's per-step exchange latency. */
 void ft_set_lstm_half_sm(int on) { ft::set_lstm_half_sm(on); }
+void ft_set_gemm_pair_mode(int mode) { ft::set_gemm_pair_mode(mode); }
 
 int ft_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const int* lens, void* hseq16, long long ldh,
                 void* gates16, float* cstate, float* h32, long long ldh32, int* flags, void* stream) {

@@ -36,6 +36,7 @@ struct GemmArgs {
     void* C16 = nullptr; long long ldc16 = 0; int c16_fmt = 0;
 };
 int launch_gemm(const GemmArgs& g, cudaStream_t st);
+void set_gemm_pair_mode(int mode);   // 0 never, 1 big contractions only (default), 2 whenever eligible
 int make_tmap_2d(CUtensorMap* out, const void* ptr, int fmt, long long rows, long long cols, long long ld,
                  int box_cols, int box_rows);
 

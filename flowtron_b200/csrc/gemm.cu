@@ -51,16 +51,24 @@ struct GemmParams {
 constexpr int G2_THREADS = 192;
 constexpr int G2_PITCH = 36;                                   // floats: 16-byte aligned rows, conflict-free float4 access
 constexpr int G2_STAGE_FLOATS = 32 * G2_PITCH;                 // per-warp transpose tile
-template <int BN_> struct G2Cfg {
-    static constexpr int STAGE_BYTES = (BM + BN_) * 128;
-    static constexpr int STAGES = BN_ == 256 ? 4 : 6;
+// NCTA = 2 (BN = 256 only): a CTA PAIR (2-CTA cluster, tcgen05 cta_group::2) owns a 256 x 256 tile.  Each CTA stages its own 128
+// rows of A and HALF of B's 256 rows (32 KB per stage instead of 48: 6 stages), the leader issues 256 x 256 x 16 MMAs that read A
+// from both CTAs' shared memory and the two B halves, each CTA's 128 accumulator rows land in its own TMEM and are drained by its
+// own epilogue warps.  Operand bytes per FLOP drop by 1.5x (the 128 x 256 tile is L2->SM bound: 87 FLOP per operand byte).
+template <int BN_, int NCTA = 1> struct G2Cfg {
+    static constexpr int STAGE_BYTES = (BM + BN_ / NCTA) * 128;
+    static constexpr int STAGES = (BN_ == 256 && NCTA == 1) ? 4 : 6;
     static constexpr int SMEM = STAGES * STAGE_BYTES + 4 * G2_STAGE_FLOATS * 4 + 256 + 1024;
 };
 
-template <bool kTf32, int BN_>
+template <bool kTf32, int BN_, int NCTA = 1>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p, int tiles_n, int n_tiles) {
-    using C = G2Cfg<BN_>;
+    using C = G2Cfg<BN_, NCTA>;
+    constexpr int TM = BM * NCTA;                   // rows of a work item's tile
+    const int rank = NCTA == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int wid0 = NCTA == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int wstep = NCTA == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
     constexpr int ST = C::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -85,10 +93,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
-        mbar_init(&tempty[0], 4); mbar_init(&tempty[1], 4);
+        mbar_init(&tempty[0], 4 * NCTA); mbar_init(&tempty[1], 4 * NCTA);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<2 * BN_>(tmem_slot);
+    if (NCTA == 2) cluster_sync_all();              // the peer's barriers exist before anything can arrive on them
+    if (warp == 1) { if (NCTA == 2) tmem_alloc_pair<2 * BN_>(tmem_slot); else tmem_alloc<2 * BN_>(tmem_slot); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -97,49 +106,54 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (warp == 0) {
         // ------------------------------------------------ TMA producer (warp-uniform loop, one elected lane issues)
         int it = 0;
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        auto ld = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+            if (NCTA == 2) tma_load_2d_pair(dst, m, bar, c0, c1); else tma_load_2d(dst, m, bar, c0, c1);
+        };
+        constexpr int BNC = BN_ / NCTA;             // B rows this CTA stages
+        for (int w = wid0; w < n_work; w += wstep) {
             const int split = w / n_tiles, tile = w - split * n_tiles;
             const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
             const int kb0 = split * kb_per_split, kb1 = min(num_kb_all, kb0 + kb_per_split);
+            const int am = tile_m * TM + rank * BM, bn = tile_n * BN_ + rank * BNC;
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % ST, ph = (it / ST) & 1;
                 mbar_wait(&empty[s], ph ^ 1, p.status, 111);
                 uint8_t* a = smem + s * C::STAGE_BYTES;
                 uint8_t* b = a + TILE_BYTES;
                 if (elect_one()) {
-                    mbar_expect_tx(&full[s], C::STAGE_BYTES);
+                    if (rank == 0) mbar_expect_tx(&full[s], C::STAGE_BYTES * NCTA);     // the pair's bytes land on the leader's barrier
                     if (!p.a_mn) {
-                        tma_load_2d(a, &tmA, &full[s], kb * BK, tile_m * BM);
+                        ld(a, &tmA, &full[s], kb * BK, am);
                     } else {
 #pragma unroll
                         for (int j = 0; j < BM / BK; ++j)
-                            tma_load_2d(a + j * (BK * 128), &tmA, &full[s], tile_m * BM + j * BK, kb * BK);
+                            ld(a + j * (BK * 128), &tmA, &full[s], am + j * BK, kb * BK);
                     }
                     if (!p.b_mn) {
-                        tma_load_2d(b, &tmB, &full[s], kb * BK, tile_n * BN_);
+                        ld(b, &tmB, &full[s], kb * BK, bn);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < BN_ / BK; ++j)
-                            tma_load_2d(b + j * (BK * 128), &tmB, &full[s], tile_n * BN_ + j * BK, kb * BK);
+                        for (int j = 0; j < BNC / BK; ++j)
+                            ld(b + j * (BK * 128), &tmB, &full[s], bn + j * BK, kb * BK);
                     }
                 }
                 __syncwarp();
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer
-        const uint32_t idesc = umma_idesc(BM, BN_, p.a_fmt, p.b_fmt, p.a_mn, p.b_mn);
+    } else if (warp == 1 && rank == 0) {
+        // ------------------------------------------------ MMA issuer (the pair's leader only)
+        const uint32_t idesc = umma_idesc(TM, BN_, p.a_fmt, p.b_fmt, p.a_mn, p.b_mn);
         const uint32_t tmem_d0 = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint64_t da0 = p.a_mn ? umma_smem_desc(smem_u32(smem), BK * 128, 1024) : umma_smem_desc(smem_u32(smem), 16, 1024);
         const uint64_t db0 = p.b_mn ? umma_smem_desc(smem_u32(smem + TILE_BYTES), BK * 128, 1024)
                                     : umma_smem_desc(smem_u32(smem + TILE_BYTES), 16, 1024);
         const uint64_t ka = p.a_mn ? (UK * 128) >> 4 : 2, kbs = p.b_mn ? (UK * 128) >> 4 : 2;
         int it = 0, tc = 0;
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tc) {
+        for (int w = wid0; w < n_work; w += wstep, ++tc) {
             const int split = w / n_tiles;
             const int kb0 = split * kb_per_split, kb1 = min(num_kb_all, kb0 + kb_per_split);
             const int buf = tc & 1, bph = (tc >> 1) & 1;
-            mbar_wait(&tempty[buf], bph ^ 1, p.status, 112);          // the epilogue drained this accumulator (first use: free)
+            mbar_wait(&tempty[buf], bph ^ 1, p.status, 112);          // the epilogue(s) drained this accumulator (first use: free)
             tc_fence_after();
             const uint32_t tmem_d = tmem_d0 + buf * BN_;
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -152,16 +166,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
                     for (int k = 0; k < BK / UK; ++k) {
                         const uint32_t acc = ((kb - kb0) | k) != 0;
-                        if (kTf32) umma_tf32(tmem_d, da + k * ka, db + k * kbs, idesc, acc);
-                        else       umma_f16(tmem_d, da + k * ka, db + k * kbs, idesc, acc);
+                        if (NCTA == 2) {
+                            if (kTf32) umma_tf32_pair(tmem_d, da + k * ka, db + k * kbs, idesc, acc);
+                            else       umma_f16_pair(tmem_d, da + k * ka, db + k * kbs, idesc, acc);
+                        } else {
+                            if (kTf32) umma_tf32(tmem_d, da + k * ka, db + k * kbs, idesc, acc);
+                            else       umma_f16(tmem_d, da + k * ka, db + k * kbs, idesc, acc);
+                        }
                     }
-                    umma_commit(&empty[s]);
-                    if (kb == kb1 - 1) umma_commit(&tfull[buf]);
+                    if (NCTA == 2) { umma_commit_pair(&empty[s]); if (kb == kb1 - 1) umma_commit_pair(&tfull[buf]); }
+                    else           { umma_commit(&empty[s]); if (kb == kb1 - 1) umma_commit(&tfull[buf]); }
                 }
                 __syncwarp();
             }
         }
-    } else {
+    } else if (warp >= 2) {
         // ------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
         // Per 32-column chunk: tcgen05.ld (lane = row) -> 32x36 shared-memory tile (16-byte vector stores, conflict-free per
         // quarter warp) -> re-read as float4 with lane = (row within a group of 4, 4-column group): one warp instruction
@@ -178,14 +197,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                             (!p.C16 || (((reinterpret_cast<uintptr_t>(p.C16) & 7) == 0) && (p.ldc16 % 4 == 0))) &&
                             (p.act != 2 || (((reinterpret_cast<uintptr_t>(p.aux16) & 7) == 0) && (p.ldaux % 4 == 0)));
         int tc = 0;
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tc) {
+        for (int w = wid0; w < n_work; w += wstep, ++tc) {
             const int tile = w % n_tiles;
             const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
             const int buf = tc & 1, bph = (tc >> 1) & 1;
             mbar_wait(&tfull[buf], bph, p.status, 114);
             tc_fence_after();
             const int ncols = min(BN_, p.N - tile_n * BN_);
-            const long long m0 = static_cast<long long>(tile_m) * BM + q * 32;
+            const long long m0 = static_cast<long long>(tile_m) * TM + rank * BM + q * 32;
             const int rows = static_cast<int>(min(static_cast<long long>(32), p.M - m0));     // may be <= 0
             const int nchunks = (ncols + 31) >> 5;
 #pragma unroll 1
@@ -195,7 +214,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 tmem_ld_wait();
                 if (c == nchunks - 1) {                              // everything this warp needs is in registers: hand the
                     tc_fence_before();                               // accumulator back to the MMA warp before the stores
-                    if (lane == 0) mbar_arrive(&tempty[buf]);
+                    if (lane == 0) { if (NCTA == 2) mbar_arrive_pair_leader(&tempty[buf]); else mbar_arrive(&tempty[buf]); }
                 }
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
@@ -286,12 +305,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 }
                 __syncwarp();
             }
-            if (nchunks == 0) { tc_fence_before(); if (lane == 0) mbar_arrive(&tempty[buf]); }
+            if (nchunks == 0) { tc_fence_before(); if (lane == 0) { if (NCTA == 2) mbar_arrive_pair_leader(&tempty[buf]); else mbar_arrive(&tempty[buf]); } }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<2 * BN_>(tmem_base);
+    if (NCTA == 2) cluster_sync_all();              // both CTAs are done with the pair's TMEM and with each other's shared memory
+    if (warp == 1) { if (NCTA == 2) tmem_dealloc_pair<2 * BN_>(tmem_base); else tmem_dealloc<2 * BN_>(tmem_base); }
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -328,6 +348,9 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int fmt, long long rows, lon
     if (r != CUDA_SUCCESS) return ft_set_error("cuTensorMapEncodeTiled failed");
     return 0;
 }
+
+static int g_pair_mode = -1;        // 0 never, 1 big contractions only, 2 whenever eligible
+void set_gemm_pair_mode(int mode) { g_pair_mode = mode; }
 
 int launch_gemm(const GemmArgs& g, cudaStream_t st) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
@@ -373,6 +396,36 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
             if (cudaMemsetAsync(g.C32, 0, sizeof(float) * static_cast<size_t>(g.M) * g.N, st) != cudaSuccess) return ft_set_error("gemm: memset failed");
         }
         p.splitk = splitk;
+        // CTA pairs for wide outputs with enough 256 x 256 tiles to fill the machine.  Mode 1 (default; FT_GEMM_2CTA / ft_set_gemm_pair_mode
+        // override): only for the big contractions (>= 1e11 FLOP) -- measured r2 call 15 on the training step: weight gradients
+        // 4096 x 1664 x 32000 +5 % (709 -> 746 TFLOP/s), the layer-0 projection 32000 x 4096 x 1664 -1 %, the per-chunk 3200-row GEMMs
+        // that run beside the recurrences on ~20 SMs -18 % (74 pairs queue worse than 148 single CTAs there).  Mode 2: whenever eligible.
+        if (g_pair_mode < 0) { const char* e = getenv("FT_GEMM_2CTA"); g_pair_mode = e ? atoi(e) : 1; }
+        const long long tiles_m2 = (g.M + 2 * BM - 1) / (2 * BM);
+        const bool big = 2.0 * g.M * g.N * g.K >= 1e11;
+        if ((g_pair_mode == 2 || (g_pair_mode == 1 && big)) && wide && splitk == 1 && tiles_m2 * tiles_n >= sms / 2) {
+            const int n_tiles2 = static_cast<int>(tiles_m2 * tiles_n);
+            const int n_pairs = n_tiles2 < sms / 2 ? n_tiles2 : sms / 2;
+            if (!g.b_mn) { if (make_tmap_2d(&tmB, g.B, g.b_fmt, g.N, g.K, g.ldb, BK, 128)) return -1; }    // half of B's rows per CTA
+            static bool attr_pair = false;
+            if (!attr_pair) {
+                cudaFuncSetAttribute(gemm2_kernel<false, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<256, 2>::SMEM);
+                cudaFuncSetAttribute(gemm2_kernel<true, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<256, 2>::SMEM);
+                attr_pair = true;
+            }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * n_pairs); cfg.blockDim = dim3(G2_THREADS); cfg.dynamicSmemBytes = G2Cfg<256, 2>::SMEM; cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            TimeScope ts(g.a_mn ? "gemm_wgrad" : (g.b_mn ? "gemm_dgrad" : "gemm_fwd"), g.M, g.N, g.K, st);
+            cudaError_t e = tf32 ? cudaLaunchKernelEx(&cfg, gemm2_kernel<true, 256, 2>, tmA, tmB, p, tiles_n, n_tiles2)
+                                 : cudaLaunchKernelEx(&cfg, gemm2_kernel<false, 256, 2>, tmA, tmB, p, tiles_n, n_tiles2);
+            if (e != cudaSuccess) return ft_set_error(cudaGetErrorString(e));
+            ft_count_launch(1);
+            return ft_check_launch("gemm2_kernel<pair>");
+        }
         const long long n_work = static_cast<long long>(n_tiles) * splitk;
         const int grid2 = n_work < sms ? static_cast<int>(n_work) : sms;
         // operand boxes: K-major A {BK, 128}; K-major B {BK, bn}; MN-major boxes are {BK, BK} as in v1

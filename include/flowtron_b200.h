@@ -57,6 +57,9 @@ void ft_debug_set_infer_trace(long long* buf);
 /* Process-wide switch: 1 = ft_lstm_fwd (and ft_ar_step_fwd) use the 64-CTA recurrence kernel so two half-batch
  * launches on two streams run concurrently (the BPTT kernel always uses 64 CTAs for B <= 32). */
 void ft_set_lstm_half_sm(int on);
+/* ft_gemm tile policy: 0 = one CTA per 128 x 256 tile always; 1 (default) = CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles) for
+ * contractions >= 1e11 FLOP; 2 = CTA pairs whenever the output is wide and has >= SMs/2 such tiles. */
+void ft_set_gemm_pair_mode(int mode);
 
 /* BPTT of the same layer (autograd of nn.LSTM).  dh_ext: gradient w.r.t. the layer outputs, fp32
  * [T*B, ldd] (ignored at t >= lens[b]; the caller may pre-multiply it by a power-of-two loss scale).  whhT16:

@@ -38,12 +38,21 @@ CASES = [
     (128 * 20, 1280, 4096, torch.float16, False, True),       # dgrad, N > 1024 not a multiple of 256
     (128 * 13, 4096, 80, torch.float16, False, False),        # the K = 80 mel projection at many tiles
     (1300, 2304, 160, torch.float32, False, False),           # tf32, wide
+    # CTA-pair path (cta_group::2, 256 x 256 tiles: taken when there are >= 74 such tiles and no split-K)
+    (128 * 40, 1280, 1024, torch.float16, False, True),       # dgrad, N tail tile (1280 = 5 x 256), B MN-major halves
+    (5000, 1024, 256, torch.bfloat16, True, False),           # A MN-major, M tail inside a pair tile
+    (2600, 2304, 160, torch.float32, False, False),           # tf32 pair, K tail
+    (128 * 64 + 130, 4096, 1664, torch.float16, False, False),   # the layer-0 input projection shape class, peer half partly out of range
 ]
 
 
+@pytest.mark.parametrize("pair_mode", [1, 2])
 @pytest.mark.parametrize("M,N,K,dt,a_mn,b_mn", CASES)
-def test_gemm_matches_fp64(M, N, K, dt, a_mn, b_mn):
+def test_gemm_matches_fp64(M, N, K, dt, a_mn, b_mn, pair_mode):
     from flowtron_b200 import _lib
+    if pair_mode == 2 and (N <= 1024 and N % 256) :
+        pytest.skip("narrow output: never a CTA-pair tile")
+    _lib.set_gemm_pair_mode(pair_mode)      # 2: CTA pairs (cta_group::2) whenever eligible, 1: the default policy
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
     A = (torch.randn((K, M) if a_mn else (M, K), device="cuda", generator=g) * 0.5).to(dt)
     B = (torch.randn((K, N) if b_mn else (N, K), device="cuda", generator=g) * 0.5).to(dt)
@@ -59,6 +68,7 @@ def test_gemm_matches_fp64(M, N, K, dt, a_mn, b_mn):
     tol = 2e-3 if dt == torch.float32 else 1e-4      # tf32 truncates fp32 inputs; 16-bit inputs are exact
     assert err <= tol * scale, (err, scale)
     assert (out16.double() - ref).abs().max().item() <= 2e-3 * scale
+    _lib.set_gemm_pair_mode(1)
 
 
 def test_gemm_epilogue_tanh_beta_alpha_strided():

@@ -4,7 +4,7 @@ cd "$(dirname "$0")/.."
 TAG=$1; O=gpurun_out; mkdir -p $O
 NCU="ncu --clock-control none"
 # launch list of one eager training step (cold-cache, serialised: shares only)
-FT_GRAPH=0 FT_BWD_COOP=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $O/${TAG}_launches.csv python bench.py --profile --steps 1 --warmup 1 > $O/${TAG}_launches.log 2>&1
+FT_GRAPH=0 FT_BWD_COOP=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 3200 --csv --log-file $O/${TAG}_launches.csv python bench.py --profile --steps 1 --warmup 1 > $O/${TAG}_launches.log 2>&1
 echo "launch list rc=$?"
 cap() { # name kernel-regex skip env... -- cmd
   local name=$1 regex=$2 skip=$3; shift 3
@@ -20,6 +20,8 @@ cap lstm_bwd4 "lstm_bwd4_kernel" 1 FT_GRAPH=0 FT_PIPE_FWD=0 FT_PIPE_BWD=0 FT_BWD
 cap gemm "gemm2_kernel" 12 FT_GRAPH=0 -- python bench.py --profile --steps 1 --warmup 1
 cap attn_fwd "attn_fwd_kernel" 1 FT_GRAPH=0 -- python bench.py --profile --steps 1 --warmup 1
 cap attn_bwd "attn_bwd_kernel" 1 FT_GRAPH=0 -- python bench.py --profile --steps 1 --warmup 1
+cap enc_bilstm_fwd "enc_bilstm_fwd_kernel" 1 FT_GRAPH=0 -- python bench.py --profile --steps 1 --warmup 1
+cap enc_bilstm_bwd "enc_bilstm_bwd_kernel" 1 FT_GRAPH=0 -- python bench.py --profile --steps 1 --warmup 1
 cap mel_fused "mel_fused_kernel" 1 X=1 -- python bench.py --workload mel --utterances 2000 --profile --steps 1 --warmup 1
 cap infer "infer_kernel" 1 X=1 -- python bench.py --workload infer --frames 100 --profile --steps 1 --warmup 1
 ls -la $O/${TAG}_ncu_* | head -30
