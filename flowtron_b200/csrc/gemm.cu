@@ -36,6 +36,8 @@ struct GemmParams {
     float* C32; long long ldc32;
     void* C16; long long ldc16; int c16_fmt;   // 0 f16, 1 bf16
     int* status;
+    int tma_out = 0;           // 1: C32, 2: C16 leave through TMA stores of 32-row staging tiles (no beta / split-K), 0: per-lane stores
+    int dbg = 0;               // FT_GEMM_EPI_DEBUG (measurement only): 1 = epilogue reads TMEM but stores nothing, 2 = stores without reading TMEM, 3 = neither
     int splitk = 1;            // v2 only: K is cut into `splitk` ranges, partial tiles are atomically added into a zeroed C32
 };
 
@@ -48,7 +50,9 @@ struct GemmParams {
 //     accumulates tile i+1, so the epilogue (and the per-CTA start-up v1 paid on every tile) leaves the critical path;
 //   * epilogue: tcgen05.ld 32 columns -> a 32x36 shared-memory transpose per warp -> float4 per lane, 4 rows x 128 contiguous
 //     bytes per warp instruction, all loads of a chunk hoisted in front of the arithmetic (details at the epilogue).
-constexpr int G2_THREADS = 192;
+constexpr int G2_THREADS = 320;                                 // w0 TMA producer, w1 MMA issuer, w2..w9 epilogue (two per TMEM lane quadrant)
+constexpr int G2_EPI_WARPS = 8;
+constexpr int G2_OUT_TILE = 32 * 128;                          // output staging tile: 32 rows x 128 bytes (32 fp32 or 64 16-bit columns)
 constexpr int G2_PITCH = 36;                                   // floats: 16-byte aligned rows, conflict-free float4 access
 constexpr int G2_STAGE_FLOATS = 32 * G2_PITCH;                 // per-warp transpose tile
 // NCTA = 2 (BN = 256 only): a CTA PAIR (2-CTA cluster, tcgen05 cta_group::2) owns a 256 x 256 tile.  Each CTA stages its own 128
@@ -58,12 +62,13 @@ constexpr int G2_STAGE_FLOATS = 32 * G2_PITCH;                 // per-warp trans
 template <int BN_, int NCTA = 1> struct G2Cfg {
     static constexpr int STAGE_BYTES = (BM + BN_ / NCTA) * 128;
     static constexpr int STAGES = (BN_ == 256 && NCTA == 1) ? 4 : 6;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 4 * G2_STAGE_FLOATS * 4 + 256 + 1024;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + G2_EPI_WARPS * G2_OUT_TILE + 256 + 1024;     // + one 4 KB output staging tile per epilogue warp
 };
 
 template <bool kTf32, int BN_, int NCTA = 1>
 __global__ void __launch_bounds__(G2_THREADS, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p, int tiles_n, int n_tiles) {
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+             GemmParams p, int tiles_n, int n_tiles) {
     using C = G2Cfg<BN_, NCTA>;
     constexpr int TM = BM * NCTA;                   // rows of a work item's tile
     const int rank = NCTA == 2 ? static_cast<int>(cluster_ctarank()) : 0;
@@ -72,12 +77,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     constexpr int ST = C::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* stage_all = reinterpret_cast<float*>(smem + ST * C::STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + 4 * G2_STAGE_FLOATS);
+    uint8_t* out_stage = smem + ST * C::STAGE_BYTES;              // [8 epilogue warps][G2_OUT_TILE] (1024-byte aligned)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + G2_EPI_WARPS * G2_OUT_TILE);
     uint64_t* full = bars;                 // [ST]
     uint64_t* empty = bars + ST;           // [ST]
     uint64_t* tfull = bars + 2 * ST;       // [2] accumulator ready
-    uint64_t* tempty = bars + 2 * ST + 2;  // [2] accumulator drained (4 arrivals: one per epilogue warp)
+    uint64_t* tempty = bars + 2 * ST + 2;  // [2] accumulator drained (one arrival per epilogue warp of the pair / CTA)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -91,9 +96,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (p.tma_out) tma_prefetch_desc(&tmC);
         for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
-        mbar_init(&tempty[0], 4 * NCTA); mbar_init(&tempty[1], 4 * NCTA);
+        mbar_init(&tempty[0], G2_EPI_WARPS * NCTA); mbar_init(&tempty[1], G2_EPI_WARPS * NCTA);
         fence_mbar_init();
     }
     if (NCTA == 2) cluster_sync_all();              // the peer's barriers exist before anything can arrive on them
@@ -182,20 +188,26 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
     } else if (warp >= 2) {
         // ------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
-        // Per 32-column chunk: tcgen05.ld (lane = row) -> 32x36 shared-memory tile (16-byte vector stores, conflict-free per
-        // quarter warp) -> re-read as float4 with lane = (row within a group of 4, 4-column group): one warp instruction
-        // covers 4 rows x 128 contiguous bytes.  All global loads of a chunk (tanh' operand, beta accumulate) are issued
-        // before any arithmetic (8 independent 8/16-byte loads per lane in flight), then alpha / bias / activation and the
-        // 16-byte (fp32) / 8-byte (16-bit) stores.  The first version walked rows with scalar loads and stores (a 600-clock
-        // load latency per row iteration, 256 iterations per tile): 13-43 TFLOP/s on the K <= 640 dgrad shapes.
-        const int q = warp & 3;
-        float* stg = stage_all + q * G2_STAGE_FLOATS;
+        // Row per lane, straight from the accumulator: tcgen05.ld hands lane i row (32 q + i) x 32 consecutive columns, so the
+        // lane applies alpha / bias / activation / beta and writes its own 128 contiguous bytes with eight 16-byte stores
+        // (16-bit outputs: four 8-byte stores; the tanh' operand and the beta read come in with matching 8 / 16-byte loads, all
+        // issued before the arithmetic).  ~60 instructions per 32-column chunk and warp.  The r2 form transposed every chunk
+        // through shared memory to get 512-byte-contiguous warp stores: ~780 instructions per chunk (ncu, call 16: 24.9 k
+        // warp-instructions per 128 x 256 tile, one epilogue warp per scheduler at 0.17 IPC = 19 us per tile), which made every
+        // GEMM with K < ~3000 epilogue-bound: 32000 x 4096 x 1664 ran at 54 % of the tensor peak, 32000 x 1024 x 1024 at 31 %,
+        // while K = 4096 / 32000 shapes reached 78-90 %.  A warp store now touches 32 rows (32 L2 requests of 16 bytes instead of
+        // 4 of 128), which the LSU absorbs in ~2 k clocks per tile and warp, far below the main loop's 21 k.
+        // Eight epilogue warps, two per TMEM lane quadrant (q = warp % 4), alternate over the tile's 32-column chunks (pairs of
+        // chunks for 16-bit TMA output tiles): with one warp per scheduler the epilogue was bound by its own dependent-instruction
+        // latency (0.17 IPC per scheduler; r2 call 20: 32000 x 1024 x 1024 + tanh took 0.100 ms even with the stores removed,
+        // 0.048 ms with the arithmetic removed too).
+        const int q = warp & 3, hw = (warp - 2) >> 2;
         const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
-        const int rsub = lane >> 3, c4 = (lane & 7) * 4;
         const bool vec_ok = (p.N % 4 == 0) &&
                             (!p.C32 || (((reinterpret_cast<uintptr_t>(p.C32) & 15) == 0) && (p.ldc32 % 4 == 0))) &&
                             (!p.C16 || (((reinterpret_cast<uintptr_t>(p.C16) & 7) == 0) && (p.ldc16 % 4 == 0))) &&
-                            (p.act != 2 || (((reinterpret_cast<uintptr_t>(p.aux16) & 7) == 0) && (p.ldaux % 4 == 0)));
+                            (p.act != 2 || (((reinterpret_cast<uintptr_t>(p.aux16) & 7) == 0) && (p.ldaux % 4 == 0))) &&
+                            (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) && (!p.bias2 || (reinterpret_cast<uintptr_t>(p.bias2) & 15) == 0);
         int tc = 0;
         for (int w = wid0; w < n_work; w += wstep, ++tc) {
             const int tile = w % n_tiles;
@@ -204,109 +216,173 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             mbar_wait(&tfull[buf], bph, p.status, 114);
             tc_fence_after();
             const int ncols = min(BN_, p.N - tile_n * BN_);
-            const long long m0 = static_cast<long long>(tile_m) * TM + rank * BM + q * 32;
-            const int rows = static_cast<int>(min(static_cast<long long>(32), p.M - m0));     // may be <= 0
+            const long long m = static_cast<long long>(tile_m) * TM + rank * BM + q * 32 + lane;      // this lane's output row
+            const bool row_ok = m < p.M;
             const int nchunks = (ncols + 31) >> 5;
+            const int gsz = p.tma_out == 2 ? 2 : 1;                   // chunks per group (this warp takes groups hw, hw + 2, ...)
+            const int ngroups = (nchunks + gsz - 1) / gsz;
+            int my_last = -1;                                         // the last chunk THIS warp reads from the accumulator
+            if (ngroups > hw) { const int gl = hw + 2 * ((ngroups - 1 - hw) / 2); my_last = min(nchunks, (gl + 1) * gsz) - 1; }
 #pragma unroll 1
-            for (int c = 0; c < nchunks; ++c) {
+            for (int cc = 0; cc < nchunks; ++cc) {
+                if (((cc / gsz) & 1) != hw) continue;
+                const int c = cc;
                 float v[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN_ + c * 32, v);
-                tmem_ld_wait();
-                if (c == nchunks - 1) {                              // everything this warp needs is in registers: hand the
+                if (p.dbg == 2 || p.dbg == 3) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 1.f;
+                } else {
+                    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN_ + c * 32, v);
+                    tmem_ld_wait();
+                }
+                if (c == my_last) {                                  // everything this warp needs is in registers: hand the
                     tc_fence_before();                               // accumulator back to the MMA warp before the stores
                     if (lane == 0) { if (NCTA == 2) mbar_arrive_pair_leader(&tempty[buf]); else mbar_arrive(&tempty[buf]); }
                 }
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(stg + lane * G2_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                __syncwarp();
                 const int nb = tile_n * BN_ + c * 32;                 // first column of the chunk
-                if (vec_ok) {
-                    const int n = nb + c4;
-                    const bool col_ok = c * 32 + c4 < ncols;          // N % 4 == 0: the whole 4-group is in or out
-                    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (col_ok) {
-                        if (p.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n)); bsum = t; }
-                        if (p.bias2) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias2 + n)); bsum.x += t.x; bsum.y += t.y; bsum.z += t.z; bsum.w += t.w; }
+                const int nv = min(32, ncols - c * 32);               // valid columns of the chunk
+                if (p.tma_out && (p.dbg == 0 || p.dbg >= 4)) {
+                    // ---- TMA-store path (r2 call 18: with per-lane OR 512-byte-coalesced register stores every GEMM with K < ~3000
+                    // was STORE-bound -- 4 epilogue warps x a handful of outstanding stores each x ~1 us write latency = 3.4 B/clk/SM:
+                    // 32000 x 4096 x 1664 ran 0.56 ms with stores and 0.29 ms (1516 TFLOP/s) without).  The lane converts its row
+                    // segment, writes it into a SWIZZLE_128B staging tile (16-byte piece j of row i at piece j ^ (i & 7): conflict-free),
+                    // and one lane hands the 4 KB tile to the TMA engine; two tiles per warp alternate.
+                    const bool f32out = p.tma_out == 1;
+                    const int sub = f32out ? 0 : (c & 1);             // 16-bit outputs: two 32-column chunks share a 64-column tile
+                    uint8_t* tile_s = out_stage + (warp - 2) * G2_OUT_TILE;
+                    if (sub == 0 && p.dbg != 4 && p.dbg < 5) {         // the tile's previous store must have read it (fast: measured free)
+                        if (lane == 0) bulk_wait_read<0>();
+                        __syncwarp();
                     }
                     uint2 aux[8];
-                    float4 old[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = rsub + 4 * i;
-                        const long long m = m0 + r;
-                        aux[i] = make_uint2(0u, 0u);
-                        old[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (col_ok && r < rows) {
-                            if (p.act == 2) aux[i] = *reinterpret_cast<const uint2*>(p.aux16 + m * p.ldaux + n);
-                            if (p.beta && p.C32) old[i] = *reinterpret_cast<const float4*>(p.C32 + m * p.ldc32 + n);
-                        }
+                    for (int j = 0; j < 8; ++j) {
+                        aux[j] = make_uint2(0u, 0u);
+                        if (p.act == 2 && row_ok && 4 * j < nv) aux[j] = *reinterpret_cast<const uint2*>(p.aux16 + m * p.ldaux + nb + 4 * j);
                     }
+                    uint8_t* row_s = tile_s + lane * 128;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = rsub + 4 * i;
-                        const long long m = m0 + r;
-                        const float4 s4 = *reinterpret_cast<const float4*>(stg + r * G2_PITCH + c4);
-                        float x[4] = {fmaf(s4.x, alpha, bsum.x), fmaf(s4.y, alpha, bsum.y), fmaf(s4.z, alpha, bsum.z), fmaf(s4.w, alpha, bsum.w)};
+                    for (int j = 0; j < 8; ++j) {
+                        const int n = nb + 4 * j;
+                        float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (4 * j < nv) {
+                            if (p.bias) bsum = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                            if (p.bias2) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias2 + n)); bsum.x += t.x; bsum.y += t.y; bsum.z += t.z; bsum.w += t.w; }
+                        }
+                        float x[4] = {fmaf(v[4 * j], alpha, bsum.x), fmaf(v[4 * j + 1], alpha, bsum.y), fmaf(v[4 * j + 2], alpha, bsum.z), fmaf(v[4 * j + 3], alpha, bsum.w)};
                         if (p.act == 1) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) x[j] = tanh_f(x[j]);
+                            for (int e = 0; e < 4; ++e) x[e] = tanh_f(x[e]);
                         } else if (p.act == 2) {
-                            const __half2* h = reinterpret_cast<const __half2*>(&aux[i]);
+                            const __half2* h = reinterpret_cast<const __half2*>(&aux[j]);
                             const float2 y0 = __half22float2(h[0]), y1 = __half22float2(h[1]);
                             x[0] *= (1.f - y0.x * y0.x); x[1] *= (1.f - y0.y * y0.y); x[2] *= (1.f - y1.x * y1.x); x[3] *= (1.f - y1.y * y1.y);
                         }
-                        if (p.beta) { x[0] += old[i].x; x[1] += old[i].y; x[2] += old[i].z; x[3] += old[i].w; }
-                        if (col_ok && r < rows) {
-                            if (p.C32) {
-                                if (p.splitk > 1) atomicAdd(reinterpret_cast<float4*>(p.C32 + m * p.ldc32 + n), make_float4(x[0], x[1], x[2], x[3]));
-                                else *reinterpret_cast<float4*>(p.C32 + m * p.ldc32 + n) = make_float4(x[0], x[1], x[2], x[3]);
+                        if (f32out) {
+                            *reinterpret_cast<float4*>(row_s + ((j ^ (lane & 7)) << 4)) = make_float4(x[0], x[1], x[2], x[3]);
+                        } else {
+                            uint2 pk;
+                            if (p.c16_fmt == 0) {
+                                const __half2 h0 = __floats2half2_rn(fminf(fmaxf(x[0], -65504.f), 65504.f), fminf(fmaxf(x[1], -65504.f), 65504.f));
+                                const __half2 h1 = __floats2half2_rn(fminf(fmaxf(x[2], -65504.f), 65504.f), fminf(fmaxf(x[3], -65504.f), 65504.f));
+                                pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                            } else {
+                                const __nv_bfloat162 h0 = __floats2bfloat162_rn(x[0], x[1]), h1 = __floats2bfloat162_rn(x[2], x[3]);
+                                pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
                             }
-                            if (p.C16) {
-                                uint2 pk;
-                                if (p.c16_fmt == 0) {      // fp16: saturate instead of overflowing to inf
-                                    const __half2 h0 = __floats2half2_rn(fminf(fmaxf(x[0], -65504.f), 65504.f), fminf(fmaxf(x[1], -65504.f), 65504.f));
-                                    const __half2 h1 = __floats2half2_rn(fminf(fmaxf(x[2], -65504.f), 65504.f), fminf(fmaxf(x[3], -65504.f), 65504.f));
-                                    pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-                                } else {
-                                    const __nv_bfloat162 h0 = __floats2bfloat162_rn(x[0], x[1]), h1 = __floats2bfloat162_rn(x[2], x[3]);
-                                    pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                            // 8-byte piece j of this chunk = half of 16-byte piece (4 sub + j / 2) of the 64-column row
+                            *reinterpret_cast<uint2*>(row_s + (((4 * sub + (j >> 1)) ^ (lane & 7)) << 4) + ((j & 1) << 3)) = pk;
+                        }
+                    }
+                    if (f32out || sub == 1 || c == nchunks - 1) {
+                        if (p.dbg < 6) fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && p.dbg < 5) {
+                            tma_store_2d(&tmC, tile_s, f32out ? nb : nb - 32 * sub, static_cast<int>(m - lane));
+                            bulk_commit();
+                        }
+                    }
+                } else if (p.dbg == 1 || p.dbg == 3) {                // measurement only: keep the loads alive, store nothing
+                    float sacc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sacc += v[j];
+                    if (sacc == 1.2345e-30f && p.C32) p.C32[0] = sacc;
+                } else if (vec_ok) {
+                    uint2 aux[8];
+                    float4 old[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        aux[j] = make_uint2(0u, 0u);
+                        old[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row_ok && 4 * j < nv) {
+                            if (p.act == 2) aux[j] = *reinterpret_cast<const uint2*>(p.aux16 + m * p.ldaux + nb + 4 * j);
+                            if (p.beta && p.C32) old[j] = *reinterpret_cast<const float4*>(p.C32 + m * p.ldc32 + nb + 4 * j);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (4 * j < nv) {                              // N % 4 == 0: a 4-group is in or out as a whole
+                            const int n = nb + 4 * j;
+                            float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.bias) bsum = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                            if (p.bias2) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias2 + n)); bsum.x += t.x; bsum.y += t.y; bsum.z += t.z; bsum.w += t.w; }
+                            float x[4] = {fmaf(v[4 * j], alpha, bsum.x), fmaf(v[4 * j + 1], alpha, bsum.y), fmaf(v[4 * j + 2], alpha, bsum.z), fmaf(v[4 * j + 3], alpha, bsum.w)};
+                            if (p.act == 1) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) x[e] = tanh_f(x[e]);
+                            } else if (p.act == 2) {
+                                const __half2* h = reinterpret_cast<const __half2*>(&aux[j]);
+                                const float2 y0 = __half22float2(h[0]), y1 = __half22float2(h[1]);
+                                x[0] *= (1.f - y0.x * y0.x); x[1] *= (1.f - y0.y * y0.y); x[2] *= (1.f - y1.x * y1.x); x[3] *= (1.f - y1.y * y1.y);
+                            }
+                            if (p.beta) { x[0] += old[j].x; x[1] += old[j].y; x[2] += old[j].z; x[3] += old[j].w; }
+                            if (row_ok) {
+                                if (p.C32) {
+                                    if (p.splitk > 1) atomicAdd(reinterpret_cast<float4*>(p.C32 + m * p.ldc32 + n), make_float4(x[0], x[1], x[2], x[3]));
+                                    else *reinterpret_cast<float4*>(p.C32 + m * p.ldc32 + n) = make_float4(x[0], x[1], x[2], x[3]);
                                 }
-                                *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.C16) + m * p.ldc16 + n) = pk;
+                                if (p.C16) {
+                                    uint2 pk;
+                                    if (p.c16_fmt == 0) {      // fp16: saturate instead of overflowing to inf
+                                        const __half2 h0 = __floats2half2_rn(fminf(fmaxf(x[0], -65504.f), 65504.f), fminf(fmaxf(x[1], -65504.f), 65504.f));
+                                        const __half2 h1 = __floats2half2_rn(fminf(fmaxf(x[2], -65504.f), 65504.f), fminf(fmaxf(x[3], -65504.f), 65504.f));
+                                        pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                                    } else {
+                                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(x[0], x[1]), h1 = __floats2bfloat162_rn(x[2], x[3]);
+                                        pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                                    }
+                                    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.C16) + m * p.ldc16 + n) = pk;
+                                }
                             }
                         }
                     }
                 } else {
-                    // unaligned / N % 4 != 0 outputs: lane = column, one row per iteration (rare: no shape on the hot path)
-                    const int n = nb + lane;
-                    const bool col_ok = c * 32 + lane < ncols;
-                    float bsum = 0.f;
-                    if (col_ok) {
-                        if (p.bias) bsum += __ldg(p.bias + n);
-                        if (p.bias2) bsum += __ldg(p.bias2 + n);
-                    }
-                    for (int r = 0; r < rows; ++r) {
-                        const long long m = m0 + r;
-                        float x = fmaf(stg[r * G2_PITCH + lane], alpha, bsum);
-                        if (p.act == 1) x = tanh_f(x);
-                        if (col_ok) {
-                            if (p.act == 2) { const float y = __half2float(p.aux16[m * p.ldaux + n]); x *= (1.f - y * y); }
-                            if (p.C32) {
-                                float* dst = p.C32 + m * p.ldc32 + n;
-                                if (p.beta) x += *dst;
-                                *dst = x;
-                            }
-                            if (p.C16) {
-                                if (p.c16_fmt == 0) reinterpret_cast<__half*>(p.C16)[m * p.ldc16 + n] = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
-                                else reinterpret_cast<__nv_bfloat16*>(p.C16)[m * p.ldc16 + n] = __float2bfloat16_rn(x);
+                    // unaligned / N % 4 != 0 outputs: scalar walk over the lane's row (rare: no shape on the hot path)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {                   // fully unrolled: v[] must stay in registers
+                        const int n = nb + j;
+                        if (j < nv) {
+                            float x = fmaf(v[j], alpha, (p.bias ? __ldg(p.bias + n) : 0.f) + (p.bias2 ? __ldg(p.bias2 + n) : 0.f));
+                            if (p.act == 1) x = tanh_f(x);
+                            if (row_ok) {
+                                if (p.act == 2) { const float y = __half2float(p.aux16[m * p.ldaux + n]); x *= (1.f - y * y); }
+                                if (p.C32) {
+                                    float* dst = p.C32 + m * p.ldc32 + n;
+                                    if (p.splitk > 1) atomicAdd(dst, x);
+                                    else { if (p.beta) x += *dst; *dst = x; }
+                                }
+                                if (p.C16) {
+                                    if (p.c16_fmt == 0) reinterpret_cast<__half*>(p.C16)[m * p.ldc16 + n] = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+                                    else reinterpret_cast<__nv_bfloat16*>(p.C16)[m * p.ldc16 + n] = __float2bfloat16_rn(x);
+                                }
                             }
                         }
                     }
                 }
-                __syncwarp();
             }
-            if (nchunks == 0) { tc_fence_before(); if (lane == 0) { if (NCTA == 2) mbar_arrive_pair_leader(&tempty[buf]); else mbar_arrive(&tempty[buf]); } }
+            if (my_last < 0) { tc_fence_before(); if (lane == 0) { if (NCTA == 2) mbar_arrive_pair_leader(&tempty[buf]); else mbar_arrive(&tempty[buf]); } }
         }
+        if (p.tma_out && lane == 0) bulk_wait_all();      // the staging tiles must outlive their stores
     }
     tc_fence_before();
     __syncthreads();
@@ -371,6 +447,27 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
     p.bias = g.bias; p.bias2 = g.bias2; p.act = g.act; p.alpha_ptr = g.alpha_ptr; p.aux16 = static_cast<const __half*>(g.aux16); p.ldaux = g.ldaux; p.beta = g.beta; p.alpha = g.alpha;
     p.C32 = g.C32; p.ldc32 = g.ldc32; p.C16 = g.C16; p.ldc16 = g.ldc16; p.c16_fmt = g.c16_fmt;
     p.status = ft_status_word();
+    // output through TMA stores when there is exactly one output tensor, nothing is accumulated into it and it is TMA-addressable
+    CUtensorMap tmC = tmA;
+    {
+        static int tma_env = -1;
+        if (tma_env < 0) { const char* e = getenv("FT_GEMM_TMA_STORE"); tma_env = (!e || atoi(e) != 0) ? 1 : 0; }
+        const bool one = (g.C32 != nullptr) != (g.C16 != nullptr);
+        const bool plain = !g.beta && (g.N % 4 == 0) && (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) &&
+                           (!g.bias2 || (reinterpret_cast<uintptr_t>(g.bias2) & 15) == 0) &&
+                           (g.act != 2 || (((reinterpret_cast<uintptr_t>(g.aux16) & 7) == 0) && (g.ldaux % 4 == 0)));
+        if (tma_env && one && plain) {
+            const void* cp = g.C32 ? static_cast<const void*>(g.C32) : g.C16;
+            const long long ldc = g.C32 ? g.ldc32 : g.ldc16;
+            const int elt_c = g.C32 ? 4 : 2;
+            if ((reinterpret_cast<uintptr_t>(cp) & 15) == 0 && ((ldc * elt_c) & 15) == 0) {
+                const int fmt_c = g.C32 ? 2 : g.c16_fmt;
+                if (make_tmap_2d(&tmC, cp, fmt_c, g.M, g.N, ldc, 128 / elt_c, 32)) return -1;
+                p.tma_out = g.C32 ? 1 : 2;
+            }
+        }
+    }
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FT_GEMM_EPI_DEBUG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
     {
         static int sms = 0;
         if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
@@ -392,6 +489,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
             if (splitk > 16) splitk = 16;
             while (splitk > 1 && num_kb_all / splitk < 16) --splitk;
         }
+        if (splitk > 1) p.tma_out = 0;              // partial tiles are added atomically
         if (splitk > 1) {
             if (cudaMemsetAsync(g.C32, 0, sizeof(float) * static_cast<size_t>(g.M) * g.N, st) != cudaSuccess) return ft_set_error("gemm: memset failed");
         }
@@ -420,8 +518,8 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
             attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;
             TimeScope ts(g.a_mn ? "gemm_wgrad" : (g.b_mn ? "gemm_dgrad" : "gemm_fwd"), g.M, g.N, g.K, st);
-            cudaError_t e = tf32 ? cudaLaunchKernelEx(&cfg, gemm2_kernel<true, 256, 2>, tmA, tmB, p, tiles_n, n_tiles2)
-                                 : cudaLaunchKernelEx(&cfg, gemm2_kernel<false, 256, 2>, tmA, tmB, p, tiles_n, n_tiles2);
+            cudaError_t e = tf32 ? cudaLaunchKernelEx(&cfg, gemm2_kernel<true, 256, 2>, tmA, tmB, tmC, p, tiles_n, n_tiles2)
+                                 : cudaLaunchKernelEx(&cfg, gemm2_kernel<false, 256, 2>, tmA, tmB, tmC, p, tiles_n, n_tiles2);
             if (e != cudaSuccess) return ft_set_error(cudaGetErrorString(e));
             ft_count_launch(1);
             return ft_check_launch("gemm2_kernel<pair>");
@@ -440,11 +538,11 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
         }
         TimeScope ts(g.a_mn ? "gemm_wgrad" : (g.b_mn ? "gemm_dgrad" : "gemm_fwd"), g.M, g.N, g.K, st);
         if (tf32) {
-            if (wide) gemm2_kernel<true, 256><<<grid2, G2_THREADS, G2Cfg<256>::SMEM, st>>>(tmA, tmB, p, tiles_n, n_tiles);
-            else      gemm2_kernel<true, 128><<<grid2, G2_THREADS, G2Cfg<128>::SMEM, st>>>(tmA, tmB, p, tiles_n, n_tiles);
+            if (wide) gemm2_kernel<true, 256><<<grid2, G2_THREADS, G2Cfg<256>::SMEM, st>>>(tmA, tmB, tmC, p, tiles_n, n_tiles);
+            else      gemm2_kernel<true, 128><<<grid2, G2_THREADS, G2Cfg<128>::SMEM, st>>>(tmA, tmB, tmC, p, tiles_n, n_tiles);
         } else {
-            if (wide) gemm2_kernel<false, 256><<<grid2, G2_THREADS, G2Cfg<256>::SMEM, st>>>(tmA, tmB, p, tiles_n, n_tiles);
-            else      gemm2_kernel<false, 128><<<grid2, G2_THREADS, G2Cfg<128>::SMEM, st>>>(tmA, tmB, p, tiles_n, n_tiles);
+            if (wide) gemm2_kernel<false, 256><<<grid2, G2_THREADS, G2Cfg<256>::SMEM, st>>>(tmA, tmB, tmC, p, tiles_n, n_tiles);
+            else      gemm2_kernel<false, 128><<<grid2, G2_THREADS, G2Cfg<128>::SMEM, st>>>(tmA, tmB, tmC, p, tiles_n, n_tiles);
         }
         ft_count_launch(1);
         return ft_check_launch("gemm2_kernel");

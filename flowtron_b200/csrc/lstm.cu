@@ -31,7 +31,7 @@
 
 namespace ft {
 
-#define FT_TRACE(p, t, slot) do { if ((p).trace && blockIdx.x == 0) (p).trace[(t) * 8 + (slot)] = clock64(); } while (0)
+#define FT_TRACE(p, t, slot) do { if ((p).trace && blockIdx.x == 0) (p).trace[(t) * 16 + (slot)] = clock64(); } while (0)
 static long long* g_lstm_trace = nullptr;      // set through ft_debug_set_lstm_trace
 void set_lstm_trace(long long* p) { g_lstm_trace = p; }
 
@@ -774,6 +774,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     tc_fence_before();
                 }
                 epi_bar();
+                if (et == 0) FT_TRACE(p, t, 8);               // accumulator transposed into shared memory
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     const int item = et + s * EPI_THREADS;
@@ -806,8 +807,10 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     *reinterpret_cast<__half2*>(p.hseq + r * p.ldh + u0 + 2 * up) = h2;     // critical path: h_t first
                 }
             }
+            if (et == 0) FT_TRACE(p, t, 9);                   // cell computed, h_t stores issued
             epi_bar();                                        // all h_t stores of this CTA precede the release
             if (et == 0) {
+                FT_TRACE(p, t, 10);
                 red_release_add(&p.flags[(t - p.t0) * FWD_NCH + cta / FWD_PROD], 1);      // cumulative release (gpu scope)
                 FT_TRACE(p, t, 7);
             }

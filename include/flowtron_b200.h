@@ -49,7 +49,7 @@ int ft_gemm(int M, int N, int K, const void* A, long long lda, int a_fmt, int a_
 int ft_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const int* lens, void* hseq16, long long ldh,
                 void* gates16, float* cstate, float* h32, long long ldh32, int* flags, void* stream);
 
-/* debug/profiling: device buffer [T][8] that receives clock64 stamps of CTA 0 of later ft_lstm_fwd launches */
+/* debug/profiling: device buffer [T][16] that receives clock64 stamps of CTA 0 of later ft_lstm_fwd launches */
 void ft_debug_set_lstm_trace(long long* buf);
 /* same for ft_ar_step_infer: [T][32] stamps of CTA 0 (phase boundaries, tools/trace_infer.py) */
 void ft_debug_set_infer_trace(long long* buf);

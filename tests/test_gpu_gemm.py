@@ -68,6 +68,14 @@ def test_gemm_matches_fp64(M, N, K, dt, a_mn, b_mn, pair_mode):
     tol = 2e-3 if dt == torch.float32 else 1e-4      # tf32 truncates fp32 inputs; 16-bit inputs are exact
     assert err <= tol * scale, (err, scale)
     assert (out16.double() - ref).abs().max().item() <= 2e-3 * scale
+    # a single output tensor leaves through TMA stores of staged tiles (the two-output call above uses per-lane stores)
+    only32 = torch.full((M, N), float("nan"), device="cuda")
+    only16 = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+    _lib.gemm(A, B, a_mn=a_mn, b_mn=b_mn, bias=bias, out32=only32)
+    _lib.gemm(A, B, a_mn=a_mn, b_mn=b_mn, bias=bias, out16=only16)
+    torch.cuda.synchronize()
+    assert _lib.device_status() == 0
+    assert torch.equal(only32, out32) and torch.equal(only16, out16)
     _lib.set_gemm_pair_mode(1)
 
 

@@ -13,7 +13,7 @@ def main():
     hseq = torch.zeros(T, B, H, device="cuda", dtype=torch.float16)
     gates = torch.zeros(T, B, 4 * H, device="cuda", dtype=torch.float16)
     cst = torch.zeros(T, B, H, device="cuda")
-    trace = torch.zeros(T, 8, dtype=torch.int64, device="cuda")
+    trace = torch.zeros(T, 16, dtype=torch.int64, device="cuda")
     L = _lib.lib()
     L.ft_debug_set_lstm_trace.argtypes = [ctypes.c_void_p]
     for it in range(3):
@@ -27,7 +27,8 @@ def main():
         print(f"run {it}: {e0.elapsed_time(e1) * 1e3 / T:.2f} us/step")
     L.ft_debug_set_lstm_trace(None)
     report(trace, T, "forward", ["flags_seen", "tma_issued", "first_group_landed", "all_mma_issued", "accum_done(epi)",
-                                 "last_group_landed", "proxy_fence_done", "release_issued"])
+                                 "last_group_landed", "proxy_fence_done", "release_issued",
+                                 "acc_in_smem(epi)", "cell_done_h_stored", "epi_barrier_done"])
     # ---- backward
     w = torch.randn(T, B, H, generator=g).cuda()
     dG = torch.zeros(T, B, 4 * H, device="cuda", dtype=torch.float16)
