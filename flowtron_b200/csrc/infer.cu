@@ -79,11 +79,6 @@ constexpr uint32_t SENT = 0xFFFFFFFFu;
 constexpr int NREP = 1;                        // replicas of the all-to-all exchanged tensors (CTA c reads replica c % NREP); r2 call 11: 8 replicas
                                                // (to spread the 128-CTA reads of the same lines over more L2 slices) were SLOWER: 26.6 -> 29.9 us/frame
 #define SL(ptr, k) (reinterpret_cast<decltype(ptr)>(reinterpret_cast<char*>(ptr) + (k)))     /* ring slot: k = slot index * slot_bytes */
-__device__ __forceinline__ uint4 ld_rlx_v4(const void* p) {
-    uint4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ uint32_t ld_rlx_u32(const void* p) {
     uint32_t v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -99,17 +94,6 @@ __device__ __forceinline__ void st_rlx_h2(__half* p, float a, float b) {
 }
 // any fp16 element of the 16-byte packet still the sentinel?
 __device__ __forceinline__ bool sent16(const uint4& v) { return (__vcmpeq2(v.x, SENT) | __vcmpeq2(v.y, SENT) | __vcmpeq2(v.z, SENT) | __vcmpeq2(v.w, SENT)) != 0u; }
-__device__ __forceinline__ uint4 poll16(const void* g, int* status, int code) {
-    uint4 v = ld_rlx_v4(g);
-    if (sent16(v)) {
-        const long long t0 = clock64();
-        do {
-            v = ld_rlx_v4(g);
-            if (clock64() - t0 > FT_WATCHDOG_CYCLES) watchdog_fail(status, code);
-        } while (sent16(v));
-    }
-    return v;
-}
 __device__ __forceinline__ float poll_f32(const float* g, int* status, int code) {
     uint32_t v = ld_rlx_u32(g);
     if (v == SENT) {
