@@ -158,6 +158,12 @@ def _declare(L):
     L.ft_encoder_bwd.argtypes = [POINTER(FtEncoderDesc), POINTER(FtEncoderWeights), c_void_p, c_longlong, c_longlong, c_void_p,
                                  c_void_p, POINTER(FtEncoderGrads), c_void_p, c_void_p]
     L.ft_encoder_bwd.restype = c_int
+    L.ft_encoder_fwd_tokens.argtypes = [POINTER(FtEncoderDesc), POINTER(FtEncoderWeights), c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                        c_void_p, c_longlong, c_longlong, c_void_p, c_void_p, c_void_p]
+    L.ft_encoder_fwd_tokens.restype = c_int
+    L.ft_encoder_bwd_tokens.argtypes = [POINTER(FtEncoderDesc), POINTER(FtEncoderWeights), c_void_p, c_longlong, c_longlong, c_void_p,
+                                        c_void_p, c_int, c_void_p, POINTER(FtEncoderGrads), c_void_p, c_void_p]
+    L.ft_encoder_bwd_tokens.restype = c_int
 
 
 def check(rc: int, what: str = ""):
@@ -469,28 +475,40 @@ def _enc_struct(cls, prefix, tensors):
     return st
 
 
-def encoder_fwd(desc, params, x, in_lens_i32, rng_state, out, out_stride_b, out_stride_l):
-    """ft_encoder_fwd.  params: dict name -> list of fp32 CUDA tensors (ENC_PARAM_FIELDS).  Returns the `saved` buffer."""
-    _need_cuda(x, out)
+def encoder_fwd(desc, params, x, in_lens_i32, rng_state, out, out_stride_b, out_stride_l, tokens=None, emb_weight=None):
+    """ft_encoder_fwd (x [B,512,L] given) or ft_encoder_fwd_tokens (tokens int64 [B,L] + embedding weight).  params: dict name ->
+    list of fp32 CUDA tensors (ENC_PARAM_FIELDS).  Returns the `saved` buffer."""
+    _need_cuda(x if tokens is None else tokens, out)
     L = lib()
-    saved = torch.empty(L.ft_encoder_saved_bytes(byref(desc)), dtype=torch.uint8, device=x.device)
-    scratch = torch.empty(L.ft_encoder_fwd_scratch_bytes(byref(desc)), dtype=torch.uint8, device=x.device)
+    saved = torch.empty(L.ft_encoder_saved_bytes(byref(desc)), dtype=torch.uint8, device=out.device)
+    scratch = torch.empty(L.ft_encoder_fwd_scratch_bytes(byref(desc)), dtype=torch.uint8, device=out.device)
     w = _enc_struct(FtEncoderWeights, "", params)
-    check(L.ft_encoder_fwd(byref(desc), byref(w), ptr(x), ptr(in_lens_i32), ptr(rng_state), ptr(out), out_stride_b, out_stride_l,
-                           ptr(saved), ptr(scratch), stream_ptr()), "ft_encoder_fwd")
+    if tokens is None:
+        check(L.ft_encoder_fwd(byref(desc), byref(w), ptr(x), ptr(in_lens_i32), ptr(rng_state), ptr(out), out_stride_b, out_stride_l,
+                               ptr(saved), ptr(scratch), stream_ptr()), "ft_encoder_fwd")
+    else:
+        check(L.ft_encoder_fwd_tokens(byref(desc), byref(w), ptr(tokens), ptr(emb_weight), emb_weight.size(0), ptr(in_lens_i32),
+                                      ptr(rng_state), ptr(out), out_stride_b, out_stride_l, ptr(saved), ptr(scratch), stream_ptr()),
+              "ft_encoder_fwd_tokens")
     return saved
 
 
-def encoder_bwd(desc, params, d_out, saved, need_dx=True):
-    """ft_encoder_bwd.  Returns (d_x [B,512,L] or None, dict of gradient tensors like `params`)."""
+def encoder_bwd(desc, params, d_out, saved, need_dx=True, tokens=None, emb_weight=None):
+    """ft_encoder_bwd / ft_encoder_bwd_tokens.  Returns (d_x [B,512,L] -- or d_emb_weight in the token form -- or None, dict of
+    gradient tensors like `params`)."""
     _need_cuda(d_out, saved)
     L = lib()
     dev = d_out.device
     grads = {n: [torch.empty_like(t) for t in params[n]] for n, _ in ENC_PARAM_FIELDS}
-    d_x = torch.empty(desc.B, 512, desc.L, dtype=torch.float32, device=dev) if need_dx else None
     scratch = torch.empty(L.ft_encoder_bwd_scratch_bytes(byref(desc)), dtype=torch.uint8, device=dev)
     w = _enc_struct(FtEncoderWeights, "", params)
     g = _enc_struct(FtEncoderGrads, "d_", grads)
-    check(L.ft_encoder_bwd(byref(desc), byref(w), ptr(d_out), d_out.stride(0), d_out.stride(1), ptr(saved), ptr(d_x), byref(g),
-                           ptr(scratch), stream_ptr()), "ft_encoder_bwd")
-    return d_x, grads
+    if tokens is None:
+        d_x = torch.empty(desc.B, 512, desc.L, dtype=torch.float32, device=dev) if need_dx else None
+        check(L.ft_encoder_bwd(byref(desc), byref(w), ptr(d_out), d_out.stride(0), d_out.stride(1), ptr(saved), ptr(d_x), byref(g),
+                               ptr(scratch), stream_ptr()), "ft_encoder_bwd")
+        return d_x, grads
+    d_emb = torch.empty_like(emb_weight)
+    check(L.ft_encoder_bwd_tokens(byref(desc), byref(w), ptr(d_out), d_out.stride(0), d_out.stride(1), ptr(saved), ptr(tokens),
+                                  emb_weight.size(0), ptr(d_emb), byref(g), ptr(scratch), stream_ptr()), "ft_encoder_bwd_tokens")
+    return d_emb, grads

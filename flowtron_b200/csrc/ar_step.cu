@@ -257,17 +257,30 @@ static void join_side(Side* sd, cudaStream_t main) {
 
 // Streams of the experimental layer pipeline: sB runs the second recurrence, sC its per-chunk input-projection GEMMs.
 struct Pipe {
-    cudaStream_t sB = nullptr, sC = nullptr;
-    cudaEvent_t evA = nullptr, evG = nullptr, evB = nullptr, ev0 = nullptr;
+    cudaStream_t sA = nullptr, sB = nullptr, sC = nullptr;      // sA / sB: HIGH-priority streams of the two recurrences, sC: their GEMMs
+    cudaEvent_t evA = nullptr, evG = nullptr, evB = nullptr, ev0 = nullptr, evJ = nullptr;
 };
+// FT_PIPE_PRIO (default 1): the chunk kernels of the pipelined recurrences are launched on high-priority streams, so that when a
+// chunk ends its 64 SMs go to the next chunk (a cooperative launch that needs all of them at once) and not to queued CTAs of the
+// GEMM / attention kernels that share the machine.
+static bool pipe_prio() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FT_PIPE_PRIO"); v = (!e || atoi(e) != 0) ? 1 : 0; }
+    return v == 1;
+}
 static std::map<cudaStream_t, Pipe> g_pipes;
 static Pipe* get_pipe(cudaStream_t main) {
     std::lock_guard<std::mutex> lk(g_side_mu);
     auto it = g_pipes.find(main);
     if (it != g_pipes.end()) return &it->second;
     Pipe pp;
-    if (cudaStreamCreateWithFlags(&pp.sB, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);            // hi is numerically smaller
+    const int pr = pipe_prio() ? prio_hi : prio_lo;
+    if (cudaStreamCreateWithPriority(&pp.sA, cudaStreamNonBlocking, pr) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithPriority(&pp.sB, cudaStreamNonBlocking, pr) != cudaSuccess) return nullptr;
     if (cudaStreamCreateWithFlags(&pp.sC, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&pp.evJ, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&pp.evA, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&pp.evG, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&pp.evB, cudaEventDisableTiming);
@@ -321,17 +334,18 @@ int ar_step_fwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
     FT_TRY(launch_prep_mel(mel, out_lens, n.T, n.B, n.M, d.reversed, S.mel_in16, S.mel_flow, st));
     const float* mel_flow = d.reversed ? S.mel_flow : mel;
 
-    // Attention-LSTM / attention overlap (OFF by default, FT_ATT_OVERLAP=N enables it with chunks of N steps, N % 64 == 0; measured
-    // r2 call 12 on B200, B=32, T=1000: 53.1 ms/step with N=128 against 51.1 serial -- the 64-CTA chunked recurrence with a separate
-    // projection GEMM and the chunk launches cost more than hiding 1.6 ms of attention + GEMMs per flow gains): the attention
-    // LSTM runs as a 64-CTA recurrence in chunks of 128 steps; as soon as a chunk's h is there, a second stream runs that chunk's
-    // query projection, fused attention, gate logits and lstm layer 0's input projection on the 84 free SMs, underneath the next
-    // chunk's recurrence.  Only the last chunk's share of that work stays exposed (r2: attention 0.93 ms + GEMMs 0.7 ms per flow
-    // were serial).  The 64-CTA kernel has no room for the folded 80-channel projection next to its 128 KB weight slice, so the
-    // projection is a per-chunk GEMM on a third stream, one chunk ahead.
+    // Attention-LSTM / attention overlap (FT_ATT_OVERLAP = chunk length in steps, a multiple of 64; default 256, 0 disables; B <= 32 and
+    // T >= chunk + 64): the attention LSTM runs as a 64-CTA recurrence in chunks; as soon as a chunk's h is there, a second stream
+    // runs that chunk's query projection, fused attention, gate logits and lstm layer 0's input projection on the 84 free SMs,
+    // underneath the next chunk's recurrence.  Only the last chunk's share of that work stays exposed (attention 0.95 ms + GEMMs
+    // 0.45 ms per flow were serial).  The 64-CTA kernel has no room for the folded 80-channel projection next to its 128 KB weight
+    // slice, so the projection is a per-chunk GEMM on a third stream, one chunk ahead.  Measured on B200, B=32, T=1000
+    // (r2 calls 12 / 30): chunks of 128 LOSE (53.1 vs 51.1 ms/step before the GEMM epilogue rewrite, 49.1 vs 48.6 after: every chunk
+    // boundary costs a kernel drain + launch + 128 KB weight reload on 64 SMs), chunks of 192 / 256 / 320 / 384 / 512 give
+    // 47.9 / 46.4 / 47.2 / 46.4 / 46.5 against 48.6 serial.
     static int att_chunk = -1;
-    if (att_chunk < 0) { const char* e = getenv("FT_ATT_OVERLAP"); att_chunk = e ? atoi(e) : 0; if (att_chunk % 64) att_chunk = 0; }
-    Pipe* pa = (att_chunk > 0 && F.X1 && n.B <= 32 && n.T > 2 * att_chunk) ? get_pipe(st) : nullptr;
+    if (att_chunk < 0) { const char* e = getenv("FT_ATT_OVERLAP"); att_chunk = e ? atoi(e) : 256; if (att_chunk % 64) att_chunk = 0; }
+    Pipe* pa = (att_chunk > 0 && F.X1 && n.B <= 32 && n.T >= att_chunk + 64) ? get_pipe(st) : nullptr;
     bool xproj0_done = false;
     auto attention_rows = [&](cudaStream_t s2, int t0, int t1) -> int {      // Q projection, attention, gate logits of steps [t0, t1)
         const long long r0 = static_cast<long long>(t0) * n.B, rows = static_cast<long long>(t1 - t0) * n.B;
@@ -365,20 +379,22 @@ int ar_step_fwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
             return gemm_fwd(s2, rows, G, n.M, S.mel_in16 + r0 * n.M, n.M, F.w.w_ih_a, n.M, w.attn_lstm_b_ih, w.attn_lstm_b_hh, 0,
                             F.X1 + r0 * G, G, nullptr, 0);
         };
+        cudaStream_t sr = pipe_prio() ? pa->sA : st;                 // the attention LSTM's stream
         cudaEventRecord(pa->ev0, st);
+        if (sr != st) cudaStreamWaitEvent(sr, pa->ev0, 0);
         cudaStreamWaitEvent(pa->sB, pa->ev0, 0);
         cudaStreamWaitEvent(pa->sC, pa->ev0, 0);
         FT_TRY(kv_projections(pa->sC));
-        FT_TRY(xa(st, 0, CH < n.T ? CH : n.T));
+        FT_TRY(xa(sr, 0, CH < n.T ? CH : n.T));
         for (int t0 = 0; t0 < n.T; t0 += CH) {
             const int t1 = t0 + CH < n.T ? t0 + CH : n.T;
             if (t1 < n.T) {                                            // next chunk's projection, one chunk ahead, on sB
                 FT_TRY(xa(pa->sB, t1, t1 + CH < n.T ? t1 + CH : n.T));
                 cudaEventRecord(pa->evB, pa->sB);
             }
-            FT_TRY(launch_lstm_fwd_chunk(n.T, n.B, t0, t1, F.X1, F.w.w_hh_a, out_lens, S.d16, n.D, S.gatesA, S.cA, F.flags, st, F.hA32, H));
-            cudaEventRecord(pa->evA, st);
-            if (t1 < n.T) cudaStreamWaitEvent(st, pa->evB, 0);        // the next launch on st needs its projection
+            FT_TRY(launch_lstm_fwd_chunk(n.T, n.B, t0, t1, F.X1, F.w.w_hh_a, out_lens, S.d16, n.D, S.gatesA, S.cA, F.flags, sr, F.hA32, H));
+            cudaEventRecord(pa->evA, sr);
+            if (t1 < n.T) cudaStreamWaitEvent(sr, pa->evB, 0);        // the next launch on sr needs its projection
             cudaStreamWaitEvent(pa->sC, pa->evA, 0);
             FT_TRY(attention_rows(pa->sC, t0, t1));
             const long long r0 = static_cast<long long>(t0) * n.B, rows = static_cast<long long>(t1 - t0) * n.B;
@@ -386,6 +402,7 @@ int ar_step_fwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
         }
         cudaEventRecord(pa->evG, pa->sC);
         cudaStreamWaitEvent(st, pa->evG, 0);
+        if (sr != st) { cudaEventRecord(pa->evJ, sr); cudaStreamWaitEvent(st, pa->evJ, 0); }
         xproj0_done = true;
     } else {
     // attention_lstm: the 80-channel input projection is folded into the persistent recurrence (no [R,4096] projection
@@ -413,14 +430,16 @@ int ar_step_fwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
         int* flagsA = F.flags;
         int* flagsB = F.flags + static_cast<size_t>(S_) * 16;
         if (!xproj0_done) FT_TRY(gemm_fwd(st, n.R, G, n.D, S.d16, n.D, F.w.w_ih0, n.D, w.lstm_b_ih0, w.lstm_b_hh0, 0, F.X, G, nullptr, 0));
+        cudaStream_t sr = pipe_prio() ? pp->sA : st;                 // layer 0's recurrence stream
         cudaEventRecord(pp->ev0, st);
+        if (sr != st) cudaStreamWaitEvent(sr, pp->ev0, 0);
         cudaStreamWaitEvent(pp->sB, pp->ev0, 0);
         cudaStreamWaitEvent(pp->sC, pp->ev0, 0);
         for (int t0 = 0; t0 < n.T; t0 += S_) {
             const int t1 = t0 + S_ < n.T ? t0 + S_ : n.T;
             const long long r0 = static_cast<long long>(t0) * n.B, rows = static_cast<long long>(t1 - t0) * n.B;
-            FT_TRY(launch_lstm_fwd_chunk(n.T, n.B, t0, t1, F.X, F.w.w_hh0, out_lens, S.h0_16, H, S.gates0, S.c0, flagsA, st));
-            cudaEventRecord(pp->evA, st);
+            FT_TRY(launch_lstm_fwd_chunk(n.T, n.B, t0, t1, F.X, F.w.w_hh0, out_lens, S.h0_16, H, S.gates0, S.c0, flagsA, sr));
+            cudaEventRecord(pp->evA, sr);
             cudaStreamWaitEvent(pp->sC, pp->evA, 0);
             FT_TRY(gemm_fwd(pp->sC, rows, G, H, S.h0_16 + r0 * H, H, F.w.w_ih1, H, w.lstm_b_ih1, w.lstm_b_hh1, 0,
                             F.X1 + r0 * G, G, nullptr, 0));
@@ -430,6 +449,7 @@ int ar_step_fwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
         }
         cudaEventRecord(pp->evB, pp->sB);
         cudaStreamWaitEvent(st, pp->evB, 0);
+        if (sr != st) { cudaEventRecord(pp->evJ, sr); cudaStreamWaitEvent(st, pp->evJ, 0); }
     } else {
         if (!xproj0_done) FT_TRY(gemm_fwd(st, n.R, G, n.D, S.d16, n.D, F.w.w_ih0, n.D, w.lstm_b_ih0, w.lstm_b_hh0, 0, F.X, G, nullptr, 0));
         FT_TRY(launch_lstm_fwd(n.T, n.B, F.X, F.w.w_hh0, out_lens, S.h0_16, H, S.gates0, S.c0, nullptr, 0, F.flags, st));
@@ -517,15 +537,17 @@ int ar_step_bwd_main(const FtArStepDesc& d, const FtArStepWeights& w, const floa
         const int S_c = pipe_chunk_steps();
         int* flagsA = F.flags;
         int* flagsB = F.flags + static_cast<size_t>(S_c) * 64;
+        cudaStream_t sr = pipe_prio() ? pp->sA : st;                 // layer 1's BPTT stream
         cudaEventRecord(pp->ev0, st);
+        if (sr != st) cudaStreamWaitEvent(sr, pp->ev0, 0);
         cudaStreamWaitEvent(pp->sB, pp->ev0, 0);
         cudaStreamWaitEvent(pp->sC, pp->ev0, 0);
         const int n_chunks = (n.T + S_c - 1) / S_c;
         for (int c = n_chunks - 1; c >= 0; --c) {
             const int t0 = c * S_c, t1 = t0 + S_c < n.T ? t0 + S_c : n.T;
             const long long r0 = static_cast<long long>(t0) * n.B, rows = static_cast<long long>(t1 - t0) * n.B;
-            FT_TRY(launch_lstm_bwd_chunk(n.T, n.B, t0, t1, F.dh, H, F.w.w_hh1, S_.gates1, S_.c1, out_lens, F.dG1, F.dcarry1, flagsA, st));
-            cudaEventRecord(pp->evA, st);
+            FT_TRY(launch_lstm_bwd_chunk(n.T, n.B, t0, t1, F.dh, H, F.w.w_hh1, S_.gates1, S_.c1, out_lens, F.dG1, F.dcarry1, flagsA, sr));
+            cudaEventRecord(pp->evA, sr);
             cudaStreamWaitEvent(pp->sC, pp->evA, 0);
             FT_TRY(gemm_dgrad(pp->sC, rows, H, G, F.dG1 + r0 * G, G, F.w.w_ih1, H, 0, F.dh + r0 * H, H, nullptr, 0, nullptr, 0));
             cudaEventRecord(pp->evG, pp->sC);
@@ -533,6 +555,7 @@ int ar_step_bwd_main(const FtArStepDesc& d, const FtArStepWeights& w, const floa
             FT_TRY(launch_lstm_bwd_chunk(n.T, n.B, t0, t1, F.dh, H, F.w.w_hh0, S_.gates0, S_.c0, out_lens, F.dG0, F.dcarry0, flagsB, pp->sB));
         }
         // layer-1 weight gradients run under the tail of layer 0 (side stream forks from st = all of layer 1 done)
+        if (sr != st) { cudaEventRecord(pp->evJ, sr); cudaStreamWaitEvent(st, pp->evJ, 0); }
         ss = fork_side(sd, st);
         FT_TRY(gemm_wgrad(ss, G, H, Rm, F.dG1 + static_cast<size_t>(n.B) * G, G, S_.h1_16, H, g.lstm_w_hh1, H, iS));
         FT_TRY(gemm_wgrad(ss, G, H, R, F.dG1, G, S_.h0_16, H, g.lstm_w_ih1, H, iS));

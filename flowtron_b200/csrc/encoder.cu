@@ -76,6 +76,30 @@ __global__ void enc_in_kernel(const float* __restrict__ x, const int* __restrict
     }
 }
 
+// Token path (the reference's `self.embedding(text)` in front of the encoder, flowtron.py:873): the embedding row gather writes the
+// first block's input grid directly (no [B, L, 512] tensor, no transposes) ...
+__global__ void enc_embed_kernel(const long long* __restrict__ tokens, const float* __restrict__ emb, int n_text, const int* __restrict__ lens,
+                                 int B, int L, __half* __restrict__ X16) {
+    const int row = blockIdx.x, b = row / L, l = row - b * L;            // one CTA per token, 128 threads x 4 channels
+    const int len = lens ? lens[b] : L;
+    long long tok = tokens[row];
+    tok = tok < 0 ? 0 : (tok >= n_text ? n_text - 1 : tok);
+    __half* dst = X16 + (static_cast<long long>(b) * (L + 2 * EPADR) + EPADR + l) * (3 * EC);
+    for (int c = threadIdx.x; c < EC; c += blockDim.x) store_hlh(dst, EC, c, l < len ? emb[tok * EC + c] : 0.f);
+}
+// ... and its backward scatters the (loss-scaled) input-grid gradient into embedding.weight.grad (zeroed by the caller)
+__global__ void enc_embed_grad_kernel(const float* __restrict__ DX, const long long* __restrict__ tokens, int n_text, const int* __restrict__ lens,
+                                      int B, int L, const float* __restrict__ scale2, float* __restrict__ d_emb) {
+    const int row = blockIdx.x, b = row / L, l = row - b * L;
+    const int len = lens ? lens[b] : L;
+    if (l >= len) return;
+    long long tok = tokens[row];
+    tok = tok < 0 ? 0 : (tok >= n_text ? n_text - 1 : tok);
+    const float inv = scale2[1];
+    const float* src = DX + (static_cast<long long>(b) * (L + 2 * EPADR) + EPADR + l) * EC;
+    for (int c = threadIdx.x; c < EC; c += blockDim.x) atomicAdd(d_emb + tok * EC + c, src[c] * inv);
+}
+
 // gradient grid rows (fp32, channels last, loss-scaled) -> d_x [B, C, L] fp32 (x 1/S); zero at l >= len
 __global__ void enc_out_grad_kernel(const float* __restrict__ DX, const int* __restrict__ lens, int B, int L, const float* __restrict__ scale2,
                                     float* __restrict__ dx) {
@@ -610,11 +634,12 @@ size_t ft_encoder_bwd_scratch_bytes(const FtEncoderDesc* d) { return ft::check_d
 #define FT_TRYE(x) do { if ((x) != 0) return -1; } while (0)
 #define FT_CU(x) do { if ((x) != cudaSuccess) return ft::ft_set_error("encoder: CUDA runtime call failed"); } while (0)
 
-int ft_encoder_fwd(const FtEncoderDesc* d, const FtEncoderWeights* w, const float* x, const int* in_lens, unsigned long long* rng_state,
-                   float* out, long long out_stride_b, long long out_stride_l, void* saved, void* scratch, void* stream) {
+static int encoder_fwd_impl(const FtEncoderDesc* d, const FtEncoderWeights* w, const float* x, const long long* tokens, const float* emb, int n_text,
+                            const int* in_lens, unsigned long long* rng_state, float* out, long long out_stride_b, long long out_stride_l,
+                            void* saved, void* scratch, void* stream) {
     using namespace ft;
     FT_TRYE(check_desc(d));
-    if (!w || !x || !out || !saved || !scratch) return ft_set_error("ft_encoder_fwd: NULL argument");
+    if (!w || (!x && !(tokens && emb && n_text > 0)) || !out || !saved || !scratch) return ft_set_error("ft_encoder_fwd: NULL argument");
     if (d->dropout_p > 0.f && !rng_state) return ft_set_error("ft_encoder_fwd: dropout needs the device rng state");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     EncPlan P = plan_enc(*d, static_cast<uint8_t*>(saved), static_cast<uint8_t*>(scratch), false);
@@ -629,7 +654,8 @@ int ft_encoder_fwd(const FtEncoderDesc* d, const FtEncoderWeights* w, const floa
         FT_CU(cudaMemsetAsync(P.cstate[k], 0, rows * EH * 4, st));
     }
     if (lens) FT_CU(cudaMemcpyAsync(P.lens, lens, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
-    enc_in_kernel<<<dim3((L + 31) / 32, EC / 32, B), 256, 0, st>>>(x, lens, B, L, P.X16[0]);
+    if (x) enc_in_kernel<<<dim3((L + 31) / 32, EC / 32, B), 256, 0, st>>>(x, lens, B, L, P.X16[0]);
+    else   enc_embed_kernel<<<B * L, 128, 0, st>>>(tokens, emb, n_text, lens, B, L, P.X16[0]);
     ft_count_launch(1);
     FT_TRYE(ft_check_launch("enc_in_kernel"));
     for (int i = 0; i < 3; ++i) {
@@ -671,8 +697,21 @@ int ft_encoder_fwd(const FtEncoderDesc* d, const FtEncoderWeights* w, const floa
     return launch_bilstm_fwd<2>(p, st);
 }
 
-int ft_encoder_bwd(const FtEncoderDesc* d, const FtEncoderWeights* w, const float* d_out, long long d_stride_b, long long d_stride_l,
-                   const void* saved, float* d_x, const FtEncoderGrads* gr, void* scratch, void* stream) {
+int ft_encoder_fwd(const FtEncoderDesc* d, const FtEncoderWeights* w, const float* x, const int* in_lens, unsigned long long* rng_state,
+                   float* out, long long out_stride_b, long long out_stride_l, void* saved, void* scratch, void* stream) {
+    if (!x) return ft::ft_set_error("ft_encoder_fwd: NULL argument");
+    return encoder_fwd_impl(d, w, x, nullptr, nullptr, 0, in_lens, rng_state, out, out_stride_b, out_stride_l, saved, scratch, stream);
+}
+int ft_encoder_fwd_tokens(const FtEncoderDesc* d, const FtEncoderWeights* w, const long long* tokens, const float* emb_weight, int n_text,
+                          const int* in_lens, unsigned long long* rng_state, float* out, long long out_stride_b, long long out_stride_l,
+                          void* saved, void* scratch, void* stream) {
+    if (!tokens || !emb_weight || n_text <= 0) return ft::ft_set_error("ft_encoder_fwd_tokens: NULL argument");
+    return encoder_fwd_impl(d, w, nullptr, tokens, emb_weight, n_text, in_lens, rng_state, out, out_stride_b, out_stride_l, saved, scratch, stream);
+}
+
+static int encoder_bwd_impl(const FtEncoderDesc* d, const FtEncoderWeights* w, const float* d_out, long long d_stride_b, long long d_stride_l,
+                            const void* saved, float* d_x, const long long* tokens, int n_text, float* d_emb, const FtEncoderGrads* gr,
+                            void* scratch, void* stream) {
     using namespace ft;
     FT_TRYE(check_desc(d));
     if (!w || !d_out || !saved || !gr || !scratch) return ft_set_error("ft_encoder_bwd: NULL argument");
@@ -739,7 +778,24 @@ int ft_encoder_bwd(const FtEncoderDesc* d, const FtEncoderWeights* w, const floa
         ft_count_launch(1);
         FT_TRYE(ft_check_launch("enc_out_grad_kernel"));
     }
+    if (d_emb) {
+        FT_CU(cudaMemsetAsync(d_emb, 0, sizeof(float) * static_cast<size_t>(n_text) * EC, st));
+        enc_embed_grad_kernel<<<B * L, 128, 0, st>>>(P.DX32, tokens, n_text, lens, B, L, P.scale2, d_emb);
+        ft_count_launch(1);
+        FT_TRYE(ft_check_launch("enc_embed_grad_kernel"));
+    }
     return 0;
+}
+
+int ft_encoder_bwd(const FtEncoderDesc* d, const FtEncoderWeights* w, const float* d_out, long long d_stride_b, long long d_stride_l,
+                   const void* saved, float* d_x, const FtEncoderGrads* gr, void* scratch, void* stream) {
+    return encoder_bwd_impl(d, w, d_out, d_stride_b, d_stride_l, saved, d_x, nullptr, 0, nullptr, gr, scratch, stream);
+}
+int ft_encoder_bwd_tokens(const FtEncoderDesc* d, const FtEncoderWeights* w, const float* d_out, long long d_stride_b, long long d_stride_l,
+                          const void* saved, const long long* tokens, int n_text, float* d_emb_weight, const FtEncoderGrads* gr, void* scratch,
+                          void* stream) {
+    if (!tokens || !d_emb_weight || n_text <= 0) return ft::ft_set_error("ft_encoder_bwd_tokens: NULL argument");
+    return encoder_bwd_impl(d, w, d_out, d_stride_b, d_stride_l, saved, nullptr, tokens, n_text, d_emb_weight, gr, scratch, stream);
 }
 
 }  // extern "C"

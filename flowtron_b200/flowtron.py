@@ -143,6 +143,39 @@ class _EncoderFn(torch.autograd.Function):
         return (None, d_x, None, None, None, *flat)
 
 
+class _EncoderTokensFn(torch.autograd.Function):
+    """embedding(text) + Encoder.forward / .infer on the CUDA kernels with the row gather fused into the first kernel and the
+    embedding gradient scattered by the last one (ft_encoder_fwd_tokens / ft_encoder_bwd_tokens)."""
+
+    @staticmethod
+    def forward(ctx, enc, tokens, emb_weight, in_lens, masked, dropout_p, *flat_params):
+        B, L = tokens.shape
+        params, i = {}, 0
+        for n, k in _lib.ENC_PARAM_FIELDS:
+            params[n] = [t.detach().contiguous() for t in flat_params[i:i + k]]
+            i += k
+        desc = _lib.encoder_desc(B, L, masked, dropout_p, enc.convolutions[0][1].eps)
+        lens32 = in_lens.to(torch.int32) if masked else None
+        tokens = tokens.contiguous()
+        embw = emb_weight.detach().contiguous()
+        out = torch.empty(B, L, embw.size(1), dtype=torch.float32, device=tokens.device)
+        rng = enc._rng_state(tokens.device) if dropout_p > 0 else None
+        saved = _lib.encoder_fwd(desc, params, None, lens32, rng, out, out.stride(0), out.stride(1), tokens=tokens, emb_weight=embw)
+        ctx.desc, ctx.params, ctx.saved, ctx.tokens, ctx.embw = desc, params, saved, tokens, embw
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        if ctx.saved is None:
+            raise RuntimeError("Encoder backward called twice (the saved activations were released)")
+        d_emb, grads = _lib.encoder_bwd(ctx.desc, ctx.params, d_out.contiguous().float(), ctx.saved, tokens=ctx.tokens, emb_weight=ctx.embw)
+        ctx.saved = None
+        flat = []
+        for n, _ in _lib.ENC_PARAM_FIELDS:
+            flat += grads[n]
+        return (None, None, d_emb, None, None, None, *flat)
+
+
 class Encoder(nn.Module):
     """flowtron.py:467-525 (3 x conv+masked instance norm+relu+dropout, packed BiLSTM).  CUDA tensors run on the encoder kernels
     (csrc/encoder.cu); the torch code below is the module's CPU mirror (host-logic tests) and the FT_ENC_KERNELS=0 A/B path."""
@@ -175,6 +208,21 @@ class Encoder(nn.Module):
         for n in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"):
             flat += [getattr(self.lstm, n), getattr(self.lstm, n + "_reverse")]
         return flat
+
+    def forward_tokens(self, tokens, embedding, in_lens):
+        """Encoder.forward(embedding(tokens).transpose(1, 2), in_lens) with the lookup fused into the encoder kernels."""
+        return _EncoderTokensFn.apply(self, tokens, embedding.weight, in_lens, tokens.size(0) > 1,
+                                      self.p_dropout if self.training else 0.0, *self._kernel_params())
+
+    def infer_tokens(self, tokens, embedding):
+        """Encoder.infer(embedding(tokens).transpose(1, 2)) likewise."""
+        return _EncoderTokensFn.apply(self, tokens, embedding.weight, None, False, self.p_dropout if self.training else 0.0,
+                                      *self._kernel_params())
+
+    def _tokens_ok(self, tokens, embedding):
+        return (self.use_kernels and tokens.is_cuda and embedding.weight.size(1) == 512 and len(self.convolutions) == 3
+                and tokens.size(0) <= 64 and embedding.padding_idx is None and embedding.max_norm is None
+                and self.convolutions[0][0].conv.kernel_size[0] == 5 and isinstance(self.convolutions[0][1], MaskedInstanceNorm1d))
 
     def _kernels_ok(self, x):
         return (self.use_kernels and x.is_cuda and x.size(1) == 512 and len(self.convolutions) == 3 and x.size(0) <= 64
@@ -528,8 +576,10 @@ class Flowtron(nn.Module):
         """flowtron.py:871-880: embeddings + Encoder + speaker vector concat -> [L, B, n_text + n_speaker]."""
         speaker_ids = speaker_ids * 0 if self.dummy_speaker_embedding else speaker_ids
         speaker_vecs = self.speaker_embedding(speaker_ids)
-        text = self.embedding(text).transpose(1, 2)
-        text = self.encoder(text, in_lens)
+        if self.encoder._tokens_ok(text, self.embedding):
+            text = self.encoder.forward_tokens(text, self.embedding, in_lens)     # embedding gather fused into the encoder kernels
+        else:
+            text = self.encoder(self.embedding(text).transpose(1, 2), in_lens)
         text = text.transpose(0, 1)
         return torch.cat([text, speaker_vecs.expand(text.size(0), -1, -1)], 2)
 
@@ -602,8 +652,10 @@ class Flowtron(nn.Module):
     def infer(self, residual, speaker_ids, text, temperature=1.0, gate_threshold=0.5, attns=None, attn_prior=None):
         speaker_ids = speaker_ids * 0 if self.dummy_speaker_embedding else speaker_ids
         speaker_vecs = self.speaker_embedding(speaker_ids)
-        text = self.embedding(text).transpose(1, 2)
-        text = self.encoder.infer(text)
+        if self.encoder._tokens_ok(text, self.embedding):
+            text = self.encoder.infer_tokens(text, self.embedding)
+        else:
+            text = self.encoder.infer(self.embedding(text).transpose(1, 2))
         text = text.transpose(0, 1)
         encoder_outputs = torch.cat([text, speaker_vecs.expand(text.size(0), -1, -1)], 2)
         residual = residual.permute(2, 0, 1)

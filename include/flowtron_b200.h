@@ -277,6 +277,14 @@ size_t ft_encoder_bwd_scratch_bytes(const FtEncoderDesc* d);
 int ft_encoder_fwd(const FtEncoderDesc* d, const FtEncoderWeights* w, const float* x, const int* in_lens,
                    unsigned long long* rng_state, float* out, long long out_stride_b, long long out_stride_l, void* saved,
                    void* scratch, void* stream);
+/* Token form: the nn.Embedding lookup in front of the encoder (flowtron.py:873 `self.embedding(text).transpose(1, 2)`) fused into
+ * the first kernel (tokens int64 [B, L], emb_weight fp32 [n_text, 512]); the backward scatters into d_emb_weight (overwritten). */
+int ft_encoder_fwd_tokens(const FtEncoderDesc* d, const FtEncoderWeights* w, const long long* tokens, const float* emb_weight,
+                          int n_text, const int* in_lens, unsigned long long* rng_state, float* out, long long out_stride_b,
+                          long long out_stride_l, void* saved, void* scratch, void* stream);
+int ft_encoder_bwd_tokens(const FtEncoderDesc* d, const FtEncoderWeights* w, const float* d_out, long long d_stride_b,
+                          long long d_stride_l, const void* saved, const long long* tokens, int n_text, float* d_emb_weight,
+                          const FtEncoderGrads* grads, void* scratch, void* stream);
 /* d_out: dense [B, L, 512] fp32; d_x [B, 512, L] fp32 (may be NULL). */
 int ft_encoder_bwd(const FtEncoderDesc* d, const FtEncoderWeights* w, const float* d_out, long long d_stride_b,
                    long long d_stride_l, const void* saved, float* d_x, const FtEncoderGrads* grads, void* scratch, void* stream);

@@ -131,3 +131,32 @@ def test_encoder_dropout_is_random_scaled_and_consistent_in_backward():
     for b, n in enumerate(in_lens.tolist()):
         if n < L:
             assert float(x.grad[b, :, n:].abs().max()) == 0.0
+
+
+def test_encoder_token_path_equals_embedding_then_encoder():
+    """ft_encoder_fwd_tokens / ft_encoder_bwd_tokens (embedding gather / scatter fused into the encoder kernels) against the
+    two-step path nn.Embedding -> Encoder kernels: identical forward, embedding gradient equal up to atomic-add order."""
+    m, _ = _model(9)
+    m.train()
+    m.encoder.p_dropout = 0.0
+    g = torch.Generator().manual_seed(21)
+    B, L = 7, 33
+    tokens = torch.randint(0, m.embedding.num_embeddings, (B, L), generator=g).cuda()
+    in_lens = torch.tensor([33, 30, 30, 21, 12, 5, 2]).cuda()
+    w_out = (torch.randn(B, L, 512, generator=g) * 0.05).cuda()
+
+    def run(fused):
+        for q in m.parameters():
+            q.grad = None
+        out = m.encoder.forward_tokens(tokens, m.embedding, in_lens) if fused else m.encoder(m.embedding(tokens).transpose(1, 2), in_lens)
+        (out * w_out).sum().backward()
+        return out.detach(), m.embedding.weight.grad.clone(), m.encoder.lstm.weight_ih_l0.grad.clone()
+    o1, e1, w1 = run(True)
+    o2, e2, w2 = run(False)
+    assert torch.equal(o1, o2)
+    assert (e1 - e2).norm().item() <= 1e-5 * e2.norm().item() and e2.norm().item() > 0
+    assert (w1 - w2).norm().item() <= 1e-5 * w2.norm().item()
+    # rows of tokens that only occur at masked positions get no gradient
+    used = set(tokens[torch.arange(L, device="cuda")[None, :] < in_lens[:, None]].tolist())
+    unused = [t for t in range(m.embedding.num_embeddings) if t not in used]
+    assert float(e1[unused].abs().max()) == 0.0
