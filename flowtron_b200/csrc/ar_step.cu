@@ -471,7 +471,8 @@ int ar_step_fwd(const FtArStepDesc& d, const FtArStepWeights& w, const float* me
 int ar_step_bwd_main(const FtArStepDesc& d, const FtArStepWeights& w, const float* mel, const int* in_lens, const int* out_lens,
                      const float* attn, const float* d_mel_out, const float* d_log_s, const float* d_gates, const float* d_attn,
                      const float* d_logprob, float* d_text, const FtArStepWeights& g, void* saved, void* scratch, void* carry,
-                     cudaStream_t st) {
+                     cudaStream_t st, bool may_fuse_bptt = false, bool* bptt_done = nullptr) {
+    if (bptt_done) *bptt_done = false;
     FT_TRY(check_desc(d));
     const Dims n(d);
     Plan ps; ps.base = static_cast<uint8_t*>(saved);
@@ -578,34 +579,68 @@ int ar_step_bwd_main(const FtArStepDesc& d, const FtArStepWeights& w, const floa
     }
     // (the weight gradients of lstm layer 0 and of the attention projections are launched by ar_step_bwd_attn, on the side
     //  stream underneath the attention LSTM's BPTT: dG0, dQ16, dK16, dV16 stay in the scratch area until then)
-    FT_TRY(gemm_dgrad(st, R, n.D, G, F.dG0, G, F.w.w_ih0, n.D, 0, C.dd, n.D, nullptr, 0, nullptr, 0));
-
-    // 7. gate layer (last flow only): dd is in the scaled domain, the gate's own parameter gradients are not
-    if (d.has_gate && g.gate_w) {
-        FT_TRY(zero(g.gate_w, sizeof(float) * n.D, st));
-        FT_TRY(zero(g.gate_b, sizeof(float), st));
-        if (d_gates) FT_TRY(launch_gate_bwd(S_.d16, n.D, n.D, w.gate_w, d_gates, R, C.dd, n.D, g.gate_w, g.gate_b, S, st));
-    }
-
-    // 8. attention (score/softmax/context) with tanh recompute
     FT_TRY(zero(F.dK, sizeof(float) * RL * n.A, st));
     FT_TRY(zero(F.dV, sizeof(float) * RL * n.A, st));
     FT_TRY(zero(g.att_v, sizeof(float) * n.A, st));
-    {
+    if (d.has_gate && g.gate_w) {
+        FT_TRY(zero(g.gate_w, sizeof(float) * n.D, st));
+        FT_TRY(zero(g.gate_b, sizeof(float), st));
+    }
+    // Steps 6b-9a for the time steps [t0, t1): lstm layer 0's input gradient (dd = [dhA ; dctx]), the gate layer, the attention
+    // backward (tanh recompute; dK / dV / dv accumulate over calls) and the query projection's share of dhA.
+    auto attention_bwd_rows = [&](cudaStream_t s2, int t0, int t1) -> int {
+        const long long r0 = static_cast<long long>(t0) * n.B, rows = static_cast<long long>(t1 - t0) * n.B;
+        FT_TRY(gemm_dgrad(s2, rows, n.D, G, F.dG0 + r0 * G, G, F.w.w_ih0, n.D, 0, C.dd + r0 * n.D, n.D, nullptr, 0, nullptr, 0));
+        // 7. gate layer (last flow only): dd is in the scaled domain, the gate's own parameter gradients are not
+        if (d.has_gate && g.gate_w && d_gates)
+            FT_TRY(launch_gate_bwd(S_.d16 + r0 * n.D, n.D, n.D, w.gate_w, d_gates + r0, rows, C.dd + r0 * n.D, n.D, g.gate_w, g.gate_b, S, s2));
+        // 8. attention (score/softmax/context) with tanh recompute
         AttnBwdArgs a;
         a.T = n.T; a.B = n.B; a.L = n.L; a.A = n.A;
         a.Q = S_.Q; a.ldq = n.A; a.K = S_.Kp; a.ldk = n.A; a.V = S_.Vp; a.ldv = n.A; a.v = w.att_v;
         a.in_lens = in_lens; a.out_lens = out_lens; a.attn = attn; a.p_save = S_.p_save; a.temperature = d.temperature;
         a.dctx = C.dd + H; a.lddc = n.D; a.dattn_ext = d_attn; a.dlp_ext = d_logprob; a.scale = S;
         a.dQ = F.dQ; a.lddq = n.A; a.dK = F.dK; a.lddk = n.A; a.dV = F.dV; a.lddv = n.A; a.dv = g.att_v;
-        FT_TRY(launch_attn_bwd(a, st));
+        a.t_begin = t0; a.t_end = t1;
+        FT_TRY(launch_attn_bwd(a, s2));
+        // 9a. query projection (d16 = [hA ; ctx] saved in fp16, row pitch D)
+        FT_TRY(launch_cast(F.dQ + r0 * n.A, 2, F.dQ16 + r0 * n.A, 0, rows * n.A, s2));
+        FT_TRY(gemm_dgrad(s2, rows, H, n.A, F.dQ16 + r0 * n.A, n.A, F.w.wq, H, 1, C.dd + r0 * n.D, n.D, nullptr, 0, nullptr, 0));   // dhA += dQ Wq
+        return 0;
+    };
+    // Attention backward / attention-LSTM BPTT overlap (the mirror image of the forward overlap; FT_ATT_OVERLAP_BWD = chunk length,
+    // default 256, 0 disables): only when the caller lets this call run the attention LSTM's BPTT as well (ft_ar_step_bwd: flows
+    // whose d_text nobody is waiting for).  Highest chunk first: the second stream prepares chunk c's dhA while the BPTT kernel
+    // (64 SMs) works on chunk c + 1.
+    static int attb_chunk = -1;
+    if (attb_chunk < 0) { const char* e = getenv("FT_ATT_OVERLAP_BWD"); attb_chunk = e ? atoi(e) : 256; if (attb_chunk % 64) attb_chunk = 0; }
+    Pipe* pq = (may_fuse_bptt && attb_chunk > 0 && F.dcarry1 && n.B <= 32 && n.T >= attb_chunk + 64) ? get_pipe(st) : nullptr;
+    if (pq) {
+        FT_TRY(launch_cast(w.attn_lstm_w_ih, 2, F.w.w_ih_a, 0, static_cast<long long>(G) * n.M, st));
+        FT_TRY(launch_transpose_cast_f16(w.attn_lstm_w_hh, F.w.w_hh_a, G, H, st));
+        cudaStream_t sr = pipe_prio() ? pq->sA : st;
+        cudaEventRecord(pq->ev0, st);
+        if (sr != st) cudaStreamWaitEvent(sr, pq->ev0, 0);
+        cudaStreamWaitEvent(pq->sC, pq->ev0, 0);
+        const int CH = attb_chunk, n_chunks = (n.T + CH - 1) / CH;
+        for (int c = n_chunks - 1; c >= 0; --c) {
+            const int t0 = c * CH, t1 = t0 + CH < n.T ? t0 + CH : n.T;
+            FT_TRY(attention_bwd_rows(pq->sC, t0, t1));
+            cudaEventRecord(pq->evG, pq->sC);
+            cudaStreamWaitEvent(sr, pq->evG, 0);
+            // 10. attention_lstm  (dhA = C.dd[:, 0:H], pitch D)
+            FT_TRY(launch_lstm_bwd_chunk(n.T, n.B, t0, t1, C.dd, n.D, F.w.w_hh_a, S_.gatesA, S_.cA, out_lens, F.dGa, F.dcarry1, F.flags, sr));
+        }
+        cudaStreamWaitEvent(st, pq->evG, 0);          // all of sC (the last record) ...
+        if (sr != st) { cudaEventRecord(pq->evJ, sr); cudaStreamWaitEvent(st, pq->evJ, 0); }     // ... and the BPTT
+        if (bptt_done) *bptt_done = true;
+    } else {
+        FT_TRY(attention_bwd_rows(st, 0, n.T));
     }
 
-    // 9. Q/K/V projections  (d16 = [hA ; ctx] saved in fp16, row pitch D)
-    FT_TRY(launch_cast(F.dQ, 2, F.dQ16, 0, R * n.A, st));
+    // 9b. key / value projections -> d_text
     FT_TRY(launch_cast(F.dK, 2, F.dK16, 0, RL * n.A, st));
     FT_TRY(launch_cast(F.dV, 2, F.dV16, 0, RL * n.A, st));
-    FT_TRY(gemm_dgrad(st, R, H, n.A, F.dQ16, n.A, F.w.wq, H, 1, C.dd, n.D, nullptr, 0, nullptr, 0));   // dhA += dQ Wq
     FT_TRY(gemm_dgrad(st, RL, n.E, n.A, F.dK16, n.A, F.w.wk, n.E, 0, d_text, n.E, nullptr, 0, nullptr, 0, iS));
     FT_TRY(gemm_dgrad(st, RL, n.E, n.A, F.dV16, n.A, F.w.wv, n.E, 1, d_text, n.E, nullptr, 0, nullptr, 0, iS));
 
@@ -616,7 +651,7 @@ int ar_step_bwd_main(const FtArStepDesc& d, const FtArStepWeights& w, const floa
 // Attention-LSTM part: BPTT over dhA (carry), its weight gradients, and the input gradient d_mel (coupling path from carry +
 // the shifted attention-LSTM path, back to natural time, loss scale undone).
 int ar_step_bwd_attn(const FtArStepDesc& d, const FtArStepWeights& w, const int* out_lens, float* d_mel, const FtArStepWeights& g,
-                     void* saved, void* scratch, void* carry, cudaStream_t st) {
+                     void* saved, void* scratch, void* carry, cudaStream_t st, bool bptt_done = false) {
     FT_TRY(check_desc(d));
     const Dims n(d);
     Plan ps; ps.base = static_cast<uint8_t*>(saved);
@@ -630,8 +665,10 @@ int ar_step_bwd_attn(const FtArStepDesc& d, const FtArStepWeights& w, const int*
     Side* sd = get_side(st);
     cudaStream_t ss;
     const long long RL = n.RL;
-    FT_TRY(launch_cast(w.attn_lstm_w_ih, 2, F.w.w_ih_a, 0, static_cast<long long>(G) * n.M, st));
-    FT_TRY(launch_transpose_cast_f16(w.attn_lstm_w_hh, F.w.w_hh_a, G, H, st));
+    if (!bptt_done) {                    // (a fused ar_step_bwd_main made these copies and ran the BPTT already)
+        FT_TRY(launch_cast(w.attn_lstm_w_ih, 2, F.w.w_ih_a, 0, static_cast<long long>(G) * n.M, st));
+        FT_TRY(launch_transpose_cast_f16(w.attn_lstm_w_hh, F.w.w_hh_a, G, H, st));
+    }
 
     // deferred from ar_step_bwd_main: weight gradients of lstm layer 0 and of the attention projections, on the side stream,
     // underneath the BPTT kernel below (64 of the 148 SMs)
@@ -645,7 +682,7 @@ int ar_step_bwd_attn(const FtArStepDesc& d, const FtArStepWeights& w, const int*
     FT_TRY(gemm_wgrad(ss, n.A, n.E, RL, F.dV16, n.A, S_.text16, n.E, g.att_value, n.E, iS));
 
     // 10. attention_lstm  (dhA = C.dd[:, 0:H], pitch D)
-    FT_TRY(launch_lstm_bwd(n.T, n.B, C.dd, n.D, F.w.w_hh_a, S_.gatesA, S_.cA, out_lens, F.dGa, F.flags, st));
+    if (!bptt_done) FT_TRY(launch_lstm_bwd(n.T, n.B, C.dd, n.D, F.w.w_hh_a, S_.gatesA, S_.cA, out_lens, F.dGa, F.flags, st));
     ss = fork_side(sd, st);
     FT_TRY(gemm_wgrad(ss, G, H, Rm, F.dGa + static_cast<size_t>(n.B) * G, G, S_.d16, n.D, g.attn_lstm_w_hh, H, iS));
     FT_TRY(gemm_wgrad(ss, G, n.M, R, F.dGa, G, S_.mel_in16, n.M, g.attn_lstm_w_ih, n.M, iS));
@@ -706,9 +743,10 @@ int ft_ar_step_bwd(const FtArStepDesc* d, const FtArStepWeights* w, const float*
     if (!d || !w || !mel || !attn || !d_text || !g || !saved || !scratch) return ft::ft_set_error("ft_ar_step_bwd: NULL argument");
     ft::Plan pb; ft::BwdScratch b; b.plan(pb, *d);
     void* carry = static_cast<uint8_t*>(scratch) + ((pb.off + 255) & ~static_cast<size_t>(255));
+    bool bptt_done = false;           // the one-call form may overlap the attention backward with the attention LSTM's BPTT
     if (ft::ar_step_bwd_main(*d, *w, mel, in_lens, out_lens, attn, d_mel_out, d_log_s, d_gates, d_attn, d_attn_logprob, d_text, *g,
-                             saved, scratch, carry, static_cast<cudaStream_t>(stream)) != 0) return -1;
-    return ft::ar_step_bwd_attn(*d, *w, out_lens, d_mel, *g, saved, scratch, carry, static_cast<cudaStream_t>(stream));
+                             saved, scratch, carry, static_cast<cudaStream_t>(stream), true, &bptt_done) != 0) return -1;
+    return ft::ar_step_bwd_attn(*d, *w, out_lens, d_mel, *g, saved, scratch, carry, static_cast<cudaStream_t>(stream), bptt_done);
 }
 
 int ft_ar_step_bwd_main(const FtArStepDesc* d, const FtArStepWeights* w, const float* mel, const int* in_lens,

@@ -282,6 +282,7 @@ attn_fwd_kernel(AttnFwdParams p) {
 
 // =================================================================================================== backward
 struct AttnBwdParams {
+    int t_begin, t_end;                  // query rows [t_begin, t_end) of this launch
     int T, B, L, A;
     const float* Q; long long ldq;
     const float* K; long long ldk;
@@ -315,10 +316,10 @@ attn_bwd_kernel(AttnBwdParams p) {
     __shared__ float s_sumde;                         // sum of de over the tile (dv needs sum de (1 - 2r) = sum de - 2 sum de r)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.y, t0 = blockIdx.x * AT_TT;
+    const int b = blockIdx.y, t0 = p.t_begin + blockIdx.x * AT_TT;
     const int out_len = p.out_lens ? p.out_lens[b] : p.T;
     const int in_len = p.in_lens ? p.in_lens[b] : p.L;
-    const int nrows = min(AT_TT, p.T - t0);
+    const int nrows = min(AT_TT, p.t_end - t0);
     const int ty = tid >> 4, tx = tid & 15;
 
     if (t0 >= out_len) {                              // forward wrote constants here: no gradient
@@ -631,8 +632,10 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t st) {
     p.dQ = a.dQ; p.lddq = a.lddq; p.dK = a.dK; p.lddk = a.lddk; p.dV = a.dV; p.lddv = a.lddv; p.dv = a.dv;
     const size_t smem = attn_bwd_smem(a.L, a.A);
     cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    dim3 grid((a.T + AT_TT - 1) / AT_TT, a.B);
-    TimeScope ts("attn_bwd", a.T, a.B, a.L, st);
+    p.t_begin = a.t_begin; p.t_end = a.t_end > 0 ? a.t_end : a.T;
+    if (p.t_begin % AT_TT || p.t_begin < 0 || p.t_end > a.T || p.t_end <= p.t_begin) return ft_set_error("attention backward: bad query range");
+    dim3 grid((p.t_end - p.t_begin + AT_TT - 1) / AT_TT, a.B);
+    TimeScope ts("attn_bwd", p.t_end - p.t_begin, a.B, a.L, st);
     attn_bwd_kernel<<<grid, AT_THREADS, smem, st>>>(p);
     ft_count_launch(1);
     return ft_check_launch("attn_bwd_kernel");

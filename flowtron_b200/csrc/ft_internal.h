@@ -93,6 +93,7 @@ struct AttnBwdArgs {
     const float* dctx; long long lddc; const float* dattn_ext; const float* dlp_ext;
     const float* scale;      // device [2] = {S, 1/S}: external grads are multiplied by S, dv by 1/S (null = 1)
     float* dQ; long long lddq; float* dK; long long lddk; float* dV; long long lddv; float* dv;
+    int t_begin = 0, t_end = 0;          // query rows of this launch (t_end == 0: all T; t_begin a multiple of 64); dK / dV / dv accumulate
 };
 int launch_attn_fwd(const AttnFwdArgs& a, cudaStream_t st);
 int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t st);

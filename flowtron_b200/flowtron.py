@@ -325,7 +325,8 @@ _MAIN_HALF = tuple(i for i in range(24) if i not in _ATTN_HALF)
 
 class _FlowState:
     """What the two autograd nodes of one flow step share between forward and the two backward calls."""
-    __slots__ = ("desc", "saved", "plist", "mel_c", "in_lens", "out_lens", "attn", "carry", "grads", "text_shape", "has_gate")
+    __slots__ = ("desc", "saved", "plist", "mel_c", "in_lens", "out_lens", "attn", "carry", "grads", "text_shape", "has_gate",
+                 "fuse_bwd", "d_mel")
 
     def clear(self):
         for k in self.__slots__:
@@ -346,6 +347,11 @@ class _ArStepAttnLstmFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_token):
         st = ctx.state
+        if st is not None and st.d_mel is not None:          # node B ran the whole backward in one call (ft_ar_step_bwd)
+            d_mel, grads_a = st.d_mel, [st.grads[i] for i in _ATTN_HALF]
+            st.clear()
+            ctx.state = None
+            return (None, d_mel, *grads_a)
         if st is None or st.saved is None or st.carry is None:
             raise FlowtronB200Error("AR_Step backward ran twice: the flow's saved activations are released after the first "
                                     "backward (retain_graph is not supported on the CUDA path)")
@@ -398,6 +404,7 @@ class _ArStepFn(torch.autograd.Function):
         state.desc, state.saved, state.plist = desc, saved, plist
         state.mel_c, state.in_lens, state.out_lens, state.attn = mel_c, in_lens, out_lens, attn
         state.text_shape, state.has_gate = text.shape, has_gate
+        state.fuse_bwd = bool(getattr(step, "_fuse_bwd", False))
         ctx.state = state
         ctx.has_gate = has_gate
         if has_gate:
@@ -421,11 +428,18 @@ class _ArStepFn(torch.autograd.Function):
         dev = st.mel_c.device
         d_text = torch.empty(st.text_shape, device=dev, dtype=torch.float32)
         st.grads = [None if p is None else torch.empty_like(p) for p in st.plist]
-        st.carry = torch.empty(_lib.ar_step_bwd_carry_bytes(desc), dtype=torch.uint8, device=dev)
         _, scratch_bytes = _lib.ar_step_sizes(desc)
         scratch = _lib.scratch_buffer(scratch_bytes, dev)
-        _lib.ar_step_bwd_main(desc, _lib.make_weights(st.plist), st.mel_c, st.in_lens, st.out_lens, st.attn, d_mel_out, d_log_s,
-                              d_gates, d_attn, d_lp, d_text, _lib.make_weights(st.grads), st.saved, scratch, st.carry)
+        if st.fuse_bwd:
+            # nobody waits for this flow's d_text alone (the encoder's backward starts after the FIRST flow's): run the whole
+            # backward in one call, which overlaps the attention backward with the attention LSTM's BPTT chunk by chunk
+            st.d_mel = torch.empty_like(st.mel_c)
+            _lib.ar_step_bwd(desc, _lib.make_weights(st.plist), st.mel_c, st.in_lens, st.out_lens, st.attn, d_mel_out, d_log_s,
+                             d_gates, d_attn, d_lp, st.d_mel, d_text, _lib.make_weights(st.grads), st.saved, scratch)
+        else:
+            st.carry = torch.empty(_lib.ar_step_bwd_carry_bytes(desc), dtype=torch.uint8, device=dev)
+            _lib.ar_step_bwd_main(desc, _lib.make_weights(st.plist), st.mel_c, st.in_lens, st.out_lens, st.attn, d_mel_out, d_log_s,
+                                  d_gates, d_attn, d_lp, d_text, _lib.make_weights(st.grads), st.saved, scratch, st.carry)
         grads_b = [st.grads[i] for i in _MAIN_HALF]
         ctx.state = None
         # (state, step, reversed, token, mel, text, in_lens, out_lens, prior, *params_b): mel's gradient comes out of node A
@@ -566,6 +580,9 @@ class Flowtron(nn.Module):
         for i, flow in enumerate(self.flows):
             # the module whose kernels run first gets the text-ready event (AR_Back_Step wraps its AR_Step as .ar_step)
             getattr(flow, "ar_step", flow)._text_event = getattr(self, "_text_event", None) if i == 0 else None
+            # flows after the first: the encoder's backward cannot start before the first flow's d_text exists, so their backward
+            # may run as one call (attention backward overlapped with the attention-LSTM BPTT); FT_FUSE_BWD=0 disables
+            getattr(flow, "ar_step", flow)._fuse_bwd = (i != 0) and os.environ.get("FT_FUSE_BWD", "0") != "0"
             mel, log_s, gate, attn_out, attn_logprob_out = flow(mel, encoder_outputs, mask, out_lens, attn_prior)
             log_s_list.append(log_s)
             attns_list.append(attn_out)

@@ -66,8 +66,10 @@ def test_attention_overlap_equals_serial_schedule(tmp_path):
         r = subprocess.run([sys.executable, "-c", CHILD_LONG, ROOT, str(out)], env=e, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
         return torch.load(out)
-    a = run("serial", {"FT_ATT_OVERLAP": "0"})
-    b = run("overlap", {"FT_ATT_OVERLAP": "64"})          # 300 steps -> 5 chunks, ragged tail (44 steps)
+    a = run("serial", {"FT_ATT_OVERLAP": "0", "FT_FUSE_BWD": "0"})
+    # 300 steps -> 5 chunks, ragged tail (44 steps); the backward of the second flow runs as one call with the attention backward
+    # of chunk c under the attention-LSTM BPTT of chunk c + 1 (FT_ATT_OVERLAP_BWD)
+    b = run("overlap", {"FT_ATT_OVERLAP": "64", "FT_FUSE_BWD": "1", "FT_ATT_OVERLAP_BWD": "64"})
     def rel(x, y):
         return (x - y).abs().max().item() / max(y.abs().max().item(), 1e-12)
     # both schedules are within the 1e-3 bar of the fp32 reference; between themselves they differ by fp16 operand rounding of
