@@ -406,6 +406,7 @@ def run_train(args):
                    "parallelism": f"dp{world}", "streams_per_rank": args.streams, "cuda_graph": graph is not None, "cuda_graph_note": graph_note,
                    "encoder_overlap": bool(model.overlap_encoder), "padded_frames_per_s": B * T * world * args.steps / (ms / 1e3),
                    "pipe_fwd": os.environ.get("FT_PIPE_FWD", "default"), "pipe_bwd": os.environ.get("FT_PIPE_BWD", "default"),
+                   "att_overlap": os.environ.get("FT_ATT_OVERLAP", "default"), "fuse_bwd": os.environ.get("FT_FUSE_BWD", "default"),
                    "l2": "working set per step (>3 GB of activations) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e, "unit": "valid mel-frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "prior": "built on the device from the lengths (ft_attn_prior)",
