@@ -257,8 +257,9 @@ static void join_side(Side* sd, cudaStream_t main) {
 
 // Streams of the experimental layer pipeline: sB runs the second recurrence, sC its per-chunk input-projection GEMMs.
 struct Pipe {
-    cudaStream_t sA = nullptr, sB = nullptr, sC = nullptr;      // sA / sB: HIGH-priority streams of the two recurrences, sC: their GEMMs
-    cudaEvent_t evA = nullptr, evG = nullptr, evB = nullptr, ev0 = nullptr, evJ = nullptr;
+    cudaStream_t sA = nullptr, sB = nullptr, sC = nullptr, sD = nullptr;      // sA / sB: HIGH-priority streams of the two recurrences, sC: their GEMMs,
+                                                                              // sD: lowest priority, work nobody waits for yet
+    cudaEvent_t evA = nullptr, evG = nullptr, evB = nullptr, ev0 = nullptr, evJ = nullptr, evD = nullptr;
 };
 // FT_PIPE_PRIO (default 1): the chunk kernels of the pipelined recurrences are launched on high-priority streams, so that when a
 // chunk ends its 64 SMs go to the next chunk (a cooperative launch that needs all of them at once) and not to queued CTAs of the
@@ -279,8 +280,11 @@ static Pipe* get_pipe(cudaStream_t main) {
     const int pr = pipe_prio() ? prio_hi : prio_lo;
     if (cudaStreamCreateWithPriority(&pp.sA, cudaStreamNonBlocking, pr) != cudaSuccess) return nullptr;
     if (cudaStreamCreateWithPriority(&pp.sB, cudaStreamNonBlocking, pr) != cudaSuccess) return nullptr;
-    if (cudaStreamCreateWithFlags(&pp.sC, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    const int mid = pipe_prio() && prio_hi < prio_lo - 1 ? prio_lo - 1 : prio_lo;      // the pipeline's own GEMMs beat sD's
+    if (cudaStreamCreateWithPriority(&pp.sC, cudaStreamNonBlocking, mid) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithPriority(&pp.sD, cudaStreamNonBlocking, prio_lo) != cudaSuccess) return nullptr;
     cudaEventCreateWithFlags(&pp.evJ, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&pp.evD, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&pp.evA, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&pp.evG, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&pp.evB, cudaEventDisableTiming);
@@ -530,55 +534,6 @@ int ar_step_bwd_main(const FtArStepDesc& d, const FtArStepWeights& w, const floa
     FT_TRY(launch_colsum(F.dy1, 0, H, R, H, g.dense_b0, iS, ss));
     FT_TRY(gemm_dgrad(st, R, H, H, F.dy1, H, F.w.w1, H, 0, F.dh, H, nullptr, 0, nullptr, 0));
 
-    Pipe* pp = (F.dcarry1 && n.B <= 32 && 2 * pipe_chunk_steps() <= n.T) ? get_pipe(st) : nullptr;
-    if (pp) {
-        // EXPERIMENTAL 5+6: BPTT of layer 1 (st) and layer 0 (sB) one chunk apart; the layer-1 dgrad of a finished chunk
-        // (sC) turns dG1 rows into layer 0's incoming dh rows (F.dh is reused row-disjointly: layer 1 only reads rows
-        // below the chunk it has finished).  Highest chunk first.
-        const int S_c = pipe_chunk_steps();
-        int* flagsA = F.flags;
-        int* flagsB = F.flags + static_cast<size_t>(S_c) * 64;
-        cudaStream_t sr = pipe_prio() ? pp->sA : st;                 // layer 1's BPTT stream
-        cudaEventRecord(pp->ev0, st);
-        if (sr != st) cudaStreamWaitEvent(sr, pp->ev0, 0);
-        cudaStreamWaitEvent(pp->sB, pp->ev0, 0);
-        cudaStreamWaitEvent(pp->sC, pp->ev0, 0);
-        const int n_chunks = (n.T + S_c - 1) / S_c;
-        for (int c = n_chunks - 1; c >= 0; --c) {
-            const int t0 = c * S_c, t1 = t0 + S_c < n.T ? t0 + S_c : n.T;
-            const long long r0 = static_cast<long long>(t0) * n.B, rows = static_cast<long long>(t1 - t0) * n.B;
-            FT_TRY(launch_lstm_bwd_chunk(n.T, n.B, t0, t1, F.dh, H, F.w.w_hh1, S_.gates1, S_.c1, out_lens, F.dG1, F.dcarry1, flagsA, sr));
-            cudaEventRecord(pp->evA, sr);
-            cudaStreamWaitEvent(pp->sC, pp->evA, 0);
-            FT_TRY(gemm_dgrad(pp->sC, rows, H, G, F.dG1 + r0 * G, G, F.w.w_ih1, H, 0, F.dh + r0 * H, H, nullptr, 0, nullptr, 0));
-            cudaEventRecord(pp->evG, pp->sC);
-            cudaStreamWaitEvent(pp->sB, pp->evG, 0);
-            FT_TRY(launch_lstm_bwd_chunk(n.T, n.B, t0, t1, F.dh, H, F.w.w_hh0, S_.gates0, S_.c0, out_lens, F.dG0, F.dcarry0, flagsB, pp->sB));
-        }
-        // layer-1 weight gradients run under the tail of layer 0 (side stream forks from st = all of layer 1 done)
-        if (sr != st) { cudaEventRecord(pp->evJ, sr); cudaStreamWaitEvent(st, pp->evJ, 0); }
-        ss = fork_side(sd, st);
-        FT_TRY(gemm_wgrad(ss, G, H, Rm, F.dG1 + static_cast<size_t>(n.B) * G, G, S_.h1_16, H, g.lstm_w_hh1, H, iS));
-        FT_TRY(gemm_wgrad(ss, G, H, R, F.dG1, G, S_.h0_16, H, g.lstm_w_ih1, H, iS));
-        FT_TRY(launch_colsum(F.dG1, 0, G, R, G, g.lstm_b_ih1, iS, ss));
-        FT_TRY(copy_f32(g.lstm_b_hh1, g.lstm_b_ih1, G, ss));
-        cudaEventRecord(pp->evB, pp->sB);
-        cudaStreamWaitEvent(st, pp->evB, 0);
-    } else {
-    // 5. lstm layer 1
-    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dh, H, F.w.w_hh1, S_.gates1, S_.c1, out_lens, F.dG1, F.flags, st));
-    ss = fork_side(sd, st);
-    FT_TRY(gemm_wgrad(ss, G, H, Rm, F.dG1 + static_cast<size_t>(n.B) * G, G, S_.h1_16, H, g.lstm_w_hh1, H, iS));
-    FT_TRY(gemm_wgrad(ss, G, H, R, F.dG1, G, S_.h0_16, H, g.lstm_w_ih1, H, iS));
-    FT_TRY(launch_colsum(F.dG1, 0, G, R, G, g.lstm_b_ih1, iS, ss));
-    FT_TRY(copy_f32(g.lstm_b_hh1, g.lstm_b_ih1, G, ss));
-    FT_TRY(gemm_dgrad(st, R, H, G, F.dG1, G, F.w.w_ih1, H, 0, F.dh, H, nullptr, 0, nullptr, 0));
-
-    // 6. lstm layer 0
-    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dh, H, F.w.w_hh0, S_.gates0, S_.c0, out_lens, F.dG0, F.flags, st));
-    }
-    // (the weight gradients of lstm layer 0 and of the attention projections are launched by ar_step_bwd_attn, on the side
-    //  stream underneath the attention LSTM's BPTT: dG0, dQ16, dK16, dV16 stay in the scratch area until then)
     FT_TRY(zero(F.dK, sizeof(float) * RL * n.A, st));
     FT_TRY(zero(F.dV, sizeof(float) * RL * n.A, st));
     FT_TRY(zero(g.att_v, sizeof(float) * n.A, st));
@@ -608,13 +563,75 @@ int ar_step_bwd_main(const FtArStepDesc& d, const FtArStepWeights& w, const floa
         FT_TRY(gemm_dgrad(s2, rows, H, n.A, F.dQ16 + r0 * n.A, n.A, F.w.wq, H, 1, C.dd + r0 * n.D, n.D, nullptr, 0, nullptr, 0));   // dhA += dQ Wq
         return 0;
     };
+    // FT_ATTB_PIPE=1 (needs FT_PIPE_CHUNK % 64 == 0): the attention backward of every chunk lstm layer 0's BPTT has finished runs on a
+    // lowest-priority stream on whatever the two recurrences and their GEMMs leave free, instead of after the pipeline.
+    static int attb_pipe = -1;
+    if (attb_pipe < 0) { const char* e = getenv("FT_ATTB_PIPE"); attb_pipe = e ? atoi(e) : 0; }
+    bool attention_bwd_done = false;
+    Pipe* pp = (F.dcarry1 && n.B <= 32 && 2 * pipe_chunk_steps() <= n.T) ? get_pipe(st) : nullptr;
+    if (pp) {
+        // EXPERIMENTAL 5+6: BPTT of layer 1 (st) and layer 0 (sB) one chunk apart; the layer-1 dgrad of a finished chunk
+        // (sC) turns dG1 rows into layer 0's incoming dh rows (F.dh is reused row-disjointly: layer 1 only reads rows
+        // below the chunk it has finished).  Highest chunk first.
+        const int S_c = pipe_chunk_steps();
+        int* flagsA = F.flags;
+        int* flagsB = F.flags + static_cast<size_t>(S_c) * 64;
+        cudaStream_t sr = pipe_prio() ? pp->sA : st;                 // layer 1's BPTT stream
+        cudaEventRecord(pp->ev0, st);
+        if (sr != st) cudaStreamWaitEvent(sr, pp->ev0, 0);
+        cudaStreamWaitEvent(pp->sB, pp->ev0, 0);
+        cudaStreamWaitEvent(pp->sC, pp->ev0, 0);
+        const int n_chunks = (n.T + S_c - 1) / S_c;
+        for (int c = n_chunks - 1; c >= 0; --c) {
+            const int t0 = c * S_c, t1 = t0 + S_c < n.T ? t0 + S_c : n.T;
+            const long long r0 = static_cast<long long>(t0) * n.B, rows = static_cast<long long>(t1 - t0) * n.B;
+            FT_TRY(launch_lstm_bwd_chunk(n.T, n.B, t0, t1, F.dh, H, F.w.w_hh1, S_.gates1, S_.c1, out_lens, F.dG1, F.dcarry1, flagsA, sr));
+            cudaEventRecord(pp->evA, sr);
+            cudaStreamWaitEvent(pp->sC, pp->evA, 0);
+            FT_TRY(gemm_dgrad(pp->sC, rows, H, G, F.dG1 + r0 * G, G, F.w.w_ih1, H, 0, F.dh + r0 * H, H, nullptr, 0, nullptr, 0));
+            cudaEventRecord(pp->evG, pp->sC);
+            cudaStreamWaitEvent(pp->sB, pp->evG, 0);
+            FT_TRY(launch_lstm_bwd_chunk(n.T, n.B, t0, t1, F.dh, H, F.w.w_hh0, S_.gates0, S_.c0, out_lens, F.dG0, F.dcarry0, flagsB, pp->sB));
+            if (attb_pipe && S_c % 64 == 0) {
+                if (c == n_chunks - 1) cudaStreamWaitEvent(pp->sD, pp->ev0, 0);
+                cudaEventRecord(pp->evD, pp->sB);
+                cudaStreamWaitEvent(pp->sD, pp->evD, 0);
+                FT_TRY(attention_bwd_rows(pp->sD, t0, t1));
+                attention_bwd_done = true;
+            }
+        }
+        if (attention_bwd_done) { cudaEventRecord(pp->evD, pp->sD); cudaStreamWaitEvent(st, pp->evD, 0); }
+        // layer-1 weight gradients run under the tail of layer 0 (side stream forks from st = all of layer 1 done)
+        if (sr != st) { cudaEventRecord(pp->evJ, sr); cudaStreamWaitEvent(st, pp->evJ, 0); }
+        ss = fork_side(sd, st);
+        FT_TRY(gemm_wgrad(ss, G, H, Rm, F.dG1 + static_cast<size_t>(n.B) * G, G, S_.h1_16, H, g.lstm_w_hh1, H, iS));
+        FT_TRY(gemm_wgrad(ss, G, H, R, F.dG1, G, S_.h0_16, H, g.lstm_w_ih1, H, iS));
+        FT_TRY(launch_colsum(F.dG1, 0, G, R, G, g.lstm_b_ih1, iS, ss));
+        FT_TRY(copy_f32(g.lstm_b_hh1, g.lstm_b_ih1, G, ss));
+        cudaEventRecord(pp->evB, pp->sB);
+        cudaStreamWaitEvent(st, pp->evB, 0);
+    } else {
+    // 5. lstm layer 1
+    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dh, H, F.w.w_hh1, S_.gates1, S_.c1, out_lens, F.dG1, F.flags, st));
+    ss = fork_side(sd, st);
+    FT_TRY(gemm_wgrad(ss, G, H, Rm, F.dG1 + static_cast<size_t>(n.B) * G, G, S_.h1_16, H, g.lstm_w_hh1, H, iS));
+    FT_TRY(gemm_wgrad(ss, G, H, R, F.dG1, G, S_.h0_16, H, g.lstm_w_ih1, H, iS));
+    FT_TRY(launch_colsum(F.dG1, 0, G, R, G, g.lstm_b_ih1, iS, ss));
+    FT_TRY(copy_f32(g.lstm_b_hh1, g.lstm_b_ih1, G, ss));
+    FT_TRY(gemm_dgrad(st, R, H, G, F.dG1, G, F.w.w_ih1, H, 0, F.dh, H, nullptr, 0, nullptr, 0));
+
+    // 6. lstm layer 0
+    FT_TRY(launch_lstm_bwd(n.T, n.B, F.dh, H, F.w.w_hh0, S_.gates0, S_.c0, out_lens, F.dG0, F.flags, st));
+    }
+    // (the weight gradients of lstm layer 0 and of the attention projections are launched by ar_step_bwd_attn, on the side
+    //  stream underneath the attention LSTM's BPTT: dG0, dQ16, dK16, dV16 stay in the scratch area until then)
     // Attention backward / attention-LSTM BPTT overlap (the mirror image of the forward overlap; FT_ATT_OVERLAP_BWD = chunk length,
     // default 256, 0 disables): only when the caller lets this call run the attention LSTM's BPTT as well (ft_ar_step_bwd: flows
     // whose d_text nobody is waiting for).  Highest chunk first: the second stream prepares chunk c's dhA while the BPTT kernel
     // (64 SMs) works on chunk c + 1.
     static int attb_chunk = -1;
     if (attb_chunk < 0) { const char* e = getenv("FT_ATT_OVERLAP_BWD"); attb_chunk = e ? atoi(e) : 256; if (attb_chunk % 64) attb_chunk = 0; }
-    Pipe* pq = (may_fuse_bptt && attb_chunk > 0 && F.dcarry1 && n.B <= 32 && n.T >= attb_chunk + 64) ? get_pipe(st) : nullptr;
+    Pipe* pq = (may_fuse_bptt && !attention_bwd_done && attb_chunk > 0 && F.dcarry1 && n.B <= 32 && n.T >= attb_chunk + 64) ? get_pipe(st) : nullptr;
     if (pq) {
         FT_TRY(launch_cast(w.attn_lstm_w_ih, 2, F.w.w_ih_a, 0, static_cast<long long>(G) * n.M, st));
         FT_TRY(launch_transpose_cast_f16(w.attn_lstm_w_hh, F.w.w_hh_a, G, H, st));
@@ -634,7 +651,7 @@ int ar_step_bwd_main(const FtArStepDesc& d, const FtArStepWeights& w, const floa
         cudaStreamWaitEvent(st, pq->evG, 0);          // all of sC (the last record) ...
         if (sr != st) { cudaEventRecord(pq->evJ, sr); cudaStreamWaitEvent(st, pq->evJ, 0); }     // ... and the BPTT
         if (bptt_done) *bptt_done = true;
-    } else {
+    } else if (!attention_bwd_done) {
         FT_TRY(attention_bwd_rows(st, 0, n.T));
     }
 

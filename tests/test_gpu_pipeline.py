@@ -70,8 +70,15 @@ def test_attention_overlap_equals_serial_schedule(tmp_path):
     # 300 steps -> 5 chunks, ragged tail (44 steps); the backward of the second flow runs as one call with the attention backward
     # of chunk c under the attention-LSTM BPTT of chunk c + 1 (FT_ATT_OVERLAP_BWD)
     b = run("overlap", {"FT_ATT_OVERLAP": "64", "FT_FUSE_BWD": "1", "FT_ATT_OVERLAP_BWD": "64"})
+    # third schedule: the attention backward of every finished layer-0 BPTT chunk on a low-priority stream under the pipeline
+    c = run("attb_pipe", {"FT_ATT_OVERLAP": "64", "FT_PIPE_CHUNK": "64", "FT_ATTB_PIPE": "1"})
+
     def rel(x, y):
         return (x - y).abs().max().item() / max(y.abs().max().item(), 1e-12)
+    gm = max(v.norm().item() for v in a["grads"].values())
+    for k in a["grads"]:
+        dd = (a["grads"][k] - c["grads"][k]).norm().item()
+        assert dd <= 1e-2 * (a["grads"][k].norm().item() + 1e-4 * gm), ("attb_pipe", k, dd)
     # both schedules are within the 1e-3 bar of the fp32 reference; between themselves they differ by fp16 operand rounding of
     # the recurrent state (measured 4.8e-4 on z)
     assert rel(b["z"], a["z"]) < 1e-3 and rel(b["gate"], a["gate"]) < 1e-3
