@@ -556,24 +556,24 @@ struct LstmFwdChunkParams : LstmFwdParams {
 constexpr int XCH = 2;                                           // extra K chunks (128 input channels max)
 
 // kPoll ("the data is the flag", as in infer.cu): the launcher fills the rows this launch will write with 0xFFFF -- fp16 NaN, a
-// pattern no h in (-1, 1) has -- the epilogue stores h_t as 16-byte pieces with st.relaxed.gpu and publishes nothing else, and
-// eight LOADER warps fetch h_{t-1} with 16-byte ld.relaxed.gpu straight into the SWIZZLE_128B operand image (piece j of row r
-// at j ^ (r & 7)), re-fetching only pieces that still hold the fill.  This removes, per step, the cumulative release (a
-// membar.gpu behind the h stores: 0.6 us), the flag's L2 atomic + poll round trip (0.9 us) and the TMA round trip that could
-// only start afterwards; what remains is one store -> L2 -> load hand-over.
-constexpr int POLL_THREADS = 256;                                // loader warps 6..13: thread j -> (row j / 8 [+32], piece j % 8)
+// pattern no h in (-1, 1) has -- the epilogue stores h_t as whole 16-byte pieces with st.relaxed.gpu and publishes nothing else,
+// and eight LOADER warps each TMA-load two K chunks of h_{t-1} speculatively (a tunable delay after this CTA's own stores),
+// then VERIFY them in shared memory: a piece that still holds the fill means its producer was late, and the warp simply loads
+// its two chunks again.  Per step this removes the cumulative release (a membar.gpu behind the h stores: 0.6 us) and the flag's
+// L2 atomic + poll round trip (0.9 us) that the TMA loads had to wait for; the verification costs 16 shared-memory reads per
+// lane.  (A first form fetched the pieces with 16-byte ld.relaxed.gpu instead of TMA: correct, but 64 KB through the LSU took
+// 1.4-1.9 us against 0.92 us through TMA -- profiles/r2_c38_trace_lstm_polled.txt.)
+constexpr int POLL_WARPS = 8, POLL_GS = FWD_NCH / POLL_WARPS;    // loader warps 6..13, K chunks per loader warp (2)
+constexpr int POLL_THREADS = 32 * POLL_WARPS;
 constexpr int LSTM_THREADS_POLL = LSTM_THREADS + POLL_THREADS;
 
-__device__ __forceinline__ uint4 ld_rlx_v4(const void* p) {
-    uint4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ void st_rlx_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void st_smem_v4(uint32_t addr, uint4 v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+__device__ __forceinline__ uint4 ld_smem_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 
 template <int FWD_GS, int FWD_UNITS, bool kXIn, bool kPoll>
@@ -581,6 +581,7 @@ __global__ void __launch_bounds__(kPoll ? LSTM_THREADS_POLL : LSTM_THREADS, 1)
 lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmWx,
                 const __grid_constant__ CUtensorMap tmX, LstmFwdChunkParams p) {
     constexpr int FWD_NG = FWD_NCH / FWD_GS;                     // TMA groups per step
+    constexpr int MMA_GS = kPoll ? POLL_GS : FWD_GS, MMA_NG = FWD_NCH / MMA_GS;   // chunk groups the MMA warp waits for
     constexpr int NCHT = FWD_NCH + (kXIn ? XCH : 0);             // K chunks per step: h (16) [+ x (2)]
     constexpr int A_SLOTS = FWD_NCH + (kXIn ? 2 * XCH : 0);      // x_t is double-buffered: it is prefetched one step ahead
     constexpr int FWD_N = 4 * FWD_UNITS, FWD_W_BYTES = NCHT * FWD_N * 128, FWD_PROD = KCH / FWD_UNITS;
@@ -593,7 +594,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     float* sAcc = reinterpret_cast<float*>(sW + FWD_W_BYTES);    // [32 * nq rows][AP]
     const int nq = (p.B + 31) / 32;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + ((nq * 32 * AP + 1) & ~1));
-    uint64_t* full = bars;                       // [FWD_NG] (<= 16)
+    uint64_t* full = bars;                       // [FWD_NG] (<= 16); kPoll: [0..7] a loader warp's TMA landed, [8..15] ... and verified
     uint64_t* wbar = bars + 16;
     uint64_t* accum_full = bars + 17;
     uint64_t* xfull = bars + 18;                 // [2] (kXIn)
@@ -608,7 +609,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         tma_prefetch_desc(&tmW);
         tma_prefetch_desc(&tmH);
         if (kXIn) { tma_prefetch_desc(&tmWx); tma_prefetch_desc(&tmX); }
-        for (int g = 0; g < FWD_NG; ++g) mbar_init(&full[g], kPoll ? POLL_THREADS : 1);
+        for (int g = 0; g < (kPoll ? 2 * POLL_WARPS : FWD_NG); ++g) mbar_init(&full[g], 1);
         mbar_init(wbar, 1);
         mbar_init(accum_full, 1);
         mbar_init(&xfull[0], 1); mbar_init(&xfull[1], 1);
@@ -696,12 +697,12 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 __syncwarp();
             }
             if (kXIn) mbar_wait(&xfull[(t - tm0) & 1], ((t - tm0) >> 1) & 1, p.status, 216);
-            for (int g = 0; g < FWD_NG; ++g) {
-                mbar_wait(&full[g], ph, p.status, 214);
+            for (int g = 0; g < MMA_NG; ++g) {
+                mbar_wait(&full[kPoll ? POLL_WARPS + g : g], ph, p.status, 214);
                 tc_fence_after();
                 if (elect_one()) {
                     if (g == 0) FT_TRACE(p, t, 2);
-                    if (g == FWD_NG - 1) FT_TRACE(p, t, 5);
+                    if (g == MMA_NG - 1) FT_TRACE(p, t, 5);
                     if (kXIn && g == 0) {                       // the (prefetched) input chunks open the accumulation
                         const int xs = (t - tm0) & 1;
                         uint64_t ya = da_base + FWD_NCH * a_chunk, yb = db_base + (FWD_NCH + xs * XCH) * b_chunk;
@@ -716,18 +717,18 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     }
                     uint64_t xa = da, xb = db;
 #pragma unroll
-                    for (int c = 0; c < FWD_GS; ++c) {
+                    for (int c = 0; c < MMA_GS; ++c) {
 #pragma unroll
                         for (int k = 0; k < KCH / 16; ++k)
                             umma_f16(tmem_d, xa + 2 * k, xb + 2 * k, idesc, kXIn || (g | c | k) != 0);
                         xa += a_chunk;
                         xb += b_chunk;
                     }
-                    if (g == FWD_NG - 1) { FT_TRACE(p, t, 3); umma_commit(accum_full); }
+                    if (g == MMA_NG - 1) { FT_TRACE(p, t, 3); umma_commit(accum_full); }
                 }
                 __syncwarp();
-                da += FWD_GS * a_chunk;
-                db += FWD_GS * b_chunk;
+                da += MMA_GS * a_chunk;
+                db += MMA_GS * b_chunk;
             }
         }
     } else if (warp < 6) {
@@ -892,68 +893,52 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             }
         }
     } else if (kPoll) {
-        // ---------------------------------------------------------------- loaders: 8 warps, 256 threads (kPoll only)
-        const int j = threadIdx.x - LSTM_THREADS;
-        const int prow = j >> 3, pc = j & 7;
-        const uint32_t sA_u32 = smem_u32(sA);                 // (the launcher uses this form for B <= 32: one row per thread)
-        if (prow >= p.B && prow < p.Bbox)                     // operand rows past the batch (box padding): never fetched; their
-            for (int c = 0; c < FWD_NCH; ++c)                 // accumulator columns are never read either -- keep them finite
-                st_smem_v4(sA_u32 + c * slot_bytes + prow * 128 + (pc << 4), make_uint4(0u, 0u, 0u, 0u));
-        fence_proxy_async_smem();
-        constexpr uint32_t GMASK = (1u << FWD_GS) - 1u;
+        // ---------------------------------------------------------------- loaders: 8 warps (kPoll only), 2 K chunks each
+        const int w = warp - LSTM_THREADS / 32;               // 0..7 -> chunks [2w, 2w + 2)
+        uint64_t* landed = &full[w];
+        uint64_t* ready = &full[POLL_WARPS + w];
+        uint8_t* dst = sA + w * POLL_GS * slot_bytes;
+        const uint32_t dst_u32 = smem_u32(dst);
+        const int rowpieces = p.B * 8;                        // 16-byte pieces of the real batch rows in one chunk
+        uint32_t lph = 0;                                     // phase of `landed` (one completion per TMA issue)
         for (int t = tm0; t < p.t1; ++t) {
-            // h_{t-1}: rows written by an earlier launch are simply there; rows of this launch are polled, starting when our own
-            // epilogue has stored its share (the CTAs run in near lock step: they all wait for the same h).  That epilogue ran after
-            // accum_full(t-1), so the operand buffer is free.
+            // h_{t-1}: rows written by an earlier launch are simply there; rows of this launch are fetched speculatively, starting
+            // when our own epilogue has stored its share (the CTAs run in near lock step: they all wait for the same h) plus the
+            // delay.  That epilogue ran after accum_full(t-1), so the operand buffer is free.
             if (t - 1 >= p.t0) {
                 mbar_wait(hdone, (t - 1 - p.t0) & 1, p.status, 217);
                 if (p.poll_delay > 0) { const long long c0 = clock64(); while (clock64() - c0 < p.poll_delay) {} }
             }
-            if (j == 0) FT_TRACE(p, t, 0);
-            uint32_t arrived = 0;                             // groups this thread has arrived on (bit g)
+            if (w == 0 && lane == 0) FT_TRACE(p, t, 0);
             int rounds = 0;
-            if (prow < p.B) {
-                const int row = prow;
-                const uint4* src = reinterpret_cast<const uint4*>(p.hseq + (static_cast<long long>(t - 1) * p.B + row) * p.ldh) + pc;
-                const uint32_t dst = sA_u32 + row * 128 + ((pc ^ (row & 7)) << 4);
-                uint32_t pending = (1u << FWD_NCH) - 1u;      // chunk c of this (row, piece) still to fetch
-                long long w0 = 0;
-                while (pending) {
-                    uint4 v[FWD_NCH];
-#pragma unroll
-                    for (int c = 0; c < FWD_NCH; ++c)
-                        if (pending & (1u << c)) v[c] = ld_rlx_v4(src + c * (KCH / 8));
-#pragma unroll
-                    for (int c = 0; c < FWD_NCH; ++c)
-                        if (pending & (1u << c)) {
-                            if (v[c].x != 0xFFFFFFFFu && v[c].y != 0xFFFFFFFFu && v[c].z != 0xFFFFFFFFu && v[c].w != 0xFFFFFFFFu) {
-                                st_smem_v4(dst + c * slot_bytes, v[c]);
-                                pending &= ~(1u << c);
-                            }
-                        }
-                    ++rounds;
-                    {                                         // groups complete for this thread: publish them in order
-                        bool fenced = false;
-#pragma unroll
-                        for (int g = 0; g < FWD_NG; ++g)
-                            if (!(arrived & (1u << g)) && !(pending & (GMASK << (g * FWD_GS)))) {
-                                if (!fenced) { fence_proxy_async_smem(); fenced = true; }
-                                mbar_arrive(&full[g]);
-                                arrived |= 1u << g;
-                            }
-                    }
-                    if (pending) {
-                        if (w0 == 0) w0 = clock64();
-                        else if (clock64() - w0 > FT_WATCHDOG_CYCLES) watchdog_fail(p.status, 219);
-                    }
+            long long w0 = 0;
+            for (;;) {
+                if (lane == 0) {
+                    fence_proxy_async_global();
+                    mbar_expect_tx(landed, POLL_GS * slot_bytes);
+                    tma_load_3d(dst, &tmH, landed, 0, (t - 1) * p.B, w * POLL_GS);
                 }
-            }
-            if (arrived != (1u << FWD_NG) - 1u) {             // threads without a row (B < 32) still count on every barrier
+                mbar_wait(landed, lph, p.status, 214);
+                lph ^= 1;
+                ++rounds;
+                bool miss = false;                            // pieces are stored whole, so one fill word condemns a piece
 #pragma unroll
-                for (int g = 0; g < FWD_NG; ++g)
-                    if (!(arrived & (1u << g))) mbar_arrive(&full[g]);
+                for (int c = 0; c < POLL_GS; ++c)
+#pragma unroll 4
+                    for (int rem = lane; rem < rowpieces; rem += 32) {     // a warp pass reads 4 rows x 128 B: conflict-free
+                        const int row = rem >> 3, pc = rem & 7;
+                        const uint4 v = ld_smem_v4(dst_u32 + c * slot_bytes + row * 128 + ((pc ^ (row & 7)) << 4));
+                        miss |= (v.x == 0xFFFFFFFFu) | (v.y == 0xFFFFFFFFu) | (v.z == 0xFFFFFFFFu) | (v.w == 0xFFFFFFFFu);
+                    }
+                if (!__any_sync(0xffffffffu, miss)) break;
+                if (w0 == 0) w0 = clock64();
+                else if (clock64() - w0 > FT_WATCHDOG_CYCLES) watchdog_fail(p.status, 219);
             }
-            if (j == 0) { FT_TRACE(p, t, 6); if (p.trace && blockIdx.x == 0) p.trace[t * 16 + 10] = rounds; }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(ready);
+                if (w == 0) { FT_TRACE(p, t, 6); if (p.trace && blockIdx.x == 0) p.trace[t * 16 + 10] = rounds; }
+            }
         }
     }
     tc_fence_before();
@@ -1006,7 +991,7 @@ static bool lstm_poll_enabled() {
         const char* e = getenv("FT_LSTM_POLL");
         g_lstm_poll = e ? (atoi(e) != 0) : 0;
         const char* d = getenv("FT_LSTM_POLL_DELAY");
-        g_lstm_poll_delay = d ? atoi(d) : 0;
+        g_lstm_poll_delay = d ? atoi(d) : 500;
     }
     return g_lstm_poll != 0;
 }
@@ -1029,7 +1014,7 @@ static int launch_fwd_tp(int T, int B, int t0, int t1, const float* xproj, const
     if (smem > smem_optin()) return ft_set_error("lstm_fwd: not enough shared memory");
     CUtensorMap tmW, tmH, tmWx, tmX;
     if (make_tmap_2d(&tmW, whh16, FMT_F16, LG, LH, LH, KCH, UNITS)) return -1;
-    if (make_tmap_chunks(&tmH, hseq16, static_cast<long long>(T) * B, FWD_NCH, ldh, p.Bbox, GS)) return -1;
+    if (make_tmap_chunks(&tmH, hseq16, static_cast<long long>(T) * B, FWD_NCH, ldh, p.Bbox, kPoll ? POLL_GS : GS)) return -1;
     if (kXIn) {
         if (kx <= 0 || kx > XCH * KCH) return ft_set_error("lstm_fwd: folded input width must be in (0, 128]");
         if (make_tmap_2d(&tmWx, wih16, FMT_F16, LG, kx, kx, KCH, UNITS)) return -1;

@@ -30,18 +30,20 @@ def main():
         print(f"run {it}: {e0.elapsed_time(e1) * 1e3 / T:.2f} us/step")
     L.ft_debug_set_lstm_trace(None)
     if os.environ.get("FT_LSTM_POLL", "0") != "0" and B <= 32:
-        # data-is-the-flag exchange: slot 0 = loader thread 0 starts fetching h_{t-1} (own epilogue has stored its share),
-        # slot 6 = its 16 pieces are in shared memory, slot 10 = fetch rounds it needed (a count, not a clock)
+        # data-is-the-flag exchange: slot 0 = loader warp 0 issues its speculative TMA load of h_{t-1} (own epilogue has stored
+        # its share + the delay), slot 6 = its two chunks are verified, slot 10 = loads it needed (a count, not a clock)
         rounds = trace[50:350, 10].double().mean().item()
         trace[:, 10] = trace[:, 0]
         trace[:, 1] = trace[:, 0]
         report(trace, T, f"forward (polled exchange, {rounds:.2f} fetch rounds per step)",
                ["fetch_started", "-", "first_group_ready(mma)", "all_mma_issued", "accum_done(epi)", "last_group_ready(mma)",
-                "loader0_pieces_landed", "h_stored(epi)", "acc_in_smem(epi)", "h_stored(epi)", "-"])
+                "loader0_verified", "h_stored(epi)", "acc_in_smem(epi)", "h_stored(epi)", "-"])
     else:
         report(trace, T, "forward", ["flags_seen", "tma_issued", "first_group_landed", "all_mma_issued", "accum_done(epi)",
                                      "last_group_landed", "proxy_fence_done", "release_issued",
                                      "acc_in_smem(epi)", "cell_done_h_stored", "epi_barrier_done"])
+    if os.environ.get("FT_TRACE_FWD_ONLY"):
+        return
     # ---- backward
     w = torch.randn(T, B, H, generator=g).cuda()
     dG = torch.zeros(T, B, 4 * H, device="cuda", dtype=torch.float16)
