@@ -545,7 +545,6 @@ lstm_bwd4_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant
 // the first step that has a recurrent term.
 struct LstmFwdChunkParams : LstmFwdParams {
     int t0, t1;                // steps [t0, t1); flags: [(t1 - t0) * 16] ints, zeroed by the launcher
-    int poll_delay;            // kPoll: clocks between this CTA's own h_t stores and its first fetch of h_t (tuning knob)
 };
 
 // kXIn: the layer's INPUT projection is folded into the recurrent contraction (narrow inputs: the attention LSTM's 80 mel
@@ -555,33 +554,11 @@ struct LstmFwdChunkParams : LstmFwdParams {
 // Requires x_0 == 0 (the teacher-forcing shift guarantees it): step 0 has no contraction at all.
 constexpr int XCH = 2;                                           // extra K chunks (128 input channels max)
 
-// kPoll ("the data is the flag", as in infer.cu): the launcher fills the rows this launch will write with 0xFFFF -- fp16 NaN, a
-// pattern no h in (-1, 1) has -- the epilogue stores h_t as whole 16-byte pieces with st.relaxed.gpu and publishes nothing else,
-// and eight LOADER warps each TMA-load two K chunks of h_{t-1} speculatively (a tunable delay after this CTA's own stores),
-// then VERIFY them in shared memory: a piece that still holds the fill means its producer was late, and the warp simply loads
-// its two chunks again.  Per step this removes the cumulative release (a membar.gpu behind the h stores: 0.6 us) and the flag's
-// L2 atomic + poll round trip (0.9 us) that the TMA loads had to wait for; the verification costs 16 shared-memory reads per
-// lane.  (A first form fetched the pieces with 16-byte ld.relaxed.gpu instead of TMA: correct, but 64 KB through the LSU took
-// 1.4-1.9 us against 0.92 us through TMA -- profiles/r2_c38_trace_lstm_polled.txt.)
-constexpr int POLL_WARPS = 8, POLL_GS = FWD_NCH / POLL_WARPS;    // loader warps 6..13, K chunks per loader warp (2)
-constexpr int POLL_THREADS = 32 * POLL_WARPS;
-constexpr int LSTM_THREADS_POLL = LSTM_THREADS + POLL_THREADS;
-
-__device__ __forceinline__ void st_rlx_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ uint4 ld_smem_v4(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-
-template <int FWD_GS, int FWD_UNITS, bool kXIn, bool kPoll>
-__global__ void __launch_bounds__(kPoll ? LSTM_THREADS_POLL : LSTM_THREADS, 1)
+template <int FWD_GS, int FWD_UNITS, bool kXIn>
+__global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmWx,
                 const __grid_constant__ CUtensorMap tmX, LstmFwdChunkParams p) {
     constexpr int FWD_NG = FWD_NCH / FWD_GS;                     // TMA groups per step
-    constexpr int MMA_GS = kPoll ? POLL_GS : FWD_GS, MMA_NG = FWD_NCH / MMA_GS;   // chunk groups the MMA warp waits for
     constexpr int NCHT = FWD_NCH + (kXIn ? XCH : 0);             // K chunks per step: h (16) [+ x (2)]
     constexpr int A_SLOTS = FWD_NCH + (kXIn ? 2 * XCH : 0);      // x_t is double-buffered: it is prefetched one step ahead
     constexpr int FWD_N = 4 * FWD_UNITS, FWD_W_BYTES = NCHT * FWD_N * 128, FWD_PROD = KCH / FWD_UNITS;
@@ -594,12 +571,11 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     float* sAcc = reinterpret_cast<float*>(sW + FWD_W_BYTES);    // [32 * nq rows][AP]
     const int nq = (p.B + 31) / 32;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + ((nq * 32 * AP + 1) & ~1));
-    uint64_t* full = bars;                       // [FWD_NG] (<= 16); kPoll: [0..7] a loader warp's TMA landed, [8..15] ... and verified
+    uint64_t* full = bars;                       // [FWD_NG] (<= 16)
     uint64_t* wbar = bars + 16;
     uint64_t* accum_full = bars + 17;
     uint64_t* xfull = bars + 18;                 // [2] (kXIn)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-    uint64_t* hdone = bars + 21;                 // kPoll: this CTA's epilogue has issued its h_t stores (128 arrivals)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x;
@@ -609,11 +585,10 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         tma_prefetch_desc(&tmW);
         tma_prefetch_desc(&tmH);
         if (kXIn) { tma_prefetch_desc(&tmWx); tma_prefetch_desc(&tmX); }
-        for (int g = 0; g < (kPoll ? 2 * POLL_WARPS : FWD_NG); ++g) mbar_init(&full[g], 1);
+        for (int g = 0; g < FWD_NG; ++g) mbar_init(&full[g], 1);
         mbar_init(wbar, 1);
         mbar_init(accum_full, 1);
         mbar_init(&xfull[0], 1); mbar_init(&xfull[1], 1);
-        mbar_init(hdone, EPI_THREADS);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<64>(tmem_slot);             // accumulator: 64 lanes (W rows) x Bbox <= 64 columns
@@ -640,7 +615,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             for (int kc = 0; kc < XCH; ++kc) tma_load_2d(sA + (FWD_NCH + kc) * slot_bytes, &tmX, &xfull[0], kc * KCH, tm0 * p.B);
         }
         __syncwarp();
-        for (int t = tm0; !kPoll && t < p.t1; ++t) {
+        for (int t = tm0; t < p.t1; ++t) {
             // the first step of a chunk has nothing to wait for: h_{t0-1} was written by the previous launch on this stream
             // (kernel boundary) and the A buffer is untouched
             if (t > p.t0 && lane < FWD_NCH) wait_flag_ge(&p.flags[(t - 1 - p.t0) * FWD_NCH + lane], FWD_PROD, p.status, 212);
@@ -683,26 +658,14 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         for (int t = tm0; t < p.t1; ++t) {
             const int ph = (t - tm0) & 1;
             uint64_t da = da_base, db = db_base;
-            if (kPoll && kXIn && t + 1 < p.t1) {
-                // x_{t+1} goes into the buffer step t-1's MMAs read: they have retired once accum_full(t-1) completed (long ago:
-                // h_{t-1} could not exist otherwise).  This warp sequences the phases itself, so it can never lag a whole phase.
-                if (t - 1 >= tm0) mbar_wait(accum_full, (t - 1 - tm0) & 1, p.status, 218);
-                if (elect_one()) {
-                    const int xs = (t + 1 - tm0) & 1;
-                    mbar_expect_tx(&xfull[xs], XCH * slot_bytes);
 #pragma unroll
-                    for (int kc = 0; kc < XCH; ++kc)
-                        tma_load_2d(sA + (FWD_NCH + xs * XCH + kc) * slot_bytes, &tmX, &xfull[xs], kc * KCH, (t + 1) * p.B);
-                }
-                __syncwarp();
-            }
             if (kXIn) mbar_wait(&xfull[(t - tm0) & 1], ((t - tm0) >> 1) & 1, p.status, 216);
-            for (int g = 0; g < MMA_NG; ++g) {
-                mbar_wait(&full[kPoll ? POLL_WARPS + g : g], ph, p.status, 214);
+            for (int g = 0; g < FWD_NG; ++g) {
+                mbar_wait(&full[g], ph, p.status, 214);
                 tc_fence_after();
                 if (elect_one()) {
                     if (g == 0) FT_TRACE(p, t, 2);
-                    if (g == MMA_NG - 1) FT_TRACE(p, t, 5);
+                    if (g == FWD_NG - 1) FT_TRACE(p, t, 5);
                     if (kXIn && g == 0) {                       // the (prefetched) input chunks open the accumulation
                         const int xs = (t - tm0) & 1;
                         uint64_t ya = da_base + FWD_NCH * a_chunk, yb = db_base + (FWD_NCH + xs * XCH) * b_chunk;
@@ -717,21 +680,21 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     }
                     uint64_t xa = da, xb = db;
 #pragma unroll
-                    for (int c = 0; c < MMA_GS; ++c) {
+                    for (int c = 0; c < FWD_GS; ++c) {
 #pragma unroll
                         for (int k = 0; k < KCH / 16; ++k)
                             umma_f16(tmem_d, xa + 2 * k, xb + 2 * k, idesc, kXIn || (g | c | k) != 0);
                         xa += a_chunk;
                         xb += b_chunk;
                     }
-                    if (g == MMA_NG - 1) { FT_TRACE(p, t, 3); umma_commit(accum_full); }
+                    if (g == FWD_NG - 1) { FT_TRACE(p, t, 3); umma_commit(accum_full); }
                 }
                 __syncwarp();
-                da += MMA_GS * a_chunk;
-                db += MMA_GS * b_chunk;
+                da += FWD_GS * a_chunk;
+                db += FWD_GS * b_chunk;
             }
         }
-    } else if (warp < 6) {
+    } else {
         // ---------------------------------------------------------------- epilogue: 4 warps, 128 threads
         const int q = warp & 3;                               // TMEM lane quadrant this warp may read
         const int et = threadIdx.x - 64;                      // 0..127
@@ -824,7 +787,6 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 }
             }
             float gi[2][2], gf[2][2], gg[2][2], go[2][2], hv[2][2];
-            uint32_t hw[2] = {0u, 0u};                        // kPoll: this thread's h pair as one 32-bit word
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 const int item = et + s * EPI_THREADS;
@@ -842,36 +804,15 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     }
                     const long long r = static_cast<long long>(t) * p.B + b;
                     const __half2 h2 = __floats2half2_rn(hv[s][0], hv[s][1]);
-                    if (kPoll) hw[s] = *reinterpret_cast<const uint32_t*>(&h2);
-                    else *reinterpret_cast<__half2*>(p.hseq + r * p.ldh + u0 + 2 * up) = h2;     // critical path: h_t first
+                    *reinterpret_cast<__half2*>(p.hseq + r * p.ldh + u0 + 2 * up) = h2;     // critical path: h_t first
                 }
             }
-            if (kPoll) {
-                // four consecutive lanes hold the four unit pairs of one 16-byte piece of row b (items are b * UP + up and UP is
-                // 4 or 8, so a piece never straddles a lane quad; n_items is a multiple of 4, so a quad is all valid or all idle):
-                // the quad's first lane stores the piece whole -- the loaders test whole pieces -- and nothing else is published.
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const uint32_t w1 = __shfl_down_sync(0xffffffffu, hw[s], 1), w2 = __shfl_down_sync(0xffffffffu, hw[s], 2),
-                                   w3 = __shfl_down_sync(0xffffffffu, hw[s], 3);
-                    const int item = et + s * EPI_THREADS;
-                    if (item < n_items && (lane & 3) == 0) {
-                        const int b = item / UP, up = item % UP;
-                        st_rlx_v4(p.hseq + (static_cast<long long>(t) * p.B + b) * p.ldh + u0 + 2 * up, hw[s], w1, w2, w3);
-                    }
-                }
-                mbar_arrive(hdone);                           // local hint for the loaders: start fetching h_t now
-                if (et == 0) { FT_TRACE(p, t, 9); FT_TRACE(p, t, 7); }
-                // no second barrier: sAcc is next written after accum_full(t+1), which needs every h_t piece of this CTA, and each
-                // piece is stored after its four lanes read their sAcc values
-            } else {
-                if (et == 0) FT_TRACE(p, t, 9);               // cell computed, h_t stores issued
-                epi_bar();                                    // all h_t stores of this CTA precede the release
-                if (et == 0) {
-                    FT_TRACE(p, t, 10);
-                    red_release_add(&p.flags[(t - p.t0) * FWD_NCH + cta / FWD_PROD], 1);  // cumulative release (gpu scope)
-                    FT_TRACE(p, t, 7);
-                }
+            if (et == 0) FT_TRACE(p, t, 9);                   // cell computed, h_t stores issued
+            epi_bar();                                        // all h_t stores of this CTA precede the release
+            if (et == 0) {
+                FT_TRACE(p, t, 10);
+                red_release_add(&p.flags[(t - p.t0) * FWD_NCH + cta / FWD_PROD], 1);      // cumulative release (gpu scope)
+                FT_TRACE(p, t, 7);
             }
             // off the critical path: tensors only the backward pass reads
 #pragma unroll
@@ -890,54 +831,6 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     }
                     if (p.cstate) *reinterpret_cast<float2*>(p.cstate + r * LH + u0 + 2 * up) = make_float2(c[s][0], c[s][1]);
                 }
-            }
-        }
-    } else if (kPoll) {
-        // ---------------------------------------------------------------- loaders: 8 warps (kPoll only), 2 K chunks each
-        const int w = warp - LSTM_THREADS / 32;               // 0..7 -> chunks [2w, 2w + 2)
-        uint64_t* landed = &full[w];
-        uint64_t* ready = &full[POLL_WARPS + w];
-        uint8_t* dst = sA + w * POLL_GS * slot_bytes;
-        const uint32_t dst_u32 = smem_u32(dst);
-        const int rowpieces = p.B * 8;                        // 16-byte pieces of the real batch rows in one chunk
-        uint32_t lph = 0;                                     // phase of `landed` (one completion per TMA issue)
-        for (int t = tm0; t < p.t1; ++t) {
-            // h_{t-1}: rows written by an earlier launch are simply there; rows of this launch are fetched speculatively, starting
-            // when our own epilogue has stored its share (the CTAs run in near lock step: they all wait for the same h) plus the
-            // delay.  That epilogue ran after accum_full(t-1), so the operand buffer is free.
-            if (t - 1 >= p.t0) {
-                mbar_wait(hdone, (t - 1 - p.t0) & 1, p.status, 217);
-                if (p.poll_delay > 0) { const long long c0 = clock64(); while (clock64() - c0 < p.poll_delay) {} }
-            }
-            if (w == 0 && lane == 0) FT_TRACE(p, t, 0);
-            int rounds = 0;
-            long long w0 = 0;
-            for (;;) {
-                if (lane == 0) {
-                    fence_proxy_async_global();
-                    mbar_expect_tx(landed, POLL_GS * slot_bytes);
-                    tma_load_3d(dst, &tmH, landed, 0, (t - 1) * p.B, w * POLL_GS);
-                }
-                mbar_wait(landed, lph, p.status, 214);
-                lph ^= 1;
-                ++rounds;
-                bool miss = false;                            // pieces are stored whole, so one fill word condemns a piece
-#pragma unroll
-                for (int c = 0; c < POLL_GS; ++c)
-#pragma unroll 4
-                    for (int rem = lane; rem < rowpieces; rem += 32) {     // a warp pass reads 4 rows x 128 B: conflict-free
-                        const int row = rem >> 3, pc = rem & 7;
-                        const uint4 v = ld_smem_v4(dst_u32 + c * slot_bytes + row * 128 + ((pc ^ (row & 7)) << 4));
-                        miss |= (v.x == 0xFFFFFFFFu) | (v.y == 0xFFFFFFFFu) | (v.z == 0xFFFFFFFFu) | (v.w == 0xFFFFFFFFu);
-                    }
-                if (!__any_sync(0xffffffffu, miss)) break;
-                if (w0 == 0) w0 = clock64();
-                else if (clock64() - w0 > FT_WATCHDOG_CYCLES) watchdog_fail(p.status, 219);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(ready);
-                if (w == 0) { FT_TRACE(p, t, 6); if (p.trace && blockIdx.x == 0) p.trace[t * 16 + 10] = rounds; }
             }
         }
     }
@@ -984,20 +877,8 @@ void set_lstm_half_sm(int on) { g_half_sm = on != 0; }
 
 // Steps [t0, t1) of one layer's forward recurrence on 1024 / UNITS CTAs.  `flags` needs (t1 - t0) * 16 ints.
 // x16 != null: folded input projection (kXIn): x16 [T*B, kx] fp16 (row pitch ldx), wih16 [4096, kx] fp16, biases fp32.
-static int g_lstm_poll = -1;         // FT_LSTM_POLL: 0 (default) = flag counters + TMA loads, 1 = data-is-the-flag h exchange
-static int g_lstm_poll_delay = 0;    // FT_LSTM_POLL_DELAY: clocks between a CTA's own h stores and its first fetch
-static bool lstm_poll_enabled() {
-    if (g_lstm_poll < 0) {
-        const char* e = getenv("FT_LSTM_POLL");
-        g_lstm_poll = e ? (atoi(e) != 0) : 0;
-        const char* d = getenv("FT_LSTM_POLL_DELAY");
-        g_lstm_poll_delay = d ? atoi(d) : 500;
-    }
-    return g_lstm_poll != 0;
-}
-
-template <int GS, int UNITS, bool kXIn, bool kPoll>
-static int launch_fwd_tp(int T, int B, int t0, int t1, const float* xproj, const void* whh16, const int* lens, void* hseq16,
+template <int GS, int UNITS, bool kXIn>
+static int launch_fwd_t(int T, int B, int t0, int t1, const float* xproj, const void* whh16, const int* lens, void* hseq16,
                         long long ldh, void* gates16, float* cstate, float* h32, long long ldh32, int* flags, cudaStream_t st,
                         const void* x16 = nullptr, long long ldx = 0, int kx = 0, const void* wih16 = nullptr,
                         const float* b_ih = nullptr, const float* b_hh = nullptr) {
@@ -1008,13 +889,12 @@ static int launch_fwd_tp(int T, int B, int t0, int t1, const float* xproj, const
     p.xproj = xproj; p.b_ih = b_ih; p.b_hh = b_hh; p.lens = lens; p.hseq = static_cast<__half*>(hseq16); p.ldh = ldh;
     p.gates = static_cast<__half*>(gates16); p.cstate = cstate; p.h32 = h32; p.ldh32 = ldh32;
     p.flags = flags; p.status = ft_status_word(); p.trace = (t0 == 0 && t1 == T) ? g_lstm_trace : nullptr;
-    p.poll_delay = g_lstm_poll_delay;
     const int slot = p.Bbox * 128, nq = (B + 31) / 32;
     const int smem = (FWD_NCH + (kXIn ? 2 * XCH : 0)) * slot + W_BYTES + nq * 32 * (N + 1) * 4 + 8 + 256 + 1024;
     if (smem > smem_optin()) return ft_set_error("lstm_fwd: not enough shared memory");
     CUtensorMap tmW, tmH, tmWx, tmX;
     if (make_tmap_2d(&tmW, whh16, FMT_F16, LG, LH, LH, KCH, UNITS)) return -1;
-    if (make_tmap_chunks(&tmH, hseq16, static_cast<long long>(T) * B, FWD_NCH, ldh, p.Bbox, kPoll ? POLL_GS : GS)) return -1;
+    if (make_tmap_chunks(&tmH, hseq16, static_cast<long long>(T) * B, FWD_NCH, ldh, p.Bbox, GS)) return -1;
     if (kXIn) {
         if (kx <= 0 || kx > XCH * KCH) return ft_set_error("lstm_fwd: folded input width must be in (0, 128]");
         if (make_tmap_2d(&tmWx, wih16, FMT_F16, LG, kx, kx, KCH, UNITS)) return -1;
@@ -1022,35 +902,15 @@ static int launch_fwd_tp(int T, int B, int t0, int t1, const float* xproj, const
     } else {
         tmWx = tmW; tmX = tmH;                                   // unused
     }
-    if (kPoll) {
-        // the rows this launch writes start out as the fill pattern the loaders test for (fp16 0xFFFF: no h value)
-        if ((ldh & 7) || (reinterpret_cast<uintptr_t>(hseq16) & 15)) return ft_set_error("lstm_fwd: h rows must be 16-byte aligned");
-        if (cudaMemset2DAsync(static_cast<__half*>(hseq16) + static_cast<long long>(t0) * B * ldh, static_cast<size_t>(ldh) * 2, 0xFF,
-                              static_cast<size_t>(LH) * 2, static_cast<size_t>(t1 - t0) * B, st) != cudaSuccess)
-            return ft_set_error("lstm_fwd: memset failed");
-    } else if (cudaMemsetAsync(flags, 0, sizeof(int) * (t1 - t0) * FWD_NCH, st) != cudaSuccess) {
-        return ft_set_error("lstm_fwd: memset failed");
-    }
-    void* fn = reinterpret_cast<void*>(lstm_fwd_kernel<GS, UNITS, kXIn, kPoll>);
+    if (cudaMemsetAsync(flags, 0, sizeof(int) * (t1 - t0) * FWD_NCH, st) != cudaSuccess) return ft_set_error("lstm_fwd: memset failed");
+    void* fn = reinterpret_cast<void*>(lstm_fwd_kernel<GS, UNITS, kXIn>);
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     TimeScope ts("lstm_fwd", t1 - t0, B, 0, st);
     void* args[] = {&tmW, &tmH, &tmWx, &tmX, &p};
-    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(CTAS), dim3(kPoll ? LSTM_THREADS_POLL : LSTM_THREADS), args, smem, st);
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(CTAS), dim3(LSTM_THREADS), args, smem, st);
     if (e != cudaSuccess) return ft_set_error(cudaGetErrorString(e));
     ft_count_launch(1);
     return ft_check_launch("lstm_fwd_kernel");
-}
-
-template <int GS, int UNITS, bool kXIn>
-static int launch_fwd_t(int T, int B, int t0, int t1, const float* xproj, const void* whh16, const int* lens, void* hseq16,
-                        long long ldh, void* gates16, float* cstate, float* h32, long long ldh32, int* flags, cudaStream_t st,
-                        const void* x16 = nullptr, long long ldx = 0, int kx = 0, const void* wih16 = nullptr,
-                        const float* b_ih = nullptr, const float* b_hh = nullptr) {
-    if (lstm_poll_enabled() && B <= 32)          // one operand row per loader thread; larger batches keep the flag + TMA form
-        return launch_fwd_tp<GS, UNITS, kXIn, true>(T, B, t0, t1, xproj, whh16, lens, hseq16, ldh, gates16, cstate, h32, ldh32, flags, st,
-                                                    x16, ldx, kx, wih16, b_ih, b_hh);
-    return launch_fwd_tp<GS, UNITS, kXIn, false>(T, B, t0, t1, xproj, whh16, lens, hseq16, ldh, gates16, cstate, h32, ldh32, flags, st,
-                                                 x16, ldx, kx, wih16, b_ih, b_hh);
 }
 
 int launch_lstm_fwd(int T, int B, const float* xproj, const void* whh16, const int* lens, void* hseq16, long long ldh,

@@ -29,19 +29,9 @@ def main():
         torch.cuda.synchronize()
         print(f"run {it}: {e0.elapsed_time(e1) * 1e3 / T:.2f} us/step")
     L.ft_debug_set_lstm_trace(None)
-    if os.environ.get("FT_LSTM_POLL", "0") != "0" and B <= 32:
-        # data-is-the-flag exchange: slot 0 = loader warp 0 issues its speculative TMA load of h_{t-1} (own epilogue has stored
-        # its share + the delay), slot 6 = its two chunks are verified, slot 10 = loads it needed (a count, not a clock)
-        rounds = trace[50:350, 10].double().mean().item()
-        trace[:, 10] = trace[:, 0]
-        trace[:, 1] = trace[:, 0]
-        report(trace, T, f"forward (polled exchange, {rounds:.2f} fetch rounds per step)",
-               ["fetch_started", "-", "first_group_ready(mma)", "all_mma_issued", "accum_done(epi)", "last_group_ready(mma)",
-                "loader0_verified", "h_stored(epi)", "acc_in_smem(epi)", "h_stored(epi)", "-"])
-    else:
-        report(trace, T, "forward", ["flags_seen", "tma_issued", "first_group_landed", "all_mma_issued", "accum_done(epi)",
-                                     "last_group_landed", "proxy_fence_done", "release_issued",
-                                     "acc_in_smem(epi)", "cell_done_h_stored", "epi_barrier_done"])
+    report(trace, T, "forward", ["flags_seen", "tma_issued", "first_group_landed", "all_mma_issued", "accum_done(epi)",
+                                 "last_group_landed", "proxy_fence_done", "release_issued",
+                                 "acc_in_smem(epi)", "cell_done_h_stored", "epi_barrier_done"])
     if os.environ.get("FT_TRACE_FWD_ONLY"):
         return
     # ---- backward
@@ -76,7 +66,7 @@ def report(trace, T, title, names, reverse=False):
         print(f"  {n:24s} +{v:8.0f} clk ({v / 1965:.2f} us)")
     # time from own release (slot 7, step t) to flags_seen of step t+1
     gap = (tr[1:, 0] - tr[:-1, 7]).mean().item()
-    print(f"  own release / h store (t) -> slot 0 of step t+1: {gap:.0f} clk ({gap / 1965:.2f} us)")
+    print(f"  own release(t) -> flags_seen(t+1): {gap:.0f} clk ({gap / 1965:.2f} us)")
 
 if __name__ == "__main__":
     main()
