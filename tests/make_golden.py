@@ -3,7 +3,7 @@
 
 Run in the build container only (the GPU box has no /root/reference):
     python tests/make_golden.py
-Weights come from oracle.synth.synth_params(cfg, seed), so fixtures carry outputs only.
+Weights come from flowtron_b200.synth.synth_params(cfg, seed), so fixtures carry outputs only.
 Reference entry points exercised: Flowtron.forward (flowtron.py:870-899), FlowtronLoss.forward
 (:200-243), autograd of both, Flowtron.infer (:901-930), TacotronSTFT.mel_spectrogram
 (audio_processing.py:117-134), RAdam.step (radam.py:44-122) after clip_grad_norm_ (train.py:326).
@@ -19,7 +19,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import ref_shims, synth  # noqa: E402
+from oracle import ref_shims  # noqa: E402
+from flowtron_b200 import synth  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 N_GRAD_SAMPLES = 32

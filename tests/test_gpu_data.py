@@ -6,7 +6,7 @@ import torch
 
 from conftest import record_parity
 from oracle import data_oracle as D
-from oracle import synth
+from flowtron_b200 import synth
 
 pytestmark = pytest.mark.gpu
 

@@ -6,7 +6,7 @@ import torch
 
 from conftest import record_parity
 from oracle import flowtron_oracle as O
-from oracle import synth
+from flowtron_b200 import synth
 
 pytestmark = pytest.mark.gpu
 

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN, record_parity
-from oracle import synth
+from flowtron_b200 import synth
 
 pytestmark = pytest.mark.gpu
 

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from conftest import record_parity
-from oracle import synth
+from flowtron_b200 import synth
 
 pytestmark = pytest.mark.gpu
 

@@ -6,7 +6,8 @@ import pytest
 import torch
 
 from oracle import data_oracle as D
-from oracle import ref_shims, synth
+from oracle import ref_shims
+from flowtron_b200 import synth
 from oracle import stft_oracle as S
 
 

@@ -10,7 +10,7 @@ import torch
 from conftest import GOLDEN
 from oracle import flowtron_oracle as O
 from oracle import stft_oracle as S
-from oracle import synth
+from flowtron_b200 import synth
 
 
 def _load(name):

@@ -3,7 +3,8 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import flowtron_oracle as O, synth
+from oracle import flowtron_oracle as O
+from flowtron_b200 import synth
 from flowtron_b200 import _lib
 from flowtron_b200.flowtron import Flowtron
 
