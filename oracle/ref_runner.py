@@ -19,7 +19,8 @@ import time
 
 import torch
 
-from . import ref_shims, synth
+from . import ref_shims
+from flowtron_b200 import synth
 
 
 def physical_cores() -> int:
